@@ -1,0 +1,200 @@
+/*
+ * xllm_b200_ops.h -- C-ABI of libxllm_b200_ops.so
+ *
+ * B200-native (sm_100a) replacement for the per-layer inference hot path of
+ * jd-opensource/xllm (reference @ 87e8d6e, v0.9.0).  Every entry point takes
+ * plain device pointers, sizes, element strides and a cudaStream_t (passed as
+ * void*); none takes a torch type.  Each one cites the reference interface it
+ * replaces (paths relative to the reference checkout, file:line).
+ *
+ * Conventions
+ *   - return value: 0 on success, non-zero on error; xb_last_error() returns a
+ *     thread-local message (the reference aborts through glog CHECK/TORCH_CHECK:
+ *     the C++ shim in xllm_b200/csrc/xllm_cuda_ops.cpp turns a non-zero code
+ *     into TORCH_CHECK(false, msg)).
+ *   - all tensors are borrowed; nothing is allocated or freed by the callee;
+ *     scratch comes from caller-provided workspaces; no host synchronisation
+ *     (every launcher is CUDA-graph-capturable).
+ *   - bf16 = __nv_bfloat16 storage (uint16), e4m3 = __nv_fp8_e4m3 storage (uint8).
+ *   - strides are in ELEMENTS unless the name ends in _bytes.
+ */
+#ifndef XLLM_B200_OPS_H_
+#define XLLM_B200_OPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XB_ABI_VERSION 1
+
+typedef void* xb_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------ */
+int xb_abi_version(void);
+const char* xb_last_error(void);
+/* number of kernels this library has launched in this process (all threads);
+ * bench.py reports the delta over the timed region as "gpu_launches". */
+uint64_t xb_launch_count(void);
+/* enable (1) / disable (0) programmatic dependent launch on our launches.
+ * Mirrors support_pdl() -> Platform::is_enable_pdl()
+ * (xllm/core/kernels/cuda/utils.cpp:370, batch_decode.cpp:79). */
+void xb_set_pdl(int enable);
+
+/* ---- K7: RMSNorm ---------------------------------------------------------
+ * replaces xllm::kernel::cuda::rms_norm          (cuda_ops_api.h:157-160,
+ *          norm.cu:43-78,430-460) and
+ *          xllm::kernel::cuda::fused_add_rms_norm (cuda_ops_api.h:162-165,
+ *          norm.cu:80-173,462-515).
+ * out[t,:] = bf16( bf16(x[t,:] * rstd_t) * w ),  rstd_t = rsqrt(mean_f32(x^2)+eps)
+ * fused:  residual <- bf16(input + residual); input <- norm(residual) (in place). */
+int xb_rms_norm_bf16(void* out, const void* input, int64_t input_stride,
+                     const void* weight, float eps, int num_tokens,
+                     int hidden_size, xb_stream_t stream);
+int xb_fused_add_rms_norm_bf16(void* input, int64_t input_stride, void* residual,
+                               const void* weight, float eps, int num_tokens,
+                               int hidden_size, xb_stream_t stream);
+
+/* ---- K8: RMSNorm + static FP8 quant ---------------------------------------
+ * replaces rms_norm_static_fp8_quant / fused_add_rms_norm_static_fp8_quant
+ * (cuda_ops_api.h:203-221, norm.cu:228-423,517-600).  scale: device float[1]. */
+int xb_rms_norm_static_fp8_quant_bf16(void* out_e4m3, const void* input,
+                                      int64_t input_stride, const void* weight,
+                                      const float* scale, float eps,
+                                      int num_tokens, int hidden_size,
+                                      xb_stream_t stream);
+int xb_fused_add_rms_norm_static_fp8_quant_bf16(
+    void* out_e4m3, void* input, int64_t input_stride, void* residual,
+    const void* weight, const float* scale, float eps, int num_tokens,
+    int hidden_size, xb_stream_t stream);
+
+/* ---- K6: static scaled FP8 quant -----------------------------------------
+ * replaces static_scaled_fp8_quant (cuda_ops_api.h:182-186, fp8_quant.cu:78-153):
+ * out = sat_e4m3(x * (1/scale)), RNE, saturating at +-448. */
+int xb_static_scaled_fp8_quant_bf16(void* out_e4m3, int64_t out_stride,
+                                    const void* input, int64_t input_stride,
+                                    const float* scale, int num_tokens,
+                                    int hidden_size, xb_stream_t stream);
+/* dynamic per-tensor scale = max(amax/448, 1e-12) (fp8_scaled_quantize.cpp:36-41),
+ * computed on device into scale_out[1] (no host sync), then quantised. */
+int xb_dynamic_scaled_fp8_quant_bf16(void* out_e4m3, int64_t out_stride,
+                                     const void* input, int64_t input_stride,
+                                     float* scale_out, int num_tokens,
+                                     int hidden_size, xb_stream_t stream);
+
+/* ---- K9: rotary embedding -------------------------------------------------
+ * replaces xllm::kernel::cuda::rotary_embedding (cuda_ops_api.h:31-37,
+ * rope.cu:27-250).  In place on query/key; cos_sin_cache[max_pos, rot_dim] =
+ * [cos(rot/2) | sin(rot/2)] in bf16; all arithmetic in bf16 with a rounding
+ * after every multiply/add, as the reference does with scalar_t = BFloat16.
+ * key may be NULL.  positions are int64. */
+int xb_rotary_embedding_bf16(const int64_t* positions, void* query, void* key,
+                             const void* cos_sin_cache, int rot_dim,
+                             int64_t query_stride, int64_t key_stride,
+                             int64_t head_stride, int num_heads,
+                             int num_kv_heads, int head_size, int is_neox,
+                             int num_tokens, xb_stream_t stream);
+
+/* ---- K12: KV-cache scatter -----------------------------------------------
+ * replaces xllm::kernel::cuda::reshape_paged_cache (cuda_ops_api.h:44-49,
+ * reshape_paged_cache.cu:23-99).  cache layout [n_blocks, block_size,
+ * n_kv_heads, head_dim]; slot<0 is skipped.  Bit-exact copy. */
+int xb_reshape_paged_cache_bf16(const int32_t* slot_ids, const void* keys,
+                                const void* values, void* key_cache,
+                                void* value_cache, int64_t k_stride,
+                                int64_t v_stride, int n_kv_heads, int head_dim,
+                                int block_size, int num_tokens,
+                                xb_stream_t stream);
+
+/* ---- K9+K12 fused: RoPE (q,k in place) + scatter of rotated k and v --------
+ * one launch instead of rotary_embedding + reshape_paged_cache
+ * (qwen2_attention.cpp:173-176 + flashinfer_attention.cpp:128-131).
+ * Results are bit-identical to calling the two ops in sequence. */
+int xb_rope_and_cache_bf16(const int64_t* positions, void* query, void* key,
+                           const void* value, const void* cos_sin_cache,
+                           const int32_t* slot_ids, void* key_cache,
+                           void* value_cache, int rot_dim, int64_t query_stride,
+                           int64_t key_stride, int64_t value_stride,
+                           int num_heads, int num_kv_heads, int head_size,
+                           int block_size, int is_neox, int num_tokens,
+                           xb_stream_t stream);
+
+/* ---- K10: fused per-head QK RMSNorm + RoPE (Qwen3) -------------------------
+ * replaces xllm::kernel::cuda::fused_qk_norm_rope (cuda_ops_api.h:252-266,
+ * fused_qknorm_rope.cu:84-471). qkv packed [T,(hq+hk+hv)*d], in place. */
+int xb_fused_qk_norm_rope_bf16(void* qkv, int num_heads_q, int num_heads_k,
+                               int num_heads_v, int head_dim, float eps,
+                               const void* q_weight, const void* k_weight,
+                               const void* cos_sin_cache, int rot_dim,
+                               int interleaved, const int64_t* position_ids,
+                               int num_tokens, xb_stream_t stream);
+
+/* ---- K11: act_and_mul ------------------------------------------------------
+ * replaces xllm::kernel::cuda::act_and_mul (cuda_ops_api.h:39-42,
+ * activation.cu:45-186).  out[t,:] = bf16( bf16(act(x[t,:d])) * x[t,d:] ).
+ * act_mode: 0 silu, 1 gelu (erf), 2 gelu_tanh. */
+int xb_act_and_mul_bf16(void* out, const void* input, int d, int num_tokens,
+                        int act_mode, xb_stream_t stream);
+
+/* ---- K1/K2-decode: paged decode attention ----------------------------------
+ * replaces the FlashInfer decode module the reference dlopen()s
+ * (xllm/core/kernels/cuda/batch_decode.cpp:26-86 `run`; planner
+ * layers/cuda/flashinfer_planinfo.cpp:249-337 `plan`).
+ *
+ * q   [batch, num_qo_heads, head_dim] bf16 (q_stride_n / q_stride_h elements)
+ * k_cache, v_cache: paged, element strides (page, token, head); NHD layout of
+ *     the reference = (block_size*H_kv*D, H_kv*D, D).
+ * kv_indptr[batch+1], kv_indices[], kv_last_page_len[batch]: the reference's
+ *     paged triplet (batch_input_builder.cpp:790-801), int32, on device.
+ * o   [batch, num_qo_heads, head_dim] bf16; lse (optional) [batch, num_qo_heads]
+ *     f32, base-2 log-sum-exp of sm_scale*log2(e)*q.k like FlashInfer's state.
+ *
+ * xb_decode_plan is host-only arithmetic (no device access, no sync): given an
+ * upper bound of pages per request it picks how many KV splits to launch so
+ * that batch*num_kv_heads*splits covers the SMs, and returns workspace needs.
+ * The plan is opaque int64[8] (plan_info is opaque to xLLM too:
+ * flashinfer_planinfo.cpp:37-62).  workspace_f32 needs plan[2] bytes,
+ * workspace_i32 needs plan[3] bytes and MUST be zero-initialised once (the
+ * kernel restores it to zero). */
+int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int num_kv_heads,
+                   int head_dim, int page_size, int max_pages_per_request,
+                   int num_sms);
+int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t q_stride_n,
+                         int64_t q_stride_h, const void* k_cache,
+                         const void* v_cache, int64_t kv_stride_page,
+                         int64_t kv_stride_token, int64_t kv_stride_head,
+                         const int32_t* kv_indptr, const int32_t* kv_indices,
+                         const int32_t* kv_last_page_len, void* o,
+                         int64_t o_stride_n, int64_t o_stride_h, float* lse,
+                         float sm_scale, void* workspace_f32,
+                         void* workspace_i32, xb_stream_t stream);
+
+/* ---- weight-only / dense linears for small M (decode) ----------------------
+ * y[M,N] = x[M,K] . W^T (+ bias).  HBM-bound streaming kernels for M <= 64.
+ * (reference: ColumnParallelLinearImpl/RowParallelLinearImpl::forward,
+ *  layers/common/linear.cpp:616-716,1405-1522 -> kernels/cuda/matmul.cpp:20-24.)
+ *
+ * bf16: W is the reference's [N,K] row-major bf16 weight, untouched.
+ * w4a16: NEW additive boundary (the reference has no weight-only
+ *   kernel).  Spec (oracle/quant.py): w[n,k] = bf16( (q[n,k]-z[n,k/g]) * s[n,k/g] )
+ *   with q,z in 0..15, s bf16, g = group_size (multiple of 64; 128 default);
+ *   y = bf16( sum_k f32(x)*f32(w) (+bias) ), fp32 accumulation.
+ *   qweight is the tile-packed layout produced by xb_w4_pack_rows() /
+ *   xllm_b200.quant.pack_w4: [N/16][K/64][32 lanes][4] uint32; meta[K/g][N]
+ *   uint32 = (bf16 scale) | (bf16(128+zero) << 16). N%16==0, K%64==0. */
+int xb_linear_bf16_small_m(void* y, int64_t y_stride, const void* x,
+                           int64_t x_stride, const void* w, const void* bias,
+                           int M, int N, int K, xb_stream_t stream);
+int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
+                            int64_t x_stride, const uint32_t* qweight,
+                            const uint32_t* meta, const void* bias, int M, int N,
+                            int K, int group_size, xb_stream_t stream);
+/* host-side packer (plain C, no CUDA): q[N,K] uint8 (0..15) -> qweight tiles. */
+int xb_w4_pack_rows(uint32_t* qweight_out, const uint8_t* q, int N, int K);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XLLM_B200_OPS_H_ */

@@ -1,0 +1,58 @@
+"""CPU checks of the drop-in boundary: the library loads and exports every symbol include/xllm_b200_ops.h declares;
+host-side packers agree; argument errors are reported through the C ABI without touching a GPU."""
+import ctypes
+import os
+import re
+
+import torch
+
+from xllm_b200 import _lib, quant
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "xllm_b200_ops.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(xb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    names = declared_symbols()
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert _lib.lib().xb_abi_version() == 1
+
+
+def test_no_torch_types_in_abi():
+    src = open(os.path.join(ROOT, "include", "xllm_b200_ops.h")).read()
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    assert 'extern "C"' in src
+
+
+def test_w4_packers_agree(built_lib):
+    g = torch.Generator().manual_seed(2026)
+    q = torch.randint(0, 16, (64, 256), dtype=torch.uint8, generator=g)
+    s = torch.rand(64, 2, generator=g).to(torch.bfloat16)
+    z = torch.randint(0, 16, (64, 2), dtype=torch.uint8, generator=g)
+    qa, meta = quant.pack_w4(q, s, z, 128)
+    assert torch.equal(qa, quant.pack_w4_c(q))
+    # meta = bf16(scale) | bf16(128+zero) << 16, laid out [K/g, N]
+    assert meta.shape == (2, 64)
+    lo = (meta & 0xFFFF).to(torch.int16).view(torch.bfloat16)
+    hi = ((meta >> 16) & 0xFFFF).to(torch.int16).view(torch.bfloat16)
+    assert torch.equal(lo.t().contiguous(), s)
+    assert torch.equal(hi.t().to(torch.float32), z.to(torch.float32) + 128.0)
+
+
+def test_argument_errors_surface(built_lib):
+    lib = _lib.lib()
+    plan = (ctypes.c_int64 * 8)()
+    rc = lib.xb_decode_plan(plan, 1, 28, 4, 96, 128, 32, 148)      # head_dim 96 unsupported
+    assert rc != 0 and b"head_dim" in lib.xb_last_error()
+    rc = lib.xb_decode_plan(plan, 1, 28, 4, 128, 128, 32, 148)
+    assert rc == 0 and plan[0] % 16 == 0 and plan[0] * plan[1] >= 4096
+    rc = lib.xb_w4_pack_rows(None, None, 15, 64)
+    assert rc != 0

@@ -1,0 +1,31 @@
+"""Shared tolerances for the parity tests.
+
+bf16 carries 8 significant bits, so two correct bf16 results of the same fp32 value can differ by one ulp
+(2^-8 relative) when the fp32 values straddle a rounding boundary.  The bar used everywhere a floating-point
+kernel is compared with the oracle (north_star: "within 1e-3 relative for bf16/FP8"):
+  * relative L2 error over the tensor   <= 1e-3
+  * every element within `ulps` bf16 ulps of the oracle (default 1; accumulation-order noise)
+Integer / copy / index work is compared with torch.equal (bit-exact).
+"""
+import torch
+
+
+def bf16_ulp(x: torch.Tensor) -> torch.Tensor:
+    a = x.abs().to(torch.float32).clamp_min(2.0 ** -126)
+    return torch.exp2(torch.floor(torch.log2(a)) - 7)
+
+
+def assert_close_bf16(got: torch.Tensor, ref: torch.Tensor, ulps: float = 1.0, rel_l2: float = 1e-3, what: str = "",
+                      atol: float = 0.0):
+    g, r = got.detach().cpu().to(torch.float32), ref.detach().cpu().to(torch.float32)
+    assert g.shape == r.shape, f"{what}: shape {g.shape} vs {r.shape}"
+    assert torch.isfinite(g).all(), f"{what}: non-finite output"
+    err = (g - r).abs()
+    den = r.norm().item()
+    l2 = (g - r).norm().item() / den if den > 0 else (g - r).norm().item()
+    assert l2 <= rel_l2, f"{what}: relative L2 error {l2:.3e} > {rel_l2:.1e}"
+    bound = ulps * torch.maximum(bf16_ulp(r), bf16_ulp(g)) + atol
+    bad = err > bound
+    assert not bad.any(), (f"{what}: {int(bad.sum())} / {bad.numel()} elements beyond {ulps} bf16 ulp; "
+                           f"worst |err|={err.max().item():.3e} at ref={r.flatten()[err.argmax()].item():.4e}")
+    return l2

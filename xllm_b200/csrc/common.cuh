@@ -1,0 +1,142 @@
+// Shared device/host helpers for libxllm_b200_ops (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/xllm_b200_ops.h"
+
+namespace xb {
+
+// ---- error plumbing (thread-local message, C-ABI returns non-zero) ----------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+extern std::atomic<int> g_pdl_enabled;
+
+#define XB_CHECK(cond, ...)          \
+  do {                               \
+    if (!(cond)) {                   \
+      ::xb::set_error(__VA_ARGS__);  \
+      return 1;                      \
+    }                                \
+  } while (0)
+
+#define XB_CUDA_OK(expr)                                                      \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) {                                                  \
+      ::xb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                      __FILE__, __LINE__);                                    \
+      return 2;                                                               \
+    }                                                                         \
+  } while (0)
+
+// Launch helper: counts launches, optionally attaches the PDL attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                          size_t smem, cudaStream_t stream, bool pdl,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int n = 0;
+  if (pdl && g_pdl_enabled.load(std::memory_order_relaxed)) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---- device helpers ---------------------------------------------------------
+#ifdef __CUDACC__
+
+// PDL: wait for the producer grid's memory to be visible / let the consumer
+// grid start its prologue early.  No-ops when not launched with the attribute.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint32_t bits16) {
+  return __uint_as_float(bits16 << 16);
+}
+__device__ __forceinline__ float bf16lo(uint32_t packed) {
+  return __uint_as_float(packed << 16);
+}
+__device__ __forceinline__ float bf16hi(uint32_t packed) {
+  return __uint_as_float(packed & 0xffff0000u);
+}
+// round-to-nearest-even float -> bf16 bits (NaN-safe via intrinsic)
+__device__ __forceinline__ uint32_t f32_to_bf16_bits(float x) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// bf16 value rounded through bf16 and back (models `static_cast<scalar_t>(f)`)
+__device__ __forceinline__ float round_bf16(float x) {
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 128-bit streaming loads/stores.  KV pages and weights are read exactly once
+// per step: keep them out of L1 (L1::no_allocate) so x / q stay resident.
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_cached(const void* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+// sat_e4m3(x*inv_scale): fp8_quant_utils.cuh:112-129 (clamp to +-448, then
+// __nv_cvt_float_to_fp8(..., __NV_SATFINITE, __NV_E4M3) = RNE).
+__device__ __forceinline__ uint8_t scaled_fp8_e4m3(float v, float inv_scale) {
+  float x = v * inv_scale;
+  float r = fmaxf(-448.0f, fminf(x, 448.0f));
+  return (uint8_t)__nv_cvt_float_to_fp8(r, __NV_SATFINITE, __NV_E4M3);
+}
+
+// mma.sync m16n8k16 bf16 x bf16 -> f32 (register-resident fragments; used by
+// the HBM-bound small-M kernels where no smem staging is wanted).
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0,
+                                               uint32_t a1, uint32_t a2,
+                                               uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
+      "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+#endif  // __CUDACC__
+}  // namespace xb

@@ -1,0 +1,315 @@
+// Small-M (decode, M <= 64) linears: y[M,N] = x[M,K] . W^T (+bias).
+//
+// These are HBM-bound weight-streaming kernels: every weight byte is read once
+// with 16-byte coalesced loads straight into mma.sync fragments (no shared
+// memory staging of W), the M<=8 token columns ride in the n8 slot of
+// m16n8k16, fp32 accumulation.  The warps of a CTA split K and reduce through
+// shared memory; the CTA grid tiles N.  Weight loads are issued BEFORE the PDL
+// dependency wait (they do not depend on the producer kernel), so in a chained
+// decode step the HBM stream of layer i+1 starts while layer i drains.
+//
+// W4A16 spec (oracle/quant.py): w = bf16((q - z) * s); dequant is 1 LOP3
+// (+1 SHF) + HSUB2.BF16 + HMUL2.BF16 per weight PAIR, bit-exact with the spec:
+//   (q | 0x4300) is bf16(128+q) exactly; (128+q)-(128+z) is exact; one rounding
+//   in the multiply by s.
+//
+// Tile-packed W4 layout (shared with the tcgen05 prefill GEMM, which writes the
+// same per-thread 16-element k runs as 16-byte swizzled smem chunks):
+//   qweight[N/16][K/64][lane 0..31][word 0..3]  (uint32)
+//   lane = 4*g + t owns rows n0+g and n0+g+8, k in [k0+16t, k0+16t+16).
+//   word j holds k = k0+16t+4j+{0,1,2,3} for both rows; nibble positions
+//     [0]=(g,s0) [4]=(g,s1) [1]=(g+8,s0) [5]=(g+8,s1)
+//     [2]=(g,s2) [6]=(g,s3) [3]=(g+8,s2) [7]=(g+8,s3)
+//   so (w >> 4i) & 0x000f000f yields the bf16x2 mma A-fragment register a_i.
+// The mma k index is a permutation of physical k (dot products do not care);
+// the x fragment is gathered with the same permutation.
+#include "common.cuh"
+
+namespace xb {
+
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ uint32_t hsub2_bf16(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint32_t orv) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xea;" : "=r"(d) : "r"(a), "r"(mask), "r"(orv));  // (a & b) | c
+  return d;
+}
+
+// x fragment for one k64 tile (4 k16 steps) and one n8 token tile:
+// lane (g,t) needs x[tok = tile*8+g][k0 + 16t .. +16) = 32 bytes.
+struct XFrag {
+  uint4 lo, hi;  // k 0..7, 8..15 of the lane's run
+};
+__device__ __forceinline__ XFrag load_x(const __nv_bfloat16* x, int64_t x_stride, int tok, int M, int k) {
+  XFrag f;
+  if (tok < M) {
+    const uint4* p = reinterpret_cast<const uint4*>(x + (int64_t)tok * x_stride + k);
+    f.lo = p[0];
+    f.hi = p[1];
+  } else {
+    f.lo = make_uint4(0, 0, 0, 0);
+    f.hi = make_uint4(0, 0, 0, 0);
+  }
+  return f;
+}
+
+// ---------------------------------------------------------------------------
+// W4A16
+// ---------------------------------------------------------------------------
+template <int kMT /* n8 token tiles: M <= 8*kMT */, int kUnroll>
+__global__ void __launch_bounds__(kWarps * 32)
+linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
+                            int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
+                            const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int group_size) {
+  __shared__ float red[kWarps][kMT][16 * 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int ntile = blockIdx.x;
+  const int n0 = ntile * 16;
+  const int ktiles = K >> 6;
+  const uint4* wbase = qweight + (int64_t)ntile * ktiles * 32 + lane;
+
+  float acc[kMT][4];
+#pragma unroll
+  for (int m = 0; m < kMT; ++m)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
+
+  // warp w takes k64 tiles w, w+kWarps, ...; kUnroll tiles per iteration.
+  for (int kt0 = warp; kt0 < ktiles; kt0 += kWarps * kUnroll) {
+    uint4 wq[kUnroll];
+    uint32_t mt0[kUnroll], mt1[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int kt = kt0 + u * kWarps;
+      if (kt < ktiles) {
+        wq[u] = ldg_stream(wbase + (int64_t)kt * 32);
+        const int grp = (kt << 6) / group_size;
+        mt0[u] = __ldg(meta + (int64_t)grp * N + n0 + g);
+        mt1[u] = __ldg(meta + (int64_t)grp * N + n0 + g + 8);
+      }
+    }
+    if (kt0 == warp) pdl_wait();  // x comes from the producer kernel; weights above do not
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int kt = kt0 + u * kWarps;
+      if (kt < ktiles) {
+        // scale / zero pairs replicated into both bf16 lanes
+        const uint32_t s0 = __byte_perm(mt0[u], 0, 0x1010), z0 = __byte_perm(mt0[u], 0, 0x3232);
+        const uint32_t s1 = __byte_perm(mt1[u], 0, 0x1010), z1 = __byte_perm(mt1[u], 0, 0x3232);
+        XFrag xf[kMT];
+#pragma unroll
+        for (int m = 0; m < kMT; ++m) xf[m] = load_x(x, x_stride, m * 8 + g, M, (kt << 6) + 16 * t);
+        const uint32_t* wp = &wq[u].x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t w = wp[j];
+          const uint32_t q0 = lop3_and_or(w, 0x000f000fu, 0x43004300u);
+          const uint32_t q1 = lop3_and_or(w >> 4, 0x000f000fu, 0x43004300u);
+          const uint32_t q2 = lop3_and_or(w >> 8, 0x000f000fu, 0x43004300u);
+          const uint32_t q3 = lop3_and_or(w >> 12, 0x000f000fu, 0x43004300u);
+          const uint32_t a0 = hmul2_bf16(hsub2_bf16(q0, z0), s0);
+          const uint32_t a1 = hmul2_bf16(hsub2_bf16(q1, z1), s1);
+          const uint32_t a2 = hmul2_bf16(hsub2_bf16(q2, z0), s0);
+          const uint32_t a3 = hmul2_bf16(hsub2_bf16(q3, z1), s1);
+#pragma unroll
+          for (int m = 0; m < kMT; ++m) {
+            // lane run element 4j+{0,1} -> b0, 4j+{2,3} -> b1
+            const uint32_t* xp = j < 2 ? &xf[m].lo.x : &xf[m].hi.x;
+            mma_bf16_16816(acc[m], a0, a1, a2, a3, xp[(j & 1) * 2], xp[(j & 1) * 2 + 1]);
+          }
+        }
+      }
+    }
+  }
+  if (ktiles <= warp) pdl_wait();
+  pdl_launch_dependents();
+
+  // cross-warp reduction: c0:(row g, tok 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
+#pragma unroll
+  for (int m = 0; m < kMT; ++m) {
+    red[warp][m][g * 8 + 2 * t] = acc[m][0];
+    red[warp][m][g * 8 + 2 * t + 1] = acc[m][1];
+    red[warp][m][(g + 8) * 8 + 2 * t] = acc[m][2];
+    red[warp][m][(g + 8) * 8 + 2 * t + 1] = acc[m][3];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMT * 128; i += blockDim.x) {
+    const int m = i >> 7, r = (i & 127) >> 3, c = i & 7;
+    const int tok = m * 8 + c;
+    if (tok < M) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += red[w][m][r * 8 + c];
+      if (bias) s += __bfloat162float(bias[n0 + r]);
+      y[(int64_t)tok * y_stride + n0 + r] = __float2bfloat16_rn(s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// bf16 weights [N,K] row-major (the reference layout, untouched).
+// lane (g,t) reads rows n0+g and n0+g+8, 16 bytes each per k32 tile:
+// k in [k0+8t, k0+8t+8) -> two k16 steps (elements 0..3 -> step 0, 4..7 -> 1).
+// ---------------------------------------------------------------------------
+template <int kMT, int kUnroll>
+__global__ void __launch_bounds__(kWarps * 32)
+linear_bf16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
+                           int64_t x_stride, const __nv_bfloat16* __restrict__ w,
+                           const __nv_bfloat16* __restrict__ bias, int M, int N, int K) {
+  __shared__ float red[kWarps][kMT][16 * 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * 16;
+  const int ktiles = K >> 5;  // k32 tiles
+  const bool r1_ok = (n0 + g + 8) < N, r0_ok = (n0 + g) < N;
+  const __nv_bfloat16* w0 = w + (int64_t)(n0 + g) * K + 8 * t;
+  const __nv_bfloat16* w1 = w + (int64_t)(n0 + g + 8) * K + 8 * t;
+
+  float acc[kMT][4];
+#pragma unroll
+  for (int m = 0; m < kMT; ++m)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
+
+  for (int kt0 = warp; kt0 < ktiles; kt0 += kWarps * kUnroll) {
+    uint4 wa[kUnroll], wb[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int kt = kt0 + u * kWarps;
+      wa[u] = make_uint4(0, 0, 0, 0);
+      wb[u] = make_uint4(0, 0, 0, 0);
+      if (kt < ktiles) {
+        if (r0_ok) wa[u] = ldg_stream(w0 + (kt << 5));
+        if (r1_ok) wb[u] = ldg_stream(w1 + (kt << 5));
+      }
+    }
+    if (kt0 == warp) pdl_wait();
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int kt = kt0 + u * kWarps;
+      if (kt < ktiles) {
+#pragma unroll
+        for (int m = 0; m < kMT; ++m) {
+          const int tok = m * 8 + g;
+          uint4 xv = make_uint4(0, 0, 0, 0);
+          if (tok < M) xv = *reinterpret_cast<const uint4*>(x + (int64_t)tok * x_stride + (kt << 5) + 8 * t);
+          mma_bf16_16816(acc[m], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
+          mma_bf16_16816(acc[m], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
+        }
+      }
+    }
+  }
+  if (ktiles <= warp) pdl_wait();
+  pdl_launch_dependents();
+
+#pragma unroll
+  for (int m = 0; m < kMT; ++m) {
+    red[warp][m][g * 8 + 2 * t] = acc[m][0];
+    red[warp][m][g * 8 + 2 * t + 1] = acc[m][1];
+    red[warp][m][(g + 8) * 8 + 2 * t] = acc[m][2];
+    red[warp][m][(g + 8) * 8 + 2 * t + 1] = acc[m][3];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMT * 128; i += blockDim.x) {
+    const int m = i >> 7, r = (i & 127) >> 3, c = i & 7;
+    const int tok = m * 8 + c;
+    if (tok < M && n0 + r < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kWarps; ++ww) s += red[ww][m][r * 8 + c];
+      if (bias) s += __bfloat162float(bias[n0 + r]);
+      y[(int64_t)tok * y_stride + n0 + r] = __float2bfloat16_rn(s);
+    }
+  }
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x, int64_t x_stride,
+                                       const uint32_t* qweight, const uint32_t* meta, const void* bias, int M, int N,
+                                       int K, int group_size, xb_stream_t stream) {
+  if (M == 0) return 0;
+  XB_CHECK(M > 0 && M <= 64, "linear_w4a16_small_m: M=%d out of range (1..64); use the tcgen05 GEMM", M);
+  XB_CHECK(N % 16 == 0 && K % 64 == 0, "linear_w4a16_small_m: N=%d must be %%16, K=%d %%64", N, K);
+  XB_CHECK(group_size >= 64 && group_size % 64 == 0 && K % group_size == 0,
+           "linear_w4a16_small_m: group_size %d must be a multiple of 64 dividing K=%d", group_size, K);
+  XB_CHECK(x_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "linear_w4a16_small_m: x not 16B aligned");
+  auto* yy = reinterpret_cast<__nv_bfloat16*>(y);
+  auto* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto* qw = reinterpret_cast<const uint4*>(qweight);
+  auto* bb = reinterpret_cast<const __nv_bfloat16*>(bias);
+  dim3 grid(N / 16), block(kWarps * 32);
+  cudaStream_t s = (cudaStream_t)stream;
+#define XB_W4(MT, U)                                                                                          \
+  XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, U>, grid, block, 0, s, true, yy, y_stride, xx, x_stride, \
+                    qw, meta, bb, M, N, K, group_size))
+  if (M <= 8) XB_W4(1, 8);
+  else if (M <= 16) XB_W4(2, 4);
+  else if (M <= 32) XB_W4(4, 2);
+  else XB_W4(8, 1);
+#undef XB_W4
+  return 0;
+}
+
+extern "C" int xb_linear_bf16_small_m(void* y, int64_t y_stride, const void* x, int64_t x_stride, const void* w,
+                                      const void* bias, int M, int N, int K, xb_stream_t stream) {
+  if (M == 0) return 0;
+  XB_CHECK(M > 0 && M <= 64, "linear_bf16_small_m: M=%d out of range (1..64); use the tcgen05 GEMM", M);
+  XB_CHECK(K % 32 == 0, "linear_bf16_small_m: K=%d must be a multiple of 32", K);
+  XB_CHECK(x_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+           "linear_bf16_small_m: x / w not 16B aligned");
+  auto* yy = reinterpret_cast<__nv_bfloat16*>(y);
+  auto* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto* ww = reinterpret_cast<const __nv_bfloat16*>(w);
+  auto* bb = reinterpret_cast<const __nv_bfloat16*>(bias);
+  dim3 grid((N + 15) / 16), block(kWarps * 32);
+  cudaStream_t s = (cudaStream_t)stream;
+#define XB_BF(MT, U) \
+  XB_CUDA_OK(launch(linear_bf16_small_m_kernel<MT, U>, grid, block, 0, s, true, yy, y_stride, xx, x_stride, ww, bb, M, N, K))
+  if (M <= 8) XB_BF(1, 8);
+  else if (M <= 16) XB_BF(2, 4);
+  else if (M <= 32) XB_BF(4, 2);
+  else XB_BF(8, 1);
+#undef XB_BF
+  return 0;
+}
+
+// Host-side packer (plain C++): q[N,K] (one 4-bit value per byte) -> tile layout.
+extern "C" int xb_w4_pack_rows(uint32_t* out, const uint8_t* q, int N, int K) {
+  XB_CHECK(N % 16 == 0 && K % 64 == 0, "w4_pack_rows: N=%d must be %%16, K=%d %%64", N, K);
+  const int ktiles = K / 64;
+  for (int nt = 0; nt < N / 16; ++nt)
+    for (int kt = 0; kt < ktiles; ++kt)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        const uint8_t* r0 = q + (size_t)(nt * 16 + g) * K + kt * 64 + 16 * t;
+        const uint8_t* r1 = q + (size_t)(nt * 16 + g + 8) * K + kt * 64 + 16 * t;
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w = 0;
+          w |= (uint32_t)(r0[4 * j + 0] & 15) << 0;
+          w |= (uint32_t)(r0[4 * j + 1] & 15) << 16;
+          w |= (uint32_t)(r1[4 * j + 0] & 15) << 4;
+          w |= (uint32_t)(r1[4 * j + 1] & 15) << 20;
+          w |= (uint32_t)(r0[4 * j + 2] & 15) << 8;
+          w |= (uint32_t)(r0[4 * j + 3] & 15) << 24;
+          w |= (uint32_t)(r1[4 * j + 2] & 15) << 12;
+          w |= (uint32_t)(r1[4 * j + 3] & 15) << 28;
+          out[(((size_t)nt * ktiles + kt) * 32 + lane) * 4 + j] = w;
+        }
+      }
+  return 0;
+}

@@ -1,0 +1,430 @@
+// Paged decode attention (q_len = 1 per request) over the block-table KV cache.
+// Replaces the FlashInfer decode module behind xllm::kernel::cuda::batch_decode
+// (xllm/core/kernels/cuda/batch_decode.cpp:26-86; planner
+//  xllm/core/layers/cuda/flashinfer_planinfo.cpp:249-337).
+//
+// Design (HBM-bound, B200):
+//   grid = (kv splits, kv heads, batch).  One CTA streams one KV chunk of one
+//   (request, kv head): all GQA query heads of that kv head share the chunk, so
+//   every KV byte is read exactly once.  Per 16-token block a thread issues 16
+//   independent 16-byte loads (8 K + 8 V) straight into mma.sync fragments -
+//   rows are gathered through the page table, each K/V row is a contiguous
+//   head_dim*2-byte segment (128-byte coalesced sectors), no shared-memory
+//   staging.  The head-dim / token permutations the fragment layout implies are
+//   absorbed by loading q with the same permutation (a dot product does not
+//   care about the order of its terms).
+//     S[head, tok]  = Q[16 heads x d] . K^T        (m16n8k16, heads in M)
+//     O[head, d]   += P[16 heads x 16 tok] . V     (C-fragments of S feed A of PV)
+//   fp32 online softmax in base 2 (sm_scale*log2(e) folded into one FMUL), P is
+//   rounded to bf16 for the PV MMA, fp32 accumulation - the same ladder as the
+//   FlashInfer tensor-core decode path the reference selects for GQA >= 4
+//   (utils.cpp:349-367).
+//   Warps of a CTA split the chunk's 16-token blocks and merge their
+//   (m, l, O) states through shared memory; CTAs of one (request, kv head)
+//   publish normalised partials + base-2 LSE to the float workspace and the
+//   LAST one to arrive (atomic ticket in the int workspace) merges them - no
+//   second launch, no host sync, CUDA-graph safe (grid is sized from an upper
+//   bound; CTAs past the live split count exit).
+#include "common.cuh"
+
+namespace xb {
+
+struct DecodeParams {
+  const __nv_bfloat16* q;
+  int64_t q_stride_n, q_stride_h;
+  const __nv_bfloat16* k_cache;
+  const __nv_bfloat16* v_cache;
+  int64_t stride_page, stride_token, stride_head;
+  const int32_t* kv_indptr;
+  const int32_t* kv_indices;
+  const int32_t* kv_last_page_len;
+  __nv_bfloat16* o;
+  int64_t o_stride_n, o_stride_h;
+  float* lse;  // optional [batch, num_qo_heads]
+  float scale_log2;
+  float* part_o;    // [batch, num_qo_heads, max_splits, D]
+  float* part_lse;  // [batch, num_qo_heads, max_splits]
+  int32_t* counters;  // [batch, num_kv_heads * head_tiles]
+  int num_qo_heads, num_kv_heads, group, head_tiles;
+  int page_size, page_shift;  // page_shift >= 0 when page_size is a power of two
+  int chunk_tokens, max_splits;
+};
+
+__device__ __forceinline__ const __nv_bfloat16* kv_row(const DecodeParams& p, const __nv_bfloat16* cache,
+                                                       int indptr0, int tok, int kvh) {
+  int page_idx, off;
+  if (p.page_shift >= 0) {
+    page_idx = tok >> p.page_shift;
+    off = tok & (p.page_size - 1);
+  } else {
+    page_idx = tok / p.page_size;
+    off = tok - page_idx * p.page_size;
+  }
+  const int64_t page = __ldg(p.kv_indices + indptr0 + page_idx);
+  return cache + page * p.stride_page + (int64_t)off * p.stride_token + (int64_t)kvh * p.stride_head;
+}
+
+template <int kD, int kGT /*1: <=8 heads per CTA, 2: <=16*/, int kWarpsT>
+__global__ void __launch_bounds__(kWarpsT * 32, 1)
+paged_decode_kernel(const DecodeParams p) {
+  constexpr int kChunks = kD / 32;  // 16-byte K chunks per lane per token
+  constexpr int kNT = kD / 8;       // n8 tiles of the output
+  constexpr int kVC = kD / 64;      // V chunk loads per token per lane
+  constexpr int kHeads = 8 * kGT;
+  constexpr int kRS = kD + 4;       // padded smem row (floats)
+  extern __shared__ __align__(16) float smem[];
+  float* sm_o = smem;                              // [warps][kHeads][kRS]
+  float* sm_m = sm_o + kWarpsT * kHeads * kRS;      // [warps][kHeads]
+  float* sm_l = sm_m + kWarpsT * kHeads;           // [warps][kHeads]
+  __shared__ int s_ticket;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int split = blockIdx.x;
+  const int kvh = blockIdx.y / p.head_tiles, htile = blockIdx.y % p.head_tiles;
+  const int b = blockIdx.z;
+
+  pdl_wait();
+
+  const int indptr0 = __ldg(p.kv_indptr + b);
+  const int n_pages = __ldg(p.kv_indptr + b + 1) - indptr0;
+  const int kv_len = n_pages > 0 ? (n_pages - 1) * p.page_size + __ldg(p.kv_last_page_len + b) : 0;
+  int n_splits = (kv_len + p.chunk_tokens - 1) / p.chunk_tokens;
+  if (n_splits < 1) n_splits = 1;
+  if (split >= n_splits) return;
+  const int t_begin = split * p.chunk_tokens;
+  const int t_end = min(kv_len, t_begin + p.chunk_tokens);
+  const int head0 = kvh * p.group + htile * kHeads;            // first qo head of this CTA
+  const int nheads = min(kHeads, p.group - htile * kHeads);    // live heads in this CTA
+
+  // ---- Q fragments (chunk 4i+t of head g / g+8, same permutation as K) -------
+  uint4 qa[kChunks], qb[kChunks];
+  {
+    const __nv_bfloat16* qrow = p.q + (int64_t)b * p.q_stride_n;
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+      qa[i] = make_uint4(0, 0, 0, 0);
+      qb[i] = make_uint4(0, 0, 0, 0);
+      if (g < nheads) qa[i] = *reinterpret_cast<const uint4*>(qrow + (int64_t)(head0 + g) * p.q_stride_h + (4 * i + t) * 8);
+      if (kGT == 2 && g + 8 < nheads)
+        qb[i] = *reinterpret_cast<const uint4*>(qrow + (int64_t)(head0 + g + 8) * p.q_stride_h + (4 * i + t) * 8);
+    }
+  }
+
+  float o_acc[kNT][4];
+#pragma unroll
+  for (int j = 0; j < kNT; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o_acc[j][i] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};  // head g, head g+8
+  float l_run[2] = {0.f, 0.f};              // per-thread partial sums
+
+  const int nblk = (t_end - t_begin + 15) >> 4;
+  const int last_tok = kv_len - 1;
+
+  for (int blk = warp; blk < nblk; blk += kWarpsT) {
+    const int tb = t_begin + (blk << 4);
+    // ---- issue all 16 loads of the block -------------------------------------
+    uint4 kf[2][kChunks];
+    uint4 vf[4][kVC];
+    {
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        const int tok = min(tb + tile * 8 + g, last_tok);
+        const __nv_bfloat16* row = kv_row(p, p.k_cache, indptr0, tok, kvh);
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) kf[tile][i] = ldg_stream(row + (4 * i + t) * 8);
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int tok = min(tb + (s >> 1) * 8 + 2 * t + (s & 1), last_tok);
+        const __nv_bfloat16* row = kv_row(p, p.v_cache, indptr0, tok, kvh);
+#pragma unroll
+        for (int c = 0; c < kVC; ++c) vf[s][c] = ldg_stream(row + (c * 8 + g) * 8);
+      }
+    }
+    // ---- S = Q K^T ----------------------------------------------------------
+    float s_acc[2][4];
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_acc[tile][i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) {
+        mma_bf16_16816(s_acc[tile], qa[i].x, qb[i].x, qa[i].y, qb[i].y, kf[tile][i].x, kf[tile][i].y);
+        mma_bf16_16816(s_acc[tile], qa[i].z, qb[i].z, qa[i].w, qb[i].w, kf[tile][i].z, kf[tile][i].w);
+      }
+    }
+    // ---- online softmax (base 2) ---------------------------------------------
+    uint32_t pa[4];  // A fragment of P: a0 (g, tile0) a1 (g+8, tile0) a2 (g, tile1) a3 (g+8, tile1)
+#pragma unroll
+    for (int hh = 0; hh < kGT; ++hh) {
+      float sv[4];
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int tok = tb + tile * 8 + 2 * t + e;
+          const float s = s_acc[tile][hh * 2 + e] * p.scale_log2;
+          sv[tile * 2 + e] = tok < t_end ? s : -INFINITY;
+        }
+      float mx = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_run[hh], mx);
+      const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+      const float alpha = exp2f(m_run[hh] - m_safe);
+      float pv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = exp2f(sv[i] - m_safe);
+      // P is rounded to bf16 for the PV MMA and the denominator sums the ROUNDED values
+      // (FlashInfer prefill.cuh compute_sfm_v: rowsum over s_frag_f16), so the weights stay normalised.
+      const uint32_t p01 = pack_bf16x2(pv[0], pv[1]), p23 = pack_bf16x2(pv[2], pv[3]);
+      const float ps = (bf16lo(p01) + bf16hi(p01)) + (bf16lo(p23) + bf16hi(p23));
+      l_run[hh] = l_run[hh] * alpha + ps;
+      m_run[hh] = m_new;
+#pragma unroll
+      for (int j = 0; j < kNT; ++j) {
+        o_acc[j][hh * 2] *= alpha;
+        o_acc[j][hh * 2 + 1] *= alpha;
+      }
+      pa[hh] = p01;
+      pa[2 + hh] = p23;
+    }
+    if (kGT == 1) {
+      pa[1] = 0;
+      pa[3] = 0;
+    }
+    // ---- O += P V -----------------------------------------------------------
+#pragma unroll
+    for (int c = 0; c < kVC; ++c) {
+      const uint32_t* v0 = &vf[0][c].x;
+      const uint32_t* v1 = &vf[1][c].x;
+      const uint32_t* v2 = &vf[2][c].x;
+      const uint32_t* v3 = &vf[3][c].x;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t b0e = __byte_perm(v0[r], v1[r], 0x5410), b1e = __byte_perm(v2[r], v3[r], 0x5410);
+        const uint32_t b0o = __byte_perm(v0[r], v1[r], 0x7632), b1o = __byte_perm(v2[r], v3[r], 0x7632);
+        mma_bf16_16816(o_acc[c * 8 + 2 * r], pa[0], pa[1], pa[2], pa[3], b0e, b1e);
+        mma_bf16_16816(o_acc[c * 8 + 2 * r + 1], pa[0], pa[1], pa[2], pa[3], b0o, b1o);
+      }
+    }
+  }
+  pdl_launch_dependents();
+
+  // ---- publish warp state ------------------------------------------------------
+#pragma unroll
+  for (int hh = 0; hh < kGT; ++hh) {
+    float l = l_run[hh];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    const int h = g + 8 * hh;
+    if (t == 0) {
+      sm_m[warp * kHeads + h] = m_run[hh];
+      sm_l[warp * kHeads + h] = l;
+    }
+    // lane (g,t) holds, for head h, d in [64c+16t, 64c+16t+16): n-tile j=8c+jj, column
+    // 2t+e  <->  d = 64c + 8*(2t+e) + jj.  Two float4 stores per (c,e).
+    float* orow = sm_o + ((warp * kHeads + h) * kRS);
+#pragma unroll
+    for (int c = 0; c < kVC; ++c)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float* dst = orow + 64 * c + 16 * t + 8 * e;
+        *reinterpret_cast<float4*>(dst) = make_float4(o_acc[c * 8 + 0][hh * 2 + e], o_acc[c * 8 + 1][hh * 2 + e],
+                                                      o_acc[c * 8 + 2][hh * 2 + e], o_acc[c * 8 + 3][hh * 2 + e]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o_acc[c * 8 + 4][hh * 2 + e], o_acc[c * 8 + 5][hh * 2 + e],
+                                                          o_acc[c * 8 + 6][hh * 2 + e], o_acc[c * 8 + 7][hh * 2 + e]);
+      }
+  }
+  __syncthreads();
+
+  // ---- merge warps; each thread owns (head, 4 consecutive d) items ---------------
+  constexpr int kItems = kHeads * (kD / 4);
+  const bool single = n_splits == 1;
+  for (int it = threadIdx.x; it < kItems; it += kWarpsT * 32) {
+    const int h = it / (kD / 4), d4 = (it % (kD / 4)) * 4;
+    if (h >= nheads) continue;
+    float m_tot = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kWarpsT; ++w) m_tot = fmaxf(m_tot, sm_m[w * kHeads + h]);
+    const float m_safe = m_tot == -INFINITY ? 0.f : m_tot;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l_tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarpsT; ++w) {
+      const float sc = exp2f(sm_m[w * kHeads + h] - m_safe);
+      l_tot += sm_l[w * kHeads + h] * sc;
+      const float4 v = *reinterpret_cast<const float4*>(sm_o + ((w * kHeads + h) * kRS) + d4);
+      acc.x += v.x * sc;
+      acc.y += v.y * sc;
+      acc.z += v.z * sc;
+      acc.w += v.w * sc;
+    }
+    const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    const float lse2 = l_tot > 0.f ? m_tot + log2f(l_tot) : -INFINITY;
+    const int qh = head0 + h;
+    if (single) {
+      uint2 ob;
+      ob.x = pack_bf16x2(acc.x, acc.y);
+      ob.y = pack_bf16x2(acc.z, acc.w);
+      *reinterpret_cast<uint2*>(p.o + (int64_t)b * p.o_stride_n + (int64_t)qh * p.o_stride_h + d4) = ob;
+      if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = lse2;
+    } else {
+      const int64_t slot = ((int64_t)b * p.num_qo_heads + qh) * p.max_splits + split;
+      *reinterpret_cast<float4*>(p.part_o + slot * kD + d4) = acc;
+      if (d4 == 0) p.part_lse[slot] = lse2;
+    }
+  }
+  if (single) return;
+
+  // ---- last CTA of this (request, kv head, head tile) merges the splits -----------
+  __threadfence();
+  __syncthreads();
+  int32_t* counter = p.counters + (int64_t)b * gridDim.y + blockIdx.y;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1);
+  __syncthreads();
+  if (s_ticket != n_splits - 1) return;
+  __threadfence();
+  if (threadIdx.x == 0) *counter = 0;  // restore for the next launch
+  for (int it = threadIdx.x; it < kItems; it += kWarpsT * 32) {
+    const int h = it / (kD / 4), d4 = (it % (kD / 4)) * 4;
+    if (h >= nheads) continue;
+    const int qh = head0 + h;
+    const int64_t base = ((int64_t)b * p.num_qo_heads + qh) * p.max_splits;
+    float m_tot = -INFINITY;
+    for (int s = 0; s < n_splits; ++s) m_tot = fmaxf(m_tot, __ldcg(p.part_lse + base + s));
+    const float m_safe = m_tot == -INFINITY ? 0.f : m_tot;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wsum = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < n_splits; ++s) {
+      const float w = exp2f(__ldcg(p.part_lse + base + s) - m_safe);
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part_o + (base + s) * kD + d4));
+      wsum += w;
+      acc.x += v.x * w;
+      acc.y += v.y * w;
+      acc.z += v.z * w;
+      acc.w += v.w * w;
+    }
+    const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
+    uint2 ob;
+    ob.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+    ob.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+    *reinterpret_cast<uint2*>(p.o + (int64_t)b * p.o_stride_n + (int64_t)qh * p.o_stride_h + d4) = ob;
+    if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = wsum > 0.f ? m_tot + log2f(wsum) : -INFINITY;
+  }
+}
+
+constexpr int kDecodeWarps = 8;
+
+template <int kD, int kGT>
+static int launch_decode(const DecodeParams& p, int batch, cudaStream_t stream) {
+  constexpr int kHeads = 8 * kGT;
+  const size_t smem = (size_t)kDecodeWarps * kHeads * (kD + 4 + 2) * sizeof(float);
+  auto kern = paged_decode_kernel<kD, kGT, kDecodeWarps>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid(p.max_splits, p.num_kv_heads * p.head_tiles, batch), block(kDecodeWarps * 32);
+  XB_CUDA_OK(launch(kern, grid, block, smem, stream, true, p));
+  return 0;
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+// plan8: [0]=chunk_tokens [1]=max_splits [2]=float ws bytes [3]=int ws bytes
+//        [4]=batch [5]=num_qo_heads [6]=num_kv_heads [7]=head_dim | page_size<<16
+extern "C" int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int num_kv_heads, int head_dim,
+                              int page_size, int max_pages_per_request, int num_sms) {
+  XB_CHECK(batch > 0 && num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0,
+           "decode_plan: bad heads %d/%d or batch %d", num_qo_heads, num_kv_heads, batch);
+  XB_CHECK(head_dim == 64 || head_dim == 128, "decode_plan: head_dim %d unsupported (64|128)", head_dim);
+  XB_CHECK(page_size > 0 && page_size < 65536 && max_pages_per_request > 0, "decode_plan: bad page geometry");
+  if (num_sms <= 0) num_sms = 148;
+  const int group = num_qo_heads / num_kv_heads;
+  const int head_tiles = (group + 15) / 16;
+  const int64_t units = (int64_t)batch * num_kv_heads * head_tiles;
+  const int64_t max_kv = (int64_t)max_pages_per_request * page_size;
+  // one resident CTA per SM; aim for one full wave, chunks are whole 16-token blocks
+  int64_t want = num_sms / units;
+  if (want < 1) want = 1;
+  int64_t chunk = (max_kv + want - 1) / want;
+  chunk = ((chunk + 15) / 16) * 16;
+  if (chunk < 64) chunk = 64;
+  const char* env = getenv("XB_DECODE_CHUNK");
+  if (env && atoi(env) >= 16) chunk = (atoi(env) / 16) * 16;
+  const int64_t splits = (max_kv + chunk - 1) / chunk;
+  plan8[0] = chunk;
+  plan8[1] = splits;
+  plan8[2] = splits > 1 ? (int64_t)batch * num_qo_heads * splits * (head_dim + 1) * 4 : 16;
+  plan8[3] = units * 4;
+  plan8[4] = batch;
+  plan8[5] = num_qo_heads;
+  plan8[6] = num_kv_heads;
+  plan8[7] = (int64_t)head_dim | ((int64_t)page_size << 16);
+  return 0;
+}
+
+extern "C" int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t q_stride_n, int64_t q_stride_h,
+                                    const void* k_cache, const void* v_cache, int64_t kv_stride_page,
+                                    int64_t kv_stride_token, int64_t kv_stride_head, const int32_t* kv_indptr,
+                                    const int32_t* kv_indices, const int32_t* kv_last_page_len, void* o,
+                                    int64_t o_stride_n, int64_t o_stride_h, float* lse, float sm_scale,
+                                    void* workspace_f32, void* workspace_i32, xb_stream_t stream) {
+  XB_CHECK(plan8 != nullptr, "paged_decode: plan is null (call xb_decode_plan first)");
+  DecodeParams p{};
+  const int batch = (int)plan8[4];
+  const int head_dim = (int)(plan8[7] & 0xffff);
+  p.page_size = (int)(plan8[7] >> 16);
+  p.page_shift = -1;
+  if ((p.page_size & (p.page_size - 1)) == 0) {
+    int s = 0;
+    while ((1 << s) < p.page_size) ++s;
+    p.page_shift = s;
+  }
+  p.num_qo_heads = (int)plan8[5];
+  p.num_kv_heads = (int)plan8[6];
+  p.group = p.num_qo_heads / p.num_kv_heads;
+  p.head_tiles = (p.group + 15) / 16;
+  p.chunk_tokens = (int)plan8[0];
+  p.max_splits = (int)plan8[1];
+  XB_CHECK(q_stride_h % 8 == 0 && q_stride_n % 8 == 0 && kv_stride_token % 8 == 0 && kv_stride_head % 8 == 0 &&
+               kv_stride_page % 8 == 0 && o_stride_h % 4 == 0 && o_stride_n % 4 == 0,
+           "paged_decode: strides must keep 16-byte alignment");
+  XB_CHECK(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k_cache) |
+             reinterpret_cast<uintptr_t>(v_cache)) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 7) == 0,
+           "paged_decode: q/k_cache/v_cache must be 16-byte aligned");
+  XB_CHECK(p.max_splits == 1 || (workspace_f32 && workspace_i32), "paged_decode: split-KV needs both workspaces");
+  p.q = reinterpret_cast<const __nv_bfloat16*>(q);
+  p.q_stride_n = q_stride_n;
+  p.q_stride_h = q_stride_h;
+  p.k_cache = reinterpret_cast<const __nv_bfloat16*>(k_cache);
+  p.v_cache = reinterpret_cast<const __nv_bfloat16*>(v_cache);
+  p.stride_page = kv_stride_page;
+  p.stride_token = kv_stride_token;
+  p.stride_head = kv_stride_head;
+  p.kv_indptr = kv_indptr;
+  p.kv_indices = kv_indices;
+  p.kv_last_page_len = kv_last_page_len;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.o_stride_n = o_stride_n;
+  p.o_stride_h = o_stride_h;
+  p.lse = lse;
+  p.scale_log2 = sm_scale * 1.44269504088896340736f;
+  p.part_o = reinterpret_cast<float*>(workspace_f32);
+  p.part_lse = p.part_o ? p.part_o + (int64_t)batch * p.num_qo_heads * p.max_splits * head_dim : nullptr;
+  p.counters = reinterpret_cast<int32_t*>(workspace_i32);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool wide = p.group > 8;
+  if (head_dim == 128) return wide ? launch_decode<128, 2>(p, batch, s) : launch_decode<128, 1>(p, batch, s);
+  if (head_dim == 64) return wide ? launch_decode<64, 2>(p, batch, s) : launch_decode<64, 1>(p, batch, s);
+  XB_CHECK(false, "paged_decode: head_dim %d unsupported", head_dim);
+  return 1;
+}

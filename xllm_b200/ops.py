@@ -1,0 +1,247 @@
+"""Host-side mirror of `xllm::kernel::cuda::*` (xllm/core/kernels/cuda/cuda_ops_api.h:31-216).
+
+Same function names, argument order and in-place/out conventions as the
+reference; tensors are torch CUDA tensors used purely as device-memory handles.
+Everything routes through the C ABI (include/xllm_b200_ops.h); errors raise
+XllmB200Error (the reference aborts via glog CHECK / throws c10::Error).
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import XllmB200Error, c_f32, c_i32, c_i64, c_ptr, check, lib
+
+BF16 = torch.bfloat16
+E4M3 = torch.float8_e4m3fn
+
+
+def _stream():
+    return c_ptr(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return c_ptr(0) if t is None else c_ptr(t.data_ptr())
+
+
+def _need(cond, msg):
+    if not cond:
+        raise XllmB200Error(msg)
+
+
+def _cuda_bf16(t, name):
+    _need(t.is_cuda, f"{name} must be a CUDA tensor (no CPU path)")
+    _need(t.dtype == BF16, f"{name} must be bfloat16, got {t.dtype}")
+
+
+# ---- K7 ---------------------------------------------------------------------
+def rms_norm(output: torch.Tensor, input: torch.Tensor, weight: torch.Tensor, eps: float) -> None:
+    """cuda_ops_api.h:157-160 / norm.cu:430-460."""
+    _cuda_bf16(input, "input"); _cuda_bf16(output, "output"); _cuda_bf16(weight, "weight")
+    _need(input.stride(-1) == 1, "input last dim must be contiguous")
+    H = input.size(-1)
+    x2 = input.reshape(-1, H) if input.dim() != 2 else input
+    _need(output.is_contiguous(), "output must be contiguous")
+    check(lib().xb_rms_norm_bf16(_p(output), _p(x2), c_i64(x2.stride(0)), _p(weight), c_f32(eps),
+                                 c_i32(x2.size(0)), c_i32(H), _stream()), "rms_norm")
+
+
+def fused_add_rms_norm(input: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, epsilon: float) -> None:
+    """cuda_ops_api.h:162-165 / norm.cu:462-515: in place on input and residual."""
+    _cuda_bf16(input, "input"); _cuda_bf16(residual, "residual"); _cuda_bf16(weight, "weight")
+    _need(input.stride(-1) == 1 and residual.is_contiguous(), "input/residual layout")
+    H = input.size(-1)
+    T = input.numel() // H
+    stride = input.stride(-2) if input.dim() >= 2 else H
+    check(lib().xb_fused_add_rms_norm_bf16(_p(input), c_i64(stride), _p(residual), _p(weight), c_f32(epsilon),
+                                           c_i32(T), c_i32(H), _stream()), "fused_add_rms_norm")
+
+
+# ---- K8 ---------------------------------------------------------------------
+def rms_norm_static_fp8_quant(out, input, weight, scale, epsilon) -> None:
+    """cuda_ops_api.h:203-209."""
+    _cuda_bf16(input, "input"); _need(out.dtype == E4M3 and out.is_contiguous(), "out must be contiguous e4m3")
+    H = input.size(-1)
+    T = input.numel() // H
+    check(lib().xb_rms_norm_static_fp8_quant_bf16(_p(out), _p(input), c_i64(input.stride(-2) if input.dim() >= 2 else H),
+                                                  _p(weight), _p(scale), c_f32(epsilon), c_i32(T), c_i32(H), _stream()),
+          "rms_norm_static_fp8_quant")
+
+
+def fused_add_rms_norm_static_fp8_quant(out, input, residual, weight, scale, epsilon) -> None:
+    """cuda_ops_api.h:214-221."""
+    _cuda_bf16(input, "input"); _cuda_bf16(residual, "residual")
+    _need(out.dtype == E4M3 and out.is_contiguous(), "out must be contiguous e4m3")
+    H = input.size(-1)
+    T = input.numel() // H
+    check(lib().xb_fused_add_rms_norm_static_fp8_quant_bf16(
+        _p(out), _p(input), c_i64(input.stride(-2) if input.dim() >= 2 else H), _p(residual), _p(weight), _p(scale),
+        c_f32(epsilon), c_i32(T), c_i32(H), _stream()), "fused_add_rms_norm_static_fp8_quant")
+
+
+# ---- K6 ---------------------------------------------------------------------
+def static_scaled_fp8_quant(out, input, scale) -> None:
+    """cuda_ops_api.h:182-186 / fp8_quant.cu:114-153."""
+    _cuda_bf16(input, "input")
+    _need(input.stride(-1) == 1, "last dimension of input must be contiguous")
+    _need(out.stride(-1) == 1, "last dimension of output must be contiguous")
+    H = input.size(-1)
+    T = input.numel() // H
+    check(lib().xb_static_scaled_fp8_quant_bf16(_p(out), c_i64(out.stride(-2) if out.dim() >= 2 else H), _p(input),
+                                                c_i64(input.stride(-2) if input.dim() >= 2 else H), _p(scale),
+                                                c_i32(T), c_i32(H), _stream()), "static_scaled_fp8_quant")
+
+
+def fp8_scaled_quantize(input, output=None, scale=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """cuda_ops_api.h:188-193 / fp8_scaled_quantize.cpp:20-48.  Dynamic scale is computed on device (no host sync)."""
+    out = output if output is not None else torch.empty_like(input, dtype=E4M3)
+    if scale is not None:
+        static_scaled_fp8_quant(out, input, scale)
+        return out, scale
+    _cuda_bf16(input, "input")
+    s = torch.empty(1, dtype=torch.float32, device=input.device)
+    H = input.size(-1)
+    T = input.numel() // H
+    check(lib().xb_dynamic_scaled_fp8_quant_bf16(_p(out), c_i64(out.stride(-2) if out.dim() >= 2 else H), _p(input),
+                                                 c_i64(input.stride(-2) if input.dim() >= 2 else H), _p(s), c_i32(T),
+                                                 c_i32(H), _stream()), "fp8_scaled_quantize")
+    return out, s
+
+
+# ---- K9 ---------------------------------------------------------------------
+def rotary_embedding(positions, query, key, cos_sin_cache, is_neox: bool) -> None:
+    """cuda_ops_api.h:31-37 / rope.cu:156-250: in place; positions int64 [T]; query [T, Hq*D] or [T, Hq, D]."""
+    _cuda_bf16(query, "query"); _cuda_bf16(cos_sin_cache, "cos_sin_cache")
+    _need(positions.dtype == torch.int64, "positions must be int64 (forward_params.h:200-206)")
+    head_size = cos_sin_cache.size(-1)
+    T = positions.numel()
+    _need(query.size(0) == T and (key is None or key.size(0) == T),
+          "query, key and positions must have the same number of tokens")
+    qh = query.numel() // T
+    kh = key.numel() // T if key is not None else 0
+    _need(qh % head_size == 0 and kh % head_size == 0, "hidden size must be a multiple of head_size")
+    nh, nkv = qh // head_size, (kh // head_size if key is not None else qh // head_size)
+    _need(nh % nkv == 0, "num_heads must be a multiple of num_kv_heads")
+    head_stride = query.stride(-2) if query.dim() == 3 else head_size
+    check(lib().xb_rotary_embedding_bf16(_p(positions), _p(query), _p(key), _p(cos_sin_cache),
+                                         c_i32(cos_sin_cache.size(1)), c_i64(query.stride(0)),
+                                         c_i64(key.stride(0) if key is not None else 0), c_i64(head_stride), c_i32(nh),
+                                         c_i32(nkv), c_i32(head_size), c_i32(1 if is_neox else 0), c_i32(T), _stream()),
+          "rotary_embedding")
+
+
+# ---- K12 --------------------------------------------------------------------
+def reshape_paged_cache(slot_ids, keys, values, key_cache, value_cache) -> None:
+    """cuda_ops_api.h:44-49 / reshape_paged_cache.cu:64-99."""
+    _cuda_bf16(keys, "keys"); _cuda_bf16(values, "values"); _cuda_bf16(key_cache, "key_cache")
+    _need(slot_ids.dtype == torch.int32, "slot_ids must be int32")
+    _need(keys.stride(-1) == 1 and keys.stride(-2) == keys.size(-1), "keys must be contiguous in (heads, dim)")
+    _need(values.stride(-1) == 1 and values.stride(-2) == values.size(-1), "values must be contiguous in (heads, dim)")
+    _need(key_cache.is_contiguous() and value_cache.is_contiguous(), "caches must be contiguous")
+    T, Hkv, D = keys.size(-3), keys.size(-2), keys.size(-1)
+    check(lib().xb_reshape_paged_cache_bf16(_p(slot_ids), _p(keys), _p(values), _p(key_cache), _p(value_cache),
+                                            c_i64(keys.stride(-3)), c_i64(values.stride(-3)), c_i32(Hkv), c_i32(D),
+                                            c_i32(key_cache.size(-3)), c_i32(T), _stream()), "reshape_paged_cache")
+
+
+def rope_and_cache(positions, query, key, value, cos_sin_cache, slot_ids, key_cache, value_cache, is_neox=True) -> None:
+    """Fused K9+K12 (one launch); bit-identical to rotary_embedding + reshape_paged_cache."""
+    _cuda_bf16(query, "query"); _cuda_bf16(key, "key"); _cuda_bf16(value, "value")
+    _need(positions.dtype == torch.int64 and slot_ids.dtype == torch.int32, "positions int64 / slot_ids int32")
+    D = key_cache.size(-1)
+    T = positions.numel()
+    nh, nkv = query.numel() // T // D, key.numel() // T // D
+    check(lib().xb_rope_and_cache_bf16(_p(positions), _p(query), _p(key), _p(value), _p(cos_sin_cache), _p(slot_ids),
+                                       _p(key_cache), _p(value_cache), c_i32(cos_sin_cache.size(1)),
+                                       c_i64(query.stride(0)), c_i64(key.stride(0)), c_i64(value.stride(0)), c_i32(nh),
+                                       c_i32(nkv), c_i32(D), c_i32(key_cache.size(-3)), c_i32(1 if is_neox else 0),
+                                       c_i32(T), _stream()), "rope_and_cache")
+
+
+# ---- K10 --------------------------------------------------------------------
+def fused_qk_norm_rope(qkv, num_heads_q, num_heads_k, num_heads_v, head_dim, eps, q_weight, k_weight, cos_sin_cache,
+                       interleaved, position_ids) -> None:
+    """cuda_ops_api.h:252-266 / fused_qknorm_rope.cu:388-471."""
+    _cuda_bf16(qkv, "qkv")
+    _need(qkv.is_contiguous(), "qkv must be contiguous")
+    _need(position_ids.dtype == torch.int64, "position_ids must be int64")
+    T = qkv.size(0)
+    check(lib().xb_fused_qk_norm_rope_bf16(_p(qkv), c_i32(num_heads_q), c_i32(num_heads_k), c_i32(num_heads_v),
+                                           c_i32(head_dim), c_f32(eps), _p(q_weight), _p(k_weight), _p(cos_sin_cache),
+                                           c_i32(cos_sin_cache.size(-1)), c_i32(1 if interleaved else 0),
+                                           _p(position_ids), c_i32(T), _stream()), "fused_qk_norm_rope")
+
+
+# ---- K11 --------------------------------------------------------------------
+_ACT = {"silu": 0, "gelu": 1, "gelu_tanh": 2, "gelu_pytorch_tanh": 2}
+
+
+def act_and_mul(out, input, act_mode: str) -> None:
+    """cuda_ops_api.h:39-42 / activation.cu:158-186."""
+    if act_mode not in _ACT:
+        raise XllmB200Error(f"Unsupported act mode: {act_mode}, only support silu, gelu, gelu_tanh, gelu_pytorch_tanh")
+    _cuda_bf16(input, "input"); _cuda_bf16(out, "out")
+    _need(input.is_contiguous() and out.is_contiguous(), "act_and_mul tensors must be contiguous")
+    d = input.size(-1) // 2
+    T = input.numel() // input.size(-1)
+    check(lib().xb_act_and_mul_bf16(_p(out), _p(input), c_i32(d), c_i32(T), c_i32(_ACT[act_mode]), _stream()),
+          "act_and_mul")
+
+
+# ---- K1: paged decode attention ------------------------------------------------
+class DecodePlan:
+    """Opaque plan (the reference deep-copies FlashInfer's plan_info: flashinfer_planinfo.cpp:37-62)."""
+
+    def __init__(self, batch, num_qo_heads, num_kv_heads, head_dim, page_size, max_pages_per_request, device,
+                 num_sms: Optional[int] = None):
+        if num_sms is None:
+            num_sms = torch.cuda.get_device_properties(device).multi_processor_count
+        self.arr = (ctypes.c_int64 * 8)()
+        check(lib().xb_decode_plan(self.arr, c_i32(batch), c_i32(num_qo_heads), c_i32(num_kv_heads), c_i32(head_dim),
+                                   c_i32(page_size), c_i32(max_pages_per_request), c_i32(num_sms)), "decode_plan")
+        self.chunk_tokens, self.max_splits = int(self.arr[0]), int(self.arr[1])
+        self.float_ws = torch.empty(int(self.arr[2]), dtype=torch.uint8, device=device)
+        self.int_ws = torch.zeros(int(self.arr[3]), dtype=torch.uint8, device=device)
+
+
+def batch_decode(plan: DecodePlan, query, k_cache, v_cache, paged_kv_indptr, paged_kv_indices,
+                 paged_kv_last_page_len, sm_scale: float, output, output_lse=None) -> None:
+    """xllm::kernel::cuda::batch_decode (cuda_ops_api.h:130-147, batch_decode.cpp:26-86), NHD layout.
+    query/output [B, Hq, D]; caches [n_blocks, block_size, Hkv, D]."""
+    _cuda_bf16(query, "query"); _cuda_bf16(k_cache, "k_cache"); _cuda_bf16(v_cache, "v_cache"); _cuda_bf16(output, "output")
+    for t, n in ((paged_kv_indptr, "paged_kv_indptr"), (paged_kv_indices, "paged_kv_indices"),
+                 (paged_kv_last_page_len, "paged_kv_last_page_len")):
+        _need(t.dtype == torch.int32 and t.is_cuda, f"{n} must be int32 on device")
+    _need(query.dim() == 3 and k_cache.dim() == 4, "query [B,Hq,D], caches [blocks,page,Hkv,D]")
+    check(lib().xb_paged_decode_bf16(plan.arr, _p(query), c_i64(query.stride(0)), c_i64(query.stride(1)), _p(k_cache),
+                                     _p(v_cache), c_i64(k_cache.stride(0)), c_i64(k_cache.stride(1)),
+                                     c_i64(k_cache.stride(2)), _p(paged_kv_indptr), _p(paged_kv_indices),
+                                     _p(paged_kv_last_page_len), _p(output), c_i64(output.stride(0)),
+                                     c_i64(output.stride(1)), _p(output_lse), c_f32(sm_scale), _p(plan.float_ws),
+                                     _p(plan.int_ws), _stream()), "batch_decode")
+
+
+# ---- linears ------------------------------------------------------------------
+def matmul_small_m(a, b, bias=None, out=None):
+    """xllm::kernel::cuda::matmul (cuda_ops_api.h:167-169, matmul.cpp:20-24) for M <= 64: a [M,K], b [N,K]."""
+    _cuda_bf16(a, "a"); _cuda_bf16(b, "b")
+    M, K = a.shape
+    N = b.size(0)
+    _need(b.is_contiguous() and a.stride(1) == 1, "a/b layout")
+    y = out if out is not None else torch.empty(M, N, dtype=BF16, device=a.device)
+    check(lib().xb_linear_bf16_small_m(_p(y), c_i64(y.stride(0)), _p(a), c_i64(a.stride(0)), _p(b), _p(bias), c_i32(M),
+                                       c_i32(N), c_i32(K), _stream()), "matmul_small_m")
+    return y
+
+
+def w4a16_linear_small_m(x, qweight, meta, group_size, bias=None, out=None):
+    """additive boundary: y = x . dequant(W)^T (+bias), M <= 64.  qweight/meta from quant.pack_w4."""
+    _cuda_bf16(x, "x")
+    _need(qweight.dtype == torch.int32 and meta.dtype == torch.int32, "qweight/meta must be int32 storage")
+    M, K = x.shape
+    N = meta.size(1)
+    y = out if out is not None else torch.empty(M, N, dtype=BF16, device=x.device)
+    check(lib().xb_linear_w4a16_small_m(_p(y), c_i64(y.stride(0)), _p(x), c_i64(x.stride(0)), _p(qweight), _p(meta),
+                                        _p(bias), c_i32(M), c_i32(N), c_i32(K), c_i32(group_size), _stream()),
+          "w4a16_linear_small_m")
+    return y
