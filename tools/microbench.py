@@ -1,0 +1,127 @@
+"""Per-kernel device timings (CUDA events, rotating buffers larger than L2 so every launch streams from HBM).
+Not the bench contract - a development aid; prints one line per kernel with achieved GB/s vs MEASURED_PEAKS."""
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from xllm_b200 import ops, quant  # noqa: E402
+
+DEV = "cuda"
+BF16 = torch.bfloat16
+PEAK = 6482.4
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+def timeit(fn, n_rot, iters=50, warm=5):
+    for i in range(warm):
+        fn(i % n_rot)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % n_rot)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us
+
+
+def timeit_graph(fn, n_rot, iters=20):
+    """all n_rot variants captured back to back in one graph: amortises launch overhead like the decode step."""
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for i in range(n_rot):
+            fn(i)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for i in range(n_rot):
+                fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters / n_rot * 1e3
+
+
+def report(name, us, nbytes, us_g=None):
+    gbs = nbytes / us / 1e3
+    extra = ""
+    if us_g is not None:
+        extra = f"  graph: {us_g:8.2f} us {nbytes / us_g / 1e3:8.1f} GB/s ({nbytes / us_g / 1e3 / PEAK:5.1%})"
+    print(f"{name:44s} {us:8.2f} us {gbs:8.1f} GB/s ({gbs / PEAK:5.1%} of measured){extra}", flush=True)
+
+
+def bench_decode(B, ctx, HQ=28, HKV=4, D=128, page=128, layers=28):
+    npg = (ctx + page - 1) // page
+    nblocks = B * npg + 1
+    caches = [(torch.randn(nblocks, page, HKV, D, device=DEV, dtype=BF16), torch.randn(nblocks, page, HKV, D, device=DEV, dtype=BF16))
+              for _ in range(layers)]
+    q = torch.randn(B, HQ, D, device=DEV, dtype=BF16)
+    out = torch.empty_like(q)
+    indptr = torch.arange(0, (B + 1) * npg, npg, dtype=torch.int32, device=DEV)
+    indices = (torch.randperm(nblocks - 1, device=DEV) + 1).to(torch.int32)
+    last = torch.full((B,), (ctx - 1) % page + 1, dtype=torch.int32, device=DEV)
+    plan = ops.DecodePlan(B, HQ, HKV, D, page, npg, DEV)
+    sc = 1 / math.sqrt(D)
+
+    def fn(i):
+        ops.batch_decode(plan, q, caches[i][0], caches[i][1], indptr, indices, last, sc, out)
+    nbytes = 2 * B * ctx * HKV * D * 2 + 2 * B * HQ * D * 2 + 4 * B * npg
+    us = timeit(fn, layers)
+    us_g = timeit_graph(fn, layers)
+    report(f"paged_decode B={B} ctx={ctx} chunk={plan.chunk_tokens} splits={plan.max_splits}", us, nbytes, us_g)
+
+
+def bench_w4(N, K, M=1, gs=128, copies=None):
+    copies = copies or max(2, int(300e6 / (N * K / 2)) + 1)
+    ws = []
+    for _ in range(copies):
+        qw = torch.randint(-2**31, 2**31 - 1, (N // 16, K // 64, 32, 4), dtype=torch.int32, device=DEV)
+        s = (torch.rand(K // gs, N, device=DEV) * 0.01 + 0.001).to(BF16).view(torch.int16).to(torch.int32) & 0xFFFF
+        meta = s | (0x4308 << 16)
+        ws.append((qw, meta.contiguous()))
+    x = torch.randn(M, K, device=DEV, dtype=BF16)
+    y = torch.empty(M, N, device=DEV, dtype=BF16)
+
+    def fn(i):
+        ops.w4a16_linear_small_m(x, ws[i][0], ws[i][1], gs, None, y)
+    nbytes = N * K // 2 + (K // gs) * N * 4 + M * K * 2 + M * N * 2
+    us = timeit(fn, copies)
+    us_g = timeit_graph(fn, copies)
+    report(f"w4a16 M={M} N={N} K={K}", us, nbytes, us_g)
+
+
+def bench_bf16(N, K, M=1):
+    copies = max(2, int(300e6 / (N * K * 2)) + 1)
+    ws = [torch.randn(N, K, device=DEV, dtype=BF16) for _ in range(copies)]
+    x = torch.randn(M, K, device=DEV, dtype=BF16)
+    y = torch.empty(M, N, device=DEV, dtype=BF16)
+
+    def fn(i):
+        ops.matmul_small_m(x, ws[i], None, y)
+    nbytes = N * K * 2 + M * K * 2 + M * N * 2
+    report(f"bf16 linear M={M} N={N} K={K}", timeit(fn, copies), nbytes, timeit_graph(fn, copies))
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0), "peak", PEAK)
+    bench_decode(1, 4096)
+    bench_decode(8, 4096)
+    bench_decode(64, 4096)
+    for N, K in [(4608, 3584), (3584, 3584), (37888, 3584), (3584, 18944)]:
+        bench_w4(N, K, 1)
+    bench_w4(37888, 3584, 8)
+    bench_w4(37888, 3584, 64)
+    bench_bf16(152064, 3584, 1)
+    bench_bf16(4608, 3584, 1)
