@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/s of the Qwen2-7B W4A16 hot path at ctx 4096 (BASELINE.json configs[1]).
+
+A "step" is one decode step of the whole Qwen2-7B stack (28 layers: RMSNorm, W4A16 qkv, RoPE+KV scatter, paged
+decode attention over 4096 cached tokens, W4A16 o_proj, RMSNorm, W4A16 gate_up, SiLU*mul, W4A16 down; final norm,
+bf16 lm_head, greedy argmax) for batch 1, replayed as one CUDA graph of libxllm_b200_ops launches.
+Synthetic data: random-init weights of the named architecture, KV cache N(0,1) with a random page permutation.
+
+  value   tokens/s with the step inputs resident in HBM (device events around K replays)
+  e2e     tokens/s through Qwen2DecodeRunner.step(): pinned-host step inputs -> H2D -> graph -> D2H token ids
+  roofline  dominant kernel (W4A16 gate_up_proj GEMV, 28 launches/step): algorithmic bytes / launch duration
+            measured with CUDA events around each launch in an instrumented pass of the same step
+  cpu_baseline  the oracle's restatement of one decoder layer (+ lm_head) on the host cores, bounded sample
+
+N > 1 (torchrun): data-parallel replicas of the same step (the path shards per request: "weak" scaling, no data-path
+collective); value = sum of tokens over ranks / max time over ranks.
+`--impl reference` times the oracle port on the host cores (the reference has no CPU build and cannot be installed
+offline: see DESIGN.md) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "decode_tokens_per_s"
+UNIT = "tokens/s"
+CTX = 4096
+WORKLOAD = "Qwen2-7B W4A16 (group 128), batch=1, ctx=4096, decode-only PagedAttention, 1xB200 per replica"
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_layer_baseline(threads=None, budget_s=20.0):
+    """The oracle port of one Qwen2-7B decoder layer (decode, batch 1, ctx 4096) + lm_head on the host cores.
+    Weights are kept as fp32 copies of bf16-representable values so the timed region is the layer math, not dtype
+    conversion.  Returns (tokens/s extrapolated to 28 layers + lm_head, description)."""
+    import torch
+    from oracle import layer as OL
+    from oracle import ops as O
+    from xllm_b200.qwen2 import Qwen2Config
+    cfg = Qwen2Config.qwen2_7b()
+    threads = threads or len(os.sched_getaffinity(0))
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(2026)
+    H, I, bs = cfg.hidden_size, cfg.intermediate_size, cfg.block_size
+    BF16 = torch.bfloat16
+
+    def w(n, k):
+        return (torch.randn(n, k, generator=g) * 0.02).to(BF16).to(torch.float32)   # dequantised W4 weights live as values
+    qkv_w, o_w, gu_w, dn_w = w(cfg.q_size + 2 * cfg.kv_size, H), w(H, cfg.q_size), w(2 * I, H), w(H, I)
+    qkv_b = (torch.randn(cfg.q_size + 2 * cfg.kv_size, generator=g) * 0.02).to(BF16)
+    npg = CTX // bs
+    kc = torch.randn(npg + 1, bs, cfg.n_kv_heads, cfg.head_dim, generator=g).to(BF16)
+    vc = torch.randn(npg + 1, bs, cfg.n_kv_heads, cfg.head_dim, generator=g).to(BF16)
+    cs = O.compute_cos_sin_cache(cfg.head_dim, 8192, cfg.rope_theta, BF16)
+    lin = lambda x, ww, b=None: O.linear(x, ww, b)
+    attn = OL.Qwen2AttentionOracle(qkv_w, qkv_b, o_w, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cs, linear=lin)
+    ones = torch.ones(H, dtype=BF16)
+    dl = OL.Qwen2DecoderLayerOracle(attn, ones, ones, cfg.rms_norm_eps, lambda h: O.linear(h, gu_w), lambda h: O.linear(h, dn_w))
+    indices = (torch.randperm(npg, generator=g) + 1).to(torch.int32)
+    slot = int(indices[-1]) * bs + (CTX - 1) % bs
+    meta = OL.AttnMeta(False, False, torch.tensor([0, 1], dtype=torch.int32), None, torch.tensor([slot], dtype=torch.int32),
+                       torch.tensor([0, npg], dtype=torch.int32), indices, torch.tensor([(CTX - 1) % bs + 1], dtype=torch.int32))
+    x = torch.randn(1, H, generator=g).to(BF16)
+    res = torch.randn(1, H, generator=g).to(BF16)
+    pos = torch.tensor([CTX - 1])
+    dl.forward(x, res, pos, meta, kc, vc)                      # warm-up
+    t0, n = time.perf_counter(), 0
+    while True:
+        dl.forward(x, res, pos, meta, kc, vc)
+        n += 1
+        if time.perf_counter() - t0 > budget_s * 0.7 or n >= 50:
+            break
+    t_layer = (time.perf_counter() - t0) / n
+    head_rows = 19008                                          # 1/8 of the vocabulary rows, scaled up
+    head = w(head_rows, H)
+    O.linear(x, head)
+    t1, m = time.perf_counter(), 0
+    while True:
+        O.linear(x, head)
+        m += 1
+        if time.perf_counter() - t1 > budget_s * 0.2 or m >= 20:
+            break
+    t_head = (time.perf_counter() - t1) / m * (cfg.vocab_size / head_rows)
+    step_s = cfg.num_layers * t_layer + t_head
+    sample = (f"{n} passes of one Qwen2-7B decoder layer (decode, batch 1, ctx {CTX}, dequantised fp32-held weights) "
+              f"+ {m} passes over 1/8 of lm_head, extrapolated to {cfg.num_layers} layers + full lm_head")
+    return 1.0 / step_s, step_s, threads, sample
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    tps, step_s, threads, sample = cpu_layer_baseline(budget_s=min(60.0, 6.0 * max(1, args.steps)))
+    line = {"metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD, "ctx": CTX, "batch": 1},
+            "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference has no CPU build (xllm/models/models.h:119-121 #error) and cannot be installed offline; "
+                    "this arm times the oracle port of the same decoder layer on the host cores"}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ctx", type=int, default=CTX)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from xllm_b200 import _lib
+    from xllm_b200.qwen2 import Qwen2Config, Qwen2DecodeRunner, Qwen2Weights
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    _lib.lib()                      # fail loudly if the CUDA library is missing: no fallback
+    peak_gbs, peak_src = load_peaks()
+
+    cfg = Qwen2Config.qwen2_7b()
+    ctx = args.ctx
+    weights = Qwen2Weights.synthetic(cfg, dev, seed=2026 + rank)
+    runner = Qwen2DecodeRunner(cfg, weights, max_batch=1, max_ctx=ctx, device=dev)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    for li in range(cfg.num_layers):
+        runner.k_caches[li].normal_(generator=g)
+        runner.v_caches[li].normal_(generator=g)
+    bs = cfg.block_size
+    npg = (ctx + bs - 1) // bs
+    pages = (torch.randperm(runner.num_blocks - 1, generator=torch.Generator().manual_seed(2026)) + 1)[:npg].tolist()
+    pos = ctx - 1
+    slot = pages[pos // bs] * bs + pos % bs
+    tok = 1234
+    runner.set_inputs_host([tok], [pos], [slot], [0, npg], pages, [(ctx - 1) % bs + 1])
+    runner.step()                   # eager pass (module load, attribute setup)
+    runner.capture()
+    launches_per_step = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timed region ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        runner.run_device_only()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        runner.run_device_only()
+        runner.token_ids.copy_(runner.next_tokens)        # greedy feedback keeps the data dependency real (device op)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    graph_launches = 0
+    # a graph replay does not pass through the library's launch counter: count the kernels in one step eagerly
+    n0 = _lib.launch_count()
+    runner.launch_step()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - n0
+
+    # ---- end-to-end region (host buffers, H2D + D2H inside) -----------------------------------------------------
+    for _ in range(3):
+        runner.step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = runner.step()
+        runner.h_token_ids[0] = int(out[0]) % cfg.vocab_size
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- dominant kernel: W4A16 gate_up GEMV, CUDA events around each launch -----------------------------------
+    gu_events = []
+    L = weights.layers
+    for rep in range(3):
+        for li in range(cfg.num_layers):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            L[li]["gate_up"].forward(runner.buf_a, runner.gate_up)
+            b.record()
+            if rep > 0:
+                gu_events.append((a, b))
+    torch.cuda.synchronize()
+    gu_us = sorted(a.elapsed_time(b) * 1e3 for a, b in gu_events)
+    gu_us_avg = sum(gu_us) / len(gu_us)
+    gu = L[0]["gate_up"]
+    gu_bytes = gu.qweight.numel() * 4 + gu.meta.numel() * 4 + gu.K * 2 + gu.N * 2
+    # attention kernel the same way (the north-star names it)
+    at_events = []
+    q3 = runner.qkv[:, :cfg.q_size].view(-1, cfg.n_heads, cfg.head_dim)
+    from xllm_b200 import ops
+    for rep in range(3):
+        for li in range(cfg.num_layers):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.batch_decode(runner.plan, q3, runner.k_caches[li], runner.v_caches[li], runner.kv_indptr, runner.kv_indices,
+                             runner.kv_last, cfg.head_dim ** -0.5, runner.attn_out.view(-1, cfg.n_heads, cfg.head_dim))
+            b.record()
+            if rep > 0:
+                at_events.append((a, b))
+    torch.cuda.synchronize()
+    at_us_avg = sum(a.elapsed_time(b) * 1e3 for a, b in at_events) / len(at_events)
+    at_bytes = 2 * ctx * cfg.n_kv_heads * cfg.head_dim * 2 + 2 * cfg.n_heads * cfg.head_dim * 2 + 4 * npg
+
+    # ---- reduce over ranks ----------------------------------------------------------------------------------------
+    t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    total_tokens = args.steps * world
+    value = total_tokens / (ms / 1e3)
+    e2e_value = total_tokens / (e2e_ms / 1e3)
+    step_bytes = weights.weight_bytes() + cfg.num_layers * at_bytes
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            tps, step_s, threads, sample = cpu_layer_baseline(budget_s=15.0)
+            cpu = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        ach = gu_bytes / gu_us_avg / 1e3
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "ctx": ctx, "batch": 1, "parallelism": f"dp{world}",
+                       "l2": "inputs larger than L2: each step streams %.2f GB of weights+KV" % (step_bytes / 1e9),
+                       "decode_chunk_tokens": runner.plan.chunk_tokens, "decode_splits": runner.plan.max_splits},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
+                    "d2h_bytes_per_step": runner.d2h_bytes},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "linear_w4a16_small_m_kernel (gate_up_proj 37888x3584, 28 launches/step)",
+                         "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None,
+                         "peak_source": peak_src, "launch_us": gu_us_avg, "bytes_per_launch": gu_bytes,
+                         "step": {"bytes": step_bytes, "achieved": step_bytes / (ms / args.steps) / 1e6,
+                                  "frac": step_bytes / (ms / args.steps) / 1e6 / peak_gbs},
+                         "paged_decode": {"bytes_per_launch": at_bytes, "launch_us": at_us_avg,
+                                          "achieved": at_bytes / at_us_avg / 1e3, "frac": at_bytes / at_us_avg / 1e3 / peak_gbs}},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

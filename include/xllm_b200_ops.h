@@ -194,6 +194,14 @@ int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
 /* host-side packer (plain C, no CUDA): q[N,K] uint8 (0..15) -> qweight tiles. */
 int xb_w4_pack_rows(uint32_t* qweight_out, const uint8_t* q, int N, int K);
 
+/* ---- step boundary helpers ---------------------------------------------------
+ * embedding row gather (WordEmbeddingImpl::forward, layers/common/word_embedding_impl.cpp:33-56,
+ * TP=1) and greedy argmax over logits rows (ties -> lowest index). */
+int xb_embedding_bf16(void* out, const int32_t* token_ids, const void* table,
+                      int num_tokens, int hidden, int vocab, xb_stream_t stream);
+int xb_argmax_bf16(int32_t* out, const void* logits, int64_t stride, int rows,
+                   int vocab, xb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

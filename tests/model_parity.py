@@ -1,0 +1,122 @@
+"""Whole-decode-step parity: Qwen2DecodeRunner (CUDA, through the C ABI) vs the oracle composition.
+Used by tests/test_gpu_model.py and by __graft_entry__.smoke()."""
+import math
+
+import torch
+
+from oracle import layer as OL
+from oracle import ops as O
+from oracle import quant as OQ
+
+BF16 = torch.bfloat16
+
+
+def build_case(cfg, B, kv_lens, seed=2026):
+    """logical weights (CPU, oracle quantiser) + prefilled KV caches + step metadata."""
+    g = torch.Generator().manual_seed(seed)
+    H, I = cfg.hidden_size, cfg.intermediate_size
+
+    def lin(n, k, bias=False):
+        w = (torch.randn(n, k, generator=g) * 0.05).to(BF16)
+        b = (torch.randn(n, generator=g) * 0.05).to(BF16) if bias else None
+        if cfg.quant == "bf16":
+            return dict(w=w, b=b)
+        q, s, z = OQ.quantize(w, 4, cfg.group_size)
+        return dict(q=q, s=s, z=z, b=b, w=OQ.dequantize(q, s, z, cfg.group_size))
+
+    W = dict(embed=(torch.randn(cfg.vocab_size, H, generator=g) * 0.5).to(BF16),
+             final_norm=(1 + 0.1 * torch.randn(H, generator=g)).to(BF16), layers=[])
+    W["lm_head"] = W["embed"] if cfg.tie_word_embeddings else (torch.randn(cfg.vocab_size, H, generator=g) * 0.05).to(BF16)
+    for _ in range(cfg.num_layers):
+        W["layers"].append(dict(input_norm=(1 + 0.1 * torch.randn(H, generator=g)).to(BF16),
+                                post_norm=(1 + 0.1 * torch.randn(H, generator=g)).to(BF16),
+                                qkv=lin(cfg.q_size + 2 * cfg.kv_size, H, True), o=lin(H, cfg.q_size),
+                                gate_up=lin(2 * I, H), down=lin(H, I)))
+    bs = cfg.block_size
+    npg = [(n + bs - 1) // bs for n in kv_lens]
+    nblocks = sum(npg) + 3
+    perm = (torch.randperm(nblocks - 1, generator=g) + 1)[:sum(npg)].to(torch.int32)
+    indptr = [0]
+    for n in npg:
+        indptr.append(indptr[-1] + n)
+    last = [(n - 1) % bs + 1 for n in kv_lens]
+    # the new token sits at position kv_len-1; its slot follows sequence_kv_state.cpp:96-101
+    slots = [int(perm[indptr[b] + (kv_lens[b] - 1) // bs]) * bs + (kv_lens[b] - 1) % bs for b in range(B)]
+    kcs = [torch.randn(nblocks, bs, cfg.n_kv_heads, cfg.head_dim, generator=g).to(BF16) for _ in range(cfg.num_layers)]
+    vcs = [torch.randn(nblocks, bs, cfg.n_kv_heads, cfg.head_dim, generator=g).to(BF16) for _ in range(cfg.num_layers)]
+    tokens = torch.randint(0, cfg.vocab_size, (B,), generator=g).tolist()
+    meta = dict(tokens=tokens, positions=[n - 1 for n in kv_lens], slots=slots, indptr=indptr, indices=perm.tolist(),
+                last=last, nblocks=nblocks)
+    return W, kcs, vcs, meta
+
+
+def oracle_step(cfg, W, kcs, vcs, meta):
+    """reference composition on CPU: returns (logits bf16 [B, vocab], next tokens)."""
+    B = len(meta["tokens"])
+    cs = O.compute_cos_sin_cache(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, BF16)
+    positions = torch.tensor(meta["positions"])
+    am = OL.AttnMeta(False, False, torch.arange(B + 1, dtype=torch.int32), None, torch.tensor(meta["slots"], dtype=torch.int32),
+                     torch.tensor(meta["indptr"], dtype=torch.int32), torch.tensor(meta["indices"], dtype=torch.int32),
+                     torch.tensor(meta["last"], dtype=torch.int32))
+    x = W["embed"][torch.tensor(meta["tokens"])]
+    residual = None
+    for li, L in enumerate(W["layers"]):
+        attn = OL.Qwen2AttentionOracle(L["qkv"]["w"], L["qkv"]["b"], L["o"]["w"], cfg.n_heads, cfg.n_kv_heads,
+                                       cfg.head_dim, cs)
+        dl = OL.Qwen2DecoderLayerOracle(attn, L["input_norm"], L["post_norm"], cfg.rms_norm_eps,
+                                        lambda h, L=L: O.linear(h, L["gate_up"]["w"]),
+                                        lambda h, L=L: O.linear(h, L["down"]["w"]))
+        x, residual = dl.forward(x, residual, positions, am, kcs[li], vcs[li])
+    x, _ = O.fused_add_rms_norm(x, residual, W["final_norm"], cfg.rms_norm_eps)
+    logits = O.linear(x, W["lm_head"])
+    return logits, logits.to(torch.float32).argmax(-1)
+
+
+def upload(cfg, W, device="cuda"):
+    from xllm_b200 import quant
+    from xllm_b200.qwen2 import Linear, Qwen2Weights
+    w = Qwen2Weights(cfg)
+    w.embed = W["embed"].to(device)
+    w.final_norm = W["final_norm"].to(device)
+    w.lm_head = Linear(cfg.vocab_size, cfg.hidden_size, "bf16")
+    w.lm_head.weight = w.embed if cfg.tie_word_embeddings else W["lm_head"].to(device)
+
+    def mk(d, n, k):
+        l = Linear(n, k, cfg.quant, cfg.group_size)
+        if cfg.quant == "bf16":
+            l.weight = d["w"].to(device)
+        else:
+            qw, meta = quant.pack_w4(d["q"], d["s"], d["z"], cfg.group_size)
+            l.qweight, l.meta = qw.to(device), meta.to(device)
+        l.bias = d["b"].to(device) if d["b"] is not None else None
+        return l
+    H, I = cfg.hidden_size, cfg.intermediate_size
+    for L in W["layers"]:
+        w.layers.append(dict(input_norm=L["input_norm"].to(device), post_norm=L["post_norm"].to(device),
+                             qkv=mk(L["qkv"], cfg.q_size + 2 * cfg.kv_size, H), o=mk(L["o"], H, cfg.q_size),
+                             gate_up=mk(L["gate_up"], 2 * I, H), down=mk(L["down"], H, I)))
+    return w
+
+
+def run_decode_parity(cfg, kv_lens, use_graph=True, fused=True, seed=2026):
+    """returns (max bf16-ulp distance of logits, tokens equal?)."""
+    from xllm_b200.qwen2 import Qwen2DecodeRunner
+    B = len(kv_lens)
+    W, kcs, vcs, meta = build_case(cfg, B, kv_lens, seed)
+    runner = Qwen2DecodeRunner(cfg, upload(cfg, W), B, max(kv_lens), num_blocks=meta["nblocks"], fused_rope_cache=fused)
+    for li in range(cfg.num_layers):
+        runner.k_caches[li].copy_(kcs[li])
+        runner.v_caches[li].copy_(vcs[li])
+    runner.set_inputs_host(meta["tokens"], meta["positions"], meta["slots"], meta["indptr"], meta["indices"], meta["last"])
+    if use_graph:
+        runner.step()            # eager once (module load), then capture
+        for li in range(cfg.num_layers):
+            runner.k_caches[li].copy_(kcs[li])
+            runner.v_caches[li].copy_(vcs[li])
+        runner.capture()
+    nxt = runner.step().clone()
+    logits = runner.logits.cpu()
+    ref_logits, ref_next = oracle_step(cfg, W, kcs, vcs, meta)
+    # KV caches after the step: the new token's rotated K and V must have been scattered bit-exactly
+    # (same qkv GEMM inputs -> within tolerance; compare the untouched part exactly)
+    return logits, ref_logits, nxt, ref_next, runner, (kcs, vcs)

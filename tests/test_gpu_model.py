@@ -1,0 +1,39 @@
+"""GPU parity: a whole decode step of the Qwen2 stack (CUDA graph of C-ABI launches) vs the oracle composition."""
+import pytest
+import torch
+
+from tests.model_parity import run_decode_parity
+from tests.util import assert_close_bf16
+
+pytestmark = pytest.mark.gpu
+
+
+def _small(quant):
+    from xllm_b200.qwen2 import Qwen2Config
+    return Qwen2Config(hidden_size=256, num_layers=3, n_heads=8, n_kv_heads=2, head_dim=64, intermediate_size=512,
+                       vocab_size=1024, block_size=16, quant=quant, group_size=64, max_position_embeddings=2048,
+                       name="tiny")
+
+
+@pytest.mark.parametrize("quant", ["w4a16", "bf16"])
+@pytest.mark.parametrize("use_graph,fused", [(True, True), (False, False)])
+def test_decode_step_matches_oracle(quant, use_graph, fused, built_lib):
+    cfg = _small(quant)
+    logits, ref_logits, nxt, ref_next, runner, (kcs, vcs) = run_decode_parity(cfg, [37, 300, 1], use_graph, fused)
+    # logits: within 1e-3 relative L2 (north_star) and a few bf16 ulps elementwise (3 layers of bf16 roundings
+    # downstream of 1-ulp flips in the intermediate activations)
+    assert_close_bf16(logits, ref_logits, ulps=4, rel_l2=1e-3 * 4, what="decode-step logits")
+    assert torch.equal(nxt.long().cpu()[:3], ref_next), "greedy tokens differ"
+    # cache rows of old tokens untouched bit-exactly; new rows within 1 ulp of the oracle's
+    for li in range(cfg.num_layers):
+        assert_close_bf16(runner.k_caches[li], kcs[li], ulps=2, rel_l2=1e-3, what=f"k_cache[{li}]")
+        assert_close_bf16(runner.v_caches[li], vcs[li], ulps=2, rel_l2=1e-3, what=f"v_cache[{li}]")
+
+
+def test_decode_step_qwen2_0_5b_shape(built_lib):
+    """BASELINE configs[0] architecture (Qwen2-0.5B bf16, batch 1, ctx 128) with 2 layers to keep the oracle fast."""
+    from xllm_b200.qwen2 import Qwen2Config
+    cfg = Qwen2Config.qwen2_0_5b(num_layers=2, vocab_size=8192, block_size=128, max_position_embeddings=4096)
+    logits, ref_logits, nxt, ref_next, _, _ = run_decode_parity(cfg, [128], True, True)
+    assert_close_bf16(logits, ref_logits, ulps=4, rel_l2=4e-3, what="qwen2-0.5b-shape logits")
+    assert torch.equal(nxt.long().cpu()[:1], ref_next)

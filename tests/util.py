@@ -6,6 +6,14 @@ kernel is compared with the oracle (north_star: "within 1e-3 relative for bf16/F
   * relative L2 error over the tensor   <= 1e-3
   * every element within `ulps` bf16 ulps of the oracle (default 1; accumulation-order noise)
 Integer / copy / index work is compared with torch.equal (bit-exact).
+
+Attention: the reference ladder (FlashInfer) rounds the softmax numerators P to bf16 before the PV tensor-core
+product, relative to whatever running maximum the tile order produced, so two correct implementations with a
+different tile / split order differ by independent 2^-9-relative perturbations of every p_j.  For
+o_d = sum_j p_j v_jd that is a forward error of up to ~1e-3 * sum_j p_j |v_jd| - NOT 1e-3 * |o_d|, which on the
+synthetic N(0,1) KV of SURVEY 8d is ~sqrt(kv_len) smaller because of cancellation.  `assert_close_attention`
+therefore states "1e-3 relative" in the standard dot-product sense: |err_d| <= 1e-3 * sum_j p_j |v_jd| + 1 bf16 ulp,
+with the scale sum_j p_j |v_jd| computed by the oracle itself (same attention with |V|).
 """
 import torch
 
@@ -29,3 +37,17 @@ def assert_close_bf16(got: torch.Tensor, ref: torch.Tensor, ulps: float = 1.0, r
     assert not bad.any(), (f"{what}: {int(bad.sum())} / {bad.numel()} elements beyond {ulps} bf16 ulp; "
                            f"worst |err|={err.max().item():.3e} at ref={r.flatten()[err.argmax()].item():.4e}")
     return l2
+
+
+def assert_close_attention(got, ref, abs_scale, rtol: float = 1e-3, what: str = ""):
+    """|got - ref| <= rtol * (sum_j p_j |v_j|) + 1 bf16 ulp(ref), elementwise (see module docstring)."""
+    g, r = got.detach().cpu().to(torch.float32), ref.detach().cpu().to(torch.float32)
+    sc = abs_scale.detach().cpu().to(torch.float32)
+    assert g.shape == r.shape == sc.shape, f"{what}: shapes {g.shape} {r.shape} {sc.shape}"
+    assert torch.isfinite(g).all(), f"{what}: non-finite output"
+    err = (g - r).abs()
+    bound = rtol * sc + torch.maximum(bf16_ulp(r), bf16_ulp(g))
+    bad = err > bound
+    assert not bad.any(), (f"{what}: {int(bad.sum())} / {bad.numel()} elements beyond {rtol:.0e} * sum p|v| + 1 ulp; "
+                           f"worst err/bound = {(err / bound).max().item():.2f}")
+    return (err / sc.clamp_min(1e-30)).max().item()

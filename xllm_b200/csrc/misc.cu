@@ -1,0 +1,92 @@
+// Step-boundary helpers of the decode path: embedding row gather
+// (WordEmbeddingImpl::forward, xllm/core/layers/common/word_embedding_impl.cpp:33-56, TP=1 slice)
+// and greedy argmax over the logits (the sampler's greedy branch).  Both are tiny and
+// exist so that a whole decode step is made of this library's launches only.
+#include "common.cuh"
+
+namespace xb {
+
+__global__ void __launch_bounds__(256)
+embedding_kernel(__nv_bfloat16* __restrict__ out, const int32_t* __restrict__ token_ids,
+                 const __nv_bfloat16* __restrict__ table, int hidden, int vocab) {
+  pdl_wait();
+  const int64_t tok = blockIdx.x;
+  int id = token_ids[tok];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const uint4* src = reinterpret_cast<const uint4*>(table + (int64_t)id * hidden);
+  uint4* dst = reinterpret_cast<uint4*>(out + tok * hidden);
+  for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+  pdl_launch_dependents();
+}
+
+// argmax over each row of logits[M, vocab] (bf16); ties -> lowest index (torch.argmax semantics on CUDA
+// are unspecified for ties; lowest index is what the CPU oracle's torch.argmax returns).
+__global__ void __launch_bounds__(1024)
+argmax_kernel(int32_t* __restrict__ out, const __nv_bfloat16* __restrict__ logits, int64_t stride, int vocab) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  pdl_wait();
+  const __nv_bfloat16* row = logits + (int64_t)blockIdx.x * stride;
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  const int nvec = vocab / 8;
+  const uint4* rv = reinterpret_cast<const uint4*>(row);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 v = rv[i];
+    const uint32_t* p = &v.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = bf16lo(p[j]), b = bf16hi(p[j]);
+      int ia = i * 8 + 2 * j, ib = ia + 1;
+      if (a > best || (a == best && ia < besti)) { best = a; besti = ia; }
+      if (b > best || (b == best && ib < besti)) { best = b; besti = ib; }
+    }
+  }
+  for (int i = nvec * 8 + threadIdx.x; i < vocab; i += blockDim.x) {
+    float a = __bfloat162float(row[i]);
+    if (a > best || (a == best && i < besti)) { best = a; besti = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = besti; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -INFINITY;
+    besti = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = besti;
+  }
+  pdl_launch_dependents();
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" int xb_embedding_bf16(void* out, const int32_t* token_ids, const void* table, int num_tokens, int hidden,
+                                 int vocab, xb_stream_t stream) {
+  if (num_tokens == 0) return 0;
+  XB_CHECK(hidden % 8 == 0, "embedding: hidden %d must be a multiple of 8", hidden);
+  XB_CUDA_OK(launch(embedding_kernel, dim3(num_tokens), dim3(256), 0, (cudaStream_t)stream, true,
+                    reinterpret_cast<__nv_bfloat16*>(out), token_ids, reinterpret_cast<const __nv_bfloat16*>(table),
+                    hidden, vocab));
+  return 0;
+}
+
+extern "C" int xb_argmax_bf16(int32_t* out, const void* logits, int64_t stride, int rows, int vocab,
+                              xb_stream_t stream) {
+  if (rows == 0) return 0;
+  XB_CHECK(stride % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0, "argmax: logits must be 16B aligned");
+  XB_CUDA_OK(launch(argmax_kernel, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, true, out,
+                    reinterpret_cast<const __nv_bfloat16*>(logits), stride, vocab));
+  return 0;
+}

@@ -245,3 +245,20 @@ def w4a16_linear_small_m(x, qweight, meta, group_size, bias=None, out=None):
                                         _p(bias), c_i32(M), c_i32(N), c_i32(K), c_i32(group_size), _stream()),
           "w4a16_linear_small_m")
     return y
+
+
+# ---- step boundary -------------------------------------------------------------
+def embedding(out, token_ids, table) -> None:
+    """WordEmbeddingImpl::forward (word_embedding_impl.cpp:33-56), TP=1."""
+    _cuda_bf16(table, "table"); _cuda_bf16(out, "out")
+    _need(token_ids.dtype == torch.int32, "token_ids must be int32")
+    check(lib().xb_embedding_bf16(_p(out), _p(token_ids), _p(table), c_i32(token_ids.numel()), c_i32(table.size(1)),
+                                  c_i32(table.size(0)), _stream()), "embedding")
+
+
+def argmax(out, logits) -> None:
+    """greedy sampling: out int32 [rows]."""
+    _cuda_bf16(logits, "logits")
+    _need(out.dtype == torch.int32, "out must be int32")
+    check(lib().xb_argmax_bf16(_p(out), _p(logits), c_i64(logits.stride(0)), c_i32(logits.size(0)),
+                               c_i32(logits.size(1)), _stream()), "argmax")

@@ -1,0 +1,282 @@
+"""Decode-step driver for the Qwen2 decoder stack on top of the C-ABI ops.
+
+Mirrors the reference composition (call stack B of SURVEY.md section 3):
+  LlmModelImplBase::forward            xllm/models/llm/llm_model_base.h:60-131
+  Qwen2DecoderLayerImpl::forward       xllm/core/layers/qwen2_decoder_layer.cpp:89-112
+  Qwen2AttentionImpl::forward          xllm/core/layers/common/qwen2_attention.cpp:132-193
+  DenseMLPImpl::forward                xllm/core/layers/common/dense_mlp.cpp:97-118
+with the per-layer launches of this library.  One decode step = one replay of
+a CUDA graph made only of libxllm_b200_ops launches chained with PDL.
+The integer inputs of a step (token ids, positions, new_cache_slots, the paged
+triplet) are exactly the reference's ForwardInput integers
+(batch_input_builder.cpp:739-831) and are copied from pinned host memory.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import ops, quant
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class Qwen2Config:
+    hidden_size: int = 3584
+    num_layers: int = 28
+    n_heads: int = 28
+    n_kv_heads: int = 4
+    head_dim: int = 128
+    intermediate_size: int = 18944
+    vocab_size: int = 152064
+    rope_theta: float = 1000000.0
+    rms_norm_eps: float = 1e-6
+    max_position_embeddings: int = 32768
+    block_size: int = 128                 # kv_cache_config.cpp:21
+    quant: str = "w4a16"                  # "w4a16" | "bf16"
+    group_size: int = 128
+    tie_word_embeddings: bool = False
+    name: str = "Qwen2-7B"
+
+    @staticmethod
+    def qwen2_7b(**kw):
+        return Qwen2Config(**kw)
+
+    @staticmethod
+    def qwen2_0_5b(**kw):
+        d = dict(hidden_size=896, num_layers=24, n_heads=14, n_kv_heads=2, head_dim=64, intermediate_size=4864,
+                 vocab_size=151936, quant="bf16", tie_word_embeddings=True, name="Qwen2-0.5B")
+        d.update(kw)
+        return Qwen2Config(**d)
+
+    @property
+    def q_size(self):
+        return self.n_heads * self.head_dim
+
+    @property
+    def kv_size(self):
+        return self.n_kv_heads * self.head_dim
+
+
+class Linear:
+    """One of qkv_proj / o_proj / gate_up_proj / down_proj / lm_head: y = x W^T (+b)."""
+
+    def __init__(self, out_features, in_features, kind, group_size=128):
+        self.N, self.K, self.kind, self.group_size = out_features, in_features, kind, group_size
+        self.weight = None      # bf16 [N,K]
+        self.qweight = None     # int32 tiles
+        self.meta = None        # int32 [K/g, N]
+        self.bias = None
+
+    def weight_bytes(self):
+        if self.kind == "bf16":
+            return self.weight.numel() * 2
+        return self.qweight.numel() * 4 + self.meta.numel() * 4
+
+    def forward(self, x, out):
+        M = x.size(0)
+        if M > 64:
+            raise NotImplementedError("M > 64 routes to the tcgen05 GEMM (xllm_b200.ops.gemm_*)")
+        if self.kind == "bf16":
+            ops.matmul_small_m(x, self.weight, self.bias, out)
+        else:
+            ops.w4a16_linear_small_m(x, self.qweight, self.meta, self.group_size, self.bias, out)
+        return out
+
+
+class Qwen2Weights:
+    def __init__(self, cfg: Qwen2Config):
+        self.cfg = cfg
+        self.embed = None
+        self.lm_head: Optional[Linear] = None
+        self.final_norm = None
+        self.layers: List[dict] = []
+
+    @staticmethod
+    def _synthetic_linear(N, K, kind, gs, gen, device, bias=False, std=0.02):
+        lin = Linear(N, K, kind, gs)
+        if kind == "bf16":
+            lin.weight = (torch.randn(N, K, generator=gen, device=device) * std).to(BF16)
+        else:
+            # uniform nibbles + scales such that w ~ N(0, std^2)-like spread; generated directly in packed form
+            lin.qweight = torch.randint(-2 ** 31, 2 ** 31 - 1, (N // 16, K // 64, 32, 4), generator=gen, device=device,
+                                        dtype=torch.int32)
+            s = (torch.rand(K // gs, N, generator=gen, device=device) * 0.5 + 0.75) * (std * 3.0 / 7.5)
+            z = torch.randint(6, 10, (K // gs, N), generator=gen, device=device)
+            s_bits = s.to(BF16).view(torch.int16).to(torch.int32) & 0xFFFF
+            z_bits = (z.float() + 128.0).to(BF16).view(torch.int16).to(torch.int32) & 0xFFFF
+            lin.meta = (s_bits | (z_bits << 16)).contiguous()
+        if bias:
+            lin.bias = (torch.randn(N, generator=gen, device=device) * std).to(BF16)
+        return lin
+
+    @staticmethod
+    def synthetic(cfg: Qwen2Config, device="cuda", seed=2026):
+        """random-init weights of the named architecture (no checkpoints offline), generated on device."""
+        g = torch.Generator(device=device).manual_seed(seed)
+        w = Qwen2Weights(cfg)
+        H, I = cfg.hidden_size, cfg.intermediate_size
+        w.embed = (torch.randn(cfg.vocab_size, H, generator=g, device=device) * 0.02).to(BF16)
+        w.final_norm = (1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16)
+        w.lm_head = Linear(cfg.vocab_size, H, "bf16")       # lm_head stays unquantised (linear.cpp:512-520)
+        w.lm_head.weight = w.embed if cfg.tie_word_embeddings else \
+            (torch.randn(cfg.vocab_size, H, generator=g, device=device) * 0.02).to(BF16)
+        for _ in range(cfg.num_layers):
+            mk = lambda n, k, b=False: Qwen2Weights._synthetic_linear(n, k, cfg.quant, cfg.group_size, g, device, b)
+            w.layers.append(dict(
+                input_norm=(1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16),
+                post_norm=(1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16),
+                qkv=mk(cfg.q_size + 2 * cfg.kv_size, H, True), o=mk(H, cfg.q_size),
+                gate_up=mk(2 * I, H), down=mk(H, I)))
+        return w
+
+    def weight_bytes(self):
+        n = self.lm_head.weight_bytes()
+        for l in self.layers:
+            n += sum(l[k].weight_bytes() for k in ("qkv", "o", "gate_up", "down"))
+        return n
+
+
+def make_cos_sin_cache(cfg: Qwen2Config, device):
+    """[max_pos, head_dim] = [cos_half | sin_half] in bf16 - the pre-sliced layout the CUDA kernel reads
+    (rotary_embedding.cpp:31-52, rotary_embedding_util.cpp:115-144,303-310; rope_theta passes through int64)."""
+    rot = cfg.head_dim
+    sl = torch.arange(0, rot, 2, dtype=torch.float32)
+    inv_freq = 1.0 / torch.pow(torch.tensor(float(int(cfg.rope_theta)), dtype=torch.float32), sl / float(rot))
+    t = torch.arange(cfg.max_position_embeddings, dtype=torch.float32)
+    freqs = torch.einsum("i,j->ij", t, inv_freq)
+    return torch.cat([freqs.cos(), freqs.sin()], dim=-1).to(BF16).to(device)
+
+
+class Qwen2DecodeRunner:
+    """Batched single-token decode over a paged KV cache (continuous-batching decode step of the reference)."""
+
+    def __init__(self, cfg: Qwen2Config, weights: Qwen2Weights, max_batch: int, max_ctx: int, device="cuda",
+                 num_blocks: Optional[int] = None, fused_rope_cache: bool = True):
+        self.cfg, self.w, self.B, self.device = cfg, weights, max_batch, device
+        bs = cfg.block_size
+        self.max_pages = (max_ctx + bs - 1) // bs
+        self.num_blocks = num_blocks or (max_batch * self.max_pages + 1)     # block 0 reserved (block_manager_impl.cpp:71-73)
+        self.fused_rope_cache = fused_rope_cache
+        H, I = cfg.hidden_size, cfg.intermediate_size
+        B = max_batch
+        dev = device
+        self.k_caches = [torch.zeros(self.num_blocks, bs, cfg.n_kv_heads, cfg.head_dim, dtype=BF16, device=dev)
+                         for _ in range(cfg.num_layers)]
+        self.v_caches = [torch.zeros_like(k) for k in self.k_caches]
+        self.cos_sin = make_cos_sin_cache(cfg, dev)
+        # step inputs (device) + pinned host mirrors
+        n_idx = B * self.max_pages
+        self.token_ids = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.positions = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.slots = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.kv_indptr = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        self.kv_indices = torch.zeros(n_idx, dtype=torch.int32, device=dev)
+        self.kv_last = torch.ones(B, dtype=torch.int32, device=dev)
+        self.h_token_ids = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.h_positions = torch.zeros(B, dtype=torch.int64).pin_memory()
+        self.h_slots = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.h_kv_indptr = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        self.h_kv_indices = torch.zeros(n_idx, dtype=torch.int32).pin_memory()
+        self.h_kv_last = torch.ones(B, dtype=torch.int32).pin_memory()
+        self.h_next = torch.zeros(B, dtype=torch.int32).pin_memory()
+        # activations
+        self.hidden = torch.empty(B, H, dtype=BF16, device=dev)
+        self.residual = torch.empty(B, H, dtype=BF16, device=dev)
+        self.normed = torch.empty(B, H, dtype=BF16, device=dev)
+        # `hidden` carries the residual stream from layer 0 on (it aliases the embedding output);
+        # o_proj writes buf_a, down_proj writes buf_b
+        self.buf_a = torch.empty(B, H, dtype=BF16, device=dev)
+        self.buf_b = torch.empty(B, H, dtype=BF16, device=dev)
+        self.qkv = torch.empty(B, cfg.q_size + 2 * cfg.kv_size, dtype=BF16, device=dev)
+        self.attn_out = torch.empty(B, cfg.q_size, dtype=BF16, device=dev)
+        self.gate_up = torch.empty(B, 2 * I, dtype=BF16, device=dev)
+        self.act = torch.empty(B, I, dtype=BF16, device=dev)
+        self.logits = torch.empty(B, cfg.vocab_size, dtype=BF16, device=dev)
+        self.next_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.plan = ops.DecodePlan(B, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, bs, self.max_pages, dev)
+        self.graph = None
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in
+                             (self.h_token_ids, self.h_positions, self.h_slots, self.h_kv_indptr, self.h_kv_indices,
+                              self.h_kv_last))
+        self.d2h_bytes = self.h_next.numel() * 4
+
+    # -- one decode step worth of launches (capturable) -----------------------------------
+    def launch_step(self):
+        cfg, w = self.cfg, self.w
+        qs, kvs = cfg.q_size, cfg.kv_size
+        scale = cfg.head_dim ** -0.5
+        ops.embedding(self.hidden, self.token_ids, w.embed)
+        x = self.hidden
+        for li, L in enumerate(w.layers):
+            if li == 0:
+                # apply_norm first layer (qwen2_decoder_layer.cpp:72-79): residual aliases the input
+                ops.rms_norm(self.normed, x, L["input_norm"], cfg.rms_norm_eps)
+                self.residual = x
+                h = self.normed
+            else:
+                ops.fused_add_rms_norm(x, self.residual, L["input_norm"], cfg.rms_norm_eps)
+                h = x
+            L["qkv"].forward(h, self.qkv)
+            q, k, v = self.qkv[:, :qs], self.qkv[:, qs:qs + kvs], self.qkv[:, qs + kvs:]
+            if self.fused_rope_cache:
+                ops.rope_and_cache(self.positions, q, k, v, self.cos_sin, self.slots, self.k_caches[li],
+                                   self.v_caches[li], True)
+            else:
+                ops.rotary_embedding(self.positions, q, k, self.cos_sin, True)
+                ops.reshape_paged_cache(self.slots, k.view(-1, cfg.n_kv_heads, cfg.head_dim),
+                                        v.view(-1, cfg.n_kv_heads, cfg.head_dim), self.k_caches[li], self.v_caches[li])
+            ops.batch_decode(self.plan, q.view(-1, cfg.n_heads, cfg.head_dim), self.k_caches[li], self.v_caches[li],
+                             self.kv_indptr, self.kv_indices, self.kv_last, scale,
+                             self.attn_out.view(-1, cfg.n_heads, cfg.head_dim))
+            o = L["o"].forward(self.attn_out, self.buf_a)
+            ops.fused_add_rms_norm(o, self.residual, L["post_norm"], cfg.rms_norm_eps)
+            L["gate_up"].forward(o, self.gate_up)
+            ops.act_and_mul(self.act, self.gate_up, "silu")
+            x = L["down"].forward(self.act, self.buf_b)
+        ops.fused_add_rms_norm(x, self.residual, w.final_norm, cfg.rms_norm_eps)
+        w.lm_head.forward(x, self.logits)
+        ops.argmax(self.next_tokens, self.logits)
+
+    def capture(self):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.launch_step()          # warm-up (sets func attributes, loads modules)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                self.launch_step()
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = g
+        return g
+
+    def run_device_only(self):
+        """replay with whatever step inputs are resident on the device."""
+        if self.graph is None:
+            self.launch_step()
+        else:
+            self.graph.replay()
+
+    def set_inputs_host(self, token_ids, positions, slots, kv_indptr, kv_indices, kv_last):
+        n = len(token_ids)
+        self.h_token_ids[:n] = torch.as_tensor(token_ids, dtype=torch.int32)
+        self.h_positions[:n] = torch.as_tensor(positions, dtype=torch.int64)
+        self.h_slots[:n] = torch.as_tensor(slots, dtype=torch.int32)
+        self.h_kv_indptr[:len(kv_indptr)] = torch.as_tensor(kv_indptr, dtype=torch.int32)
+        self.h_kv_indices[:len(kv_indices)] = torch.as_tensor(kv_indices, dtype=torch.int32)
+        self.h_kv_last[:n] = torch.as_tensor(kv_last, dtype=torch.int32)
+
+    def step(self):
+        """end-to-end step: H2D of the pinned step inputs, graph replay, D2H of the sampled tokens."""
+        self.token_ids.copy_(self.h_token_ids, non_blocking=True)
+        self.positions.copy_(self.h_positions, non_blocking=True)
+        self.slots.copy_(self.h_slots, non_blocking=True)
+        self.kv_indptr.copy_(self.h_kv_indptr, non_blocking=True)
+        self.kv_indices.copy_(self.h_kv_indices, non_blocking=True)
+        self.kv_last.copy_(self.h_kv_last, non_blocking=True)
+        self.run_device_only()
+        self.h_next.copy_(self.next_tokens, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.h_next
