@@ -161,6 +161,10 @@ int xb_act_and_mul_bf16(void* out, const void* input, int d, int num_tokens,
 int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int num_kv_heads,
                    int head_dim, int page_size, int max_pages_per_request,
                    int num_sms);
+/* flags bit 0 ("early prefetch"): the caller guarantees that no kernel still in flight writes KV rows other than the
+ * newest token of each request, nor the paged triplet (true inside a decode step); the kernel then streams KV before
+ * its programmatic-dependent-launch wait, overlapping the producer kernel's tail. */
+int xb_decode_plan_set_flags(int64_t* plan8, int flags);
 int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t q_stride_n,
                          int64_t q_stride_h, const void* k_cache,
                          const void* v_cache, int64_t kv_stride_page,

@@ -57,6 +57,7 @@ rms_norm_vec_kernel(void* __restrict__ out_, __nv_bfloat16* __restrict__ input,
     int idx = threadIdx.x + i * blockDim.x;
     if (idx < nvec) wreg[i] = __ldg(w_v + idx);
   }
+  pdl_launch_dependents();  // consumer prologues (weight / KV prefetch) may start now
   pdl_wait();
 
   uint4 xr[kMaxVec];
@@ -167,6 +168,7 @@ rms_norm_scalar_kernel(void* __restrict__ out_, __nv_bfloat16* __restrict__ inpu
   const int64_t tok = blockIdx.x;
   __nv_bfloat16* in = input + tok * input_stride;
   __nv_bfloat16* res = kFusedAdd ? residual + tok * (int64_t)hidden_size : nullptr;
+  pdl_launch_dependents();  // consumer prologues (weight / KV prefetch) may start now
   pdl_wait();
   float ss = 0.f;
   for (int i = threadIdx.x; i < hidden_size; i += blockDim.x) {
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(256)
 fp8_quant_kernel(uint8_t* __restrict__ out, int64_t out_stride, const __nv_bfloat16* __restrict__ in,
                  int64_t in_stride, const float* __restrict__ scale, int hidden_size, bool vec) {
   const int64_t tok = blockIdx.x;
+  pdl_launch_dependents();  // consumer prologues (weight / KV prefetch) may start now
   pdl_wait();
   const float inv_scale = 1.0f / __ldg(scale);
   const __nv_bfloat16* src = in + tok * in_stride;
@@ -300,6 +303,7 @@ rotary_embedding_kernel(const int64_t* __restrict__ positions, __nv_bfloat16* __
                         int rot_dim, int64_t query_stride, int64_t key_stride, int64_t head_stride,
                         int num_heads, int num_kv_heads) {
   const int64_t tok = blockIdx.x;
+  pdl_launch_dependents();  // consumer prologues (weight / KV prefetch) may start now
   pdl_wait();
   const int64_t pos = positions[tok];
   const __nv_bfloat16* cache = cos_sin_cache + pos * rot_dim;
@@ -328,6 +332,7 @@ reshape_paged_cache_kernel(const int32_t* __restrict__ slot_ids, const __nv_bflo
                            __nv_bfloat16* __restrict__ value_cache, int64_t k_stride, int64_t v_stride,
                            int row_elems /* n_kv_heads*head_dim */, bool vec) {
   const int64_t tok = blockIdx.x;
+  pdl_launch_dependents();  // consumer prologues (weight / KV prefetch) may start now
   pdl_wait();
   const int64_t slot = slot_ids[tok];
   if (slot < 0) return;
@@ -365,6 +370,7 @@ rope_and_cache_kernel(const int64_t* __restrict__ positions, __nv_bfloat16* __re
                       int rot_dim, int64_t query_stride, int64_t key_stride, int64_t value_stride,
                       int num_heads, int num_kv_heads, int head_size) {
   const int64_t tok = blockIdx.x;
+  pdl_launch_dependents();  // consumer prologues (weight / KV prefetch) may start now
   pdl_wait();
   const int64_t pos = positions[tok];
   const int64_t slot = slot_ids[tok];
@@ -429,6 +435,7 @@ fused_qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int num_heads_q, int 
   const int tok = warp_global / heads_qk;
   const int head = warp_global % heads_qk;
   if (tok >= num_tokens) return;
+  pdl_launch_dependents();  // consumer prologues (weight / KV prefetch) may start now
   pdl_wait();
   const bool is_q = head < num_heads_q;
   const int total_heads = num_heads_q + num_heads_k + num_heads_v;
@@ -501,6 +508,7 @@ act_and_mul_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restr
   const __nv_bfloat16* x = in + tok * 2 * (int64_t)d;
   const __nv_bfloat16* y = x + d;
   __nv_bfloat16* o = out + tok * (int64_t)d;
+  pdl_launch_dependents();  // consumer prologues (weight / KV prefetch) may start now
   pdl_wait();
   if (vec) {
     const uint4* xv = reinterpret_cast<const uint4*>(x);

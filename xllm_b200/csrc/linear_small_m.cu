@@ -64,20 +64,31 @@ __device__ __forceinline__ XFrag load_x(const __nv_bfloat16* x, int64_t x_stride
 }
 
 // ---------------------------------------------------------------------------
-// W4A16
+// W4A16.  Work unit = (16-row tile, k split).  A warp owns one unit and streams its k64 tiles with a
+// register ring of kDepth outstanding 16-byte loads (continuous prefetch: the HBM pipe never drains
+// between tiles).  kSplit warps of a CTA share a row tile and reduce through shared memory; with
+// kSplit == 1 (wide N, e.g. gate_up) a warp owns its rows outright and writes them directly.
 // ---------------------------------------------------------------------------
-template <int kMT /* n8 token tiles: M <= 8*kMT */, int kUnroll>
-__global__ void __launch_bounds__(kWarps * 32)
+template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth>
+__global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : 2)
 linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
                             int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
                             const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int group_size) {
-  __shared__ float red[kWarps][kMT][16 * 8];
+  constexpr int kTilesPerCta = kWarps / kSplit;
+  __shared__ float red[kSplit > 1 ? kWarps : 1][kMT][16 * 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int ntile = blockIdx.x;
+  const int ntiles = N >> 4;
+  const int ntile = blockIdx.x * kTilesPerCta + warp / kSplit;
+  const int split = warp % kSplit;
+  const bool live = ntile < ntiles;
   const int n0 = ntile * 16;
   const int ktiles = K >> 6;
+  const int per = (ktiles + kSplit - 1) / kSplit;
+  const int kt_begin = split * per;
+  const int kt_end = live ? min(ktiles, kt_begin + per) : kt_begin;
   const uint4* wbase = qweight + (int64_t)ntile * ktiles * 32 + lane;
+  const int tiles_per_group = group_size >> 6;
 
   float acc[kMT][4];
 #pragma unroll
@@ -85,32 +96,34 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
 
-  // warp w takes k64 tiles w, w+kWarps, ...; kUnroll tiles per iteration.
-  for (int kt0 = warp; kt0 < ktiles; kt0 += kWarps * kUnroll) {
-    uint4 wq[kUnroll];
-    uint32_t mt0[kUnroll], mt1[kUnroll];
+  // ---- prologue: fill the ring (weights do not depend on the producer kernel) ----
+  uint4 ring[kDepth];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int kt = kt0 + u * kWarps;
-      if (kt < ktiles) {
-        wq[u] = ldg_stream(wbase + (int64_t)kt * 32);
-        const int grp = (kt << 6) / group_size;
-        mt0[u] = __ldg(meta + (int64_t)grp * N + n0 + g);
-        mt1[u] = __ldg(meta + (int64_t)grp * N + n0 + g + 8);
-      }
-    }
-    if (kt0 == warp) pdl_wait();  // x comes from the producer kernel; weights above do not
+  for (int i = 0; i < kDepth; ++i)
+    if (kt_begin + i < kt_end) ring[i] = ldg_stream(wbase + (int64_t)(kt_begin + i) * 32);
+  pdl_wait();  // x (and bias) come from the producer kernel
+
+  uint32_t s0 = 0, z0 = 0, s1 = 0, z1 = 0;
+  int cur_grp = -1;
+  for (int kt0 = kt_begin; kt0 < kt_end; kt0 += kDepth) {
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int kt = kt0 + u * kWarps;
-      if (kt < ktiles) {
-        // scale / zero pairs replicated into both bf16 lanes
-        const uint32_t s0 = __byte_perm(mt0[u], 0, 0x1010), z0 = __byte_perm(mt0[u], 0, 0x3232);
-        const uint32_t s1 = __byte_perm(mt1[u], 0, 0x1010), z1 = __byte_perm(mt1[u], 0, 0x3232);
+    for (int i = 0; i < kDepth; ++i) {
+      const int kt = kt0 + i;
+      if (kt < kt_end) {
+        const uint4 wq = ring[i];
+        if (kt + kDepth < kt_end) ring[i] = ldg_stream(wbase + (int64_t)(kt + kDepth) * 32);
+        const int grp = kt / tiles_per_group;
+        if (grp != cur_grp) {  // warp-uniform
+          cur_grp = grp;
+          const uint32_t mt0 = __ldg(meta + (int64_t)grp * N + n0 + g);
+          const uint32_t mt1 = __ldg(meta + (int64_t)grp * N + n0 + g + 8);
+          s0 = __byte_perm(mt0, 0, 0x1010); z0 = __byte_perm(mt0, 0, 0x3232);
+          s1 = __byte_perm(mt1, 0, 0x1010); z1 = __byte_perm(mt1, 0, 0x3232);
+        }
         XFrag xf[kMT];
 #pragma unroll
         for (int m = 0; m < kMT; ++m) xf[m] = load_x(x, x_stride, m * 8 + g, M, (kt << 6) + 16 * t);
-        const uint32_t* wp = &wq[u].x;
+        const uint32_t* wp = &wq.x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t w = wp[j];
@@ -132,10 +145,25 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
       }
     }
   }
-  if (ktiles <= warp) pdl_wait();
   pdl_launch_dependents();
 
-  // cross-warp reduction: c0:(row g, tok 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
+  // c0:(row g, tok 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
+  if constexpr (kSplit == 1) {
+    if (live) {
+#pragma unroll
+      for (int m = 0; m < kMT; ++m)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int tok = m * 8 + 2 * t + (i & 1), r = g + (i >> 1) * 8;
+          if (tok < M) {
+            float v = acc[m][i];
+            if (bias) v += __bfloat162float(bias[n0 + r]);
+            y[(int64_t)tok * y_stride + n0 + r] = __float2bfloat16_rn(v);
+          }
+        }
+    }
+    return;
+  } else {
 #pragma unroll
   for (int m = 0; m < kMT; ++m) {
     red[warp][m][g * 8 + 2 * t] = acc[m][0];
@@ -144,16 +172,19 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     red[warp][m][(g + 8) * 8 + 2 * t + 1] = acc[m][3];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kMT * 128; i += blockDim.x) {
-    const int m = i >> 7, r = (i & 127) >> 3, c = i & 7;
+  for (int i = threadIdx.x; i < kTilesPerCta * kMT * 128; i += blockDim.x) {
+    const int tl = i / (kMT * 128), rem = i % (kMT * 128);
+    const int m = rem >> 7, r = (rem & 127) >> 3, c = rem & 7;
     const int tok = m * 8 + c;
-    if (tok < M) {
+    const int nt = blockIdx.x * kTilesPerCta + tl;
+    if (tok < M && nt < ntiles) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) s += red[w][m][r * 8 + c];
-      if (bias) s += __bfloat162float(bias[n0 + r]);
-      y[(int64_t)tok * y_stride + n0 + r] = __float2bfloat16_rn(s);
+      for (int w = 0; w < kSplit; ++w) s += red[tl * kSplit + w][m][r * 8 + c];
+      if (bias) s += __bfloat162float(bias[nt * 16 + r]);
+      y[(int64_t)tok * y_stride + nt * 16 + r] = __float2bfloat16_rn(s);
     }
+  }
   }
 }
 
@@ -251,15 +282,29 @@ extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
   auto* xx = reinterpret_cast<const __nv_bfloat16*>(x);
   auto* qw = reinterpret_cast<const uint4*>(qweight);
   auto* bb = reinterpret_cast<const __nv_bfloat16*>(bias);
-  dim3 grid(N / 16), block(kWarps * 32);
   cudaStream_t s = (cudaStream_t)stream;
-#define XB_W4(MT, U)                                                                                          \
-  XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, U>, grid, block, 0, s, true, yy, y_stride, xx, x_stride, \
-                    qw, meta, bb, M, N, K, group_size))
-  if (M <= 8) XB_W4(1, 8);
-  else if (M <= 16) XB_W4(2, 4);
-  else if (M <= 32) XB_W4(4, 2);
-  else XB_W4(8, 1);
+  // pick the k split so that (row tiles x splits) covers ~16 warps on each of the 148 SMs
+  const int ntiles = N / 16, ktiles = K / 64;
+  int split = 1;
+  while (split < 8 && ntiles * split < 148 * 16 && ktiles / (split * 2) >= 3) split *= 2;
+#define XB_W4_LAUNCH(MT, SP, DP)                                                                             \
+  {                                                                                                          \
+    dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                             \
+    XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, DP>, grid, block, 0, s, true, yy, y_stride, xx,    \
+                      x_stride, qw, meta, bb, M, N, K, group_size));                                         \
+  }
+#define XB_W4(MT, DP)                                   \
+  switch (split) {                                      \
+    case 1: XB_W4_LAUNCH(MT, 1, DP) break;              \
+    case 2: XB_W4_LAUNCH(MT, 2, DP) break;              \
+    case 4: XB_W4_LAUNCH(MT, 4, DP) break;              \
+    default: XB_W4_LAUNCH(MT, 8, DP) break;             \
+  }
+  if (M <= 8) XB_W4(1, 8)
+  else if (M <= 16) XB_W4(2, 6)
+  else if (M <= 32) XB_W4(4, 4)
+  else XB_W4(8, 2)
+#undef XB_W4_LAUNCH
 #undef XB_W4
   return 0;
 }

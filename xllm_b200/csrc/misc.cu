@@ -9,6 +9,7 @@ namespace xb {
 __global__ void __launch_bounds__(256)
 embedding_kernel(__nv_bfloat16* __restrict__ out, const int32_t* __restrict__ token_ids,
                  const __nv_bfloat16* __restrict__ table, int hidden, int vocab) {
+  pdl_launch_dependents();  // consumer prologues (weight / KV prefetch) may start now
   pdl_wait();
   const int64_t tok = blockIdx.x;
   int id = token_ids[tok];
@@ -25,6 +26,7 @@ __global__ void __launch_bounds__(1024)
 argmax_kernel(int32_t* __restrict__ out, const __nv_bfloat16* __restrict__ logits, int64_t stride, int vocab) {
   __shared__ float sv[32];
   __shared__ int si[32];
+  pdl_launch_dependents();  // consumer prologues (weight / KV prefetch) may start now
   pdl_wait();
   const __nv_bfloat16* row = logits + (int64_t)blockIdx.x * stride;
   float best = -INFINITY;

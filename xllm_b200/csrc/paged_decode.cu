@@ -48,6 +48,7 @@ struct DecodeParams {
   int num_qo_heads, num_kv_heads, group, head_tiles;
   int page_size, page_shift;  // page_shift >= 0 when page_size is a power of two
   int chunk_tokens, max_splits;
+  int early_prefetch;  // KV rows of old tokens + the paged triplet are not written by any in-flight kernel
 };
 
 __device__ __forceinline__ const __nv_bfloat16* kv_row(const DecodeParams& p, const __nv_bfloat16* cache,
@@ -84,7 +85,8 @@ paged_decode_kernel(const DecodeParams p) {
   const int kvh = blockIdx.y / p.head_tiles, htile = blockIdx.y % p.head_tiles;
   const int b = blockIdx.z;
 
-  pdl_wait();
+  pdl_launch_dependents();  // let the consumer's prologue (weight prefetch) start as early as possible
+  if (!p.early_prefetch) pdl_wait();
 
   const int indptr0 = __ldg(p.kv_indptr + b);
   const int n_pages = __ldg(p.kv_indptr + b + 1) - indptr0;
@@ -96,6 +98,40 @@ paged_decode_kernel(const DecodeParams p) {
   const int t_end = min(kv_len, t_begin + p.chunk_tokens);
   const int head0 = kvh * p.group + htile * kHeads;            // first qo head of this CTA
   const int nheads = min(kHeads, p.group - htile * kHeads);    // live heads in this CTA
+  const int nblk = (t_end - t_begin + 15) >> 4;
+  const int last_tok = kv_len - 1;
+
+  struct KVFrag {
+    uint4 kf[2][kChunks];
+    uint4 vf[4][kVC];
+  };
+  // 16 independent 16-byte loads of one 16-token block, straight into MMA fragment registers
+  auto load_block = [&](KVFrag& f, int blk) {
+    const int tb = t_begin + (blk << 4);
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
+      const int tok = min(tb + tile * 8 + g, last_tok);
+      const __nv_bfloat16* row = kv_row(p, p.k_cache, indptr0, tok, kvh);
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) f.kf[tile][i] = ldg_stream(row + (4 * i + t) * 8);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int tok = min(tb + (s >> 1) * 8 + 2 * t + (s & 1), last_tok);
+      const __nv_bfloat16* row = kv_row(p, p.v_cache, indptr0, tok, kvh);
+#pragma unroll
+      for (int c = 0; c < kVC; ++c) f.vf[s][c] = ldg_stream(row + (c * 8 + g) * 8);
+    }
+  };
+
+  int blk = warp;
+  bool have = blk < nblk;
+  KVFrag cur;
+  // With early_prefetch the first block of every warp is fetched while the producer kernel (RoPE + KV scatter of the
+  // NEWEST token) may still be running - except the block that holds that newest token.
+  const bool early = p.early_prefetch && have && (t_begin + (blk << 4) + 16 <= last_tok);
+  if (early) load_block(cur, blk);
+  if (p.early_prefetch) pdl_wait();
 
   // ---- Q fragments (chunk 4i+t of head g / g+8, same permutation as K) -------
   uint4 qa[kChunks], qb[kChunks];
@@ -110,6 +146,7 @@ paged_decode_kernel(const DecodeParams p) {
         qb[i] = *reinterpret_cast<const uint4*>(qrow + (int64_t)(head0 + g + 8) * p.q_stride_h + (4 * i + t) * 8);
     }
   }
+  if (have && !early) load_block(cur, blk);
 
   float o_acc[kNT][4];
 #pragma unroll
@@ -119,30 +156,15 @@ paged_decode_kernel(const DecodeParams p) {
   float m_run[2] = {-INFINITY, -INFINITY};  // head g, head g+8
   float l_run[2] = {0.f, 0.f};              // per-thread partial sums
 
-  const int nblk = (t_end - t_begin + 15) >> 4;
-  const int last_tok = kv_len - 1;
-
-  for (int blk = warp; blk < nblk; blk += kWarpsT) {
+  while (have) {
     const int tb = t_begin + (blk << 4);
-    // ---- issue all 16 loads of the block -------------------------------------
-    uint4 kf[2][kChunks];
-    uint4 vf[4][kVC];
-    {
-#pragma unroll
-      for (int tile = 0; tile < 2; ++tile) {
-        const int tok = min(tb + tile * 8 + g, last_tok);
-        const __nv_bfloat16* row = kv_row(p, p.k_cache, indptr0, tok, kvh);
-#pragma unroll
-        for (int i = 0; i < kChunks; ++i) kf[tile][i] = ldg_stream(row + (4 * i + t) * 8);
-      }
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int tok = min(tb + (s >> 1) * 8 + 2 * t + (s & 1), last_tok);
-        const __nv_bfloat16* row = kv_row(p, p.v_cache, indptr0, tok, kvh);
-#pragma unroll
-        for (int c = 0; c < kVC; ++c) vf[s][c] = ldg_stream(row + (c * 8 + g) * 8);
-      }
-    }
+    // ---- prefetch the warp's next block while this one is consumed -----------
+    const int nblk_next = blk + kWarpsT;
+    const bool have_next = nblk_next < nblk;
+    KVFrag nxt;
+    if (have_next) load_block(nxt, nblk_next);
+    const uint4 (&kf)[2][kChunks] = cur.kf;
+    const uint4 (&vf)[4][kVC] = cur.vf;
     // ---- S = Q K^T ----------------------------------------------------------
     float s_acc[2][4];
 #pragma unroll
@@ -210,8 +232,10 @@ paged_decode_kernel(const DecodeParams p) {
         mma_bf16_16816(o_acc[c * 8 + 2 * r + 1], pa[0], pa[1], pa[2], pa[3], b0o, b1o);
       }
     }
+    if (have_next) cur = nxt;
+    blk = nblk_next;
+    have = have_next;
   }
-  pdl_launch_dependents();
 
   // ---- publish warp state ------------------------------------------------------
 #pragma unroll
@@ -318,21 +342,24 @@ paged_decode_kernel(const DecodeParams p) {
   }
 }
 
-constexpr int kDecodeWarps = 8;
-
-template <int kD, int kGT>
-static int launch_decode(const DecodeParams& p, int batch, cudaStream_t stream) {
+template <int kD, int kGT, int kW>
+static int launch_decode_w(const DecodeParams& p, int batch, cudaStream_t stream) {
   constexpr int kHeads = 8 * kGT;
-  const size_t smem = (size_t)kDecodeWarps * kHeads * (kD + 4 + 2) * sizeof(float);
-  auto kern = paged_decode_kernel<kD, kGT, kDecodeWarps>;
+  const size_t smem = (size_t)kW * kHeads * (kD + 4 + 2) * sizeof(float);
+  auto kern = paged_decode_kernel<kD, kGT, kW>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid(p.max_splits, p.num_kv_heads * p.head_tiles, batch), block(kDecodeWarps * 32);
+  dim3 grid(p.max_splits, p.num_kv_heads * p.head_tiles, batch), block(kW * 32);
   XB_CUDA_OK(launch(kern, grid, block, smem, stream, true, p));
   return 0;
+}
+
+template <int kD, int kGT>
+static int launch_decode(const DecodeParams& p, int batch, int cta_warps, cudaStream_t stream) {
+  return cta_warps == 4 ? launch_decode_w<kD, kGT, 4>(p, batch, stream) : launch_decode_w<kD, kGT, 8>(p, batch, stream);
 }
 
 }  // namespace xb
@@ -340,7 +367,7 @@ static int launch_decode(const DecodeParams& p, int batch, cudaStream_t stream) 
 using namespace xb;
 
 // plan8: [0]=chunk_tokens [1]=max_splits [2]=float ws bytes [3]=int ws bytes
-//        [4]=batch [5]=num_qo_heads [6]=num_kv_heads [7]=head_dim | page_size<<16
+//        [4]=batch [5]=num_qo_heads [6]=num_kv_heads [7]=head_dim | page_size<<16 | cta_warps<<40
 extern "C" int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int num_kv_heads, int head_dim,
                               int page_size, int max_pages_per_request, int num_sms) {
   XB_CHECK(batch > 0 && num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0,
@@ -364,11 +391,15 @@ extern "C" int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int n
   plan8[0] = chunk;
   plan8[1] = splits;
   plan8[2] = splits > 1 ? (int64_t)batch * num_qo_heads * splits * (head_dim + 1) * 4 : 16;
-  plan8[3] = units * 4;
+  plan8[3] = units * 4;  // low 32 bits: int workspace bytes; bit 32: early-prefetch flag (xb_decode_plan_set_flags)
   plan8[4] = batch;
   plan8[5] = num_qo_heads;
   plan8[6] = num_kv_heads;
-  plan8[7] = (int64_t)head_dim | ((int64_t)page_size << 16);
+  // warps per CTA: 8 by default; 4 leaves register room for a co-resident consumer CTA under PDL (XB_DECODE_WARPS)
+  int cta_warps = 8;
+  const char* envw = getenv("XB_DECODE_WARPS");
+  if (envw && atoi(envw) == 4) cta_warps = 4;
+  plan8[7] = (int64_t)head_dim | ((int64_t)page_size << 16) | ((int64_t)cta_warps << 40);
   return 0;
 }
 
@@ -382,7 +413,8 @@ extern "C" int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t
   DecodeParams p{};
   const int batch = (int)plan8[4];
   const int head_dim = (int)(plan8[7] & 0xffff);
-  p.page_size = (int)(plan8[7] >> 16);
+  p.page_size = (int)((plan8[7] >> 16) & 0xffffff);
+  const int cta_warps = (int)(plan8[7] >> 40);
   p.page_shift = -1;
   if ((p.page_size & (p.page_size - 1)) == 0) {
     int s = 0;
@@ -421,10 +453,22 @@ extern "C" int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t
   p.part_o = reinterpret_cast<float*>(workspace_f32);
   p.part_lse = p.part_o ? p.part_o + (int64_t)batch * p.num_qo_heads * p.max_splits * head_dim : nullptr;
   p.counters = reinterpret_cast<int32_t*>(workspace_i32);
+  p.early_prefetch = (int)(plan8[3] >> 32) & 1;
   cudaStream_t s = (cudaStream_t)stream;
   const bool wide = p.group > 8;
-  if (head_dim == 128) return wide ? launch_decode<128, 2>(p, batch, s) : launch_decode<128, 1>(p, batch, s);
-  if (head_dim == 64) return wide ? launch_decode<64, 2>(p, batch, s) : launch_decode<64, 1>(p, batch, s);
+  if (head_dim == 128)
+    return wide ? launch_decode<128, 2>(p, batch, cta_warps, s) : launch_decode<128, 1>(p, batch, cta_warps, s);
+  if (head_dim == 64)
+    return wide ? launch_decode<64, 2>(p, batch, cta_warps, s) : launch_decode<64, 1>(p, batch, cta_warps, s);
   XB_CHECK(false, "paged_decode: head_dim %d unsupported", head_dim);
   return 1;
+}
+
+// flags bit 0: early prefetch - the caller guarantees that KV rows other than the newest token of each request, and the
+// paged triplet, are not written by any kernel still in flight when this one is launched (true for the decode step:
+// the only producer in flight is RoPE+scatter of the newest token).  The kernel then fetches KV before the PDL wait.
+extern "C" int xb_decode_plan_set_flags(int64_t* plan8, int flags) {
+  XB_CHECK(plan8 != nullptr, "decode_plan_set_flags: null plan");
+  plan8[3] = (plan8[3] & 0xffffffffll) | ((int64_t)(flags & 1) << 32);
+  return 0;
 }

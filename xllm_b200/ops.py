@@ -193,7 +193,7 @@ class DecodePlan:
     """Opaque plan (the reference deep-copies FlashInfer's plan_info: flashinfer_planinfo.cpp:37-62)."""
 
     def __init__(self, batch, num_qo_heads, num_kv_heads, head_dim, page_size, max_pages_per_request, device,
-                 num_sms: Optional[int] = None):
+                 num_sms: Optional[int] = None, early_prefetch: bool = False):
         if num_sms is None:
             num_sms = torch.cuda.get_device_properties(device).multi_processor_count
         self.arr = (ctypes.c_int64 * 8)()
@@ -201,7 +201,10 @@ class DecodePlan:
                                    c_i32(page_size), c_i32(max_pages_per_request), c_i32(num_sms)), "decode_plan")
         self.chunk_tokens, self.max_splits = int(self.arr[0]), int(self.arr[1])
         self.float_ws = torch.empty(int(self.arr[2]), dtype=torch.uint8, device=device)
-        self.int_ws = torch.zeros(int(self.arr[3]), dtype=torch.uint8, device=device)
+        self.int_ws = torch.zeros(int(self.arr[3]) & 0xFFFFFFFF, dtype=torch.uint8, device=device)
+        if early_prefetch:
+            # only inside a decode step: nothing in flight writes old KV rows or the paged triplet
+            check(lib().xb_decode_plan_set_flags(self.arr, c_i32(1)), "decode_plan_set_flags")
 
 
 def batch_decode(plan: DecodePlan, query, k_cache, v_cache, paged_kv_indptr, paged_kv_indices,

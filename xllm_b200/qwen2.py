@@ -195,7 +195,8 @@ class Qwen2DecodeRunner:
         self.act = torch.empty(B, I, dtype=BF16, device=dev)
         self.logits = torch.empty(B, cfg.vocab_size, dtype=BF16, device=dev)
         self.next_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
-        self.plan = ops.DecodePlan(B, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, bs, self.max_pages, dev)
+        self.plan = ops.DecodePlan(B, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, bs, self.max_pages, dev,
+                                   early_prefetch=True)
         self.graph = None
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in
                              (self.h_token_ids, self.h_positions, self.h_slots, self.h_kv_indptr, self.h_kv_indices,
