@@ -40,7 +40,11 @@ def assert_close_bf16(got: torch.Tensor, ref: torch.Tensor, ulps: float = 1.0, r
 
 
 def assert_close_attention(got, ref, abs_scale, rtol: float = 1e-3, what: str = ""):
-    """|got - ref| <= rtol * (sum_j p_j |v_j|) + 1 bf16 ulp(ref), elementwise (see module docstring)."""
+    """|got - ref| <= rtol * (sum_j p_j |v_j|) + 1 bf16 ulp(ref), elementwise (see module docstring).
+
+    The same bound with rtol = 1e-5 is used for fp32-accumulated dot products (linears): two correct summation orders
+    of sum_k x_k w_k differ by O(eps_fp32 * sqrt(K)) * sum_k |x_k w_k|, which is many bf16 ulps of an output that
+    happens to cancel to ~0, so the absolute term has to be relative to sum_k |x_k w_k| (computed by the oracle)."""
     g, r = got.detach().cpu().to(torch.float32), ref.detach().cpu().to(torch.float32)
     sc = abs_scale.detach().cpu().to(torch.float32)
     assert g.shape == r.shape == sc.shape, f"{what}: shapes {g.shape} {r.shape} {sc.shape}"
@@ -51,3 +55,6 @@ def assert_close_attention(got, ref, abs_scale, rtol: float = 1e-3, what: str = 
     assert not bad.any(), (f"{what}: {int(bad.sum())} / {bad.numel()} elements beyond {rtol:.0e} * sum p|v| + 1 ulp; "
                            f"worst err/bound = {(err / bound).max().item():.2f}")
     return (err / sc.clamp_min(1e-30)).max().item()
+
+
+assert_close_sum = assert_close_attention

@@ -96,33 +96,50 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
 
-  // ---- prologue: fill the ring (weights do not depend on the producer kernel) ----
+  // ---- prologue: fill the ring (weights + scale/zero words do not depend on the producer kernel) ----
   uint4 ring[kDepth];
+  uint32_t ring_m0[kDepth], ring_m1[kDepth];
+  const uint32_t* mrow = meta + n0 + g;
 #pragma unroll
-  for (int i = 0; i < kDepth; ++i)
-    if (kt_begin + i < kt_end) ring[i] = ldg_stream(wbase + (int64_t)(kt_begin + i) * 32);
+  for (int i = 0; i < kDepth; ++i) {
+    const int kt = kt_begin + i;
+    if (kt < kt_end) {
+      ring[i] = ldg_stream(wbase + (int64_t)kt * 32);
+      const int64_t go = (int64_t)(kt / tiles_per_group) * N;
+      ring_m0[i] = __ldg(mrow + go);
+      ring_m1[i] = __ldg(mrow + go + 8);
+    }
+  }
   pdl_wait();  // x (and bias) come from the producer kernel
 
-  uint32_t s0 = 0, z0 = 0, s1 = 0, z1 = 0;
-  int cur_grp = -1;
+  // x fragments are software-pipelined one tile ahead
+  XFrag xn[kMT];
+  if (kt_begin < kt_end) {
+#pragma unroll
+    for (int m = 0; m < kMT; ++m) xn[m] = load_x(x, x_stride, m * 8 + g, M, (kt_begin << 6) + 16 * t);
+  }
   for (int kt0 = kt_begin; kt0 < kt_end; kt0 += kDepth) {
 #pragma unroll
     for (int i = 0; i < kDepth; ++i) {
       const int kt = kt0 + i;
       if (kt < kt_end) {
         const uint4 wq = ring[i];
-        if (kt + kDepth < kt_end) ring[i] = ldg_stream(wbase + (int64_t)(kt + kDepth) * 32);
-        const int grp = kt / tiles_per_group;
-        if (grp != cur_grp) {  // warp-uniform
-          cur_grp = grp;
-          const uint32_t mt0 = __ldg(meta + (int64_t)grp * N + n0 + g);
-          const uint32_t mt1 = __ldg(meta + (int64_t)grp * N + n0 + g + 8);
-          s0 = __byte_perm(mt0, 0, 0x1010); z0 = __byte_perm(mt0, 0, 0x3232);
-          s1 = __byte_perm(mt1, 0, 0x1010); z1 = __byte_perm(mt1, 0, 0x3232);
+        const uint32_t mt0 = ring_m0[i], mt1 = ring_m1[i];
+        if (kt + kDepth < kt_end) {
+          ring[i] = ldg_stream(wbase + (int64_t)(kt + kDepth) * 32);
+          const int64_t go = (int64_t)((kt + kDepth) / tiles_per_group) * N;
+          ring_m0[i] = __ldg(mrow + go);
+          ring_m1[i] = __ldg(mrow + go + 8);
         }
         XFrag xf[kMT];
 #pragma unroll
-        for (int m = 0; m < kMT; ++m) xf[m] = load_x(x, x_stride, m * 8 + g, M, (kt << 6) + 16 * t);
+        for (int m = 0; m < kMT; ++m) xf[m] = xn[m];
+        if (kt + 1 < kt_end) {
+#pragma unroll
+          for (int m = 0; m < kMT; ++m) xn[m] = load_x(x, x_stride, m * 8 + g, M, ((kt + 1) << 6) + 16 * t);
+        }
+        const uint32_t s0 = __byte_perm(mt0, 0, 0x1010), z0 = __byte_perm(mt0, 0, 0x3232);
+        const uint32_t s1 = __byte_perm(mt1, 0, 0x1010), z1 = __byte_perm(mt1, 0, 0x3232);
         const uint32_t* wp = &wq.x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
