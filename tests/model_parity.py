@@ -120,3 +120,45 @@ def run_decode_parity(cfg, kv_lens, use_graph=True, fused=True, seed=2026):
     # KV caches after the step: the new token's rotated K and V must have been scattered bit-exactly
     # (same qkv GEMM inputs -> within tolerance; compare the untouched part exactly)
     return logits, ref_logits, nxt, ref_next, runner, (kcs, vcs)
+
+
+def oracle_layer(cfg, W, li, x, residual, kcs, vcs, meta):
+    """one decoder layer of the oracle on given inputs (teacher forcing with the GPU's own layer inputs)."""
+    B = len(meta["tokens"])
+    cs = O.compute_cos_sin_cache(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, BF16)
+    am = OL.AttnMeta(False, False, torch.arange(B + 1, dtype=torch.int32), None, torch.tensor(meta["slots"], dtype=torch.int32),
+                     torch.tensor(meta["indptr"], dtype=torch.int32), torch.tensor(meta["indices"], dtype=torch.int32),
+                     torch.tensor(meta["last"], dtype=torch.int32))
+    L = W["layers"][li]
+    attn = OL.Qwen2AttentionOracle(L["qkv"]["w"], L["qkv"]["b"], L["o"]["w"], cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cs)
+    dl = OL.Qwen2DecoderLayerOracle(attn, L["input_norm"], L["post_norm"], cfg.rms_norm_eps,
+                                    lambda h: O.linear(h, L["gate_up"]["w"]), lambda h: O.linear(h, L["down"]["w"]))
+    return dl.forward(x, residual, torch.tensor(meta["positions"]), am, kcs[li].clone(), vcs[li].clone())
+
+
+def run_layerwise_parity(cfg, kv_lens, seed=2026):
+    """Eager GPU step with a per-layer trace; every layer of the oracle is then fed the GPU's own input of that layer,
+    so each comparison isolates ONE decoder layer (no compounding of bf16 rounding flips across layers).
+    Returns a list of (gpu_out, ref_out, gpu_res, ref_res) per layer."""
+    from xllm_b200.qwen2 import Qwen2DecodeRunner
+    B = len(kv_lens)
+    W, kcs, vcs, meta = build_case(cfg, B, kv_lens, seed)
+    runner = Qwen2DecodeRunner(cfg, upload(cfg, W), B, max(kv_lens), num_blocks=meta["nblocks"])
+    for li in range(cfg.num_layers):
+        runner.k_caches[li].copy_(kcs[li])
+        runner.v_caches[li].copy_(vcs[li])
+    runner.set_inputs_host(meta["tokens"], meta["positions"], meta["slots"], meta["indptr"], meta["indices"], meta["last"])
+    for d, h in ((runner.token_ids, runner.h_token_ids), (runner.positions, runner.h_positions), (runner.slots, runner.h_slots),
+                 (runner.kv_indptr, runner.h_kv_indptr), (runner.kv_indices, runner.h_kv_indices), (runner.kv_last, runner.h_kv_last)):
+        d.copy_(h)
+    trace = []
+    runner.launch_step(trace)
+    torch.cuda.synchronize()
+    out = []
+    x_in, res_in = W["embed"][torch.tensor(meta["tokens"])], None
+    for li in range(cfg.num_layers):
+        ref_x, ref_res = oracle_layer(cfg, W, li, x_in, res_in, kcs, vcs, meta)
+        gx, gres = trace[li][0].cpu(), trace[li][1].cpu()
+        out.append((gx, ref_x, gres, ref_res))
+        x_in, res_in = gx, gres          # teacher forcing: next layer sees what the GPU produced
+    return out

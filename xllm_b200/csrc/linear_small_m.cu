@@ -64,16 +64,25 @@ __device__ __forceinline__ XFrag load_x(const __nv_bfloat16* x, int64_t x_stride
 }
 
 // ---------------------------------------------------------------------------
-// W4A16.  Work unit = (16-row tile, k split).  A warp owns one unit and streams its k64 tiles with a
-// register ring of kDepth outstanding 16-byte loads (continuous prefetch: the HBM pipe never drains
-// between tiles).  kSplit warps of a CTA share a row tile and reduce through shared memory; with
-// kSplit == 1 (wide N, e.g. gate_up) a warp owns its rows outright and writes them directly.
+// W4A16.  Work unit = (16-row tile, k split).  A warp owns one unit and streams its k range with a
+// register ring of kDepth slots (one slot = kTG k64 tiles = kTG 16-byte loads + the group's scale/zero
+// words) that is refilled as it is consumed: the HBM pipe never drains between tiles.  kSplit warps of a
+// CTA share a row tile and reduce through shared memory; with kSplit == 1 (wide N, e.g. gate_up) a warp
+// owns its rows outright and writes them directly.  The inner loop is instruction-bound next to HBM on
+// B200 (5.5 lane-ops per HBM byte): addresses are running pointers, the group index is a shift, and the
+// per-weight work is exactly LOP3(+SHF) / HSUB2 / HMUL2 per bf16 PAIR plus one HMMA per 8 weights.
 // ---------------------------------------------------------------------------
-template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth>
+template <int kMT>
+struct XRing {
+  uint4 lo[kMT], hi[kMT];
+};
+
+template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth,
+          int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */>
 __global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : 2)
 linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
                             int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
-                            const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int group_size) {
+                            const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int gshift /* log2(tiles per group) */) {
   constexpr int kTilesPerCta = kWarps / kSplit;
   __shared__ float red[kSplit > 1 ? kWarps : 1][kMT][16 * 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,11 +93,10 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   const bool live = ntile < ntiles;
   const int n0 = ntile * 16;
   const int ktiles = K >> 6;
-  const int per = (ktiles + kSplit - 1) / kSplit;
-  const int kt_begin = split * per;
-  const int kt_end = live ? min(ktiles, kt_begin + per) : kt_begin;
-  const uint4* wbase = qweight + (int64_t)ntile * ktiles * 32 + lane;
-  const int tiles_per_group = group_size >> 6;
+  const int nslots = ktiles / kTG;
+  const int per = (nslots + kSplit - 1) / kSplit;
+  const int s_begin = split * per;
+  const int s_end = live ? min(nslots, s_begin + per) : s_begin;
 
   float acc[kMT][4];
 #pragma unroll
@@ -96,70 +104,116 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
 
+  // running pointers (one 64-bit add per slot instead of a multiply per tile)
+  const uint4* wp = qweight + ((int64_t)ntile * ktiles + (int64_t)s_begin * kTG) * 32 + lane;
+  const uint32_t* mbase = meta + n0 + g;
+
   // ---- prologue: fill the ring (weights + scale/zero words do not depend on the producer kernel) ----
-  uint4 ring[kDepth];
+  uint4 ring[kDepth][kTG];
   uint32_t ring_m0[kDepth], ring_m1[kDepth];
-  const uint32_t* mrow = meta + n0 + g;
 #pragma unroll
   for (int i = 0; i < kDepth; ++i) {
-    const int kt = kt_begin + i;
-    if (kt < kt_end) {
-      ring[i] = ldg_stream(wbase + (int64_t)kt * 32);
-      const int64_t go = (int64_t)(kt / tiles_per_group) * N;
-      ring_m0[i] = __ldg(mrow + go);
-      ring_m1[i] = __ldg(mrow + go + 8);
+    if (s_begin + i < s_end) {
+#pragma unroll
+      for (int u = 0; u < kTG; ++u) ring[i][u] = ldg_stream(wp + (i * kTG + u) * 32);
+      const uint32_t* mr = mbase + (int64_t)(((s_begin + i) * kTG) >> gshift) * N;
+      ring_m0[i] = __ldg(mr);
+      ring_m1[i] = __ldg(mr + 8);
     }
   }
+  wp += kDepth * kTG * 32;   // next slot to prefetch
   pdl_wait();  // x (and bias) come from the producer kernel
 
-  // x fragments are software-pipelined one tile ahead
-  XFrag xn[kMT];
-  if (kt_begin < kt_end) {
+  // x fragments: lane (g,t) needs x[tok = 8m+g][k0 + 16t .. +16) per tile; pipelined one slot ahead
+  // token columns past M read the last valid token instead of zeros: their accumulator columns are
+  // finite garbage that is never stored, and the loads need neither a predicate nor a zero fill
+  const __nv_bfloat16* xp[kMT];
 #pragma unroll
-    for (int m = 0; m < kMT; ++m) xn[m] = load_x(x, x_stride, m * 8 + g, M, (kt_begin << 6) + 16 * t);
+  for (int m = 0; m < kMT; ++m) {
+    const int tok = min(m * 8 + g, M - 1);
+    xp[m] = x + (int64_t)tok * x_stride + (int64_t)s_begin * kTG * 64 + 16 * t;
   }
-  for (int kt0 = kt_begin; kt0 < kt_end; kt0 += kDepth) {
+  constexpr bool kPrefetchX = kMT <= 2;   // wider token tiles have no registers to spare
+  auto load_xslot = [&](XRing<kMT> (&d)[kTG]) {
 #pragma unroll
-    for (int i = 0; i < kDepth; ++i) {
-      const int kt = kt0 + i;
-      if (kt < kt_end) {
-        const uint4 wq = ring[i];
-        const uint32_t mt0 = ring_m0[i], mt1 = ring_m1[i];
-        if (kt + kDepth < kt_end) {
-          ring[i] = ldg_stream(wbase + (int64_t)(kt + kDepth) * 32);
-          const int64_t go = (int64_t)((kt + kDepth) / tiles_per_group) * N;
-          ring_m0[i] = __ldg(mrow + go);
-          ring_m1[i] = __ldg(mrow + go + 8);
-        }
-        XFrag xf[kMT];
+    for (int u = 0; u < kTG; ++u)
 #pragma unroll
-        for (int m = 0; m < kMT; ++m) xf[m] = xn[m];
-        if (kt + 1 < kt_end) {
+      for (int m = 0; m < kMT; ++m) {
+        d[u].lo[m] = *reinterpret_cast<const uint4*>(xp[m] + u * 64);
+        d[u].hi[m] = *reinterpret_cast<const uint4*>(xp[m] + u * 64 + 8);
+      }
 #pragma unroll
-          for (int m = 0; m < kMT; ++m) xn[m] = load_x(x, x_stride, m * 8 + g, M, ((kt + 1) << 6) + 16 * t);
-        }
-        const uint32_t s0 = __byte_perm(mt0, 0, 0x1010), z0 = __byte_perm(mt0, 0, 0x3232);
-        const uint32_t s1 = __byte_perm(mt1, 0, 0x1010), z1 = __byte_perm(mt1, 0, 0x3232);
-        const uint32_t* wp = &wq.x;
+    for (int m = 0; m < kMT; ++m) xp[m] += kTG * 64;
+  };
+  auto consume = [&](const uint4 (&wq)[kTG], uint32_t mt0, uint32_t mt1, const XRing<kMT> (&xf)[kTG]) {
+    const uint32_t s0 = __byte_perm(mt0, 0, 0x1010), z0 = __byte_perm(mt0, 0, 0x3232);
+    const uint32_t s1 = __byte_perm(mt1, 0, 0x1010), z1 = __byte_perm(mt1, 0, 0x3232);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t w = wp[j];
-          const uint32_t q0 = lop3_and_or(w, 0x000f000fu, 0x43004300u);
-          const uint32_t q1 = lop3_and_or(w >> 4, 0x000f000fu, 0x43004300u);
-          const uint32_t q2 = lop3_and_or(w >> 8, 0x000f000fu, 0x43004300u);
-          const uint32_t q3 = lop3_and_or(w >> 12, 0x000f000fu, 0x43004300u);
-          const uint32_t a0 = hmul2_bf16(hsub2_bf16(q0, z0), s0);
-          const uint32_t a1 = hmul2_bf16(hsub2_bf16(q1, z1), s1);
-          const uint32_t a2 = hmul2_bf16(hsub2_bf16(q2, z0), s0);
-          const uint32_t a3 = hmul2_bf16(hsub2_bf16(q3, z1), s1);
+    for (int u = 0; u < kTG; ++u) {
+      const uint32_t* wv = &wq[u].x;
 #pragma unroll
-          for (int m = 0; m < kMT; ++m) {
-            // lane run element 4j+{0,1} -> b0, 4j+{2,3} -> b1
-            const uint32_t* xp = j < 2 ? &xf[m].lo.x : &xf[m].hi.x;
-            mma_bf16_16816(acc[m], a0, a1, a2, a3, xp[(j & 1) * 2], xp[(j & 1) * 2 + 1]);
-          }
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w = wv[j];
+        const uint32_t q0 = lop3_and_or(w, 0x000f000fu, 0x43004300u);
+        const uint32_t q1 = lop3_and_or(w >> 4, 0x000f000fu, 0x43004300u);
+        const uint32_t q2 = lop3_and_or(w >> 8, 0x000f000fu, 0x43004300u);
+        const uint32_t q3 = lop3_and_or(w >> 12, 0x000f000fu, 0x43004300u);
+        const uint32_t a0 = hmul2_bf16(hsub2_bf16(q0, z0), s0);
+        const uint32_t a1 = hmul2_bf16(hsub2_bf16(q1, z1), s1);
+        const uint32_t a2 = hmul2_bf16(hsub2_bf16(q2, z0), s0);
+        const uint32_t a3 = hmul2_bf16(hsub2_bf16(q3, z1), s1);
+#pragma unroll
+        for (int m = 0; m < kMT; ++m) {
+          // lane run element 4j+{0,1} -> b0, 4j+{2,3} -> b1
+          const uint32_t* xv = j < 2 ? &xf[u].lo[m].x : &xf[u].hi[m].x;
+          mma_bf16_16816(acc[m], a0, a1, a2, a3, xv[(j & 1) * 2], xv[(j & 1) * 2 + 1]);
         }
       }
+    }
+  };
+
+  // Meta words: when a ring slot is exactly one quantisation group (group 128 with kTG 2, group 64 with kTG 1) the
+  // row pointer just advances by N per slot; otherwise it is recomputed from the slot index.
+  const bool slot_is_group = (1 << gshift) == kTG;
+  const uint32_t* mp = mbase + (int64_t)(((s_begin + kDepth) * kTG) >> gshift) * N;   // next slot to prefetch
+  auto refill = [&](int i, int slot) {
+#pragma unroll
+    for (int u = 0; u < kTG; ++u) ring[i][u] = ldg_stream(wp + u * 32);
+    const uint32_t* mr = slot_is_group ? mp : mbase + (int64_t)((slot * kTG) >> gshift) * N;
+    ring_m0[i] = __ldg(mr);
+    ring_m1[i] = __ldg(mr + 8);
+  };
+
+  static_assert(kDepth % 2 == 0 || kDepth == 1, "x double buffer relies on an even ring depth");
+  XRing<kMT> xbuf[2][kTG];   // x fragments ping-pong one slot ahead (static parity: the loops are fully unrolled)
+  if (kPrefetchX && s_begin < s_end) load_xslot(xbuf[0]);
+
+  int sl = s_begin;
+  // full rounds: every ring slot is consumed, then (while data remains) refilled kDepth slots ahead
+  for (; sl + kDepth <= s_end; sl += kDepth) {
+#pragma unroll
+    for (int i = 0; i < kDepth; ++i) {
+      if (kPrefetchX) {
+        if (sl + i + 1 < s_end) load_xslot(xbuf[(i + 1) & 1]);
+      } else {
+        load_xslot(xbuf[i & 1]);
+      }
+      consume(ring[i], ring_m0[i], ring_m1[i], xbuf[i & 1]);
+      if (sl + i + kDepth < s_end) refill(i, sl + i + kDepth);
+      wp += kTG * 32;
+      mp += N;
+    }
+  }
+  // tail: fewer than kDepth slots left, all already in the ring
+#pragma unroll
+  for (int i = 0; i < kDepth; ++i) {
+    if (sl + i < s_end) {
+      if (kPrefetchX) {
+        if (sl + i + 1 < s_end) load_xslot(xbuf[(i + 1) & 1]);
+      } else {
+        load_xslot(xbuf[i & 1]);
+      }
+      consume(ring[i], ring_m0[i], ring_m1[i], xbuf[i & 1]);
     }
   }
   pdl_launch_dependents();
@@ -182,26 +236,26 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     return;
   } else {
 #pragma unroll
-  for (int m = 0; m < kMT; ++m) {
-    red[warp][m][g * 8 + 2 * t] = acc[m][0];
-    red[warp][m][g * 8 + 2 * t + 1] = acc[m][1];
-    red[warp][m][(g + 8) * 8 + 2 * t] = acc[m][2];
-    red[warp][m][(g + 8) * 8 + 2 * t + 1] = acc[m][3];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kTilesPerCta * kMT * 128; i += blockDim.x) {
-    const int tl = i / (kMT * 128), rem = i % (kMT * 128);
-    const int m = rem >> 7, r = (rem & 127) >> 3, c = rem & 7;
-    const int tok = m * 8 + c;
-    const int nt = blockIdx.x * kTilesPerCta + tl;
-    if (tok < M && nt < ntiles) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < kSplit; ++w) s += red[tl * kSplit + w][m][r * 8 + c];
-      if (bias) s += __bfloat162float(bias[nt * 16 + r]);
-      y[(int64_t)tok * y_stride + nt * 16 + r] = __float2bfloat16_rn(s);
+    for (int m = 0; m < kMT; ++m) {
+      red[warp][m][g * 8 + 2 * t] = acc[m][0];
+      red[warp][m][g * 8 + 2 * t + 1] = acc[m][1];
+      red[warp][m][(g + 8) * 8 + 2 * t] = acc[m][2];
+      red[warp][m][(g + 8) * 8 + 2 * t + 1] = acc[m][3];
     }
-  }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTilesPerCta * kMT * 128; i += blockDim.x) {
+      const int tl = i / (kMT * 128), rem = i % (kMT * 128);
+      const int m = rem >> 7, r = (rem & 127) >> 3, c = rem & 7;
+      const int tok = m * 8 + c;
+      const int nt = blockIdx.x * kTilesPerCta + tl;
+      if (tok < M && nt < ntiles) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < kSplit; ++w) sum += red[tl * kSplit + w][m][r * 8 + c];
+        if (bias) sum += __bfloat162float(bias[nt * 16 + r]);
+        y[(int64_t)tok * y_stride + nt * 16 + r] = __float2bfloat16_rn(sum);
+      }
+    }
   }
 }
 
@@ -304,11 +358,21 @@ extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
   const int ntiles = N / 16, ktiles = K / 64;
   int split = 1;
   while (split < 8 && ntiles * split < 148 * 16 && ktiles / (split * 2) >= 3) split *= 2;
-#define XB_W4_LAUNCH(MT, SP, DP)                                                                             \
-  {                                                                                                          \
-    dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                             \
-    XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, DP>, grid, block, 0, s, true, yy, y_stride, xx,    \
-                      x_stride, qw, meta, bb, M, N, K, group_size));                                         \
+  const int tpg = group_size / 64;   // k64 tiles per quantisation group
+  XB_CHECK((tpg & (tpg - 1)) == 0, "linear_w4a16_small_m: group_size/64 must be a power of two (got %d)", group_size);
+  int gshift = 0;
+  while ((1 << gshift) < tpg) ++gshift;
+  const bool tg2 = tpg >= 2;
+#define XB_W4_LAUNCH(MT, SP, DP)                                                                              \
+  {                                                                                                           \
+    dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                              \
+    if (tg2) {                                                                                                \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2>, grid, block, 0, s, true, yy,    \
+                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
+    } else {                                                                                                  \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, DP, 1>, grid, block, 0, s, true, yy, y_stride,    \
+                        xx, x_stride, qw, meta, bb, M, N, K, gshift));                                        \
+    }                                                                                                         \
   }
 #define XB_W4(MT, DP)                                   \
   switch (split) {                                      \
@@ -318,7 +382,7 @@ extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
     default: XB_W4_LAUNCH(MT, 8, DP) break;             \
   }
   if (M <= 8) XB_W4(1, 8)
-  else if (M <= 16) XB_W4(2, 6)
+  else if (M <= 16) XB_W4(2, 8)
   else if (M <= 32) XB_W4(4, 4)
   else XB_W4(8, 2)
 #undef XB_W4_LAUNCH

@@ -204,7 +204,8 @@ class Qwen2DecodeRunner:
         self.d2h_bytes = self.h_next.numel() * 4
 
     # -- one decode step worth of launches (capturable) -----------------------------------
-    def launch_step(self):
+    def launch_step(self, trace=None):
+        """trace (eager only): list that receives (layer_output, residual) clones after every decoder layer."""
         cfg, w = self.cfg, self.w
         qs, kvs = cfg.q_size, cfg.kv_size
         scale = cfg.head_dim ** -0.5
@@ -236,6 +237,8 @@ class Qwen2DecodeRunner:
             L["gate_up"].forward(o, self.gate_up)
             ops.act_and_mul(self.act, self.gate_up, "silu")
             x = L["down"].forward(self.act, self.buf_b)
+            if trace is not None:
+                trace.append((x.clone(), self.residual.clone()))
         ops.fused_add_rms_norm(x, self.residual, w.final_norm, cfg.rms_norm_eps)
         w.lm_head.forward(x, self.logits)
         ops.argmax(self.next_tokens, self.logits)
