@@ -177,9 +177,11 @@ def test_act_and_mul(T, d, mode, built_lib):
     ref = O.act_and_mul(x, mode)
     out = torch.empty(T, d, dtype=BF16, device=DEV)
     ops.act_and_mul(out, x.to(DEV), mode)
-    assert_close_bf16(out, ref, ulps=1, what=f"act_and_mul {mode}")   # reference's own test: allclose 5e-3
+    # two roundings (bf16(act) then the bf16 product): a 1-ulp difference of the device expf/erff/tanhf vs torch's
+    # in the first can become 2 ulps after the second.  The reference's own test uses allclose(5e-3).
+    assert_close_bf16(out, ref, ulps=2, what=f"act_and_mul {mode}")
     frac = (out.cpu() != ref).float().mean().item()
-    assert frac < 2e-3, f"{frac:.4f} of elements differ (expf vs torch.exp ulp)"
+    assert frac < 5e-3, f"{frac:.4f} of elements differ (device vs host transcendental ulp)"
 
 
 def test_act_and_mul_bad_mode(built_lib):

@@ -114,6 +114,16 @@ def bench_bf16(N, K, M=1):
     report(f"bf16 linear M={M} N={N} K={K}", timeit(fn, copies), nbytes, timeit_graph(fn, copies))
 
 
+if __name__ == "__main__" and len(sys.argv) > 1:
+    # profiling entry: `microbench.py w4 N K M` | `microbench.py decode B ctx`
+    if sys.argv[1] == "w4":
+        bench_w4(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    elif sys.argv[1] == "decode":
+        bench_decode(int(sys.argv[2]), int(sys.argv[3]))
+    elif sys.argv[1] == "bf16":
+        bench_bf16(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    sys.exit(0)
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), "peak", PEAK)
     bench_decode(1, 4096)

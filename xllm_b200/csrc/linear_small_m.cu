@@ -78,8 +78,8 @@ struct XRing {
 };
 
 template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth,
-          int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */>
-__global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : 2)
+          int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */, int kOcc = 2 /* CTAs per SM */>
+__global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : kOcc)
 linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
                             int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
                             const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int gshift /* log2(tiles per group) */) {
@@ -98,11 +98,16 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   const int s_begin = split * per;
   const int s_end = live ? min(nslots, s_begin + per) : s_begin;
 
-  float acc[kMT][4];
+  // kAcc independent accumulator sets (one per k16 step of a tile when registers allow): legacy HMMA has a long
+  // issue-to-result latency on sm_100, a single chain per warp leaves the scheduler with nothing eligible
+  constexpr int kAcc = kMT == 1 ? 4 : (kMT == 2 ? 2 : 1);
+  float accj[kAcc][kMT][4];
 #pragma unroll
-  for (int m = 0; m < kMT; ++m)
+  for (int a = 0; a < kAcc; ++a)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
+    for (int m = 0; m < kMT; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) accj[a][m][i] = 0.f;
 
   // running pointers (one 64-bit add per slot instead of a multiply per tile)
   const uint4* wp = qweight + ((int64_t)ntile * ktiles + (int64_t)s_begin * kTG) * 32 + lane;
@@ -133,23 +138,23 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     const int tok = min(m * 8 + g, M - 1);
     xp[m] = x + (int64_t)tok * x_stride + (int64_t)s_begin * kTG * 64 + 16 * t;
   }
-  constexpr bool kPrefetchX = kMT <= 2;   // wider token tiles have no registers to spare
-  auto load_xslot = [&](XRing<kMT> (&d)[kTG]) {
+  // x fragments come from L1 (~35 cycles), hidden by the other warps: registers go to occupancy instead of an x ring
+  auto load_xtile = [&](XRing<kMT>& d) {
 #pragma unroll
-    for (int u = 0; u < kTG; ++u)
-#pragma unroll
-      for (int m = 0; m < kMT; ++m) {
-        d[u].lo[m] = *reinterpret_cast<const uint4*>(xp[m] + u * 64);
-        d[u].hi[m] = *reinterpret_cast<const uint4*>(xp[m] + u * 64 + 8);
-      }
-#pragma unroll
-    for (int m = 0; m < kMT; ++m) xp[m] += kTG * 64;
+    for (int m = 0; m < kMT; ++m) {
+      d.lo[m] = *reinterpret_cast<const uint4*>(xp[m]);
+      d.hi[m] = *reinterpret_cast<const uint4*>(xp[m] + 8);
+      xp[m] += 64;
+    }
   };
-  auto consume = [&](const uint4 (&wq)[kTG], uint32_t mt0, uint32_t mt1, const XRing<kMT> (&xf)[kTG]) {
+
+  auto consume = [&](const uint4 (&wq)[kTG], uint32_t mt0, uint32_t mt1) {
     const uint32_t s0 = __byte_perm(mt0, 0, 0x1010), z0 = __byte_perm(mt0, 0, 0x3232);
     const uint32_t s1 = __byte_perm(mt1, 0, 0x1010), z1 = __byte_perm(mt1, 0, 0x3232);
 #pragma unroll
     for (int u = 0; u < kTG; ++u) {
+      XRing<kMT> xf;
+      load_xtile(xf);
       const uint32_t* wv = &wq[u].x;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -165,8 +170,8 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 #pragma unroll
         for (int m = 0; m < kMT; ++m) {
           // lane run element 4j+{0,1} -> b0, 4j+{2,3} -> b1
-          const uint32_t* xv = j < 2 ? &xf[u].lo[m].x : &xf[u].hi[m].x;
-          mma_bf16_16816(acc[m], a0, a1, a2, a3, xv[(j & 1) * 2], xv[(j & 1) * 2 + 1]);
+          const uint32_t* xv = j < 2 ? &xf.lo[m].x : &xf.hi[m].x;
+          mma_bf16_16816(accj[j % kAcc][m], a0, a1, a2, a3, xv[(j & 1) * 2], xv[(j & 1) * 2 + 1]);
         }
       }
     }
@@ -184,21 +189,13 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     ring_m1[i] = __ldg(mr + 8);
   };
 
-  static_assert(kDepth % 2 == 0 || kDepth == 1, "x double buffer relies on an even ring depth");
-  XRing<kMT> xbuf[2][kTG];   // x fragments ping-pong one slot ahead (static parity: the loops are fully unrolled)
-  if (kPrefetchX && s_begin < s_end) load_xslot(xbuf[0]);
 
   int sl = s_begin;
   // full rounds: every ring slot is consumed, then (while data remains) refilled kDepth slots ahead
   for (; sl + kDepth <= s_end; sl += kDepth) {
 #pragma unroll
     for (int i = 0; i < kDepth; ++i) {
-      if (kPrefetchX) {
-        if (sl + i + 1 < s_end) load_xslot(xbuf[(i + 1) & 1]);
-      } else {
-        load_xslot(xbuf[i & 1]);
-      }
-      consume(ring[i], ring_m0[i], ring_m1[i], xbuf[i & 1]);
+      consume(ring[i], ring_m0[i], ring_m1[i]);
       if (sl + i + kDepth < s_end) refill(i, sl + i + kDepth);
       wp += kTG * 32;
       mp += N;
@@ -208,15 +205,20 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 #pragma unroll
   for (int i = 0; i < kDepth; ++i) {
     if (sl + i < s_end) {
-      if (kPrefetchX) {
-        if (sl + i + 1 < s_end) load_xslot(xbuf[(i + 1) & 1]);
-      } else {
-        load_xslot(xbuf[i & 1]);
-      }
-      consume(ring[i], ring_m0[i], ring_m1[i], xbuf[i & 1]);
+      consume(ring[i], ring_m0[i], ring_m1[i]);
     }
   }
   pdl_launch_dependents();
+  float acc[kMT][4];
+#pragma unroll
+  for (int m = 0; m < kMT; ++m)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v = accj[0][m][i];
+#pragma unroll
+      for (int a = 1; a < kAcc; ++a) v += accj[a][m][i];
+      acc[m][i] = v;
+    }
 
   // c0:(row g, tok 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
   if constexpr (kSplit == 1) {
@@ -363,10 +365,14 @@ extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
   int gshift = 0;
   while ((1 << gshift) < tpg) ++gshift;
   const bool tg2 = tpg >= 2;
+  static const bool occ3 = [] { const char* e = getenv("XB_W4_OCC"); return e && atoi(e) == 3; }();
 #define XB_W4_LAUNCH(MT, SP, DP)                                                                              \
   {                                                                                                           \
     dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                              \
-    if (tg2) {                                                                                                \
+    if (tg2 && MT == 1 && occ3) {                                                                             \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2, 3>, grid, block, 0, s, true, yy, \
+                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
+    } else if (tg2) {                                                                                         \
       XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2>, grid, block, 0, s, true, yy,    \
                         y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
     } else {                                                                                                  \

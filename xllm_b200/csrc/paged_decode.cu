@@ -313,32 +313,58 @@ paged_decode_kernel(const DecodeParams p) {
   if (s_ticket != n_splits - 1) return;
   __threadfence();
   if (threadIdx.x == 0) *counter = 0;  // restore for the next launch
+  // Stage 1: one warp per head turns the splits' base-2 LSEs into normalised weights in shared memory
+  // (lanes read different splits in parallel: no dependent-load chain).  sm_o is free again: reuse it.
+  float* sm_w = sm_o;                       // [kHeads][n_splits]
+  float* sm_lse = sm_m;                     // [kHeads] merged LSE
+  __syncthreads();
+  for (int h = warp; h < nheads; h += kWarpsT) {
+    const int64_t base = ((int64_t)b * p.num_qo_heads + head0 + h) * p.max_splits;
+    float mx = -INFINITY;
+    for (int s = lane; s < n_splits; s += 32) mx = fmaxf(mx, __ldcg(p.part_lse + base + s));
+    mx = warp_max(mx);
+    const float m_safe = mx == -INFINITY ? 0.f : mx;
+    float wsum = 0.f;
+    for (int s = lane; s < n_splits; s += 32) {
+      const float w = exp2f(__ldcg(p.part_lse + base + s) - m_safe);
+      sm_w[h * n_splits + s] = w;
+      wsum += w;
+    }
+    wsum = warp_sum(wsum);
+    const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
+    for (int s = lane; s < n_splits; s += 32) sm_w[h * n_splits + s] *= inv;
+    if (lane == 0) sm_lse[h] = wsum > 0.f ? mx + log2f(wsum) : -INFINITY;
+  }
+  __syncthreads();
+  // Stage 2: weighted sum of the partial outputs; all addresses are known up front, 8 loads in flight per thread
   for (int it = threadIdx.x; it < kItems; it += kWarpsT * 32) {
     const int h = it / (kD / 4), d4 = (it % (kD / 4)) * 4;
     if (h >= nheads) continue;
     const int qh = head0 + h;
-    const int64_t base = ((int64_t)b * p.num_qo_heads + qh) * p.max_splits;
-    float m_tot = -INFINITY;
-    for (int s = 0; s < n_splits; ++s) m_tot = fmaxf(m_tot, __ldcg(p.part_lse + base + s));
-    const float m_safe = m_tot == -INFINITY ? 0.f : m_tot;
+    const float4* src = reinterpret_cast<const float4*>(p.part_o + (((int64_t)b * p.num_qo_heads + qh) * p.max_splits) * kD + d4);
+    const float* wrow = sm_w + h * n_splits;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float wsum = 0.f;
-#pragma unroll 4
-    for (int s = 0; s < n_splits; ++s) {
-      const float w = exp2f(__ldcg(p.part_lse + base + s) - m_safe);
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part_o + (base + s) * kD + d4));
-      wsum += w;
-      acc.x += v.x * w;
-      acc.y += v.y * w;
-      acc.z += v.z * w;
-      acc.w += v.w * w;
+    int s = 0;
+    for (; s + 8 <= n_splits; s += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(s + u) * (kD / 4));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float w = wrow[s + u];
+        acc.x += v[u].x * w; acc.y += v[u].y * w; acc.z += v[u].z * w; acc.w += v[u].w * w;
+      }
     }
-    const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
+    for (; s < n_splits; ++s) {
+      const float4 v = __ldcg(src + (int64_t)s * (kD / 4));
+      const float w = wrow[s];
+      acc.x += v.x * w; acc.y += v.y * w; acc.z += v.z * w; acc.w += v.w * w;
+    }
     uint2 ob;
-    ob.x = pack_bf16x2(acc.x * inv, acc.y * inv);
-    ob.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+    ob.x = pack_bf16x2(acc.x, acc.y);
+    ob.y = pack_bf16x2(acc.z, acc.w);
     *reinterpret_cast<uint2*>(p.o + (int64_t)b * p.o_stride_n + (int64_t)qh * p.o_stride_h + d4) = ob;
-    if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = wsum > 0.f ? m_tot + log2f(wsum) : -INFINITY;
+    if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = sm_lse[h];
   }
 }
 
@@ -387,7 +413,12 @@ extern "C" int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int n
   if (chunk < 64) chunk = 64;
   const char* env = getenv("XB_DECODE_CHUNK");
   if (env && atoi(env) >= 16) chunk = (atoi(env) / 16) * 16;
-  const int64_t splits = (max_kv + chunk - 1) / chunk;
+  int64_t splits = (max_kv + chunk - 1) / chunk;
+  const int64_t max_splits = 2 * head_dim;   // merge buffer in shared memory
+  if (splits > max_splits) {
+    chunk = (((max_kv + max_splits - 1) / max_splits + 15) / 16) * 16;
+    splits = (max_kv + chunk - 1) / chunk;
+  }
   plan8[0] = chunk;
   plan8[1] = splits;
   plan8[2] = splits > 1 ? (int64_t)batch * num_qo_heads * splits * (head_dim + 1) * 4 : 16;
@@ -434,6 +465,7 @@ extern "C" int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t
              reinterpret_cast<uintptr_t>(v_cache)) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 7) == 0,
            "paged_decode: q/k_cache/v_cache must be 16-byte aligned");
   XB_CHECK(p.max_splits == 1 || (workspace_f32 && workspace_i32), "paged_decode: split-KV needs both workspaces");
+  XB_CHECK(p.max_splits <= 2 * head_dim, "paged_decode: %d KV splits exceed the merge buffer (max %d)", p.max_splits, 2 * head_dim);
   p.q = reinterpret_cast<const __nv_bfloat16*>(q);
   p.q_stride_n = q_stride_n;
   p.q_stride_h = q_stride_h;
