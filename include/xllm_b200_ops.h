@@ -198,6 +198,24 @@ int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
 /* host-side packer (plain C, no CUDA): q[N,K] uint8 (0..15) -> qweight tiles. */
 int xb_w4_pack_rows(uint32_t* qweight_out, const uint8_t* q, int N, int K);
 
+/* ---- tcgen05 GEMMs for prefill-sized M (any M; TMA zero-fills ragged edges) ---------------------
+ * C[M,N] = A[M,K] . B[N,K]^T (+ bias), fp32 accumulation in TMEM, bf16 output.
+ * bf16:  replaces xllm::kernel::cuda::matmul (cuda_ops_api.h:167-169, matmul.cpp:20-24 -> F::linear).
+ * fp8:   replaces xllm::kernel::cuda::cutlass_scaled_mm (cuda_ops_api.h:171-176,
+ *        cutlass_w8a8/scaled_mm_entry.cu:55-108): a,b e4m3 [M,K] / [N,K] (b is the reference's b.t() view),
+ *        C = a_scale * (b_scale * acc) (+ bias); scales fp32 with numel 1 (per-tensor) or M / N.
+ * w4a16: the weight-only GEMM: same packed operands as xb_linear_w4a16_small_m, int4->bf16
+ *        unpack fused into the tcgen05 main loop. */
+int xb_gemm_bf16(void* c, int64_t ldc, const void* a, int64_t lda, const void* b,
+                 const void* bias, int M, int N, int K, xb_stream_t stream);
+int xb_gemm_fp8_scaled(void* c, int64_t ldc, const void* a_e4m3, int64_t lda,
+                       const void* b_e4m3, const float* a_scale, int a_scale_numel,
+                       const float* b_scale, int b_scale_numel, const void* bias,
+                       int M, int N, int K, xb_stream_t stream);
+int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda,
+                  const uint32_t* qweight, const uint32_t* meta, const void* bias,
+                  int M, int N, int K, int group_size, xb_stream_t stream);
+
 /* ---- step boundary helpers ---------------------------------------------------
  * embedding row gather (WordEmbeddingImpl::forward, layers/common/word_embedding_impl.cpp:33-56,
  * TP=1) and greedy argmax over logits rows (ties -> lowest index). */

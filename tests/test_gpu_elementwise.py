@@ -179,7 +179,9 @@ def test_act_and_mul(T, d, mode, built_lib):
     ops.act_and_mul(out, x.to(DEV), mode)
     # two roundings (bf16(act) then the bf16 product): a 1-ulp difference of the device expf/erff/tanhf vs torch's
     # in the first can become 2 ulps after the second.  The reference's own test uses allclose(5e-3).
-    assert_close_bf16(out, ref, ulps=2, what=f"act_and_mul {mode}")
+    # gelu: 1 + erf(x/sqrt2) cancels for x << 0, so outputs of magnitude ~1e-6 carry the ABSOLUTE error of erff
+    # (~6e-8), i.e. many bf16 ulps of a value that small: an absolute floor of 1e-5 (inputs are O(1)) covers it.
+    assert_close_bf16(out, ref, ulps=2, what=f"act_and_mul {mode}", atol=1e-5 if mode != "silu" else 0.0)
     frac = (out.cpu() != ref).float().mean().item()
     assert frac < 5e-3, f"{frac:.4f} of elements differ (device vs host transcendental ulp)"
 

@@ -114,6 +114,33 @@ def bench_bf16(N, K, M=1):
     report(f"bf16 linear M={M} N={N} K={K}", timeit(fn, copies), nbytes, timeit_graph(fn, copies))
 
 
+def bench_gemm(kind, M, N, K, gs=128):
+    E4M3 = torch.float8_e4m3fn
+    if kind == "bf16":
+        a = torch.randn(M, K, device=DEV, dtype=BF16)
+        w = torch.randn(N, K, device=DEV, dtype=BF16)
+        fn = lambda i: ops.gemm_bf16(a, w, None, y)
+    elif kind == "fp8":
+        a = torch.randn(M, K, device=DEV).to(E4M3)
+        w = torch.randn(N, K, device=DEV).to(E4M3)
+        s1 = torch.ones(1, device=DEV)
+        fn = lambda i: ops.cutlass_scaled_mm(y, a, w.t(), s1, s1)
+    elif kind == "w4":
+        a = torch.randn(M, K, device=DEV, dtype=BF16)
+        qw = torch.randint(-2**31, 2**31 - 1, (N // 16, K // 64, 32, 4), dtype=torch.int32, device=DEV)
+        sb = (torch.rand(K // gs, N, device=DEV) * 0.01 + 0.001).to(BF16).view(torch.int16).to(torch.int32) & 0xFFFF
+        meta = (sb | (0x4308 << 16)).contiguous()
+        fn = lambda i: ops.gemm_w4a16(a, qw, meta, gs, None, y)
+    elif kind == "torch":
+        a = torch.randn(M, K, device=DEV, dtype=BF16)
+        w = torch.randn(N, K, device=DEV, dtype=BF16)
+        fn = lambda i: torch.matmul(a, w.t(), out=y)
+    y = torch.empty(M, N, device=DEV, dtype=BF16)
+    us = timeit(fn, 1, iters=20, warm=3)
+    tf = 2.0 * M * N * K / us / 1e6
+    print(f"gemm {kind:5s} M={M:6d} N={N:6d} K={K:6d}  {us:9.1f} us  {tf:8.1f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__" and len(sys.argv) > 1:
     # profiling entry: `microbench.py w4 N K M` | `microbench.py decode B ctx`
     if sys.argv[1] == "w4":
@@ -122,6 +149,10 @@ if __name__ == "__main__" and len(sys.argv) > 1:
         bench_decode(int(sys.argv[2]), int(sys.argv[3]))
     elif sys.argv[1] == "bf16":
         bench_bf16(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    elif sys.argv[1] == "gemm":
+        for kind in sys.argv[2].split(","):
+            for M, N, K in [(2048, 4608, 3584), (2048, 37888, 3584), (2048, 3584, 18944), (8192, 37888, 3584), (8192, 8192, 8192)]:
+                bench_gemm(kind, M, N, K)
     sys.exit(0)
 
 if __name__ == "__main__":

@@ -1,0 +1,421 @@
+// tcgen05 / TMEM / TMA GEMM for the prefill-sized linears:  C[M,N] = A[M,K] . B[N,K]^T (+bias)
+//   kind BF16 : A, B bf16 (K-major, as the reference stores activations [T,in] and weights [out,in])
+//               replaces xllm::kernel::cuda::matmul -> F::linear (kernels/cuda/matmul.cpp:20-24)
+//   kind FP8  : A, B e4m3, C = a_scale * (b_scale * acc) + bias, per-tensor or per-token / per-channel scales
+//               replaces cutlass_scaled_mm (cutlass_w8a8/scaled_mm_entry.cu:55-108, c3x/scaled_mm_sm100_fp8_dispatch.cuh)
+//   kind W4   : B is the tile-packed int4 weight of linear_small_m.cu; 4 converter warps dequantise
+//               bf16((q-z)*s) (bit-exact with the spec) straight into the 128B-swizzled K-major stage buffer the
+//               MMA reads, so the unpack is fused into the tcgen05 main loop (no bf16 copy of W ever exists in HBM).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer (A tiles, and B tiles / packed-B bulk copies), one elected lane
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1, 128 x BLOCK_N x 16 (x32 for fp8) per instruction, one elected lane;
+//               owns the TMEM allocation (2 accumulator stages so the epilogue of tile i overlaps tile i+1)
+//   warps 2..5  epilogue: tcgen05.ld 32x32b -> scale/bias -> bf16 -> global   (warp w owns TMEM lanes 32*(w%4)..)
+//   warps 6..9  (W4 only) converters: packed smem -> LOP3/HSUB2/HMUL2 -> swizzled bf16 smem -> fence.proxy.async
+// Pipelines are mbarrier rings: smem full/empty (TMA <-> MMA), packed full / B ready (TMA <-> converters <-> MMA),
+// TMEM full/empty (MMA <-> epilogue).
+#include "tc_common.cuh"
+
+namespace xb {
+namespace tc {
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_rows,
+                 uint32_t box_cols, int elem_bytes) {
+  EncodeTiledFn enc = get_encode_tiled();
+  XB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu pitch %llu)", (int)r,
+           (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_bytes);
+  return 0;
+}
+
+enum { kKindBF16 = 0, kKindFP8 = 1, kKindW4 = 2 };
+
+struct GemmParams {
+  __nv_bfloat16* c;
+  int64_t ldc;
+  const __nv_bfloat16* bias;   // [N] or null
+  const float* a_scale;        // fp8: [1] or [M]
+  const float* b_scale;        // fp8: [1] or [N]
+  int a_scale_per_row, b_scale_per_col;
+  // W4
+  const uint4* qweight;        // tile-packed [N/16][K/64][32]
+  const uint32_t* meta;        // [K/g][N]
+  int gshift;                  // log2(k64 tiles per quantisation group)
+  int M, N, K;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kNumEpiWarps = 4;
+
+template <int kKind, int kBlockN>
+struct GemmCfg {
+  static constexpr int kElemA = kKind == kKindFP8 ? 1 : 2;
+  static constexpr int kBlockK = 128 / kElemA;                     // one 128-byte swizzle row per tile row
+  static constexpr int kUmmaK = 32 / kElemA;                       // 16 (bf16) / 32 (fp8) elements = 32 bytes
+  static constexpr int kABytes = kBlockM * 128;
+  static constexpr int kBBytes = kBlockN * 128;
+  static constexpr int kPackedBytes = kKind == kKindW4 ? kBlockN * kBlockK / 2 : 0;   // int4 tile
+  static constexpr int kMetaBytes = kKind == kKindW4 ? kBlockN * 4 : 0;
+  static constexpr int kStageBytes = kABytes + kBBytes + kPackedBytes + ((kMetaBytes + 1023) / 1024) * 1024;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kThreads = (2 + kNumEpiWarps + (kKind == kKindW4 ? 4 : 0)) * 32;
+  static constexpr int kTmemCols = 2 * kBlockN;                    // two accumulator stages
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int kKind, int kBlockN>
+__global__ void __launch_bounds__(GemmCfg<kKind, kBlockN>::kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<kKind, kBlockN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_mem = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_mem);          // [kStages] TMA -> MMA (A, and B for BF16/FP8)
+  uint64_t* empty_bar = full_bar + kStages;                           // [kStages] MMA -> TMA
+  uint64_t* packed_bar = empty_bar + kStages;                         // [kStages] TMA -> converters (W4)
+  uint64_t* bready_bar = packed_bar + kStages;                        // [kStages] converters -> MMA (W4)
+  uint64_t* tmem_full = bready_bar + kStages;                         // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                               // [2]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blocks = (p.M + kBlockM - 1) / kBlockM;
+  const int n_blocks = (p.N + kBlockN - 1) / kBlockN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_kb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;
+
+  auto stage_a = [&](int s) { return smem + s * Cfg::kStageBytes; };
+  auto stage_b = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes; };
+  auto stage_packed = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes + Cfg::kBBytes; };
+  auto stage_meta = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes + Cfg::kBBytes + Cfg::kPackedBytes; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+      mbar_init(packed_bar + s, 1);
+      mbar_init(bready_bar + s, 4);          // one elected arrive per converter warp
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full + s, 1);
+      mbar_init(tmem_empty + s, kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    if (kKind != kKindW4) tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  pdl_launch_dependents();
+  pdl_wait();   // A (activations) comes from the producer kernel
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % m_blocks, n_blk = tile / m_blocks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + s, ph ^ 1);
+          if (kKind == kKindW4) {
+            // packed B: kBlockN/16 row tiles, each (row tile, k tile) block is 512 contiguous bytes; plus the group's
+            // scale/zero words for these kBlockN rows
+            const int ktiles = p.K >> 6;
+            mbar_expect_tx(packed_bar + s, Cfg::kPackedBytes + Cfg::kMetaBytes);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.qweight);
+#pragma unroll 1
+            for (int r = 0; r < kBlockN / 16; ++r) {
+              const int64_t ntile = (int64_t)n_blk * (kBlockN / 16) + r;
+              bulk_load(stage_packed(s) + r * 512, src + (ntile * ktiles + kb) * 512, 512, packed_bar + s);
+            }
+            bulk_load(stage_meta(s), p.meta + (int64_t)(kb >> p.gshift) * p.N + (int64_t)n_blk * kBlockN, Cfg::kMetaBytes,
+                      packed_bar + s);
+            mbar_expect_tx(full_bar + s, Cfg::kABytes);
+            tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, m_blk * kBlockM);
+          } else {
+            mbar_expect_tx(full_bar + s, Cfg::kABytes + Cfg::kBBytes);
+            tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, m_blk * kBlockM);
+            tma_load_2d(stage_b(s), &tmap_b, full_bar + s, kb * Cfg::kBlockK, n_blk * kBlockN);
+          }
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    constexpr uint32_t idesc = kKind == kKindFP8 ? umma_idesc(0, 0, kBlockM, kBlockN) : umma_idesc(1, 1, kBlockM, kBlockN);
+    int s = 0;
+    uint32_t ph = 0;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tmem_empty + as, aph ^ 1);     // epilogue has drained this accumulator stage
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + as * kBlockN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar + s, ph);
+        if (kKind == kKindW4) mbar_wait(bready_bar + s, ph);
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(stage_a(s)), b_addr = smem_u32(stage_b(s));
+#pragma unroll
+          for (int k = 0; k < Cfg::kBlockK / Cfg::kUmmaK; ++k) {
+            const uint64_t da = umma_desc_sw128(a_addr + k * 32), db = umma_desc_sw128(b_addr + k * 32);
+            if (kKind == kKindFP8) umma_f8(d_tmem, da, db, idesc, (kb | k) != 0);
+            else umma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar + s);                 // smem slot is free once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(tmem_full + as);
+        }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else if (warp < 2 + kNumEpiWarps) {
+    // ======================= epilogue =======================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may read
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % m_blocks, n_blk = tile / m_blocks;
+      mbar_wait(tmem_full + as, aph);
+      tc_fence_after_sync();
+      const int row = m_blk * kBlockM + q * 32 + lane;
+      float a_s = 1.f;
+      if (kKind == kKindFP8) a_s = p.a_scale[p.a_scale_per_row ? min(row, p.M - 1) : 0];
+#pragma unroll 1
+      for (int c = 0; c < kBlockN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * kBlockN + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * kBlockN + c * 32;
+        if (row < p.M && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            const int col = col0 + j;
+            if (kKind == kKindFP8) {
+              const float b_s = p.b_scale[p.b_scale_per_col ? min(col, p.N - 1) : 0];
+              x = a_s * (b_s * x);                 // ScaledEpilogue order: scale_a * (scale_b * acc)
+            }
+            if (p.bias) x += __bfloat162float(p.bias[min(col, p.N - 1)]);
+            v[j] = x;
+          }
+          __nv_bfloat16* dst = p.c + (int64_t)row * p.ldc + col0;
+          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              reinterpret_cast<uint4*>(dst)[j] = o;
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + as);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else if (kKind == kKindW4) {
+    // ======================= W4 converters (warps 6..9) =======================
+    // converter warp cw handles row tiles cw, cw+4, ... of the stage; a lane's 16 bytes of packed data are
+    // rows (g, g+8) x k in [16t, 16t+16) of its row tile  ->  four 16-byte chunks of the swizzled bf16 tile.
+    const int cw = warp - (2 + kNumEpiWarps);
+    const int g = lane >> 2, t = lane & 3;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(packed_bar + s, ph);          // packed tile + meta landed
+        // the bf16 B buffer of this stage is free: the producer only refills `packed` after empty_bar, which the
+        // MMA commits after reading B; packed_bar completing therefore implies B(s) is free as well
+        const uint8_t* pk = stage_packed(s);
+        const uint32_t* mt = reinterpret_cast<const uint32_t*>(stage_meta(s));
+        uint8_t* bt = stage_b(s);
+#pragma unroll
+        for (int r = cw; r < kBlockN / 16; r += 4) {
+          const uint4 wq = *reinterpret_cast<const uint4*>(pk + r * 512 + lane * 16);
+          const uint32_t m0 = mt[r * 16 + g], m1 = mt[r * 16 + g + 8];
+          const uint32_t s0 = __byte_perm(m0, 0, 0x1010), z0 = __byte_perm(m0, 0, 0x3232);
+          const uint32_t s1 = __byte_perm(m1, 0, 0x1010), z1 = __byte_perm(m1, 0, 0x3232);
+          uint32_t lo[8], hi[8];   // row g / row g+8: 16 bf16 = 8 packed registers, k ascending
+          const uint32_t* wv = &wq.x;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w = wv[j];
+            uint32_t q0, q1, q2, q3;
+            asm("lop3.b32 %0, %1, 0x000f000f, 0x43004300, 0xea;" : "=r"(q0) : "r"(w));
+            asm("lop3.b32 %0, %1, 0x000f000f, 0x43004300, 0xea;" : "=r"(q1) : "r"(w >> 4));
+            asm("lop3.b32 %0, %1, 0x000f000f, 0x43004300, 0xea;" : "=r"(q2) : "r"(w >> 8));
+            asm("lop3.b32 %0, %1, 0x000f000f, 0x43004300, 0xea;" : "=r"(q3) : "r"(w >> 12));
+            uint32_t d;
+            asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(q0), "r"(z0));
+            asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(lo[2 * j]) : "r"(d), "r"(s0));
+            asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(q2), "r"(z0));
+            asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(lo[2 * j + 1]) : "r"(d), "r"(s0));
+            asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(q1), "r"(z1));
+            asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(hi[2 * j]) : "r"(d), "r"(s1));
+            asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(q3), "r"(z1));
+            asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(hi[2 * j + 1]) : "r"(d), "r"(s1));
+          }
+          // swizzled K-major tile: row n at n*128 bytes, 16-byte chunk c stored at chunk (c ^ (n & 7))
+          const int n_lo = r * 16 + g, n_hi = n_lo + 8;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = 2 * t + h;
+            *reinterpret_cast<uint4*>(bt + n_lo * 128 + ((c ^ (n_lo & 7)) << 4)) =
+                make_uint4(lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
+            *reinterpret_cast<uint4*>(bt + n_hi * 128 + ((c ^ (n_hi & 7)) << 4)) =
+                make_uint4(hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
+          }
+        }
+        fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bready_bar + s);
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int kKind, int kBlockN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<kKind, kBlockN>;
+  auto kern = gemm_tcgen05_kernel<kKind, kBlockN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  static int num_sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const int tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + kBlockN - 1) / kBlockN);
+  dim3 grid(tiles < num_sms ? tiles : num_sms), block(Cfg::kThreads);
+  XB_CUDA_OK(launch(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, ta, tb, p));
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace xb
+
+using namespace xb;
+using namespace xb::tc;
+
+// pick BLOCK_N so that small problems still spread over the SMs (the reference buckets by M the same way:
+// scaled_mm_sm100_fp8_dispatch.cuh:148-287)
+static int pick_block_n(int M, int N) {
+  const int m_blocks = (M + kBlockM - 1) / kBlockM;
+  if ((int64_t)m_blocks * ((N + 127) / 128) >= 120) return 128;
+  return 64;
+}
+
+extern "C" int xb_gemm_bf16(void* c, int64_t ldc, const void* a, int64_t lda, const void* b, const void* bias, int M, int N,
+                            int K, xb_stream_t stream) {
+  if (M == 0 || N == 0) return 0;
+  XB_CHECK(K % 8 == 0 && lda % 8 == 0, "gemm_bf16: K=%d and lda=%lld must be multiples of 8 (16-byte rows for TMA)", K,
+           (long long)lda);
+  XB_CHECK((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0, "gemm_bf16: a/b alignment");
+  GemmParams p{};
+  p.c = reinterpret_cast<__nv_bfloat16*>(c);
+  p.ldc = ldc;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.M = M; p.N = N; p.K = K;
+  const int bn = pick_block_n(M, N);
+  CUtensorMap ta, tb;
+  if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, kBlockM, 64, 2)) return 1;
+  if (make_tmap_2d(&tb, b, N, K, (uint64_t)K * 2, bn, 64, 2)) return 1;
+  return bn == 128 ? launch_gemm<kKindBF16, 128>(ta, tb, p, (cudaStream_t)stream)
+                   : launch_gemm<kKindBF16, 64>(ta, tb, p, (cudaStream_t)stream);
+}
+
+extern "C" int xb_gemm_fp8_scaled(void* c, int64_t ldc, const void* a, int64_t lda, const void* b, const float* a_scale,
+                                  int a_scale_numel, const float* b_scale, int b_scale_numel, const void* bias, int M, int N,
+                                  int K, xb_stream_t stream) {
+  if (M == 0 || N == 0) return 0;
+  // same argument checks as cutlass_scaled_mm (scaled_mm_entry.cu:62-85)
+  XB_CHECK(K % 16 == 0 && lda % 16 == 0, "cutlass_scaled_mm: K=%d / lda=%lld must be multiples of 16", K, (long long)lda);
+  XB_CHECK(ldc % 8 == 0, "cutlass_scaled_mm: c.stride(0) %% 16 bytes != 0");
+  XB_CHECK(a_scale_numel == 1 || a_scale_numel == M, "cutlass_scaled_mm: a_scales must have numel 1 or M");
+  XB_CHECK(b_scale_numel == 1 || b_scale_numel == N, "cutlass_scaled_mm: b_scales must have numel 1 or N");
+  GemmParams p{};
+  p.c = reinterpret_cast<__nv_bfloat16*>(c);
+  p.ldc = ldc;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.a_scale = a_scale; p.b_scale = b_scale;
+  p.a_scale_per_row = a_scale_numel > 1; p.b_scale_per_col = b_scale_numel > 1;
+  p.M = M; p.N = N; p.K = K;
+  const int bn = pick_block_n(M, N);
+  CUtensorMap ta, tb;
+  if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda, kBlockM, 128, 1)) return 1;
+  if (make_tmap_2d(&tb, b, N, K, (uint64_t)K, bn, 128, 1)) return 1;
+  return bn == 128 ? launch_gemm<kKindFP8, 128>(ta, tb, p, (cudaStream_t)stream)
+                   : launch_gemm<kKindFP8, 64>(ta, tb, p, (cudaStream_t)stream);
+}
+
+extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, const uint32_t* qweight, const uint32_t* meta,
+                             const void* bias, int M, int N, int K, int group_size, xb_stream_t stream) {
+  if (M == 0 || N == 0) return 0;
+  XB_CHECK(N % 64 == 0 && K % 64 == 0, "gemm_w4a16: N=%d and K=%d must be multiples of 64", N, K);
+  XB_CHECK(group_size >= 64 && K % group_size == 0, "gemm_w4a16: bad group_size %d", group_size);
+  const int tpg = group_size / 64;
+  XB_CHECK((tpg & (tpg - 1)) == 0, "gemm_w4a16: group_size/64 must be a power of two");
+  XB_CHECK(lda % 8 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0, "gemm_w4a16: a alignment");
+  GemmParams p{};
+  p.c = reinterpret_cast<__nv_bfloat16*>(c);
+  p.ldc = ldc;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.qweight = reinterpret_cast<const uint4*>(qweight);
+  p.meta = meta;
+  p.gshift = 0;
+  while ((1 << p.gshift) < tpg) ++p.gshift;
+  p.M = M; p.N = N; p.K = K;
+  int bn = pick_block_n(M, N);
+  if (N % 128 != 0) bn = 64;
+  CUtensorMap ta;
+  if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, kBlockM, 64, 2)) return 1;
+  return bn == 128 ? launch_gemm<kKindW4, 128>(ta, ta, p, (cudaStream_t)stream)
+                   : launch_gemm<kKindW4, 64>(ta, ta, p, (cudaStream_t)stream);
+}

@@ -265,3 +265,86 @@ def argmax(out, logits) -> None:
     _need(out.dtype == torch.int32, "out must be int32")
     check(lib().xb_argmax_bf16(_p(out), _p(logits), c_i64(logits.stride(0)), c_i32(logits.size(0)),
                                c_i32(logits.size(1)), _stream()), "argmax")
+
+
+# ---- tcgen05 GEMMs ---------------------------------------------------------------
+def matmul(a, b, bias=None, out=None):
+    """xllm::kernel::cuda::matmul (cuda_ops_api.h:167-169): F::linear(a, b, bias); a [M,K], b [N,K] bf16.
+    M <= 16 streams the weight once through the small-M kernel; larger M runs the tcgen05 GEMM."""
+    _cuda_bf16(a, "a"); _cuda_bf16(b, "b")
+    M, K = a.shape
+    N = b.size(0)
+    _need(b.is_contiguous() and a.stride(1) == 1, "a/b layout")
+    y = out if out is not None else torch.empty(M, N, dtype=BF16, device=a.device)
+    if M <= 16 and K % 32 == 0:
+        return matmul_small_m(a, b, bias, y)
+    check(lib().xb_gemm_bf16(_p(y), c_i64(y.stride(0)), _p(a), c_i64(a.stride(0)), _p(b), _p(bias), c_i32(M), c_i32(N),
+                             c_i32(K), _stream()), "matmul")
+    return y
+
+
+def gemm_bf16(a, b, bias=None, out=None):
+    """always the tcgen05 kernel (tests / benchmarks)."""
+    _cuda_bf16(a, "a"); _cuda_bf16(b, "b")
+    M, K = a.shape
+    N = b.size(0)
+    y = out if out is not None else torch.empty(M, N, dtype=BF16, device=a.device)
+    check(lib().xb_gemm_bf16(_p(y), c_i64(y.stride(0)), _p(a), c_i64(a.stride(0)), _p(b), _p(bias), c_i32(M), c_i32(N),
+                             c_i32(K), _stream()), "gemm_bf16")
+    return y
+
+
+def cutlass_scaled_mm(c, a, b, a_scales, b_scales, bias=None) -> None:
+    """xllm::kernel::cuda::cutlass_scaled_mm (cuda_ops_api.h:171-176): c [M,N] bf16 = a_s * b_s * (a @ b) + bias with
+    a [M,K] e4m3 row-major and b [K,N] e4m3 COLUMN-major (the reference passes weight.t(): fp8_scaled_matmul.cpp:20-45)."""
+    _need(a.dtype == E4M3 and b.dtype == E4M3, "a and b must be float8_e4m3fn")
+    _need(c.dtype == BF16, "c must be bfloat16")
+    _need(a.dim() == 2 and b.dim() == 2 and c.dim() == 2, "2-D tensors expected")
+    _need(c.size(0) == a.size(0) and a.size(1) == b.size(0) and b.size(1) == c.size(1), "shape mismatch")
+    _need(a.stride(1) == 1 and c.stride(1) == 1, "a and c must be row major")
+    _need(b.stride(0) == 1, "b must be column major")
+    _need(c.stride(0) % 16 == 0 and b.stride(1) % 16 == 0, "row strides must be multiples of 16")
+    _need(a_scales.is_contiguous() and b_scales.is_contiguous(), "scales must be contiguous")
+    _need(a_scales.dtype == torch.float32 and b_scales.dtype == torch.float32, "scales must be float32")
+    M, K = a.shape
+    N = b.size(1)
+    _need(b.stride(1) == K, "b must be a dense column-major [K,N] view of a [N,K] weight")
+    _need(a_scales.numel() in (1, M) and b_scales.numel() in (1, N), "scale numel must be 1 or M / N")
+    if bias is not None:
+        _need(bias.numel() == N and bias.is_contiguous() and bias.dim() == 1 and bias.dtype == BF16, "bias must be [N] bf16")
+    check(lib().xb_gemm_fp8_scaled(_p(c), c_i64(c.stride(0)), _p(a), c_i64(a.stride(0)), _p(b), _p(a_scales),
+                                   c_i32(a_scales.numel()), _p(b_scales), c_i32(b_scales.numel()), _p(bias), c_i32(M),
+                                   c_i32(N), c_i32(K), _stream()), "cutlass_scaled_mm")
+
+
+def fp8_scaled_matmul(a, b, a_scale, b_scale, output_dtype=BF16, bias=None, output=None):
+    """xllm::kernel::cuda::fp8_scaled_matmul (cuda_ops_api.h:223-233, fp8_scaled_matmul.cpp:20-45): b is the [N,K] weight."""
+    _need(output_dtype == BF16, "only bfloat16 output is implemented")
+    M, N = a.size(0), b.size(0)
+    out = output if output is not None else torch.empty(M, N, dtype=BF16, device=a.device)
+    cutlass_scaled_mm(out, a, b.t(), a_scale, b_scale, bias)
+    return out
+
+
+def w4a16_linear(x, qweight, meta, group_size, bias=None, out=None):
+    """weight-only linear for any M: small-M streaming kernel up to 16 tokens, tcgen05 dequant-GEMM above."""
+    _cuda_bf16(x, "x")
+    M, K = x.shape
+    N = meta.size(1)
+    y = out if out is not None else torch.empty(M, N, dtype=BF16, device=x.device)
+    if M <= 16:
+        return w4a16_linear_small_m(x, qweight, meta, group_size, bias, y)
+    check(lib().xb_gemm_w4a16(_p(y), c_i64(y.stride(0)), _p(x), c_i64(x.stride(0)), _p(qweight), _p(meta), _p(bias),
+                              c_i32(M), c_i32(N), c_i32(K), c_i32(group_size), _stream()), "w4a16_linear")
+    return y
+
+
+def gemm_w4a16(x, qweight, meta, group_size, bias=None, out=None):
+    """always the tcgen05 dequant-GEMM (tests / benchmarks)."""
+    _cuda_bf16(x, "x")
+    M, K = x.shape
+    N = meta.size(1)
+    y = out if out is not None else torch.empty(M, N, dtype=BF16, device=x.device)
+    check(lib().xb_gemm_w4a16(_p(y), c_i64(y.stride(0)), _p(x), c_i64(x.stride(0)), _p(qweight), _p(meta), _p(bias),
+                              c_i32(M), c_i32(N), c_i32(K), c_i32(group_size), _stream()), "gemm_w4a16")
+    return y
