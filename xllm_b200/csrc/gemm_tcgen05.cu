@@ -60,6 +60,7 @@ struct GemmParams {
   const uint32_t* meta;        // [K/g][N]
   int gshift;                  // log2(k64 tiles per quantisation group)
   int M, N, K;
+  int use_tma_store;           // C rows are 16-byte aligned: epilogue stages through smem and TMA-stores
 };
 
 constexpr int kBlockM = 128;
@@ -75,21 +76,25 @@ struct GemmCfg {
   static constexpr int kPackedBytes = kKind == kKindW4 ? kBlockN * kBlockK / 2 : 0;   // int4 tile
   static constexpr int kMetaBytes = kKind == kKindW4 ? kBlockN * 4 : 0;
   static constexpr int kStageBytes = kABytes + kBBytes + kPackedBytes + ((kMetaBytes + 1023) / 1024) * 1024;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kThreads = (2 + kNumEpiWarps + (kKind == kKindW4 ? 4 : 0)) * 32;
+  static constexpr int kConvWarps = kKind == kKindW4 ? 8 : 0;      // two converter warps per SM sub-partition
+  static constexpr int kEpiStageBytes = kNumEpiWarps * 2 * 4096;   // per epilogue warp: 2 x [32 rows x 64 cols] bf16
+  static constexpr int kBudget = 227 * 1024 - 1024 - 512 - kEpiStageBytes;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kThreads = (2 + kNumEpiWarps + kConvWarps) * 32;
   static constexpr int kTmemCols = 2 * kBlockN;                    // two accumulator stages
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 template <int kKind, int kBlockN>
 __global__ void __launch_bounds__(GemmCfg<kKind, kBlockN>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   using Cfg = GemmCfg<kKind, kBlockN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_mem = smem + kStages * Cfg::kStageBytes;
+  uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;             // [kNumEpiWarps][2][4096]
+  uint8_t* bar_mem = epi_stage + Cfg::kEpiStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_mem);          // [kStages] TMA -> MMA (A, and B for BF16/FP8)
   uint64_t* empty_bar = full_bar + kStages;                           // [kStages] MMA -> TMA
   uint64_t* packed_bar = empty_bar + kStages;                         // [kStages] TMA -> converters (W4)
@@ -114,7 +119,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
       mbar_init(packed_bar + s, 1);
-      mbar_init(bready_bar + s, 4);          // one elected arrive per converter warp
+      mbar_init(bready_bar + s, Cfg::kConvWarps > 0 ? Cfg::kConvWarps : 1);   // one elected arrive per converter warp
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full + s, 1);
@@ -125,6 +130,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     if (kKind != kKindW4) tma_prefetch_desc(&tmap_b);
+    if (p.use_tma_store) tma_prefetch_desc(&tmap_c);
   }
   if (warp == 1) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
   tc_fence_before_sync();
@@ -201,14 +207,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp < 2 + kNumEpiWarps) {
     // ======================= epilogue =======================
+    // TMEM -> registers (tcgen05.ld 32x32b: thread = accumulator row) -> scale/bias -> bf16 -> 128B-swizzled staging
+    // tile in smem -> TMA store (clips ragged M / N edges).  Falls back to direct global stores when C rows are not
+    // 16-byte aligned.
     const int q = warp & 3;                     // TMEM lane quarter this warp may read
+    const int ew = warp - 2;
+    uint8_t* my_stage = epi_stage + ew * 2 * 4096;
+    int sbuf = 0;
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % m_blocks, n_blk = tile / m_blocks;
       mbar_wait(tmem_full + as, aph);
       tc_fence_after_sync();
-      const int row = m_blk * kBlockM + q * 32 + lane;
+      const int row0 = m_blk * kBlockM + q * 32;
+      const int row = row0 + lane;
       float a_s = 1.f;
       if (kKind == kKindFP8) a_s = p.a_scale[p.a_scale_per_row ? min(row, p.M - 1) : 0];
 #pragma unroll 1
@@ -217,33 +230,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * kBlockN + c * 32, r);
         tmem_ld_wait();
         const int col0 = n_blk * kBlockN + c * 32;
-        if (row < p.M && col0 < p.N) {
-          float v[32];
+        uint32_t o[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
-            const int col = col0 + j;
-            if (kKind == kKindFP8) {
-              const float b_s = p.b_scale[p.b_scale_per_col ? min(col, p.N - 1) : 0];
-              x = a_s * (b_s * x);                 // ScaledEpilogue order: scale_a * (scale_b * acc)
-            }
-            if (p.bias) x += __bfloat162float(p.bias[min(col, p.N - 1)]);
-            v[j] = x;
+        for (int j = 0; j < 32; j += 2) {
+          float x0 = __uint_as_float(r[j]), x1 = __uint_as_float(r[j + 1]);
+          const int col = col0 + j;
+          if (kKind == kKindFP8) {
+            const float b0 = p.b_scale[p.b_scale_per_col ? min(col, p.N - 1) : 0];
+            const float b1 = p.b_scale[p.b_scale_per_col ? min(col + 1, p.N - 1) : 0];
+            x0 = a_s * (b0 * x0);                 // ScaledEpilogue order: scale_a * (scale_b * acc)
+            x1 = a_s * (b1 * x1);
           }
+          if (p.bias) {
+            x0 += __bfloat162float(p.bias[min(col, p.N - 1)]);
+            x1 += __bfloat162float(p.bias[min(col + 1, p.N - 1)]);
+          }
+          o[j >> 1] = pack_bf16x2(x0, x1);
+        }
+        if (p.use_tma_store) {
+          // staging tile [32 rows][64 cols] bf16, row = 128 bytes, 16-byte chunk j stored at (j ^ (row & 7))
+          uint8_t* st = my_stage + sbuf * 4096;
+          if ((c & 1) == 0) tma_store_wait_read<1>();   // the buffer we are about to overwrite was stored 2 groups ago
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = (c & 1) * 4 + j;
+            *reinterpret_cast<uint4*>(st + lane * 128 + ((chunk ^ (lane & 7)) << 4)) =
+                make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          if ((c & 1) == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M && col0 - 32 < p.N) {
+              tma_store_2d(&tmap_c, st, col0 - 32, row0);
+              tma_store_commit();
+            } else if (lane == 0) {
+              tma_store_commit();   // keep the group count in step
+            }
+            sbuf ^= 1;
+          }
+        } else if (row < p.M && col0 < p.N) {
           __nv_bfloat16* dst = p.c + (int64_t)row * p.ldc + col0;
-          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              reinterpret_cast<uint4*>(dst)[j] = o;
-            }
-          } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
-          }
+          const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(o);
+          for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = ob[j];
         }
       }
       tc_fence_before_sync();
@@ -251,9 +280,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (lane == 0) mbar_arrive(tmem_empty + as);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (p.use_tma_store && lane == 0) tma_store_wait_all();
   } else if (kKind == kKindW4) {
-    // ======================= W4 converters (warps 6..9) =======================
-    // converter warp cw handles row tiles cw, cw+4, ... of the stage; a lane's 16 bytes of packed data are
+    // ======================= W4 converters (warps 6..13) =======================
+    // converter warp cw handles row tiles cw, cw+8, ... of the stage; a lane's 16 bytes of packed data are
     // rows (g, g+8) x k in [16t, 16t+16) of its row tile  ->  four 16-byte chunks of the swizzled bf16 tile.
     const int cw = warp - (2 + kNumEpiWarps);
     const int g = lane >> 2, t = lane & 3;
@@ -268,7 +298,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t* mt = reinterpret_cast<const uint32_t*>(stage_meta(s));
         uint8_t* bt = stage_b(s);
 #pragma unroll
-        for (int r = cw; r < kBlockN / 16; r += 4) {
+        for (int r = cw; r < kBlockN / 16; r += Cfg::kConvWarps) {
           const uint4 wq = *reinterpret_cast<const uint4*>(pk + r * 512 + lane * 16);
           const uint32_t m0 = mt[r * 16 + g], m1 = mt[r * 16 + g + 8];
           const uint32_t s0 = __byte_perm(m0, 0, 0x1010), z0 = __byte_perm(m0, 0, 0x3232);
@@ -318,7 +348,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 template <int kKind, int kBlockN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
   using Cfg = GemmCfg<kKind, kBlockN>;
   auto kern = gemm_tcgen05_kernel<kKind, kBlockN>;
   static bool attr_done = false;
@@ -334,7 +364,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }();
   const int tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + kBlockN - 1) / kBlockN);
   dim3 grid(tiles < num_sms ? tiles : num_sms), block(Cfg::kThreads);
-  XB_CUDA_OK(launch(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, ta, tb, p));
+  CUtensorMap tc = ta;   // placeholder when the direct-store epilogue is used
+  p.use_tma_store = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+  if (p.use_tma_store && make_tmap_2d(&tc, p.c, p.M, p.N, (uint64_t)p.ldc * 2, 32, 64, 2)) return 1;
+  XB_CUDA_OK(launch(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, ta, tb, tc, p));
   return 0;
 }
 
@@ -348,6 +381,9 @@ using namespace xb::tc;
 // scaled_mm_sm100_fp8_dispatch.cuh:148-287)
 static int pick_block_n(int M, int N) {
   const int m_blocks = (M + kBlockM - 1) / kBlockM;
+  static const int force = [] { const char* e = getenv("XB_GEMM_BN"); return e ? atoi(e) : 0; }();
+  if (force == 64 || force == 128 || force == 256) return force;
+  if ((int64_t)m_blocks * ((N + 255) / 256) >= 140) return 256;   // UMMA N=256: A re-read from smem half as often
   if ((int64_t)m_blocks * ((N + 127) / 128) >= 120) return 128;
   return 64;
 }
@@ -367,6 +403,7 @@ extern "C" int xb_gemm_bf16(void* c, int64_t ldc, const void* a, int64_t lda, co
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, kBlockM, 64, 2)) return 1;
   if (make_tmap_2d(&tb, b, N, K, (uint64_t)K * 2, bn, 64, 2)) return 1;
+  if (bn == 256) return launch_gemm<kKindBF16, 256>(ta, tb, p, (cudaStream_t)stream);
   return bn == 128 ? launch_gemm<kKindBF16, 128>(ta, tb, p, (cudaStream_t)stream)
                    : launch_gemm<kKindBF16, 64>(ta, tb, p, (cudaStream_t)stream);
 }
@@ -391,6 +428,7 @@ extern "C" int xb_gemm_fp8_scaled(void* c, int64_t ldc, const void* a, int64_t l
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda, kBlockM, 128, 1)) return 1;
   if (make_tmap_2d(&tb, b, N, K, (uint64_t)K, bn, 128, 1)) return 1;
+  if (bn == 256) return launch_gemm<kKindFP8, 256>(ta, tb, p, (cudaStream_t)stream);
   return bn == 128 ? launch_gemm<kKindFP8, 128>(ta, tb, p, (cudaStream_t)stream)
                    : launch_gemm<kKindFP8, 64>(ta, tb, p, (cudaStream_t)stream);
 }
@@ -413,9 +451,11 @@ extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   while ((1 << p.gshift) < tpg) ++p.gshift;
   p.M = M; p.N = N; p.K = K;
   int bn = pick_block_n(M, N);
-  if (N % 128 != 0) bn = 64;
+  if (bn == 256 && N % 256 != 0) bn = 128;
+  if (bn == 128 && N % 128 != 0) bn = 64;
   CUtensorMap ta;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, kBlockM, 64, 2)) return 1;
+  if (bn == 256) return launch_gemm<kKindW4, 256>(ta, ta, p, (cudaStream_t)stream);
   return bn == 128 ? launch_gemm<kKindW4, 128>(ta, ta, p, (cudaStream_t)stream)
                    : launch_gemm<kKindW4, 64>(ta, ta, p, (cudaStream_t)stream);
 }
