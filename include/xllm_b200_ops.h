@@ -198,6 +198,31 @@ int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
 /* host-side packer (plain C, no CUDA): q[N,K] uint8 (0..15) -> qweight tiles. */
 int xb_w4_pack_rows(uint32_t* qweight_out, const uint8_t* q, int N, int K);
 
+/* ---- K3 / K2: prefill and chunked-prefill attention (tcgen05 + TMEM + TMA) ---------------------------
+ * ragged: replaces the FlashInfer `ragged_run` module behind xllm::kernel::cuda::batch_prefill
+ *   (cuda_ops_api.h:52-66, batch_prefill.cpp:21-163): q [total_q, Hq, D], k/v [total_kv, Hkv, D] contiguous ragged,
+ *   q_cu_seq_lens / kv_cu_seq_lens int32 [batch+1] on device, causal self-attention.
+ * paged:  replaces `paged_run` behind xllm::kernel::cuda::batch_chunked_prefill (cuda_ops_api.h:110-128,
+ *   batch_chunked_prefill.cpp:26-92): ragged q (qo_indptr) over the NHD paged cache [pages, page_size, Hkv, D]
+ *   (contiguous) with the paged triplet; causal => query i of a chunk sees kv_idx <= kv_len - qo_len + i.
+ * o [total_q, Hq, D] bf16; lse optional [total_q, Hq] f32 (base 2).  max_qo_len: host upper bound of the longest
+ * request's query length (grid sizing; the reference planner has it from qo_indptr_host). head_dim 64 | 128. */
+int xb_prefill_ragged_bf16(const void* q, int64_t q_stride_n, int64_t q_stride_h,
+                           const void* k, const void* v, int64_t kv_stride_n,
+                           const int32_t* q_cu_seq_lens, const int32_t* kv_cu_seq_lens,
+                           void* o, int64_t o_stride_n, int64_t o_stride_h, float* lse,
+                           int batch, int64_t total_q, int64_t total_kv, int max_qo_len,
+                           int num_qo_heads, int num_kv_heads, int head_dim, int causal,
+                           float sm_scale, xb_stream_t stream);
+int xb_prefill_paged_bf16(const void* q, int64_t q_stride_n, int64_t q_stride_h,
+                          const void* k_cache, const void* v_cache, int64_t num_pages,
+                          int page_size, const int32_t* qo_indptr, const int32_t* kv_indptr,
+                          const int32_t* kv_indices, const int32_t* kv_last_page_len,
+                          void* o, int64_t o_stride_n, int64_t o_stride_h, float* lse,
+                          int batch, int64_t total_q, int max_qo_len, int num_qo_heads,
+                          int num_kv_heads, int head_dim, int causal, float sm_scale,
+                          xb_stream_t stream);
+
 /* ---- tcgen05 GEMMs for prefill-sized M (any M; TMA zero-fills ragged edges) ---------------------
  * C[M,N] = A[M,K] . B[N,K]^T (+ bias), fp32 accumulation in TMEM, bf16 output.
  * bf16:  replaces xllm::kernel::cuda::matmul (cuda_ops_api.h:167-169, matmul.cpp:20-24 -> F::linear).

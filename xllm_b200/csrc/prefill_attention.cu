@@ -1,0 +1,436 @@
+// Prefill / chunked-prefill attention on tcgen05 tensor cores with TMEM accumulators and TMA staging.
+// Replaces the FlashInfer fa2 (mma.sync) modules the reference dlopen()s on B200:
+//   ragged_run  - xllm::kernel::cuda::batch_prefill          (kernels/cuda/batch_prefill.cpp:21-163): contiguous ragged q/k/v
+//   paged_run   - xllm::kernel::cuda::batch_chunked_prefill  (kernels/cuda/batch_chunked_prefill.cpp:26-92): ragged q over the
+//                 paged KV cache (chunked prefill with causal offset; also "decode on tensor cores", causal = false)
+//
+// One CTA per (q tile, kv head, request).  A q tile packs (token, head-of-the-GQA-group) pairs into the 128 MMA rows
+// (tokens_per_tile = 128 / group), so every K/V tile is fetched once per kv head for the whole group.
+//   warp 0      TMA producer: Q tile once (3-D tensor map token x head x d), then K and V tiles through 2-stage rings.
+//               Paged KV: one 2-D TMA per page fragment, the row coordinate comes from the page table.
+//   warp 1      MMA issuer (one elected lane):  S = Q K^T  (128 x 128 x d, both operands K-major, fp32 in TMEM, double
+//               buffered so S(j+1) is computed while softmax works on S(j));  O += P V  (P from smem K-major, V straight
+//               from its [kv, d] TMA tile as an MN-major operand - no transpose pass).
+//   warps 2..5  softmax / correction / epilogue, thread = row: tcgen05.ld the S row, base-2 online softmax
+//               (sm_scale*log2e folded), causal / length mask only on tiles that need it, P rounded to bf16 into the
+//               128B-swizzled smem tile (denominator summed from the ROUNDED P like the reference ladder), lazy
+//               O rescale with tcgen05.ld/st when the running max moved, final O / l -> bf16 -> global.
+// TMEM: S0 [0,128)  S1 [128,256)  O [256, 256+d).
+#include "tc_common.cuh"
+
+namespace xb {
+namespace tc {
+
+struct PrefillParams {
+  const int32_t* qo_indptr;
+  const int32_t* kv_indptr;        // paged: page indptr; ragged: kv_cu_seq_lens
+  const int32_t* kv_indices;       // paged only
+  const int32_t* kv_last_page_len; // paged only
+  int paged, page_size;
+  __nv_bfloat16* o;
+  int64_t o_stride_n, o_stride_h;
+  float* lse;                      // [T, Hq] base-2, optional
+  float scale_log2;
+  int num_qo_heads, num_kv_heads, group, tokens_per_tile, causal;
+  int box_rows;                    // kv rows per TMA load (min(page_size, 128) or 128 for ragged)
+};
+
+constexpr int kQT = 128;   // MMA rows
+constexpr int kKT = 128;   // kv tile
+
+template <int kD>
+struct PrefillCfg {
+  static constexpr int kHalves = kD / 64;
+  static constexpr int kSub = 128 * 128;                           // one [128 rows x 64 elems] swizzled sub-tile
+  static constexpr int kQBytes = kHalves * kSub;
+  static constexpr int kKVBytes = kHalves * kSub;                  // K tile or V tile
+  static constexpr int kPBytes = 2 * kSub;                         // P [128 x 128 kv]
+  static constexpr int kSmemBytes = kQBytes + 4 * kKVBytes + kPBytes + 1024 + 256;
+  static constexpr int kTmemCols = 512;
+};
+
+template <int kD>
+__global__ void __launch_bounds__(192, 1)
+prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                         const __grid_constant__ CUtensorMap tmap_v, const PrefillParams p) {
+  using Cfg = PrefillCfg<kD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + Cfg::kQBytes;                // [2][kKVBytes]
+  uint8_t* v_s = k_s + 2 * Cfg::kKVBytes;           // [2][kKVBytes]
+  uint8_t* p_s = v_s + 2 * Cfg::kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + Cfg::kPBytes);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* v_full = bars + 5;        // 2
+  uint64_t* v_empty = bars + 7;       // 2
+  uint64_t* s_full = bars + 9;        // 2
+  uint64_t* s_empty = bars + 11;      // 2
+  uint64_t* p_full = bars + 13;       // 1
+  uint64_t* pv_done = bars + 14;      // 1
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, kvh = blockIdx.y;
+  const int ti = gridDim.x - 1 - blockIdx.x;          // heavy (late, causal) tiles first
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(k_full + i, 1);
+      mbar_init(k_empty + i, 1);
+      mbar_init(v_full + i, 1);
+      mbar_init(v_empty + i, 1);
+      mbar_init(s_full + i, 1);
+      mbar_init(s_empty + i, 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // ---- work item geometry (uniform across the CTA) ------------------------------------------------------------
+  const int q0 = __ldg(p.qo_indptr + b);
+  const int qo_len = __ldg(p.qo_indptr + b + 1) - q0;
+  const int tq0 = ti * p.tokens_per_tile;              // first q token of this tile (request-local)
+  int kv_len, kv_base = 0, indptr0 = 0, n_pages = 0;
+  if (p.paged) {
+    indptr0 = __ldg(p.kv_indptr + b);
+    n_pages = __ldg(p.kv_indptr + b + 1) - indptr0;
+    kv_len = n_pages > 0 ? (n_pages - 1) * p.page_size + __ldg(p.kv_last_page_len + b) : 0;
+  } else {
+    kv_base = __ldg(p.kv_indptr + b);
+    kv_len = __ldg(p.kv_indptr + b + 1) - kv_base;
+  }
+  const bool live = tq0 < qo_len;
+  const int tq_last = min(qo_len, tq0 + p.tokens_per_tile) - 1;
+  const int kv_off = kv_len - qo_len;                  // causal offset of chunked prefill (prefill.cuh:1017 semantics)
+  int kv_limit = p.causal ? min(kv_len, tq_last + kv_off + 1) : kv_len;
+  if (kv_limit < 0) kv_limit = 0;
+  const int n_tiles = live ? (kv_limit + kKT - 1) / kKT : 0;
+  const int rows_used = p.tokens_per_tile * p.group;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0 && n_tiles > 0) {
+      mbar_expect_tx(q_full, rows_used * kD * 2);
+#pragma unroll
+      for (int h = 0; h < Cfg::kHalves; ++h)
+        tma_load_3d(q_s + h * Cfg::kSub, &tmap_q, q_full, h * 64, kvh * p.group, q0 + tq0);
+      const int loads = kKT / p.box_rows;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t par = ((j >> 1) & 1) ^ 1;
+        for (int kv = 0; kv < 2; ++kv) {           // kv = 0: K tile, 1: V tile
+          uint64_t* full = kv ? v_full + st : k_full + st;
+          mbar_wait(kv ? v_empty + st : k_empty + st, par);
+          mbar_expect_tx(full, kKT * kD * 2);
+          uint8_t* dst = (kv ? v_s : k_s) + st * Cfg::kKVBytes;
+          const CUtensorMap* map = kv ? &tmap_v : &tmap_k;
+          for (int i = 0; i < loads; ++i) {
+            const int t0 = j * kKT + i * p.box_rows;
+            int row;
+            if (p.paged) {
+              int pg = t0 / p.page_size;
+              if (pg >= n_pages) pg = n_pages - 1;    // beyond the request: masked anyway, keep the address valid
+              row = __ldg(p.kv_indices + indptr0 + pg) * p.page_size + (t0 % p.page_size);
+            } else {
+              row = kv_base + t0;
+            }
+#pragma unroll
+            for (int h = 0; h < Cfg::kHalves; ++h)
+              tma_load_2d(dst + h * Cfg::kSub + i * p.box_rows * 128, map, full, kvh * kD + h * 64, row);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc_qk = umma_idesc(1, 1, kQT, kKT);
+    constexpr uint32_t idesc_pv = umma_idesc(1, 1, kQT, kD, 0, 1);     // B = V is MN-major
+    const uint32_t s_tmem[2] = {tmem_base, tmem_base + 128};
+    const uint32_t o_tmem = tmem_base + 256;
+    auto issue_qk = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(k_full + st, (j >> 1) & 1);
+      mbar_wait(s_empty + st, ((j >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        const uint32_t qa = smem_u32(q_s), ka = smem_u32(k_s + st * Cfg::kKVBytes);
+#pragma unroll
+        for (int s = 0; s < kD / 16; ++s) {
+          const uint32_t off = (s >> 2) * Cfg::kSub + (s & 3) * 32;
+          umma_f16(s_tmem[st], umma_desc_sw128(qa + off), umma_desc_sw128(ka + off), idesc_qk, s != 0);
+        }
+        umma_commit(k_empty + st);
+        umma_commit(s_full + st);
+      }
+      __syncwarp();
+    };
+    if (n_tiles > 0) {
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        const int st = j & 1;
+        mbar_wait(v_full + st, (j >> 1) & 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint32_t pa = smem_u32(p_s), va = smem_u32(v_s + st * Cfg::kKVBytes);
+#pragma unroll
+          for (int s = 0; s < kKT / 16; ++s) {
+            const uint64_t da = umma_desc_sw128(pa + (s >> 2) * Cfg::kSub + (s & 3) * 32);
+            const uint64_t db = umma_desc_sw128_mn(va + s * 2048, Cfg::kSub, 1024);
+            umma_f16(o_tmem, da, db, idesc_pv, (j | s) != 0);
+          }
+          umma_commit(v_empty + st);
+          umma_commit(pv_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================== softmax / correction / epilogue ==============================
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;                       // my row of the tile = my TMEM lane
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const int tok_local = r / p.group, head_local = r - tok_local * p.group;
+    const int q_idx = tq0 + tok_local;
+    const bool row_valid = live && r < rows_used && q_idx < qo_len;
+    const int my_lim = p.causal ? min(kv_len, q_idx + kv_off + 1) : kv_len;       // #visible keys of my row
+    const int lim_first = p.causal ? min(kv_len, tq0 + kv_off + 1) : kv_len;      // smallest limit in the tile
+    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t o_tmem = tmem_base + 256 + lane_addr;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int sb = j & 1;
+      const uint32_t s_tmem = tmem_base + sb * 128 + lane_addr;
+      mbar_wait(s_full + sb, (j >> 1) & 1);
+      tc_fence_after_sync();
+      const bool need_mask = (j + 1) * kKT > lim_first;
+      const int col_lim = my_lim - j * kKT;             // columns >= col_lim are masked
+      // ---- pass 1: row max ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(s_tmem + c * 32, v);
+        tmem_ld_wait();
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i) < col_lim ? __uint_as_float(v[i]) : -INFINITY);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+      const float alpha = exp2f(m_run - m_safe);
+      // ---- P smem / O are free once PV(j-1) has completed ----
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha < 1.0f)) {     // lazy correction: only when some row's max moved
+#pragma unroll 1
+          for (int c = 0; c < kD / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(o_tmem + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(o_tmem + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // ---- pass 2: P = exp2(s*scale - m), rounded to bf16, into the swizzled [128 x 128] K-major tile ----
+      float psum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(s_tmem + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_safe);
+          float p1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_safe);
+          if (need_mask) {
+            if (c * 32 + i >= col_lim) p0 = 0.f;
+            if (c * 32 + i + 1 >= col_lim) p1 = 0.f;
+          }
+          const uint32_t pp = pack_bf16x2(p0, p1);
+          pk[i >> 1] = pp;
+          psum += bf16lo(pp) + bf16hi(pp);              // denominator from the ROUNDED P (reference ladder)
+        }
+        // row r, columns [32c, 32c+32): sub-tile (c >> 1), 16-byte chunks ((c & 1) * 4 + i) ^ (r & 7)
+        uint8_t* rowp = p_s + (c >> 1) * Cfg::kSub + r * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int chunk = ((c & 1) * 4 + i) ^ (r & 7);
+          *reinterpret_cast<uint4*>(rowp + (chunk << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      }
+      l_run = l_run * alpha + psum;
+      m_run = m_new;
+      tc_fence_before_sync();          // my TMEM reads of S (and O stores) are ordered before the arrives below
+      fence_proxy_async_smem();        // P stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_empty + sb);
+        mbar_arrive(p_full);
+      }
+    }
+    // ---- epilogue: O / l -> bf16 -> global ----
+    if (n_tiles > 0) {
+      mbar_wait(pv_done, (n_tiles - 1) & 1);
+      tc_fence_after_sync();
+    }
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* dst = nullptr;
+    if (row_valid) {
+      const int64_t tq = q0 + q_idx;
+      const int head = kvh * p.group + head_local;
+      dst = p.o + tq * p.o_stride_n + (int64_t)head * p.o_stride_h;
+      if (p.lse) p.lse[tq * p.num_qo_heads + head] = l_run > 0.f ? m_run + log2f(l_run) : -INFINITY;
+    }
+#pragma unroll 1
+    for (int c = 0; c < kD / 32; ++c) {
+      uint32_t v[32];
+      if (n_tiles > 0) {
+        tmem_ld_32x32b_x32(o_tmem + c * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0;
+      }
+      if (row_valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int kD>
+static int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const PrefillParams& p,
+                          int batch, int q_tiles, cudaStream_t stream) {
+  using Cfg = PrefillCfg<kD>;
+  auto kern = prefill_attention_kernel<kD>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  dim3 grid(q_tiles, p.num_kv_heads, batch), block(192);
+  XB_CUDA_OK(launch(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, tq, tk, tv, p));
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace xb
+
+using namespace xb;
+using namespace xb::tc;
+
+// Shared host path of ragged_run / paged_run.
+static int prefill_common(const void* q, int64_t q_stride_n, int64_t q_stride_h, int64_t total_q, const void* k,
+                          const void* v, int64_t kv_rows, int64_t kv_row_stride, int paged, int page_size,
+                          const int32_t* qo_indptr, const int32_t* kv_indptr, const int32_t* kv_indices,
+                          const int32_t* kv_last_page_len, void* o, int64_t o_stride_n, int64_t o_stride_h, float* lse,
+                          int batch, int max_qo_len, int num_qo_heads, int num_kv_heads, int head_dim, int causal,
+                          float sm_scale, cudaStream_t stream) {
+  if (batch == 0 || total_q == 0 || max_qo_len == 0) return 0;
+  XB_CHECK(head_dim == 64 || head_dim == 128, "prefill attention: head_dim %d unsupported (64|128)", head_dim);
+  XB_CHECK(num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0, "prefill attention: bad head counts %d/%d", num_qo_heads,
+           num_kv_heads);
+  const int group = num_qo_heads / num_kv_heads;
+  XB_CHECK(group <= 128, "prefill attention: GQA group %d > 128", group);
+  XB_CHECK(q_stride_h == head_dim, "prefill attention: q heads must be contiguous (stride %lld)", (long long)q_stride_h);
+  XB_CHECK(q_stride_n % 8 == 0 && kv_row_stride % 8 == 0 && o_stride_n % 8 == 0 && o_stride_h % 8 == 0,
+           "prefill attention: strides must keep 16-byte alignment");
+  XB_CHECK(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+             reinterpret_cast<uintptr_t>(o)) & 15) == 0, "prefill attention: pointers must be 16-byte aligned");
+  PrefillParams p{};
+  p.qo_indptr = qo_indptr;
+  p.kv_indptr = kv_indptr;
+  p.kv_indices = kv_indices;
+  p.kv_last_page_len = kv_last_page_len;
+  p.paged = paged;
+  p.page_size = page_size;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.o_stride_n = o_stride_n;
+  p.o_stride_h = o_stride_h;
+  p.lse = lse;
+  p.scale_log2 = sm_scale * 1.44269504088896340736f;
+  p.num_qo_heads = num_qo_heads;
+  p.num_kv_heads = num_kv_heads;
+  p.group = group;
+  p.tokens_per_tile = 128 / group;
+  p.causal = causal;
+  if (paged) {
+    XB_CHECK(page_size > 0 && ((page_size <= 128 && 128 % page_size == 0) || page_size % 128 == 0),
+             "prefill attention: page_size %d must divide 128 or be a multiple of it", page_size);
+    p.box_rows = page_size < 128 ? page_size : 128;
+  } else {
+    p.box_rows = 128;
+  }
+  CUtensorMap tq, tk, tv;
+  if (make_tmap_3d_bf16(&tq, q, head_dim, num_qo_heads, total_q, (uint64_t)q_stride_h * 2, (uint64_t)q_stride_n * 2, 64,
+                        group, p.tokens_per_tile))
+    return 1;
+  if (make_tmap_2d(&tk, k, kv_rows, (uint64_t)num_kv_heads * head_dim, (uint64_t)kv_row_stride * 2, p.box_rows, 64, 2)) return 1;
+  if (make_tmap_2d(&tv, v, kv_rows, (uint64_t)num_kv_heads * head_dim, (uint64_t)kv_row_stride * 2, p.box_rows, 64, 2)) return 1;
+  const int q_tiles = (max_qo_len + p.tokens_per_tile - 1) / p.tokens_per_tile;
+  return head_dim == 128 ? launch_prefill<128>(tq, tk, tv, p, batch, q_tiles, stream)
+                         : launch_prefill<64>(tq, tk, tv, p, batch, q_tiles, stream);
+}
+
+extern "C" int xb_prefill_ragged_bf16(const void* q, int64_t q_stride_n, int64_t q_stride_h, const void* k, const void* v,
+                                      int64_t kv_stride_n, const int32_t* q_cu_seq_lens, const int32_t* kv_cu_seq_lens,
+                                      void* o, int64_t o_stride_n, int64_t o_stride_h, float* lse, int batch,
+                                      int64_t total_q, int64_t total_kv, int max_qo_len, int num_qo_heads, int num_kv_heads,
+                                      int head_dim, int causal, float sm_scale, xb_stream_t stream) {
+  return prefill_common(q, q_stride_n, q_stride_h, total_q, k, v, total_kv, kv_stride_n, 0, 1, q_cu_seq_lens, kv_cu_seq_lens,
+                        nullptr, nullptr, o, o_stride_n, o_stride_h, lse, batch, max_qo_len, num_qo_heads, num_kv_heads,
+                        head_dim, causal, sm_scale, (cudaStream_t)stream);
+}
+
+extern "C" int xb_prefill_paged_bf16(const void* q, int64_t q_stride_n, int64_t q_stride_h, const void* k_cache,
+                                     const void* v_cache, int64_t num_pages, int page_size, const int32_t* qo_indptr,
+                                     const int32_t* kv_indptr, const int32_t* kv_indices, const int32_t* kv_last_page_len,
+                                     void* o, int64_t o_stride_n, int64_t o_stride_h, float* lse, int batch, int64_t total_q,
+                                     int max_qo_len, int num_qo_heads, int num_kv_heads, int head_dim, int causal,
+                                     float sm_scale, xb_stream_t stream) {
+  // NHD cache [pages, page_size, Hkv, D] contiguous: a 2-D [pages*page_size, Hkv*D] row tensor
+  return prefill_common(q, q_stride_n, q_stride_h, total_q, k_cache, v_cache, num_pages * page_size,
+                        (int64_t)num_kv_heads * head_dim, 1, page_size, qo_indptr, kv_indptr, kv_indices, kv_last_page_len, o,
+                        o_stride_n, o_stride_h, lse, batch, max_qo_len, num_qo_heads, num_kv_heads, head_dim, causal, sm_scale,
+                        (cudaStream_t)stream);
+}

@@ -348,3 +348,44 @@ def gemm_w4a16(x, qweight, meta, group_size, bias=None, out=None):
     check(lib().xb_gemm_w4a16(_p(y), c_i64(y.stride(0)), _p(x), c_i64(x.stride(0)), _p(qweight), _p(meta), _p(bias),
                               c_i32(M), c_i32(N), c_i32(K), c_i32(group_size), _stream()), "gemm_w4a16")
     return y
+
+
+# ---- K3 / K2 prefill attention ------------------------------------------------------
+def batch_prefill(query, key, value, q_cu_seq_lens, kv_cu_seq_lens, sm_scale, output, output_lse=None, max_qo_len=None,
+                  causal=True) -> None:
+    """xllm::kernel::cuda::batch_prefill (cuda_ops_api.h:52-66, batch_prefill.cpp:21-163): contiguous ragged q/k/v.
+    query [T, Hq, D] (may be a strided view of the packed qkv), key/value [T_kv, Hkv, D]."""
+    _cuda_bf16(query, "query"); _cuda_bf16(key, "key"); _cuda_bf16(value, "value"); _cuda_bf16(output, "output")
+    _need(q_cu_seq_lens.dtype == torch.int32 and kv_cu_seq_lens.dtype == torch.int32, "cu_seq_lens must be int32")
+    _need(key.stride(0) == value.stride(0), "key/value must share the token stride")
+    T, Hq, D = query.shape
+    Hkv = key.size(1)
+    _need(key.stride(1) == D and value.stride(1) == D, "kv heads must be contiguous")
+    if max_qo_len is None:
+        max_qo_len = int((q_cu_seq_lens[1:] - q_cu_seq_lens[:-1]).max().item())   # host sync; pass it to avoid
+    check(lib().xb_prefill_ragged_bf16(_p(query), c_i64(query.stride(0)), c_i64(query.stride(1)), _p(key), _p(value),
+                                       c_i64(key.stride(0)), _p(q_cu_seq_lens), _p(kv_cu_seq_lens), _p(output),
+                                       c_i64(output.stride(0)), c_i64(output.stride(1)), _p(output_lse),
+                                       c_i32(q_cu_seq_lens.numel() - 1), c_i64(T), c_i64(key.size(0)), c_i32(max_qo_len),
+                                       c_i32(Hq), c_i32(Hkv), c_i32(D), c_i32(1 if causal else 0), c_f32(sm_scale), _stream()),
+          "batch_prefill")
+
+
+def batch_chunked_prefill(query, k_cache, v_cache, paged_kv_indptr, paged_kv_indices, paged_kv_last_page_len, sm_scale,
+                          output, output_lse=None, qo_indptr=None, causal=True, max_qo_len=None) -> None:
+    """xllm::kernel::cuda::batch_chunked_prefill (cuda_ops_api.h:110-128, batch_chunked_prefill.cpp:26-92)."""
+    _cuda_bf16(query, "query"); _cuda_bf16(k_cache, "k_cache"); _cuda_bf16(v_cache, "v_cache"); _cuda_bf16(output, "output")
+    _need(k_cache.is_contiguous() and v_cache.is_contiguous(), "caches must be contiguous NHD")
+    T, Hq, D = query.shape
+    B = paged_kv_indptr.numel() - 1
+    if qo_indptr is None:
+        qo_indptr = torch.arange(B + 1, dtype=torch.int32, device=query.device)
+        max_qo_len = 1
+    if max_qo_len is None:
+        max_qo_len = int((qo_indptr[1:] - qo_indptr[:-1]).max().item())
+    check(lib().xb_prefill_paged_bf16(_p(query), c_i64(query.stride(0)), c_i64(query.stride(1)), _p(k_cache), _p(v_cache),
+                                      c_i64(k_cache.size(0)), c_i32(k_cache.size(1)), _p(qo_indptr), _p(paged_kv_indptr),
+                                      _p(paged_kv_indices), _p(paged_kv_last_page_len), _p(output), c_i64(output.stride(0)),
+                                      c_i64(output.stride(1)), _p(output_lse), c_i32(B), c_i64(T), c_i32(max_qo_len),
+                                      c_i32(Hq), c_i32(k_cache.size(2)), c_i32(D), c_i32(1 if causal else 0),
+                                      c_f32(sm_scale), _stream()), "batch_chunked_prefill")
