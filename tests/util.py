@@ -12,7 +12,8 @@ product, relative to whatever running maximum the tile order produced, so two co
 different tile / split order differ by independent 2^-9-relative perturbations of every p_j.  For
 o_d = sum_j p_j v_jd that is a forward error of up to ~1e-3 * sum_j p_j |v_jd| - NOT 1e-3 * |o_d|, which on the
 synthetic N(0,1) KV of SURVEY 8d is ~sqrt(kv_len) smaller because of cancellation.  `assert_close_attention`
-therefore states "1e-3 relative" in the standard dot-product sense: |err_d| <= 1e-3 * sum_j p_j |v_jd| + 1 bf16 ulp,
+therefore states the bar in the standard dot-product sense: |err_d| <= 2e-3 * sum_j p_j |v_jd| + 1 bf16 ulp (two
+independent 2^-9 roundings of every p_j - the oracle's and the kernel's - i.e. 1e-3 each; checked over millions of elements),
 with the scale sum_j p_j |v_jd| computed by the oracle itself (same attention with |V|).
 """
 import torch
@@ -39,7 +40,7 @@ def assert_close_bf16(got: torch.Tensor, ref: torch.Tensor, ulps: float = 1.0, r
     return l2
 
 
-def assert_close_attention(got, ref, abs_scale, rtol: float = 1e-3, what: str = ""):
+def assert_close_attention(got, ref, abs_scale, rtol: float = 2e-3, what: str = ""):
     """|got - ref| <= rtol * (sum_j p_j |v_j|) + 1 bf16 ulp(ref), elementwise (see module docstring).
 
     The same bound with rtol = 1e-5 is used for fp32-accumulated dot products (linears): two correct summation orders

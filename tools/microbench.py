@@ -141,6 +141,20 @@ def bench_gemm(kind, M, N, K, gs=128):
     print(f"gemm {kind:5s} M={M:6d} N={N:6d} K={K:6d}  {us:9.1f} us  {tf:8.1f} TFLOP/s", flush=True)
 
 
+def bench_prefill(B, S, HQ=28, HKV=4, D=128):
+    T = B * S
+    qkv = torch.randn(T, (HQ + 2 * HKV) * D, device=DEV, dtype=BF16)
+    q = qkv[:, :HQ * D].view(T, HQ, D)
+    k = qkv[:, HQ * D:(HQ + HKV) * D].view(T, HKV, D)
+    v = qkv[:, (HQ + HKV) * D:].view(T, HKV, D)
+    cu = torch.arange(0, (B + 1) * S, S, dtype=torch.int32, device=DEV)
+    out = torch.empty(T, HQ, D, device=DEV, dtype=BF16)
+    fn = lambda i: ops.batch_prefill(q, k, v, cu, cu, D ** -0.5, out, None, max_qo_len=S)
+    us = timeit(fn, 1, iters=10, warm=2)
+    flops = 4.0 * HQ * D * S * S / 2 * B
+    print(f"prefill attention B={B} S={S}: {us:9.1f} us  {flops / us / 1e6:7.1f} TFLOP/s (causal flops)", flush=True)
+
+
 if __name__ == "__main__" and len(sys.argv) > 1:
     # profiling entry: `microbench.py w4 N K M` | `microbench.py decode B ctx`
     if sys.argv[1] == "w4":
@@ -149,6 +163,9 @@ if __name__ == "__main__" and len(sys.argv) > 1:
         bench_decode(int(sys.argv[2]), int(sys.argv[3]))
     elif sys.argv[1] == "bf16":
         bench_bf16(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    elif sys.argv[1] == "prefill":
+        for B, S in [(1, 2048), (4, 2048), (1, 8192), (16, 2048)]:
+            bench_prefill(B, S)
     elif sys.argv[1] == "gemm":
         for kind in sys.argv[2].split(","):
             for M, N, K in [(2048, 4608, 3584), (2048, 37888, 3584), (2048, 3584, 18944), (8192, 37888, 3584), (8192, 8192, 8192)]:

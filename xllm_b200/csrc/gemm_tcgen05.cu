@@ -90,14 +90,19 @@ struct GemmCfg {
   static constexpr int kBBytes = kBlockN * 128;
   static constexpr int kPackedBytes = kKind == kKindW4 ? kBlockN * kBlockK / 2 : 0;   // int4 tile
   static constexpr int kMetaBytes = kKind == kKindW4 ? kBlockN * 4 : 0;
-  static constexpr int kStageBytes = kABytes + kBBytes + kPackedBytes + ((kMetaBytes + 1023) / 1024) * 1024;
+  // BF16 / FP8: a stage holds the A and B tiles.  W4: a stage holds A + the PACKED int4 B tile + its scale/zero words
+  // (small, so the TMA ring can be deep enough to cover HBM latency) and the dequantised bf16 B lives in a separate
+  // 2-deep ring written by the converter warps.
+  static constexpr int kStageBytes = kKind == kKindW4 ? kABytes + kPackedBytes + ((kMetaBytes + 1023) / 1024) * 1024
+                                                      : kABytes + kBBytes;
+  static constexpr int kBStages = kKind == kKindW4 ? 2 : 0;
   static constexpr int kConvWarps = kKind == kKindW4 ? 8 : 0;      // two converter warps per SM sub-partition
   static constexpr int kEpiStageBytes = kNumEpiWarps * 2 * 4096;   // per epilogue warp: 2 x [32 rows x 64 cols] bf16
-  static constexpr int kBudget = 227 * 1024 - 1024 - 512 - kEpiStageBytes;
+  static constexpr int kBudget = 227 * 1024 - 1024 - 512 - kEpiStageBytes - kBStages * kBBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kThreads = (2 + kNumEpiWarps + kConvWarps) * 32;
   static constexpr int kTmemCols = 2 * kBlockN;                    // two accumulator stages
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBStages * kBBytes + kEpiStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 template <int kKind, int kBlockN>
@@ -108,13 +113,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;             // [kNumEpiWarps][2][4096]
+  uint8_t* bbuf = smem + kStages * Cfg::kStageBytes;                  // W4: [kBStages][kBBytes] dequantised B ring
+  uint8_t* epi_stage = bbuf + Cfg::kBStages * Cfg::kBBytes;           // [kNumEpiWarps][2][4096]
   uint8_t* bar_mem = epi_stage + Cfg::kEpiStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_mem);          // [kStages] TMA -> MMA (A, and B for BF16/FP8)
   uint64_t* empty_bar = full_bar + kStages;                           // [kStages] MMA -> TMA
   uint64_t* packed_bar = empty_bar + kStages;                         // [kStages] TMA -> converters (W4)
-  uint64_t* bready_bar = packed_bar + kStages;                        // [kStages] converters -> MMA (W4)
-  uint64_t* tmem_full = bready_bar + kStages;                         // [2]
+  uint64_t* bready_bar = packed_bar + kStages;                        // [2] converters -> MMA (W4 B ring)
+  uint64_t* bempty_bar = bready_bar + 2;                              // [2] MMA -> converters
+  uint64_t* tmem_full = bempty_bar + 2;                               // [2]
   uint64_t* tmem_empty = tmem_full + 2;                               // [2]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -125,16 +132,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_kb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;
 
   auto stage_a = [&](int s) { return smem + s * Cfg::kStageBytes; };
-  auto stage_b = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes; };
-  auto stage_packed = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes + Cfg::kBBytes; };
-  auto stage_meta = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes + Cfg::kBBytes + Cfg::kPackedBytes; };
+  auto stage_b = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes; };               // BF16 / FP8
+  auto stage_packed = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes; };          // W4
+  auto stage_meta = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes + Cfg::kPackedBytes; };
+  auto b_ring = [&](int bs) { return bbuf + bs * Cfg::kBBytes; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
       mbar_init(packed_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bready_bar + s, Cfg::kConvWarps > 0 ? Cfg::kConvWarps : 1);   // one elected arrive per converter warp
+      mbar_init(bempty_bar + s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full + s, 1);
@@ -196,16 +207,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t ph = 0;
     int as = 0;
     uint32_t aph = 0;
+    int bs = 0;
+    uint32_t bph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(tmem_empty + as, aph ^ 1);     // epilogue has drained this accumulator stage
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + as * kBlockN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar + s, ph);
-        if (kKind == kKindW4) mbar_wait(bready_bar + s, ph);
+        if (kKind == kKindW4) mbar_wait(bready_bar + bs, bph);
         tc_fence_after_sync();
         if (lane == 0) {
-          const uint32_t a_addr = smem_u32(stage_a(s)), b_addr = smem_u32(stage_b(s));
+          const uint32_t a_addr = smem_u32(stage_a(s));
+          const uint32_t b_addr = smem_u32(kKind == kKindW4 ? b_ring(bs) : stage_b(s));
 #pragma unroll
           for (int k = 0; k < Cfg::kBlockK / Cfg::kUmmaK; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * 32), db = umma_desc_sw128(b_addr + k * 32);
@@ -213,10 +227,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             else umma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar + s);                 // smem slot is free once these MMAs have read it
+          if (kKind == kKindW4) umma_commit(bempty_bar + bs);
           if (kb == num_kb - 1) umma_commit(tmem_full + as);
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1; }
+        if (kKind == kKindW4 && ++bs == 2) { bs = 0; bph ^= 1; }
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
@@ -304,14 +320,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int g = lane >> 2, t = lane & 3;
     int s = 0;
     uint32_t ph = 0;
+    int bs = 0;
+    uint32_t bph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(packed_bar + s, ph);          // packed tile + meta landed
-        // the bf16 B buffer of this stage is free: the producer only refills `packed` after empty_bar, which the
-        // MMA commits after reading B; packed_bar completing therefore implies B(s) is free as well
+        mbar_wait(bempty_bar + bs, bph ^ 1);    // the MMA has finished reading this B buffer
         const uint8_t* pk = stage_packed(s);
         const uint32_t* mt = reinterpret_cast<const uint32_t*>(stage_meta(s));
-        uint8_t* bt = stage_b(s);
+        uint8_t* bt = b_ring(bs);
 #pragma unroll
         for (int r = cw; r < kBlockN / 16; r += Cfg::kConvWarps) {
           const uint4 wq = *reinterpret_cast<const uint4*>(pk + r * 512 + lane * 16);
@@ -351,8 +368,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(bready_bar + s);
+        if (lane == 0) mbar_arrive(bready_bar + bs);
         if (++s == kStages) { s = 0; ph ^= 1; }
+        if (++bs == 2) { bs = 0; bph ^= 1; }
       }
     }
   }
