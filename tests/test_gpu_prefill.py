@@ -89,7 +89,8 @@ def test_batch_chunked_prefill_paged(q_lens, kv_lens, HQ, HKV, D, page, causal, 
     ops.batch_chunked_prefill(q.to(DEV), kc.to(DEV), vc.to(DEV), indptr.to(DEV), perm.to(DEV), last.to(DEV), sc, out, lse,
                               qo.to(DEV), causal, max_qo_len=max(q_lens))
     assert_close_attention(out, ref, scale, what=f"batch_chunked_prefill q={q_lens} kv={kv_lens}")
-    assert torch.allclose(lse.cpu(), ref_lse, rtol=1e-4, atol=1e-4), "base-2 LSE mismatch"
+    # l sums bf16-rounded P relative to the running maximum of the tile order: log2(l) moves by ~2^-9 / ln 2
+    assert torch.allclose(lse.cpu(), ref_lse, rtol=1e-4, atol=5e-3), "base-2 LSE mismatch"
 
 
 def test_prefill_decode_kernels_agree(built_lib):

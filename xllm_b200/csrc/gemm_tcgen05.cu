@@ -46,6 +46,21 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   return 0;
 }
 
+int make_tmap_2d_raw(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                     uint32_t box_rows, uint32_t box_cols, int swizzle) {
+  EncodeTiledFn enc = get_encode_tiled();
+  XB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, (CUtensorMapDataType)dtype, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(raw) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                       uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
   EncodeTiledFn enc = get_encode_tiled();
@@ -108,7 +123,8 @@ struct GemmCfg {
 template <int kKind, int kBlockN>
 __global__ void __launch_bounds__(GemmCfg<kKind, kBlockN>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_m,
+                    const GemmParams p) {
   using Cfg = GemmCfg<kKind, kBlockN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -155,7 +171,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
-    if (kKind != kKindW4) tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_b);
+    if (kKind == kKindW4) tma_prefetch_desc(&tmap_m);
     if (p.use_tma_store) tma_prefetch_desc(&tmap_c);
   }
   if (warp == 1) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
@@ -177,18 +194,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1);
           if (kKind == kKindW4) {
-            // packed B: kBlockN/16 row tiles, each (row tile, k tile) block is 512 contiguous bytes; plus the group's
-            // scale/zero words for these kBlockN rows
-            const int ktiles = p.K >> 6;
+            // packed B: the kBlockN/16 row tiles of this k tile are one 2-D TMA box (tensor [N/16][K/64 * 128 words],
+            // box [kBlockN/16][128 words], no swizzle) - one instruction instead of kBlockN/16 bulk copies - plus the
+            // group's scale/zero words for these kBlockN rows (tensor [K/g][N], box [1][kBlockN])
             mbar_expect_tx(packed_bar + s, Cfg::kPackedBytes + Cfg::kMetaBytes);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.qweight);
-#pragma unroll 1
-            for (int r = 0; r < kBlockN / 16; ++r) {
-              const int64_t ntile = (int64_t)n_blk * (kBlockN / 16) + r;
-              bulk_load(stage_packed(s) + r * 512, src + (ntile * ktiles + kb) * 512, 512, packed_bar + s);
-            }
-            bulk_load(stage_meta(s), p.meta + (int64_t)(kb >> p.gshift) * p.N + (int64_t)n_blk * kBlockN, Cfg::kMetaBytes,
-                      packed_bar + s);
+            tma_load_2d(stage_packed(s), &tmap_b, packed_bar + s, kb * 128, n_blk * (kBlockN / 16));
+            tma_load_2d(stage_meta(s), &tmap_m, packed_bar + s, n_blk * kBlockN, kb >> p.gshift);
             mbar_expect_tx(full_bar + s, Cfg::kABytes);
             tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, m_blk * kBlockM);
           } else {
@@ -381,7 +392,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 template <int kKind, int kBlockN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream,
+                       const CUtensorMap* tm = nullptr) {
   using Cfg = GemmCfg<kKind, kBlockN>;
   auto kern = gemm_tcgen05_kernel<kKind, kBlockN>;
   static bool attr_done = false;
@@ -400,7 +412,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
   CUtensorMap tc = ta;   // placeholder when the direct-store epilogue is used
   p.use_tma_store = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
   if (p.use_tma_store && make_tmap_2d(&tc, p.c, p.M, p.N, (uint64_t)p.ldc * 2, 32, 64, 2)) return 1;
-  XB_CUDA_OK(launch(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, ta, tb, tc, p));
+  XB_CUDA_OK(launch(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, ta, tb, tc, tm ? *tm : ta, p));
   return 0;
 }
 
@@ -486,9 +498,16 @@ extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   int bn = pick_block_n(M, N);
   if (bn == 256 && N % 256 != 0) bn = 128;
   if (bn == 128 && N % 128 != 0) bn = 64;
-  CUtensorMap ta;
+  CUtensorMap ta, tb, tm;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, kBlockM, 64, 2)) return 1;
-  if (bn == 256) return launch_gemm<kKindW4, 256>(ta, ta, p, (cudaStream_t)stream);
-  return bn == 128 ? launch_gemm<kKindW4, 128>(ta, ta, p, (cudaStream_t)stream)
-                   : launch_gemm<kKindW4, 64>(ta, ta, p, (cudaStream_t)stream);
+  const uint64_t ktiles = K / 64;
+  if (make_tmap_2d_raw(&tb, qweight, CU_TENSOR_MAP_DATA_TYPE_UINT32, N / 16, ktiles * 128, ktiles * 512, bn / 16, 128,
+                       CU_TENSOR_MAP_SWIZZLE_NONE))
+    return 1;
+  if (make_tmap_2d_raw(&tm, meta, CU_TENSOR_MAP_DATA_TYPE_UINT32, K / group_size, N, (uint64_t)N * 4, 1, bn,
+                       CU_TENSOR_MAP_SWIZZLE_NONE))
+    return 1;
+  if (bn == 256) return launch_gemm<kKindW4, 256>(ta, tb, p, (cudaStream_t)stream, &tm);
+  return bn == 128 ? launch_gemm<kKindW4, 128>(ta, tb, p, (cudaStream_t)stream, &tm)
+                   : launch_gemm<kKindW4, 64>(ta, tb, p, (cudaStream_t)stream, &tm);
 }

@@ -185,6 +185,9 @@ EncodeTiledFn get_encode_tiled();
 // 128-byte swizzle (box_cols * elem_bytes must be 128).
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_rows,
                  uint32_t box_cols, int elem_bytes);
+// generic 2-D map: element type / swizzle chosen by the caller (used for the packed int4 tiles: uint32, no swizzle)
+int make_tmap_2d_raw(CUtensorMap* out, const void* base, int dtype /*CUtensorMapDataType*/, uint64_t rows, uint64_t cols,
+                     uint64_t pitch_bytes, uint32_t box_rows, uint32_t box_cols, int swizzle /*CUtensorMapSwizzle*/);
 // 3-D bf16 tensor [d2][d1][d0] (d0 contiguous), byte strides for d1 and d2, box [b2][b1][b0], 128-byte swizzle.
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                       uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
