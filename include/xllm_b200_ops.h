@@ -241,6 +241,22 @@ int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda,
                   const uint32_t* qweight, const uint32_t* meta, const void* bias,
                   int M, int N, int K, int group_size, xb_stream_t stream);
 
+/* ---- tensor-parallel exchange over NVLink peer memory (decode-sized messages) ---------------------------------
+ * replaces parallel_state::reduce -> ProcessGroup::allreduce (framework/parallel_state/parallel_state.cpp:183-192,
+ * process_group.cpp:97-107) after the row-parallel linears (layers/common/linear.cpp:1518-1520).
+ * peer_data[r] / peer_flags[r]: device pointers, valid on THIS GPU, to rank r's symmetric partial buffer and signal
+ * pad ([max_ctas][8] uint32, zero-initialised once); epoch: local uint32[max_ctas], zero-initialised once.
+ * Sum order is rank 0..world-1 in fp32, one rounding: bit-identical on all ranks.
+ * xb_allreduce_add_rms_norm_bf16 fuses the exchange with the fused_add_rms_norm that follows every row-parallel
+ * linear: residual <- bf16(allreduce(partials)) + residual; out <- rms_norm(residual) * weight. */
+int xb_oneshot_allreduce_bf16(void* out, const void* const* peer_data, void* const* peer_flags,
+                              void* epoch, int rank, int world, int64_t numel, int max_ctas,
+                              xb_stream_t stream);
+int xb_allreduce_add_rms_norm_bf16(void* out, void* residual, const void* weight,
+                                   const void* const* peer_data, void* const* peer_flags,
+                                   void* epoch, int rank, int world, float eps, int num_tokens,
+                                   int hidden, int max_ctas, xb_stream_t stream);
+
 /* ---- step boundary helpers ---------------------------------------------------
  * embedding row gather (WordEmbeddingImpl::forward, layers/common/word_embedding_impl.cpp:33-56,
  * TP=1) and greedy argmax over logits rows (ties -> lowest index). */

@@ -1,0 +1,141 @@
+"""CPU tests (gloo, world_size 2) of the tensor-parallel host logic: head / weight partitioning and the row-parallel
+exchange, checked against the single-rank oracle layer."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import layer as OL
+from oracle import ops as O
+from oracle import quant as OQ
+from xllm_b200 import parallel as P
+
+BF16 = torch.bfloat16
+
+
+def test_partition_heads_rules():
+    # qwen2_attention.cpp:47-65
+    hp = P.partition_heads(28, 4, 1, 2)
+    assert (hp.num_heads, hp.num_kv_heads, hp.kv_replicas, hp.q_head0, hp.kv_head0) == (14, 2, 1, 14, 2)
+    hp = P.partition_heads(28, 4, 3, 4)
+    assert (hp.num_heads, hp.num_kv_heads, hp.q_head0, hp.kv_head0) == (7, 1, 21, 3)
+    hp = P.partition_heads(64, 8, 5, 8)                     # Llama-3-70B TP8: 8 q / 1 kv head per GPU
+    assert (hp.num_heads, hp.num_kv_heads, hp.kv_replicas, hp.kv_head0) == (8, 1, 1, 5)
+    hp = P.partition_heads(32, 4, 5, 8)                     # kv heads replicated on tp / n_kv = 2 ranks
+    assert (hp.num_heads, hp.num_kv_heads, hp.kv_replicas, hp.kv_head0) == (4, 1, 2, 2)
+    with pytest.raises(ValueError):
+        P.partition_heads(28, 4, 0, 8)                      # CHECK(total_num_heads % tp_size == 0)
+
+
+def test_shard_indices_cover_everything_once():
+    HQ, HKV, D, I, tp = 28, 4, 128, 18944, 4
+    rows = torch.cat([P.shard_qkv_rows(HQ, HKV, D, r, tp) for r in range(tp)])
+    assert sorted(rows.tolist()) == list(range((HQ + 2 * HKV) * D))
+    gu = torch.cat([P.shard_gate_up_rows(I, r, tp) for r in range(tp)])
+    assert sorted(gu.tolist()) == list(range(2 * I))
+    cols = [P.shard_cols(I, r, tp) for r in range(tp)]
+    assert cols[0].start == 0 and cols[-1].stop == I and all(cols[i].stop == cols[i + 1].start for i in range(tp - 1))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+H, NH, NKV, D, I, GS = 256, 8, 2, 64, 512, 64
+
+
+def _logical_layer(seed=2026):
+    g = torch.Generator().manual_seed(seed)
+
+    def lin(n, k, bias=False):
+        w = (torch.randn(n, k, generator=g) * 0.05).to(BF16)
+        q, s, z = OQ.quantize(w, 4, GS)
+        return dict(q=q, s=s, z=z, w=OQ.dequantize(q, s, z, GS), b=(torch.randn(n, generator=g) * 0.05).to(BF16) if bias else None)
+    return dict(qkv=lin((NH + 2 * NKV) * D, H, True), o=lin(H, NH * D), gate_up=lin(2 * I, H), down=lin(H, I),
+                in_norm=(1 + 0.1 * torch.randn(H, generator=g)).to(BF16), post_norm=(1 + 0.1 * torch.randn(H, generator=g)).to(BF16))
+
+
+def _inputs(seed=7):
+    g = torch.Generator().manual_seed(seed)
+    T = 5
+    x = torch.randn(T, H, generator=g).to(BF16)
+    res = torch.randn(T, H, generator=g).to(BF16)
+    nblk, bs = 6, 16
+    kc = torch.randn(nblk, bs, NKV, D, generator=g).to(BF16)
+    vc = torch.randn(nblk, bs, NKV, D, generator=g).to(BF16)
+    # one prefill request of 5 tokens written to block 2
+    meta = OL.AttnMeta(True, False, torch.tensor([0, T], dtype=torch.int32), torch.tensor([0, T], dtype=torch.int32),
+                       torch.arange(2 * bs, 2 * bs + T, dtype=torch.int32))
+    return x, res, kc, vc, meta, torch.arange(T)
+
+
+def _layer_forward(L, x, res, kc, vc, meta, pos, nh, nkv, reduce_fn):
+    cs = O.compute_cos_sin_cache(D, 128, 1000000, BF16)
+    attn = OL.Qwen2AttentionOracle(L["qkv"]["w"], L["qkv"]["b"], L["o"]["w"], nh, nkv, D, cs,
+                                   o_linear=lambda a, w, b: reduce_fn(O.linear(a, w, b)))
+    dl = OL.Qwen2DecoderLayerOracle(attn, L["in_norm"], L["post_norm"], 1e-6, lambda h: O.linear(h, L["gate_up"]["w"]),
+                                    lambda h: reduce_fn(O.linear(h, L["down"]["w"])))
+    return dl.forward(x, res, pos, meta, kc, vc)
+
+
+def _worker(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pg = P.ProcessGroup()
+    L = _logical_layer()
+    x, res, kc, vc, meta, pos = _inputs()
+    hp = P.partition_heads(NH, NKV, rank, world)
+    shard = dict(
+        qkv=P.shard_linear("w4", L["qkv"], P.shard_qkv_rows(NH, NKV, D, rank, world), None, GS),
+        o=P.shard_linear("w4", L["o"], None, P.shard_cols(NH * D, rank, world), GS),
+        gate_up=P.shard_linear("w4", L["gate_up"], P.shard_gate_up_rows(I, rank, world), None, GS),
+        down=P.shard_linear("w4", L["down"], None, P.shard_cols(I, rank, world), GS),
+        in_norm=L["in_norm"], post_norm=L["post_norm"])
+    # the sharded int4 tensors dequantise to exactly the matching slice of the full dequantised weight
+    for name in ("qkv", "o", "gate_up", "down"):
+        assert torch.equal(OQ.dequantize(shard[name]["q"], shard[name]["s"], shard[name]["z"], GS), shard[name]["w"])
+
+    def reduce_fn(t):                       # fp32 sum of the bf16 partials, one rounding (what csrc/allreduce.cu does)
+        f = t.float()
+        P.reduce(f, pg)
+        return f.to(BF16)
+    kv_sl = slice(hp.kv_head0, hp.kv_head0 + hp.num_kv_heads)
+    y, r = _layer_forward(shard, x, res, kc[:, :, kv_sl].contiguous(), vc[:, :, kv_sl].contiguous(), meta, pos,
+                          hp.num_heads, hp.num_kv_heads, reduce_fn)
+    # gather (lm_head-style) sanity: ranks hold different column blocks
+    g = P.gather(torch.full((2, 3), float(rank)), pg, dim=-1)
+    assert g.shape == (2, 3 * world) and torch.equal(g[:, 3 * rank:3 * rank + 3], torch.full((2, 3), float(rank)))
+    if rank == 0:
+        out_q.put((y.float().numpy(), r.float().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tp2_layer_matches_single_rank_oracle():
+    from tests.util import assert_close_bf16
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    y_tp, r_tp = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    L = _logical_layer()
+    x, res, kc, vc, meta, pos = _inputs()
+    y, r = _layer_forward(L, x, res, kc, vc, meta, pos, NH, NKV, lambda t: t)
+    # partial sums are rounded to bf16 per rank before the exchange: a 1-2 ulp effect on the reduced rows
+    # (elements that cancel to ~0 are compared on the scale of the terms: atol = 1 ulp of an O(1) value)
+    assert_close_bf16(torch.from_numpy(r_tp), r, ulps=2, rel_l2=2e-3, what="TP2 residual stream", atol=2.0 ** -7)
+    assert_close_bf16(torch.from_numpy(y_tp), y, ulps=1e9, rel_l2=5e-3, what="TP2 layer output")
