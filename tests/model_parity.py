@@ -122,8 +122,10 @@ def run_decode_parity(cfg, kv_lens, use_graph=True, fused=True, seed=2026):
     return logits, ref_logits, nxt, ref_next, runner, (kcs, vcs)
 
 
-def oracle_layer(cfg, W, li, x, residual, kcs, vcs, meta):
-    """one decoder layer of the oracle on given inputs (teacher forcing with the GPU's own layer inputs)."""
+def oracle_layer_state(cfg, W, li, h, residual, kcs, vcs, meta):
+    """One decoder layer of the oracle in the runner's state convention: (h = normalised layer input, residual =
+    residual stream) -> (normalised input of the next layer / final norm, updated residual stream).
+    Composition per qwen2_decoder_layer.cpp:89-112 with the next layer's input add+norm folded in."""
     B = len(meta["tokens"])
     cs = O.compute_cos_sin_cache(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, BF16)
     am = OL.AttnMeta(False, False, torch.arange(B + 1, dtype=torch.int32), None, torch.tensor(meta["slots"], dtype=torch.int32),
@@ -131,15 +133,17 @@ def oracle_layer(cfg, W, li, x, residual, kcs, vcs, meta):
                      torch.tensor(meta["last"], dtype=torch.int32))
     L = W["layers"][li]
     attn = OL.Qwen2AttentionOracle(L["qkv"]["w"], L["qkv"]["b"], L["o"]["w"], cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cs)
-    dl = OL.Qwen2DecoderLayerOracle(attn, L["input_norm"], L["post_norm"], cfg.rms_norm_eps,
-                                    lambda h: O.linear(h, L["gate_up"]["w"]), lambda h: O.linear(h, L["down"]["w"]))
-    return dl.forward(x, residual, torch.tensor(meta["positions"]), am, kcs[li].clone(), vcs[li].clone())
+    a = attn.forward(torch.tensor(meta["positions"]), h, am, kcs[li].clone(), vcs[li].clone())
+    h_mid, res_mid = O.fused_add_rms_norm(a, residual, L["post_norm"], cfg.rms_norm_eps)
+    down = O.linear(O.act_and_mul(O.linear(h_mid, L["gate_up"]["w"]), "silu"), L["down"]["w"])
+    next_w = W["layers"][li + 1]["input_norm"] if li + 1 < cfg.num_layers else W["final_norm"]
+    return O.fused_add_rms_norm(down, res_mid, next_w, cfg.rms_norm_eps)
 
 
 def run_layerwise_parity(cfg, kv_lens, seed=2026):
-    """Eager GPU step with a per-layer trace; every layer of the oracle is then fed the GPU's own input of that layer,
-    so each comparison isolates ONE decoder layer (no compounding of bf16 rounding flips across layers).
-    Returns a list of (gpu_out, ref_out, gpu_res, ref_res) per layer."""
+    """Eager GPU step with a per-layer trace; every layer of the oracle is then fed the GPU's own state before that
+    layer, so each comparison isolates ONE decoder layer (no compounding of bf16 rounding flips across layers).
+    Returns a list of (gpu_h, ref_h, gpu_res, ref_res) per layer."""
     from xllm_b200.qwen2 import Qwen2DecodeRunner
     B = len(kv_lens)
     W, kcs, vcs, meta = build_case(cfg, B, kv_lens, seed)
@@ -155,10 +159,11 @@ def run_layerwise_parity(cfg, kv_lens, seed=2026):
     runner.launch_step(trace)
     torch.cuda.synchronize()
     out = []
-    x_in, res_in = W["embed"][torch.tensor(meta["tokens"])], None
+    res_in = W["embed"][torch.tensor(meta["tokens"])]
+    h_in = O.rms_norm(res_in, W["layers"][0]["input_norm"], cfg.rms_norm_eps)
     for li in range(cfg.num_layers):
-        ref_x, ref_res = oracle_layer(cfg, W, li, x_in, res_in, kcs, vcs, meta)
-        gx, gres = trace[li][0].cpu(), trace[li][1].cpu()
-        out.append((gx, ref_x, gres, ref_res))
-        x_in, res_in = gx, gres          # teacher forcing: next layer sees what the GPU produced
+        ref_h, ref_res = oracle_layer_state(cfg, W, li, h_in, res_in, kcs, vcs, meta)
+        gh, gres = trace[li][0].cpu(), trace[li][1].cpu()
+        out.append((gh, ref_h, gres, ref_res))
+        h_in, res_in = gh, gres          # teacher forcing: next layer sees what the GPU produced
     return out

@@ -153,8 +153,20 @@ class Qwen2DecodeRunner:
     """Batched single-token decode over a paged KV cache (continuous-batching decode step of the reference)."""
 
     def __init__(self, cfg: Qwen2Config, weights: Qwen2Weights, max_batch: int, max_ctx: int, device="cuda",
-                 num_blocks: Optional[int] = None, fused_rope_cache: bool = True):
+                 num_blocks: Optional[int] = None, fused_rope_cache: bool = True, pg=None, exchange: str = "peer"):
+        """pg: xllm_b200.parallel.ProcessGroup for tensor parallelism (weights must already be this rank's shards);
+        exchange: "peer" = NVLink one-shot all-reduce fused with add+RMSNorm, "nccl" = c10d all-reduce (baseline)."""
         self.cfg, self.w, self.B, self.device = cfg, weights, max_batch, device
+        self.pg = pg if (pg is not None and pg.world_size > 1) else None
+        self.tp = self.pg.world_size if self.pg else 1
+        self.tp_rank = self.pg.rank if self.pg else 0
+        from .parallel import partition_heads
+        hp = partition_heads(cfg.n_heads, cfg.n_kv_heads, self.tp_rank, self.tp)
+        self.nh, self.nkv = hp.num_heads, hp.num_kv_heads
+        self.q_size, self.kv_size = self.nh * cfg.head_dim, self.nkv * cfg.head_dim
+        self.inter = cfg.intermediate_size // self.tp
+        self.exchange = None
+        self.exchange_mode = exchange
         bs = cfg.block_size
         self.max_pages = (max_ctx + bs - 1) // bs
         self.num_blocks = num_blocks or (max_batch * self.max_pages + 1)     # block 0 reserved (block_manager_impl.cpp:71-73)
@@ -162,7 +174,7 @@ class Qwen2DecodeRunner:
         H, I = cfg.hidden_size, cfg.intermediate_size
         B = max_batch
         dev = device
-        self.k_caches = [torch.zeros(self.num_blocks, bs, cfg.n_kv_heads, cfg.head_dim, dtype=BF16, device=dev)
+        self.k_caches = [torch.zeros(self.num_blocks, bs, self.nkv, cfg.head_dim, dtype=BF16, device=dev)
                          for _ in range(cfg.num_layers)]
         self.v_caches = [torch.zeros_like(k) for k in self.k_caches]
         self.cos_sin = make_cos_sin_cache(cfg, dev)
@@ -189,14 +201,17 @@ class Qwen2DecodeRunner:
         # o_proj writes buf_a, down_proj writes buf_b
         self.buf_a = torch.empty(B, H, dtype=BF16, device=dev)
         self.buf_b = torch.empty(B, H, dtype=BF16, device=dev)
-        self.qkv = torch.empty(B, cfg.q_size + 2 * cfg.kv_size, dtype=BF16, device=dev)
-        self.attn_out = torch.empty(B, cfg.q_size, dtype=BF16, device=dev)
-        self.gate_up = torch.empty(B, 2 * I, dtype=BF16, device=dev)
-        self.act = torch.empty(B, I, dtype=BF16, device=dev)
+        self.qkv = torch.empty(B, self.q_size + 2 * self.kv_size, dtype=BF16, device=dev)
+        self.attn_out = torch.empty(B, self.q_size, dtype=BF16, device=dev)
+        self.gate_up = torch.empty(B, 2 * self.inter, dtype=BF16, device=dev)
+        self.act = torch.empty(B, self.inter, dtype=BF16, device=dev)
         self.logits = torch.empty(B, cfg.vocab_size, dtype=BF16, device=dev)
+        self.logits_local = torch.empty(B, cfg.vocab_size // self.tp, dtype=BF16, device=dev) if self.pg else self.logits
+        if self.pg and exchange == "peer":
+            from .parallel import PeerExchange
+            self.exchange = PeerExchange(self.pg, B, H, dev)
         self.next_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
-        self.plan = ops.DecodePlan(B, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, bs, self.max_pages, dev,
-                                   early_prefetch=True)
+        self.plan = ops.DecodePlan(B, self.nh, self.nkv, cfg.head_dim, bs, self.max_pages, dev, early_prefetch=True)
         self.graph = None
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in
                              (self.h_token_ids, self.h_positions, self.h_slots, self.h_kv_indptr, self.h_kv_indices,
@@ -204,22 +219,36 @@ class Qwen2DecodeRunner:
         self.d2h_bytes = self.h_next.numel() * 4
 
     # -- one decode step worth of launches (capturable) -----------------------------------
+    def _row_parallel(self, lin, x, which, norm_w, out):
+        """row-parallel linear + exchange + the fused add+RMSNorm that follows it in the layer
+        (linear.cpp:1405-1522 + qwen2_decoder_layer.cpp:103-109).  Returns the normalised activations."""
+        cfg = self.cfg
+        if self.pg is None:
+            lin.forward(x, out)
+            ops.fused_add_rms_norm(out, self.residual, norm_w, cfg.rms_norm_eps)
+            return out
+        if self.exchange is not None:
+            part = self.exchange.partial_buffer(which, x.size(0))
+            lin.forward(x, part)                                    # partial straight into the symmetric buffer
+            self.exchange.allreduce_add_rms_norm(which, out, self.residual, norm_w, cfg.rms_norm_eps, x.size(0))
+            return out
+        lin.forward(x, out)
+        self.pg.allreduce(out)                                      # NCCL baseline
+        ops.fused_add_rms_norm(out, self.residual, norm_w, cfg.rms_norm_eps)
+        return out
+
     def launch_step(self, trace=None):
-        """trace (eager only): list that receives (layer_output, residual) clones after every decoder layer."""
+        """trace (eager only): list that receives (normed layer output, residual) clones after every decoder layer."""
         cfg, w = self.cfg, self.w
-        qs, kvs = cfg.q_size, cfg.kv_size
+        qs, kvs = self.q_size, self.kv_size
         scale = cfg.head_dim ** -0.5
         ops.embedding(self.hidden, self.token_ids, w.embed)
-        x = self.hidden
+        # apply_norm, first layer (qwen2_decoder_layer.cpp:72-79): the residual stream aliases the embedding output
+        self.residual = self.hidden
+        ops.rms_norm(self.normed, self.hidden, w.layers[0]["input_norm"], cfg.rms_norm_eps)
+        h = self.normed
+        n_layers = len(w.layers)
         for li, L in enumerate(w.layers):
-            if li == 0:
-                # apply_norm first layer (qwen2_decoder_layer.cpp:72-79): residual aliases the input
-                ops.rms_norm(self.normed, x, L["input_norm"], cfg.rms_norm_eps)
-                self.residual = x
-                h = self.normed
-            else:
-                ops.fused_add_rms_norm(x, self.residual, L["input_norm"], cfg.rms_norm_eps)
-                h = x
             L["qkv"].forward(h, self.qkv)
             q, k, v = self.qkv[:, :qs], self.qkv[:, qs:qs + kvs], self.qkv[:, qs + kvs:]
             if self.fused_rope_cache:
@@ -227,20 +256,25 @@ class Qwen2DecodeRunner:
                                    self.v_caches[li], True)
             else:
                 ops.rotary_embedding(self.positions, q, k, self.cos_sin, True)
-                ops.reshape_paged_cache(self.slots, k.view(-1, cfg.n_kv_heads, cfg.head_dim),
-                                        v.view(-1, cfg.n_kv_heads, cfg.head_dim), self.k_caches[li], self.v_caches[li])
-            ops.batch_decode(self.plan, q.view(-1, cfg.n_heads, cfg.head_dim), self.k_caches[li], self.v_caches[li],
+                ops.reshape_paged_cache(self.slots, k.view(-1, self.nkv, cfg.head_dim), v.view(-1, self.nkv, cfg.head_dim),
+                                        self.k_caches[li], self.v_caches[li])
+            ops.batch_decode(self.plan, q.view(-1, self.nh, cfg.head_dim), self.k_caches[li], self.v_caches[li],
                              self.kv_indptr, self.kv_indices, self.kv_last, scale,
-                             self.attn_out.view(-1, cfg.n_heads, cfg.head_dim))
-            o = L["o"].forward(self.attn_out, self.buf_a)
-            ops.fused_add_rms_norm(o, self.residual, L["post_norm"], cfg.rms_norm_eps)
-            L["gate_up"].forward(o, self.gate_up)
+                             self.attn_out.view(-1, self.nh, cfg.head_dim))
+            # o_proj (+ all-reduce) + post-attention add+norm
+            h = self._row_parallel(L["o"], self.attn_out, 0, L["post_norm"], self.buf_a)
+            L["gate_up"].forward(h, self.gate_up)
             ops.act_and_mul(self.act, self.gate_up, "silu")
-            x = L["down"].forward(self.act, self.buf_b)
+            # down_proj (+ all-reduce) + the NEXT layer's input add+norm (or the final norm)
+            next_w = w.layers[li + 1]["input_norm"] if li + 1 < n_layers else w.final_norm
+            h = self._row_parallel(L["down"], self.act, 1, next_w, self.buf_b)
             if trace is not None:
-                trace.append((x.clone(), self.residual.clone()))
-        ops.fused_add_rms_norm(x, self.residual, w.final_norm, cfg.rms_norm_eps)
-        w.lm_head.forward(x, self.logits)
+                trace.append((h.clone(), self.residual.clone()))
+        w.lm_head.forward(h, self.logits_local)
+        if self.pg is not None:
+            # column-parallel lm_head with gather_output (linear.cpp:712-714 -> parallel_state.cpp:89-102)
+            from .parallel import gather
+            self.logits.copy_(gather(self.logits_local, self.pg, dim=-1))
         ops.argmax(self.next_tokens, self.logits)
 
     def capture(self):
