@@ -183,7 +183,7 @@ def test_act_and_mul(T, d, mode, built_lib):
     # (~6e-8), i.e. many bf16 ulps of a value that small: an absolute floor of 1e-5 (inputs are O(1)) covers it.
     assert_close_bf16(out, ref, ulps=2, what=f"act_and_mul {mode}", atol=1e-5 if mode != "silu" else 0.0)
     frac = (out.cpu() != ref).float().mean().item()
-    assert frac < 5e-3, f"{frac:.4f} of elements differ (device vs host transcendental ulp)"
+    assert frac < (5e-3 if mode == "silu" else 2e-2), f"{frac:.4f} of elements differ (device vs host transcendental ulp)"
 
 
 def test_act_and_mul_bad_mode(built_lib):
