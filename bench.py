@@ -12,8 +12,11 @@ Synthetic data: random-init weights of the named architecture, KV cache N(0,1) w
             measured with CUDA events around each launch in an instrumented pass of the same step
   cpu_baseline  the oracle's restatement of one decoder layer (+ lm_head) on the host cores, bounded sample
 
-N > 1 (torchrun): data-parallel replicas of the same step (the path shards per request: "weak" scaling, no data-path
-collective); value = sum of tokens over ranks / max time over ranks.
+N > 1 (torchrun): tensor parallelism as the reference shards the path: column-parallel qkv / gate_up / lm_head,
+row-parallel o / down with one exchange after each, done by this library's NVLink one-shot all-reduce fused with the
+following add+RMSNorm (NCCL all-gather for the logits).  Qwen2-7B has 28 q heads, so tp = min(N, 4); at N = 8 two TP4
+groups each decode their own request (data parallel replicas of the TP4 group).  `--parallelism dp` runs N independent
+replicas instead.  value = tokens of all groups / max time over ranks.
 `--impl reference` times the oracle port on the host cores (the reference has no CPU build and cannot be installed
 offline: see DESIGN.md) and prints the same line with "impl": "reference".
 """
@@ -183,6 +186,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctx", type=int, default=CTX)
+    ap.add_argument("--parallelism", default="tp", choices=["tp", "dp"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -206,8 +211,23 @@ def main():
 
     cfg = Qwen2Config.qwen2_7b()
     ctx = args.ctx
-    weights = Qwen2Weights.synthetic(cfg, dev, seed=2026 + rank)
-    runner = Qwen2DecodeRunner(cfg, weights, max_batch=1, max_ctx=ctx, device=dev)
+    tp = 1
+    if world > 1 and args.parallelism == "tp":
+        tp = 4 if world % 4 == 0 else (2 if world % 2 == 0 else 1)
+    dp = world // tp
+    pg = None
+    if tp > 1:
+        from xllm_b200.parallel import ProcessGroup
+        my_group = None
+        for gidx in range(dp):
+            ranks = list(range(gidx * tp, (gidx + 1) * tp))
+            grp = dist.new_group(ranks)
+            if rank in ranks:
+                my_group = grp
+        pg = ProcessGroup(my_group)
+    tp_rank = rank % tp
+    weights = Qwen2Weights.synthetic(cfg, dev, seed=2026 + rank, tp_rank=tp_rank, tp=tp)
+    runner = Qwen2DecodeRunner(cfg, weights, max_batch=1, max_ctx=ctx, device=dev, pg=pg, exchange=args.exchange)
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     for li in range(cfg.num_layers):
         runner.k_caches[li].normal_(generator=g)
@@ -280,10 +300,10 @@ def main():
     gu_us = sorted(a.elapsed_time(b) * 1e3 for a, b in gu_events)
     gu_us_avg = sum(gu_us) / len(gu_us)
     gu = L[0]["gate_up"]
-    gu_bytes = gu.qweight.numel() * 4 + gu.meta.numel() * 4 + gu.K * 2 + gu.N * 2
+    gu_bytes = gu.qweight.numel() * 4 + gu.meta.numel() * 4 + gu.K * 2 + gu.N * 2      # this rank's shard
     # attention kernel the same way (the north-star names it)
     at_events = []
-    q3 = runner.qkv[:, :cfg.q_size].view(-1, cfg.n_heads, cfg.head_dim)
+    q3 = runner.qkv[:, :runner.q_size].view(-1, runner.nh, cfg.head_dim)
     from xllm_b200 import ops
     torch.cuda._sleep(int(20e6))
     for rep in range(3):
@@ -291,23 +311,23 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             ops.batch_decode(runner.plan, q3, runner.k_caches[li], runner.v_caches[li], runner.kv_indptr, runner.kv_indices,
-                             runner.kv_last, cfg.head_dim ** -0.5, runner.attn_out.view(-1, cfg.n_heads, cfg.head_dim))
+                             runner.kv_last, cfg.head_dim ** -0.5, runner.attn_out.view(-1, runner.nh, cfg.head_dim))
             b.record()
             if rep > 0:
                 at_events.append((a, b))
     torch.cuda.synchronize()
     at_us_avg = sum(a.elapsed_time(b) * 1e3 for a, b in at_events) / len(at_events)
-    at_bytes = 2 * ctx * cfg.n_kv_heads * cfg.head_dim * 2 + 2 * cfg.n_heads * cfg.head_dim * 2 + 4 * npg
+    at_bytes = 2 * ctx * runner.nkv * cfg.head_dim * 2 + 2 * runner.nh * cfg.head_dim * 2 + 4 * npg
 
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
     t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
-    total_tokens = args.steps * world
+    total_tokens = args.steps * dp
     value = total_tokens / (ms / 1e3)
     e2e_value = total_tokens / (e2e_ms / 1e3)
-    step_bytes = weights.weight_bytes() + cfg.num_layers * at_bytes
+    step_bytes = weights.weight_bytes() + cfg.num_layers * at_bytes      # per rank
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -316,17 +336,20 @@ def main():
         ach = gu_bytes / gu_us_avg / 1e3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if tp == 1 else "strong",
+            "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "ctx": ctx, "batch": 1, "parallelism": f"dp{world}",
+            "config": {"workload": WORKLOAD, "ctx": ctx, "batch": 1,
+                       "parallelism": (f"tp{tp}" if dp == 1 else f"tp{tp}xdp{dp}") if tp > 1 else f"dp{world}",
+                       "exchange": (args.exchange if tp > 1 else None),
                        "l2": "inputs larger than L2: each step streams %.2f GB of weights+KV" % (step_bytes / 1e9),
                        "decode_chunk_tokens": runner.plan.chunk_tokens, "decode_splits": runner.plan.max_splits},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
                     "d2h_bytes_per_step": runner.d2h_bytes},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "linear_w4a16_small_m_kernel (gate_up_proj 37888x3584, 28 launches/step)",
-                         "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": f"linear_w4a16_small_m_kernel (gate_up_proj {gu.N}x{gu.K}, 28 launches/step)",
+                         "per_rank": True, "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None,
                          "peak_source": peak_src, "launch_us": gu_us_avg, "bytes_per_launch": gu_bytes,
                          "step": {"bytes": step_bytes, "achieved": step_bytes / (ms / args.steps) / 1e6,
                                   "frac": step_bytes / (ms / args.steps) / 1e6 / peak_gbs},

@@ -56,3 +56,28 @@ def test_argument_errors_surface(built_lib):
     assert rc == 0 and plan[0] % 16 == 0 and plan[0] * plan[1] >= 4096
     rc = lib.xb_w4_pack_rows(None, None, 15, 64)
     assert rc != 0
+
+
+def test_tvm_ffi_modules_export_reference_entry_points(built_lib):
+    """xLLM resolves __tvm_ffi_<name> in "$FLASHINFER_OPS_PATH/<uri>/<uri>.so" (utils.cpp:371-374,526-564)."""
+    from xllm_b200 import build_ffi
+    ops_dir = build_ffi.build()
+    dec, pre = build_ffi.uris()
+    for uri in dec:
+        so = ctypes.CDLL(os.path.join(ops_dir, uri, uri + ".so"))
+        assert hasattr(so, "__tvm_ffi_plan") and hasattr(so, "__tvm_ffi_run")
+    for uri in pre:
+        so = ctypes.CDLL(os.path.join(ops_dir, uri, uri + ".so"))
+        assert all(hasattr(so, "__tvm_ffi_" + n) for n in ("plan", "ragged_run", "paged_run"))
+
+
+def test_cpp_shim_exports_reference_namespace(built_lib):
+    """the link-time boundary: every xllm::kernel::cuda::* function of cuda_ops_api.h that is on the path."""
+    import subprocess
+    from xllm_b200 import build_shim
+    so = build_shim.build()
+    syms = subprocess.run(["nm", "-D", "-C", so], capture_output=True, text=True).stdout
+    for fn in ("rotary_embedding", "act_and_mul", "reshape_paged_cache", "rms_norm", "fused_add_rms_norm", "matmul",
+               "cutlass_scaled_mm", "static_scaled_fp8_quant", "fp8_scaled_quantize", "rms_norm_static_fp8_quant",
+               "fused_add_rms_norm_static_fp8_quant", "fp8_scaled_matmul", "fused_qk_norm_rope"):
+        assert f"xllm::kernel::cuda::{fn}(" in syms, fn

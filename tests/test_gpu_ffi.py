@@ -1,0 +1,96 @@
+"""GPU parity THROUGH the run-time boundary xLLM uses: the TVM-FFI modules are loaded from the FlashInfer-style
+"$OPS/<uri>/<uri>.so" layout and called with the reference's exact argument lists (batch_decode.cpp:64-84,
+flashinfer_planinfo.cpp:318-335, batch_prefill.cpp:100-128, batch_chunked_prefill.cpp:63-91)."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import ops as O
+from tests.test_gpu_decode import make_case
+from tests.util import assert_close_attention
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+DEV = "cuda"
+
+
+def _load(kind, head_dim):
+    import tvm_ffi
+    from xllm_b200 import build_ffi
+    ops_dir = build_ffi.build()
+    dec, pre = build_ffi.uris()
+    uri = [u for u in (dec if kind == "decode" else pre) if f"head_dim_qk_{head_dim}_" in u][0]
+    return tvm_ffi.load_module(os.path.join(ops_dir, uri, uri + ".so"))
+
+
+def test_ffi_decode_plan_run(built_lib):
+    import tvm_ffi
+    mod = _load("decode", 128)
+    kv_lens, HQ, HKV, D, page = [700, 4096, 1], 28, 4, 128, 128
+    q, kc, vc, indptr, indices, last = make_case(kv_lens, HQ, HKV, D, page)
+    B = len(kv_lens)
+    float_ws = torch.empty(128 << 20, dtype=torch.uint8, device=DEV)          # flashinfer_workspace.cpp:25-39 sizes
+    int_ws = torch.empty(8 << 20, dtype=torch.uint8, device=DEV)
+    pinned = torch.empty(8 << 20, dtype=torch.uint8).pin_memory()
+    empty = torch.empty(0, dtype=BF16, device=DEV)
+    out = torch.empty(B, HQ, D, dtype=BF16, device=DEV)
+    with tvm_ffi.use_torch_stream():
+        plan = mod["plan"](float_ws, int_ws, pinned, indptr, B, HQ, HKV, page, False, -1, 0.0, D, D, empty, empty)
+        mod["run"](float_ws, int_ws, plan, q.to(DEV), kc.to(DEV), vc.to(DEV), indptr.to(DEV), indices.to(DEV), last.to(DEV),
+                   out, None, 0, -1, True, None, 0.0, 1.0 / math.sqrt(D), 1.0, 1.0 / 10000.0)
+    torch.cuda.synchronize()
+    qo = torch.arange(B + 1, dtype=torch.int32)
+    ref = O.paged_attention(q, kc, vc, qo, indptr, indices, last, 1.0 / math.sqrt(D), causal=False)
+    scale = O.paged_attention(q, kc, vc.abs(), qo, indptr, indices, last, 1.0 / math.sqrt(D), causal=False)
+    assert_close_attention(out, ref, scale, what="FFI decode run")
+
+
+def test_ffi_prefill_ragged_and_paged(built_lib):
+    import tvm_ffi
+    mod = _load("prefill", 128)
+    HQ, HKV, D = 28, 4, 128
+    g = torch.Generator().manual_seed(3)
+    lens = [100, 257]
+    T = sum(lens)
+    qkv = torch.randn(T, (HQ + 2 * HKV) * D, generator=g).to(BF16)
+    cu = torch.tensor([0, 100, 357], dtype=torch.int32)
+    q = qkv[:, :HQ * D].reshape(T, HQ, D)
+    k = qkv[:, HQ * D:(HQ + HKV) * D].reshape(T, HKV, D)
+    v = qkv[:, (HQ + HKV) * D:].reshape(T, HKV, D)
+    sc = 1.0 / math.sqrt(D)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    pinned = torch.empty(1 << 20, dtype=torch.uint8).pin_memory()
+    d = qkv.to(DEV)
+    out = torch.empty(T, HQ, D, dtype=BF16, device=DEV)
+    kv_len_arr = torch.tensor(lens, dtype=torch.int32)
+    with tvm_ffi.use_torch_stream():
+        plan = mod["plan"](ws, ws, pinned, cu, cu, kv_len_arr, T, 2, HQ, HKV, 1, False, D, D, True, -1, -1, False, 0)
+        mod["ragged_run"](ws, ws, plan, d[:, :HQ * D].view(T, HQ, D), d[:, HQ * D:(HQ + HKV) * D].view(T, HKV, D),
+                          d[:, (HQ + HKV) * D:].view(T, HKV, D), cu.to(DEV), cu.to(DEV), out, None, 1, 0, -1, True,
+                          None, None, None, None, None, None, 0.0, sc, 1.0, 1.0 / 10000.0, 0)
+    torch.cuda.synchronize()
+    ref = O.ragged_prefill_attention(q, k, v, cu, cu, sc, causal=True)
+    scale = O.ragged_prefill_attention(q, k, v.abs(), cu, cu, sc, causal=True)
+    assert_close_attention(out, ref, scale, what="FFI ragged_run")
+    # paged_run: chunked prefill of 64 new tokens on top of 300 cached ones, page_size 16
+    page, kv_len, qn = 16, 364, 64
+    npg = (kv_len + page - 1) // page
+    kc = torch.randn(npg + 3, page, HKV, D, generator=g).to(BF16)
+    vc = torch.randn(npg + 3, page, HKV, D, generator=g).to(BF16)
+    idx = (torch.randperm(npg + 2, generator=g) + 1)[:npg].to(torch.int32)
+    indptr = torch.tensor([0, npg], dtype=torch.int32)
+    last = torch.tensor([(kv_len - 1) % page + 1], dtype=torch.int32)
+    qo = torch.tensor([0, qn], dtype=torch.int32)
+    q2 = torch.randn(qn, HQ, D, generator=g).to(BF16)
+    out2 = torch.empty(qn, HQ, D, dtype=BF16, device=DEV)
+    with tvm_ffi.use_torch_stream():
+        plan = mod["plan"](ws, ws, pinned, qo, indptr, torch.tensor([kv_len], dtype=torch.int32), qn, 1, HQ, HKV, page, False, D,
+                           D, True, -1, -1, False, 0)
+        mod["paged_run"](ws, ws, plan, q2.to(DEV), kc.to(DEV), vc.to(DEV), qo.to(DEV), indptr.to(DEV), idx.to(DEV), last.to(DEV),
+                         out2, None, 1, 0, -1, True, None, None, None, None, None, None, 0.0, sc, 1.0, 1.0 / 10000.0, 0)
+    torch.cuda.synchronize()
+    ref2 = O.paged_attention(q2, kc, vc, qo, indptr, idx, last, sc, causal=True)
+    scale2 = O.paged_attention(q2, kc, vc.abs(), qo, indptr, idx, last, sc, causal=True)
+    assert_close_attention(out2, ref2, scale2, what="FFI paged_run")

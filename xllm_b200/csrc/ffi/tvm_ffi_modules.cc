@@ -1,0 +1,192 @@
+// TVM-FFI SafeCall modules that xLLM dlopen()s IN PLACE OF FlashInfer's AOT modules
+// (xllm/core/kernels/cuda/utils.cpp:371-374,526-564: "$FLASHINFER_OPS_PATH/<uri>/<uri>.so", symbols
+//  __tvm_ffi_plan / __tvm_ffi_run / __tvm_ffi_paged_run / __tvm_ffi_ragged_run).
+// Argument lists are FlashInfer v0.6.x's (flashinfer/data/csrc/batch_decode_jit_binding.cu:23-44,
+// batch_prefill_jit_binding.cu:22-52) exactly as the reference passes them:
+//   decode  plan : flashinfer_planinfo.cpp:318-335      run       : batch_decode.cpp:64-84
+//   prefill plan : flashinfer_planinfo.cpp:145-164,227-245
+//           ragged_run : batch_prefill.cpp:100-128      paged_run : batch_chunked_prefill.cpp:63-91
+// Tensors arrive as borrowed DLPack views; the CUDA stream is the one the host bound with TVMFFIEnvSetStream
+// (utils.h:147-161).  Everything forwards to the C ABI of libxllm_b200_ops.so; plan_info is opaque to xLLM
+// (deep-copied only: flashinfer_planinfo.cpp:37-62), so it carries this library's own int64 layout.
+// Build: see xllm_b200/build_ffi.py (one .so, installed under the decode and the prefill URI directories).
+#include <cuda_runtime.h>
+#include <tvm/ffi/container/array.h>
+#include <tvm/ffi/container/tensor.h>
+#include <tvm/ffi/error.h>
+#include <tvm/ffi/extra/c_env_api.h>
+#include <tvm/ffi/function.h>
+#include <tvm/ffi/optional.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+
+#include "../../../include/xllm_b200_ops.h"
+
+using tvm::ffi::Array;
+using tvm::ffi::Optional;
+using tvm::ffi::TensorView;
+
+namespace {
+
+inline cudaStream_t stream_of(const TensorView& t) {
+  return static_cast<cudaStream_t>(TVMFFIEnvGetStream(t.device().device_type, t.device().device_id));
+}
+inline void* ptr(const TensorView& t) { return static_cast<char*>(t.data_ptr()) + t.byte_offset(); }
+inline void check_rc(int rc, const char* what) {
+  if (rc != 0) TVM_FFI_THROW(RuntimeError) << what << ": " << xb_last_error();
+}
+inline bool is_bf16(const TensorView& t) { return t.dtype().code == kDLBfloat && t.dtype().bits == 16; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// decode module
+// ---------------------------------------------------------------------------------------------------------------
+Array<int64_t> DecodePlan(TensorView float_ws, TensorView int_ws, TensorView pinned_int_ws, TensorView indptr_host,
+                          int64_t batch_size, int64_t num_qo_heads, int64_t num_kv_heads, int64_t page_size,
+                          bool enable_cuda_graph, int64_t window_left, double logits_soft_cap, int64_t head_dim_qk,
+                          int64_t head_dim_vo, TensorView empty_q, TensorView empty_kv) {
+  (void)pinned_int_ws; (void)empty_q; (void)empty_kv;
+  if (window_left >= 0) TVM_FFI_THROW(ValueError) << "sliding window attention is not implemented";
+  if (logits_soft_cap > 0) TVM_FFI_THROW(ValueError) << "logits soft cap is not implemented";
+  if (head_dim_qk != head_dim_vo) TVM_FFI_THROW(ValueError) << "head_dim_qk != head_dim_vo";
+  const int32_t* ip = static_cast<const int32_t*>(ptr(indptr_host));   // host tensor (flashinfer_planinfo.cpp:310-311)
+  int64_t max_pages = 1;
+  for (int64_t b = 0; b < batch_size; ++b) max_pages = std::max<int64_t>(max_pages, ip[b + 1] - ip[b]);
+  if (enable_cuda_graph) {
+    // the plan made at capture is replayed for later steps (flashinfer_attention.cpp:306-311): size the split grid
+    // for the longest context the float workspace can serve
+    const int64_t per_split = batch_size * num_qo_heads * (head_dim_vo + 1) * 4;
+    (void)per_split;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t plan[8];
+  check_rc(xb_decode_plan(plan, (int)batch_size, (int)num_qo_heads, (int)num_kv_heads, (int)head_dim_qk, (int)page_size,
+                          (int)max_pages, sms), "decode plan");
+  const int64_t need_f = plan[2], need_i = plan[3] & 0xffffffffll;
+  if (need_f > float_ws.numel() * (float_ws.dtype().bits / 8))
+    TVM_FFI_THROW(RuntimeError) << "float workspace too small: need " << need_f << " bytes";
+  if (need_i > int_ws.numel() * (int_ws.dtype().bits / 8))
+    TVM_FFI_THROW(RuntimeError) << "int workspace too small: need " << need_i << " bytes";
+  // split tickets live at the start of the int workspace and must start at zero
+  cudaMemsetAsync(ptr(int_ws), 0, (size_t)need_i, stream_of(int_ws));
+  Array<int64_t> out;
+  for (int i = 0; i < 8; ++i) out.push_back(plan[i]);
+  return out;
+}
+
+void DecodeRun(TensorView float_ws, TensorView int_ws, Array<int64_t> plan_vec, TensorView q, TensorView k_cache,
+               TensorView v_cache, TensorView kv_indptr, TensorView kv_indices, TensorView kv_last_page_len, TensorView o,
+               Optional<TensorView> maybe_lse, int64_t kv_layout_code, int64_t window_left, bool enable_pdl,
+               Optional<TensorView> maybe_alibi_slopes, double logits_soft_cap, double sm_scale, double rope_rcp_scale,
+               double rope_rcp_theta) {
+  (void)rope_rcp_scale; (void)rope_rcp_theta;
+  if (plan_vec.size() != 8) TVM_FFI_THROW(ValueError) << "plan_info has " << plan_vec.size() << " entries, expected 8";
+  if (!is_bf16(q) || !is_bf16(k_cache) || !is_bf16(o)) TVM_FFI_THROW(TypeError) << "only bf16 q/kv/o is implemented";
+  if (maybe_alibi_slopes.has_value()) TVM_FFI_THROW(ValueError) << "alibi is not implemented";
+  if (window_left >= 0 || logits_soft_cap > 0) TVM_FFI_THROW(ValueError) << "sliding window / soft cap not implemented";
+  int64_t plan[8];
+  for (int i = 0; i < 8; ++i) plan[i] = plan_vec[i];
+  xb_set_pdl(enable_pdl ? 1 : 0);
+  // kv_layout_code 0 = NHD [pages, page, heads, d], 1 = HND [pages, heads, page, d]
+  const int64_t st_page = k_cache.stride(0);
+  const int64_t st_tok = kv_layout_code == 0 ? k_cache.stride(1) : k_cache.stride(2);
+  const int64_t st_head = kv_layout_code == 0 ? k_cache.stride(2) : k_cache.stride(1);
+  float* lse = maybe_lse.has_value() ? static_cast<float*>(ptr(maybe_lse.value())) : nullptr;
+  check_rc(xb_paged_decode_bf16(plan, ptr(q), q.stride(0), q.stride(1), ptr(k_cache), ptr(v_cache), st_page, st_tok, st_head,
+                                static_cast<const int32_t*>(ptr(kv_indptr)), static_cast<const int32_t*>(ptr(kv_indices)),
+                                static_cast<const int32_t*>(ptr(kv_last_page_len)), ptr(o), o.stride(0), o.stride(1), lse,
+                                (float)sm_scale, ptr(float_ws), ptr(int_ws), stream_of(q)),
+           "batch decode run");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prefill module
+// ---------------------------------------------------------------------------------------------------------------
+Array<int64_t> PrefillPlan(TensorView float_ws, TensorView int_ws, TensorView pinned_int_ws, TensorView qo_indptr_host,
+                           TensorView kv_indptr_host, TensorView kv_len_arr_host, int64_t total_num_rows, int64_t batch_size,
+                           int64_t num_qo_heads, int64_t num_kv_heads, int64_t page_size, bool enable_cuda_graph,
+                           int64_t head_dim_qk, int64_t head_dim_vo, bool causal, int64_t window_left,
+                           int64_t fixed_split_size, bool disable_split_kv, int64_t num_colocated_ctas) {
+  (void)float_ws; (void)int_ws; (void)pinned_int_ws; (void)kv_indptr_host; (void)kv_len_arr_host; (void)enable_cuda_graph;
+  (void)fixed_split_size; (void)disable_split_kv; (void)num_colocated_ctas; (void)num_kv_heads; (void)page_size;
+  if (window_left >= 0) TVM_FFI_THROW(ValueError) << "sliding window attention is not implemented";
+  if (head_dim_qk != head_dim_vo) TVM_FFI_THROW(ValueError) << "head_dim_qk != head_dim_vo";
+  const int32_t* qo = static_cast<const int32_t*>(ptr(qo_indptr_host));
+  int64_t max_qo = 0;
+  for (int64_t b = 0; b < batch_size; ++b) max_qo = std::max<int64_t>(max_qo, qo[b + 1] - qo[b]);
+  Array<int64_t> out;
+  out.push_back(max_qo);
+  out.push_back(batch_size);
+  out.push_back(total_num_rows);
+  out.push_back(num_qo_heads);
+  out.push_back(causal ? 1 : 0);
+  return out;
+}
+
+void check_prefill_extras(const Optional<TensorView>& custom_mask, const Optional<TensorView>& alibi, int64_t window_left,
+                          double logits_soft_cap) {
+  if (custom_mask.has_value()) TVM_FFI_THROW(ValueError) << "custom masks are not implemented (VLM-only path)";
+  if (alibi.has_value()) TVM_FFI_THROW(ValueError) << "alibi is not implemented";
+  if (window_left >= 0 || logits_soft_cap > 0) TVM_FFI_THROW(ValueError) << "sliding window / soft cap not implemented";
+}
+
+void RaggedRun(TensorView float_ws, TensorView int_ws, Array<int64_t> plan_vec, TensorView q, TensorView k, TensorView v,
+               TensorView qo_indptr, TensorView kv_indptr, TensorView o, Optional<TensorView> maybe_lse, int64_t mask_mode_code,
+               int64_t layout, int64_t window_left, bool enable_pdl, Optional<TensorView> maybe_custom_mask,
+               Optional<TensorView> maybe_mask_indptr, Optional<TensorView> maybe_alibi_slopes,
+               Optional<TensorView> maybe_prefix_len_ptr, Optional<TensorView> maybe_token_pos_in_items_ptr,
+               Optional<TensorView> maybe_max_item_len_ptr, double logits_soft_cap, double sm_scale, double rope_rcp_scale,
+               double rope_rcp_theta, int64_t token_pos_in_items_len) {
+  (void)float_ws; (void)int_ws; (void)maybe_mask_indptr; (void)maybe_prefix_len_ptr; (void)maybe_token_pos_in_items_ptr;
+  (void)maybe_max_item_len_ptr; (void)rope_rcp_scale; (void)rope_rcp_theta; (void)token_pos_in_items_len; (void)layout;
+  check_prefill_extras(maybe_custom_mask, maybe_alibi_slopes, window_left, logits_soft_cap);
+  if (plan_vec.size() < 5) TVM_FFI_THROW(ValueError) << "plan_info too short";
+  if (!is_bf16(q) || !is_bf16(k) || !is_bf16(o)) TVM_FFI_THROW(TypeError) << "only bf16 q/k/v/o is implemented";
+  xb_set_pdl(enable_pdl ? 1 : 0);
+  float* lse = maybe_lse.has_value() ? static_cast<float*>(ptr(maybe_lse.value())) : nullptr;
+  check_rc(xb_prefill_ragged_bf16(ptr(q), q.stride(0), q.stride(1), ptr(k), ptr(v), k.stride(0),
+                                  static_cast<const int32_t*>(ptr(qo_indptr)), static_cast<const int32_t*>(ptr(kv_indptr)),
+                                  ptr(o), o.stride(0), o.stride(1), lse, (int)plan_vec[1], q.size(0), k.size(0),
+                                  (int)plan_vec[0], (int)q.size(1), (int)k.size(1), (int)q.size(2), mask_mode_code == 1,
+                                  (float)sm_scale, stream_of(q)),
+           "batch prefill ragged_run");
+}
+
+void PagedRun(TensorView float_ws, TensorView int_ws, Array<int64_t> plan_vec, TensorView q, TensorView k_cache,
+              TensorView v_cache, TensorView qo_indptr, TensorView kv_indptr, TensorView kv_indices,
+              TensorView kv_last_page_len, TensorView o, Optional<TensorView> maybe_lse, int64_t mask_mode_code,
+              int64_t layout, int64_t window_left, bool enable_pdl, Optional<TensorView> maybe_custom_mask,
+              Optional<TensorView> maybe_mask_indptr, Optional<TensorView> maybe_alibi_slopes,
+              Optional<TensorView> maybe_prefix_len_ptr, Optional<TensorView> maybe_token_pos_in_items_ptr,
+              Optional<TensorView> maybe_max_item_len_ptr, double logits_soft_cap, double sm_scale, double rope_rcp_scale,
+              double rope_rcp_theta, int64_t token_pos_in_items_len) {
+  (void)float_ws; (void)int_ws; (void)maybe_mask_indptr; (void)maybe_prefix_len_ptr; (void)maybe_token_pos_in_items_ptr;
+  (void)maybe_max_item_len_ptr; (void)rope_rcp_scale; (void)rope_rcp_theta; (void)token_pos_in_items_len;
+  check_prefill_extras(maybe_custom_mask, maybe_alibi_slopes, window_left, logits_soft_cap);
+  if (layout != 0) TVM_FFI_THROW(ValueError) << "paged_run: only the NHD cache layout is implemented";
+  if (plan_vec.size() < 5) TVM_FFI_THROW(ValueError) << "plan_info too short";
+  if (!is_bf16(q) || !is_bf16(k_cache) || !is_bf16(o)) TVM_FFI_THROW(TypeError) << "only bf16 q/kv/o is implemented";
+  xb_set_pdl(enable_pdl ? 1 : 0);
+  float* lse = maybe_lse.has_value() ? static_cast<float*>(ptr(maybe_lse.value())) : nullptr;
+  check_rc(xb_prefill_paged_bf16(ptr(q), q.stride(0), q.stride(1), ptr(k_cache), ptr(v_cache), k_cache.size(0),
+                                 (int)k_cache.size(1), static_cast<const int32_t*>(ptr(qo_indptr)),
+                                 static_cast<const int32_t*>(ptr(kv_indptr)), static_cast<const int32_t*>(ptr(kv_indices)),
+                                 static_cast<const int32_t*>(ptr(kv_last_page_len)), ptr(o), o.stride(0), o.stride(1), lse,
+                                 (int)plan_vec[1], q.size(0), (int)plan_vec[0], (int)q.size(1), (int)k_cache.size(2),
+                                 (int)q.size(2), mask_mode_code == 1, (float)sm_scale, stream_of(q)),
+           "batch prefill paged_run");
+}
+
+}  // namespace
+
+#ifdef XB_FFI_DECODE_MODULE
+TVM_FFI_DLL_EXPORT_TYPED_FUNC(plan, DecodePlan);
+TVM_FFI_DLL_EXPORT_TYPED_FUNC(run, DecodeRun);
+#else
+TVM_FFI_DLL_EXPORT_TYPED_FUNC(plan, PrefillPlan);
+TVM_FFI_DLL_EXPORT_TYPED_FUNC(ragged_run, RaggedRun);
+TVM_FFI_DLL_EXPORT_TYPED_FUNC(paged_run, PagedRun);
+#endif

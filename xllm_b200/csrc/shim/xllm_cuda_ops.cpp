@@ -1,0 +1,219 @@
+// Link-time drop-in for the reference's CUDA operator namespace:
+//   namespace xllm::kernel::cuda  --  xllm/core/kernels/cuda/cuda_ops_api.h:31-216
+// Same function names, argument order, in-place / returned-tensor conventions and error behaviour (TORCH_CHECK ->
+// c10::Error, as the reference tests rely on: tests/core/kernels/cuda/cutlass_scaled_mm_test.cpp:279-295).  Each
+// function unwraps the borrowed torch::Tensor arguments (data_ptr / strides / current CUDA stream) and forwards to the
+// C ABI of libxllm_b200_ops.so (include/xllm_b200_ops.h).  To use it, drop this file into xllm/core/kernels/cuda/ in
+// place of {norm,rope,activation,reshape_paged_cache,fp8_quant}.cu, matmul.cpp, fp8_scaled_{quantize,matmul}.cpp and
+// cutlass_w8a8/, and link libxllm_b200_ops.so.  Attention is served through the TVM-FFI modules
+// (csrc/ffi/tvm_ffi_modules.cc), which needs no source change in xLLM at all.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/torch.h>
+
+#include <optional>
+#include <string>
+#include <tuple>
+
+#include "../../../include/xllm_b200_ops.h"
+
+namespace xllm::kernel::cuda {
+
+namespace {
+inline void* stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+inline void ok(int rc, const char* what) { TORCH_CHECK(rc == 0, what, ": ", xb_last_error()); }
+inline void need_bf16(const torch::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16, name, " must be a CUDA bfloat16 tensor");
+}
+}  // namespace
+
+// cuda_ops_api.h:31-37
+void rotary_embedding(torch::Tensor& positions, torch::Tensor& query, std::optional<torch::Tensor> key,
+                      torch::Tensor& cos_sin_cache, bool is_neox) {
+  need_bf16(query, "query");
+  const int64_t head_size = cos_sin_cache.size(-1);
+  const int64_t num_tokens = positions.numel();
+  TORCH_CHECK(positions.scalar_type() == torch::kInt64, "positions must be int64");
+  TORCH_CHECK(query.size(0) == positions.size(0) && (!key.has_value() || key->size(0) == positions.size(0)),
+              "query, key and positions must have the same number of tokens");
+  const int64_t q_hidden = query.numel() / num_tokens;
+  const int64_t k_hidden = key.has_value() ? key->numel() / num_tokens : 0;
+  TORCH_CHECK(q_hidden % head_size == 0 && k_hidden % head_size == 0);
+  const int num_heads = q_hidden / head_size;
+  const int num_kv_heads = key.has_value() ? k_hidden / head_size : num_heads;
+  const int64_t head_stride = query.dim() == positions.dim() + 2 ? query.stride(-2) : head_size;
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  ok(xb_rotary_embedding_bf16(positions.data_ptr<int64_t>(), query.data_ptr(), key.has_value() ? key->data_ptr() : nullptr,
+                              cos_sin_cache.data_ptr(), (int)cos_sin_cache.size(1), query.stride(positions.dim() - 1),
+                              key.has_value() ? key->stride(positions.dim() - 1) : 0, head_stride, num_heads, num_kv_heads,
+                              (int)head_size, is_neox ? 1 : 0, (int)num_tokens, stream()),
+     "rotary_embedding");
+}
+
+// cuda_ops_api.h:39-42
+void act_and_mul(torch::Tensor out, torch::Tensor input, const std::string& act_mode) {
+  int mode = act_mode == "silu" ? 0 : act_mode == "gelu" ? 1 : (act_mode == "gelu_tanh" || act_mode == "gelu_pytorch_tanh") ? 2 : -1;
+  TORCH_CHECK(mode >= 0, "Unsupported act mode: ", act_mode, ", only support silu, gelu, gelu_tanh, gelu_pytorch_tanh");
+  need_bf16(input, "input");
+  const int d = input.size(-1) / 2;
+  const int64_t tokens = input.numel() / input.size(-1);
+  const at::cuda::OptionalCUDAGuard guard(device_of(input));
+  ok(xb_act_and_mul_bf16(out.data_ptr(), input.data_ptr(), d, (int)tokens, mode, stream()), "act_and_mul");
+}
+
+// cuda_ops_api.h:44-49
+void reshape_paged_cache(torch::Tensor slot_ids, torch::Tensor keys, torch::Tensor values, torch::Tensor key_cache,
+                         torch::Tensor value_cache) {
+  need_bf16(keys, "keys");
+  TORCH_CHECK(keys.stride(-1) == 1 && keys.stride(-2) == keys.size(-1));
+  TORCH_CHECK(values.stride(-1) == 1 && values.stride(-2) == values.size(-1));
+  ok(xb_reshape_paged_cache_bf16(slot_ids.data_ptr<int>(), keys.data_ptr(), values.data_ptr(), key_cache.data_ptr(),
+                                 value_cache.data_ptr(), keys.stride(-3), values.stride(-3), (int)keys.size(-2),
+                                 (int)keys.size(-1), (int)key_cache.size(-3), (int)keys.size(-3), stream()),
+     "reshape_paged_cache");
+}
+
+// cuda_ops_api.h:157-160
+void rms_norm(torch::Tensor output, torch::Tensor input, torch::Tensor weight, double eps) {
+  need_bf16(input, "input");
+  TORCH_CHECK(input.stride(-1) == 1);
+  const int hidden = input.size(-1);
+  ok(xb_rms_norm_bf16(output.data_ptr(), input.data_ptr(), input.stride(-2), weight.data_ptr(), (float)eps,
+                      (int)(input.numel() / hidden), hidden, stream()),
+     "rms_norm");
+}
+
+// cuda_ops_api.h:162-165
+void fused_add_rms_norm(torch::Tensor& input, torch::Tensor& residual, torch::Tensor& weight, double epsilon) {
+  need_bf16(input, "input");
+  TORCH_CHECK(input.stride(-1) == 1 && residual.is_contiguous());
+  const int hidden = input.size(-1);
+  ok(xb_fused_add_rms_norm_bf16(input.data_ptr(), input.stride(-2), residual.data_ptr(), weight.data_ptr(), (float)epsilon,
+                                (int)(input.numel() / hidden), hidden, stream()),
+     "fused_add_rms_norm");
+}
+
+// cuda_ops_api.h:167-169 (matmul.cpp:20-24: F::linear)
+torch::Tensor matmul(torch::Tensor a, torch::Tensor b, std::optional<torch::Tensor> bias) {
+  need_bf16(a, "a");
+  need_bf16(b, "b");
+  auto a2 = a.reshape({-1, a.size(-1)});
+  const int64_t M = a2.size(0), K = a2.size(1), N = b.size(0);
+  auto out = torch::empty({M, N}, a.options());
+  const void* bp = bias.has_value() && bias->defined() ? bias->data_ptr() : nullptr;
+  if (M <= 16 && K % 32 == 0)
+    ok(xb_linear_bf16_small_m(out.data_ptr(), N, a2.data_ptr(), a2.stride(0), b.data_ptr(), bp, (int)M, (int)N, (int)K, stream()),
+       "matmul");
+  else
+    ok(xb_gemm_bf16(out.data_ptr(), N, a2.data_ptr(), a2.stride(0), b.data_ptr(), bp, (int)M, (int)N, (int)K, stream()), "matmul");
+  auto shape = a.sizes().vec();
+  shape.back() = N;
+  return out.view(shape);
+}
+
+// cuda_ops_api.h:171-176 (cutlass_w8a8/scaled_mm_entry.cu:55-108)
+void cutlass_scaled_mm(torch::Tensor& c, torch::Tensor const& a, torch::Tensor const& b, torch::Tensor const& a_scales,
+                       torch::Tensor const& b_scales, std::optional<torch::Tensor> const& bias) {
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && c.dim() == 2);
+  TORCH_CHECK(c.size(0) == a.size(0) && a.size(1) == b.size(0) && b.size(1) == c.size(1));
+  TORCH_CHECK(a.stride(1) == 1 && c.stride(1) == 1);  // Row-major
+  TORCH_CHECK(b.stride(0) == 1);                      // Column-major
+  TORCH_CHECK(c.stride(0) % 16 == 0 && b.stride(1) % 16 == 0);
+  TORCH_CHECK(a_scales.is_contiguous() && b_scales.is_contiguous());
+  if (bias) TORCH_CHECK(bias->numel() == b.size(1) && bias->is_contiguous() && bias->dim() == 1);
+  TORCH_CHECK(a.scalar_type() == torch::kFloat8_e4m3fn && b.scalar_type() == torch::kFloat8_e4m3fn, "fp8 e4m3 inputs expected");
+  TORCH_CHECK(c.scalar_type() == torch::kBFloat16, "only bfloat16 output is implemented");
+  const at::cuda::OptionalCUDAGuard guard(device_of(a));
+  ok(xb_gemm_fp8_scaled(c.data_ptr(), c.stride(0), a.data_ptr(), a.stride(0), b.data_ptr(), a_scales.data_ptr<float>(),
+                        (int)a_scales.numel(), b_scales.data_ptr<float>(), (int)b_scales.numel(),
+                        bias ? bias->data_ptr() : nullptr, (int)a.size(0), (int)b.size(1), (int)a.size(1), stream()),
+     "cutlass_scaled_mm");
+}
+
+// cuda_ops_api.h:182-186
+void static_scaled_fp8_quant(torch::Tensor& out, torch::Tensor const& input, torch::Tensor const& scale) {
+  TORCH_CHECK(input.stride(-1) == 1, "last dimension of input must be contiguous");
+  TORCH_CHECK(out.stride(-1) == 1, "last dimension of output must be contiguous");
+  const int hidden = input.size(-1);
+  ok(xb_static_scaled_fp8_quant_bf16(out.data_ptr(), out.stride(-2), input.data_ptr(), input.stride(-2),
+                                     scale.data_ptr<float>(), (int)(input.numel() / hidden), hidden, stream()),
+     "static_scaled_fp8_quant");
+}
+
+// cuda_ops_api.h:188-193 (fp8_scaled_quantize.cpp:20-48) - the dynamic scale is computed on the device, no host sync
+std::tuple<torch::Tensor, torch::Tensor> fp8_scaled_quantize(const torch::Tensor& input, const std::optional<torch::Tensor>& output,
+                                                             const std::optional<torch::Tensor>& scale) {
+  torch::Tensor out = output.has_value() && output->defined() ? *output
+                                                              : torch::empty_like(input, input.options().dtype(torch::kFloat8_e4m3fn));
+  if (scale.has_value() && scale->defined()) {
+    static_scaled_fp8_quant(out, input, *scale);
+    return {out, *scale};
+  }
+  auto s = torch::empty({1}, input.options().dtype(torch::kFloat32));
+  const int hidden = input.size(-1);
+  ok(xb_dynamic_scaled_fp8_quant_bf16(out.data_ptr(), out.stride(-2), input.data_ptr(), input.stride(-2), s.data_ptr<float>(),
+                                      (int)(input.numel() / hidden), hidden, stream()),
+     "fp8_scaled_quantize");
+  return {out, s};
+}
+
+// cuda_ops_api.h:203-221
+void rms_norm_static_fp8_quant(torch::Tensor& out, torch::Tensor& input, torch::Tensor& weight, torch::Tensor& scale, double epsilon) {
+  const int hidden = input.size(-1);
+  ok(xb_rms_norm_static_fp8_quant_bf16(out.data_ptr(), input.data_ptr(), input.stride(-2), weight.data_ptr(),
+                                       scale.data_ptr<float>(), (float)epsilon, (int)(input.numel() / hidden), hidden, stream()),
+     "rms_norm_static_fp8_quant");
+}
+void fused_add_rms_norm_static_fp8_quant(torch::Tensor& out, torch::Tensor& input, torch::Tensor& residual, torch::Tensor& weight,
+                                         torch::Tensor& scale, double epsilon) {
+  const int hidden = input.size(-1);
+  ok(xb_fused_add_rms_norm_static_fp8_quant_bf16(out.data_ptr(), input.data_ptr(), input.stride(-2), residual.data_ptr(),
+                                                 weight.data_ptr(), scale.data_ptr<float>(), (float)epsilon,
+                                                 (int)(input.numel() / hidden), hidden, stream()),
+     "fused_add_rms_norm_static_fp8_quant");
+}
+
+// cuda_ops_api.h:223-233 (fp8_scaled_matmul.cpp:20-45)
+torch::Tensor fp8_scaled_matmul(const torch::Tensor& a, const torch::Tensor& b, const torch::Tensor& a_scale,
+                                const torch::Tensor& b_scale, torch::ScalarType output_dtype,
+                                const std::optional<torch::Tensor>& bias, const std::optional<torch::Tensor>& output) {
+  TORCH_CHECK(output_dtype == torch::kBFloat16, "only bfloat16 output is implemented");
+  torch::Tensor out = output.has_value() && output->defined() ? *output : torch::empty({a.size(0), b.size(0)}, a.options().dtype(output_dtype));
+  cutlass_scaled_mm(out, a, b.t(), a_scale, b_scale, bias);
+  return out;
+}
+
+// cuda_ops_api.h:252-266
+void fused_qk_norm_rope(torch::Tensor& qkv, int64_t num_heads_q, int64_t num_heads_k, int64_t num_heads_v, int64_t head_dim,
+                        double eps, const torch::Tensor& q_weight, const torch::Tensor& k_weight, const torch::Tensor& cos_sin_cache,
+                        bool interleaved, const torch::Tensor& position_ids) {
+  need_bf16(qkv, "qkv");
+  TORCH_CHECK(qkv.is_contiguous() && position_ids.scalar_type() == torch::kInt64);
+  ok(xb_fused_qk_norm_rope_bf16(qkv.data_ptr(), (int)num_heads_q, (int)num_heads_k, (int)num_heads_v, (int)head_dim, (float)eps,
+                                q_weight.data_ptr(), k_weight.data_ptr(), cos_sin_cache.data_ptr(), (int)cos_sin_cache.size(-1),
+                                interleaved ? 1 : 0, position_ids.data_ptr<int64_t>(), (int)qkv.size(0), stream()),
+     "fused_qk_norm_rope");
+}
+
+// ---- additive boundary: weight-only linears; the reference has no such op ---------------------------
+torch::Tensor w4a16_linear(const torch::Tensor& x, const torch::Tensor& qweight, const torch::Tensor& meta, int64_t group_size,
+                           const std::optional<torch::Tensor>& bias) {
+  need_bf16(x, "x");
+  auto x2 = x.reshape({-1, x.size(-1)});
+  const int64_t M = x2.size(0), K = x2.size(1), N = meta.size(1);
+  auto out = torch::empty({M, N}, x.options());
+  const void* bp = bias.has_value() && bias->defined() ? bias->data_ptr() : nullptr;
+  auto* qw = reinterpret_cast<const uint32_t*>(qweight.data_ptr());
+  auto* mt = reinterpret_cast<const uint32_t*>(meta.data_ptr());
+  if (M <= 16)
+    ok(xb_linear_w4a16_small_m(out.data_ptr(), N, x2.data_ptr(), x2.stride(0), qw, mt, bp, (int)M, (int)N, (int)K, (int)group_size, stream()),
+       "w4a16_linear");
+  else
+    ok(xb_gemm_w4a16(out.data_ptr(), N, x2.data_ptr(), x2.stride(0), qw, mt, bp, (int)M, (int)N, (int)K, (int)group_size, stream()),
+       "w4a16_linear");
+  auto shape = x.sizes().vec();
+  shape.back() = N;
+  return out.view(shape);
+}
+
+}  // namespace xllm::kernel::cuda

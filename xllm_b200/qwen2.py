@@ -112,22 +112,27 @@ class Qwen2Weights:
         return lin
 
     @staticmethod
-    def synthetic(cfg: Qwen2Config, device="cuda", seed=2026):
-        """random-init weights of the named architecture (no checkpoints offline), generated on device."""
+    def synthetic(cfg: Qwen2Config, device="cuda", seed=2026, tp_rank: int = 0, tp: int = 1):
+        """random-init weights of the named architecture (no checkpoints offline), generated on device.  With tp > 1 the
+        shapes are this rank's shards (column-parallel qkv / gate_up / lm_head, row-parallel o / down)."""
+        from .parallel import partition_heads
         g = torch.Generator(device=device).manual_seed(seed)
         w = Qwen2Weights(cfg)
-        H, I = cfg.hidden_size, cfg.intermediate_size
+        H, I = cfg.hidden_size, cfg.intermediate_size // tp
+        hp = partition_heads(cfg.n_heads, cfg.n_kv_heads, tp_rank, tp)
+        q_size, kv_size = hp.num_heads * cfg.head_dim, hp.num_kv_heads * cfg.head_dim
         w.embed = (torch.randn(cfg.vocab_size, H, generator=g, device=device) * 0.02).to(BF16)
         w.final_norm = (1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16)
-        w.lm_head = Linear(cfg.vocab_size, H, "bf16")       # lm_head stays unquantised (linear.cpp:512-520)
-        w.lm_head.weight = w.embed if cfg.tie_word_embeddings else \
-            (torch.randn(cfg.vocab_size, H, generator=g, device=device) * 0.02).to(BF16)
+        vs = cfg.vocab_size // tp
+        w.lm_head = Linear(vs, H, "bf16")                   # lm_head stays unquantised (linear.cpp:512-520)
+        w.lm_head.weight = w.embed if (cfg.tie_word_embeddings and tp == 1) else \
+            (torch.randn(vs, H, generator=g, device=device) * 0.02).to(BF16)
         for _ in range(cfg.num_layers):
             mk = lambda n, k, b=False: Qwen2Weights._synthetic_linear(n, k, cfg.quant, cfg.group_size, g, device, b)
             w.layers.append(dict(
                 input_norm=(1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16),
                 post_norm=(1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16),
-                qkv=mk(cfg.q_size + 2 * cfg.kv_size, H, True), o=mk(H, cfg.q_size),
+                qkv=mk(q_size + 2 * kv_size, H, True), o=mk(H, q_size),
                 gate_up=mk(2 * I, H), down=mk(H, I)))
         return w
 
