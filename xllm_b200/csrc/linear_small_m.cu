@@ -78,7 +78,8 @@ struct XRing {
 };
 
 template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth,
-          int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */, int kOcc = 2 /* CTAs per SM */>
+          int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */, int kOcc = 2 /* CTAs per SM */,
+          int kAccSets = 0 /* 0: default for kMT */>
 __global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : kOcc)
 linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
                             int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
@@ -100,7 +101,7 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 
   // kAcc independent accumulator sets (one per k16 step of a tile when registers allow): legacy HMMA has a long
   // issue-to-result latency on sm_100, a single chain per warp leaves the scheduler with nothing eligible
-  constexpr int kAcc = kMT == 1 ? 4 : (kMT == 2 ? 2 : 1);
+  constexpr int kAcc = kAccSets > 0 ? kAccSets : (kMT == 1 ? 4 : (kMT == 2 ? 2 : 1));
   float accj[kAcc][kMT][4];
 #pragma unroll
   for (int a = 0; a < kAcc; ++a)
@@ -365,12 +366,15 @@ extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
   int gshift = 0;
   while ((1 << gshift) < tpg) ++gshift;
   const bool tg2 = tpg >= 2;
-  static const bool occ3 = [] { const char* e = getenv("XB_W4_OCC"); return e && atoi(e) == 3; }();
+  static const int occ3 = [] { const char* e = getenv("XB_W4_OCC"); return e ? atoi(e) : 0; }();
 #define XB_W4_LAUNCH(MT, SP, DP)                                                                              \
   {                                                                                                           \
     dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                              \
-    if (tg2 && MT == 1 && occ3) {                                                                             \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2, 3>, grid, block, 0, s, true, yy, \
+    if (tg2 && MT == 1 && occ3 == 3) {                                                                        \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, 2, 2, 3, 2>, grid, block, 0, s, true, yy,         \
+                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
+    } else if (tg2 && MT == 1 && occ3 == 4) {                                                                 \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, 2, 2, 4, 1>, grid, block, 0, s, true, yy,         \
                         y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
     } else if (tg2) {                                                                                         \
       XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2>, grid, block, 0, s, true, yy,    \
