@@ -71,7 +71,8 @@ def test_paged_decode_matches_oracle(kv_lens, HQ, HKV, D, page, built_lib):
     out, lse, plan = run_gpu(q, kc, vc, indptr, indices, last, page, max_pages, lse=True)
     scale = O.paged_attention(q, kc, vc.abs(), qo, indptr, indices, last, 1.0 / math.sqrt(D), causal=False)
     assert_close_attention(out, ref, scale, what=f"paged_decode {kv_lens} splits={plan.max_splits}")
-    assert torch.allclose(lse.cpu(), ref_lse, rtol=1e-4, atol=1e-4), "base-2 LSE mismatch"
+    # l sums bf16-rounded P relative to the running maximum of the tile order: log2(l) moves by ~2^-9 / ln 2
+    assert torch.allclose(lse.cpu(), ref_lse, rtol=1e-4, atol=5e-3), "base-2 LSE mismatch"
 
 
 def test_paged_decode_upper_bound_plan(built_lib):

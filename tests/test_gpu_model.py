@@ -59,5 +59,5 @@ def test_layerwise_teacher_forced(quant, built_lib):
     per op in test_gpu_{elementwise,linear,decode,prefill,gemm}.py."""
     cfg = _small(quant)
     for li, (gx, rx, gres, rres) in enumerate(run_layerwise_parity(cfg, [37, 300, 1])):
-        assert_close_bf16(gres, rres, ulps=2, rel_l2=3e-3, what=f"layer {li} residual stream", atol=2.0 ** -7)
+        assert_close_bf16(gres, rres, ulps=2, rel_l2=3e-3, what=f"layer {li} residual stream", atol=2.0 ** -6)
         assert_close_bf16(gx, rx, ulps=1e9, rel_l2=1e-2, what=f"layer {li} normalised output")
