@@ -79,7 +79,7 @@ struct XRing {
 
 template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth,
           int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */, int kOcc = 2 /* CTAs per SM */,
-          int kAccSets = 0 /* 0: default for kMT */>
+          int kAccSets = 0 /* 0: default for kMT */, bool kFmaShift = false /* right shifts as IMAD.HI (fma pipe) */>
 __global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : kOcc)
 linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
                             int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
@@ -161,9 +161,10 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
       for (int j = 0; j < 4; ++j) {
         const uint32_t w = wv[j];
         const uint32_t q0 = lop3_and_or(w, 0x000f000fu, 0x43004300u);
-        const uint32_t q1 = lop3_and_or(w >> 4, 0x000f000fu, 0x43004300u);
-        const uint32_t q2 = lop3_and_or(w >> 8, 0x000f000fu, 0x43004300u);
-        const uint32_t q3 = lop3_and_or(w >> 12, 0x000f000fu, 0x43004300u);
+        // right shifts either as SHF (alu pipe) or as IMAD.HI (fma pipe) to balance the two issue pipes
+        const uint32_t q1 = lop3_and_or(kFmaShift ? __umulhi(w, 1u << 28) : (w >> 4), 0x000f000fu, 0x43004300u);
+        const uint32_t q2 = lop3_and_or(kFmaShift ? __umulhi(w, 1u << 24) : (w >> 8), 0x000f000fu, 0x43004300u);
+        const uint32_t q3 = lop3_and_or(kFmaShift ? __umulhi(w, 1u << 20) : (w >> 12), 0x000f000fu, 0x43004300u);
         const uint32_t a0 = hmul2_bf16(hsub2_bf16(q0, z0), s0);
         const uint32_t a1 = hmul2_bf16(hsub2_bf16(q1, z1), s1);
         const uint32_t a2 = hmul2_bf16(hsub2_bf16(q2, z0), s0);
@@ -372,6 +373,15 @@ extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
     dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                              \
     if (tg2 && MT == 1 && occ3 == 3) {                                                                        \
       XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, 2, 2, 3, 2>, grid, block, 0, s, true, yy,         \
+                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
+    } else if (tg2 && MT == 1 && occ3 == 5) {                                                                 \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2, 2, 0, true>, grid, block, 0, s,  \
+                        true, yy, y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                    \
+    } else if (tg2 && MT == 1 && occ3 == 6) {                                                                 \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, 3, 2, 3, 2>, grid, block, 0, s, true, yy,         \
+                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
+    } else if (tg2 && MT == 1 && occ3 == 7) {                                                                 \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, 4, 2, 3, 1>, grid, block, 0, s, true, yy,         \
                         y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
     } else if (tg2 && MT == 1 && occ3 == 4) {                                                                 \
       XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, 2, 2, 4, 1>, grid, block, 0, s, true, yy,         \
