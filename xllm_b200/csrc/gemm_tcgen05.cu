@@ -96,12 +96,13 @@ struct GemmParams {
 constexpr int kBlockM = 128;
 constexpr int kNumEpiWarps = 4;
 
-template <int kKind, int kBlockN>
+template <int kKind, int kBlockN, int kMT = 1 /* 128-row M tiles per CTA sharing one B stage */>
 struct GemmCfg {
+  static constexpr int kCtaM = kBlockM * kMT;
   static constexpr int kElemA = kKind == kKindFP8 ? 1 : 2;
   static constexpr int kBlockK = 128 / kElemA;                     // one 128-byte swizzle row per tile row
   static constexpr int kUmmaK = 32 / kElemA;                       // 16 (bf16) / 32 (fp8) elements = 32 bytes
-  static constexpr int kABytes = kBlockM * 128;
+  static constexpr int kABytes = kCtaM * 128;
   static constexpr int kBBytes = kBlockN * 128;
   static constexpr int kPackedBytes = kKind == kKindW4 ? kBlockN * kBlockK / 2 : 0;   // int4 tile
   static constexpr int kMetaBytes = kKind == kKindW4 ? kBlockN * 4 : 0;
@@ -116,16 +117,18 @@ struct GemmCfg {
   static constexpr int kBudget = 227 * 1024 - 1024 - 512 - kEpiStageBytes - kBStages * kBBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kThreads = (2 + kNumEpiWarps + kConvWarps) * 32;
-  static constexpr int kTmemCols = 2 * kBlockN;                    // two accumulator stages
+  static constexpr int kAccCols = kMT * kBlockN;                     // one accumulator stage
+  static constexpr int kTmemCols = 2 * kAccCols;                   // two accumulator stages
+  static_assert(kTmemCols <= 512, "TMEM has 512 columns");
   static constexpr int kSmemBytes = kStages * kStageBytes + kBStages * kBBytes + kEpiStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
-template <int kKind, int kBlockN>
-__global__ void __launch_bounds__(GemmCfg<kKind, kBlockN>::kThreads, 1)
+template <int kKind, int kBlockN, int kMT>
+__global__ void __launch_bounds__(GemmCfg<kKind, kBlockN, kMT>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_m,
                     const GemmParams p) {
-  using Cfg = GemmCfg<kKind, kBlockN>;
+  using Cfg = GemmCfg<kKind, kBlockN, kMT>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -142,7 +145,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blocks = (p.M + kBlockM - 1) / kBlockM;
+  const int m_blocks = (p.M + Cfg::kCtaM - 1) / Cfg::kCtaM;
   const int n_blocks = (p.N + kBlockN - 1) / kBlockN;
   const int num_tiles = m_blocks * n_blocks;
   const int num_kb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;
@@ -201,10 +204,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_load_2d(stage_packed(s), &tmap_b, packed_bar + s, kb * 128, n_blk * (kBlockN / 16));
             tma_load_2d(stage_meta(s), &tmap_m, packed_bar + s, n_blk * kBlockN, kb >> p.gshift);
             mbar_expect_tx(full_bar + s, Cfg::kABytes);
-            tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, m_blk * kBlockM);
+            tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, m_blk * Cfg::kCtaM);
           } else {
             mbar_expect_tx(full_bar + s, Cfg::kABytes + Cfg::kBBytes);
-            tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, m_blk * kBlockM);
+            tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, m_blk * Cfg::kCtaM);
             tma_load_2d(stage_b(s), &tmap_b, full_bar + s, kb * Cfg::kBlockK, n_blk * kBlockN);
           }
           if (++s == kStages) { s = 0; ph ^= 1; }
@@ -223,7 +226,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(tmem_empty + as, aph ^ 1);     // epilogue has drained this accumulator stage
       tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + as * kBlockN;
+      const uint32_t d_tmem = tmem_base + as * Cfg::kAccCols;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar + s, ph);
         if (kKind == kKindW4) mbar_wait(bready_bar + bs, bph);
@@ -233,9 +236,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t b_addr = smem_u32(kKind == kKindW4 ? b_ring(bs) : stage_b(s));
 #pragma unroll
           for (int k = 0; k < Cfg::kBlockK / Cfg::kUmmaK; ++k) {
-            const uint64_t da = umma_desc_sw128(a_addr + k * 32), db = umma_desc_sw128(b_addr + k * 32);
-            if (kKind == kKindFP8) umma_f8(d_tmem, da, db, idesc, (kb | k) != 0);
-            else umma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
+            const uint64_t db = umma_desc_sw128(b_addr + k * 32);
+#pragma unroll
+            for (int mt = 0; mt < kMT; ++mt) {       // the M tiles of this CTA reuse the same B stage
+              const uint64_t da = umma_desc_sw128(a_addr + mt * (kBlockM * 128) + k * 32);
+              if (kKind == kKindFP8) umma_f8(d_tmem + mt * kBlockN, da, db, idesc, (kb | k) != 0);
+              else umma_f16(d_tmem + mt * kBlockN, da, db, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(empty_bar + s);                 // smem slot is free once these MMAs have read it
           if (kKind == kKindW4) umma_commit(bempty_bar + bs);
@@ -262,14 +269,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int m_blk = tile % m_blocks, n_blk = tile / m_blocks;
       mbar_wait(tmem_full + as, aph);
       tc_fence_after_sync();
-      const int row0 = m_blk * kBlockM + q * 32;
+#pragma unroll 1
+      for (int mt = 0; mt < kMT; ++mt) {
+      const int row0 = m_blk * Cfg::kCtaM + mt * kBlockM + q * 32;
       const int row = row0 + lane;
       float a_s = 1.f;
       if (kKind == kKindFP8) a_s = p.a_scale[p.a_scale_per_row ? min(row, p.M - 1) : 0];
 #pragma unroll 1
       for (int c = 0; c < kBlockN / 32; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * kBlockN + c * 32, r);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::kAccCols + mt * kBlockN + c * 32, r);
         tmem_ld_wait();
         const int col0 = n_blk * kBlockN + c * 32;
         uint32_t o[16];
@@ -316,6 +325,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(o);
           for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = ob[j];
         }
+      }
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -391,11 +401,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-template <int kKind, int kBlockN>
+template <int kKind, int kBlockN, int kMT = 1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream,
                        const CUtensorMap* tm = nullptr) {
-  using Cfg = GemmCfg<kKind, kBlockN>;
-  auto kern = gemm_tcgen05_kernel<kKind, kBlockN>;
+  using Cfg = GemmCfg<kKind, kBlockN, kMT>;
+  auto kern = gemm_tcgen05_kernel<kKind, kBlockN, kMT>;
   static bool attr_done = false;
   if (!attr_done) {
     XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -407,7 +417,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
   }();
-  const int tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + kBlockN - 1) / kBlockN);
+  const int tiles = ((p.M + Cfg::kCtaM - 1) / Cfg::kCtaM) * ((p.N + kBlockN - 1) / kBlockN);
   dim3 grid(tiles < num_sms ? tiles : num_sms), block(Cfg::kThreads);
   CUtensorMap tc = ta;   // placeholder when the direct-store epilogue is used
   p.use_tma_store = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
@@ -498,8 +508,13 @@ extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   int bn = pick_block_n(M, N);
   if (bn == 256 && N % 256 != 0) bn = 128;
   if (bn == 128 && N % 128 != 0) bn = 64;
+  // M >= 256: two 128-row M tiles per CTA share every dequantised B stage (BLOCK_N 128), which halves the converter
+  // work per MMA flop - the converters' bf16x2 SUB/MUL rate, not the tensor pipe, bounds the single-tile kernel
+  static const int force_mt = [] { const char* e = getenv("XB_GEMM_W4_MT"); return e ? atoi(e) : 0; }();
+  const bool two_m = force_mt ? force_mt == 2 : (M >= 256 && N % 128 == 0 && (int64_t)((M + 255) / 256) * (N / 128) >= 100);
+  if (two_m) bn = 128;
   CUtensorMap ta, tb, tm;
-  if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, kBlockM, 64, 2)) return 1;
+  if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, two_m ? 256 : kBlockM, 64, 2)) return 1;
   const uint64_t ktiles = K / 64;
   if (make_tmap_2d_raw(&tb, qweight, CU_TENSOR_MAP_DATA_TYPE_UINT32, N / 16, ktiles * 128, ktiles * 512, bn / 16, 128,
                        CU_TENSOR_MAP_SWIZZLE_NONE))
@@ -507,6 +522,7 @@ extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   if (make_tmap_2d_raw(&tm, meta, CU_TENSOR_MAP_DATA_TYPE_UINT32, K / group_size, N, (uint64_t)N * 4, 1, bn,
                        CU_TENSOR_MAP_SWIZZLE_NONE))
     return 1;
+  if (two_m) return launch_gemm<kKindW4, 128, 2>(ta, tb, p, (cudaStream_t)stream, &tm);
   if (bn == 256) return launch_gemm<kKindW4, 256>(ta, tb, p, (cudaStream_t)stream, &tm);
   return bn == 128 ? launch_gemm<kKindW4, 128>(ta, tb, p, (cudaStream_t)stream, &tm)
                    : launch_gemm<kKindW4, 64>(ta, tb, p, (cudaStream_t)stream, &tm);
