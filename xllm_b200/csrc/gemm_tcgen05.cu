@@ -508,10 +508,12 @@ extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   int bn = pick_block_n(M, N);
   if (bn == 256 && N % 256 != 0) bn = 128;
   if (bn == 128 && N % 128 != 0) bn = 64;
-  // M >= 256: two 128-row M tiles per CTA share every dequantised B stage (BLOCK_N 128), which halves the converter
-  // work per MMA flop - the converters' bf16x2 SUB/MUL rate, not the tensor pipe, bounds the single-tile kernel
+  // XB_GEMM_W4_MT=2: two 128-row M tiles per CTA share every dequantised B stage (BLOCK_N 128), halving the converter
+  // work per MMA flop.  Measured on B200 it is ~5 % SLOWER than the single-tile BLOCK_N 256 kernel (1.05 vs 1.10 PF/s):
+  // both move ~115-120 KB of shared memory per 512 MMA cycles, i.e. the kernel is shared-memory-bandwidth bound, not
+  // converter bound; the fix is cta_group::2 (each CTA converts and holds half of B).  Kept as an experiment switch.
   static const int force_mt = [] { const char* e = getenv("XB_GEMM_W4_MT"); return e ? atoi(e) : 0; }();
-  const bool two_m = force_mt ? force_mt == 2 : (M >= 256 && N % 128 == 0 && (int64_t)((M + 255) / 256) * (N / 128) >= 100);
+  const bool two_m = force_mt == 2 && M >= 256 && N % 128 == 0;
   if (two_m) bn = 128;
   CUtensorMap ta, tb, tm;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, two_m ? 256 : kBlockM, 64, 2)) return 1;
