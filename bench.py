@@ -319,6 +319,55 @@ def main():
     at_us_avg = sum(a.elapsed_time(b) * 1e3 for a, b in at_events) / len(at_events)
     at_bytes = 2 * ctx * runner.nkv * cfg.head_dim * 2 + 2 * runner.nh * cfg.head_dim * 2 + 4 * npg
 
+    # ---- prefill half of the metric (BASELINE.json: "... + prefill TFLOPS"): one decoder layer of the chunked-prefill
+    # shape of configs[2] (4 prompts x 2048 tokens per chunk): the four W4A16 tcgen05 GEMMs + causal prefill attention ----
+    prefill = None
+    if rank == 0 and tp == 1:
+        try:
+            Mp, Sp = 8192, 2048
+            xin = torch.randn(Mp, cfg.hidden_size, device=dev, dtype=torch.bfloat16)
+            l0 = L[0]
+            bufs = {k: torch.empty(Mp, l0[k].N, device=dev, dtype=torch.bfloat16) for k in ("qkv", "o", "gate_up", "down")}
+            xi = {"qkv": xin, "o": torch.randn(Mp, l0["o"].K, device=dev, dtype=torch.bfloat16), "gate_up": xin,
+                  "down": torch.randn(Mp, l0["down"].K, device=dev, dtype=torch.bfloat16)}
+            qkv_p = torch.randn(Mp, cfg.q_size + 2 * cfg.kv_size, device=dev, dtype=torch.bfloat16)
+            cu = torch.arange(0, Mp + 1, Sp, dtype=torch.int32, device=dev)
+            o_p = torch.empty(Mp, cfg.n_heads, cfg.head_dim, device=dev, dtype=torch.bfloat16)
+
+            def gemms():
+                for k in ("qkv", "o", "gate_up", "down"):
+                    ops.gemm_w4a16(xi[k], l0[k].qweight, l0[k].meta, cfg.group_size, None, bufs[k])
+
+            def attn():
+                ops.batch_prefill(qkv_p[:, :cfg.q_size].view(Mp, cfg.n_heads, cfg.head_dim),
+                                  qkv_p[:, cfg.q_size:cfg.q_size + cfg.kv_size].view(Mp, cfg.n_kv_heads, cfg.head_dim),
+                                  qkv_p[:, cfg.q_size + cfg.kv_size:].view(Mp, cfg.n_kv_heads, cfg.head_dim), cu, cu,
+                                  cfg.head_dim ** -0.5, o_p, None, max_qo_len=Sp)
+
+            def t(fn, it=5):
+                fn(); fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(it):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / it * 1e-3
+            tg, ta = t(gemms), t(attn)
+            gflop = 2.0 * Mp * sum(l0[k].N * l0[k].K for k in ("qkv", "o", "gate_up", "down"))
+            aflop = 4.0 * cfg.n_heads * cfg.head_dim * Sp * Sp / 2 * (Mp // Sp)
+            try:
+                tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+            except Exception:
+                tf_peak = 1400.0
+            prefill = {"workload": "one Qwen2-7B decoder layer, chunk of 4 x 2048 tokens (W4A16 linears + causal attention)",
+                       "linear_tflops": gflop / tg / 1e12, "linear_frac_of_bf16_sustained": gflop / tg / 1e12 / tf_peak,
+                       "attention_tflops_causal": aflop / ta / 1e12, "layer_tflops": (gflop + aflop) / (tg + ta) / 1e12,
+                       "prefill_tokens_per_s_extrapolated": Mp / ((tg + ta) * cfg.num_layers), "bf16_peak_tflops": tf_peak}
+        except Exception as e:      # the decode line must still be printed
+            prefill = {"error": str(e)[:200]}
+
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
     t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
@@ -356,6 +405,7 @@ def main():
                          "paged_decode": {"bytes_per_launch": at_bytes, "launch_us": at_us_avg,
                                           "achieved": at_bytes / at_us_avg / 1e3, "frac": at_bytes / at_us_avg / 1e3 / peak_gbs}},
             "cpu_baseline": cpu,
+            "prefill": prefill,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

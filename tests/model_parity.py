@@ -21,6 +21,11 @@ def build_case(cfg, B, kv_lens, seed=2026):
         b = (torch.randn(n, generator=g) * 0.05).to(BF16) if bias else None
         if cfg.quant == "bf16":
             return dict(w=w, b=b)
+        if cfg.quant == "fp8":
+            # per-tensor static W8A8 (compressed-tensors style): weight = e4m3(w / w_scale), activations e4m3(x / in_scale)
+            w_scale = (w.float().abs().max() / 448.0).reshape(1)
+            w8 = (w.float() / w_scale).clamp(-448, 448).to(torch.float8_e4m3fn)
+            return dict(w8=w8, w_scale=w_scale, in_scale=torch.tensor([0.02]), b=b)
         q, s, z = OQ.quantize(w, 4, cfg.group_size)
         return dict(q=q, s=s, z=z, b=b, w=OQ.dequantize(q, s, z, cfg.group_size))
 
@@ -30,7 +35,7 @@ def build_case(cfg, B, kv_lens, seed=2026):
     for _ in range(cfg.num_layers):
         W["layers"].append(dict(input_norm=(1 + 0.1 * torch.randn(H, generator=g)).to(BF16),
                                 post_norm=(1 + 0.1 * torch.randn(H, generator=g)).to(BF16),
-                                qkv=lin(cfg.q_size + 2 * cfg.kv_size, H, True), o=lin(H, cfg.q_size),
+                                qkv=lin(cfg.q_size + 2 * cfg.kv_size, H, cfg.qkv_bias), o=lin(H, cfg.q_size),
                                 gate_up=lin(2 * I, H), down=lin(H, I)))
     bs = cfg.block_size
     npg = [(n + bs - 1) // bs for n in kv_lens]
@@ -50,6 +55,13 @@ def build_case(cfg, B, kv_lens, seed=2026):
     return W, kcs, vcs, meta
 
 
+def _olin(d):
+    """oracle linear for one logical weight dict (bf16 / dequantised W4 / fp8 W8A8 static)."""
+    if "w8" in d:
+        return lambda x, _w=None, b=None: O.fp8_linear(x, d["w8"], d["w_scale"], d["in_scale"], d["b"])
+    return lambda x, _w=None, b=None: O.linear(x, d["w"], d["b"])
+
+
 def oracle_step(cfg, W, kcs, vcs, meta):
     """reference composition on CPU: returns (logits bf16 [B, vocab], next tokens)."""
     B = len(meta["tokens"])
@@ -61,11 +73,10 @@ def oracle_step(cfg, W, kcs, vcs, meta):
     x = W["embed"][torch.tensor(meta["tokens"])]
     residual = None
     for li, L in enumerate(W["layers"]):
-        attn = OL.Qwen2AttentionOracle(L["qkv"]["w"], L["qkv"]["b"], L["o"]["w"], cfg.n_heads, cfg.n_kv_heads,
-                                       cfg.head_dim, cs)
+        attn = OL.Qwen2AttentionOracle(None, None, None, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cs,
+                                       linear=_olin(L["qkv"]), o_linear=_olin(L["o"]))
         dl = OL.Qwen2DecoderLayerOracle(attn, L["input_norm"], L["post_norm"], cfg.rms_norm_eps,
-                                        lambda h, L=L: O.linear(h, L["gate_up"]["w"]),
-                                        lambda h, L=L: O.linear(h, L["down"]["w"]))
+                                        _olin(L["gate_up"]), _olin(L["down"]))
         x, residual = dl.forward(x, residual, positions, am, kcs[li], vcs[li])
     x, _ = O.fused_add_rms_norm(x, residual, W["final_norm"], cfg.rms_norm_eps)
     logits = O.linear(x, W["lm_head"])
@@ -85,6 +96,10 @@ def upload(cfg, W, device="cuda"):
         l = Linear(n, k, cfg.quant, cfg.group_size)
         if cfg.quant == "bf16":
             l.weight = d["w"].to(device)
+        elif cfg.quant == "fp8":
+            l.weight = d["w8"].to(device)
+            l.weight_scale = d["w_scale"].float().to(device)
+            l.input_scale = d["in_scale"].float().to(device)
         else:
             qw, meta = quant.pack_w4(d["q"], d["s"], d["z"], cfg.group_size)
             l.qweight, l.meta = qw.to(device), meta.to(device)
@@ -132,10 +147,11 @@ def oracle_layer_state(cfg, W, li, h, residual, kcs, vcs, meta):
                      torch.tensor(meta["indptr"], dtype=torch.int32), torch.tensor(meta["indices"], dtype=torch.int32),
                      torch.tensor(meta["last"], dtype=torch.int32))
     L = W["layers"][li]
-    attn = OL.Qwen2AttentionOracle(L["qkv"]["w"], L["qkv"]["b"], L["o"]["w"], cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cs)
+    attn = OL.Qwen2AttentionOracle(None, None, None, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cs,
+                                   linear=_olin(L["qkv"]), o_linear=_olin(L["o"]))
     a = attn.forward(torch.tensor(meta["positions"]), h, am, kcs[li].clone(), vcs[li].clone())
     h_mid, res_mid = O.fused_add_rms_norm(a, residual, L["post_norm"], cfg.rms_norm_eps)
-    down = O.linear(O.act_and_mul(O.linear(h_mid, L["gate_up"]["w"]), "silu"), L["down"]["w"])
+    down = _olin(L["down"])(O.act_and_mul(_olin(L["gate_up"])(h_mid), "silu"))
     next_w = W["layers"][li + 1]["input_norm"] if li + 1 < cfg.num_layers else W["final_norm"]
     return O.fused_add_rms_norm(down, res_mid, next_w, cfg.rms_norm_eps)
 

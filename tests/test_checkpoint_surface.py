@@ -1,0 +1,75 @@
+"""CPU tests of the checkpoint surface: AutoAWQ / AutoGPTQ tensor conventions -> logical form ->
+kernel layout.  The packers below restate the two libraries' published packing independently of the converters."""
+import pytest
+import torch
+
+from oracle import quant as OQ
+from xllm_b200 import quant
+
+AWQ_ORDER = [0, 2, 4, 6, 1, 3, 5, 7]
+
+
+def _logical(N=64, K=256, gs=128, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randint(0, 16, (N, K), dtype=torch.uint8, generator=g)
+    z = torch.randint(1, 16, (N, K // gs), dtype=torch.uint8, generator=g)
+    s = (torch.rand(N, K // gs, generator=g) * 0.02 + 0.001).to(torch.float16)
+    return q, z, s
+
+
+def _pack_awq(vals_kn):                     # [K, N] -> int32 [K, N/8], AutoAWQ order_map
+    K, N = vals_kn.shape
+    v = vals_kn.to(torch.int64).view(K, N // 8, 8)
+    word = torch.zeros(K, N // 8, dtype=torch.int64)
+    for i, col in enumerate(AWQ_ORDER):
+        word |= v[:, :, col] << (4 * i)
+    return word.to(torch.int32)             # wraps bit 31 into the sign like the real checkpoints
+
+
+def _pack_seq_lastdim(vals):                # [..., 8C] -> int32 [..., C], low nibble first
+    v = vals.to(torch.int64).view(*vals.shape[:-1], vals.shape[-1] // 8, 8)
+    word = torch.zeros(v.shape[:-1], dtype=torch.int64)
+    for i in range(8):
+        word |= v[..., i] << (4 * i)
+    return word.to(torch.int32)
+
+
+def test_from_awq_roundtrip():
+    q, z, s = _logical()
+    qw = _pack_awq(q.t().contiguous())
+    qz = _pack_awq(z.t().contiguous())
+    q2, s2, z2 = quant.from_awq(qw, qz, s.t().contiguous(), 128)
+    assert torch.equal(q2, q) and torch.equal(z2, z) and torch.equal(s2, s.to(torch.bfloat16))
+
+
+def test_from_gptq_roundtrip_and_desc_act_rejected():
+    q, z, s = _logical(seed=1)
+    N, K = q.shape
+    qw = _pack_seq_lastdim(q).t().contiguous()                  # [K/8, N]
+    qz = _pack_seq_lastdim((z.t().to(torch.int16) - 1).contiguous())   # stores z - 1, packed along N
+    g_idx = torch.arange(K, dtype=torch.int32) // 128
+    q2, s2, z2 = quant.from_gptq(qw, qz, s.t().contiguous(), g_idx, 128)
+    assert torch.equal(q2, q) and torch.equal(z2, z) and torch.equal(s2, s.to(torch.bfloat16))
+    with pytest.raises(ValueError):
+        quant.from_gptq(qw, qz, s.t().contiguous(), g_idx.flip(0), 128)
+
+
+def test_checkpoint_to_kernel_layout_matches_spec():
+    """AWQ tensors -> logical -> kernel layout; the packed words decode (by the documented nibble positions) back to the
+    oracle's dequantised weight."""
+    q, z, s = _logical(N=32, K=128, seed=2)
+    q2, s2, z2 = quant.from_awq(_pack_awq(q.t().contiguous()), _pack_awq(z.t().contiguous()), s.t().contiguous(), 128)
+    qw, meta = quant.pack_w4(q2, s2, z2, 128)
+    wd = OQ.dequantize(q2, s2, z2, 128).float()
+    # decode tile (nt=1, kt=1), lane (g=3, t=2), word j=1: rows 16+3 / 16+11, k = 64 + 32 + 4 + {0..3}
+    w = int(qw[1, 1, 3 * 4 + 2, 1]) & 0xFFFFFFFF
+    nib = [(w >> (4 * i)) & 15 for i in range(8)]
+    k0 = 64 + 16 * 2 + 4
+    assert [nib[0], nib[4], nib[2], nib[6]] == q2[19, k0:k0 + 4].tolist()
+    assert [nib[1], nib[5], nib[3], nib[7]] == q2[27, k0:k0 + 4].tolist()
+    m = int(meta[0, 19]) & 0xFFFFFFFF
+    sc = torch.tensor([m & 0xFFFF], dtype=torch.int32).to(torch.int16).view(torch.bfloat16).float().item()
+    zb = torch.tensor([m >> 16], dtype=torch.int32).to(torch.int16).view(torch.bfloat16).float().item()
+    assert zb == 128 + int(z2[19, 0])
+    ref = torch.tensor((nib[0] - int(z2[19, 0])) * sc).to(torch.bfloat16).float().item()
+    assert ref == wd[19, k0].item()

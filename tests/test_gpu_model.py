@@ -61,3 +61,17 @@ def test_layerwise_teacher_forced(quant, built_lib):
     for li, (gx, rx, gres, rres) in enumerate(run_layerwise_parity(cfg, [37, 300, 1])):
         assert_close_bf16(gres, rres, ulps=2, rel_l2=3e-3, what=f"layer {li} residual stream", atol=2.0 ** -6)
         assert_close_bf16(gx, rx, ulps=1e9, rel_l2=1e-2, what=f"layer {li} normalised output")
+
+
+def test_decode_step_llama_fp8_shape(built_lib):
+    """BASELINE configs[3] flavour at toy size: Llama-style layer (no qkv bias, GQA 8) with FP8 W8A8 per-tensor static
+    linears (fp8_linear_forward, linear.cpp:137-182 -> cutlass_scaled_mm), decode batch of 3."""
+    from xllm_b200.qwen2 import Qwen2Config
+    cfg = Qwen2Config(hidden_size=512, num_layers=2, n_heads=16, n_kv_heads=2, head_dim=64, intermediate_size=1024,
+                      vocab_size=2048, block_size=16, quant="fp8", qkv_bias=False, rope_theta=500000.0, rms_norm_eps=1e-5,
+                      max_position_embeddings=2048, name="tiny-llama-fp8")
+    logits, ref_logits, nxt, ref_next, _, _ = run_decode_parity(cfg, [200, 33, 5], True, True)
+    # e4m3 activations: a 1-ulp bf16 flip upstream can move an activation across an fp8 rounding boundary (2^-4
+    # relative), so the logits bar is looser than for bf16 pipelines
+    assert_close_bf16(logits, ref_logits, ulps=1e9, rel_l2=5e-2, what="llama-fp8 logits")
+    assert torch.equal(nxt.long().cpu()[:3], ref_next)

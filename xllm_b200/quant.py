@@ -36,3 +36,56 @@ def pack_w4_c(q: torch.Tensor) -> torch.Tensor:
     check(lib().xb_w4_pack_rows(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(qc.data_ptr()), ctypes.c_int(N),
                                 ctypes.c_int(K)), "w4_pack_rows")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# checkpoint surface: AutoAWQ / AutoGPTQ tensors -> the logical (q, scales, zeros) form above.
+# The reference parses `bits / group_size / sym / desc_act` into QuantArgs (framework/quant_args.h:36-60,
+# hf_model_loader.cpp:384-440) but loads no qweight/qzeros/scales; these converters are what its loader would call.
+# Formats (published conventions of the two libraries):
+#   AWQ  (GEMM):  qweight int32 [K, N/8], qzeros int32 [K/g, N/8], scales fp16 [K/g, N]; the 8 nibbles of a word hold
+#                 columns 8j + [0, 2, 4, 6, 1, 3, 5, 7] from the low nibble up ("order_map"); w = (q - z) * s.
+#   GPTQ (v1):    qweight int32 [K/8, N] (8 consecutive k per word, low nibble first), qzeros int32 [K/g, N/8]
+#                 (8 consecutive n per word) storing z - 1, scales fp16 [K/g, N], g_idx int32 [K]; w = (q - (qz + 1)) * s.
+# ---------------------------------------------------------------------------------------------------------------
+_AWQ_ORDER = [0, 2, 4, 6, 1, 3, 5, 7]
+
+
+def _unpack_nibbles_lastdim(t: torch.Tensor, order=None) -> torch.Tensor:
+    """int32 [..., C] -> uint8 [..., 8C]: nibble i of a word goes to position order[i] within its group of 8."""
+    shifts = torch.arange(0, 32, 4, dtype=torch.int32, device=t.device)
+    nib = ((t.unsqueeze(-1) >> shifts) & 0xF).to(torch.uint8)            # [..., C, 8] nibble-position order
+    if order is not None:
+        out = torch.empty_like(nib)
+        out[..., torch.tensor(order, device=t.device)] = nib              # position i -> column order[i]
+        nib = out
+    return nib.reshape(*t.shape[:-1], t.shape[-1] * 8)
+
+
+def from_awq(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, group_size: int = 128):
+    """AutoAWQ GEMM tensors -> (q uint8 [N,K], scales bf16 [N,K/g], zeros uint8 [N,K/g])."""
+    K = qweight.shape[0]
+    q = _unpack_nibbles_lastdim(qweight, _AWQ_ORDER)                       # [K, N]
+    z = _unpack_nibbles_lastdim(qzeros, _AWQ_ORDER)                        # [K/g, N]
+    if K % group_size != 0 or z.shape[0] != K // group_size:
+        raise ValueError("AWQ tensors do not match group_size")
+    return q.t().contiguous(), scales.to(torch.bfloat16).t().contiguous(), z.t().contiguous()
+
+
+def from_gptq(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, g_idx=None, group_size: int = 128,
+              zeros_plus_one: bool = True):
+    """AutoGPTQ 4-bit tensors -> (q uint8 [N,K], scales bf16 [N,K/g], zeros uint8 [N,K/g]).
+    desc_act (a g_idx that is not k // group_size) permutes K and is not supported by the kernels."""
+    K8, N = qweight.shape
+    K = K8 * 8
+    q = _unpack_nibbles_lastdim(qweight.t().contiguous()).reshape(N, K)    # words along K: [N, K/8] -> [N, K]
+    z = _unpack_nibbles_lastdim(qzeros).to(torch.int16)                    # [K/g, N]
+    if zeros_plus_one:
+        z = z + 1
+    if g_idx is not None:
+        expect = torch.arange(K, device=g_idx.device, dtype=g_idx.dtype) // group_size
+        if not torch.equal(g_idx, expect):
+            raise ValueError("desc_act / act-order checkpoints (non-monotonic g_idx) are not supported")
+    if (z < 0).any() or (z > 15).any():
+        raise ValueError("zero points out of the 4-bit range after the +1 correction")
+    return q.contiguous(), scales.to(torch.bfloat16).t().contiguous(), z.to(torch.uint8).t().contiguous()

@@ -34,9 +34,10 @@ class Qwen2Config:
     rms_norm_eps: float = 1e-6
     max_position_embeddings: int = 32768
     block_size: int = 128                 # kv_cache_config.cpp:21
-    quant: str = "w4a16"                  # "w4a16" | "bf16"
+    quant: str = "w4a16"                  # "w4a16" | "bf16" | "fp8" (W8A8 per-tensor static, linear.cpp:137-182)
     group_size: int = 128
     tie_word_embeddings: bool = False
+    qkv_bias: bool = True                 # qwen2_attention.cpp:52; Llama: False
     name: str = "Qwen2-7B"
 
     @staticmethod
@@ -47,6 +48,16 @@ class Qwen2Config:
     def qwen2_0_5b(**kw):
         d = dict(hidden_size=896, num_layers=24, n_heads=14, n_kv_heads=2, head_dim=64, intermediate_size=4864,
                  vocab_size=151936, quant="bf16", tie_word_embeddings=True, name="Qwen2-0.5B")
+        d.update(kw)
+        return Qwen2Config(**d)
+
+    @staticmethod
+    def llama3_70b(**kw):
+        """BASELINE configs[3] architecture (the reference registers Llama only under models/llm/npu/llama3.h; the layer
+        graph is Qwen2's without the qkv bias).  NOTE: llama3 rope scaling is not applied (plain rope_theta)."""
+        d = dict(hidden_size=8192, num_layers=80, n_heads=64, n_kv_heads=8, head_dim=128, intermediate_size=28672,
+                 vocab_size=128256, rope_theta=500000.0, rms_norm_eps=1e-5, quant="fp8", qkv_bias=False,
+                 max_position_embeddings=8192, name="Llama-3-70B")
         d.update(kw)
         return Qwen2Config(**d)
 
@@ -64,24 +75,33 @@ class Linear:
 
     def __init__(self, out_features, in_features, kind, group_size=128):
         self.N, self.K, self.kind, self.group_size = out_features, in_features, kind, group_size
-        self.weight = None      # bf16 [N,K]
+        self.weight = None      # bf16 [N,K] (or e4m3 [N,K] for kind "fp8")
         self.qweight = None     # int32 tiles
         self.meta = None        # int32 [K/g, N]
         self.bias = None
+        self.weight_scale = None   # fp8: float32 [1] per-tensor weight scale
+        self.input_scale = None    # fp8: float32 [1] static activation scale (None -> dynamic per-tensor)
+        self._x8 = None
 
     def weight_bytes(self):
         if self.kind == "bf16":
             return self.weight.numel() * 2
+        if self.kind == "fp8":
+            return self.weight.numel()
         return self.qweight.numel() * 4 + self.meta.numel() * 4
 
     def forward(self, x, out):
-        M = x.size(0)
-        if M > 64:
-            raise NotImplementedError("M > 64 routes to the tcgen05 GEMM (xllm_b200.ops.gemm_*)")
+        """M <= 16: HBM-bound streaming kernels; larger M: tcgen05 GEMMs.  fp8 follows fp8_linear_forward
+        (linear.cpp:137-182): quantise the activation (static scale if present) then the scaled matmul."""
         if self.kind == "bf16":
-            ops.matmul_small_m(x, self.weight, self.bias, out)
+            ops.matmul(x, self.weight, self.bias, out)
+        elif self.kind == "fp8":
+            if self._x8 is None or self._x8.shape != x.shape:
+                self._x8 = torch.empty(x.shape, dtype=torch.float8_e4m3fn, device=x.device)
+            x8, sc = ops.fp8_scaled_quantize(x, self._x8, self.input_scale)
+            ops.fp8_scaled_matmul(x8, self.weight, sc, self.weight_scale, BF16, self.bias, out)
         else:
-            ops.w4a16_linear_small_m(x, self.qweight, self.meta, self.group_size, self.bias, out)
+            ops.w4a16_linear(x, self.qweight, self.meta, self.group_size, self.bias, out)
         return out
 
 
@@ -98,6 +118,10 @@ class Qwen2Weights:
         lin = Linear(N, K, kind, gs)
         if kind == "bf16":
             lin.weight = (torch.randn(N, K, generator=gen, device=device) * std).to(BF16)
+        elif kind == "fp8":
+            lin.weight = (torch.randn(N, K, generator=gen, device=device)).clamp(-3, 3).to(torch.float8_e4m3fn)
+            lin.weight_scale = torch.full((1,), std, dtype=torch.float32, device=device)
+            lin.input_scale = torch.full((1,), 0.05, dtype=torch.float32, device=device)
         else:
             # uniform nibbles + scales such that w ~ N(0, std^2)-like spread; generated directly in packed form
             lin.qweight = torch.randint(-2 ** 31, 2 ** 31 - 1, (N // 16, K // 64, 32, 4), generator=gen, device=device,
@@ -132,7 +156,7 @@ class Qwen2Weights:
             w.layers.append(dict(
                 input_norm=(1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16),
                 post_norm=(1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16),
-                qkv=mk(q_size + 2 * kv_size, H, True), o=mk(H, q_size),
+                qkv=mk(q_size + 2 * kv_size, H, cfg.qkv_bias), o=mk(H, q_size),
                 gate_up=mk(2 * I, H), down=mk(H, I)))
         return w
 
