@@ -74,4 +74,9 @@ def test_decode_step_llama_fp8_shape(built_lib):
     # e4m3 activations: a 1-ulp bf16 flip upstream can move an activation across an fp8 rounding boundary (2^-4
     # relative), so the logits bar is looser than for bf16 pipelines
     assert_close_bf16(logits, ref_logits, ulps=1e9, rel_l2=5e-2, what="llama-fp8 logits")
-    assert torch.equal(nxt.long().cpu()[:3], ref_next)
+    # random-init logits are nearly flat, so the argmax may flip between near-ties: the token the GPU picked must be
+    # (near-)maximal under the oracle as well
+    rl = ref_logits.float()
+    for b in range(3):
+        top = rl[b].max().item()
+        assert rl[b, int(nxt[b])].item() >= top - 0.05 * abs(top), f"request {b}: GPU token is not a near-argmax of the oracle"
