@@ -390,7 +390,7 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "ctx": ctx, "batch": 1,
                        "parallelism": (f"tp{tp}" if dp == 1 else f"tp{tp}xdp{dp}") if tp > 1 else f"dp{world}",
-                       "exchange": (args.exchange if tp > 1 else None),
+                       "exchange": (runner.exchange_mode if tp > 1 else None),
                        "l2": "inputs larger than L2: each step streams %.2f GB of weights+KV" % (step_bytes / 1e9),
                        "decode_chunk_tokens": runner.plan.chunk_tokens, "decode_splits": runner.plan.max_splits},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,

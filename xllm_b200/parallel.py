@@ -159,6 +159,10 @@ class PeerExchange:
         self.pg, self.hidden, self.max_tokens = pg, hidden, max_tokens
         self.lib = lib()
         n = max_tokens * hidden
+        try:                                   # older torch needs the group enabled explicitly; newer ones do it lazily
+            symm_mem.enable_symm_mem_for_group(pg.group.group_name)
+        except Exception:
+            pass
         self.bufs, self.handles = [], []
         for _ in range(2):
             t = symm_mem.empty(n, dtype=BF16, device=device)

@@ -238,7 +238,12 @@ class Qwen2DecodeRunner:
         self.logits_local = torch.empty(B, cfg.vocab_size // self.tp, dtype=BF16, device=dev) if self.pg else self.logits
         if self.pg and exchange == "peer":
             from .parallel import PeerExchange
-            self.exchange = PeerExchange(self.pg, B, H, dev)
+            try:
+                self.exchange = PeerExchange(self.pg, B, H, dev)
+            except Exception as e:          # no P2P mapping available: the NCCL exchange is the baseline path
+                import warnings
+                warnings.warn(f"NVLink peer exchange unavailable ({e}); falling back to NCCL all-reduce")
+                self.exchange, self.exchange_mode = None, "nccl (peer exchange unavailable)"
         self.next_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
         self.plan = ops.DecodePlan(B, self.nh, self.nkv, cfg.head_dim, bs, self.max_pages, dev, early_prefetch=True)
         self.graph = None
