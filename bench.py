@@ -205,7 +205,9 @@ def main():
     dev = f"cuda:{local_rank}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        import datetime
+        # a short timeout turns a rendezvous problem into an error (and the NCCL fallback below) instead of a hang
+        dist.init_process_group("nccl", device_id=torch.device(dev), timeout=datetime.timedelta(seconds=240))
     _lib.lib()                      # fail loudly if the CUDA library is missing: no fallback
     peak_gbs, peak_src = load_peaks()
 
@@ -216,18 +218,23 @@ def main():
         tp = 4 if world % 4 == 0 else (2 if world % 2 == 0 else 1)
     dp = world // tp
     pg = None
+    exchange = args.exchange
     if tp > 1:
         from xllm_b200.parallel import ProcessGroup
-        my_group = None
-        for gidx in range(dp):
-            ranks = list(range(gidx * tp, (gidx + 1) * tp))
-            grp = dist.new_group(ranks)
-            if rank in ranks:
-                my_group = grp
-        pg = ProcessGroup(my_group)
+        if dp == 1:
+            pg = ProcessGroup()                       # the default group: the configuration tests/test_gpu_tp.py covers
+        else:
+            my_group = None
+            for gidx in range(dp):
+                ranks = list(range(gidx * tp, (gidx + 1) * tp))
+                grp = dist.new_group(ranks)
+                if rank in ranks:
+                    my_group = grp
+            pg = ProcessGroup(my_group)
+            exchange = "nccl"                         # symmetric-memory rendezvous on sub-groups is not validated yet
     tp_rank = rank % tp
     weights = Qwen2Weights.synthetic(cfg, dev, seed=2026 + rank, tp_rank=tp_rank, tp=tp)
-    runner = Qwen2DecodeRunner(cfg, weights, max_batch=1, max_ctx=ctx, device=dev, pg=pg, exchange=args.exchange)
+    runner = Qwen2DecodeRunner(cfg, weights, max_batch=1, max_ctx=ctx, device=dev, pg=pg, exchange=exchange)
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     for li in range(cfg.num_layers):
         runner.k_caches[li].normal_(generator=g)
