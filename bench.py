@@ -196,9 +196,18 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import faulthandler
     import torch
     import torch.distributed as dist
     from xllm_b200 import _lib
+    wd = int(os.environ.get("XB_BENCH_WATCHDOG", "0"))
+    if wd > 0:                      # dump every thread's stack and exit if the run has not finished after `wd` seconds
+        faulthandler.dump_traceback_later(wd, exit=True)
+
+    def log(msg):
+        if os.environ.get("XB_BENCH_VERBOSE"):
+            sys.stderr.write(f"[bench rank {rank}] {msg}\n")
+            sys.stderr.flush()
     from xllm_b200.qwen2 import Qwen2Config, Qwen2DecodeRunner, Qwen2Weights
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
     torch.cuda.set_device(local_rank)
@@ -208,6 +217,7 @@ def main():
         import datetime
         # a short timeout turns a rendezvous problem into an error (and the NCCL fallback below) instead of a hang
         dist.init_process_group("nccl", device_id=torch.device(dev), timeout=datetime.timedelta(seconds=240))
+    log("process group ready")
     _lib.lib()                      # fail loudly if the CUDA library is missing: no fallback
     peak_gbs, peak_src = load_peaks()
 
@@ -246,8 +256,11 @@ def main():
     slot = pages[pos // bs] * bs + pos % bs
     tok = 1234
     runner.set_inputs_host([tok], [pos], [slot], [0, npg], pages, [(ctx - 1) % bs + 1])
+    log("runner built")
     runner.step()                   # eager pass (module load, attribute setup)
+    log("eager step done")
     runner.capture()
+    log("graph captured")
     launches_per_step = None
 
     def barrier():
@@ -270,6 +283,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    log(f"timed region done: {ms:.1f} ms")
     clocks = sampler.stop()
     graph_launches = 0
     # a graph replay does not pass through the library's launch counter: count the kernels in one step eagerly
@@ -288,6 +302,7 @@ def main():
         runner.h_token_ids[0] = int(out[0]) % cfg.vocab_size
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    log("e2e region done")
 
     # ---- dominant kernel: W4A16 gate_up GEMV, CUDA events around each launch -----------------------------------
     gu_events = []
