@@ -431,7 +431,13 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # destroy_process_group() blocks here (captured NCCL / symmetric-memory graphs still hold communicator
+        # references); every rank is done and rank 0 has printed, so leave without the collective teardown
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
 
 
 if __name__ == "__main__":
