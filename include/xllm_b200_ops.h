@@ -195,6 +195,18 @@ int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
                             int64_t x_stride, const uint32_t* qweight,
                             const uint32_t* meta, const void* bias, int M, int N,
                             int K, int group_size, xb_stream_t stream);
+/* gate_up_proj with SiLU*mul (or GELU*mul) fused into the epilogue (DenseMLPImpl::forward, dense_mlp.cpp:97-118 =
+ * gate_up linear + act_and_mul): qweight / meta / bias rows in the interleaved order of
+ * xllm_b200.quant.interleave_gate_up (per 16-row tile 8 gate rows then the matching 8 up rows); y [M, N/2]; M <= 16.
+ * Same rounding ladder as the two separate ops (both linear outputs -> bf16, bf16(act(gate)) * up -> bf16). */
+int xb_linear_w4a16_gate_up_act_small_m(void* y, int64_t y_stride, const void* x, int64_t x_stride,
+                                        const uint32_t* qweight, const uint32_t* meta,
+                                        const void* bias, int M, int N, int K, int group_size,
+                                        int act_mode, xb_stream_t stream);
+/* act_and_mul over that interleaved column layout (prefill path sharing the same packed weight):
+ * out[t, 8j+i] = act(x[t, 16j+i]) * x[t, 16j+8+i]. */
+int xb_act_and_mul_interleaved8_bf16(void* out, const void* input, int d, int num_tokens,
+                                     int act_mode, xb_stream_t stream);
 /* host-side packer (plain C, no CUDA): q[N,K] uint8 (0..15) -> qweight tiles. */
 int xb_w4_pack_rows(uint32_t* qweight_out, const uint8_t* q, int N, int K);
 

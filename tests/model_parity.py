@@ -92,8 +92,13 @@ def upload(cfg, W, device="cuda"):
     w.lm_head = Linear(cfg.vocab_size, cfg.hidden_size, "bf16")
     w.lm_head.weight = w.embed if cfg.tie_word_embeddings else W["lm_head"].to(device)
 
-    def mk(d, n, k):
+    def mk(d, n, k, gate_up=False):
         l = Linear(n, k, cfg.quant, cfg.group_size)
+        if gate_up and cfg.quant == "w4a16":
+            qw, meta, b = quant.pack_w4_gate_up(d["q"], d["s"], d["z"], cfg.group_size, d["b"])
+            l.qweight, l.meta, l.bias = qw.to(device), meta.to(device), (b.to(device) if b is not None else None)
+            l.gate_up_interleaved = True
+            return l
         if cfg.quant == "bf16":
             l.weight = d["w"].to(device)
         elif cfg.quant == "fp8":
@@ -109,7 +114,7 @@ def upload(cfg, W, device="cuda"):
     for L in W["layers"]:
         w.layers.append(dict(input_norm=L["input_norm"].to(device), post_norm=L["post_norm"].to(device),
                              qkv=mk(L["qkv"], cfg.q_size + 2 * cfg.kv_size, H), o=mk(L["o"], H, cfg.q_size),
-                             gate_up=mk(L["gate_up"], 2 * I, H), down=mk(L["down"], H, I)))
+                             gate_up=mk(L["gate_up"], 2 * I, H, gate_up=True), down=mk(L["down"], H, I)))
     return w
 
 

@@ -102,3 +102,32 @@ def test_linear_linearity_full_size(built_lib):
     y12 = ops.w4a16_linear_small_m(x1, qw, meta, gs).float() + ops.w4a16_linear_small_m(x2, qw, meta, gs).float()
     rel = ((y - y12).norm() / y.norm()).item()
     assert rel < 4e-3, f"linearity violated: {rel:.3e}"   # two extra bf16 output roundings
+
+
+@pytest.mark.parametrize("M", [1, 7, 8, 16, 40])
+@pytest.mark.parametrize("I,K,bias", [(18944, 3584, False), (512, 256, True), (4864, 896, False)])
+def test_w4a16_gate_up_act_fused(M, I, K, bias, built_lib):
+    """gate_up linear + SiLU*mul in one kernel (interleaved gate/up packing) == act_and_mul(linear(x)) of the oracle."""
+    from xllm_b200 import ops, quant
+    if M > 8 and I * K > 5e7:
+        pytest.skip("full size covered at M<=8")
+    gs = 128 if K % 128 == 0 else 64
+    g = torch.Generator().manual_seed(2026)
+    w = (torch.randn(2 * I, K, generator=g) * 0.05).to(BF16)
+    q, s, z = Q.quantize(w, 4, gs)
+    b = (torch.randn(2 * I, generator=g) * 0.1).to(BF16) if bias else None
+    x = torch.randn(M, K, generator=g).to(BF16)
+    ref = O.act_and_mul(Q.linear_wna16(x, q, s, z, gs, b), "silu")
+    qw, meta, bi = quant.pack_w4_gate_up(q, s, z, gs, b)
+    y = ops.w4a16_gate_up_act(x.to(DEV), qw.to(DEV), meta.to(DEV), gs, "silu", bi.to(DEV) if bi is not None else None)
+    # act(gate)*up of two 1-ulp-accurate linears: a flip in either input moves the product by up to ~2 ulps
+    assert_close_bf16(y, ref, ulps=3, rel_l2=2e-3, what=f"gate_up_act M={M} I={I}", atol=1e-4)
+    frac = (y.cpu() != ref).float().mean().item()
+    assert frac < 0.05, f"{frac:.3f} of elements differ"
+
+
+def test_interleave_index_is_a_permutation():
+    from xllm_b200 import quant
+    idx = quant.interleave_gate_up_index(64)
+    assert sorted(idx.tolist()) == list(range(128))
+    assert idx[:16].tolist() == list(range(8)) + list(range(64, 72))

@@ -534,6 +534,30 @@ act_and_mul_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restr
   pdl_launch_dependents();
 }
 
+// act_and_mul over the INTERLEAVED gate/up layout the fused decode GEMV uses (per 16 columns: 8 gate then 8 up), so the
+// prefill GEMM can share the same packed gate_up weight: out[t, 8j + i] = act(x[t, 16j + i]) * x[t, 16j + 8 + i].
+template <int kAct>
+__global__ void __launch_bounds__(256)
+act_and_mul_interleaved8_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ in, int d /* out cols */) {
+  const int64_t tok = blockIdx.y;
+  const uint4* x = reinterpret_cast<const uint4*>(in + tok * 2 * (int64_t)d);
+  uint4* o = reinterpret_cast<uint4*>(out + tok * (int64_t)d);
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d / 8; j += gridDim.x * blockDim.x) {
+    const uint4 a = x[2 * j], b = x[2 * j + 1];
+    const uint32_t* ap = &a.x;
+    const uint32_t* bp = &b.x;
+    uint4 r;
+    uint32_t* rp = &r.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      rp[i] = pack_bf16x2(round_bf16(act_fn<kAct>(bf16lo(ap[i]))) * bf16lo(bp[i]),
+                          round_bf16(act_fn<kAct>(bf16hi(ap[i]))) * bf16hi(bp[i]));
+    o[j] = r;
+  }
+}
+
 }  // namespace xb
 
 // ===========================================================================
@@ -705,5 +729,22 @@ extern "C" int xb_act_and_mul_bf16(void* out, const void* input, int d, int num_
   if (act_mode == 0) XB_CUDA_OK(launch(act_and_mul_kernel<0>, grid, block, 0, s, true, o, in, d, vec));
   else if (act_mode == 1) XB_CUDA_OK(launch(act_and_mul_kernel<1>, grid, block, 0, s, true, o, in, d, vec));
   else XB_CUDA_OK(launch(act_and_mul_kernel<2>, grid, block, 0, s, true, o, in, d, vec));
+  return 0;
+}
+
+extern "C" int xb_act_and_mul_interleaved8_bf16(void* out, const void* input, int d, int num_tokens, int act_mode,
+                                                xb_stream_t stream) {
+  if (num_tokens == 0) return 0;
+  XB_CHECK(act_mode >= 0 && act_mode <= 2, "act_and_mul_interleaved8: unsupported act mode %d", act_mode);
+  XB_CHECK(d % 8 == 0 && aligned16(input) && aligned16(out), "act_and_mul_interleaved8: d %% 8 and 16-byte alignment required");
+  int bx = (d / 8 + 255) / 256;
+  if (num_tokens >= 512) bx = 1;
+  dim3 grid(bx, num_tokens), block(256);
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  auto* in = reinterpret_cast<const __nv_bfloat16*>(input);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (act_mode == 0) XB_CUDA_OK(launch(act_and_mul_interleaved8_kernel<0>, grid, block, 0, s, true, o, in, d));
+  else if (act_mode == 1) XB_CUDA_OK(launch(act_and_mul_interleaved8_kernel<1>, grid, block, 0, s, true, o, in, d));
+  else XB_CUDA_OK(launch(act_and_mul_interleaved8_kernel<2>, grid, block, 0, s, true, o, in, d));
   return 0;
 }

@@ -79,11 +79,13 @@ struct XRing {
 
 template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth,
           int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */, int kOcc = 2 /* CTAs per SM */,
-          int kAccSets = 0 /* 0: default for kMT */, bool kFmaShift = false /* right shifts as IMAD.HI (fma pipe) */>
+          int kAccSets = 0 /* 0: default for kMT */, bool kFmaShift = false /* right shifts as IMAD.HI (fma pipe) */,
+          bool kGateUp = false /* rows are interleaved [8 gate | 8 up] per 16-row tile: epilogue = act(gate) * up */>
 __global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : kOcc)
 linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
                             int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
-                            const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int gshift /* log2(tiles per group) */) {
+                            const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int gshift /* log2(tiles per group) */,
+                            int act_mode) {
   constexpr int kTilesPerCta = kWarps / kSplit;
   __shared__ float red[kSplit > 1 ? kWarps : 1][kMT][16 * 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -223,19 +225,43 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     }
 
   // c0:(row g, tok 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
+  // kGateUp: row g of the tile is gate row 8*ntile+g and row g+8 the matching up row, so SiLU*mul (activation.cu:45-130:
+  // both linear outputs rounded to bf16, bf16(act(gate)) * up rounded again) is applied right here and only
+  // N/2 values per token are written - the separate act_and_mul launch and its 3*N bytes of traffic disappear.
+  auto gate_up = [&](float gate, float up) -> __nv_bfloat16 {
+    const float gr = round_bf16(gate), ur = round_bf16(up);
+    float a;
+    if (act_mode == 0) a = gr / (1.0f + expf(-gr));
+    else if (act_mode == 1) a = gr * 0.5f * (1.0f + erff(gr * 0.70710678118654752440f));
+    else a = 0.5f * gr * (1.0f + tanhf(0.79788456080286535588f * (gr + 0.044715f * gr * gr * gr)));
+    return __float2bfloat16_rn(round_bf16(a) * ur);
+  };
   if constexpr (kSplit == 1) {
     if (live) {
 #pragma unroll
-      for (int m = 0; m < kMT; ++m)
+      for (int m = 0; m < kMT; ++m) {
+        if constexpr (kGateUp) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int tok = m * 8 + 2 * t + (i & 1), r = g + (i >> 1) * 8;
-          if (tok < M) {
-            float v = acc[m][i];
-            if (bias) v += __bfloat162float(bias[n0 + r]);
-            y[(int64_t)tok * y_stride + n0 + r] = __float2bfloat16_rn(v);
+          for (int e = 0; e < 2; ++e) {
+            const int tok = m * 8 + 2 * t + e;
+            if (tok < M) {
+              float gv = acc[m][e], uv = acc[m][2 + e];
+              if (bias) { gv += __bfloat162float(bias[n0 + g]); uv += __bfloat162float(bias[n0 + g + 8]); }
+              y[(int64_t)tok * y_stride + ntile * 8 + g] = gate_up(gv, uv);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int tok = m * 8 + 2 * t + (i & 1), r = g + (i >> 1) * 8;
+            if (tok < M) {
+              float v = acc[m][i];
+              if (bias) v += __bfloat162float(bias[n0 + r]);
+              y[(int64_t)tok * y_stride + n0 + r] = __float2bfloat16_rn(v);
+            }
           }
         }
+      }
     }
     return;
   } else {
@@ -257,7 +283,17 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 #pragma unroll
         for (int w = 0; w < kSplit; ++w) sum += red[tl * kSplit + w][m][r * 8 + c];
         if (bias) sum += __bfloat162float(bias[nt * 16 + r]);
-        y[(int64_t)tok * y_stride + nt * 16 + r] = __float2bfloat16_rn(sum);
+        if constexpr (kGateUp) {
+          if (r < 8) {
+            float up = 0.f;
+#pragma unroll
+            for (int w = 0; w < kSplit; ++w) up += red[tl * kSplit + w][m][(r + 8) * 8 + c];
+            if (bias) up += __bfloat162float(bias[nt * 16 + r + 8]);
+            y[(int64_t)tok * y_stride + nt * 8 + r] = gate_up(sum, up);
+          }
+        } else {
+          y[(int64_t)tok * y_stride + nt * 16 + r] = __float2bfloat16_rn(sum);
+        }
       }
     }
   }
@@ -344,9 +380,10 @@ linear_bf16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, cons
 
 using namespace xb;
 
-extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x, int64_t x_stride,
-                                       const uint32_t* qweight, const uint32_t* meta, const void* bias, int M, int N,
-                                       int K, int group_size, xb_stream_t stream) {
+static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_stride, const uint32_t* qweight,
+                           const uint32_t* meta, const void* bias, int M, int N, int K, int group_size, int act_mode,
+                           xb_stream_t stream) {
+  const bool gate_up = act_mode >= 0;
   if (M == 0) return 0;
   XB_CHECK(M > 0 && M <= 64, "linear_w4a16_small_m: M=%d out of range (1..64); use the tcgen05 GEMM", M);
   XB_CHECK(N % 16 == 0 && K % 64 == 0, "linear_w4a16_small_m: N=%d must be %%16, K=%d %%64", N, K);
@@ -367,32 +404,24 @@ extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
   int gshift = 0;
   while ((1 << gshift) < tpg) ++gshift;
   const bool tg2 = tpg >= 2;
-  static const int occ3 = [] { const char* e = getenv("XB_W4_OCC"); return e ? atoi(e) : 0; }();
-#define XB_W4_LAUNCH(MT, SP, DP)                                                                              \
-  {                                                                                                           \
-    dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                              \
-    if (tg2 && MT == 1 && occ3 == 3) {                                                                        \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, 2, 2, 3, 2>, grid, block, 0, s, true, yy,         \
-                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
-    } else if (tg2 && MT == 1 && occ3 == 5) {                                                                 \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2, 2, 0, true>, grid, block, 0, s,  \
-                        true, yy, y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                    \
-    } else if (tg2 && MT == 1 && occ3 == 6) {                                                                 \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, 3, 2, 3, 2>, grid, block, 0, s, true, yy,         \
-                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
-    } else if (tg2 && MT == 1 && occ3 == 7) {                                                                 \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, 4, 2, 3, 1>, grid, block, 0, s, true, yy,         \
-                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
-    } else if (tg2 && MT == 1 && occ3 == 4) {                                                                 \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, 2, 2, 4, 1>, grid, block, 0, s, true, yy,         \
-                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
-    } else if (tg2) {                                                                                         \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2>, grid, block, 0, s, true, yy,    \
-                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift));                              \
-    } else {                                                                                                  \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, DP, 1>, grid, block, 0, s, true, yy, y_stride,    \
-                        xx, x_stride, qw, meta, bb, M, N, K, gshift));                                        \
-    }                                                                                                         \
+  // (tuning notes, B200: 2 CTAs/SM with an 8-tile ring beats 3-4 CTAs/SM with a shallower ring by 20-30 %; moving the
+  //  right shifts to IMAD.HI on the fma pipe is 29 % slower - the bf16x2 SUB/MUL on that pipe are the binding resource)
+#define XB_W4_LAUNCH(MT, SP, DP)                                                                               \
+  {                                                                                                            \
+    dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                               \
+    if (gate_up && tg2) {                                                                                      \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2, 2, 0, false, true>, grid, block, 0, s, true, \
+                        yy, y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift, act_mode));                 \
+    } else if (gate_up) {                                                                                      \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, DP, 1, 2, 0, false, true>, grid, block, 0, s, true, yy,  \
+                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift, act_mode));                     \
+    } else if (tg2) {                                                                                          \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2>, grid, block, 0, s, true, yy,     \
+                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift, act_mode));                     \
+    } else {                                                                                                   \
+      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, DP, 1>, grid, block, 0, s, true, yy, y_stride,     \
+                        xx, x_stride, qw, meta, bb, M, N, K, gshift, act_mode));                               \
+    }                                                                                                          \
   }
 #define XB_W4(MT, DP)                                   \
   switch (split) {                                      \
@@ -401,13 +430,30 @@ extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x,
     case 4: XB_W4_LAUNCH(MT, 4, DP) break;              \
     default: XB_W4_LAUNCH(MT, 8, DP) break;             \
   }
-  if (M <= 8) XB_W4(1, 8)
-  else if (M <= 16) XB_W4(2, 8)
-  else if (M <= 32) XB_W4(4, 4)
-  else XB_W4(8, 2)
+  XB_CHECK(!(gate_up && M > 16), "linear_w4a16_gate_up_act_small_m: M=%d > 16, use the GEMM + act_and_mul_interleaved8", M);
+  if (M <= 8) { XB_W4(1, 8) }
+  else if (M <= 16) { XB_W4(2, 8) }
+  else if (M <= 32) { XB_W4(4, 4) }
+  else { XB_W4(8, 2) }
 #undef XB_W4_LAUNCH
 #undef XB_W4
   return 0;
+}
+
+extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x, int64_t x_stride,
+                                       const uint32_t* qweight, const uint32_t* meta, const void* bias, int M, int N,
+                                       int K, int group_size, xb_stream_t stream) {
+  return w4_small_m_impl(y, y_stride, x, x_stride, qweight, meta, bias, M, N, K, group_size, -1, stream);
+}
+
+// gate_up_proj with the activation fused into the epilogue.  qweight / meta / bias rows must be in the interleaved
+// order produced by xllm_b200.quant.interleave_gate_up (per 16-row tile: 8 gate rows then the matching 8 up rows).
+// y [M, N/2].  act_mode: 0 silu, 1 gelu, 2 gelu_tanh.
+extern "C" int xb_linear_w4a16_gate_up_act_small_m(void* y, int64_t y_stride, const void* x, int64_t x_stride,
+                                                   const uint32_t* qweight, const uint32_t* meta, const void* bias,
+                                                   int M, int N, int K, int group_size, int act_mode, xb_stream_t stream) {
+  XB_CHECK(act_mode >= 0 && act_mode <= 2, "gate_up_act: unsupported act mode %d", act_mode);
+  return w4_small_m_impl(y, y_stride, x, x_stride, qweight, meta, bias, M, N, K, group_size, act_mode, stream);
 }
 
 extern "C" int xb_linear_bf16_small_m(void* y, int64_t y_stride, const void* x, int64_t x_stride, const void* w,

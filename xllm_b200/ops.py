@@ -389,3 +389,25 @@ def batch_chunked_prefill(query, k_cache, v_cache, paged_kv_indptr, paged_kv_ind
                                       c_i64(output.stride(1)), _p(output_lse), c_i32(B), c_i64(T), c_i32(max_qo_len),
                                       c_i32(Hq), c_i32(k_cache.size(2)), c_i32(D), c_i32(1 if causal else 0),
                                       c_f32(sm_scale), _stream()), "batch_chunked_prefill")
+
+
+def w4a16_gate_up_act(x, qweight, meta, group_size, act_mode="silu", bias=None, out=None, gate_up_buf=None):
+    """DenseMLPImpl's gate_up linear + act_and_mul (dense_mlp.cpp:97-118) with the INTERLEAVED gate/up packing
+    (quant.pack_w4_gate_up).  M <= 16: one fused kernel (activation in the GEMV epilogue); larger M: tcgen05
+    dequant-GEMM into `gate_up_buf` + act_and_mul over the interleaved columns."""
+    _cuda_bf16(x, "x")
+    if act_mode not in _ACT:
+        raise XllmB200Error(f"Unsupported act mode: {act_mode}")
+    M, K = x.shape
+    N = meta.size(1)
+    y = out if out is not None else torch.empty(M, N // 2, dtype=BF16, device=x.device)
+    if M <= 16:
+        check(lib().xb_linear_w4a16_gate_up_act_small_m(_p(y), c_i64(y.stride(0)), _p(x), c_i64(x.stride(0)), _p(qweight),
+                                                        _p(meta), _p(bias), c_i32(M), c_i32(N), c_i32(K), c_i32(group_size),
+                                                        c_i32(_ACT[act_mode]), _stream()), "w4a16_gate_up_act")
+        return y
+    gu = gate_up_buf if gate_up_buf is not None else torch.empty(M, N, dtype=BF16, device=x.device)
+    gemm_w4a16(x, qweight, meta, group_size, bias, gu)
+    check(lib().xb_act_and_mul_interleaved8_bf16(_p(y), _p(gu), c_i32(N // 2), c_i32(M), c_i32(_ACT[act_mode]), _stream()),
+          "act_and_mul_interleaved8")
+    return y

@@ -28,6 +28,22 @@ def pack_w4(q: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor, group_si
     return qweight, meta
 
 
+def interleave_gate_up_index(intermediate: int, device=None) -> torch.Tensor:
+    """Row permutation of a fused gate_up projection [2I, K] (gate rows then up rows) into the layout the fused
+    gate_up+activation kernel expects: per 16-row tile, 8 gate rows followed by the matching 8 up rows."""
+    assert intermediate % 8 == 0
+    t = torch.arange(intermediate // 8, device=device).repeat_interleave(16)
+    i = torch.arange(16, device=device).repeat(intermediate // 8)
+    return torch.where(i < 8, 8 * t + i, intermediate + 8 * t + (i - 8))
+
+
+def pack_w4_gate_up(q, scales, zeros, group_size=128, bias=None):
+    """pack a fused gate_up weight with interleaved rows -> (qweight, meta, bias_interleaved)."""
+    idx = interleave_gate_up_index(q.shape[0] // 2, q.device)
+    qw, meta = pack_w4(q[idx], scales[idx], zeros[idx], group_size)
+    return qw, meta, (bias[idx].contiguous() if bias is not None else None)
+
+
 def pack_w4_c(q: torch.Tensor) -> torch.Tensor:
     """Same nibble packing through the C routine (used by tests to pin the two packers against each other)."""
     N, K = q.shape

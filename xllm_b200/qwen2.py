@@ -79,6 +79,7 @@ class Linear:
         self.qweight = None     # int32 tiles
         self.meta = None        # int32 [K/g, N]
         self.bias = None
+        self.gate_up_interleaved = False   # w4a16 gate_up packed with quant.pack_w4_gate_up: activation fuses into the GEMV
         self.weight_scale = None   # fp8: float32 [1] per-tensor weight scale
         self.input_scale = None    # fp8: float32 [1] static activation scale (None -> dynamic per-tensor)
         self._x8 = None
@@ -158,6 +159,8 @@ class Qwen2Weights:
                 post_norm=(1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16),
                 qkv=mk(q_size + 2 * kv_size, H, cfg.qkv_bias), o=mk(H, q_size),
                 gate_up=mk(2 * I, H), down=mk(H, I)))
+            # synthetic packed nibbles are random anyway: declare the gate_up rows interleaved so the fused epilogue runs
+            w.layers[-1]["gate_up"].gate_up_interleaved = cfg.quant == "w4a16"
         return w
 
     def weight_bytes(self):
@@ -297,8 +300,13 @@ class Qwen2DecodeRunner:
                              self.attn_out.view(-1, self.nh, cfg.head_dim))
             # o_proj (+ all-reduce) + post-attention add+norm
             h = self._row_parallel(L["o"], self.attn_out, 0, L["post_norm"], self.buf_a)
-            L["gate_up"].forward(h, self.gate_up)
-            ops.act_and_mul(self.act, self.gate_up, "silu")
+            gu = L["gate_up"]
+            if gu.kind == "w4a16" and gu.gate_up_interleaved:
+                # gate_up GEMV with SiLU*mul in its epilogue (one launch instead of two)
+                ops.w4a16_gate_up_act(h, gu.qweight, gu.meta, gu.group_size, "silu", gu.bias, self.act, self.gate_up)
+            else:
+                gu.forward(h, self.gate_up)
+                ops.act_and_mul(self.act, self.gate_up, "silu")
             # down_proj (+ all-reduce) + the NEXT layer's input add+norm (or the final norm)
             next_w = w.layers[li + 1]["input_norm"] if li + 1 < n_layers else w.final_norm
             h = self._row_parallel(L["down"], self.act, 1, next_w, self.buf_b)
