@@ -121,7 +121,7 @@ def test_w4a16_gate_up_act_fused(M, I, K, bias, built_lib):
     qw, meta, bi = quant.pack_w4_gate_up(q, s, z, gs, b)
     y = ops.w4a16_gate_up_act(x.to(DEV), qw.to(DEV), meta.to(DEV), gs, "silu", bi.to(DEV) if bi is not None else None)
     # act(gate)*up of two 1-ulp-accurate linears: a flip in either input moves the product by up to ~2 ulps
-    assert_close_bf16(y, ref, ulps=3, rel_l2=2e-3, what=f"gate_up_act M={M} I={I}", atol=1e-4)
+    assert_close_bf16(y, ref, ulps=4, rel_l2=2e-3, what=f"gate_up_act M={M} I={I}", atol=1e-4)
     frac = (y.cpu() != ref).float().mean().item()
     assert frac < 0.05, f"{frac:.3f} of elements differ"
 
