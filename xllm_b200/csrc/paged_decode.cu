@@ -320,23 +320,35 @@ paged_decode_kernel(const DecodeParams p) {
   __syncthreads();
   for (int h = warp; h < nheads; h += kWarpsT) {
     const int64_t base = ((int64_t)b * p.num_qo_heads + head0 + h) * p.max_splits;
+    // all of this head's split LSEs in one round trip (<= 8 per lane: max_splits <= 2 * head_dim = 256)
+    float ls[8];
     float mx = -INFINITY;
-    for (int s = lane; s < n_splits; s += 32) mx = fmaxf(mx, __ldcg(p.part_lse + base + s));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int s = lane + 32 * u;
+      ls[u] = s < n_splits ? __ldcg(p.part_lse + base + s) : -INFINITY;
+      mx = fmaxf(mx, ls[u]);
+    }
     mx = warp_max(mx);
     const float m_safe = mx == -INFINITY ? 0.f : mx;
     float wsum = 0.f;
-    for (int s = lane; s < n_splits; s += 32) {
-      const float w = exp2f(__ldcg(p.part_lse + base + s) - m_safe);
-      sm_w[h * n_splits + s] = w;
-      wsum += w;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      ls[u] = exp2f(ls[u] - m_safe);     // 0 for the padding entries
+      wsum += ls[u];
     }
     wsum = warp_sum(wsum);
     const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
-    for (int s = lane; s < n_splits; s += 32) sm_w[h * n_splits + s] *= inv;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int s = lane + 32 * u;
+      if (s < n_splits) sm_w[h * n_splits + s] = ls[u] * inv;
+    }
     if (lane == 0) sm_lse[h] = wsum > 0.f ? mx + log2f(wsum) : -INFINITY;
   }
   __syncthreads();
-  // Stage 2: weighted sum of the partial outputs; all addresses are known up front, 8 loads in flight per thread
+  // Stage 2: weighted sum of the partial outputs; all addresses are known up front, 16 predicated loads in flight per
+  // thread (37 splits = 3 round trips to L2 instead of one per split)
   for (int it = threadIdx.x; it < kItems; it += kWarpsT * 32) {
     const int h = it / (kD / 4), d4 = (it % (kD / 4)) * 4;
     if (h >= nheads) continue;
@@ -344,21 +356,15 @@ paged_decode_kernel(const DecodeParams p) {
     const float4* src = reinterpret_cast<const float4*>(p.part_o + (((int64_t)b * p.num_qo_heads + qh) * p.max_splits) * kD + d4);
     const float* wrow = sm_w + h * n_splits;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int s = 0;
-    for (; s + 8 <= n_splits; s += 8) {
-      float4 v[8];
+    for (int s = 0; s < n_splits; s += 16) {
+      float4 v[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(s + u) * (kD / 4));
+      for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (int64_t)min(s + u, n_splits - 1) * (kD / 4));
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float w = wrow[s + u];
+      for (int u = 0; u < 16; ++u) {
+        const float w = s + u < n_splits ? wrow[s + u] : 0.f;
         acc.x += v[u].x * w; acc.y += v[u].y * w; acc.z += v[u].z * w; acc.w += v[u].w * w;
       }
-    }
-    for (; s < n_splits; ++s) {
-      const float4 v = __ldcg(src + (int64_t)s * (kD / 4));
-      const float w = wrow[s];
-      acc.x += v.x * w; acc.y += v.y * w; acc.z += v.z * w; acc.w += v.w * w;
     }
     uint2 ob;
     ob.x = pack_bf16x2(acc.x, acc.y);
