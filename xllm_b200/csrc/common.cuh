@@ -93,6 +93,14 @@ __device__ __forceinline__ float round_bf16(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
 
+// 2^x on the SFU, one MUFU.EX2 (flush-to-zero, ~2 ulp): the softmax inner loops are MUFU-throughput bound
+// (16 ex2 / clk / SM), the range/denormal fix-up code of exp2f() would only add issue slots
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -115,6 +123,37 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
 }
 __device__ __forceinline__ uint4 ldg_cached(const void* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+// Ampere-style async copies global -> shared.  Used by the HBM-streaming small-M kernels as a per-lane private
+// staging ring: completion is tracked in ORDER by commit groups (wait_group N = "all but the N youngest"), which a
+// register ring of plain LDGs cannot express - ptxas puts every in-flight LDG of a loop on one scoreboard and a wait
+// on the oldest load then waits for the youngest too, so the prefetch depth silently collapses to zero.
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {   // L2 only (streamed once)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ uint4 lds_128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint2 lds_64(uint32_t addr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+  return r;
 }
 
 // sat_e4m3(x*inv_scale): fp8_quant_utils.cuh:112-129 (clamp to +-448, then

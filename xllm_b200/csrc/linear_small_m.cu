@@ -23,6 +23,8 @@
 //   so (w >> 4i) & 0x000f000f yields the bf16x2 mma A-fragment register a_i.
 // The mma k index is a permutation of physical k (dot products do not care);
 // the x fragment is gathered with the same permutation.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace xb {
@@ -116,23 +118,32 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   const uint4* wp = qweight + ((int64_t)ntile * ktiles + (int64_t)s_begin * kTG) * 32 + lane;
   const uint32_t* mbase = meta + n0 + g;
 
+  // ---- staging ring: per-lane PRIVATE shared-memory slots filled with cp.async ------------------------------
+  // Every lane copies exactly the 16 bytes (and the two scale/zero words) it will consume itself and reads them
+  // back with LDS: no cross-lane hand-off, so no barrier - only the in-order commit-group wait.  (A register ring
+  // of LDGs looks equivalent but is not: ptxas tracks all in-flight LDGs of the loop on one scoreboard, so waiting
+  // for the oldest slot waits for the refill issued a moment ago and the HBM latency is exposed on every slot.)
+  extern __shared__ __align__(16) uint8_t ring_smem[];
+  constexpr int kSlotBytes = kTG * 512 + 256;          // kTG k64 tiles (32 lanes x 16 B) + 32 lanes x 2 meta words
+  const uint32_t ring_w = smem_addr_u32(ring_smem) + warp * (kDepth * kSlotBytes) + lane * 16;
+  const uint32_t ring_m = smem_addr_u32(ring_smem) + warp * (kDepth * kSlotBytes) + kTG * 512 + lane * 8;
+  auto issue = [&](int i, const uint4* wsrc, const uint32_t* msrc) {
+#pragma unroll
+    for (int u = 0; u < kTG; ++u) cp_async_16(ring_w + i * kSlotBytes + u * 512, wsrc + u * 32);
+    cp_async_4(ring_m + i * kSlotBytes, msrc);
+    cp_async_4(ring_m + i * kSlotBytes + 4, msrc + 8);
+  };
+
   // ---- prologue: fill the ring (weights + scale/zero words do not depend on the producer kernel) ----
-  uint4 ring[kDepth][kTG];
-  uint32_t ring_m0[kDepth], ring_m1[kDepth];
 #pragma unroll
   for (int i = 0; i < kDepth; ++i) {
-    if (s_begin + i < s_end) {
-#pragma unroll
-      for (int u = 0; u < kTG; ++u) ring[i][u] = ldg_stream(wp + (i * kTG + u) * 32);
-      const uint32_t* mr = mbase + (int64_t)(((s_begin + i) * kTG) >> gshift) * N;
-      ring_m0[i] = __ldg(mr);
-      ring_m1[i] = __ldg(mr + 8);
-    }
+    if (s_begin + i < s_end) issue(i, wp + i * kTG * 32, mbase + (int64_t)(((s_begin + i) * kTG) >> gshift) * N);
+    cp_async_commit();     // one group per slot, empty or not: group n <-> slot n of this warp
   }
   wp += kDepth * kTG * 32;   // next slot to prefetch
   pdl_wait();  // x (and bias) come from the producer kernel
 
-  // x fragments: lane (g,t) needs x[tok = 8m+g][k0 + 16t .. +16) per tile; pipelined one slot ahead
+  // x fragments: lane (g,t) needs x[tok = 8m+g][k0 + 16t .. +16) per tile
   // token columns past M read the last valid token instead of zeros: their accumulator columns are
   // finite garbage that is never stored, and the loads need neither a predicate nor a zero fill
   const __nv_bfloat16* xp[kMT];
@@ -141,7 +152,7 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     const int tok = min(m * 8 + g, M - 1);
     xp[m] = x + (int64_t)tok * x_stride + (int64_t)s_begin * kTG * 64 + 16 * t;
   }
-  // x fragments come from L1 (~35 cycles), hidden by the other warps: registers go to occupancy instead of an x ring
+  // x fragments come from L1 (~35 cycles), hidden by the other warps
   auto load_xtile = [&](XRing<kMT>& d) {
 #pragma unroll
     for (int m = 0; m < kMT; ++m) {
@@ -151,9 +162,13 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     }
   };
 
-  auto consume = [&](const uint4 (&wq)[kTG], uint32_t mt0, uint32_t mt1) {
-    const uint32_t s0 = __byte_perm(mt0, 0, 0x1010), z0 = __byte_perm(mt0, 0, 0x3232);
-    const uint32_t s1 = __byte_perm(mt1, 0, 0x1010), z1 = __byte_perm(mt1, 0, 0x3232);
+  auto consume = [&](int i) {
+    uint4 wq[kTG];
+#pragma unroll
+    for (int u = 0; u < kTG; ++u) wq[u] = lds_128(ring_w + i * kSlotBytes + u * 512);
+    const uint2 mt = lds_64(ring_m + i * kSlotBytes);
+    const uint32_t s0 = __byte_perm(mt.x, 0, 0x1010), z0 = __byte_perm(mt.x, 0, 0x3232);
+    const uint32_t s1 = __byte_perm(mt.y, 0, 0x1010), z1 = __byte_perm(mt.y, 0, 0x3232);
 #pragma unroll
     for (int u = 0; u < kTG; ++u) {
       XRing<kMT> xf;
@@ -185,32 +200,27 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   // row pointer just advances by N per slot; otherwise it is recomputed from the slot index.
   const bool slot_is_group = (1 << gshift) == kTG;
   const uint32_t* mp = mbase + (int64_t)(((s_begin + kDepth) * kTG) >> gshift) * N;   // next slot to prefetch
-  auto refill = [&](int i, int slot) {
-#pragma unroll
-    for (int u = 0; u < kTG; ++u) ring[i][u] = ldg_stream(wp + u * 32);
-    const uint32_t* mr = slot_is_group ? mp : mbase + (int64_t)((slot * kTG) >> gshift) * N;
-    ring_m0[i] = __ldg(mr);
-    ring_m1[i] = __ldg(mr + 8);
-  };
-
 
   int sl = s_begin;
-  // full rounds: every ring slot is consumed, then (while data remains) refilled kDepth slots ahead
+  // full rounds: every ring slot is consumed, then (while data remains) refilled kDepth slots ahead.  The LDS of a
+  // slot have returned before the HMMAs that use them issue, so the refill that follows cannot overtake them.
   for (; sl + kDepth <= s_end; sl += kDepth) {
 #pragma unroll
     for (int i = 0; i < kDepth; ++i) {
-      consume(ring[i], ring_m0[i], ring_m1[i]);
-      if (sl + i + kDepth < s_end) refill(i, sl + i + kDepth);
+      cp_async_wait<kDepth - 1>();
+      consume(i);
+      if (sl + i + kDepth < s_end)
+        issue(i, wp, slot_is_group ? mp : mbase + (int64_t)(((sl + i + kDepth) * kTG) >> gshift) * N);
+      cp_async_commit();
       wp += kTG * 32;
       mp += N;
     }
   }
-  // tail: fewer than kDepth slots left, all already in the ring
+  // tail: fewer than kDepth slots left, all already in flight
+  cp_async_wait<0>();
 #pragma unroll
   for (int i = 0; i < kDepth; ++i) {
-    if (sl + i < s_end) {
-      consume(ring[i], ring_m0[i], ring_m1[i]);
-    }
+    if (sl + i < s_end) consume(i);
   }
   pdl_launch_dependents();
   float acc[kMT][4];
@@ -380,6 +390,9 @@ linear_bf16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, cons
 
 using namespace xb;
 
+// dynamic shared memory of the W4 kernel: kWarps private rings of `depth` slots (kTG tiles + meta words each)
+static constexpr size_t w4_ring_bytes(int depth, int tg) { return (size_t)kWarps * depth * (tg * 512 + 256); }
+
 static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_stride, const uint32_t* qweight,
                            const uint32_t* meta, const void* bias, int M, int N, int K, int group_size, int act_mode,
                            xb_stream_t stream) {
@@ -404,24 +417,29 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   int gshift = 0;
   while ((1 << gshift) < tpg) ++gshift;
   const bool tg2 = tpg >= 2;
-  // (tuning notes, B200: 2 CTAs/SM with an 8-tile ring beats 3-4 CTAs/SM with a shallower ring by 20-30 %; moving the
-  //  right shifts to IMAD.HI on the fma pipe is 29 % slower - the bf16x2 SUB/MUL on that pipe are the binding resource)
+  static const bool occ3 = [] { const char* e = getenv("XB_W4_OCC"); return e && atoi(e) == 3; }();   // experiment switch
+#define XB_W4_GO(MT, SP, DEPTH, TG, OCC, GU)                                                                      \
+  {                                                                                                                 \
+    auto kern = linear_w4a16_small_m_kernel<MT, SP, DEPTH, TG, OCC, 0, false, GU>;                                  \
+    static bool attr_done = false; /* per instantiation: static reduction scratch + ring may exceed 48 KB */        \
+    if (!attr_done) {                                                                                               \
+      XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
+                                      (int)w4_ring_bytes(DEPTH, TG)));                                              \
+      attr_done = true;                                                                                             \
+    }                                                                                                               \
+    XB_CUDA_OK(launch(kern, grid, block, w4_ring_bytes(DEPTH, TG), s, true, yy, y_stride, xx, x_stride, qw, meta,   \
+                      bb, M, N, K, gshift, act_mode));                                                              \
+  }
+#define XB_W4_OCC(MT, SP, DEPTH, TG, GU)                                                                           \
+  if (MT == 1 && occ3) XB_W4_GO(MT, SP, DEPTH, TG, (MT == 1 ? 3 : 2), GU)                                         \
+  else XB_W4_GO(MT, SP, DEPTH, TG, 2, GU)
 #define XB_W4_LAUNCH(MT, SP, DP)                                                                               \
   {                                                                                                            \
     dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                               \
-    if (gate_up && tg2) {                                                                                      \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2, 2, 0, false, true>, grid, block, 0, s, true, \
-                        yy, y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift, act_mode));                 \
-    } else if (gate_up) {                                                                                      \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, DP, 1, 2, 0, false, true>, grid, block, 0, s, true, yy,  \
-                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift, act_mode));                     \
-    } else if (tg2) {                                                                                          \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, (DP + 1) / 2, 2>, grid, block, 0, s, true, yy,     \
-                        y_stride, xx, x_stride, qw, meta, bb, M, N, K, gshift, act_mode));                     \
-    } else {                                                                                                   \
-      XB_CUDA_OK(launch(linear_w4a16_small_m_kernel<MT, SP, DP, 1>, grid, block, 0, s, true, yy, y_stride,     \
-                        xx, x_stride, qw, meta, bb, M, N, K, gshift, act_mode));                               \
-    }                                                                                                          \
+    if (gate_up && tg2) { XB_W4_OCC(MT, SP, (DP + 1) / 2, 2, true) }                                           \
+    else if (gate_up) { XB_W4_OCC(MT, SP, DP, 1, true) }                                                       \
+    else if (tg2) { XB_W4_OCC(MT, SP, (DP + 1) / 2, 2, false) }                                                \
+    else { XB_W4_OCC(MT, SP, DP, 1, false) }                                                                   \
   }
 #define XB_W4(MT, DP)                                   \
   switch (split) {                                      \
@@ -431,10 +449,14 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
     default: XB_W4_LAUNCH(MT, 8, DP) break;             \
   }
   XB_CHECK(!(gate_up && M > 16), "linear_w4a16_gate_up_act_small_m: M=%d > 16, use the GEMM + act_and_mul_interleaved8", M);
+  // ring depth: 8 k64 tiles (4 KB) per warp in flight = 64 KB per SM at 2 CTAs/SM, ~1.5x the HBM latency-bandwidth
+  // product; the ring lives in shared memory, so the depth no longer competes with the accumulators for registers
   if (M <= 8) { XB_W4(1, 8) }
   else if (M <= 16) { XB_W4(2, 8) }
-  else if (M <= 32) { XB_W4(4, 4) }
-  else { XB_W4(8, 2) }
+  else if (M <= 32) { XB_W4(4, 8) }
+  else { XB_W4(8, 8) }
+#undef XB_W4_GO
+#undef XB_W4_OCC
 #undef XB_W4_LAUNCH
 #undef XB_W4
   return 0;

@@ -241,7 +241,7 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       }
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float m_safe = m_new == -INFINITY ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_safe);
+      const float alpha = fast_exp2(m_run - m_safe);
       // ---- P smem / O are free once PV(j-1) has completed ----
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);
@@ -269,8 +269,8 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_safe);
-          float p1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_safe);
+          float p0 = fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - m_safe);
+          float p1 = fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - m_safe);
           if (need_mask) {
             if (c * 32 + i >= col_lim) p0 = 0.f;
             if (c * 32 + i + 1 >= col_lim) p1 = 0.f;
