@@ -200,8 +200,10 @@ def main():
     import torch
     import torch.distributed as dist
     from xllm_b200 import _lib
-    wd = int(os.environ.get("XB_BENCH_WATCHDOG", "0"))
-    if wd > 0:                      # dump every thread's stack and exit if the run has not finished after `wd` seconds
+    # watchdog: dump every thread's stack and exit if the run has not finished after `wd` seconds.  On by default for
+    # multi-rank runs (a wedged collective must fail the run, not hang the box); XB_BENCH_WATCHDOG=0 disables it.
+    wd = int(os.environ.get("XB_BENCH_WATCHDOG", "600" if world > 1 else "0"))
+    if wd > 0:
         faulthandler.dump_traceback_later(wd, exit=True)
 
     def log(msg):

@@ -65,8 +65,11 @@ def report(name, us, nbytes, us_g=None):
 def bench_decode(B, ctx, HQ=28, HKV=4, D=128, page=128, layers=28):
     npg = (ctx + page - 1) // page
     nblocks = B * npg + 1
-    caches = [(torch.randn(nblocks, page, HKV, D, device=DEV, dtype=BF16), torch.randn(nblocks, page, HKV, D, device=DEV, dtype=BF16))
-              for _ in range(layers)]
+    if os.environ.get("XB_MB_LAYOUT", "NHD") == "HND":     # head-major pages: each kv head's rows are contiguous
+        mk = lambda: torch.randn(nblocks, HKV, page, D, device=DEV, dtype=BF16).permute(0, 2, 1, 3)
+    else:                                                  # the reference layout [blocks, page, Hkv, D]
+        mk = lambda: torch.randn(nblocks, page, HKV, D, device=DEV, dtype=BF16)
+    caches = [(mk(), mk()) for _ in range(layers)]
     q = torch.randn(B, HQ, D, device=DEV, dtype=BF16)
     out = torch.empty_like(q)
     indptr = torch.arange(0, (B + 1) * npg, npg, dtype=torch.int32, device=DEV)

@@ -73,14 +73,6 @@ paged_decode_kernel(const DecodeParams p) {
   constexpr int kVC = kD / 64;      // V chunk loads per token per lane
   constexpr int kHeads = 8 * kGT;
   constexpr int kRS = kD + 4;       // padded smem row (floats)
-  // KV staging ring: per-lane PRIVATE 16-byte slots filled by cp.async and read back by the same lane with LDS (no
-  // cross-lane hand-off, so no barrier; completion is the in-order commit-group wait).  A register double buffer of
-  // LDGs is NOT equivalent: ptxas tracks every in-flight LDG of the loop on one scoreboard, so the wait for the
-  // current block also waits for the block just requested and nothing overlaps.  The ring is dead once the block
-  // loop ends; the warp-merge scratch below aliases it (one __syncthreads in between).
-  constexpr int kStages = 3;
-  constexpr int kLaneChunks = 2 * kChunks + 4 * kVC;   // 16-byte chunks per lane per 16-token block (K + V)
-  constexpr int kStageBytes = kLaneChunks * 512;
   extern __shared__ __align__(16) float smem[];
   float* sm_o = smem;                              // [warps][kHeads][kRS]
   float* sm_m = sm_o + kWarpsT * kHeads * kRS;      // [warps][kHeads]
@@ -113,56 +105,33 @@ paged_decode_kernel(const DecodeParams p) {
     uint4 kf[2][kChunks];
     uint4 vf[4][kVC];
   };
-  const uint32_t ring = smem_addr_u32(smem) + warp * (kStages * kStageBytes) + lane * 16;
-  // 16 independent 16-byte async copies of one 16-token block; chunk order = MMA fragment order
-  auto issue_block = [&](int stage, int blk) {
+  // 16 independent 16-byte loads of one 16-token block, straight into MMA fragment registers
+  auto load_block = [&](KVFrag& f, int blk) {
     const int tb = t_begin + (blk << 4);
-    const uint32_t dst = ring + stage * kStageBytes;
 #pragma unroll
     for (int tile = 0; tile < 2; ++tile) {
       const int tok = min(tb + tile * 8 + g, last_tok);
       const __nv_bfloat16* row = kv_row(p, p.k_cache, indptr0, tok, kvh);
 #pragma unroll
-      for (int i = 0; i < kChunks; ++i) cp_async_16(dst + (tile * kChunks + i) * 512, row + (4 * i + t) * 8);
+      for (int i = 0; i < kChunks; ++i) f.kf[tile][i] = ldg_stream(row + (4 * i + t) * 8);
     }
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const int tok = min(tb + (s >> 1) * 8 + 2 * t + (s & 1), last_tok);
       const __nv_bfloat16* row = kv_row(p, p.v_cache, indptr0, tok, kvh);
 #pragma unroll
-      for (int c = 0; c < kVC; ++c) cp_async_16(dst + (2 * kChunks + s * kVC + c) * 512, row + (c * 8 + g) * 8);
+      for (int c = 0; c < kVC; ++c) f.vf[s][c] = ldg_stream(row + (c * 8 + g) * 8);
     }
-  };
-  auto read_block = [&](KVFrag& f, int stage) {
-    const uint32_t src = ring + stage * kStageBytes;
-#pragma unroll
-    for (int tile = 0; tile < 2; ++tile)
-#pragma unroll
-      for (int i = 0; i < kChunks; ++i) f.kf[tile][i] = lds_128(src + (tile * kChunks + i) * 512);
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-      for (int c = 0; c < kVC; ++c) f.vf[s][c] = lds_128(src + (2 * kChunks + s * kVC + c) * 512);
   };
 
   int blk = warp;
   bool have = blk < nblk;
-  // Prologue: up to kStages blocks of this warp in flight.  With early_prefetch they are requested while the producer
-  // kernel (RoPE + KV scatter of the NEWEST token) may still be running - except the block that holds that newest
-  // token, which is the last block of the request and therefore the last one in issue order as well.
-  int n_issued = 0;
-  if (p.early_prefetch) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      const int bs = warp + s * kWarpsT;
-      if (n_issued == s && bs < nblk && t_begin + (bs << 4) + 16 <= last_tok) {
-        issue_block(s, bs);
-        cp_async_commit();
-        n_issued = s + 1;
-      }
-    }
-    pdl_wait();
-  }
+  KVFrag cur;
+  // With early_prefetch the first block of every warp is fetched while the producer kernel (RoPE + KV scatter of the
+  // NEWEST token) may still be running - except the block that holds that newest token.
+  const bool early = p.early_prefetch && have && (t_begin + (blk << 4) + 16 <= last_tok);
+  if (early) load_block(cur, blk);
+  if (p.early_prefetch) pdl_wait();
 
   // ---- Q fragments (chunk 4i+t of head g / g+8, same permutation as K) -------
   uint4 qa[kChunks], qb[kChunks];
@@ -177,14 +146,7 @@ paged_decode_kernel(const DecodeParams p) {
         qb[i] = *reinterpret_cast<const uint4*>(qrow + (int64_t)(head0 + g + 8) * p.q_stride_h + (4 * i + t) * 8);
     }
   }
-#pragma unroll
-  for (int s = 0; s < kStages; ++s) {
-    if (s >= n_issued) {                      // one commit group per stage, empty or not: group n <-> block n of the warp
-      const int bs = warp + s * kWarpsT;
-      if (bs < nblk) issue_block(s, bs);
-      cp_async_commit();
-    }
-  }
+  if (have && !early) load_block(cur, blk);
 
   float o_acc[kNT][4];
 #pragma unroll
@@ -194,12 +156,13 @@ paged_decode_kernel(const DecodeParams p) {
   float m_run[2] = {-INFINITY, -INFINITY};  // head g, head g+8
   float l_run[2] = {0.f, 0.f};              // per-thread partial sums
 
-  int stage = 0;
   while (have) {
     const int tb = t_begin + (blk << 4);
-    cp_async_wait<kStages - 1>();             // the oldest outstanding group = this block
-    KVFrag cur;
-    read_block(cur, stage);
+    // ---- prefetch the warp's next block while this one is consumed -----------
+    const int nblk_next = blk + kWarpsT;
+    const bool have_next = nblk_next < nblk;
+    KVFrag nxt;
+    if (have_next) load_block(nxt, nblk_next);
     const uint4 (&kf)[2][kChunks] = cur.kf;
     const uint4 (&vf)[4][kVC] = cur.vf;
     // ---- S = Q K^T ----------------------------------------------------------
@@ -269,16 +232,10 @@ paged_decode_kernel(const DecodeParams p) {
         mma_bf16_16816(o_acc[c * 8 + 2 * r + 1], pa[0], pa[1], pa[2], pa[3], b0o, b1o);
       }
     }
-    // refill this stage kStages blocks ahead (its LDS have returned: every fragment fed an HMMA issued above)
-    const int nb = blk + kStages * kWarpsT;
-    if (nb < nblk) issue_block(stage, nb);
-    cp_async_commit();
-    blk += kWarpsT;
-    have = blk < nblk;
-    stage = stage + 1 == kStages ? 0 : stage + 1;
+    if (have_next) cur = nxt;
+    blk = nblk_next;
+    have = have_next;
   }
-  cp_async_wait<0>();
-  __syncthreads();   // every warp is done with its ring: the merge scratch below aliases it
 
   // ---- publish warp state ------------------------------------------------------
 #pragma unroll
@@ -420,9 +377,7 @@ paged_decode_kernel(const DecodeParams p) {
 template <int kD, int kGT, int kW>
 static int launch_decode_w(const DecodeParams& p, int batch, cudaStream_t stream) {
   constexpr int kHeads = 8 * kGT;
-  const size_t merge = (size_t)kW * kHeads * (kD + 4 + 2) * sizeof(float);
-  const size_t ring = (size_t)kW * 3 * (kD / 8) * 512;   // kWarps x kStages x (K+V 16-byte chunks per lane) x 32 lanes x 16 B
-  const size_t smem = merge > ring ? merge : ring;
+  const size_t smem = (size_t)kW * kHeads * (kD + 4 + 2) * sizeof(float);
   auto kern = paged_decode_kernel<kD, kGT, kW>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
