@@ -1,0 +1,105 @@
+"""Host-side logic of the C ABI that needs no GPU: the decode planner's invariants over a sweep of batch / head /
+page geometries, the plan flag word, and the argument validation every launcher performs before its first CUDA call
+(errors come back as a non-zero code + xb_last_error(), never as a crash or a silent CPU path)."""
+import ctypes
+import itertools
+
+import pytest
+
+from xllm_b200 import _lib
+
+c_void = ctypes.c_void_p
+
+
+def _plan(lib, batch, hq, hkv, d, page, max_pages, sms=148):
+    plan = (ctypes.c_int64 * 8)()
+    rc = lib.xb_decode_plan(plan, batch, hq, hkv, d, page, max_pages, sms)
+    return rc, plan
+
+
+@pytest.mark.parametrize("batch,hq,hkv,d", [(1, 28, 4, 128), (8, 28, 4, 128), (64, 28, 4, 128), (256, 28, 4, 128),
+                                            (1, 64, 8, 128), (3, 14, 2, 64), (1, 32, 32, 128), (5, 40, 8, 128)])
+@pytest.mark.parametrize("page,max_pages", [(16, 256), (128, 32), (1, 4096), (48, 100), (128, 1024)])
+def test_decode_plan_invariants(batch, hq, hkv, d, page, max_pages, built_lib, monkeypatch):
+    monkeypatch.delenv("XB_DECODE_CHUNK", raising=False)
+    monkeypatch.delenv("XB_DECODE_WARPS", raising=False)
+    lib = _lib.lib()
+    rc, p = _plan(lib, batch, hq, hkv, d, page, max_pages)
+    assert rc == 0, lib.xb_last_error()
+    chunk, splits = p[0], p[1]
+    max_kv = page * max_pages
+    assert chunk % 16 == 0 and chunk >= 16, "chunks are whole 16-token blocks"
+    assert splits >= 1 and chunk * splits >= max_kv, "the chunks cover the longest admissible request"
+    assert chunk * (splits - 1) < max_kv, "no empty trailing split"
+    assert splits <= 2 * d, "split merge scratch is sized for 2*head_dim splits"
+    # workspaces: partial O + LSE per (request, q head, split); one ticket word per (request, kv head, head tile)
+    if splits > 1:
+        assert p[2] >= batch * hq * splits * (d + 1) * 4
+    group = hq // hkv
+    head_tiles = (group + 15) // 16
+    assert (p[3] & 0xFFFFFFFF) >= batch * hkv * head_tiles * 4
+    assert (p[4], p[5], p[6]) == (batch, hq, hkv)
+    assert p[7] & 0xFFFF == d and (p[7] >> 16) & 0xFFFFFF == page and (p[7] >> 40) in (4, 8)
+    # one wave: with few (request, kv head) units the planner splits the KV range to fill the SMs, never beyond them
+    units = batch * hkv * head_tiles
+    if units >= 148:
+        assert splits == 1 or chunk * (splits - 1) < max_kv
+    else:
+        assert units * splits <= max(148, units) + units, f"{units} units x {splits} splits overshoots one wave"
+
+
+def test_decode_plan_flags_and_env(built_lib, monkeypatch):
+    lib = _lib.lib()
+    rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)
+    assert rc == 0 and (p[3] >> 32) & 1 == 0
+    assert lib.xb_decode_plan_set_flags(p, 1) == 0 and (p[3] >> 32) & 1 == 1
+    low = p[3] & 0xFFFFFFFF
+    assert lib.xb_decode_plan_set_flags(p, 0) == 0 and (p[3] >> 32) & 1 == 0 and p[3] & 0xFFFFFFFF == low
+    assert lib.xb_decode_plan_set_flags(None, 1) != 0
+    monkeypatch.setenv("XB_DECODE_CHUNK", "200")          # rounded down to whole blocks
+    rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)
+    assert rc == 0 and p[0] == 192
+    monkeypatch.setenv("XB_DECODE_WARPS", "4")
+    rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)
+    assert rc == 0 and p[7] >> 40 == 4
+
+
+@pytest.mark.parametrize("args", [(0, 28, 4, 128, 128, 32), (1, 28, 3, 128, 128, 32), (1, 28, 4, 256, 128, 32),
+                                  (1, 28, 4, 128, 0, 32), (1, 28, 4, 128, 128, 0), (1, 28, 0, 128, 128, 32)])
+def test_decode_plan_rejects_bad_geometry(args, built_lib):
+    lib = _lib.lib()
+    rc, _ = _plan(lib, *args)
+    assert rc != 0 and len(lib.xb_last_error()) > 0
+
+
+def test_launchers_validate_before_touching_the_gpu(built_lib):
+    """Every call below must fail in the argument checks (no device pointer is ever dereferenced: they are NULL)."""
+    lib = _lib.lib()
+    i32, i64, f32 = ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    null = c_void(0)
+    cases = {
+        "small-M W4: M out of range": lambda: lib.xb_linear_w4a16_small_m(null, i64(0), null, i64(0), null, null, null, i32(65),
+                                                                         i32(4608), i32(3584), i32(128), null),
+        "small-M W4: N not a multiple of 16": lambda: lib.xb_linear_w4a16_small_m(null, i64(0), null, i64(0), null, null, null,
+                                                                                 i32(1), i32(4600), i32(3584), i32(128), null),
+        "small-M W4: group does not divide K": lambda: lib.xb_linear_w4a16_small_m(null, i64(0), null, i64(0), null, null, null,
+                                                                                  i32(1), i32(4608), i32(3584), i32(96), null),
+        "gate_up act: unknown activation": lambda: lib.xb_linear_w4a16_gate_up_act_small_m(null, i64(0), null, i64(0), null, null,
+                                                                                            null, i32(1), i32(4608), i32(3584),
+                                                                                            i32(128), i32(7), null),
+        "small-M bf16: M out of range": lambda: lib.xb_linear_bf16_small_m(null, i64(0), null, i64(0), null, null, i32(99), i32(64),
+                                                                           i32(64), null),
+        "small-M bf16: K not a multiple of 32": lambda: lib.xb_linear_bf16_small_m(null, i64(0), null, i64(0), null, null, i32(1),
+                                                                                   i32(64), i32(48), null),
+        "paged decode: null plan": lambda: lib.xb_paged_decode_bf16(None, null, i64(0), i64(0), null, null, i64(0), i64(0), i64(0),
+                                                                    null, null, null, null, i64(0), i64(0), null, f32(1.0), null,
+                                                                    null, null),
+    }
+    for what, call in cases.items():
+        rc = call()
+        assert rc != 0, f"{what}: accepted"
+        assert len(lib.xb_last_error()) > 0, f"{what}: no message"
+    # M == 0 is a no-op, not an error (empty decode batch)
+    assert lib.xb_linear_w4a16_small_m(null, i64(0), null, i64(0), null, null, null, i32(0), i32(4608), i32(3584), i32(128),
+                                       null) == 0
+    assert lib.xb_linear_bf16_small_m(null, i64(0), null, i64(0), null, null, i32(0), i32(64), i32(64), null) == 0
