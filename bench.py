@@ -46,6 +46,24 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(name="r01_w4_gemv_gateup.md"):
+    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full` summary of the
+    same kernel on the same shape (profiles/, written by tools/ncu_summary.py).  None when the summary is absent."""
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        for ln in open(os.path.join(ROOT, "profiles", name)):
+            if ln.startswith("traffic = dram read + write ="):
+                parts = ln.split("=")[-1].split("+")
+                total = 0.0
+                for part in parts:
+                    v, u = part.split()
+                    total += float(v) * unit[u]
+                return int(total)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -422,7 +440,9 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": f"linear_w4a16_small_m_kernel (gate_up_proj {gu.N}x{gu.K}, 28 launches/step)",
-                         "per_rank": True, "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None,
+                         "per_rank": True, "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                         # ncu dram__bytes_read+write of the same kernel and shape (single GPU, unsharded shape only)
+                         "traffic": profiled_traffic() if tp == 1 else None,
                          "peak_source": peak_src, "launch_us": gu_us_avg, "bytes_per_launch": gu_bytes,
                          "step": {"bytes": step_bytes, "achieved": step_bytes / (ms / args.steps) / 1e6,
                                   "frac": step_bytes / (ms / args.steps) / 1e6 / peak_gbs},
