@@ -83,6 +83,26 @@ def oracle_step(cfg, W, kcs, vcs, meta):
     return logits, logits.to(torch.float32).argmax(-1)
 
 
+def oracle_prefill(cfg, W, kcs, vcs, tokens, meta, chunked):
+    """reference composition of a prefill (chunked=False: ragged, no history) or chunked-prefill step on CPU.
+    meta: oracle.batch.PagedMeta of the step; caches are updated in place.  Returns last-token logits [B, vocab]."""
+    cs = O.compute_cos_sin_cache(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, BF16)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32)
+    am = OL.AttnMeta(True, chunked, i32(meta.q_cu_seq_lens), i32(meta.kv_cu_seq_lens), i32(meta.new_cache_slots),
+                     i32(meta.paged_kv_indptr), i32(meta.paged_kv_indices), i32(meta.paged_kv_last_page_len))
+    x, residual = W["embed"][torch.tensor(tokens)], None
+    positions = torch.tensor(meta.positions)
+    for li, L in enumerate(W["layers"]):
+        attn = OL.Qwen2AttentionOracle(None, None, None, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cs,
+                                       linear=_olin(L["qkv"]), o_linear=_olin(L["o"]))
+        dl = OL.Qwen2DecoderLayerOracle(attn, L["input_norm"], L["post_norm"], cfg.rms_norm_eps,
+                                        _olin(L["gate_up"]), _olin(L["down"]))
+        x, residual = dl.forward(x, residual, positions, am, kcs[li], vcs[li])
+    x, _ = O.fused_add_rms_norm(x, residual, W["final_norm"], cfg.rms_norm_eps)
+    last = torch.tensor(meta.q_cu_seq_lens[1:]) - 1
+    return O.linear(x[last], W["lm_head"])
+
+
 def upload(cfg, W, device="cuda"):
     from xllm_b200 import quant
     from xllm_b200.qwen2 import Linear, Qwen2Weights

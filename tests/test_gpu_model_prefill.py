@@ -1,0 +1,85 @@
+"""OPT-IN (XB_TEST_PREFILL_E2E=1): SURVEY 8(d) cfg1 - a prompt is prefilled (one shot and in chunks) through
+Qwen2PrefillRunner, then greedy-decoded through Qwen2DecodeRunner on the SAME paged KV cache, against the CPU oracle:
+same tokens, last-token logits within the whole-step tolerance of tests/test_gpu_model.py.
+
+Opt-in because it was written after the round's GPU budget was spent: the composition is CPU-checked
+(tests/test_prefill_composition_cpu.py) and every kernel has its own GPU parity test, but this file has not run on a
+GPU yet - the first enabled run validates the test as well.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import batch as OB
+from tests import model_parity as MP
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("XB_TEST_PREFILL_E2E") != "1", reason="opt-in: XB_TEST_PREFILL_E2E=1")]
+BF16 = torch.bfloat16
+DEV = "cuda"
+
+
+def _rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.mark.parametrize("quant", ["bf16", "w4a16"])
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_prefill_then_greedy_decode_matches_oracle(quant, chunks, built_lib):
+    from xllm_b200.qwen2 import Qwen2Config, Qwen2DecodeRunner
+    from xllm_b200.qwen2_prefill import Qwen2PrefillRunner
+    cfg = Qwen2Config.qwen2_0_5b(num_layers=2, vocab_size=4096, block_size=16, max_position_embeddings=512, quant=quant,
+                                 tie_word_embeddings=False)
+    W, _, _, _ = MP.build_case(cfg, 1, [1], seed=11)
+    g = torch.Generator().manual_seed(5)
+    prompt_len, n_decode = 128, 4
+    bs = cfg.block_size
+    total = prompt_len + n_decode
+    nblk = (total + bs - 1) // bs
+    nblocks = nblk + 4
+    blocks = (torch.randperm(nblocks - 1, generator=g) + 1)[:nblk].tolist()
+    prompt = torch.randint(0, cfg.vocab_size, (prompt_len,), generator=g).tolist()
+
+    # ---- oracle: one-shot prefill + greedy decode -----------------------------------------------------------------
+    mk = lambda: [torch.zeros(nblocks, bs, cfg.n_kv_heads, cfg.head_dim, dtype=BF16) for _ in range(cfg.num_layers)]
+    kc_o, vc_o = mk(), mk()
+    used = lambda n: blocks[: (n + bs - 1) // bs]
+    meta = OB.build_paged_meta([OB.SeqState(used(prompt_len), 0, prompt_len)], bs)
+    ref_logits = MP.oracle_prefill(cfg, W, kc_o, vc_o, prompt, meta, chunked=False)
+    ref_tokens = [int(ref_logits.float().argmax(-1))]
+    for i in range(n_decode - 1):
+        n = prompt_len + i + 1
+        m = OB.build_paged_meta([OB.SeqState(used(n), n - 1, n)], bs)
+        step = dict(tokens=[ref_tokens[-1]], positions=m.positions, slots=m.new_cache_slots, indptr=m.paged_kv_indptr,
+                    indices=m.paged_kv_indices, last=m.paged_kv_last_page_len, nblocks=nblocks)
+        _, nxt = MP.oracle_step(cfg, W, kc_o, vc_o, step)
+        ref_tokens.append(int(nxt[0]))
+
+    # ---- GPU: prefill (1 or 3 chunks) + decode on the same cache -------------------------------------------------
+    runner = Qwen2DecodeRunner(cfg, MP.upload(cfg, W), max_batch=1, max_ctx=nblk * bs, device=DEV, num_blocks=nblocks)
+    pre = Qwen2PrefillRunner.from_decode_runner(runner)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    bounds = [prompt_len * i // chunks for i in range(chunks + 1)]
+    logits = tokens = None
+    for ci in range(chunks):
+        a, b = bounds[ci], bounds[ci + 1]
+        m = OB.build_paged_meta([OB.SeqState(used(b), a, b)], bs)
+        logits, tokens = pre.forward(i32(prompt[a:b]), torch.tensor(m.positions, dtype=torch.int64, device=DEV),
+                                     i32(m.new_cache_slots), i32(m.q_cu_seq_lens), i32(m.kv_cu_seq_lens),
+                                     i32(m.paged_kv_indptr), i32(m.paged_kv_indices), i32(m.paged_kv_last_page_len),
+                                     chunked=(a > 0), max_qo_len=b - a)
+    torch.cuda.synchronize()
+    assert _rel_l2(logits, ref_logits) <= 2e-2, "prefill logits"
+    got = [int(tokens[0])]
+    top2 = ref_logits.float().topk(2, -1).values[0]
+    if float(top2[0] - top2[1]) > 0.05:                      # a near-tie may legitimately flip under bf16 rounding
+        assert got[0] == ref_tokens[0]
+    for i in range(n_decode - 1):
+        n = prompt_len + i + 1
+        m = OB.build_paged_meta([OB.SeqState(used(n), n - 1, n)], bs)
+        runner.set_inputs_host([ref_tokens[i]], m.positions, m.new_cache_slots, m.paged_kv_indptr, m.paged_kv_indices,
+                               m.paged_kv_last_page_len)       # teacher-forced on the oracle's token: isolates each step
+        got.append(int(runner.step()[0]))
+    assert got[1:] == ref_tokens[1:] or sum(x != y for x, y in zip(got, ref_tokens)) <= 1, (got, ref_tokens)
