@@ -250,17 +250,10 @@ def main():
     pg = None
     exchange = args.exchange
     if tp > 1:
-        from xllm_b200.parallel import ProcessGroup
-        if dp == 1:
-            pg = ProcessGroup()                       # the default group: the configuration tests/test_gpu_tp.py covers
-        else:
-            my_group = None
-            for gidx in range(dp):
-                ranks = list(range(gidx * tp, (gidx + 1) * tp))
-                grp = dist.new_group(ranks)
-                if rank in ranks:
-                    my_group = grp
-            pg = ProcessGroup(my_group)
+        from xllm_b200.parallel import make_tp_group
+        # dp == 1: the default group (the configuration tests/test_gpu_tp.py covers); dp > 1: one sub-group per replica
+        pg = make_tp_group(rank, world, tp)
+        if dp > 1:
             exchange = "nccl"                         # symmetric-memory rendezvous on sub-groups is not validated yet
     tp_rank = rank % tp
     weights = Qwen2Weights.synthetic(cfg, dev, seed=2026 + rank, tp_rank=tp_rank, tp=tp)

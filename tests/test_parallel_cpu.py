@@ -139,3 +139,37 @@ def test_tp2_layer_matches_single_rank_oracle():
     # (elements that cancel to ~0 are compared on the scale of the terms: atol = 1 ulp of an O(1) value)
     assert_close_bf16(torch.from_numpy(r_tp), r, ulps=2, rel_l2=2e-3, what="TP2 residual stream", atol=2.0 ** -7)
     assert_close_bf16(torch.from_numpy(y_tp), y, ulps=1e9, rel_l2=1e-2, what="TP2 layer output")   # MLP of a 1-ulp-perturbed input
+
+
+def _subgroup_worker(rank, world, tp, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pg = P.make_tp_group(rank, world, tp)
+    assert pg.world_size == tp and pg.rank == rank % tp
+    # reduce / gather stay inside the replica: ranks of the other replica hold different values
+    t = torch.full((3,), float(rank + 1))
+    P.reduce(t, pg)
+    g = P.gather(torch.full((1, 2), float(rank)), pg, dim=-1)
+    out_q.put((rank, t.tolist(), g.flatten().tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tp_x_dp_subgroups_world4():
+    """bench.py --gpus 8 runs two TP4 replicas; the same group construction at world 4 = 2 replicas x TP2 on gloo."""
+    world, tp = 4, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_subgroup_worker, args=(r, world, tp, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, red, gat in got:
+        base = (rank // tp) * tp
+        assert red == [float(sum(r + 1 for r in range(base, base + tp)))] * 3
+        assert gat == [float(base), float(base), float(base + 1), float(base + 1)]

@@ -129,6 +129,24 @@ class ProcessGroup:
         return out.view((self.world_size,) + tuple(t.shape))
 
 
+def make_tp_group(rank: int, world: int, tp: int) -> ProcessGroup:
+    """TP x DP layout of one node: `world // tp` replicas of `tp` consecutive ranks (ParallelArgs dp_size / tp groups,
+    framework/parallel_state/parallel_args.h).  dp == 1 uses the default group; otherwise EVERY rank creates every
+    sub-group in the same order (a c10d requirement) and keeps its own."""
+    if tp < 1 or world % tp != 0:
+        raise ValueError(f"world {world} is not a multiple of tp {tp}")
+    dp = world // tp
+    if dp == 1:
+        return ProcessGroup()
+    mine = None
+    for gidx in range(dp):
+        ranks = list(range(gidx * tp, (gidx + 1) * tp))
+        grp = dist.new_group(ranks)
+        if rank in ranks:
+            mine = grp
+    return ProcessGroup(mine)
+
+
 def reduce(t: torch.Tensor, pg: Optional[ProcessGroup]) -> torch.Tensor:
     """parallel_state::reduce (parallel_state.cpp:183-192): in-place sum all-reduce."""
     if pg is None or pg.world_size == 1:
