@@ -8,9 +8,15 @@ Synthetic data: random-init weights of the named architecture, KV cache N(0,1) w
 
   value   tokens/s with the step inputs resident in HBM (device events around K replays)
   e2e     tokens/s through Qwen2DecodeRunner.step(): pinned-host step inputs -> H2D -> graph -> D2H token ids
-  roofline  dominant kernel (W4A16 gate_up_proj GEMV, 28 launches/step): algorithmic bytes / launch duration
-            measured with CUDA events around each launch in an instrumented pass of the same step
-  cpu_baseline  the oracle's restatement of one decoder layer (+ lm_head) on the host cores, bounded sample
+  roofline  dominant kernel (W4A16 gate_up_proj GEMV with the fused SiLU*mul epilogue - the variant the graph runs -
+            28 launches/step): algorithmic bytes / launch duration, CUDA events around each launch in an instrumented
+            pass; plus the paged decode attention kernel the north-star names, and the whole-step bytes/time
+  cpu_baseline  the oracle's restatement of one decoder layer (+ lm_head) on the host cores, bounded sample,
+            median of >= 5 passes with the spread reported
+  comparators   same-box library kernels (NOT the reference arm): FlashInfer fa2 decode / prefill (what the reference
+            dlopen()s), F.linear bf16 (cuBLASLt, the reference's matmul), torch._scaled_mm fp8 (CUTLASS stand-in)
+  tp_parity (N > 1) tiny-config TP-vs-single-GPU logits / tokens / cross-rank bit-identity check, run BEFORE the timed
+            region; the run exits non-zero when it fails
 
 N > 1 (torchrun): tensor parallelism as the reference shards the path: column-parallel qkv / gate_up / lm_head,
 row-parallel o / down with one exchange after each, done by this library's NVLink one-shot all-reduce fused with the
@@ -23,6 +29,7 @@ offline: see DESIGN.md) and prints the same line with "impl": "reference".
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -46,9 +53,10 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def profiled_traffic(name="r01_w4_gemv_gateup.md"):
-    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full` summary of the
-    same kernel on the same shape (profiles/, written by tools/ncu_summary.py).  None when the summary is absent."""
+def profiled_traffic(name):
+    """DRAM bytes (read + write) per launch from a committed `ncu --set full` summary (profiles/, written by
+    tools/ncu_summary.py) of the SAME kernel variant and shape.  A cross-reference, not a live measurement: the key
+    `traffic_source` names the file so a stale summary is visible.  None when the summary is absent."""
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
         for ln in open(os.path.join(ROOT, "profiles", name)):
@@ -125,7 +133,9 @@ def host_threads():
 def cpu_layer_baseline(threads=None, budget_s=20.0):
     """The oracle port of one Qwen2-7B decoder layer (decode, batch 1, ctx 4096) + lm_head on the host cores.
     Weights are kept as fp32 copies of bf16-representable values so the timed region is the layer math, not dtype
-    conversion.  Returns (tokens/s extrapolated to 28 layers + lm_head, description)."""
+    conversion.  Every pass is timed on its own; the MEDIAN of >= 5 passes is reported with the min..max spread (a
+    shared box makes single passes noisy).  Returns (tokens/s extrapolated to 28 layers + lm_head, step seconds,
+    threads, sample description, spread dict)."""
     import torch
     from oracle import layer as OL
     from oracle import ops as O
@@ -157,42 +167,180 @@ def cpu_layer_baseline(threads=None, budget_s=20.0):
     res = torch.randn(1, H, generator=g).to(BF16)
     pos = torch.tensor([CTX - 1])
     dl.forward(x, res, pos, meta, kc, vc)                      # warm-up
-    t0, n = time.perf_counter(), 0
+    dl.forward(x, res, pos, meta, kc, vc)
+    t_start, layer_t = time.perf_counter(), []
     while True:
+        t0 = time.perf_counter()
         dl.forward(x, res, pos, meta, kc, vc)
-        n += 1
-        if time.perf_counter() - t0 > budget_s * 0.7 or n >= 50:
+        layer_t.append(time.perf_counter() - t0)
+        if len(layer_t) >= 5 and (time.perf_counter() - t_start > budget_s * 0.7 or len(layer_t) >= 60):
             break
-    t_layer = (time.perf_counter() - t0) / n
     head_rows = 19008                                          # 1/8 of the vocabulary rows, scaled up
     head = w(head_rows, H)
     O.linear(x, head)
-    t1, m = time.perf_counter(), 0
+    t_start, head_t = time.perf_counter(), []
     while True:
+        t0 = time.perf_counter()
         O.linear(x, head)
-        m += 1
-        if time.perf_counter() - t1 > budget_s * 0.2 or m >= 20:
+        head_t.append(time.perf_counter() - t0)
+        if len(head_t) >= 5 and (time.perf_counter() - t_start > budget_s * 0.2 or len(head_t) >= 30):
             break
-    t_head = (time.perf_counter() - t1) / m * (cfg.vocab_size / head_rows)
+    scale = cfg.vocab_size / head_rows
+    t_layer, t_head = statistics.median(layer_t), statistics.median(head_t) * scale
     step_s = cfg.num_layers * t_layer + t_head
-    sample = (f"{n} passes of one Qwen2-7B decoder layer (decode, batch 1, ctx {CTX}, dequantised fp32-held weights) "
-              f"+ {m} passes over 1/8 of lm_head, extrapolated to {cfg.num_layers} layers + full lm_head")
-    return 1.0 / step_s, step_s, threads, sample
+    step_fast = cfg.num_layers * min(layer_t) + min(head_t) * scale
+    step_slow = cfg.num_layers * max(layer_t) + max(head_t) * scale
+    sample = (f"median of {len(layer_t)} passes of one Qwen2-7B decoder layer (decode, batch 1, ctx {CTX}, dequantised "
+              f"fp32-held weights) + median of {len(head_t)} passes over 1/8 of lm_head, extrapolated to {cfg.num_layers} "
+              f"layers + full lm_head")
+    spread = {"tokens_per_s_min": 1.0 / step_slow, "tokens_per_s_max": 1.0 / step_fast, "layer_passes": len(layer_t),
+              "layer_ms_median": t_layer * 1e3, "layer_ms_min": min(layer_t) * 1e3, "layer_ms_max": max(layer_t) * 1e3}
+    return 1.0 / step_s, step_s, threads, sample, spread
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    tps, step_s, threads, sample = cpu_layer_baseline(budget_s=min(60.0, 6.0 * max(1, args.steps)))
+    tps, step_s, threads, sample, spread = cpu_layer_baseline(budget_s=min(60.0, 6.0 * max(1, args.steps)))
     line = {"metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD, "ctx": CTX, "batch": 1},
-            "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "spread": spread},
             "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "reference has no CPU build (xllm/models/models.h:119-121 #error) and cannot be installed offline; "
                     "this arm times the oracle port of the same decoder layer on the host cores"}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def _events_per_launch(torch, fns, reps=3):
+    """CUDA events around EACH launch (first repetition dropped).  A few ms of queued GPU work first, so every launch +
+    event is already enqueued when the GPU reaches it: the pairs bracket device time, not Python launch latency."""
+    ev = []
+    torch.cuda._sleep(int(20e6))
+    for rep in range(reps):
+        for fn in fns:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            if rep > 0:
+                ev.append((a, b))
+    torch.cuda.synchronize()
+    us = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
+    return sum(us) / len(us), us[len(us) // 2]
+
+
+def _events_chained(torch, fns, reps=5):
+    """mean duration of a launch inside a back-to-back stream of launches (one per layer: different weights / caches,
+    together larger than L2), events around the whole batch.  Consecutive launches are PDL-chained exactly as inside
+    the decode step, so a kernel's launch latency and prologue overlap its predecessor's tail."""
+    for fn in fns:
+        fn()
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(20e6))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        for fn in fns:
+            fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / (reps * len(fns))
+
+
+def _time_fn(torch, fn, it=5):
+    fn(); fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(it):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / it * 1e-3
+
+
+def gpu_comparators(torch, ops, cfg, runner, weights, dev, ctx):
+    """Same-box LIBRARY kernels next to ours (extra keys; not the reference arm, never on the product path):
+    FlashInfer fa2 (the module the reference dlopen()s: kernels/cuda/utils.cpp:371-450), F.linear bf16 = cuBLASLt (the
+    reference's matmul, matmul.cpp:20-24), torch._scaled_mm fp8 (stand-in for cutlass_scaled_mm).  us per call."""
+    out = []
+
+    def add(name, ours_us, theirs_us, note=None):
+        d = {"name": name, "ours_us": round(ours_us, 2), "theirs_us": round(theirs_us, 2),
+             "speedup_vs_library": round(theirs_us / ours_us, 3)}
+        if note:
+            d["note"] = note
+        out.append(d)
+    D, HQ, HKV = cfg.head_dim, cfg.n_heads, cfg.n_kv_heads
+    BF16 = torch.bfloat16
+    sc = D ** -0.5
+    # ---- attention: FlashInfer fa2 -------------------------------------------------------------------------------
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import build_flashinfer_cache as FIC
+        FIC.set_env()
+        import flashinfer
+        from flashinfer.jit import core as jc
+        if not all(s.jit_library_path.exists() for s in FIC.specs((D,))):
+            raise RuntimeError("FlashInfer modules not pre-built (tools/build_flashinfer_cache.py)")
+        orig = jc.JitSpec.build
+        jc.JitSpec.build = lambda self, verbose, need_lock=True: None if self.jit_library_path.exists() else orig(self, verbose, need_lock)
+        ws = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        q3 = runner.qkv[:, :runner.q_size].view(-1, HQ, D)
+        o3 = runner.attn_out.view(-1, HQ, D)
+        L = cfg.num_layers
+        ours = [lambda li=li: ops.batch_decode(runner.plan, q3, runner.k_caches[li], runner.v_caches[li], runner.kv_indptr,
+                                               runner.kv_indices, runner.kv_last, sc, o3) for li in range(L)]
+        t_ours = _events_chained(torch, ours)
+        npg = (ctx + cfg.block_size - 1) // cfg.block_size
+        for tc in (True, False):
+            w = flashinfer.BatchDecodeWithPagedKVCacheWrapper(ws, "NHD", use_tensor_cores=tc)
+            w.plan(runner.kv_indptr[:2], runner.kv_indices[:npg], runner.kv_last[:1], HQ, HKV, D, cfg.block_size,
+                   pos_encoding_mode="NONE", q_data_type=BF16, kv_data_type=BF16, sm_scale=sc)
+            theirs = [lambda li=li: w.run(q3, (runner.k_caches[li], runner.v_caches[li]), out=o3) for li in range(L)]
+            add(f"paged decode attention B=1 ctx={ctx} {HQ}/{HKV}x{D} vs FlashInfer fa2 (use_tensor_cores={tc}"
+                f"{', the path the reference takes for GQA>=4' if tc else ''})", t_ours, _events_chained(torch, theirs),
+                "mean of 28 back-to-back launches over 28 layers' caches (235 MB > L2); FlashInfer time includes its "
+                "Python wrapper dispatch")
+        Mp, Sp = 8192, 2048
+        qkv_p = torch.randn(Mp, cfg.q_size + 2 * cfg.kv_size, device=dev, dtype=BF16)
+        cu = torch.arange(0, Mp + 1, Sp, dtype=torch.int32, device=dev)
+        o_p = torch.empty(Mp, HQ, D, device=dev, dtype=BF16)
+        qp = qkv_p[:, :cfg.q_size].view(Mp, HQ, D)
+        kp = qkv_p[:, cfg.q_size:cfg.q_size + cfg.kv_size].view(Mp, HKV, D)
+        vp = qkv_p[:, cfg.q_size + cfg.kv_size:].view(Mp, HKV, D)
+        wp = flashinfer.BatchPrefillWithRaggedKVCacheWrapper(ws, "NHD", backend="fa2")
+        wp.plan(cu, cu, HQ, HKV, D, causal=True, pos_encoding_mode="NONE", sm_scale=sc, q_data_type=BF16, kv_data_type=BF16)
+        t_o = _time_fn(torch, lambda: ops.batch_prefill(qp, kp, vp, cu, cu, sc, o_p, None, max_qo_len=Sp)) * 1e6
+        t_t = _time_fn(torch, lambda: wp.run(qp, kp, vp, out=o_p)) * 1e6
+        add(f"ragged causal prefill attention 4x{Sp} {HQ}/{HKV}x{D} vs FlashInfer fa2", t_o, t_t)
+    except Exception as e:
+        out.append({"name": "FlashInfer fa2 attention", "error": str(e)[:200]})
+    # ---- linears: cuBLASLt bf16 and torch._scaled_mm fp8 at the four projection shapes, M = 8192 ----------------------
+    try:
+        import torch.nn.functional as F
+        M = 8192
+        shapes = {"qkv": (cfg.q_size + 2 * cfg.kv_size, cfg.hidden_size), "o": (cfg.hidden_size, cfg.q_size),
+                  "gate_up": (2 * cfg.intermediate_size, cfg.hidden_size), "down": (cfg.hidden_size, cfg.intermediate_size)}
+        for name, (N, K) in shapes.items():
+            a = torch.randn(M, K, device=dev, dtype=BF16)
+            wt = torch.randn(N, K, device=dev, dtype=BF16) * 0.02
+            y = torch.empty(M, N, device=dev, dtype=BF16)
+            t_o = _time_fn(torch, lambda: ops.gemm_bf16(a, wt, None, y)) * 1e6
+            t_t = _time_fn(torch, lambda: F.linear(a, wt)) * 1e6
+            add(f"bf16 linear {name} {M}x{N}x{K} vs F.linear (cuBLASLt, the reference's matmul)", t_o, t_t)
+            a8, w8 = a.to(torch.float8_e4m3fn), wt.clamp(-1, 1).to(torch.float8_e4m3fn)
+            one = torch.ones(1, device=dev, dtype=torch.float32)
+            t_o = _time_fn(torch, lambda: ops.cutlass_scaled_mm(y, a8, w8.t(), one, one, None)) * 1e6
+            t_t = _time_fn(torch, lambda: torch._scaled_mm(a8, w8.t(), scale_a=one, scale_b=one, out_dtype=BF16)) * 1e6
+            add(f"fp8 scaled mm {name} {M}x{N}x{K} vs torch._scaled_mm (stand-in for cutlass_scaled_mm)", t_o, t_t)
+            del a, wt, y, a8, w8
+    except Exception as e:
+        out.append({"name": "library GEMMs", "error": str(e)[:200]})
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -203,8 +351,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-comparators", action="store_true")
     ap.add_argument("--ctx", type=int, default=CTX)
     ap.add_argument("--parallelism", default="tp", choices=["tp", "dp"])
+    ap.add_argument("--tp", type=int, default=0, help="tensor-parallel degree (default: min(N, 4) for Qwen2-7B's 28 heads)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -228,6 +378,7 @@ def main():
         if os.environ.get("XB_BENCH_VERBOSE"):
             sys.stderr.write(f"[bench rank {rank}] {msg}\n")
             sys.stderr.flush()
+    from xllm_b200 import ops
     from xllm_b200.qwen2 import Qwen2Config, Qwen2DecodeRunner, Qwen2Weights
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
     torch.cuda.set_device(local_rank)
@@ -245,18 +396,30 @@ def main():
     ctx = args.ctx
     tp = 1
     if world > 1 and args.parallelism == "tp":
-        tp = 4 if world % 4 == 0 else (2 if world % 2 == 0 else 1)
+        tp = args.tp if args.tp > 0 else (4 if world % 4 == 0 else (2 if world % 2 == 0 else 1))
+        assert world % tp == 0 and cfg.n_heads % tp == 0, f"tp {tp} must divide world {world} and {cfg.n_heads} q heads"
     dp = world // tp
     pg = None
     exchange = args.exchange
+    tp_parity = None
     if tp > 1:
         from xllm_b200.parallel import make_tp_group
-        # dp == 1: the default group (the configuration tests/test_gpu_tp.py covers); dp > 1: one sub-group per replica
+        from xllm_b200.tp_check import tp_parity as run_tp_parity
+        # dp == 1: the default group; dp > 1: one sub-group per replica (symmetric-memory rendezvous on the sub-group)
         pg = make_tp_group(rank, world, tp)
-        if dp > 1:
-            exchange = "nccl"                         # symmetric-memory rendezvous on sub-groups is not validated yet
+        # TP correctness first (tiny config, same exchange + CUDA graph as the timed run): TP logits vs single GPU
+        tp_parity = run_tp_parity(pg, dev, exchange)
+        log(f"tp parity {tp_parity}")
+        ok = tp_parity["rel_l2"] <= 2e-2 and tp_parity["tokens_equal"] and tp_parity["ranks_bit_identical"]
+        if not ok:
+            if rank == 0:
+                print(json.dumps({"error": "tp_parity failed", "tp_parity": tp_parity}), flush=True)
+            sys.stdout.flush()
+            os._exit(3)
     tp_rank = rank % tp
-    weights = Qwen2Weights.synthetic(cfg, dev, seed=2026 + rank, tp_rank=tp_rank, tp=tp)
+    dp_index = rank // tp
+    # replicated tensors (embedding, norms) share the seed within a TP group; shards are seeded per rank
+    weights = Qwen2Weights.synthetic(cfg, dev, seed=2026 + dp_index, tp_rank=tp_rank, tp=tp)
     runner = Qwen2DecodeRunner(cfg, weights, max_batch=1, max_ctx=ctx, device=dev, pg=pg, exchange=exchange)
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     for li in range(cfg.num_layers):
@@ -274,7 +437,6 @@ def main():
     log("eager step done")
     runner.capture()
     log("graph captured")
-    launches_per_step = None
 
     def barrier():
         if world > 1:
@@ -287,7 +449,6 @@ def main():
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -298,7 +459,6 @@ def main():
     ms = e0.elapsed_time(e1)
     log(f"timed region done: {ms:.1f} ms")
     clocks = sampler.stop()
-    graph_launches = 0
     # a graph replay does not pass through the library's launch counter: count the kernels in one step eagerly
     n0 = _lib.launch_count()
     runner.launch_step()
@@ -317,46 +477,36 @@ def main():
     e2e_s = time.perf_counter() - t0
     log("e2e region done")
 
-    # ---- dominant kernel: W4A16 gate_up GEMV, CUDA events around each launch -----------------------------------
-    gu_events = []
+    # ---- dominant kernel: W4A16 gate_up GEMV + SiLU*mul epilogue (the variant the graph runs) ----------------------
     L = weights.layers
-    # queue a few ms of GPU work first so that every launch + event below is already enqueued when the GPU reaches it:
-    # the event pairs then bracket device time only, not the Python launch latency
-    torch.cuda._sleep(int(20e6))
-    for rep in range(3):
-        for li in range(cfg.num_layers):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            L[li]["gate_up"].forward(runner.buf_a, runner.gate_up)
-            b.record()
-            if rep > 0:
-                gu_events.append((a, b))
-    torch.cuda.synchronize()
-    gu_us = sorted(a.elapsed_time(b) * 1e3 for a, b in gu_events)
-    gu_us_avg = sum(gu_us) / len(gu_us)
+
+    def gate_up_fn(li):
+        gu = L[li]["gate_up"]
+        if gu.kind == "w4a16" and gu.gate_up_interleaved:
+            return lambda: ops.w4a16_gate_up_act(runner.buf_a, gu.qweight, gu.meta, gu.group_size, "silu", gu.bias, runner.act,
+                                                 runner.gate_up)
+        return lambda: gu.forward(runner.buf_a, runner.gate_up)
+    gu_fns = [gate_up_fn(li) for li in range(cfg.num_layers)]
+    gu_us_avg, gu_us_med = _events_per_launch(torch, gu_fns)
+    gu_us_chained = _events_chained(torch, gu_fns)
     gu = L[0]["gate_up"]
-    gu_bytes = gu.qweight.numel() * 4 + gu.meta.numel() * 4 + gu.K * 2 + gu.N * 2      # this rank's shard
-    # attention kernel the same way (the north-star names it)
-    at_events = []
+    fused_act = gu.kind == "w4a16" and gu.gate_up_interleaved
+    n_out = gu.N // 2 if fused_act else gu.N
+    gu_bytes = gu.qweight.numel() * 4 + gu.meta.numel() * 4 + gu.K * 2 + n_out * 2      # this rank's shard
+    # ---- the decode attention kernel the north-star names ----------------------------------------------------------
     q3 = runner.qkv[:, :runner.q_size].view(-1, runner.nh, cfg.head_dim)
-    from xllm_b200 import ops
-    torch.cuda._sleep(int(20e6))
-    for rep in range(3):
-        for li in range(cfg.num_layers):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            ops.batch_decode(runner.plan, q3, runner.k_caches[li], runner.v_caches[li], runner.kv_indptr, runner.kv_indices,
-                             runner.kv_last, cfg.head_dim ** -0.5, runner.attn_out.view(-1, runner.nh, cfg.head_dim))
-            b.record()
-            if rep > 0:
-                at_events.append((a, b))
-    torch.cuda.synchronize()
-    at_us_avg = sum(a.elapsed_time(b) * 1e3 for a, b in at_events) / len(at_events)
+    o3 = runner.attn_out.view(-1, runner.nh, cfg.head_dim)
+    at_fns = [lambda li=li: ops.batch_decode(runner.plan, q3, runner.k_caches[li], runner.v_caches[li], runner.kv_indptr,
+                                             runner.kv_indices, runner.kv_last, cfg.head_dim ** -0.5, o3)
+              for li in range(cfg.num_layers)]
+    at_us_iso, _ = _events_per_launch(torch, at_fns)
+    at_us_chained = _events_chained(torch, at_fns)
     at_bytes = 2 * ctx * runner.nkv * cfg.head_dim * 2 + 2 * runner.nh * cfg.head_dim * 2 + 4 * npg
 
     # ---- prefill half of the metric (BASELINE.json: "... + prefill TFLOPS"): one decoder layer of the chunked-prefill
     # shape of configs[2] (4 prompts x 2048 tokens per chunk): the four W4A16 tcgen05 GEMMs + causal prefill attention ----
     prefill = None
+    comparators = None
     if rank == 0 and tp == 1:
         try:
             Mp, Sp = 8192, 2048
@@ -378,18 +528,7 @@ def main():
                                   qkv_p[:, cfg.q_size:cfg.q_size + cfg.kv_size].view(Mp, cfg.n_kv_heads, cfg.head_dim),
                                   qkv_p[:, cfg.q_size + cfg.kv_size:].view(Mp, cfg.n_kv_heads, cfg.head_dim), cu, cu,
                                   cfg.head_dim ** -0.5, o_p, None, max_qo_len=Sp)
-
-            def t(fn, it=5):
-                fn(); fn()
-                torch.cuda.synchronize()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(it):
-                    fn()
-                b.record()
-                torch.cuda.synchronize()
-                return a.elapsed_time(b) / it * 1e-3
-            tg, ta = t(gemms), t(attn)
+            tg, ta = _time_fn(torch, gemms), _time_fn(torch, attn)
             gflop = 2.0 * Mp * sum(l0[k].N * l0[k].K for k in ("qkv", "o", "gate_up", "down"))
             aflop = 4.0 * cfg.n_heads * cfg.head_dim * Sp * Sp / 2 * (Mp // Sp)
             try:
@@ -400,8 +539,14 @@ def main():
                        "linear_tflops": gflop / tg / 1e12, "linear_frac_of_bf16_sustained": gflop / tg / 1e12 / tf_peak,
                        "attention_tflops_causal": aflop / ta / 1e12, "layer_tflops": (gflop + aflop) / (tg + ta) / 1e12,
                        "prefill_tokens_per_s_extrapolated": Mp / ((tg + ta) * cfg.num_layers), "bf16_peak_tflops": tf_peak}
+            del xin, bufs, xi, qkv_p, o_p
         except Exception as e:      # the decode line must still be printed
             prefill = {"error": str(e)[:200]}
+        if not args.no_comparators:
+            try:
+                comparators = gpu_comparators(torch, ops, cfg, runner, weights, dev, ctx)
+            except Exception as e:
+                comparators = [{"error": str(e)[:200]}]
 
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
     t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
@@ -415,35 +560,56 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            tps, step_s, threads, sample = cpu_layer_baseline(budget_s=15.0)
-            cpu = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+            tps, step_s, threads, sample, spread = cpu_layer_baseline(budget_s=15.0)
+            cpu = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "spread": spread}
         ach = gu_bytes / gu_us_avg / 1e3
+        traffic_file = "r02_w4_gemv_gateup_fused.md"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if tp == 1 else "strong",
+            "ms_per_step": ms / args.steps, "higher_is_better": True,
+            # tensor parallelism splits ONE request's step over the GPUs of a group (strong scaling, the reference's TP);
+            # N = 8 runs two TP4 groups (28 q heads do not divide by 8), each decoding its own request
+            "scaling": "strong" if args.parallelism == "tp" else "weak",
             "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "ctx": ctx, "batch": 1,
                        "parallelism": (f"tp{tp}" if dp == 1 else f"tp{tp}xdp{dp}") if tp > 1 else f"dp{world}",
                        "exchange": (runner.exchange_mode if tp > 1 else None),
                        "l2": "inputs larger than L2: each step streams %.2f GB of weights+KV" % (step_bytes / 1e9),
-                       "decode_chunk_tokens": runner.plan.chunk_tokens, "decode_splits": runner.plan.max_splits},
+                       "decode_chunk_tokens": runner.plan.chunk_tokens, "decode_splits": runner.plan.max_splits,
+                       "decode_cluster": runner.plan.cluster, "launches_per_step": launches_per_step},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
                     "d2h_bytes_per_step": runner.d2h_bytes},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": f"linear_w4a16_small_m_kernel (gate_up_proj {gu.N}x{gu.K}, 28 launches/step)",
+            "roofline": {"bound": "hbm",
+                         "kernel": f"linear_w4a16_small_m_kernel{' + SiLU*mul epilogue' if fused_act else ''} "
+                                   f"(gate_up_proj {gu.N}x{gu.K}, 28 launches/step)",
                          "per_rank": True, "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                         # ncu dram__bytes_read+write of the same kernel and shape (single GPU, unsharded shape only)
-                         "traffic": profiled_traffic() if tp == 1 else None,
-                         "peak_source": peak_src, "launch_us": gu_us_avg, "bytes_per_launch": gu_bytes,
+                         # ncu dram__bytes_read+write of the same kernel variant and shape (single GPU, unsharded shape)
+                         "traffic": profiled_traffic(traffic_file) if tp == 1 else None,
+                         "traffic_source": f"profiles/{traffic_file} (committed ncu --set full summary; cross-reference)",
+                         "peak_source": peak_src, "launch_us": gu_us_avg, "launch_us_median": gu_us_med,
+                         "launch_us_chained": gu_us_chained, "bytes_per_launch": gu_bytes,
+                         "method": "CUDA events around each of 2 x 28 launches (one per layer's weights: 1.9 GB > L2)",
                          "step": {"bytes": step_bytes, "achieved": step_bytes / (ms / args.steps) / 1e6,
                                   "frac": step_bytes / (ms / args.steps) / 1e6 / peak_gbs},
-                         "paged_decode": {"bytes_per_launch": at_bytes, "launch_us": at_us_avg,
-                                          "achieved": at_bytes / at_us_avg / 1e3, "frac": at_bytes / at_us_avg / 1e3 / peak_gbs}},
+                         "paged_decode": {"bytes_per_launch": at_bytes, "launch_us": at_us_chained,
+                                          "launch_us_isolated": at_us_iso,
+                                          "achieved": at_bytes / at_us_chained / 1e3,
+                                          "frac": at_bytes / at_us_chained / 1e3 / peak_gbs,
+                                          "frac_isolated": at_bytes / at_us_iso / 1e3 / peak_gbs,
+                                          "method": "launch_us = mean over 5 x 28 back-to-back launches (one per layer's "
+                                                    "KV cache, 235 MB > L2), PDL-chained as inside the decode step, one "
+                                                    "event pair around the batch; launch_us_isolated = event pair "
+                                                    "around every single launch"}},
             "cpu_baseline": cpu,
             "prefill": prefill,
         }
+        if tp_parity is not None:
+            line["tp_parity"] = tp_parity
+        if comparators is not None:
+            line["comparators"] = comparators
         print(json.dumps(line), flush=True)
     if world > 1:
         # destroy_process_group() blocks here (captured NCCL / symmetric-memory graphs still hold communicator

@@ -153,11 +153,16 @@ int xb_act_and_mul_bf16(void* out, const void* input, int d, int num_tokens,
  *
  * xb_decode_plan is host-only arithmetic (no device access, no sync): given an
  * upper bound of pages per request it picks how many KV splits to launch so
- * that batch*num_kv_heads*splits covers the SMs, and returns workspace needs.
+ * that batch*num_kv_heads*splits covers the SMs (and how many of them form one
+ * thread-block cluster), and returns workspace needs.  The split SIZE is not
+ * part of the plan: the kernel derives it from the live kv_len and the launched
+ * grid, so a plan made at CUDA-graph capture stays correct for any later
+ * context length (the reference replays a captured `run`:
+ * layers/cuda/flashinfer_attention.cpp:306-311).
  * The plan is opaque int64[8] (plan_info is opaque to xLLM too:
  * flashinfer_planinfo.cpp:37-62).  workspace_f32 needs plan[2] bytes,
- * workspace_i32 needs plan[3] bytes and MUST be zero-initialised once (the
- * kernel restores it to zero). */
+ * workspace_i32 needs plan[3] & 0xffffffff bytes and MUST be zero-initialised
+ * once (the kernel restores it to zero). */
 int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int num_kv_heads,
                    int head_dim, int page_size, int max_pages_per_request,
                    int num_sms);
@@ -165,6 +170,12 @@ int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int num_kv_heads
  * newest token of each request, nor the paged triplet (true inside a decode step); the kernel then streams KV before
  * its programmatic-dependent-launch wait, overlapping the producer kernel's tail. */
 int xb_decode_plan_set_flags(int64_t* plan8, int flags);
+/* debug aid: the next xb_paged_decode_bf16 launches write per-CTA stage timestamps (%globaltimer, ns) to
+ * buf = uint64[grid CTAs][8] (device memory); null switches it off. */
+int xb_debug_set_decode_trace(void* buf);
+/* debug aid: number of thread-block clusters of `cluster` CTAs of the paged decode kernel the current device can run
+ * concurrently (cudaOccupancyMaxActiveClusters), -1 if that cluster size cannot be launched. */
+int xb_debug_max_active_clusters(int cluster);
 int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t q_stride_n,
                          int64_t q_stride_h, const void* k_cache,
                          const void* v_cache, int64_t kv_stride_page,

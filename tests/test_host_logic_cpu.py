@@ -23,29 +23,33 @@ def _plan(lib, batch, hq, hkv, d, page, max_pages, sms=148):
 def test_decode_plan_invariants(batch, hq, hkv, d, page, max_pages, built_lib, monkeypatch):
     monkeypatch.delenv("XB_DECODE_CHUNK", raising=False)
     monkeypatch.delenv("XB_DECODE_WARPS", raising=False)
+    monkeypatch.delenv("XB_DECODE_CLUSTER", raising=False)
     lib = _lib.lib()
     rc, p = _plan(lib, batch, hq, hkv, d, page, max_pages)
     assert rc == 0, lib.xb_last_error()
     chunk, splits = p[0], p[1]
+    cluster = (p[7] >> 44) & 0x1F
     max_kv = page * max_pages
-    assert chunk % 16 == 0 and chunk >= 16, "chunks are whole 16-token blocks"
+    assert chunk % 16 == 0 and chunk >= 64, "nominal chunks are whole 16-token blocks of at least 64 tokens"
     assert splits >= 1 and chunk * splits >= max_kv, "the chunks cover the longest admissible request"
-    assert chunk * (splits - 1) < max_kv, "no empty trailing split"
+    assert splits == 1 or 64 * (splits - 1) < max_kv, "never more splits than 64-token chunks in the longest request"
     assert splits <= 2 * d, "split merge scratch is sized for 2*head_dim splits"
-    # workspaces: partial O + LSE per (request, q head, split); one ticket word per (request, kv head, head tile)
+    assert 1 <= cluster <= 16 and splits % cluster == 0, "splits = clusters x cluster size, at most 16 CTAs per cluster"
+    # workspaces: partial O + LSE per (request, q head, split) - sized for the cluster-less fallback; one ticket word
+    # per (request, kv head, head tile)
     if splits > 1:
         assert p[2] >= batch * hq * splits * (d + 1) * 4
     group = hq // hkv
     head_tiles = (group + 15) // 16
     assert (p[3] & 0xFFFFFFFF) >= batch * hkv * head_tiles * 4
     assert (p[4], p[5], p[6]) == (batch, hq, hkv)
-    assert p[7] & 0xFFFF == d and (p[7] >> 16) & 0xFFFFFF == page and (p[7] >> 40) in (4, 8)
+    assert p[7] & 0xFFFF == d and (p[7] >> 16) & 0xFFFFFF == page and (p[7] >> 40) & 0xF in (4, 8)
     # one wave: with few (request, kv head) units the planner splits the KV range to fill the SMs, never beyond them
     units = batch * hkv * head_tiles
     if units >= 148:
-        assert splits == 1 or chunk * (splits - 1) < max_kv
+        assert splits == 1
     else:
-        assert units * splits <= max(148, units) + units, f"{units} units x {splits} splits overshoots one wave"
+        assert units * splits <= 148, f"{units} units x {splits} splits overshoots one wave"
 
 
 def test_decode_plan_flags_and_env(built_lib, monkeypatch):
@@ -56,12 +60,19 @@ def test_decode_plan_flags_and_env(built_lib, monkeypatch):
     low = p[3] & 0xFFFFFFFF
     assert lib.xb_decode_plan_set_flags(p, 0) == 0 and (p[3] >> 32) & 1 == 0 and p[3] & 0xFFFFFFFF == low
     assert lib.xb_decode_plan_set_flags(None, 1) != 0
-    monkeypatch.setenv("XB_DECODE_CHUNK", "200")          # rounded down to whole blocks
+    monkeypatch.setenv("XB_DECODE_CHUNK", "200")          # rounded down to whole blocks -> 192 -> 22 splits of <= 192
     rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)
-    assert rc == 0 and p[0] == 192
+    assert rc == 0 and p[1] == 2 * 11 and p[0] == 192 and (p[7] >> 44) & 0x1F == 11
+    monkeypatch.setenv("XB_DECODE_CLUSTER", "1")          # no clusters: every split is a workspace partial
+    rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)
+    assert rc == 0 and p[1] == 22 and (p[7] >> 44) & 0x1F == 1
+    monkeypatch.delenv("XB_DECODE_CLUSTER")
+    monkeypatch.delenv("XB_DECODE_CHUNK")
+    rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)            # BASELINE configs[1]: 37 wanted -> 3 clusters of 12
+    assert rc == 0 and p[1] == 36 and (p[7] >> 44) & 0x1F == 12
     monkeypatch.setenv("XB_DECODE_WARPS", "4")
     rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)
-    assert rc == 0 and p[7] >> 40 == 4
+    assert rc == 0 and (p[7] >> 40) & 0xF == 4
 
 
 @pytest.mark.parametrize("args", [(0, 28, 4, 128, 128, 32), (1, 28, 3, 128, 128, 32), (1, 28, 4, 256, 128, 32),

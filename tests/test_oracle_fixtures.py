@@ -66,7 +66,6 @@ def test_attention_fixtures(fx):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("XB_TEST_FIXTURES_GPU") != "1", reason="opt-in: XB_TEST_FIXTURES_GPU=1 (not yet run on a GPU)")
 def test_kernels_against_frozen_outputs(fx, built_lib):
     """the CUDA kernels against the FROZEN outputs (not against a fresh oracle evaluation)."""
     from xllm_b200 import ops

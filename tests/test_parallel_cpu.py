@@ -95,9 +95,9 @@ def _worker(rank, world, port, out_q):
     hp = P.partition_heads(NH, NKV, rank, world)
     shard = dict(
         qkv=P.shard_linear("w4", L["qkv"], P.shard_qkv_rows(NH, NKV, D, rank, world), None, GS),
-        o=P.shard_linear("w4", L["o"], None, P.shard_cols(NH * D, rank, world), GS),
+        o=P.shard_linear("w4", L["o"], None, P.shard_cols(NH * D, rank, world), GS, rank),
         gate_up=P.shard_linear("w4", L["gate_up"], P.shard_gate_up_rows(I, rank, world), None, GS),
-        down=P.shard_linear("w4", L["down"], None, P.shard_cols(I, rank, world), GS),
+        down=P.shard_linear("w4", L["down"], None, P.shard_cols(I, rank, world), GS, rank),
         in_norm=L["in_norm"], post_norm=L["post_norm"])
     # the sharded int4 tensors dequantise to exactly the matching slice of the full dequantised weight
     for name in ("qkv", "o", "gate_up", "down"):
@@ -173,3 +173,23 @@ def test_tp_x_dp_subgroups_world4():
         base = (rank // tp) * tp
         assert red == [float(sum(r + 1 for r in range(base, base + tp)))] * 3
         assert gat == [float(base), float(base), float(base + 1), float(base + 1)]
+
+
+def test_row_parallel_bias_only_on_rank0():
+    """linear.cpp:1508-1511: the bias of a row-parallel linear is added once, i.e. carried by rank 0 only, so the
+    all-reduced sum of the per-rank outputs equals the unsharded linear."""
+    g = torch.Generator().manual_seed(3)
+    w = (torch.randn(32, 128, generator=g) * 0.05).to(BF16)
+    b = (torch.randn(32, generator=g) * 0.5).to(BF16)
+    x = torch.randn(4, 128, generator=g).to(BF16)
+    tp = 4
+    total = torch.zeros(4, 32)
+    for rank in range(tp):
+        sh = P.shard_linear("bf16", dict(w=w, b=b), None, P.shard_cols(128, rank, tp), 64, rank)
+        assert (sh["b"] is not None) == (rank == 0)
+        total += O.linear(x[:, P.shard_cols(128, rank, tp)], sh["w"], sh["b"]).float()
+    ref = O.linear(x, w, b).float()
+    assert (total - ref).abs().max() < 0.05 and (total - ref - b.float()).abs().max() > 0.1
+    # column-parallel shards keep their own rows of the bias on every rank
+    rows = torch.arange(8, 16)
+    assert torch.equal(P.shard_linear("bf16", dict(w=w, b=b), rows, None, 64, 3)["b"], b[rows])

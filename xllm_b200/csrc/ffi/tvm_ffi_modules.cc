@@ -19,6 +19,7 @@
 #include <tvm/ffi/optional.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdint>
 #include <cstring>
 
@@ -40,6 +41,36 @@ inline void check_rc(int rc, const char* what) {
 inline bool is_bf16(const TensorView& t) { return t.dtype().code == kDLBfloat && t.dtype().bits == 16; }
 
 // ---------------------------------------------------------------------------------------------------------------
+// decode planning shared by the decode module's `plan` and the prefill module's `plan` (the reference serves decode
+// through the PREFILL module's paged_run when should_use_tensor_core() holds - GQA group >= 4, i.e. Qwen2-7B and
+// Llama-3: kernels/cuda/utils.cpp:349-367, batch_decode.cpp:43-60)
+// ---------------------------------------------------------------------------------------------------------------
+void make_decode_plan(int64_t* plan, const TensorView& float_ws, const TensorView& int_ws, const int32_t* indptr_host,
+                      int64_t batch_size, int64_t num_qo_heads, int64_t num_kv_heads, int64_t page_size, int64_t head_dim,
+                      bool enable_cuda_graph) {
+  int64_t max_pages = 1;
+  for (int64_t b = 0; b < batch_size; ++b) max_pages = std::max<int64_t>(max_pages, indptr_host[b + 1] - indptr_host[b]);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (enable_cuda_graph) {
+    // The plan made at capture is replayed for later, longer steps (flashinfer_attention.cpp:306-311 skips `plan` under
+    // replay; cuda_graph_executor_impl.cpp:751-822).  The kernel derives the split size from the live kv_len on the
+    // device, so only the split COUNT is fixed here: size it for the SM count alone, as if the context were long.
+    max_pages = std::max<int64_t>(max_pages, (int64_t)64 * sms / page_size + 1);
+  }
+  check_rc(xb_decode_plan(plan, (int)batch_size, (int)num_qo_heads, (int)num_kv_heads, (int)head_dim, (int)page_size,
+                          (int)max_pages, sms), "decode plan");
+  const int64_t need_f = plan[2], need_i = plan[3] & 0xffffffffll;
+  if (need_f > float_ws.numel() * (float_ws.dtype().bits / 8))
+    TVM_FFI_THROW(RuntimeError) << "float workspace too small: need " << need_f << " bytes";
+  if (need_i > int_ws.numel() * (int_ws.dtype().bits / 8))
+    TVM_FFI_THROW(RuntimeError) << "int workspace too small: need " << need_i << " bytes";
+  // split tickets live at the start of the int workspace and must start at zero (the kernel restores them)
+  cudaMemsetAsync(ptr(int_ws), 0, (size_t)need_i, stream_of(int_ws));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // decode module
 // ---------------------------------------------------------------------------------------------------------------
 Array<int64_t> DecodePlan(TensorView float_ws, TensorView int_ws, TensorView pinned_int_ws, TensorView indptr_host,
@@ -51,27 +82,9 @@ Array<int64_t> DecodePlan(TensorView float_ws, TensorView int_ws, TensorView pin
   if (logits_soft_cap > 0) TVM_FFI_THROW(ValueError) << "logits soft cap is not implemented";
   if (head_dim_qk != head_dim_vo) TVM_FFI_THROW(ValueError) << "head_dim_qk != head_dim_vo";
   const int32_t* ip = static_cast<const int32_t*>(ptr(indptr_host));   // host tensor (flashinfer_planinfo.cpp:310-311)
-  int64_t max_pages = 1;
-  for (int64_t b = 0; b < batch_size; ++b) max_pages = std::max<int64_t>(max_pages, ip[b + 1] - ip[b]);
-  if (enable_cuda_graph) {
-    // the plan made at capture is replayed for later steps (flashinfer_attention.cpp:306-311): size the split grid
-    // for the longest context the float workspace can serve
-    const int64_t per_split = batch_size * num_qo_heads * (head_dim_vo + 1) * 4;
-    (void)per_split;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t plan[8];
-  check_rc(xb_decode_plan(plan, (int)batch_size, (int)num_qo_heads, (int)num_kv_heads, (int)head_dim_qk, (int)page_size,
-                          (int)max_pages, sms), "decode plan");
-  const int64_t need_f = plan[2], need_i = plan[3] & 0xffffffffll;
-  if (need_f > float_ws.numel() * (float_ws.dtype().bits / 8))
-    TVM_FFI_THROW(RuntimeError) << "float workspace too small: need " << need_f << " bytes";
-  if (need_i > int_ws.numel() * (int_ws.dtype().bits / 8))
-    TVM_FFI_THROW(RuntimeError) << "int workspace too small: need " << need_i << " bytes";
-  // split tickets live at the start of the int workspace and must start at zero
-  cudaMemsetAsync(ptr(int_ws), 0, (size_t)need_i, stream_of(int_ws));
+  make_decode_plan(plan, float_ws, int_ws, ip, batch_size, num_qo_heads, num_kv_heads, page_size, head_dim_qk,
+                   enable_cuda_graph);
   Array<int64_t> out;
   for (int i = 0; i < 8; ++i) out.push_back(plan[i]);
   return out;
@@ -105,24 +118,40 @@ void DecodeRun(TensorView float_ws, TensorView int_ws, Array<int64_t> plan_vec, 
 // ---------------------------------------------------------------------------------------------------------------
 // prefill module
 // ---------------------------------------------------------------------------------------------------------------
+// plan_info of the prefill module: [0] max_qo_len [1] batch [2] total rows [3] qo heads [4] causal
+//   [5] 1 = every request has exactly one query row: paged_run is served by the split-KV decode kernel, whose plan8
+//       follows in [6..13]  (a one-row query sees the whole KV under either mask mode: FlashInfer masks
+//       kv_idx + qo_len > kv_len + q_idx, prefill.cuh:1017)
 Array<int64_t> PrefillPlan(TensorView float_ws, TensorView int_ws, TensorView pinned_int_ws, TensorView qo_indptr_host,
                            TensorView kv_indptr_host, TensorView kv_len_arr_host, int64_t total_num_rows, int64_t batch_size,
                            int64_t num_qo_heads, int64_t num_kv_heads, int64_t page_size, bool enable_cuda_graph,
                            int64_t head_dim_qk, int64_t head_dim_vo, bool causal, int64_t window_left,
                            int64_t fixed_split_size, bool disable_split_kv, int64_t num_colocated_ctas) {
-  (void)float_ws; (void)int_ws; (void)pinned_int_ws; (void)kv_indptr_host; (void)kv_len_arr_host; (void)enable_cuda_graph;
-  (void)fixed_split_size; (void)disable_split_kv; (void)num_colocated_ctas; (void)num_kv_heads; (void)page_size;
+  (void)pinned_int_ws; (void)kv_len_arr_host; (void)fixed_split_size; (void)disable_split_kv; (void)num_colocated_ctas;
   if (window_left >= 0) TVM_FFI_THROW(ValueError) << "sliding window attention is not implemented";
   if (head_dim_qk != head_dim_vo) TVM_FFI_THROW(ValueError) << "head_dim_qk != head_dim_vo";
   const int32_t* qo = static_cast<const int32_t*>(ptr(qo_indptr_host));
-  int64_t max_qo = 0;
-  for (int64_t b = 0; b < batch_size; ++b) max_qo = std::max<int64_t>(max_qo, qo[b + 1] - qo[b]);
+  int64_t max_qo = 0, min_qo = INT64_MAX;
+  for (int64_t b = 0; b < batch_size; ++b) {
+    max_qo = std::max<int64_t>(max_qo, qo[b + 1] - qo[b]);
+    min_qo = std::min<int64_t>(min_qo, qo[b + 1] - qo[b]);
+  }
+  const bool one_row = batch_size > 0 && max_qo == 1 && min_qo == 1 && total_num_rows == batch_size &&
+                       (head_dim_qk == 64 || head_dim_qk == 128);
   Array<int64_t> out;
   out.push_back(max_qo);
   out.push_back(batch_size);
   out.push_back(total_num_rows);
   out.push_back(num_qo_heads);
   out.push_back(causal ? 1 : 0);
+  out.push_back(one_row ? 1 : 0);
+  if (one_row) {
+    int64_t plan[8];
+    // page_size 1 with kv_indptr = cu_seq_lens is how the reference plans ragged prefill; only real page tables land here
+    make_decode_plan(plan, float_ws, int_ws, static_cast<const int32_t*>(ptr(kv_indptr_host)), batch_size, num_qo_heads,
+                     num_kv_heads, page_size, head_dim_qk, enable_cuda_graph);
+    for (int i = 0; i < 8; ++i) out.push_back(plan[i]);
+  }
   return out;
 }
 
@@ -143,7 +172,7 @@ void RaggedRun(TensorView float_ws, TensorView int_ws, Array<int64_t> plan_vec, 
   (void)float_ws; (void)int_ws; (void)maybe_mask_indptr; (void)maybe_prefix_len_ptr; (void)maybe_token_pos_in_items_ptr;
   (void)maybe_max_item_len_ptr; (void)rope_rcp_scale; (void)rope_rcp_theta; (void)token_pos_in_items_len; (void)layout;
   check_prefill_extras(maybe_custom_mask, maybe_alibi_slopes, window_left, logits_soft_cap);
-  if (plan_vec.size() < 5) TVM_FFI_THROW(ValueError) << "plan_info too short";
+  if (plan_vec.size() < 6) TVM_FFI_THROW(ValueError) << "plan_info too short";
   if (!is_bf16(q) || !is_bf16(k) || !is_bf16(o)) TVM_FFI_THROW(TypeError) << "only bf16 q/k/v/o is implemented";
   xb_set_pdl(enable_pdl ? 1 : 0);
   float* lse = maybe_lse.has_value() ? static_cast<float*>(ptr(maybe_lse.value())) : nullptr;
@@ -163,14 +192,32 @@ void PagedRun(TensorView float_ws, TensorView int_ws, Array<int64_t> plan_vec, T
               Optional<TensorView> maybe_prefix_len_ptr, Optional<TensorView> maybe_token_pos_in_items_ptr,
               Optional<TensorView> maybe_max_item_len_ptr, double logits_soft_cap, double sm_scale, double rope_rcp_scale,
               double rope_rcp_theta, int64_t token_pos_in_items_len) {
-  (void)float_ws; (void)int_ws; (void)maybe_mask_indptr; (void)maybe_prefix_len_ptr; (void)maybe_token_pos_in_items_ptr;
+  (void)maybe_mask_indptr; (void)maybe_prefix_len_ptr; (void)maybe_token_pos_in_items_ptr;
   (void)maybe_max_item_len_ptr; (void)rope_rcp_scale; (void)rope_rcp_theta; (void)token_pos_in_items_len;
   check_prefill_extras(maybe_custom_mask, maybe_alibi_slopes, window_left, logits_soft_cap);
-  if (layout != 0) TVM_FFI_THROW(ValueError) << "paged_run: only the NHD cache layout is implemented";
-  if (plan_vec.size() < 5) TVM_FFI_THROW(ValueError) << "plan_info too short";
+  if (plan_vec.size() < 6) TVM_FFI_THROW(ValueError) << "plan_info too short";
   if (!is_bf16(q) || !is_bf16(k_cache) || !is_bf16(o)) TVM_FFI_THROW(TypeError) << "only bf16 q/kv/o is implemented";
   xb_set_pdl(enable_pdl ? 1 : 0);
   float* lse = maybe_lse.has_value() ? static_cast<float*>(ptr(maybe_lse.value())) : nullptr;
+  if (plan_vec[5] == 1) {
+    // decode served through the prefill module (batch_decode.cpp:43-60 -> batch_chunked_prefill.cpp:63-91 with
+    // qo_indptr = arange): one query row per request -> the HBM-streaming split-KV decode kernel
+    if (plan_vec.size() != 14) TVM_FFI_THROW(ValueError) << "plan_info has " << plan_vec.size() << " entries, expected 14";
+    if (q.size(0) != plan_vec[1]) TVM_FFI_THROW(ValueError) << "paged_run: " << q.size(0) << " query rows, plan has " << plan_vec[1];
+    int64_t plan[8];
+    for (int i = 0; i < 8; ++i) plan[i] = plan_vec[6 + i];
+    const int64_t st_page = k_cache.stride(0);
+    const int64_t st_tok = layout == 0 ? k_cache.stride(1) : k_cache.stride(2);
+    const int64_t st_head = layout == 0 ? k_cache.stride(2) : k_cache.stride(1);
+    check_rc(xb_paged_decode_bf16(plan, ptr(q), q.stride(0), q.stride(1), ptr(k_cache), ptr(v_cache), st_page, st_tok,
+                                  st_head, static_cast<const int32_t*>(ptr(kv_indptr)),
+                                  static_cast<const int32_t*>(ptr(kv_indices)),
+                                  static_cast<const int32_t*>(ptr(kv_last_page_len)), ptr(o), o.stride(0), o.stride(1), lse,
+                                  (float)sm_scale, ptr(float_ws), ptr(int_ws), stream_of(q)),
+             "batch prefill paged_run (one-row decode path)");
+    return;
+  }
+  if (layout != 0) TVM_FFI_THROW(ValueError) << "paged_run: only the NHD cache layout is implemented";
   check_rc(xb_prefill_paged_bf16(ptr(q), q.stride(0), q.stride(1), ptr(k_cache), ptr(v_cache), k_cache.size(0),
                                  (int)k_cache.size(1), static_cast<const int32_t*>(ptr(qo_indptr)),
                                  static_cast<const int32_t*>(ptr(kv_indptr)), static_cast<const int32_t*>(ptr(kv_indices)),

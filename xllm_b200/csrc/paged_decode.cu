@@ -20,11 +20,20 @@
 //   FlashInfer tensor-core decode path the reference selects for GQA >= 4
 //   (utils.cpp:349-367).
 //   Warps of a CTA split the chunk's 16-token blocks and merge their
-//   (m, l, O) states through shared memory; CTAs of one (request, kv head)
-//   publish normalised partials + base-2 LSE to the float workspace and the
-//   LAST one to arrive (atomic ticket in the int workspace) merges them - no
-//   second launch, no host sync, CUDA-graph safe (grid is sized from an upper
-//   bound; CTAs past the live split count exit).
+//   (m, l, O) states through shared memory.  The splits of one (request, kv
+//   head) are merged in up to two more levels, both inside this launch:
+//     * thread-block CLUSTER (<= 16 CTAs along the split axis): every CTA keeps
+//       its normalised partial + base-2 LSE in shared memory; after one
+//       cluster barrier CTA r merges slice r of the (head, d) items of all
+//       peers through distributed shared memory (reduce-scatter: 215-cycle
+//       DSMEM loads instead of a round trip through L2) and writes it out;
+//     * if one request's splits span K > 1 clusters, the cluster results go to
+//       the float workspace and the LAST CTA to arrive (atomic ticket in the
+//       int workspace) merges the K partials.
+//   No second launch, no host sync, CUDA-graph safe: the split size is derived
+//   ON THE DEVICE from the live kv_len and the launched grid, so a plan made at
+//   graph capture serves any later context length (flashinfer_attention.cpp:
+//   306-311 replays a captured `run`); clusters past the live split count exit.
 #include "common.cuh"
 
 namespace xb {
@@ -42,14 +51,50 @@ struct DecodeParams {
   int64_t o_stride_n, o_stride_h;
   float* lse;  // optional [batch, num_qo_heads]
   float scale_log2;
-  float* part_o;    // [batch, num_qo_heads, max_splits, D]
-  float* part_lse;  // [batch, num_qo_heads, max_splits]
+  float* part_o;    // [batch, num_qo_heads, max_parts, D]
+  float* part_lse;  // [batch, num_qo_heads, max_parts]
   int32_t* counters;  // [batch, num_kv_heads * head_tiles]
   int num_qo_heads, num_kv_heads, group, head_tiles;
   int page_size, page_shift;  // page_shift >= 0 when page_size is a power of two
-  int chunk_tokens, max_splits;
+  int min_chunk;              // smallest KV chunk a split may get (multiple of 16)
+  int max_parts;              // stride of the partial buffers (>= gridDim.x / cluster)
+  int cluster;                // CTAs per cluster along the split axis (1 = no cluster launch)
   int early_prefetch;  // KV rows of old tokens + the paged triplet are not written by any in-flight kernel
+  unsigned long long* trace;  // debug: per-CTA stage timestamps (xb_debug_set_decode_trace), else null
 };
+
+// ---- thread-block cluster primitives (sm_90+): rank, barrier, distributed shared memory loads ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_dsmem_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ const __nv_bfloat16* kv_row(const DecodeParams& p, const __nv_bfloat16* cache,
                                                        int indptr0, int tok, int kvh) {
@@ -77,6 +122,8 @@ paged_decode_kernel(const DecodeParams p) {
   float* sm_o = smem;                              // [warps][kHeads][kRS]
   float* sm_m = sm_o + kWarpsT * kHeads * kRS;      // [warps][kHeads]
   float* sm_l = sm_m + kWarpsT * kHeads;           // [warps][kHeads]
+  float* sm_co = sm_l + kWarpsT * kHeads;          // [kHeads][kD]  this CTA's normalised partial (read by cluster peers)
+  float* sm_clse = sm_co + kHeads * kD;            // [kHeads]      its base-2 LSE
   __shared__ int s_ticket;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,15 +134,28 @@ paged_decode_kernel(const DecodeParams p) {
 
   pdl_launch_dependents();  // let the consumer's prologue (weight prefetch) start as early as possible
   if (!p.early_prefetch) pdl_wait();
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  auto stamp = [&](int i) {
+    if (p.trace && threadIdx.x == 0) p.trace[(size_t)cta_lin * 8 + i] = globaltimer_ns();
+  };
+  stamp(0);
 
   const int indptr0 = __ldg(p.kv_indptr + b);
   const int n_pages = __ldg(p.kv_indptr + b + 1) - indptr0;
   const int kv_len = n_pages > 0 ? (n_pages - 1) * p.page_size + __ldg(p.kv_last_page_len + b) : 0;
-  int n_splits = (kv_len + p.chunk_tokens - 1) / p.chunk_tokens;
+  // Split geometry is derived HERE from the live kv_len and the launched grid (not baked into the plan): any context
+  // length is covered by gridDim.x splits of whole 16-token blocks, so a plan / CUDA graph made for a short context
+  // stays correct when replayed on a longer one.
+  const int S = gridDim.x, C = p.cluster;
+  int chunk = (((kv_len + S - 1) / S) + 15) & ~15;
+  if (chunk < p.min_chunk) chunk = p.min_chunk;
+  int n_splits = (kv_len + chunk - 1) / chunk;
   if (n_splits < 1) n_splits = 1;
-  if (split >= n_splits) return;
-  const int t_begin = split * p.chunk_tokens;
-  const int t_end = min(kv_len, t_begin + p.chunk_tokens);
+  const int n_parts = (n_splits + C - 1) / C;     // live clusters (= partials that reach the workspace) of this unit
+  const int part = split / C;
+  if (part >= n_parts) return;                    // uniform over the whole cluster: nobody waits for this CTA
+  const int t_begin = min(split * chunk, kv_len);
+  const int t_end = min(kv_len, t_begin + chunk);
   const int head0 = kvh * p.group + htile * kHeads;            // first qo head of this CTA
   const int nheads = min(kHeads, p.group - htile * kHeads);    // live heads in this CTA
   const int nblk = (t_end - t_begin + 15) >> 4;
@@ -264,9 +324,10 @@ paged_decode_kernel(const DecodeParams p) {
   }
   __syncthreads();
 
+  stamp(2);
   // ---- merge warps; each thread owns (head, 4 consecutive d) items ---------------
   constexpr int kItems = kHeads * (kD / 4);
-  const bool single = n_splits == 1;
+  const bool single = C == 1 && n_splits == 1;
   for (int it = threadIdx.x; it < kItems; it += kWarpsT * 32) {
     const int h = it / (kD / 4), d4 = (it % (kD / 4)) * 4;
     if (h >= nheads) continue;
@@ -296,37 +357,106 @@ paged_decode_kernel(const DecodeParams p) {
       ob.y = pack_bf16x2(acc.z, acc.w);
       *reinterpret_cast<uint2*>(p.o + (int64_t)b * p.o_stride_n + (int64_t)qh * p.o_stride_h + d4) = ob;
       if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = lse2;
-    } else {
-      const int64_t slot = ((int64_t)b * p.num_qo_heads + qh) * p.max_splits + split;
+    } else if (C == 1) {
+      const int64_t slot = ((int64_t)b * p.num_qo_heads + qh) * p.max_parts + part;
       *reinterpret_cast<float4*>(p.part_o + slot * kD + d4) = acc;
       if (d4 == 0) p.part_lse[slot] = lse2;
+    } else {
+      *reinterpret_cast<float4*>(sm_co + h * kD + d4) = acc;
+      if (d4 == 0) sm_clse[h] = lse2;
     }
   }
   if (single) return;
+  stamp(3);
 
-  // ---- last CTA of this (request, kv head, head tile) merges the splits -----------
+  // ---- cluster level: reduce-scatter of the C partials through distributed shared memory ---------------------------
+  if (C > 1) {
+    cluster_arrive_release();
+    cluster_wait_acquire();          // every peer's sm_co / sm_clse is complete and visible
+    const int rank = (int)cluster_ctarank();
+    const int per = (kItems + C - 1) / C;
+    const int first = rank * per, lim = min(kItems, first + per);
+    const int sub = threadIdx.x & 15, grp = threadIdx.x >> 4;     // 16 lanes = the (up to 16) peers of one item
+    const uint32_t co_base = smem_addr_u32(sm_co), clse_base = smem_addr_u32(sm_clse);
+    for (int base = first; base < lim; base += kWarpsT * 2) {
+      const int it = base + grp;
+      const bool item_ok = it < lim;
+      const int h = item_ok ? it / (kD / 4) : 0, d4 = item_ok ? (it % (kD / 4)) * 4 : 0;
+      const bool head_ok = item_ok && h < nheads;
+      float ls = -INFINITY;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (head_ok && sub < C) {
+        ls = ld_dsmem_f1(dsmem_addr(clse_base + h * 4, (uint32_t)sub));
+        v = ld_dsmem_f4(dsmem_addr(co_base + (h * kD + d4) * 4, (uint32_t)sub));
+      }
+      float mx = ls;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float m_safe = mx == -INFINITY ? 0.f : mx;
+      const float w = fast_exp2(ls - m_safe);                     // 0 for empty / padding peers
+      float wsum = w;
+      float4 acc = make_float4(v.x * w, v.y * w, v.z * w, v.w * w);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      }
+      if (head_ok && sub == 0) {
+        const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+        const float lse2 = wsum > 0.f ? mx + log2f(wsum) : -INFINITY;
+        const int qh = head0 + h;
+        if (n_parts == 1) {
+          uint2 ob;
+          ob.x = pack_bf16x2(acc.x, acc.y);
+          ob.y = pack_bf16x2(acc.z, acc.w);
+          *reinterpret_cast<uint2*>(p.o + (int64_t)b * p.o_stride_n + (int64_t)qh * p.o_stride_h + d4) = ob;
+          if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = lse2;
+        } else {
+          const int64_t slot = ((int64_t)b * p.num_qo_heads + qh) * p.max_parts + part;
+          *reinterpret_cast<float4*>(p.part_o + slot * kD + d4) = acc;
+          if (d4 == 0) p.part_lse[slot] = lse2;
+        }
+      }
+    }
+    cluster_arrive_release();        // this CTA no longer reads its peers' shared memory
+    stamp(4);
+    if (n_parts == 1) {
+      cluster_wait_acquire();        // ... and may exit once no peer reads ITS shared memory any more
+      return;
+    }
+  }
+
+  // ---- last CTA of this (request, kv head, head tile) merges the n_parts partials ----------------------------------
   __threadfence();
   __syncthreads();
   int32_t* counter = p.counters + (int64_t)b * gridDim.y + blockIdx.y;
   if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1);
   __syncthreads();
-  if (s_ticket != n_splits - 1) return;
+  if (s_ticket != n_parts * C - 1) {
+    if (C > 1) cluster_wait_acquire();
+    return;
+  }
   __threadfence();
   if (threadIdx.x == 0) *counter = 0;  // restore for the next launch
+  const int n_splits_m = n_parts;      // number of partials to merge
   // Stage 1: one warp per head turns the splits' base-2 LSEs into normalised weights in shared memory
   // (lanes read different splits in parallel: no dependent-load chain).  sm_o is free again: reuse it.
-  float* sm_w = sm_o;                       // [kHeads][n_splits]
+  float* sm_w = sm_o;                       // [kHeads][n_splits_m]
   float* sm_lse = sm_m;                     // [kHeads] merged LSE
   __syncthreads();
   for (int h = warp; h < nheads; h += kWarpsT) {
-    const int64_t base = ((int64_t)b * p.num_qo_heads + head0 + h) * p.max_splits;
+    const int64_t base = ((int64_t)b * p.num_qo_heads + head0 + h) * p.max_parts;
     // all of this head's split LSEs in one round trip (<= 8 per lane: max_splits <= 2 * head_dim = 256)
     float ls[8];
     float mx = -INFINITY;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int s = lane + 32 * u;
-      ls[u] = s < n_splits ? __ldcg(p.part_lse + base + s) : -INFINITY;
+      ls[u] = s < n_splits_m ? __ldcg(p.part_lse + base + s) : -INFINITY;
       mx = fmaxf(mx, ls[u]);
     }
     mx = warp_max(mx);
@@ -342,7 +472,7 @@ paged_decode_kernel(const DecodeParams p) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int s = lane + 32 * u;
-      if (s < n_splits) sm_w[h * n_splits + s] = ls[u] * inv;
+      if (s < n_splits_m) sm_w[h * n_splits_m + s] = ls[u] * inv;
     }
     if (lane == 0) sm_lse[h] = wsum > 0.f ? mx + log2f(wsum) : -INFINITY;
   }
@@ -353,16 +483,16 @@ paged_decode_kernel(const DecodeParams p) {
     const int h = it / (kD / 4), d4 = (it % (kD / 4)) * 4;
     if (h >= nheads) continue;
     const int qh = head0 + h;
-    const float4* src = reinterpret_cast<const float4*>(p.part_o + (((int64_t)b * p.num_qo_heads + qh) * p.max_splits) * kD + d4);
-    const float* wrow = sm_w + h * n_splits;
+    const float4* src = reinterpret_cast<const float4*>(p.part_o + (((int64_t)b * p.num_qo_heads + qh) * p.max_parts) * kD + d4);
+    const float* wrow = sm_w + h * n_splits_m;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < n_splits; s += 16) {
+    for (int s = 0; s < n_splits_m; s += 16) {
       float4 v[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (int64_t)min(s + u, n_splits - 1) * (kD / 4));
+      for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (int64_t)min(s + u, n_splits_m - 1) * (kD / 4));
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
-        const float w = s + u < n_splits ? wrow[s + u] : 0.f;
+        const float w = s + u < n_splits_m ? wrow[s + u] : 0.f;
         acc.x += v[u].x * w; acc.y += v[u].y * w; acc.z += v[u].z * w; acc.w += v[u].w * w;
       }
     }
@@ -372,34 +502,69 @@ paged_decode_kernel(const DecodeParams p) {
     *reinterpret_cast<uint2*>(p.o + (int64_t)b * p.o_stride_n + (int64_t)qh * p.o_stride_h + d4) = ob;
     if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = sm_lse[h];
   }
+  stamp(5);
+  if (C > 1) cluster_wait_acquire();
+}
+
+namespace {
+unsigned long long* g_decode_trace = nullptr;   // debug only (xb_debug_set_decode_trace)
 }
 
 template <int kD, int kGT, int kW>
-static int launch_decode_w(const DecodeParams& p, int batch, cudaStream_t stream) {
+static int launch_decode_w(DecodeParams& p, int batch, int splits, cudaStream_t stream) {
   constexpr int kHeads = 8 * kGT;
-  const size_t smem = (size_t)kW * kHeads * (kD + 4 + 2) * sizeof(float);
+  const size_t smem = ((size_t)kW * kHeads * (kD + 4 + 2) + (size_t)kHeads * (kD + 1) + 3) * sizeof(float);
   auto kern = paged_decode_kernel<kD, kGT, kW>;
   static bool attr_done = false;  // per instantiation
+  static int max_cluster = 1;     // largest cluster size this device can co-schedule for this kernel
   if (!attr_done) {
     XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // clusters of more than 8 CTAs are "non-portable": allowed explicitly, then verified with an occupancy query
+    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (int c : {16, 8, 4, 2}) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(c, 1, 1);
+      cfg.blockDim = dim3(kW * 32);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = c;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) {
+        max_cluster = c;
+        break;
+      }
+    }
+    cudaGetLastError();   // a failed probe must not poison the next launch's error state
     attr_done = true;
   }
-  dim3 grid(p.max_splits, p.num_kv_heads * p.head_tiles, batch), block(kW * 32);
-  XB_CUDA_OK(launch(kern, grid, block, smem, stream, true, p));
+  // the plan's cluster size is a request: fall back to per-CTA partials (cluster 1) when the device cannot co-schedule it
+  if (p.cluster > max_cluster || splits % p.cluster != 0) p.cluster = 1;
+  p.trace = g_decode_trace;
+  dim3 grid(splits, p.num_kv_heads * p.head_tiles, batch), block(kW * 32);
+  XB_CUDA_OK(launch_cluster(kern, grid, block, smem, stream, true, p.cluster, p));
   return 0;
 }
 
 template <int kD, int kGT>
-static int launch_decode(const DecodeParams& p, int batch, int cta_warps, cudaStream_t stream) {
-  return cta_warps == 4 ? launch_decode_w<kD, kGT, 4>(p, batch, stream) : launch_decode_w<kD, kGT, 8>(p, batch, stream);
+static int launch_decode(DecodeParams& p, int batch, int splits, int cta_warps, cudaStream_t stream) {
+  return cta_warps == 4 ? launch_decode_w<kD, kGT, 4>(p, batch, splits, stream)
+                        : launch_decode_w<kD, kGT, 8>(p, batch, splits, stream);
 }
 
 }  // namespace xb
 
 using namespace xb;
 
-// plan8: [0]=chunk_tokens [1]=max_splits [2]=float ws bytes [3]=int ws bytes
-//        [4]=batch [5]=num_qo_heads [6]=num_kv_heads [7]=head_dim | page_size<<16 | cta_warps<<40
+// plan8: [0]=nominal chunk tokens at the planned maximum context (informational: the kernel derives the live value)
+//        [1]=splits launched per (request, kv head, head tile) = gridDim.x = clusters x cluster size
+//        [2]=float ws bytes [3]=int ws bytes | flags << 32
+//        [4]=batch [5]=num_qo_heads [6]=num_kv_heads
+//        [7]=head_dim | page_size<<16 | cta_warps<<40 | cluster size<<44
 extern "C" int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int num_kv_heads, int head_dim,
                               int page_size, int max_pages_per_request, int num_sms) {
   XB_CHECK(batch > 0 && num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0,
@@ -411,22 +576,38 @@ extern "C" int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int n
   const int head_tiles = (group + 15) / 16;
   const int64_t units = (int64_t)batch * num_kv_heads * head_tiles;
   const int64_t max_kv = (int64_t)max_pages_per_request * page_size;
-  // one resident CTA per SM; aim for one full wave, chunks are whole 16-token blocks
+  const int64_t kMinChunk = 64;
+  // one resident CTA per SM; aim for one full wave, chunks are whole 16-token blocks of at least kMinChunk tokens
   int64_t want = num_sms / units;
   if (want < 1) want = 1;
-  int64_t chunk = (max_kv + want - 1) / want;
-  chunk = ((chunk + 15) / 16) * 16;
-  if (chunk < 64) chunk = 64;
-  const char* env = getenv("XB_DECODE_CHUNK");
-  if (env && atoi(env) >= 16) chunk = (atoi(env) / 16) * 16;
-  int64_t splits = (max_kv + chunk - 1) / chunk;
-  const int64_t max_splits = 2 * head_dim;   // merge buffer in shared memory
-  if (splits > max_splits) {
-    chunk = (((max_kv + max_splits - 1) / max_splits + 15) / 16) * 16;
-    splits = (max_kv + chunk - 1) / chunk;
+  const int64_t by_len = (max_kv + kMinChunk - 1) / kMinChunk;
+  if (want > by_len) want = by_len;
+  const int64_t max_splits = 2 * head_dim;   // final-merge scratch in shared memory
+  if (want > max_splits) want = max_splits;
+  const char* env = getenv("XB_DECODE_CHUNK");     // tuning / tests: force the nominal chunk
+  if (env && atoi(env) >= 16) {
+    const int64_t chunk = (atoi(env) / 16) * 16;
+    want = (max_kv + chunk - 1) / chunk;
+    if (want > max_splits) want = max_splits;
   }
+  // Cluster geometry: up to 16 splits merge through distributed shared memory inside one cluster; more splits than
+  // that use K = ceil(want / 16) clusters whose K results meet in the workspace (last-arriver merge).
+  int64_t cluster = 1, parts = want;
+  const char* envc = getenv("XB_DECODE_CLUSTER");  // 0 / 1: no clusters (every split is a workspace partial)
+  const int64_t cmax = envc ? atoi(envc) : 16;
+  if (want > 1 && cmax > 1) {
+    parts = (want + cmax - 1) / cmax;
+    const char* envp = getenv("XB_DECODE_PARTS");  // tuning: force the number of clusters per (request, kv head)
+    if (envp && atoi(envp) >= 1 && atoi(envp) <= want) parts = atoi(envp);
+    cluster = want / parts;
+    if (cluster > cmax) cluster = cmax;
+  }
+  const int64_t splits = parts * cluster;
+  int64_t chunk = (((max_kv + splits - 1) / splits + 15) / 16) * 16;
+  if (chunk < kMinChunk) chunk = kMinChunk;
   plan8[0] = chunk;
   plan8[1] = splits;
+  // sized for one partial per split so that the launcher may fall back to cluster size 1 on any device
   plan8[2] = splits > 1 ? (int64_t)batch * num_qo_heads * splits * (head_dim + 1) * 4 : 16;
   plan8[3] = units * 4;  // low 32 bits: int workspace bytes; bit 32: early-prefetch flag (xb_decode_plan_set_flags)
   plan8[4] = batch;
@@ -436,7 +617,7 @@ extern "C" int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int n
   int cta_warps = 8;
   const char* envw = getenv("XB_DECODE_WARPS");
   if (envw && atoi(envw) == 4) cta_warps = 4;
-  plan8[7] = (int64_t)head_dim | ((int64_t)page_size << 16) | ((int64_t)cta_warps << 40);
+  plan8[7] = (int64_t)head_dim | ((int64_t)page_size << 16) | ((int64_t)cta_warps << 40) | (cluster << 44);
   return 0;
 }
 
@@ -451,7 +632,9 @@ extern "C" int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t
   const int batch = (int)plan8[4];
   const int head_dim = (int)(plan8[7] & 0xffff);
   p.page_size = (int)((plan8[7] >> 16) & 0xffffff);
-  const int cta_warps = (int)(plan8[7] >> 40);
+  const int cta_warps = (int)((plan8[7] >> 40) & 0xf);
+  p.cluster = (int)((plan8[7] >> 44) & 0x1f);
+  if (p.cluster < 1) p.cluster = 1;
   p.page_shift = -1;
   if ((p.page_size & (p.page_size - 1)) == 0) {
     int s = 0;
@@ -462,16 +645,18 @@ extern "C" int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t
   p.num_kv_heads = (int)plan8[6];
   p.group = p.num_qo_heads / p.num_kv_heads;
   p.head_tiles = (p.group + 15) / 16;
-  p.chunk_tokens = (int)plan8[0];
-  p.max_splits = (int)plan8[1];
+  p.min_chunk = 64;
+  const int splits = (int)plan8[1];
+  p.max_parts = splits;
   XB_CHECK(q_stride_h % 8 == 0 && q_stride_n % 8 == 0 && kv_stride_token % 8 == 0 && kv_stride_head % 8 == 0 &&
                kv_stride_page % 8 == 0 && o_stride_h % 4 == 0 && o_stride_n % 4 == 0,
            "paged_decode: strides must keep 16-byte alignment");
   XB_CHECK(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k_cache) |
              reinterpret_cast<uintptr_t>(v_cache)) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 7) == 0,
            "paged_decode: q/k_cache/v_cache must be 16-byte aligned");
-  XB_CHECK(p.max_splits == 1 || (workspace_f32 && workspace_i32), "paged_decode: split-KV needs both workspaces");
-  XB_CHECK(p.max_splits <= 2 * head_dim, "paged_decode: %d KV splits exceed the merge buffer (max %d)", p.max_splits, 2 * head_dim);
+  XB_CHECK(splits >= 1 && splits % p.cluster == 0, "paged_decode: corrupt plan (splits %d, cluster %d)", splits, p.cluster);
+  XB_CHECK(splits == 1 || (workspace_f32 && workspace_i32), "paged_decode: split-KV needs both workspaces");
+  XB_CHECK(splits <= 2 * head_dim, "paged_decode: %d KV splits exceed the merge buffer (max %d)", splits, 2 * head_dim);
   p.q = reinterpret_cast<const __nv_bfloat16*>(q);
   p.q_stride_n = q_stride_n;
   p.q_stride_h = q_stride_h;
@@ -489,15 +674,15 @@ extern "C" int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t
   p.lse = lse;
   p.scale_log2 = sm_scale * 1.44269504088896340736f;
   p.part_o = reinterpret_cast<float*>(workspace_f32);
-  p.part_lse = p.part_o ? p.part_o + (int64_t)batch * p.num_qo_heads * p.max_splits * head_dim : nullptr;
+  p.part_lse = p.part_o ? p.part_o + (int64_t)batch * p.num_qo_heads * p.max_parts * head_dim : nullptr;
   p.counters = reinterpret_cast<int32_t*>(workspace_i32);
   p.early_prefetch = (int)(plan8[3] >> 32) & 1;
   cudaStream_t s = (cudaStream_t)stream;
   const bool wide = p.group > 8;
   if (head_dim == 128)
-    return wide ? launch_decode<128, 2>(p, batch, cta_warps, s) : launch_decode<128, 1>(p, batch, cta_warps, s);
+    return wide ? launch_decode<128, 2>(p, batch, splits, cta_warps, s) : launch_decode<128, 1>(p, batch, splits, cta_warps, s);
   if (head_dim == 64)
-    return wide ? launch_decode<64, 2>(p, batch, cta_warps, s) : launch_decode<64, 1>(p, batch, cta_warps, s);
+    return wide ? launch_decode<64, 2>(p, batch, splits, cta_warps, s) : launch_decode<64, 1>(p, batch, splits, cta_warps, s);
   XB_CHECK(false, "paged_decode: head_dim %d unsupported", head_dim);
   return 1;
 }
@@ -508,5 +693,36 @@ extern "C" int xb_paged_decode_bf16(const int64_t* plan8, const void* q, int64_t
 extern "C" int xb_decode_plan_set_flags(int64_t* plan8, int flags) {
   XB_CHECK(plan8 != nullptr, "decode_plan_set_flags: null plan");
   plan8[3] = (plan8[3] & 0xffffffffll) | ((int64_t)(flags & 1) << 32);
+  return 0;
+}
+
+// debug: how many clusters of `cluster` CTAs of the (head_dim 128, group <= 8, 8 warps) kernel the device co-schedules.
+extern "C" int xb_debug_max_active_clusters(int cluster) {
+  auto kern = paged_decode_kernel<128, 1, 8>;
+  const size_t smem = ((size_t)8 * 8 * (128 + 4 + 2) + (size_t)8 * (128 + 1) + 3) * sizeof(float);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cluster, 1, 1);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return n;
+}
+
+// debug: per-CTA stage timestamps (%globaltimer, ns) of the next paged_decode launches: buf = uint64[ctas][8], or null.
+extern "C" int xb_debug_set_decode_trace(void* buf) {
+  g_decode_trace = reinterpret_cast<unsigned long long*>(buf);
   return 0;
 }

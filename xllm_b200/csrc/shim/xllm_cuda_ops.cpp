@@ -22,15 +22,24 @@ namespace xllm::kernel::cuda {
 namespace {
 inline void* stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 inline void ok(int rc, const char* what) { TORCH_CHECK(rc == 0, what, ": ", xb_last_error()); }
+// The reference dispatches on fp16 / bf16 / fp32 (DISPATCH_FLOATING_TYPES); this library implements the serving dtype
+// only, so every tensor argument is checked and an unsupported dtype raises instead of being reinterpreted.
 inline void need_bf16(const torch::Tensor& t, const char* name) {
-  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16, name, " must be a CUDA bfloat16 tensor");
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16, name,
+              " must be a CUDA bfloat16 tensor (xllm_b200 implements bfloat16 only), got ", t.scalar_type());
 }
+inline void need_dtype(const torch::Tensor& t, torch::ScalarType st, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == st, name, " must be a CUDA tensor of ", st, ", got ", t.scalar_type());
+}
+#define XB_GUARD(t) const at::cuda::OptionalCUDAGuard device_guard(device_of(t))
 }  // namespace
 
 // cuda_ops_api.h:31-37
 void rotary_embedding(torch::Tensor& positions, torch::Tensor& query, std::optional<torch::Tensor> key,
                       torch::Tensor& cos_sin_cache, bool is_neox) {
   need_bf16(query, "query");
+  need_bf16(cos_sin_cache, "cos_sin_cache");
+  if (key.has_value()) need_bf16(*key, "key");
   const int64_t head_size = cos_sin_cache.size(-1);
   const int64_t num_tokens = positions.numel();
   TORCH_CHECK(positions.scalar_type() == torch::kInt64, "positions must be int64");
@@ -55,6 +64,8 @@ void act_and_mul(torch::Tensor out, torch::Tensor input, const std::string& act_
   int mode = act_mode == "silu" ? 0 : act_mode == "gelu" ? 1 : (act_mode == "gelu_tanh" || act_mode == "gelu_pytorch_tanh") ? 2 : -1;
   TORCH_CHECK(mode >= 0, "Unsupported act mode: ", act_mode, ", only support silu, gelu, gelu_tanh, gelu_pytorch_tanh");
   need_bf16(input, "input");
+  need_bf16(out, "out");
+  TORCH_CHECK(input.is_contiguous() && out.is_contiguous(), "act_and_mul: tensors must be contiguous");
   const int d = input.size(-1) / 2;
   const int64_t tokens = input.numel() / input.size(-1);
   const at::cuda::OptionalCUDAGuard guard(device_of(input));
@@ -65,6 +76,12 @@ void act_and_mul(torch::Tensor out, torch::Tensor input, const std::string& act_
 void reshape_paged_cache(torch::Tensor slot_ids, torch::Tensor keys, torch::Tensor values, torch::Tensor key_cache,
                          torch::Tensor value_cache) {
   need_bf16(keys, "keys");
+  need_bf16(values, "values");
+  need_bf16(key_cache, "key_cache");
+  need_bf16(value_cache, "value_cache");
+  need_dtype(slot_ids, torch::kInt32, "slot_ids");
+  TORCH_CHECK(key_cache.is_contiguous() && value_cache.is_contiguous(), "caches must be contiguous");
+  XB_GUARD(keys);
   TORCH_CHECK(keys.stride(-1) == 1 && keys.stride(-2) == keys.size(-1));
   TORCH_CHECK(values.stride(-1) == 1 && values.stride(-2) == values.size(-1));
   ok(xb_reshape_paged_cache_bf16(slot_ids.data_ptr<int>(), keys.data_ptr(), values.data_ptr(), key_cache.data_ptr(),
@@ -76,9 +93,15 @@ void reshape_paged_cache(torch::Tensor slot_ids, torch::Tensor keys, torch::Tens
 // cuda_ops_api.h:157-160
 void rms_norm(torch::Tensor output, torch::Tensor input, torch::Tensor weight, double eps) {
   need_bf16(input, "input");
+  need_bf16(output, "output");
+  need_bf16(weight, "weight");
+  TORCH_CHECK(output.is_contiguous(), "output must be contiguous");
   TORCH_CHECK(input.stride(-1) == 1);
+  // norm.cu:436-441: inputs with more than 2 dims are made contiguous so that one row stride describes them
+  if (input.dim() > 2 && !input.is_contiguous()) input = input.contiguous();
+  XB_GUARD(input);
   const int hidden = input.size(-1);
-  ok(xb_rms_norm_bf16(output.data_ptr(), input.data_ptr(), input.stride(-2), weight.data_ptr(), (float)eps,
+  ok(xb_rms_norm_bf16(output.data_ptr(), input.data_ptr(), input.dim() >= 2 ? input.stride(-2) : hidden, weight.data_ptr(), (float)eps,
                       (int)(input.numel() / hidden), hidden, stream()),
      "rms_norm");
 }
@@ -86,7 +109,11 @@ void rms_norm(torch::Tensor output, torch::Tensor input, torch::Tensor weight, d
 // cuda_ops_api.h:162-165
 void fused_add_rms_norm(torch::Tensor& input, torch::Tensor& residual, torch::Tensor& weight, double epsilon) {
   need_bf16(input, "input");
+  need_bf16(residual, "residual");
+  need_bf16(weight, "weight");
   TORCH_CHECK(input.stride(-1) == 1 && residual.is_contiguous());
+  TORCH_CHECK(input.dim() <= 2 || input.is_contiguous(), "fused_add_rms_norm: input with more than 2 dims must be contiguous");
+  XB_GUARD(input);
   const int hidden = input.size(-1);
   ok(xb_fused_add_rms_norm_bf16(input.data_ptr(), input.stride(-2), residual.data_ptr(), weight.data_ptr(), (float)epsilon,
                                 (int)(input.numel() / hidden), hidden, stream()),
@@ -97,7 +124,11 @@ void fused_add_rms_norm(torch::Tensor& input, torch::Tensor& residual, torch::Te
 torch::Tensor matmul(torch::Tensor a, torch::Tensor b, std::optional<torch::Tensor> bias) {
   need_bf16(a, "a");
   need_bf16(b, "b");
+  if (bias.has_value() && bias->defined()) need_bf16(*bias, "bias");
+  TORCH_CHECK(b.dim() == 2 && b.is_contiguous() && a.size(-1) == b.size(1), "matmul: b must be a contiguous [N, K] weight");
+  XB_GUARD(a);
   auto a2 = a.reshape({-1, a.size(-1)});
+  if (a2.stride(-1) != 1) a2 = a2.contiguous();
   const int64_t M = a2.size(0), K = a2.size(1), N = b.size(0);
   auto out = torch::empty({M, N}, a.options());
   const void* bp = bias.has_value() && bias->defined() ? bias->data_ptr() : nullptr;
@@ -119,7 +150,15 @@ void cutlass_scaled_mm(torch::Tensor& c, torch::Tensor const& a, torch::Tensor c
   TORCH_CHECK(a.stride(1) == 1 && c.stride(1) == 1);  // Row-major
   TORCH_CHECK(b.stride(0) == 1);                      // Column-major
   TORCH_CHECK(c.stride(0) % 16 == 0 && b.stride(1) % 16 == 0);
+  // the C ABI takes the weight as a dense [N, K] matrix (ldb == K): a padded column-major b is rejected, not misread
+  TORCH_CHECK(b.stride(1) == a.size(1), "cutlass_scaled_mm: b must be a dense column-major [K, N] view (stride(1) == K), got ",
+              b.stride(1));
   TORCH_CHECK(a_scales.is_contiguous() && b_scales.is_contiguous());
+  need_dtype(a_scales, torch::kFloat32, "a_scales");
+  need_dtype(b_scales, torch::kFloat32, "b_scales");
+  TORCH_CHECK((a_scales.numel() == 1 || a_scales.numel() == a.size(0)) && (b_scales.numel() == 1 || b_scales.numel() == b.size(1)),
+              "scale numel must be 1 or M / N");
+  if (bias) need_bf16(*bias, "bias");
   if (bias) TORCH_CHECK(bias->numel() == b.size(1) && bias->is_contiguous() && bias->dim() == 1);
   TORCH_CHECK(a.scalar_type() == torch::kFloat8_e4m3fn && b.scalar_type() == torch::kFloat8_e4m3fn, "fp8 e4m3 inputs expected");
   TORCH_CHECK(c.scalar_type() == torch::kBFloat16, "only bfloat16 output is implemented");
@@ -134,6 +173,11 @@ void cutlass_scaled_mm(torch::Tensor& c, torch::Tensor const& a, torch::Tensor c
 void static_scaled_fp8_quant(torch::Tensor& out, torch::Tensor const& input, torch::Tensor const& scale) {
   TORCH_CHECK(input.stride(-1) == 1, "last dimension of input must be contiguous");
   TORCH_CHECK(out.stride(-1) == 1, "last dimension of output must be contiguous");
+  need_bf16(input, "input");
+  need_dtype(out, torch::kFloat8_e4m3fn, "out");
+  need_dtype(scale, torch::kFloat32, "scale");
+  TORCH_CHECK(input.dim() >= 2 && out.dim() >= 2, "static_scaled_fp8_quant: [tokens, hidden] tensors expected");
+  XB_GUARD(input);
   const int hidden = input.size(-1);
   ok(xb_static_scaled_fp8_quant_bf16(out.data_ptr(), out.stride(-2), input.data_ptr(), input.stride(-2),
                                      scale.data_ptr<float>(), (int)(input.numel() / hidden), hidden, stream()),
@@ -149,6 +193,10 @@ std::tuple<torch::Tensor, torch::Tensor> fp8_scaled_quantize(const torch::Tensor
     static_scaled_fp8_quant(out, input, *scale);
     return {out, *scale};
   }
+  need_bf16(input, "input");
+  need_dtype(out, torch::kFloat8_e4m3fn, "output");
+  TORCH_CHECK(input.stride(-1) == 1 && out.stride(-1) == 1 && input.dim() >= 2, "fp8_scaled_quantize: [tokens, hidden] row-major tensors expected");
+  XB_GUARD(input);
   auto s = torch::empty({1}, input.options().dtype(torch::kFloat32));
   const int hidden = input.size(-1);
   ok(xb_dynamic_scaled_fp8_quant_bf16(out.data_ptr(), out.stride(-2), input.data_ptr(), input.stride(-2), s.data_ptr<float>(),
@@ -159,6 +207,12 @@ std::tuple<torch::Tensor, torch::Tensor> fp8_scaled_quantize(const torch::Tensor
 
 // cuda_ops_api.h:203-221
 void rms_norm_static_fp8_quant(torch::Tensor& out, torch::Tensor& input, torch::Tensor& weight, torch::Tensor& scale, double epsilon) {
+  need_bf16(input, "input");
+  need_bf16(weight, "weight");
+  need_dtype(out, torch::kFloat8_e4m3fn, "out");
+  need_dtype(scale, torch::kFloat32, "scale");
+  TORCH_CHECK(out.is_contiguous() && input.stride(-1) == 1 && input.dim() >= 2);
+  XB_GUARD(input);
   const int hidden = input.size(-1);
   ok(xb_rms_norm_static_fp8_quant_bf16(out.data_ptr(), input.data_ptr(), input.stride(-2), weight.data_ptr(),
                                        scale.data_ptr<float>(), (float)epsilon, (int)(input.numel() / hidden), hidden, stream()),
@@ -166,6 +220,13 @@ void rms_norm_static_fp8_quant(torch::Tensor& out, torch::Tensor& input, torch::
 }
 void fused_add_rms_norm_static_fp8_quant(torch::Tensor& out, torch::Tensor& input, torch::Tensor& residual, torch::Tensor& weight,
                                          torch::Tensor& scale, double epsilon) {
+  need_bf16(input, "input");
+  need_bf16(residual, "residual");
+  need_bf16(weight, "weight");
+  need_dtype(out, torch::kFloat8_e4m3fn, "out");
+  need_dtype(scale, torch::kFloat32, "scale");
+  TORCH_CHECK(out.is_contiguous() && residual.is_contiguous() && input.stride(-1) == 1 && input.dim() >= 2);
+  XB_GUARD(input);
   const int hidden = input.size(-1);
   ok(xb_fused_add_rms_norm_static_fp8_quant_bf16(out.data_ptr(), input.data_ptr(), input.stride(-2), residual.data_ptr(),
                                                  weight.data_ptr(), scale.data_ptr<float>(), (float)epsilon,
@@ -188,7 +249,11 @@ void fused_qk_norm_rope(torch::Tensor& qkv, int64_t num_heads_q, int64_t num_hea
                         double eps, const torch::Tensor& q_weight, const torch::Tensor& k_weight, const torch::Tensor& cos_sin_cache,
                         bool interleaved, const torch::Tensor& position_ids) {
   need_bf16(qkv, "qkv");
+  need_bf16(q_weight, "q_weight");
+  need_bf16(k_weight, "k_weight");
+  need_bf16(cos_sin_cache, "cos_sin_cache");
   TORCH_CHECK(qkv.is_contiguous() && position_ids.scalar_type() == torch::kInt64);
+  XB_GUARD(qkv);
   ok(xb_fused_qk_norm_rope_bf16(qkv.data_ptr(), (int)num_heads_q, (int)num_heads_k, (int)num_heads_v, (int)head_dim, (float)eps,
                                 q_weight.data_ptr(), k_weight.data_ptr(), cos_sin_cache.data_ptr(), (int)cos_sin_cache.size(-1),
                                 interleaved ? 1 : 0, position_ids.data_ptr<int64_t>(), (int)qkv.size(0), stream()),
@@ -199,7 +264,12 @@ void fused_qk_norm_rope(torch::Tensor& qkv, int64_t num_heads_q, int64_t num_hea
 torch::Tensor w4a16_linear(const torch::Tensor& x, const torch::Tensor& qweight, const torch::Tensor& meta, int64_t group_size,
                            const std::optional<torch::Tensor>& bias) {
   need_bf16(x, "x");
+  need_dtype(qweight, torch::kInt32, "qweight");
+  need_dtype(meta, torch::kInt32, "meta");
+  if (bias.has_value() && bias->defined()) need_bf16(*bias, "bias");
+  XB_GUARD(x);
   auto x2 = x.reshape({-1, x.size(-1)});
+  if (x2.stride(-1) != 1) x2 = x2.contiguous();
   const int64_t M = x2.size(0), K = x2.size(1), N = meta.size(1);
   auto out = torch::empty({M, N}, x.options());
   const void* bp = bias.has_value() && bias->defined() ? bias->data_ptr() : nullptr;

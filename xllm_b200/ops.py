@@ -199,7 +199,10 @@ class DecodePlan:
         self.arr = (ctypes.c_int64 * 8)()
         check(lib().xb_decode_plan(self.arr, c_i32(batch), c_i32(num_qo_heads), c_i32(num_kv_heads), c_i32(head_dim),
                                    c_i32(page_size), c_i32(max_pages_per_request), c_i32(num_sms)), "decode_plan")
+        # chunk_tokens: nominal split size at the planned maximum context (the kernel derives the live one on the device);
+        # max_splits: splits launched per (request, kv head) = clusters x cluster size
         self.chunk_tokens, self.max_splits = int(self.arr[0]), int(self.arr[1])
+        self.cluster = int(self.arr[7] >> 44) & 0x1F
         self.float_ws = torch.empty(int(self.arr[2]), dtype=torch.uint8, device=device)
         self.int_ws = torch.zeros(int(self.arr[3]) & 0xFFFFFFFF, dtype=torch.uint8, device=device)
         if early_prefetch:

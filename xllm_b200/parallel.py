@@ -78,9 +78,12 @@ def shard_cols(in_features, rank, tp) -> slice:
     return slice(rank * per, (rank + 1) * per)
 
 
-def shard_linear(kind: str, part: dict, rows: Optional[torch.Tensor], cols: Optional[slice], group_size: int) -> dict:
+def shard_linear(kind: str, part: dict, rows: Optional[torch.Tensor], cols: Optional[slice], group_size: int,
+                 rank: int = 0) -> dict:
     """Shard one logical linear (dict with w | (q, s, z) and optional b).  `rows` selects output rows (column
-    parallel), `cols` selects input columns (row parallel; must be aligned to the quantisation group)."""
+    parallel), `cols` selects input columns (row parallel; must be aligned to the quantisation group).  `rank` decides
+    who carries the bias of a ROW-parallel shard: rank 0 only, so that it is added once after the all-reduce
+    (linear.cpp:1508-1511)."""
     out = {}
     if "q" in part:
         q, s, z = part["q"], part["s"], part["z"]
@@ -103,7 +106,12 @@ def shard_linear(kind: str, part: dict, rows: Optional[torch.Tensor], cols: Opti
     b = part.get("b")
     if b is not None:
         # bias is added once: column-parallel shards carry their rows; row-parallel only on rank 0 (linear.cpp:1508-1511)
-        out["b"] = b[rows].contiguous() if rows is not None else b
+        if rows is not None:
+            out["b"] = b[rows].contiguous()
+        elif cols is not None:
+            out["b"] = b if rank == 0 else None
+        else:
+            out["b"] = b
     else:
         out["b"] = None
     return out

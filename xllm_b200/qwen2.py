@@ -139,15 +139,18 @@ class Qwen2Weights:
     @staticmethod
     def synthetic(cfg: Qwen2Config, device="cuda", seed=2026, tp_rank: int = 0, tp: int = 1):
         """random-init weights of the named architecture (no checkpoints offline), generated on device.  With tp > 1 the
-        shapes are this rank's shards (column-parallel qkv / gate_up / lm_head, row-parallel o / down)."""
+        shapes are this rank's shards (column-parallel qkv / gate_up / lm_head, row-parallel o / down).  Tensors that the
+        reference REPLICATES across a TP group (embedding table, every RMSNorm weight) come from a generator seeded by
+        `seed` alone, so all ranks of a group hold identical copies; shards are seeded per rank."""
         from .parallel import partition_heads
-        g = torch.Generator(device=device).manual_seed(seed)
+        g_rep = torch.Generator(device=device).manual_seed(seed)
+        g = torch.Generator(device=device).manual_seed(seed + 7919 * (tp_rank + 1)) if tp > 1 else g_rep
         w = Qwen2Weights(cfg)
         H, I = cfg.hidden_size, cfg.intermediate_size // tp
         hp = partition_heads(cfg.n_heads, cfg.n_kv_heads, tp_rank, tp)
         q_size, kv_size = hp.num_heads * cfg.head_dim, hp.num_kv_heads * cfg.head_dim
-        w.embed = (torch.randn(cfg.vocab_size, H, generator=g, device=device) * 0.02).to(BF16)
-        w.final_norm = (1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16)
+        w.embed = (torch.randn(cfg.vocab_size, H, generator=g_rep, device=device) * 0.02).to(BF16)
+        w.final_norm = (1.0 + 0.05 * torch.randn(H, generator=g_rep, device=device)).to(BF16)
         vs = cfg.vocab_size // tp
         w.lm_head = Linear(vs, H, "bf16")                   # lm_head stays unquantised (linear.cpp:512-520)
         w.lm_head.weight = w.embed if (cfg.tie_word_embeddings and tp == 1) else \
@@ -155,8 +158,8 @@ class Qwen2Weights:
         for _ in range(cfg.num_layers):
             mk = lambda n, k, b=False: Qwen2Weights._synthetic_linear(n, k, cfg.quant, cfg.group_size, g, device, b)
             w.layers.append(dict(
-                input_norm=(1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16),
-                post_norm=(1.0 + 0.05 * torch.randn(H, generator=g, device=device)).to(BF16),
+                input_norm=(1.0 + 0.05 * torch.randn(H, generator=g_rep, device=device)).to(BF16),
+                post_norm=(1.0 + 0.05 * torch.randn(H, generator=g_rep, device=device)).to(BF16),
                 qkv=mk(q_size + 2 * kv_size, H, cfg.qkv_bias), o=mk(H, q_size),
                 gate_up=mk(2 * I, H), down=mk(H, I)))
             # synthetic packed nibbles are random anyway: declare the gate_up rows interleaved so the fused epilogue runs
@@ -264,7 +267,7 @@ class Qwen2DecodeRunner:
             lin.forward(x, out)
             ops.fused_add_rms_norm(out, self.residual, norm_w, cfg.rms_norm_eps)
             return out
-        if self.exchange is not None:
+        if self.exchange is not None and x.size(0) <= self.exchange.MAX_CTAS:
             part = self.exchange.partial_buffer(which, x.size(0))
             lin.forward(x, part)                                    # partial straight into the symmetric buffer
             self.exchange.allreduce_add_rms_norm(which, out, self.residual, norm_w, cfg.rms_norm_eps, x.size(0))
@@ -340,13 +343,34 @@ class Qwen2DecodeRunner:
             self.graph.replay()
 
     def set_inputs_host(self, token_ids, positions, slots, kv_indptr, kv_indices, kv_last):
-        n = len(token_ids)
+        """Step inputs of `n <= max_batch` live requests.  The captured graph always processes max_batch rows, so rows
+        n..B-1 are padded EXACTLY as the reference pads a decode batch (padding_decode_batch_size,
+        batch_input_builder.cpp:833-875): token 0, position 0, slot 0 and one page = block 0 (the reserved padding block,
+        block_manager_impl.cpp:71-73) with last_page_len 1.  Stale rows from a previous, larger batch would otherwise
+        scatter K/V into slots the block manager may have handed to another request."""
+        n, B = len(token_ids), self.B
+        if n > B:
+            raise ValueError(f"{n} requests exceed max_batch {B}")
+        kv_indptr, kv_indices = list(kv_indptr), list(kv_indices)
+        if len(kv_indptr) != n + 1 or kv_indptr[-1] != len(kv_indices):
+            raise ValueError("paged_kv_indptr / paged_kv_indices are inconsistent")
+        pad = B - n
+        if len(kv_indices) + pad > self.h_kv_indices.numel():
+            raise ValueError("paged_kv_indices exceed the runner's page budget")
         self.h_token_ids[:n] = torch.as_tensor(token_ids, dtype=torch.int32)
         self.h_positions[:n] = torch.as_tensor(positions, dtype=torch.int64)
         self.h_slots[:n] = torch.as_tensor(slots, dtype=torch.int32)
-        self.h_kv_indptr[:len(kv_indptr)] = torch.as_tensor(kv_indptr, dtype=torch.int32)
+        self.h_kv_indptr[:n + 1] = torch.as_tensor(kv_indptr, dtype=torch.int32)
         self.h_kv_indices[:len(kv_indices)] = torch.as_tensor(kv_indices, dtype=torch.int32)
         self.h_kv_last[:n] = torch.as_tensor(kv_last, dtype=torch.int32)
+        if pad:
+            self.h_token_ids[n:] = 0
+            self.h_positions[n:] = 0
+            self.h_slots[n:] = 0
+            base = kv_indptr[-1]
+            self.h_kv_indices[base:base + pad] = 0
+            self.h_kv_indptr[n + 1:] = torch.arange(base + 1, base + pad + 1, dtype=torch.int32)
+            self.h_kv_last[n:] = 1
 
     def step(self):
         """end-to-end step: H2D of the pinned step inputs, graph replay, D2H of the sampled tokens."""
