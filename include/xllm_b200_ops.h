@@ -121,6 +121,17 @@ int xb_rope_and_cache_bf16(const int64_t* positions, void* query, void* key,
                            int block_size, int is_neox, int num_tokens,
                            xb_stream_t stream);
 
+/* the same two ops on a qkv projection whose output columns are in the rope-pair packed order of the weight-only
+ * decode layout (quant.pack_w4_qkv_rope; the decode GEMV does this work in its epilogue, see
+ * xb_linear_w4a16_decode_fused): reads qkv_packed [T, (Hq+2Hkv)*D], writes q | k | v in LOGICAL order to qkv_out
+ * (a different buffer) and the new k / v rows to the paged caches.  NeoX halves, full rotary. */
+int xb_rope_and_cache_packed_bf16(const int64_t* positions, const void* qkv_packed,
+                                  int64_t in_stride, void* qkv_out, int64_t out_stride,
+                                  const void* cos_sin_cache, const int32_t* slot_ids,
+                                  void* key_cache, void* value_cache, int num_heads,
+                                  int num_kv_heads, int head_size, int num_tokens,
+                                  xb_stream_t stream);
+
 /* ---- K10: fused per-head QK RMSNorm + RoPE (Qwen3) -------------------------
  * replaces xllm::kernel::cuda::fused_qk_norm_rope (cuda_ops_api.h:252-266,
  * fused_qknorm_rope.cu:84-471). qkv packed [T,(hq+hk+hv)*d], in place. */
@@ -214,6 +225,25 @@ int xb_linear_w4a16_gate_up_act_small_m(void* y, int64_t y_stride, const void* x
                                         const uint32_t* qweight, const uint32_t* meta,
                                         const void* bias, int M, int N, int K, int group_size,
                                         int act_mode, xb_stream_t stream);
+/* decode-step form of a weight-only linear (M <= 8): the work the step does right before and after the GEMV rides in
+ * the same launch (north-star "RMSNorm+RoPE as a single fused epilogue"):
+ *   prologue  norm_weight != NULL: x := RMSNorm(x (+ residual_in)) * norm_weight  (fused_add_rms_norm / rms_norm,
+ *             xllm/core/kernels/cuda/norm.cu:43-136); residual_out (may be NULL, must not alias residual_in)
+ *             receives the updated residual stream.  stage_x != 0 stages x in shared memory without a norm.
+ *   epilogue  0: +bias; 1: act(gate)*up on interleaved rows, y [M, N/2] (activation.cu:45-130);
+ *             2: qkv_proj: +bias, NeoX RoPE on q / k heads (rope.cu:27-137) and scatter of the new k / v rows into
+ *                the paged caches (reshape_paged_cache.cu:23-62); weight rows packed by quant.pack_w4_qkv_rope;
+ *                y [M, N] in logical [q | k | v] order.
+ * xb_linear_w4a16_decode_fused_fits(M, K) tells whether the [M, K] activation block fits the shared-memory stage. */
+int xb_linear_w4a16_decode_fused(void* y, int64_t y_stride, const void* x, int64_t x_stride,
+                                 const uint32_t* qweight, const uint32_t* meta, const void* bias,
+                                 int M, int N, int K, int group_size, const void* norm_weight, float eps,
+                                 const void* residual_in, void* residual_out, int stage_x, int epilogue,
+                                 int act_mode, const int64_t* positions, const void* cos_sin_cache,
+                                 const int32_t* slot_ids, void* k_cache, void* v_cache, int num_heads,
+                                 int num_kv_heads, int head_dim, xb_stream_t stream);
+int xb_linear_w4a16_decode_fused_fits(int M, int K);
+
 /* act_and_mul over that interleaved column layout (prefill path sharing the same packed weight):
  * out[t, 8j+i] = act(x[t, 16j+i]) * x[t, 16j+8+i]. */
 int xb_act_and_mul_interleaved8_bf16(void* out, const void* input, int d, int num_tokens,

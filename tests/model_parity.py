@@ -112,8 +112,15 @@ def upload(cfg, W, device="cuda"):
     w.lm_head = Linear(cfg.vocab_size, cfg.hidden_size, "bf16")
     w.lm_head.weight = w.embed if cfg.tie_word_embeddings else W["lm_head"].to(device)
 
-    def mk(d, n, k, gate_up=False):
+    def mk(d, n, k, gate_up=False, qkv=False):
         l = Linear(n, k, cfg.quant, cfg.group_size)
+        if qkv and cfg.quant == "w4a16":
+            # decode layout: rows in rope-pair order so that RoPE + KV scatter fuse into the GEMV epilogue
+            qw, meta, b = quant.pack_w4_qkv_rope(d["q"], d["s"], d["z"], cfg.n_heads, cfg.n_kv_heads, cfg.head_dim,
+                                                 cfg.group_size, d["b"])
+            l.qweight, l.meta, l.bias = qw.to(device), meta.to(device), (b.to(device) if b is not None else None)
+            l.qkv_rope_packed = True
+            return l
         if gate_up and cfg.quant == "w4a16":
             qw, meta, b = quant.pack_w4_gate_up(d["q"], d["s"], d["z"], cfg.group_size, d["b"])
             l.qweight, l.meta, l.bias = qw.to(device), meta.to(device), (b.to(device) if b is not None else None)
@@ -133,7 +140,7 @@ def upload(cfg, W, device="cuda"):
     H, I = cfg.hidden_size, cfg.intermediate_size
     for L in W["layers"]:
         w.layers.append(dict(input_norm=L["input_norm"].to(device), post_norm=L["post_norm"].to(device),
-                             qkv=mk(L["qkv"], cfg.q_size + 2 * cfg.kv_size, H), o=mk(L["o"], H, cfg.q_size),
+                             qkv=mk(L["qkv"], cfg.q_size + 2 * cfg.kv_size, H, qkv=True), o=mk(L["o"], H, cfg.q_size),
                              gate_up=mk(L["gate_up"], 2 * I, H, gate_up=True), down=mk(L["down"], H, I)))
     return w
 

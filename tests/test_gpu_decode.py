@@ -57,6 +57,8 @@ CASES = [
     ([45, 46, 47],             8, 1, 128, 1),      # page_size 1
     ([100, 260],               12, 4, 64, 12),     # non power-of-two page size
     ([8192],                   8, 1, 128, 128),    # Llama-3-70B TP8 per-GPU heads, ctx 8192
+    ([133],                    14, 2, 64, 128),    # BASELINE configs[0] heads a few tokens into the second page
+    ([4096, 9, 300],           28, 4, 128, 128),   # ragged lengths under one split count
 ]
 
 
@@ -73,6 +75,23 @@ def test_paged_decode_matches_oracle(kv_lens, HQ, HKV, D, page, built_lib):
     assert_close_attention(out, ref, scale, what=f"paged_decode {kv_lens} splits={plan.max_splits}")
     # l sums bf16-rounded P relative to the running maximum of the tile order: log2(l) moves by ~2^-9 / ln 2
     assert torch.allclose(lse.cpu(), ref_lse, rtol=1e-4, atol=5e-3), "base-2 LSE mismatch"
+
+
+def test_paged_decode_distance_from_exact_math(built_lib):
+    """how far ONE implementation of the bf16-P ladder sits from un-rounded softmax numerators (oracle with fp32 P,
+    same bf16 output rounding): analytically 1.66e-3 relative L2 from the rounding of P alone (tests/util.py), plus the
+    partly independent bf16 roundings of the two outputs.  Asserted for the kernel AND for the reference-ladder oracle,
+    at the BASELINE configs[1] attention shape."""
+    kv_lens, HQ, HKV, D, page = [4096], 28, 4, 128, 128
+    q, kc, vc, indptr, indices, last = make_case(kv_lens, HQ, HKV, D, page)
+    qo = torch.arange(2, dtype=torch.int32)
+    sc = 1.0 / math.sqrt(D)
+    exact = O.paged_attention(q, kc, vc, qo, indptr, indices, last, sc, causal=False, round_p=False)
+    ladder = O.paged_attention(q, kc, vc, qo, indptr, indices, last, sc, causal=False)
+    out, _, _ = run_gpu(q, kc, vc, indptr, indices, last, page, 32)
+    scale = O.paged_attention(q, kc, vc.abs(), qo, indptr, indices, last, sc, causal=False)
+    assert_close_attention(out, exact, scale, what="paged_decode kernel vs fp32-P oracle (one bf16-P implementation)", rel_l2=2.6e-3)
+    assert_close_attention(ladder, exact, scale, what="reference-ladder oracle vs fp32-P oracle", rel_l2=2.6e-3)
 
 
 def test_paged_decode_upper_bound_plan(built_lib):

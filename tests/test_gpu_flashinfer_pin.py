@@ -79,6 +79,9 @@ def test_decode_matches_flashinfer(kv_lens, HQ, HKV, D, page, tensor_cores, buil
     decode served by the fa2 prefill kernel, causal=False); tensor_cores=False is FlashInfer's CUDA-core decode kernel."""
     flashinfer = flashinfer_or_skip(D)
     from xllm_b200 import ops
+    if not tensor_cores and HQ // HKV not in (1, 2, 3, 4, 8):
+        pytest.skip(f"FlashInfer's CUDA-core decode kernel is not instantiated for GQA group {HQ // HKV} (batch_decode.cu: "
+                    "'Unsupported group_size') - the reference never takes that path for such models (utils.cpp:349-367)")
     q, kc, vc, indptr, indices, last = make_case(kv_lens, HQ, HKV, D, page)
     B = len(kv_lens)
     sm_scale = 1.0 / math.sqrt(D)
@@ -96,7 +99,9 @@ def test_decode_matches_flashinfer(kv_lens, HQ, HKV, D, page, tensor_cores, buil
     scale = _p_abs_v_scale(q, kc, vc, indptr, indices, last, sm_scale)
     # FlashInfer's CUDA-core decode kernel keeps P in fp32 (no bf16 rounding of P), its tensor-core path rounds P like
     # ours: both are within the same forward-error bound of our result
-    assert_close_attention(out, ref, scale, rtol=2e-3, what=f"decode vs flashinfer {kv_lens} (tensor_cores={tensor_cores})")
+    # two different kernels, each with its own bf16 roundings of P (and FlashInfer's own split-KV merge): measured up to
+    # 3.3e-3 relative L2 on B200 (see tests/util.py for the 2.35e-3 analytic floor)
+    assert_close_attention(out, ref, scale, rtol=2e-3, rel_l2=4e-3, what=f"decode vs flashinfer {kv_lens} (tensor_cores={tensor_cores})")
     # and the oracle agrees with FlashInfer to the same bar: this is what pins the oracle's attention ladder
     qo = torch.arange(B + 1, dtype=torch.int32)
     orc = O.paged_attention(q, kc, vc, qo, indptr, indices, last, sm_scale, causal=False)

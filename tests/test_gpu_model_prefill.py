@@ -139,7 +139,7 @@ def test_cfg0_qwen2_0_5b_full_model_prompt128_greedy16(built_lib):
             runner.capture()
         got_tokens.append(int(runner.step()[0]))
         got_logits.append(runner.logits[:1].cpu().clone())
-    worst, exact, decided = 0.0, 0, 0
+    worst, exact, decided, report, bad = 0.0, 0, 0, [], []
     for i in range(n_decode):
         rl = ref_logits[i].float()[0]
         l2 = _rel_l2(got_logits[i], ref_logits[i])
@@ -147,13 +147,18 @@ def test_cfg0_qwen2_0_5b_full_model_prompt128_greedy16(built_lib):
         top2 = rl.topk(2).values
         margin = float(top2[0] - top2[1])
         tol = 0.02 * abs(float(top2[0]))
-        exact += int(got_tokens[i] == ref_tokens[i])
+        same = got_tokens[i] == ref_tokens[i]
+        exact += int(same)
+        near = float(rl[got_tokens[i]]) >= float(top2[0]) - tol
+        report.append(f"step {i}: rel_l2 {l2:.2e} top {float(top2[0]):.2f} margin {margin:.2f} tol {tol:.2f} "
+                      f"got {got_tokens[i]} ref {ref_tokens[i]} {'ok' if same else ('near-tie' if near else 'MISMATCH')}")
         if margin > tol:
             decided += 1
-            assert got_tokens[i] == ref_tokens[i], f"step {i}: token {got_tokens[i]} != oracle {ref_tokens[i]} (margin {margin:.3f})"
-        assert float(rl[got_tokens[i]]) >= float(top2[0]) - tol, f"step {i}: GPU token is not a near-argmax of the oracle"
+            if not same:
+                bad.append(i)
+        if not near:
+            bad.append(i)
     from tests.util import REL_L2_LOG
     REL_L2_LOG.append((f"cfg0 Qwen2-0.5B full model: worst logits rel-L2 over {n_decode} steps; {exact}/{n_decode} tokens "
                        f"exact, {decided} steps with a decisive oracle margin", worst))
-    assert worst <= 5e-2, f"logits rel-L2 {worst:.3e}"
-    assert exact >= n_decode - 2, (got_tokens, ref_tokens)
+    assert not bad and worst <= 5e-2 and exact >= n_decode - 2, "\n".join(report)

@@ -41,7 +41,7 @@ def test_decode_plan_invariants(batch, hq, hkv, d, page, max_pages, built_lib, m
         assert p[2] >= batch * hq * splits * (d + 1) * 4
     group = hq // hkv
     head_tiles = (group + 15) // 16
-    assert (p[3] & 0xFFFFFFFF) >= batch * hkv * head_tiles * 4
+    assert (p[3] & 0xFFFFFFFF) >= batch * hkv * head_tiles * 8
     assert (p[4], p[5], p[6]) == (batch, hq, hkv)
     assert p[7] & 0xFFFF == d and (p[7] >> 16) & 0xFFFFFF == page and (p[7] >> 40) & 0xF in (4, 8)
     # one wave: with few (request, kv head) units the planner splits the KV range to fill the SMs, never beyond them
@@ -62,14 +62,14 @@ def test_decode_plan_flags_and_env(built_lib, monkeypatch):
     assert lib.xb_decode_plan_set_flags(None, 1) != 0
     monkeypatch.setenv("XB_DECODE_CHUNK", "200")          # rounded down to whole blocks -> 192 -> 22 splits of <= 192
     rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)
-    assert rc == 0 and p[1] == 2 * 11 and p[0] == 192 and (p[7] >> 44) & 0x1F == 11
-    monkeypatch.setenv("XB_DECODE_CLUSTER", "1")          # no clusters: every split is a workspace partial
+    assert rc == 0 and p[1] == 22 and p[0] == 192 and (p[7] >> 44) & 0x1F == 1
+    monkeypatch.setenv("XB_DECODE_CLUSTER", "16")         # opt-in clusters: 22 splits = 2 clusters of 11 CTAs
     rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)
-    assert rc == 0 and p[1] == 22 and (p[7] >> 44) & 0x1F == 1
+    assert rc == 0 and p[1] == 2 * 11 and (p[7] >> 44) & 0x1F == 11
     monkeypatch.delenv("XB_DECODE_CLUSTER")
     monkeypatch.delenv("XB_DECODE_CHUNK")
-    rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)            # BASELINE configs[1]: 37 wanted -> 3 clusters of 12
-    assert rc == 0 and p[1] == 36 and (p[7] >> 44) & 0x1F == 12
+    rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)            # BASELINE configs[1]: 37 splits of 112 tokens, no clusters
+    assert rc == 0 and p[1] == 37 and p[0] == 112 and (p[7] >> 44) & 0x1F == 1
     monkeypatch.setenv("XB_DECODE_WARPS", "4")
     rc, p = _plan(lib, 1, 28, 4, 128, 128, 32)
     assert rc == 0 and (p[7] >> 40) & 0xF == 4

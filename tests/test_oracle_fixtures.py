@@ -83,4 +83,8 @@ def test_kernels_against_frozen_outputs(fx, built_lib):
     plan = ops.DecodePlan(B, HQ, kc.shape[2], D, page, int((indptr[1:] - indptr[:-1]).max()), dev)
     o = torch.empty(B, HQ, D, dtype=BF16, device=dev)
     ops.batch_decode(plan, qd.to(dev), kc.to(dev), vc.to(dev), indptr.to(dev), perm.to(dev), last.to(dev), 1 / math.sqrt(D), o, None)
-    assert_close_bf16(o, fx["paged_decode"]["out"][0], ulps=4, rel_l2=1e-2, what="paged decode kernel vs fixture")
+    # attention: forward-error bound of tests/util.py (bf16 P roundings; elements that cancel to ~0 cannot be held to ulps)
+    from tests.util import assert_close_attention
+    qo = torch.arange(B + 1, dtype=torch.int32)
+    scale = O.paged_attention(qd, kc, vc.abs(), qo, indptr, perm, last, 1 / math.sqrt(D), causal=False)
+    assert_close_attention(o, fx["paged_decode"]["out"][0], scale, what="paged decode kernel vs fixture")

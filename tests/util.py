@@ -43,11 +43,20 @@ def assert_close_bf16(got: torch.Tensor, ref: torch.Tensor, ulps: float = 1.0, r
     return l2
 
 
-def assert_close_attention(got, ref, abs_scale, rtol: float = 2e-3, what: str = "", rel_l2: float = 2e-3):
+def assert_close_attention(got, ref, abs_scale, rtol: float = 2e-3, what: str = "", rel_l2: float = 3e-3):
     """|got - ref| <= rtol * (sum_j p_j |v_j|) + 1 bf16 ulp(ref), elementwise (see module docstring), AND relative L2
-    error over the tensor <= rel_l2 (the north-star's "1e-3 relative" per implementation: the oracle's and the kernel's
-    independent bf16 roundings of P add in quadrature, plus the final bf16 rounding of o; a regression in the
-    accumulation ladder shows up here long before it trips the forward-error bound).  rel_l2=None disables it.
+    error over the tensor <= rel_l2, so that a regression in the accumulation ladder is visible long before it trips
+    the forward-error bound.  rel_l2=None disables it.
+
+    Why 3e-3 and not the north-star's 1e-3: the reference ladder (FlashInfer) rounds every softmax numerator p_j to bf16
+    (8 significant bits: relative error uniform in +-2^-8/m, m the significand in [1,2) - RMS 2^-8 * sqrt(E[1/m^2]/3) =
+    1.66e-3).  On synthetic N(0,1) V the output o = sum p_j v_j has the same magnitude as the error-carrying sum, so ONE
+    implementation of the reference ladder sits 1.66e-3 (relative L2) from the un-rounded result, and two independent
+    implementations (different tile / split order => different running maxima => independent roundings) sit
+    sqrt(2) * 1.66e-3 = 2.35e-3 apart before the bf16 rounding of o itself.  Measured on B200: this kernel vs the oracle
+    2.1-2.8e-3, FlashInfer's CUDA-core decode (fp32 P) vs the oracle 2.1e-3, this kernel vs FlashInfer's tensor-core
+    decode 0.5-3.3e-3 - the reference's own two decode paths differ from each other by as much.  The single-implementation
+    distance is asserted separately against the fp32-P oracle (test_paged_decode_distance_from_exact_math).
 
     The same bound with rtol = 1e-5 is used for fp32-accumulated dot products (linears): two correct summation orders
     of sum_k x_k w_k differ by O(eps_fp32 * sqrt(K)) * sum_k |x_k w_k|, which is many bf16 ulps of an output that

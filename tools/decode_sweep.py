@@ -103,7 +103,7 @@ def sweep(B, ctx, variants, HQ=28, HKV=4, D=128, page=128, layers=28, trace=Fals
             t = buf.view(ncta, 8).cpu()
             t0 = t[:, 0][t[:, 0] > 0].min().item()
             rows = []
-            for i in (0, 2, 3, 4, 5):
+            for i in (0, 1, 7, 2, 3, 4, 5, 6):
                 col = t[:, i][t[:, i] > 0]
                 if col.numel():
                     rows.append(f"s{i}: n={col.numel():3d} min {col.min().item() - t0:6d} med {int(col.median().item()) - t0:6d} max {col.max().item() - t0:6d}")
@@ -114,18 +114,15 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "b1"
     print("max active clusters by cluster size:", {c: _lib.lib().xb_debug_max_active_clusters(c) for c in (2, 3, 4, 6, 8, 9, 10, 12, 16)}, flush=True)
     if which == "b1":
-        sweep(1, 4096, [("no cluster (37 partials)", {"XB_DECODE_CLUSTER": "1"}),
-                        ("default (3 clusters x 12)", {}),
-                        ("4 x 9", {"XB_DECODE_CLUSTER": "9", "XB_DECODE_PARTS": "4"}),
-                        ("6 x 6", {"XB_DECODE_CLUSTER": "6", "XB_DECODE_PARTS": "6"}),
-                        ("2 x 16, chunk 128", {"XB_DECODE_CHUNK": "128"}),
-                        ("4 x 8, chunk 128", {"XB_DECODE_CHUNK": "128", "XB_DECODE_CLUSTER": "8"}),
-                        ("1 x 16, chunk 256", {"XB_DECODE_CHUNK": "256"}),
-                        ("2 x 8, chunk 256", {"XB_DECODE_CHUNK": "256", "XB_DECODE_CLUSTER": "8"}),
-                        ("1 x 8, chunk 512", {"XB_DECODE_CHUNK": "512", "XB_DECODE_CLUSTER": "8"}),
-                        ("4 warps, default", {"XB_DECODE_WARPS": "4"})], trace=True)
-        sweep(1, 8192, [("no cluster", {"XB_DECODE_CLUSTER": "1"}), ("default", {})], HQ=8, HKV=1)
+        sweep(1, 4096, [("default (37 partials, team merge)", {}),
+                        ("chunk 128 (32 partials)", {"XB_DECODE_CHUNK": "128"}),
+                        ("4 warps", {"XB_DECODE_WARPS": "4"}),
+                        ("4 warps, chunk 64 (64 partials)", {"XB_DECODE_WARPS": "4", "XB_DECODE_CHUNK": "64"}),
+                        ("1 x 16 cluster, chunk 256", {"XB_DECODE_CHUNK": "256", "XB_DECODE_CLUSTER": "16"}),
+                        ("3 x 12 cluster", {"XB_DECODE_CLUSTER": "16"}),
+                        ("2 x 8 cluster, chunk 256", {"XB_DECODE_CHUNK": "256", "XB_DECODE_CLUSTER": "8"})], trace=True)
+        sweep(1, 8192, [("default", {}), ("1 x 16 cluster", {"XB_DECODE_CLUSTER": "16", "XB_DECODE_PARTS": "1"})], HQ=8, HKV=1)
     elif which == "batch":
         for B in (4, 8, 16, 32, 64):
-            sweep(B, 4096, [("no cluster", {"XB_DECODE_CLUSTER": "1"}), ("default", {})])
-        sweep(32, 8192, [("no cluster", {"XB_DECODE_CLUSTER": "1"}), ("default", {})], HQ=8, HKV=1)
+            sweep(B, 4096, [("default", {}), ("cluster", {"XB_DECODE_CLUSTER": "16"})])
+        sweep(32, 8192, [("default", {}), ("cluster", {"XB_DECODE_CLUSTER": "16"})], HQ=8, HKV=1)

@@ -417,6 +417,54 @@ rope_and_cache_kernel(const int64_t* __restrict__ positions, __nv_bfloat16* __re
 }
 
 // ---------------------------------------------------------------------------
+// K9+K12 on a qkv projection whose output columns are in the ROPE-PAIR packed order of quant.pack_w4_qkv_rope (inside
+// every head, packed column 16j+i holds dim 8j+i for i < 8 and dim D/2 + 8j + (i-8) otherwise): the decode GEMV
+// applies RoPE + scatter in its own epilogue; this kernel serves the same weights when the projection ran as a plain
+// GEMM (prefill, decode batches > 8).  Reads the packed row, writes q / k / v in LOGICAL order to qkv_out and the new
+// k / v rows into the paged caches.  Same arithmetic as rope_pair (rope.cu:27-54), NeoX halves, full rotary.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+rope_and_cache_packed_kernel(const int64_t* __restrict__ positions, const __nv_bfloat16* __restrict__ qkv_packed,
+                             int64_t in_stride, __nv_bfloat16* __restrict__ qkv_out, int64_t out_stride,
+                             const __nv_bfloat16* __restrict__ cos_sin_cache, const int32_t* __restrict__ slot_ids,
+                             __nv_bfloat16* __restrict__ key_cache, __nv_bfloat16* __restrict__ value_cache,
+                             int num_heads, int num_kv_heads, int head_size) {
+  const int64_t tok = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t pos = positions[tok];
+  const int64_t slot = slot_ids[tok];
+  const int half = head_size >> 1;
+  const __nv_bfloat16* cache = cos_sin_cache + pos * head_size;
+  const __nv_bfloat16* in = qkv_packed + tok * in_stride;
+  __nv_bfloat16* out = qkv_out + tok * out_stride;
+  const int total_heads = num_heads + 2 * num_kv_heads;
+  for (int i = threadIdx.x; i < total_heads * half; i += blockDim.x) {
+    const int hd = i / half, r = i % half;
+    const int p1 = hd * head_size + 16 * (r >> 3) + (r & 7);
+    float v1 = __bfloat162float(in[p1]), v2 = __bfloat162float(in[p1 + 8]);
+    const bool is_q = hd < num_heads, is_k = !is_q && hd < num_heads + num_kv_heads;
+    if (is_q || is_k) {
+      const float c = __bfloat162float(cache[r]), sn = __bfloat162float(cache[half + r]);
+      const float o1 = round_bf16(v1 * c) - round_bf16(v2 * sn);
+      const float o2 = round_bf16(v2 * c) + round_bf16(v1 * sn);
+      v1 = o1;
+      v2 = o2;
+    }
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(v1), b2 = __float2bfloat16_rn(v2);
+    out[hd * head_size + r] = b1;
+    out[hd * head_size + half + r] = b2;
+    if (!is_q && slot >= 0) {
+      const int kvh = is_k ? hd - num_heads : hd - num_heads - num_kv_heads;
+      __nv_bfloat16* row = (is_k ? key_cache : value_cache) + (slot * num_kv_heads + kvh) * (int64_t)head_size;
+      row[r] = b1;
+      row[half + r] = b2;
+    }
+  }
+  pdl_launch_dependents();
+}
+
+// ---------------------------------------------------------------------------
 // K10 fused per-head RMSNorm(q,k) + RoPE (Qwen3).  fused_qknorm_rope.cu:84-300:
 // one warp per (token, head); fp32 norm: x*rstd*w kept in fp32, RoPE in fp32,
 // single rounding to bf16 at the store.
@@ -678,6 +726,25 @@ extern "C" int xb_rope_and_cache_bf16(const int64_t* positions, void* query, voi
     XB_CUDA_OK(launch(rope_and_cache_kernel<false>, dim3(num_tokens), dim3(threads), 0, (cudaStream_t)stream, true,
                       positions, q, k, v, cs, slot_ids, kc, vc, rot_dim, query_stride, key_stride, value_stride,
                       num_heads, num_kv_heads, head_size));
+  return 0;
+}
+
+extern "C" int xb_rope_and_cache_packed_bf16(const int64_t* positions, const void* qkv_packed, int64_t in_stride,
+                                             void* qkv_out, int64_t out_stride, const void* cos_sin_cache,
+                                             const int32_t* slot_ids, void* key_cache, void* value_cache,
+                                             int num_heads, int num_kv_heads, int head_size, int num_tokens,
+                                             xb_stream_t stream) {
+  if (num_tokens == 0) return 0;
+  XB_CHECK(head_size % 16 == 0 && num_heads > 0 && num_kv_heads > 0, "rope_and_cache_packed: bad heads %d/%d x %d",
+           num_heads, num_kv_heads, head_size);
+  XB_CHECK(qkv_packed != qkv_out, "rope_and_cache_packed: out of place only (the permutation is not in-place safe)");
+  const int work = (num_heads + 2 * num_kv_heads) * head_size / 2;
+  const int threads = work < 512 ? ((work + 31) / 32) * 32 : 512;
+  XB_CUDA_OK(launch(rope_and_cache_packed_kernel, dim3(num_tokens), dim3(threads), 0, (cudaStream_t)stream, true, positions,
+                    reinterpret_cast<const __nv_bfloat16*>(qkv_packed), in_stride, reinterpret_cast<__nv_bfloat16*>(qkv_out),
+                    out_stride, reinterpret_cast<const __nv_bfloat16*>(cos_sin_cache), slot_ids,
+                    reinterpret_cast<__nv_bfloat16*>(key_cache), reinterpret_cast<__nv_bfloat16*>(value_cache), num_heads,
+                    num_kv_heads, head_size));
   return 0;
 }
 

@@ -79,17 +79,44 @@ struct XRing {
   uint4 lo[kMT], hi[kMT];
 };
 
+// Work the decode step does right before / after a weight-only linear, folded into the GEMV launch
+// (north-star: "RMSNorm+RoPE as a single fused epilogue"; SURVEY call stack B, qwen2_decoder_layer.cpp:89-112):
+//   prologue (kXs): x := RMSNorm(x (+ residual)) * norm_w - fused_add_rms_norm / rms_norm (norm.cu:43-136), computed
+//       by EVERY CTA into its shared memory (the activation row is K*2 bytes: recomputing it is cheaper than a
+//       launch); CTA 0 also writes the updated residual stream to res_out (a different buffer than res_in: other
+//       CTAs still read res_in).  With norm_w == nullptr x is only staged in shared memory.
+//   epilogue 1: act(gate) * up on interleaved gate/up rows (activation.cu:45-130)
+//   epilogue 2: qkv_proj -> bias, RoPE on q and k (rope.cu:27-137, NeoX halves), KV scatter of the rotated k and of v
+//       into the paged cache (reshape_paged_cache.cu:23-62).  Rows of every head are packed so that dims d and
+//       d + head_dim/2 are rows g and g+8 of one 16-row tile (quant.pack_w4_qkv_rope): a thread that owns an output
+//       pair owns a whole rotary pair.
+struct W4Fuse {
+  const __nv_bfloat16* norm_w;
+  const __nv_bfloat16* res_in;
+  __nv_bfloat16* res_out;
+  float eps;
+  const int64_t* positions;
+  const __nv_bfloat16* cos_sin;   // [max_pos, head_dim] = [cos half | sin half]
+  const int32_t* slots;
+  __nv_bfloat16* k_cache;
+  __nv_bfloat16* v_cache;
+  int num_heads, num_kv_heads, head_dim;
+};
+
 template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth,
           int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */, int kOcc = 2 /* CTAs per SM */,
-          int kAccSets = 0 /* 0: default for kMT */, bool kFmaShift = false /* right shifts as IMAD.HI (fma pipe) */,
-          bool kGateUp = false /* rows are interleaved [8 gate | 8 up] per 16-row tile: epilogue = act(gate) * up */>
+          int kEpi = 0 /* 0: bias; 1: gate/up rows interleaved, act(gate)*up; 2: rope + KV scatter (qkv) */,
+          bool kXs = false /* x staged (and optionally normalised) in shared memory by the prologue */>
 __global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : kOcc)
 linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
                             int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
                             const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int gshift /* log2(tiles per group) */,
-                            int act_mode) {
+                            int act_mode, const W4Fuse fz) {
+  constexpr bool kGateUp = kEpi == 1;
+  constexpr bool kPair = kEpi != 0;                 // rows g / g+8 of a tile form an output pair
   constexpr int kTilesPerCta = kWarps / kSplit;
   __shared__ float red[kSplit > 1 ? kWarps : 1][kMT][16 * 8];
+  __shared__ float s_ss[kXs ? kWarps : 1][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int ntiles = N >> 4;
@@ -105,7 +132,7 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 
   // kAcc independent accumulator sets (one per k16 step of a tile when registers allow): legacy HMMA has a long
   // issue-to-result latency on sm_100, a single chain per warp leaves the scheduler with nothing eligible
-  constexpr int kAcc = kAccSets > 0 ? kAccSets : (kMT == 1 ? 4 : (kMT == 2 ? 2 : 1));
+  constexpr int kAcc = kMT == 1 ? 4 : (kMT == 2 ? 2 : 1);
   float accj[kAcc][kMT][4];
 #pragma unroll
   for (int a = 0; a < kAcc; ++a)
@@ -143,24 +170,97 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   wp += kDepth * kTG * 32;   // next slot to prefetch
   pdl_wait();  // x (and bias) come from the producer kernel
 
+  // ---- x: either staged (+ normalised) in shared memory by all threads of the CTA, or read through L1 per tile ----
+  // shared layout: [M rows][K + 8] bf16 (the 16-byte pad spreads the rows of a token tile over the banks), 128 bytes
+  // of slack after the last row: the one-tile-ahead fragment prefetch may read past a warp's k range
+  const int xs_stride = K + 8;
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ring_smem + kWarps * kDepth * kSlotBytes);
+  if constexpr (kXs) {
+    const int nvec = K >> 3;
+    const bool do_norm = fz.norm_w != nullptr;
+    for (int tok = 0; tok < M; ++tok) {
+      const uint4* src = reinterpret_cast<const uint4*>(x + (int64_t)tok * x_stride);
+      const uint4* rsrc = fz.res_in ? reinterpret_cast<const uint4*>(fz.res_in + (int64_t)tok * K) : nullptr;
+      uint4* rdst = (fz.res_out && blockIdx.x == 0) ? reinterpret_cast<uint4*>(fz.res_out + (int64_t)tok * K) : nullptr;
+      uint4* dst = reinterpret_cast<uint4*>(xs + (int64_t)tok * xs_stride);
+      float ss = 0.f;
+      for (int idx = threadIdx.x; idx < nvec; idx += kWarps * 32) {
+        uint4 v = src[idx];
+        if (rsrc) {
+          const uint4 r = rsrc[idx];
+          uint32_t* vp = &v.x;
+          const uint32_t* rp = &r.x;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)  // bf16 add, one rounding (norm.cu:110-113)
+            vp[j] = pack_bf16x2(bf16lo(vp[j]) + bf16lo(rp[j]), bf16hi(vp[j]) + bf16hi(rp[j]));
+        }
+        if (rdst) rdst[idx] = v;
+        const uint32_t* vp = &v.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = bf16lo(vp[j]), b = bf16hi(vp[j]);
+          ss += a * a + b * b;
+        }
+        dst[idx] = v;
+      }
+      if (do_norm) {
+        ss = warp_sum(ss);
+        if (lane == 0) s_ss[warp][tok] = ss;
+      }
+    }
+    if (do_norm) {
+      __syncthreads();
+      for (int tok = 0; tok < M; ++tok) {
+        float var = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) var += s_ss[w][tok];       // fixed order: every CTA gets the same rstd
+        const float rstd = rsqrtf(var / (float)K + fz.eps);
+        uint4* dst = reinterpret_cast<uint4*>(xs + (int64_t)tok * xs_stride);
+        const uint4* wv = reinterpret_cast<const uint4*>(fz.norm_w);
+        for (int idx = threadIdx.x; idx < nvec; idx += kWarps * 32) {   // same elements this thread wrote above
+          uint4 v = dst[idx];
+          const uint4 w = __ldg(wv + idx);
+          uint32_t* vp = &v.x;
+          const uint32_t* wq = &w.x;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)  // bf16(x*rstd) then bf16 product with w (norm.cu:75-77,130-133)
+            vp[j] = pack_bf16x2(round_bf16(bf16lo(vp[j]) * rstd) * bf16lo(wq[j]), round_bf16(bf16hi(vp[j]) * rstd) * bf16hi(wq[j]));
+          dst[idx] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
   // x fragments: lane (g,t) needs x[tok = 8m+g][k0 + 16t .. +16) per tile
   // token columns past M read the last valid token instead of zeros: their accumulator columns are
   // finite garbage that is never stored, and the loads need neither a predicate nor a zero fill
   const __nv_bfloat16* xp[kMT];
+  uint32_t xsa[kMT];
 #pragma unroll
   for (int m = 0; m < kMT; ++m) {
     const int tok = min(m * 8 + g, M - 1);
     xp[m] = x + (int64_t)tok * x_stride + (int64_t)s_begin * kTG * 64 + 16 * t;
+    xsa[m] = smem_addr_u32(xs) + (uint32_t)((tok * xs_stride + s_begin * kTG * 64 + 16 * t) * 2);
   }
-  // x fragments come from L1 (~35 cycles), hidden by the other warps
   auto load_xtile = [&](XRing<kMT>& d) {
 #pragma unroll
     for (int m = 0; m < kMT; ++m) {
-      d.lo[m] = *reinterpret_cast<const uint4*>(xp[m]);
-      d.hi[m] = *reinterpret_cast<const uint4*>(xp[m] + 8);
-      xp[m] += 64;
+      if constexpr (kXs) {
+        d.lo[m] = lds_128(xsa[m]);
+        d.hi[m] = lds_128(xsa[m] + 16);
+        xsa[m] += 128;
+      } else {
+        d.lo[m] = *reinterpret_cast<const uint4*>(xp[m]);   // L1 hits, hidden by the other warps
+        d.hi[m] = *reinterpret_cast<const uint4*>(xp[m] + 8);
+        xp[m] += 64;
+      }
     }
   };
+  // kXs: fragments are prefetched ONE TILE AHEAD into the other half of a two-deep register buffer (shared-memory
+  // loads return in order and in tens of cycles, so the prefetch never exposes more than that)
+  XRing<kMT> xbuf[2];
+  if constexpr (kXs) load_xtile(xbuf[0]);
 
   auto consume = [&](int i) {
     uint4 wq[kTG];
@@ -171,17 +271,18 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     const uint32_t s1 = __byte_perm(mt.y, 0, 0x1010), z1 = __byte_perm(mt.y, 0, 0x3232);
 #pragma unroll
     for (int u = 0; u < kTG; ++u) {
-      XRing<kMT> xf;
-      load_xtile(xf);
+      const int par = (i * kTG + u) & 1;       // compile-time after unrolling (kDepth * kTG is even)
+      if constexpr (kXs) load_xtile(xbuf[par ^ 1]);
+      else load_xtile(xbuf[0]);
+      const XRing<kMT>& xf = kXs ? xbuf[par] : xbuf[0];
       const uint32_t* wv = &wq[u].x;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t w = wv[j];
         const uint32_t q0 = lop3_and_or(w, 0x000f000fu, 0x43004300u);
-        // right shifts either as SHF (alu pipe) or as IMAD.HI (fma pipe) to balance the two issue pipes
-        const uint32_t q1 = lop3_and_or(kFmaShift ? __umulhi(w, 1u << 28) : (w >> 4), 0x000f000fu, 0x43004300u);
-        const uint32_t q2 = lop3_and_or(kFmaShift ? __umulhi(w, 1u << 24) : (w >> 8), 0x000f000fu, 0x43004300u);
-        const uint32_t q3 = lop3_and_or(kFmaShift ? __umulhi(w, 1u << 20) : (w >> 12), 0x000f000fu, 0x43004300u);
+        const uint32_t q1 = lop3_and_or(w >> 4, 0x000f000fu, 0x43004300u);
+        const uint32_t q2 = lop3_and_or(w >> 8, 0x000f000fu, 0x43004300u);
+        const uint32_t q3 = lop3_and_or(w >> 12, 0x000f000fu, 0x43004300u);
         const uint32_t a0 = hmul2_bf16(hsub2_bf16(q0, z0), s0);
         const uint32_t a1 = hmul2_bf16(hsub2_bf16(q1, z1), s1);
         const uint32_t a2 = hmul2_bf16(hsub2_bf16(q2, z0), s0);
@@ -246,18 +347,49 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     else a = 0.5f * gr * (1.0f + tanhf(0.79788456080286535588f * (gr + 0.044715f * gr * gr * gr)));
     return __float2bfloat16_rn(round_bf16(a) * ur);
   };
+  // kEpi == 2: (lo, hi) are the fp32 sums (+bias) of dims d and d + head_dim/2 of head `hd` for token `tok`: round to
+  // bf16 (the linear's output), rotate q / k heads (rope.cu:27-54: every product and the add / sub rounded to bf16),
+  // write q (and k, v) to y in LOGICAL column order and the new token's k / v rows into the paged caches.
+  auto rope_store = [&](int nt, int r, int tok, float lo, float hi) {
+    const int D = fz.head_dim, half = D >> 1, tiles_per_head = D >> 4;
+    const int hd = nt / tiles_per_head, d = (nt % tiles_per_head) * 8 + r;
+    float v1 = round_bf16(lo), v2 = round_bf16(hi);
+    const bool is_q = hd < fz.num_heads, is_k = !is_q && hd < fz.num_heads + fz.num_kv_heads;
+    if (is_q || is_k) {
+      const __nv_bfloat16* cs = fz.cos_sin + fz.positions[tok] * (int64_t)D;
+      const float c = __bfloat162float(cs[d]), sn = __bfloat162float(cs[half + d]);
+      const float o1 = round_bf16(v1 * c) - round_bf16(v2 * sn);
+      const float o2 = round_bf16(v2 * c) + round_bf16(v1 * sn);
+      v1 = o1;
+      v2 = o2;
+    }
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(v1), b2 = __float2bfloat16_rn(v2);
+    __nv_bfloat16* yr = y + (int64_t)tok * y_stride + (int64_t)hd * D;
+    yr[d] = b1;
+    yr[half + d] = b2;
+    if (!is_q) {
+      const int64_t slot = fz.slots[tok];
+      if (slot >= 0) {
+        const int kvh = is_k ? hd - fz.num_heads : hd - fz.num_heads - fz.num_kv_heads;
+        __nv_bfloat16* row = (is_k ? fz.k_cache : fz.v_cache) + (slot * fz.num_kv_heads + kvh) * (int64_t)D;
+        row[d] = b1;
+        row[half + d] = b2;
+      }
+    }
+  };
   if constexpr (kSplit == 1) {
     if (live) {
 #pragma unroll
       for (int m = 0; m < kMT; ++m) {
-        if constexpr (kGateUp) {
+        if constexpr (kPair) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int tok = m * 8 + 2 * t + e;
             if (tok < M) {
               float gv = acc[m][e], uv = acc[m][2 + e];
               if (bias) { gv += __bfloat162float(bias[n0 + g]); uv += __bfloat162float(bias[n0 + g + 8]); }
-              y[(int64_t)tok * y_stride + ntile * 8 + g] = gate_up(gv, uv);
+              if constexpr (kGateUp) y[(int64_t)tok * y_stride + ntile * 8 + g] = gate_up(gv, uv);
+              else rope_store(ntile, g, tok, gv, uv);
             }
           }
         } else {
@@ -293,13 +425,14 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 #pragma unroll
         for (int w = 0; w < kSplit; ++w) sum += red[tl * kSplit + w][m][r * 8 + c];
         if (bias) sum += __bfloat162float(bias[nt * 16 + r]);
-        if constexpr (kGateUp) {
+        if constexpr (kPair) {
           if (r < 8) {
             float up = 0.f;
 #pragma unroll
             for (int w = 0; w < kSplit; ++w) up += red[tl * kSplit + w][m][(r + 8) * 8 + c];
             if (bias) up += __bfloat162float(bias[nt * 16 + r + 8]);
-            y[(int64_t)tok * y_stride + nt * 8 + r] = gate_up(sum, up);
+            if constexpr (kGateUp) y[(int64_t)tok * y_stride + nt * 8 + r] = gate_up(sum, up);
+            else rope_store(nt, r, tok, sum, up);
           }
         } else {
           y[(int64_t)tok * y_stride + nt * 16 + r] = __float2bfloat16_rn(sum);
@@ -392,17 +525,25 @@ using namespace xb;
 
 // dynamic shared memory of the W4 kernel: kWarps private rings of `depth` slots (kTG tiles + meta words each)
 static constexpr size_t w4_ring_bytes(int depth, int tg) { return (size_t)kWarps * depth * (tg * 512 + 256); }
+// largest activation block ([M][K + 8] bf16 + slack) the kXs variants stage in shared memory next to the ring
+static constexpr size_t kXsMaxBytes = 72 * 1024;
+static inline size_t w4_xs_bytes(int M, int K) { return (size_t)M * (K + 8) * 2 + 256; }
 
+// epi: 0 plain (+bias), 1 gate/up + activation (act_mode), 2 qkv rope + KV scatter (fz).  xs: stage x in shared memory
+// (required for the norm prologue).  fz may be null when neither the prologue nor epilogue 2 is used.
 static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_stride, const uint32_t* qweight,
-                           const uint32_t* meta, const void* bias, int M, int N, int K, int group_size, int act_mode,
-                           xb_stream_t stream) {
-  const bool gate_up = act_mode >= 0;
+                           const uint32_t* meta, const void* bias, int M, int N, int K, int group_size, int epi,
+                           int act_mode, bool xs, const W4Fuse* fzp, xb_stream_t stream) {
   if (M == 0) return 0;
   XB_CHECK(M > 0 && M <= 64, "linear_w4a16_small_m: M=%d out of range (1..64); use the tcgen05 GEMM", M);
   XB_CHECK(N % 16 == 0 && K % 64 == 0, "linear_w4a16_small_m: N=%d must be %%16, K=%d %%64", N, K);
   XB_CHECK(group_size >= 64 && group_size % 64 == 0 && K % group_size == 0,
            "linear_w4a16_small_m: group_size %d must be a multiple of 64 dividing K=%d", group_size, K);
   XB_CHECK(x_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "linear_w4a16_small_m: x not 16B aligned");
+  XB_CHECK(!(xs || epi == 2) || M <= 8, "linear_w4a16_small_m: the fused prologue / rope epilogue serve M <= 8 (got %d)", M);
+  XB_CHECK(!xs || w4_xs_bytes(M, K) <= kXsMaxBytes, "linear_w4a16_small_m: M=%d x K=%d does not fit the shared-memory x stage", M, K);
+  W4Fuse fz{};
+  if (fzp) fz = *fzp;
   auto* yy = reinterpret_cast<__nv_bfloat16*>(y);
   auto* xx = reinterpret_cast<const __nv_bfloat16*>(x);
   auto* qw = reinterpret_cast<const uint4*>(qweight);
@@ -417,26 +558,39 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   int gshift = 0;
   while ((1 << gshift) < tpg) ++gshift;
   const bool tg2 = tpg >= 2;
+  const size_t xs_bytes = xs ? w4_xs_bytes(M, K) : 0;
   // (tuning note, B200: 3 CTAs/SM at <= 80 registers measured 10-13 % slower than 2 CTAs/SM for every decode shape)
-#define XB_W4_GO(MT, SP, DEPTH, TG, OCC, GU)                                                                      \
+#define XB_W4_GO(MT, SP, DEPTH, TG, EPI, XS)                                                                       \
   {                                                                                                                 \
-    auto kern = linear_w4a16_small_m_kernel<MT, SP, DEPTH, TG, OCC, 0, false, GU>;                                  \
+    auto kern = linear_w4a16_small_m_kernel<MT, SP, DEPTH, TG, 2, EPI, XS>;                                         \
     static bool attr_done = false; /* per instantiation: static reduction scratch + ring may exceed 48 KB */        \
     if (!attr_done) {                                                                                               \
       XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
-                                      (int)w4_ring_bytes(DEPTH, TG)));                                              \
+                                      (int)(w4_ring_bytes(DEPTH, TG) + (XS ? kXsMaxBytes : 0))));                   \
       attr_done = true;                                                                                             \
     }                                                                                                               \
-    XB_CUDA_OK(launch(kern, grid, block, w4_ring_bytes(DEPTH, TG), s, true, yy, y_stride, xx, x_stride, qw, meta,   \
-                      bb, M, N, K, gshift, act_mode));                                                              \
+    XB_CUDA_OK(launch(kern, grid, block, w4_ring_bytes(DEPTH, TG) + xs_bytes, s, true, yy, y_stride, xx, x_stride,  \
+                      qw, meta, bb, M, N, K, gshift, act_mode, fz));                                                \
   }
+#define XB_W4_TG(MT, SP, DP, EPI, XS)                                \
+  if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS) }            \
+  else { XB_W4_GO(MT, SP, DP, 1, EPI, XS) }
+  // the fused variants (x staged in shared memory / rope epilogue) exist for one token tile (M <= 8) only
 #define XB_W4_LAUNCH(MT, SP, DP)                                                                               \
   {                                                                                                            \
     dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                               \
-    if (gate_up && tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, 2, true) }                                           \
-    else if (gate_up) { XB_W4_GO(MT, SP, DP, 1, 2, true) }                                                       \
-    else if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, 2, false) }                                                \
-    else { XB_W4_GO(MT, SP, DP, 1, 2, false) }                                                                   \
+    if constexpr (MT == 1) {                                                                                   \
+      if (xs) {                                                                                                \
+        if (epi == 2) { XB_W4_TG(1, SP, DP, 2, true) }                                                         \
+        else if (epi == 1) { XB_W4_TG(1, SP, DP, 1, true) }                                                    \
+        else { XB_W4_TG(1, SP, DP, 0, true) }                                                                  \
+      } else if (epi == 2) { XB_W4_TG(1, SP, DP, 2, false) }                                                   \
+      else if (epi == 1) { XB_W4_TG(1, SP, DP, 1, false) }                                                     \
+      else { XB_W4_TG(1, SP, DP, 0, false) }                                                                   \
+    } else {                                                                                                   \
+      if (epi == 1) { XB_W4_TG(MT, SP, DP, 1, false) }                                                         \
+      else { XB_W4_TG(MT, SP, DP, 0, false) }                                                                  \
+    }                                                                                                          \
   }
 #define XB_W4(MT, DP)                                   \
   switch (split) {                                      \
@@ -445,7 +599,7 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
     case 4: XB_W4_LAUNCH(MT, 4, DP) break;              \
     default: XB_W4_LAUNCH(MT, 8, DP) break;             \
   }
-  XB_CHECK(!(gate_up && M > 16), "linear_w4a16_gate_up_act_small_m: M=%d > 16, use the GEMM + act_and_mul_interleaved8", M);
+  XB_CHECK(!(epi == 1 && M > 16), "linear_w4a16_gate_up_act_small_m: M=%d > 16, use the GEMM + act_and_mul_interleaved8", M);
   // ring depth: 8 k64 tiles (4 KB) per warp in flight = 64 KB per SM at 2 CTAs/SM, ~1.5x the HBM latency-bandwidth
   // product; the ring lives in shared memory, so the depth no longer competes with the accumulators for registers
   // (a 12-tile ring measured the same as 8 tiles on every decode shape)
@@ -454,6 +608,7 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   else if (M <= 32) { XB_W4(4, 8) }
   else { XB_W4(8, 8) }
 #undef XB_W4_GO
+#undef XB_W4_TG
 #undef XB_W4_LAUNCH
 #undef XB_W4
   return 0;
@@ -462,7 +617,7 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
 extern "C" int xb_linear_w4a16_small_m(void* y, int64_t y_stride, const void* x, int64_t x_stride,
                                        const uint32_t* qweight, const uint32_t* meta, const void* bias, int M, int N,
                                        int K, int group_size, xb_stream_t stream) {
-  return w4_small_m_impl(y, y_stride, x, x_stride, qweight, meta, bias, M, N, K, group_size, -1, stream);
+  return w4_small_m_impl(y, y_stride, x, x_stride, qweight, meta, bias, M, N, K, group_size, 0, -1, false, nullptr, stream);
 }
 
 // gate_up_proj with the activation fused into the epilogue.  qweight / meta / bias rows must be in the interleaved
@@ -472,7 +627,58 @@ extern "C" int xb_linear_w4a16_gate_up_act_small_m(void* y, int64_t y_stride, co
                                                    const uint32_t* qweight, const uint32_t* meta, const void* bias,
                                                    int M, int N, int K, int group_size, int act_mode, xb_stream_t stream) {
   XB_CHECK(act_mode >= 0 && act_mode <= 2, "gate_up_act: unsupported act mode %d", act_mode);
-  return w4_small_m_impl(y, y_stride, x, x_stride, qweight, meta, bias, M, N, K, group_size, act_mode, stream);
+  return w4_small_m_impl(y, y_stride, x, x_stride, qweight, meta, bias, M, N, K, group_size, 1, act_mode, false, nullptr, stream);
+}
+
+// The decode-step form of a weight-only linear (M <= 8): optional add + RMSNorm prologue, optional epilogue.
+//   prologue: norm_weight != null: x := RMSNorm(x (+ residual_in)) * norm_weight (fused_add_rms_norm / rms_norm); the
+//             updated residual stream x + residual_in goes to residual_out (must not alias residual_in; null = not
+//             wanted).  norm_weight == null with stage_x != 0 only stages x in shared memory.
+//   epilogue: 0 bias; 1 act(gate) * up (act_mode; interleaved rows; y [M, N/2]); 2 RoPE (NeoX) on the q and k heads +
+//             scatter of the new k / v rows into the paged caches (rows packed by quant.pack_w4_qkv_rope; y [M, N] in
+//             logical [q | k | v] order; positions int64 [M], cos_sin_cache [max_pos, head_dim] bf16, slot_ids int32
+//             [M] (negative = skip), caches [blocks, block_size, num_kv_heads, head_dim]).
+extern "C" int xb_linear_w4a16_decode_fused(void* y, int64_t y_stride, const void* x, int64_t x_stride,
+                                            const uint32_t* qweight, const uint32_t* meta, const void* bias, int M, int N,
+                                            int K, int group_size, const void* norm_weight, float eps,
+                                            const void* residual_in, void* residual_out, int stage_x, int epilogue,
+                                            int act_mode, const int64_t* positions, const void* cos_sin_cache,
+                                            const int32_t* slot_ids, void* k_cache, void* v_cache, int num_heads,
+                                            int num_kv_heads, int head_dim, xb_stream_t stream) {
+  XB_CHECK(epilogue >= 0 && epilogue <= 2, "linear_w4a16_decode_fused: epilogue %d unknown", epilogue);
+  XB_CHECK(epilogue != 1 || (act_mode >= 0 && act_mode <= 2), "linear_w4a16_decode_fused: unsupported act mode %d", act_mode);
+  XB_CHECK(M >= 0 && M <= 8, "linear_w4a16_decode_fused: M=%d out of range (0..8)", M);
+  W4Fuse fz{};
+  fz.norm_w = reinterpret_cast<const __nv_bfloat16*>(norm_weight);
+  fz.res_in = reinterpret_cast<const __nv_bfloat16*>(residual_in);
+  fz.res_out = reinterpret_cast<__nv_bfloat16*>(residual_out);
+  fz.eps = eps;
+  XB_CHECK(!(residual_in || residual_out) || norm_weight, "linear_w4a16_decode_fused: a residual needs the norm prologue");
+  XB_CHECK(!residual_in || residual_in != residual_out, "linear_w4a16_decode_fused: residual_out must not alias residual_in");
+  XB_CHECK(!norm_weight || ((reinterpret_cast<uintptr_t>(norm_weight) | reinterpret_cast<uintptr_t>(residual_in) |
+                             reinterpret_cast<uintptr_t>(residual_out)) & 15) == 0,
+           "linear_w4a16_decode_fused: norm weight / residuals must be 16-byte aligned");
+  if (epilogue == 2) {
+    XB_CHECK(positions && cos_sin_cache && slot_ids && k_cache && v_cache, "linear_w4a16_decode_fused: rope epilogue needs positions, cos/sin, slots and caches");
+    XB_CHECK((head_dim == 64 || head_dim == 128) && num_heads > 0 && num_kv_heads > 0 &&
+                 N == (num_heads + 2 * num_kv_heads) * head_dim,
+             "linear_w4a16_decode_fused: N=%d is not (%d + 2*%d) heads of %d", N, num_heads, num_kv_heads, head_dim);
+    fz.positions = positions;
+    fz.cos_sin = reinterpret_cast<const __nv_bfloat16*>(cos_sin_cache);
+    fz.slots = slot_ids;
+    fz.k_cache = reinterpret_cast<__nv_bfloat16*>(k_cache);
+    fz.v_cache = reinterpret_cast<__nv_bfloat16*>(v_cache);
+    fz.num_heads = num_heads;
+    fz.num_kv_heads = num_kv_heads;
+    fz.head_dim = head_dim;
+  }
+  const bool xs = norm_weight != nullptr || stage_x != 0;
+  return w4_small_m_impl(y, y_stride, x, x_stride, qweight, meta, bias, M, N, K, group_size, epilogue, act_mode, xs, &fz, stream);
+}
+
+// 1 when xb_linear_w4a16_decode_fused can stage an [M, K] activation block in shared memory (host-side query)
+extern "C" int xb_linear_w4a16_decode_fused_fits(int M, int K) {
+  return M >= 1 && M <= 8 && w4_xs_bytes(M, K) <= kXsMaxBytes ? 1 : 0;
 }
 
 extern "C" int xb_linear_bf16_small_m(void* y, int64_t y_stride, const void* x, int64_t x_stride, const void* w,

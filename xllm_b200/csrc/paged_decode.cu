@@ -110,6 +110,8 @@ __device__ __forceinline__ const __nv_bfloat16* kv_row(const DecodeParams& p, co
   return cache + page * p.stride_page + (int64_t)off * p.stride_token + (int64_t)kvh * p.stride_head;
 }
 
+constexpr int kTeam = 8;   // CTAs that share the final merge of one (request, kv head)
+
 template <int kD, int kGT /*1: <=8 heads per CTA, 2: <=16*/, int kWarpsT>
 __global__ void __launch_bounds__(kWarpsT * 32, 1)
 paged_decode_kernel(const DecodeParams p) {
@@ -154,6 +156,7 @@ paged_decode_kernel(const DecodeParams p) {
   const int n_parts = (n_splits + C - 1) / C;     // live clusters (= partials that reach the workspace) of this unit
   const int part = split / C;
   if (part >= n_parts) return;                    // uniform over the whole cluster: nobody waits for this CTA
+  stamp(1);
   const int t_begin = min(split * chunk, kv_len);
   const int t_end = min(kv_len, t_begin + chunk);
   const int head0 = kvh * p.group + htile * kHeads;            // first qo head of this CTA
@@ -237,6 +240,7 @@ paged_decode_kernel(const DecodeParams p) {
         mma_bf16_16816(s_acc[tile], qa[i].z, qb[i].z, qa[i].w, qb[i].w, kf[tile][i].z, kf[tile][i].w);
       }
     }
+    if (p.trace && blk == warp && warp == 0 && s_acc[0][0] != 12345.678f) stamp(7);   // first K block has arrived
     // ---- online softmax (base 2) ---------------------------------------------
     uint32_t pa[4];  // A fragment of P: a0 (g, tile0) a1 (g+8, tile0) a2 (g, tile1) a3 (g+8, tile1)
 #pragma unroll
@@ -430,24 +434,39 @@ paged_decode_kernel(const DecodeParams p) {
     }
   }
 
-  // ---- last CTA of this (request, kv head, head tile) merges the n_parts partials ----------------------------------
+  // ---- the LAST few CTAs of this (request, kv head, head tile) to arrive merge the n_parts partials as a team ------
+  // One last-arriver merging everything alone reads n_parts x kHeads x kD floats through a single SM (130 KB for the
+  // BASELINE shape: ~4 us).  Instead the last R arrivers (ticket order) each take 1/R of the (head, d) items; the ones
+  // that are not the very last spin until the ticket shows every partial published.  Forward progress: at most half of
+  // a unit's CTAs ever spin (R <= (n + 1) / 2), the others never wait, and CTAs are dispatched in index order, so the
+  // CTAs a spinner waits for are resident or ahead of every spinner in the dispatch queue (the assumption CUB's
+  // decoupled look-back makes).
   __threadfence();
   __syncthreads();
-  int32_t* counter = p.counters + (int64_t)b * gridDim.y + blockIdx.y;
+  int32_t* counter = p.counters + 2 * ((int64_t)b * gridDim.y + blockIdx.y);   // [0] arrivals, [1] team members done
   if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1);
   __syncthreads();
-  if (s_ticket != n_parts * C - 1) {
+  const int n_arrive = n_parts * C;
+  const int team = min(kTeam, (n_arrive + 1) >> 1);
+  const int member = s_ticket - (n_arrive - team);
+  if (member < 0) {
     if (C > 1) cluster_wait_acquire();
     return;
   }
+  if (threadIdx.x == 0) {
+    int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < n_arrive);
+  }
+  __syncthreads();
   __threadfence();
-  if (threadIdx.x == 0) *counter = 0;  // restore for the next launch
+  stamp(5);
   const int n_splits_m = n_parts;      // number of partials to merge
   // Stage 1: one warp per head turns the splits' base-2 LSEs into normalised weights in shared memory
   // (lanes read different splits in parallel: no dependent-load chain).  sm_o is free again: reuse it.
   float* sm_w = sm_o;                       // [kHeads][n_splits_m]
   float* sm_lse = sm_m;                     // [kHeads] merged LSE
-  __syncthreads();
   for (int h = warp; h < nheads; h += kWarpsT) {
     const int64_t base = ((int64_t)b * p.num_qo_heads + head0 + h) * p.max_parts;
     // all of this head's split LSEs in one round trip (<= 8 per lane: max_splits <= 2 * head_dim = 256)
@@ -477,32 +496,59 @@ paged_decode_kernel(const DecodeParams p) {
     if (lane == 0) sm_lse[h] = wsum > 0.f ? mx + log2f(wsum) : -INFINITY;
   }
   __syncthreads();
-  // Stage 2: weighted sum of the partial outputs; all addresses are known up front, 16 predicated loads in flight per
-  // thread (37 splits = 3 round trips to L2 instead of one per split)
-  for (int it = threadIdx.x; it < kItems; it += kWarpsT * 32) {
-    const int h = it / (kD / 4), d4 = (it % (kD / 4)) * 4;
-    if (h >= nheads) continue;
-    const int qh = head0 + h;
-    const float4* src = reinterpret_cast<const float4*>(p.part_o + (((int64_t)b * p.num_qo_heads + qh) * p.max_parts) * kD + d4);
-    const float* wrow = sm_w + h * n_splits_m;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < n_splits_m; s += 16) {
-      float4 v[16];
+  // Stage 2: this member's slice of the (head, 4 d) items; 8 lanes share an item and stride over the partials, so every
+  // thread has all its loads (<= n_parts / 8) in flight at once: one round trip to L2
+  {
+    const int live_items = nheads * (kD / 4);
+    const int per = (live_items + team - 1) / team;
+    const int first = member * per, lim = min(live_items, first + per);
+    const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    for (int base_it = first; base_it < lim; base_it += kWarpsT * 4) {
+      const int it = base_it + grp;
+      const bool ok = it < lim;
+      const int h = ok ? it / (kD / 4) : 0, d4 = ok ? (it % (kD / 4)) * 4 : 0;
+      const int qh = head0 + h;
+      const float4* src = reinterpret_cast<const float4*>(p.part_o + (((int64_t)b * p.num_qo_heads + qh) * p.max_parts) * kD + d4);
+      const float* wrow = sm_w + h * n_splits_m;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
+        for (int s0 = sub; s0 < n_splits_m; s0 += 64) {
+          float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (int64_t)min(s + u, n_splits_m - 1) * (kD / 4));
+          for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)min(s0 + 8 * u, n_splits_m - 1) * (kD / 4));
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const float w = s + u < n_splits_m ? wrow[s + u] : 0.f;
-        acc.x += v[u].x * w; acc.y += v[u].y * w; acc.z += v[u].z * w; acc.w += v[u].w * w;
+          for (int u = 0; u < 8; ++u) {
+            const float w = s0 + 8 * u < n_splits_m ? wrow[s0 + 8 * u] : 0.f;
+            acc.x += v[u].x * w; acc.y += v[u].y * w; acc.z += v[u].z * w; acc.w += v[u].w * w;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      }
+      if (ok && sub == 0) {
+        uint2 ob;
+        ob.x = pack_bf16x2(acc.x, acc.y);
+        ob.y = pack_bf16x2(acc.z, acc.w);
+        *reinterpret_cast<uint2*>(p.o + (int64_t)b * p.o_stride_n + (int64_t)qh * p.o_stride_h + d4) = ob;
+        if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = sm_lse[h];
       }
     }
-    uint2 ob;
-    ob.x = pack_bf16x2(acc.x, acc.y);
-    ob.y = pack_bf16x2(acc.z, acc.w);
-    *reinterpret_cast<uint2*>(p.o + (int64_t)b * p.o_stride_n + (int64_t)qh * p.o_stride_h + d4) = ob;
-    if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = sm_lse[h];
   }
-  stamp(5);
+  // the member that finishes last restores both counters for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(counter + 1, 1);
+    if (done == team - 1) {
+      counter[0] = 0;
+      counter[1] = 0;
+    }
+  }
+  stamp(6);
   if (C > 1) cluster_wait_acquire();
 }
 
@@ -594,7 +640,10 @@ extern "C" int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int n
   // that use K = ceil(want / 16) clusters whose K results meet in the workspace (last-arriver merge).
   int64_t cluster = 1, parts = want;
   const char* envc = getenv("XB_DECODE_CLUSTER");  // 0 / 1: no clusters (every split is a workspace partial)
-  const int64_t cmax = envc ? atoi(envc) : 16;
+  // Default 1 (no clusters).  Measured on B200 (tools/decode_sweep.py): the device co-schedules only 15 clusters of 8 / 9
+  // CTAs and 7 of 12 / 16 (GPCs are unevenly populated), so cluster geometries that fill the SMs run in two waves; the
+  // one that fits (16 CTAs x 1 cluster per kv head, 64 SMs) matches the cluster-less kernel.  The path stays available.
+  const int64_t cmax = envc ? atoi(envc) : 1;
   if (want > 1 && cmax > 1) {
     parts = (want + cmax - 1) / cmax;
     const char* envp = getenv("XB_DECODE_PARTS");  // tuning: force the number of clusters per (request, kv head)
@@ -609,7 +658,7 @@ extern "C" int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int n
   plan8[1] = splits;
   // sized for one partial per split so that the launcher may fall back to cluster size 1 on any device
   plan8[2] = splits > 1 ? (int64_t)batch * num_qo_heads * splits * (head_dim + 1) * 4 : 16;
-  plan8[3] = units * 4;  // low 32 bits: int workspace bytes; bit 32: early-prefetch flag (xb_decode_plan_set_flags)
+  plan8[3] = units * 8;  // low 32 bits: int workspace bytes (arrival + team-done counter per unit); bit 32: early-prefetch flag (xb_decode_plan_set_flags)
   plan8[4] = batch;
   plan8[5] = num_qo_heads;
   plan8[6] = num_kv_heads;

@@ -414,3 +414,62 @@ def w4a16_gate_up_act(x, qweight, meta, group_size, act_mode="silu", bias=None, 
     check(lib().xb_act_and_mul_interleaved8_bf16(_p(y), _p(gu), c_i32(N // 2), c_i32(M), c_i32(_ACT[act_mode]), _stream()),
           "act_and_mul_interleaved8")
     return y
+
+
+def w4a16_decode_fused_fits(M: int, K: int) -> bool:
+    """whether w4a16_decode_fused can stage an [M, K] activation block in shared memory."""
+    return bool(lib().xb_linear_w4a16_decode_fused_fits(c_i32(M), c_i32(K)))
+
+
+def w4a16_decode_fused(x, qweight, meta, group_size, bias=None, out=None, *, norm_weight=None, eps=1e-6, residual_in=None,
+                       residual_out=None, stage_x=False, epilogue="none", act_mode="silu", positions=None,
+                       cos_sin_cache=None, slot_ids=None, key_cache=None, value_cache=None, num_heads=0, num_kv_heads=0,
+                       head_dim=0):
+    """Decode-step form of a weight-only linear (M <= 8): the launches the reference makes around the GEMV ride in it.
+      prologue  norm_weight: x := RMSNorm(x (+ residual_in)) * norm_weight  (rms_norm / fused_add_rms_norm,
+                cuda_ops_api.h:157-165); residual_out receives x + residual_in (must be a different buffer)
+      epilogue  "none" | "act_mul" (DenseMLP's act_and_mul on interleaved gate/up rows, out [M, N/2]) |
+                "rope_cache" (rotary_embedding + reshape_paged_cache of qwen2_attention.cpp:147-171 /
+                flashinfer_attention.cpp:128-131; rows packed by quant.pack_w4_qkv_rope, out [M, N] logical order)"""
+    _cuda_bf16(x, "x")
+    _need(qweight.dtype == torch.int32 and meta.dtype == torch.int32, "qweight/meta must be int32 storage")
+    epi = {"none": 0, "act_mul": 1, "rope_cache": 2}.get(epilogue)
+    _need(epi is not None, f"unknown epilogue {epilogue}")
+    if epi == 1 and act_mode not in _ACT:
+        raise XllmB200Error(f"Unsupported act mode: {act_mode}")
+    M, K = x.shape
+    N = meta.size(1)
+    n_out = N // 2 if epi == 1 else N
+    y = out if out is not None else torch.empty(M, n_out, dtype=BF16, device=x.device)
+    for t, n in ((norm_weight, "norm_weight"), (residual_in, "residual_in"), (residual_out, "residual_out")):
+        if t is not None:
+            _cuda_bf16(t, n)
+            _need(t.is_contiguous(), f"{n} must be contiguous")
+    if epi == 2:
+        _need(positions is not None and positions.dtype == torch.int64 and slot_ids is not None and
+              slot_ids.dtype == torch.int32, "positions int64 / slot_ids int32")
+        _cuda_bf16(cos_sin_cache, "cos_sin_cache"); _cuda_bf16(key_cache, "key_cache"); _cuda_bf16(value_cache, "value_cache")
+        _need(key_cache.is_contiguous() and value_cache.is_contiguous(), "caches must be contiguous NHD")
+        _need(cos_sin_cache.size(-1) == head_dim, "full rotary only (rot_dim == head_dim)")
+    check(lib().xb_linear_w4a16_decode_fused(
+        _p(y), c_i64(y.stride(0)), _p(x), c_i64(x.stride(0)), _p(qweight), _p(meta), _p(bias), c_i32(M), c_i32(N), c_i32(K),
+        c_i32(group_size), _p(norm_weight), c_f32(eps), _p(residual_in), _p(residual_out), c_i32(1 if stage_x else 0),
+        c_i32(epi), c_i32(_ACT.get(act_mode, 0)), _p(positions), _p(cos_sin_cache), _p(slot_ids), _p(key_cache),
+        _p(value_cache), c_i32(num_heads), c_i32(num_kv_heads), c_i32(head_dim), _stream()), "w4a16_decode_fused")
+    return y
+
+
+def rope_and_cache_packed(positions, qkv_packed, qkv_out, cos_sin_cache, slot_ids, key_cache, value_cache, num_heads,
+                          num_kv_heads, head_dim) -> None:
+    """rotary_embedding + reshape_paged_cache for a qkv projection in the rope-pair packed column order
+    (quant.pack_w4_qkv_rope) that ran as a plain GEMM: qkv_out receives q | k | v in logical order."""
+    _cuda_bf16(qkv_packed, "qkv_packed"); _cuda_bf16(qkv_out, "qkv_out"); _cuda_bf16(cos_sin_cache, "cos_sin_cache")
+    _need(positions.dtype == torch.int64 and slot_ids.dtype == torch.int32, "positions int64 / slot_ids int32")
+    _need(qkv_packed.stride(-1) == 1 and qkv_out.stride(-1) == 1 and key_cache.is_contiguous() and value_cache.is_contiguous(),
+          "layout")
+    _need(cos_sin_cache.size(-1) == head_dim, "full rotary only (rot_dim == head_dim)")
+    T = positions.numel()
+    check(lib().xb_rope_and_cache_packed_bf16(_p(positions), _p(qkv_packed), c_i64(qkv_packed.stride(0)), _p(qkv_out),
+                                              c_i64(qkv_out.stride(0)), _p(cos_sin_cache), _p(slot_ids), _p(key_cache),
+                                              _p(value_cache), c_i32(num_heads), c_i32(num_kv_heads), c_i32(head_dim),
+                                              c_i32(T), _stream()), "rope_and_cache_packed")

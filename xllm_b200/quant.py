@@ -44,6 +44,27 @@ def pack_w4_gate_up(q, scales, zeros, group_size=128, bias=None):
     return qw, meta, (bias[idx].contiguous() if bias is not None else None)
 
 
+def qkv_rope_index(num_heads: int, num_kv_heads: int, head_dim: int, device=None) -> torch.Tensor:
+    """Row permutation of a fused qkv projection [(Hq + 2 Hkv) * D, K] into the layout the rope-fused GEMV epilogue
+    expects (csrc/linear_small_m.cu, epilogue 2): inside every head, 16-row tile j holds dims 8j..8j+7 followed by
+    D/2 + 8j..D/2 + 8j+7 - the two halves of 8 NeoX rotary pairs sit in rows g and g+8 of one tile."""
+    assert head_dim % 16 == 0
+    half = head_dim // 2
+    j = torch.arange(head_dim // 16, device=device).repeat_interleave(16)
+    i = torch.arange(16, device=device).repeat(head_dim // 16)
+    within = torch.where(i < 8, 8 * j + i, half + 8 * j + (i - 8))                     # [D] permuted -> logical dim
+    heads = torch.arange(num_heads + 2 * num_kv_heads, device=device).unsqueeze(1) * head_dim
+    return (heads + within.unsqueeze(0)).reshape(-1)
+
+
+def pack_w4_qkv_rope(q, scales, zeros, num_heads, num_kv_heads, head_dim, group_size=128, bias=None):
+    """pack a fused qkv weight with the rope-pair row order -> (qweight, meta, bias_permuted)."""
+    idx = qkv_rope_index(num_heads, num_kv_heads, head_dim, q.device)
+    assert idx.numel() == q.shape[0]
+    qw, meta = pack_w4(q[idx], scales[idx], zeros[idx], group_size)
+    return qw, meta, (bias[idx].contiguous() if bias is not None else None)
+
+
 def pack_w4_c(q: torch.Tensor) -> torch.Tensor:
     """Same nibble packing through the C routine (used by tests to pin the two packers against each other)."""
     N, K = q.shape

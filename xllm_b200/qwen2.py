@@ -80,6 +80,7 @@ class Linear:
         self.meta = None        # int32 [K/g, N]
         self.bias = None
         self.gate_up_interleaved = False   # w4a16 gate_up packed with quant.pack_w4_gate_up: activation fuses into the GEMV
+        self.qkv_rope_packed = False       # w4a16 qkv packed with quant.pack_w4_qkv_rope: RoPE + KV scatter fuse into the GEMV
         self.weight_scale = None   # fp8: float32 [1] per-tensor weight scale
         self.input_scale = None    # fp8: float32 [1] static activation scale (None -> dynamic per-tensor)
         self._x8 = None
@@ -164,6 +165,7 @@ class Qwen2Weights:
                 gate_up=mk(2 * I, H), down=mk(H, I)))
             # synthetic packed nibbles are random anyway: declare the gate_up rows interleaved so the fused epilogue runs
             w.layers[-1]["gate_up"].gate_up_interleaved = cfg.quant == "w4a16"
+            w.layers[-1]["qkv"].qkv_rope_packed = cfg.quant == "w4a16"
         return w
 
     def weight_bytes(self):
@@ -188,9 +190,12 @@ class Qwen2DecodeRunner:
     """Batched single-token decode over a paged KV cache (continuous-batching decode step of the reference)."""
 
     def __init__(self, cfg: Qwen2Config, weights: Qwen2Weights, max_batch: int, max_ctx: int, device="cuda",
-                 num_blocks: Optional[int] = None, fused_rope_cache: bool = True, pg=None, exchange: str = "peer"):
+                 num_blocks: Optional[int] = None, fused_rope_cache: bool = True, pg=None, exchange: str = "peer",
+                 fuse_gemv: bool = True):
         """pg: xllm_b200.parallel.ProcessGroup for tensor parallelism (weights must already be this rank's shards);
-        exchange: "peer" = NVLink one-shot all-reduce fused with add+RMSNorm, "nccl" = c10d all-reduce (baseline)."""
+        exchange: "peer" = NVLink one-shot all-reduce fused with add+RMSNorm, "nccl" = c10d all-reduce (baseline);
+        fuse_gemv: W4A16 decode with batch <= 8 folds add+RMSNorm into the prologue of the qkv / gate_up GEMVs and
+        RoPE + KV scatter into the qkv epilogue (5 launches per layer instead of 8)."""
         self.cfg, self.w, self.B, self.device = cfg, weights, max_batch, device
         self.pg = pg if (pg is not None and pg.world_size > 1) else None
         self.tp = self.pg.world_size if self.pg else 1
@@ -237,6 +242,10 @@ class Qwen2DecodeRunner:
         self.buf_a = torch.empty(B, H, dtype=BF16, device=dev)
         self.buf_b = torch.empty(B, H, dtype=BF16, device=dev)
         self.qkv = torch.empty(B, self.q_size + 2 * self.kv_size, dtype=BF16, device=dev)
+        self.qkv_raw = torch.empty_like(self.qkv)       # rope-pair packed projection output when RoPE is not fused
+        self.res_pp = [torch.empty(B, H, dtype=BF16, device=dev) for _ in range(2)]   # residual stream ping-pong (fused GEMVs)
+        w4 = cfg.quant == "w4a16" and all(L["qkv"].kind == "w4a16" for L in weights.layers)
+        self.fuse_gemv = bool(fuse_gemv and w4 and B <= 8 and ops.w4a16_decode_fused_fits(B, H))
         self.attn_out = torch.empty(B, self.q_size, dtype=BF16, device=dev)
         self.gate_up = torch.empty(B, 2 * self.inter, dtype=BF16, device=dev)
         self.act = torch.empty(B, self.inter, dtype=BF16, device=dev)
@@ -277,11 +286,77 @@ class Qwen2DecodeRunner:
         ops.fused_add_rms_norm(out, self.residual, norm_w, cfg.rms_norm_eps)
         return out
 
+    def _qkv_and_rope(self, L, li, h, norm_w=None, res_in=None, res_out=None):
+        """qkv_proj + RoPE + KV scatter of layer li (qwen2_attention.cpp:147-176, flashinfer_attention.cpp:128-131);
+        with norm_w the add+RMSNorm in front of it rides in the same launch.  Leaves q | k | v (logical) in self.qkv."""
+        cfg = self.cfg
+        qs, kvs = self.q_size, self.kv_size
+        lin = L["qkv"]
+        packed = lin.kind == "w4a16" and lin.qkv_rope_packed
+        if packed and h.size(0) <= 8 and (self.fuse_gemv or norm_w is None):
+            ops.w4a16_decode_fused(h, lin.qweight, lin.meta, lin.group_size, lin.bias, self.qkv, norm_weight=norm_w,
+                                   eps=cfg.rms_norm_eps, residual_in=res_in, residual_out=res_out, stage_x=self.fuse_gemv,
+                                   epilogue="rope_cache", positions=self.positions, cos_sin_cache=self.cos_sin,
+                                   slot_ids=self.slots, key_cache=self.k_caches[li], value_cache=self.v_caches[li],
+                                   num_heads=self.nh, num_kv_heads=self.nkv, head_dim=cfg.head_dim)
+            return
+        assert norm_w is None
+        if packed:
+            lin.forward(h, self.qkv_raw)
+            ops.rope_and_cache_packed(self.positions, self.qkv_raw, self.qkv, self.cos_sin, self.slots, self.k_caches[li],
+                                      self.v_caches[li], self.nh, self.nkv, cfg.head_dim)
+            return
+        lin.forward(h, self.qkv)
+        q, k, v = self.qkv[:, :qs], self.qkv[:, qs:qs + kvs], self.qkv[:, qs + kvs:]
+        if self.fused_rope_cache:
+            ops.rope_and_cache(self.positions, q, k, v, self.cos_sin, self.slots, self.k_caches[li], self.v_caches[li], True)
+        else:
+            ops.rotary_embedding(self.positions, q, k, self.cos_sin, True)
+            ops.reshape_paged_cache(self.slots, k.view(-1, self.nkv, cfg.head_dim), v.view(-1, self.nkv, cfg.head_dim),
+                                    self.k_caches[li], self.v_caches[li])
+
+    def _attention(self, li):
+        cfg = self.cfg
+        ops.batch_decode(self.plan, self.qkv[:, :self.q_size].view(-1, self.nh, cfg.head_dim), self.k_caches[li],
+                         self.v_caches[li], self.kv_indptr, self.kv_indices, self.kv_last, cfg.head_dim ** -0.5,
+                         self.attn_out.view(-1, self.nh, cfg.head_dim))
+
+    def _launch_step_fused(self):
+        """TP = 1, W4A16, batch <= 8: five launches per layer.  The residual add + RMSNorm that the reference runs as
+        its own kernel after o_proj / down_proj (qwen2_decoder_layer.cpp:89-112) is computed in the prologue of the NEXT
+        GEMV (every CTA normalises the 7 KB activation row into its shared memory), RoPE + KV scatter in the qkv
+        epilogue, SiLU*mul in the gate_up epilogue.  The residual stream ping-pongs between two buffers because the
+        CTAs of a GEMV read it while CTA 0 writes the updated one."""
+        cfg, w = self.cfg, self.w
+        ops.embedding(self.hidden, self.token_ids, w.embed)
+        x, res_in, pp = self.hidden, None, 0          # pending un-normalised activations + residual stream
+        for li, L in enumerate(w.layers):
+            self._qkv_and_rope(L, li, x, L["input_norm"], res_in, self.res_pp[pp])
+            res_in, pp = self.res_pp[pp], pp ^ 1
+            self._attention(li)
+            L["o"].forward(self.attn_out, self.buf_a)
+            gu = L["gate_up"]
+            epi = "act_mul" if gu.gate_up_interleaved else "none"
+            ops.w4a16_decode_fused(self.buf_a, gu.qweight, gu.meta, gu.group_size, gu.bias,
+                                   self.act if epi == "act_mul" else self.gate_up, norm_weight=L["post_norm"],
+                                   eps=cfg.rms_norm_eps, residual_in=res_in, residual_out=self.res_pp[pp], epilogue=epi,
+                                   act_mode="silu")
+            res_in, pp = self.res_pp[pp], pp ^ 1
+            if epi == "none":
+                ops.act_and_mul(self.act, self.gate_up, "silu")
+            L["down"].forward(self.act, self.buf_b)
+            x = self.buf_b
+        # final add + norm in front of the (bf16) lm_head
+        self.residual = res_in
+        ops.fused_add_rms_norm(x, self.residual, w.final_norm, cfg.rms_norm_eps)
+        w.lm_head.forward(x, self.logits_local)
+        ops.argmax(self.next_tokens, self.logits)
+
     def launch_step(self, trace=None):
         """trace (eager only): list that receives (normed layer output, residual) clones after every decoder layer."""
         cfg, w = self.cfg, self.w
-        qs, kvs = self.q_size, self.kv_size
-        scale = cfg.head_dim ** -0.5
+        if self.fuse_gemv and self.pg is None and trace is None:
+            return self._launch_step_fused()
         ops.embedding(self.hidden, self.token_ids, w.embed)
         # apply_norm, first layer (qwen2_decoder_layer.cpp:72-79): the residual stream aliases the embedding output
         self.residual = self.hidden
@@ -289,18 +364,8 @@ class Qwen2DecodeRunner:
         h = self.normed
         n_layers = len(w.layers)
         for li, L in enumerate(w.layers):
-            L["qkv"].forward(h, self.qkv)
-            q, k, v = self.qkv[:, :qs], self.qkv[:, qs:qs + kvs], self.qkv[:, qs + kvs:]
-            if self.fused_rope_cache:
-                ops.rope_and_cache(self.positions, q, k, v, self.cos_sin, self.slots, self.k_caches[li],
-                                   self.v_caches[li], True)
-            else:
-                ops.rotary_embedding(self.positions, q, k, self.cos_sin, True)
-                ops.reshape_paged_cache(self.slots, k.view(-1, self.nkv, cfg.head_dim), v.view(-1, self.nkv, cfg.head_dim),
-                                        self.k_caches[li], self.v_caches[li])
-            ops.batch_decode(self.plan, q.view(-1, self.nh, cfg.head_dim), self.k_caches[li], self.v_caches[li],
-                             self.kv_indptr, self.kv_indices, self.kv_last, scale,
-                             self.attn_out.view(-1, self.nh, cfg.head_dim))
+            self._qkv_and_rope(L, li, h)
+            self._attention(li)
             # o_proj (+ all-reduce) + post-attention add+norm
             h = self._row_parallel(L["o"], self.attn_out, 0, L["post_norm"], self.buf_a)
             gu = L["gate_up"]

@@ -59,6 +59,7 @@ class Qwen2PrefillRunner:
         buf_a = torch.empty(T, H, dtype=BF16, device=dev)
         buf_b = torch.empty(T, H, dtype=BF16, device=dev)
         qkv = torch.empty(T, qs + 2 * kvs, dtype=BF16, device=dev)
+        qkv_raw = torch.empty_like(qkv) if any(L["qkv"].qkv_rope_packed for L in w.layers) else None
         attn_out = torch.empty(T, qs, dtype=BF16, device=dev)
         inter = cfg.intermediate_size
         gate_up = torch.empty(T, 2 * inter, dtype=BF16, device=dev)
@@ -70,10 +71,16 @@ class Qwen2PrefillRunner:
         h = normed
         n_layers = len(w.layers)
         for li, L in enumerate(w.layers):
-            L["qkv"].forward(h, qkv)
             q, k, v = qkv[:, :qs], qkv[:, qs:qs + kvs], qkv[:, qs + kvs:]
             # RoPE on q/k and the KV scatter of this chunk (flashinfer_attention.cpp:128-131 scatters before attending)
-            ops.rope_and_cache(positions, q, k, v, self.cos_sin, slots, self.k_caches[li], self.v_caches[li], True)
+            if L["qkv"].qkv_rope_packed:
+                # decode-layout weights (rows in rope-pair order): the GEMM output is un-permuted by the rope kernel
+                L["qkv"].forward(h, qkv_raw)
+                ops.rope_and_cache_packed(positions, qkv_raw, qkv, self.cos_sin, slots, self.k_caches[li], self.v_caches[li],
+                                          self.nh, self.nkv, D)
+            else:
+                L["qkv"].forward(h, qkv)
+                ops.rope_and_cache(positions, q, k, v, self.cos_sin, slots, self.k_caches[li], self.v_caches[li], True)
             q3, o3 = q.view(T, self.nh, D), attn_out.view(T, self.nh, D)
             if chunked:
                 ops.batch_chunked_prefill(q3, self.k_caches[li], self.v_caches[li], paged_kv_indptr, paged_kv_indices,

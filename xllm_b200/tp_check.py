@@ -56,10 +56,14 @@ def shard_weights(cfg: Qwen2Config, W: dict, rank: int, tp: int, device, fuse_ga
     w.lm_head = Linear(vs, cfg.hidden_size, "bf16")
     w.lm_head.weight = W["lm_head"][rank * vs:(rank + 1) * vs].contiguous().to(device)
 
-    def mk(d, gate_up=False):
+    def mk(d, gate_up=False, qkv=False):
         n, k = d["q"].shape
         l = Linear(n, k, "w4a16", cfg.group_size)
-        if gate_up and fuse_gate_up:
+        if qkv:
+            qw, meta, b = quant.pack_w4_qkv_rope(d["q"], d["s"], d["z"], hp.num_heads, hp.num_kv_heads, cfg.head_dim,
+                                                 cfg.group_size, d["b"])
+            l.qkv_rope_packed = True
+        elif gate_up and fuse_gate_up:
             qw, meta, b = quant.pack_w4_gate_up(d["q"], d["s"], d["z"], cfg.group_size, d["b"])
             l.gate_up_interleaved = True
         else:
@@ -74,7 +78,7 @@ def shard_weights(cfg: Qwen2Config, W: dict, rank: int, tp: int, device, fuse_ga
         o = P.shard_linear("w4", L["o"], None, P.shard_cols(cfg.q_size, rank, tp), gs, rank)
         gu = P.shard_linear("w4", L["gate_up"], P.shard_gate_up_rows(cfg.intermediate_size, rank, tp), None, gs, rank)
         dn = P.shard_linear("w4", L["down"], None, P.shard_cols(cfg.intermediate_size, rank, tp), gs, rank)
-        w.layers.append(dict(input_norm=L["input_norm"].to(device), post_norm=L["post_norm"].to(device), qkv=mk(qkv),
+        w.layers.append(dict(input_norm=L["input_norm"].to(device), post_norm=L["post_norm"].to(device), qkv=mk(qkv, qkv=True),
                              o=mk(o), gate_up=mk(gu, True), down=mk(dn)))
     return w, hp
 
