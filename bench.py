@@ -343,6 +343,81 @@ def gpu_comparators(torch, ops, cfg, runner, weights, dev, ctx):
     return out
 
 
+def scale_target_llama70b(torch, dist, dev, rank, world, exchange, steps=8, warmup=3, batch=32, ctx=8192):
+    """The configuration the north-star's scaling target is defined on (BASELINE.json configs[3]): Llama-3-70B FP8 (W8A8,
+    per-tensor static scales: fp8_linear_forward, linear.cpp:137-182), batch 32, ctx 8192, decode step, TP = N over the
+    world group (64 q / 8 kv heads divide by 1, 2, 4, 8).  Random-init weights of the architecture, KV N(0,1).  Returns
+    a dict for the extra key "scale_target" (collective: every rank calls it); an {"error": ...} dict when the box
+    cannot hold the shard."""
+    from xllm_b200.parallel import ProcessGroup
+    from xllm_b200.qwen2 import Qwen2Config, Qwen2DecodeRunner, Qwen2Weights
+    cfg = Qwen2Config.llama3_70b()
+    tp = world
+    out = {"workload": f"Llama-3-70B FP8 W8A8 (static per-tensor), batch={batch}, ctx={ctx}, decode step, tp{tp}", "tp": tp,
+           "n_gpus": world, "steps": steps}
+    try:
+        torch.cuda.empty_cache()
+        free, _total = torch.cuda.mem_get_info()
+        per_layer = ((cfg.q_size + 2 * cfg.kv_size) * cfg.hidden_size + cfg.hidden_size * cfg.q_size +
+                     3 * cfg.intermediate_size * cfg.hidden_size) // tp
+        kv = cfg.num_layers * 2 * (batch * (ctx // cfg.block_size) + 1) * cfg.block_size * max(1, cfg.n_kv_heads // tp) * cfg.head_dim * 2
+        need = cfg.num_layers * per_layer + kv + 2 * cfg.vocab_size * cfg.hidden_size * 2 // max(1, tp) + (6 << 30)
+        out["bytes_needed_per_gpu"] = need
+        ok = torch.tensor([1.0 if free > need else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 0.5:
+            out["error"] = f"needs {need / 2**30:.0f} GiB per GPU, {free / 2**30:.0f} GiB free"
+            return out
+        pg = ProcessGroup() if world > 1 else None
+        weights = Qwen2Weights.synthetic(cfg, dev, seed=2026, tp_rank=rank if world > 1 else 0, tp=tp)
+        runner = Qwen2DecodeRunner(cfg, weights, max_batch=batch, max_ctx=ctx, device=dev, pg=pg, exchange=exchange)
+        g = torch.Generator(device=dev).manual_seed(11 + rank)
+        for li in range(cfg.num_layers):
+            runner.k_caches[li].normal_(generator=g)
+            runner.v_caches[li].normal_(generator=g)
+        bs = cfg.block_size
+        npg = ctx // bs
+        perm = (torch.randperm(runner.num_blocks - 1, generator=torch.Generator().manual_seed(2026)) + 1).tolist()
+        pages, indptr, slots = [], [0], []
+        for b in range(batch):
+            pb = perm[b * npg:(b + 1) * npg]
+            pages += pb
+            indptr.append(len(pages))
+            slots.append(pb[(ctx - 1) // bs] * bs + (ctx - 1) % bs)
+        runner.set_inputs_host(list(range(100, 100 + batch)), [ctx - 1] * batch, slots, indptr, pages, [(ctx - 1) % bs + 1] * batch)
+        runner.step()
+        runner.capture()
+        for _ in range(warmup):
+            runner.run_device_only()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            runner.run_device_only()
+            runner.token_ids.copy_(runner.next_tokens)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0]) / steps
+        step_bytes = weights.weight_bytes() + cfg.num_layers * 2 * batch * ctx * runner.nkv * cfg.head_dim * 2
+        peak, _ = load_peaks()
+        out.update({"tokens_per_s": batch / (ms / 1e3), "ms_per_step": ms, "step_bytes_per_gpu": step_bytes,
+                    "hbm_frac_per_gpu": step_bytes / ms / 1e6 / peak, "exchange": runner.exchange_mode if world > 1 else None,
+                    "timing": "CUDA events around the replays of one CUDA graph per rank, max over ranks"})
+        del runner, weights
+        torch.cuda.empty_cache()
+    except Exception as e:                                   # the headline line must still be printed
+        out["error"] = f"{type(e).__name__}: {str(e)[:160]}"
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -356,6 +431,7 @@ def main():
     ap.add_argument("--parallelism", default="tp", choices=["tp", "dp"])
     ap.add_argument("--tp", type=int, default=0, help="tensor-parallel degree (default: min(N, 4) for Qwen2-7B's 28 heads)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--no-scale-target", action="store_true", help="skip the Llama-3-70B FP8 batch-32 ctx-8192 measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -490,6 +566,7 @@ def main():
     gu_us_avg, gu_us_med = _events_per_launch(torch, gu_fns)
     gu_us_chained = _events_chained(torch, gu_fns)
     gu = L[0]["gate_up"]
+    gu_N, gu_K = gu.N, gu.K
     fused_act = gu.kind == "w4a16" and gu.gate_up_interleaved
     n_out = gu.N // 2 if fused_act else gu.N
     gu_bytes = gu.qweight.numel() * 4 + gu.meta.numel() * 4 + gu.K * 2 + n_out * 2      # this rank's shard
@@ -539,7 +616,7 @@ def main():
                        "linear_tflops": gflop / tg / 1e12, "linear_frac_of_bf16_sustained": gflop / tg / 1e12 / tf_peak,
                        "attention_tflops_causal": aflop / ta / 1e12, "layer_tflops": (gflop + aflop) / (tg + ta) / 1e12,
                        "prefill_tokens_per_s_extrapolated": Mp / ((tg + ta) * cfg.num_layers), "bf16_peak_tflops": tf_peak}
-            del xin, bufs, xi, qkv_p, o_p
+            del xin, bufs, xi, qkv_p, o_p, l0
         except Exception as e:      # the decode line must still be printed
             prefill = {"error": str(e)[:200]}
         if not args.no_comparators:
@@ -547,6 +624,26 @@ def main():
                 comparators = gpu_comparators(torch, ops, cfg, runner, weights, dev, ctx)
             except Exception as e:
                 comparators = [{"error": str(e)[:200]}]
+
+    # ---- the configuration the 1 -> 8 scaling target is defined on (extra key; the headline stays Qwen2-7B) ----------
+    scale_target = None
+    if not args.no_scale_target and args.parallelism == "tp" and world in (1, 2, 4, 8):
+        plan_info = (runner.plan.chunk_tokens, runner.plan.max_splits, runner.plan.cluster)
+        exch_mode = runner.exchange_mode if tp > 1 else None
+        h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
+        weights_bytes = weights.weight_bytes()
+        # release the Qwen2-7B runner (weights, caches, graph) before the 70B shard is built
+        runner = weights = L = gu = q3 = o3 = at_fns = gu_fns = gate_up_fn = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        scale_target = scale_target_llama70b(torch, dist, dev, rank, world, exchange)
+        log(f"scale target {scale_target}")
+    else:
+        plan_info = (runner.plan.chunk_tokens, runner.plan.max_splits, runner.plan.cluster)
+        exch_mode = runner.exchange_mode if tp > 1 else None
+        h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
+        weights_bytes = weights.weight_bytes()
 
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
     t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
@@ -556,7 +653,7 @@ def main():
     total_tokens = args.steps * dp
     value = total_tokens / (ms / 1e3)
     e2e_value = total_tokens / (e2e_ms / 1e3)
-    step_bytes = weights.weight_bytes() + cfg.num_layers * at_bytes      # per rank
+    step_bytes = weights_bytes + cfg.num_layers * at_bytes      # per rank
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -574,17 +671,16 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "ctx": ctx, "batch": 1,
                        "parallelism": (f"tp{tp}" if dp == 1 else f"tp{tp}xdp{dp}") if tp > 1 else f"dp{world}",
-                       "exchange": (runner.exchange_mode if tp > 1 else None),
+                       "exchange": exch_mode,
                        "l2": "inputs larger than L2: each step streams %.2f GB of weights+KV" % (step_bytes / 1e9),
-                       "decode_chunk_tokens": runner.plan.chunk_tokens, "decode_splits": runner.plan.max_splits,
-                       "decode_cluster": runner.plan.cluster, "launches_per_step": launches_per_step},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
-                    "d2h_bytes_per_step": runner.d2h_bytes},
+                       "decode_chunk_tokens": plan_info[0], "decode_splits": plan_info[1],
+                       "decode_cluster": plan_info[2], "launches_per_step": launches_per_step},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm",
                          "kernel": f"linear_w4a16_small_m_kernel{' + SiLU*mul epilogue' if fused_act else ''} "
-                                   f"(gate_up_proj {gu.N}x{gu.K}, 28 launches/step)",
+                                   f"(gate_up_proj {gu_N}x{gu_K}, 28 launches/step)",
                          "per_rank": True, "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                          # ncu dram__bytes_read+write of the same kernel variant and shape (single GPU, unsharded shape)
                          "traffic": profiled_traffic(traffic_file) if tp == 1 else None,
@@ -610,6 +706,8 @@ def main():
             line["tp_parity"] = tp_parity
         if comparators is not None:
             line["comparators"] = comparators
+        if scale_target is not None:
+            line["scale_target"] = scale_target
         print(json.dumps(line), flush=True)
     if world > 1:
         # destroy_process_group() blocks here (captured NCCL / symmetric-memory graphs still hold communicator

@@ -244,6 +244,30 @@ int xb_linear_w4a16_decode_fused(void* y, int64_t y_stride, const void* x, int64
                                  int num_kv_heads, int head_dim, xb_stream_t stream);
 int xb_linear_w4a16_decode_fused_fits(int M, int K);
 
+/* ---- W8A16 weight-only linears (north-star "W4A16 / W8A16 / FP8"; additive boundary) -------------
+ * spec oracle/quant.py with bits = 8: w = bf16((q - z) * s), y = bf16(sum_k f32(x) f32(w) + b).
+ * qweight: tile-packed bytes [N/16][K/64][32 lanes][8 words] (xb_w8_pack_rows / quant.pack_w8): lane 4g+t holds rows
+ * n0+g (words 0..3) and n0+g+8 (words 4..7), k in [k0+16t, k0+16t+16) ascending; meta [K/g][N] = bf16 scale | zero<<16.
+ * xb_linear_w8a16_small_m: M <= 64 streaming kernel (decode); xb_gemm_w8a16: tcgen05 GEMM with the int8 -> bf16
+ * unpack fused into the MMA main loop (prefill). */
+int xb_linear_w8a16_small_m(void* y, int64_t y_stride, const void* x, int64_t x_stride,
+                            const uint32_t* qweight, const uint32_t* meta, const void* bias,
+                            int M, int N, int K, int group_size, xb_stream_t stream);
+int xb_gemm_w8a16(void* c, int64_t ldc, const void* a, int64_t lda, const uint32_t* qweight,
+                  const uint32_t* meta, const void* bias, int M, int N, int K, int group_size,
+                  xb_stream_t stream);
+int xb_w8_pack_rows(uint32_t* out, const uint8_t* q, int N, int K);
+
+/* ---- FP8 W8A8 small-M (decode) --------------------------------------------------------------------------------
+ * cutlass_scaled_mm for M <= 64 (the reference buckets M <= 16 / <= 64 into swap-AB tiles:
+ * cutlass_w8a8/c3x/scaled_mm_sm100_fp8_dispatch.cuh:148-287): c [M,N] bf16 = a_s * (b_s * (a . b^T)) + bias,
+ * a [M,K] e4m3 (lda bytes), b [N,K] e4m3 dense (the reference's weight layout), scales f32 with numel 1 or M / N.
+ * HBM-streaming kernel: weight rows in the M slot of mma.sync m16n8k32.e4m3, tokens in the n8 slot. */
+int xb_linear_fp8_small_m(void* c, int64_t ldc, const void* a, int64_t lda, const void* b,
+                          const float* a_scale, int a_scale_numel, const float* b_scale,
+                          int b_scale_numel, const void* bias, int M, int N, int K,
+                          xb_stream_t stream);
+
 /* act_and_mul over that interleaved column layout (prefill path sharing the same packed weight):
  * out[t, 8j+i] = act(x[t, 16j+i]) * x[t, 16j+8+i]. */
 int xb_act_and_mul_interleaved8_bf16(void* out, const void* input, int d, int num_tokens,

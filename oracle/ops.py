@@ -92,6 +92,24 @@ def compute_inv_freq(rotary_dim: int, rope_theta) -> torch.Tensor:
     return 1.0 / torch.pow(torch.tensor(float(int(rope_theta)), dtype=F32), sl / float(rotary_dim))
 
 
+def llama3_inv_freq(inv_freq: torch.Tensor, factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max_pos=8192):
+    """Llama-3.1 "llama3" rope_type, restated element by element from the published algorithm (Hugging Face
+    modeling_rope_utils._compute_llama3_parameters): not on the reference's path (its llama.h parses the fields,
+    models/llm/npu/llama.h:341-346, and ignores them, :77-106) - spec for integration/patches/0002."""
+    out = []
+    low_wl, high_wl = original_max_pos / low_freq_factor, original_max_pos / high_freq_factor
+    for f in inv_freq.tolist():
+        wl = 2 * math.pi / f
+        if wl < high_wl:
+            out.append(f)
+        elif wl > low_wl:
+            out.append(f / factor)
+        else:
+            smooth = (original_max_pos / wl - low_freq_factor) / (high_freq_factor - low_freq_factor)
+            out.append((1 - smooth) * f / factor + smooth * f)
+    return torch.tensor(out, dtype=F32)
+
+
 def compute_cos_sin_cache(rotary_dim: int, max_pos: int, rope_theta, dtype=BF16, interleaved=False) -> torch.Tensor:
     """[max_pos, rotary_dim] = [cos(rot/2) | sin(rot/2)]: the pre-sliced view the CUDA kernel receives
     (rotary_embedding.cpp:47-52 takes chunks 0 and 2 of cat(cos(cat(f,f)), sin(cat(f,f))))."""

@@ -11,13 +11,14 @@ from oracle import quant as OQ
 BF16 = torch.bfloat16
 
 
-def build_case(cfg, B, kv_lens, seed=2026):
-    """logical weights (CPU, oracle quantiser) + prefilled KV caches + step metadata."""
+def build_case(cfg, B, kv_lens, seed=2026, w_std=0.05):
+    """logical weights (CPU, oracle quantiser) + prefilled KV caches + step metadata.  w_std: std of the linear weights
+    (0.05 gives a per-layer gain > 1 on small hidden sizes - fine for a few layers, chaotic over 24; deep stacks use 0.02)."""
     g = torch.Generator().manual_seed(seed)
     H, I = cfg.hidden_size, cfg.intermediate_size
 
     def lin(n, k, bias=False):
-        w = (torch.randn(n, k, generator=g) * 0.05).to(BF16)
+        w = (torch.randn(n, k, generator=g) * w_std).to(BF16)
         b = (torch.randn(n, generator=g) * 0.05).to(BF16) if bias else None
         if cfg.quant == "bf16":
             return dict(w=w, b=b)
@@ -26,8 +27,11 @@ def build_case(cfg, B, kv_lens, seed=2026):
             w_scale = (w.float().abs().max() / 448.0).reshape(1)
             w8 = (w.float() / w_scale).clamp(-448, 448).to(torch.float8_e4m3fn)
             return dict(w8=w8, w_scale=w_scale, in_scale=torch.tensor([0.02]), b=b)
-        q, s, z = OQ.quantize(w, 4, cfg.group_size)
-        return dict(q=q, s=s, z=z, b=b, w=OQ.dequantize(q, s, z, cfg.group_size))
+        q, s, z = OQ.quantize(w, 8 if cfg.quant == "w8a16" else 4, cfg.group_size)
+        d = dict(q=q, s=s, z=z, b=b, w=OQ.dequantize(q, s, z, cfg.group_size))
+        if cfg.quant == "w4a16":
+            d["w_exact"] = OQ.dequantize_exact(q, s, z, cfg.group_size)    # form of the decode kernel at M <= 8
+        return d
 
     W = dict(embed=(torch.randn(cfg.vocab_size, H, generator=g) * 0.5).to(BF16),
              final_norm=(1 + 0.1 * torch.randn(H, generator=g)).to(BF16), layers=[])
@@ -59,6 +63,9 @@ def _olin(d):
     """oracle linear for one logical weight dict (bf16 / dequantised W4 / fp8 W8A8 static)."""
     if "w8" in d:
         return lambda x, _w=None, b=None: O.fp8_linear(x, d["w8"], d["w_scale"], d["in_scale"], d["b"])
+    if "w_exact" in d:
+        # W4A16: the library computes the exact-weight form for M <= 8 tokens, the bf16-weight form above (oracle/quant.py)
+        return lambda x, _w=None, b=None: O.linear(x, d["w_exact"] if OQ.w4a16_form(x.shape[0]) == "exact" else d["w"], d["b"])
     return lambda x, _w=None, b=None: O.linear(x, d["w"], d["b"])
 
 
@@ -132,6 +139,9 @@ def upload(cfg, W, device="cuda"):
             l.weight = d["w8"].to(device)
             l.weight_scale = d["w_scale"].float().to(device)
             l.input_scale = d["in_scale"].float().to(device)
+        elif cfg.quant == "w8a16":
+            qw, meta = quant.pack_w8(d["q"], d["s"], d["z"], cfg.group_size)
+            l.qweight, l.meta = qw.to(device), meta.to(device)
         else:
             qw, meta = quant.pack_w4(d["q"], d["s"], d["z"], cfg.group_size)
             l.qweight, l.meta = qw.to(device), meta.to(device)

@@ -47,6 +47,24 @@ def test_w4_packers_agree(built_lib):
     assert torch.equal(hi.t().to(torch.float32), z.to(torch.float32) + 128.0)
 
 
+def test_w8_packers_agree_and_qkv_rope_index(built_lib):
+    g = torch.Generator().manual_seed(2026)
+    q = torch.randint(0, 256, (64, 256), dtype=torch.uint8, generator=g)
+    s = torch.rand(64, 2, generator=g).to(torch.bfloat16)
+    z = torch.randint(0, 256, (64, 2), dtype=torch.uint8, generator=g)
+    qa, meta = quant.pack_w8(q, s, z, 128)
+    assert qa.shape == (4, 4, 32, 8) and torch.equal(qa, quant.pack_w8_c(q))
+    # lane 4g+t of tile (nt, kt): words 0..3 = row 16nt+g, bytes k = 64kt+16t .. +15 ascending; words 4..7 = row +8
+    raw = qa.view(torch.uint8).view(4, 4, 32, 2, 16)
+    assert torch.equal(raw[1, 2, 4 * 3 + 1, 0], q[16 + 3, 128 + 16:128 + 32]) and torch.equal(raw[1, 2, 4 * 3 + 1, 1], q[16 + 11, 128 + 16:128 + 32])
+    assert torch.equal((meta & 0xFFFF).to(torch.int16).view(torch.bfloat16).t().contiguous(), s)
+    assert torch.equal((meta >> 16).t().contiguous().to(torch.uint8), z)
+    # rope-pair row order of the decode qkv layout: inside each head, tile j = dims 8j..8j+7 then D/2+8j..D/2+8j+7
+    idx = quant.qkv_rope_index(2, 1, 64)
+    assert sorted(idx.tolist()) == list(range(4 * 64))
+    assert idx[:16].tolist() == list(range(8)) + list(range(32, 40)) and idx[64 + 16:64 + 24].tolist() == list(range(64 + 8, 64 + 16))
+
+
 def test_argument_errors_surface(built_lib):
     lib = _lib.lib()
     plan = (ctypes.c_int64 * 8)()
@@ -56,6 +74,13 @@ def test_argument_errors_surface(built_lib):
     assert rc == 0 and plan[0] % 16 == 0 and plan[0] * plan[1] >= 4096
     rc = lib.xb_w4_pack_rows(None, None, 15, 64)
     assert rc != 0
+    assert lib.xb_w8_pack_rows(None, None, 16, 60) != 0
+    # the fused decode GEMV serves one token tile and needs its activation block to fit the shared-memory stage
+    assert lib.xb_linear_w4a16_decode_fused_fits(8, 3584) == 1 and lib.xb_linear_w4a16_decode_fused_fits(9, 3584) == 0
+    assert lib.xb_linear_w4a16_decode_fused_fits(1, 18944) == 1 and lib.xb_linear_w4a16_decode_fused_fits(8, 18944) == 0
+    assert lib.xb_linear_w8a16_small_m(None, 0, None, 0, None, None, None, 65, 64, 64, 64, None) != 0
+    assert b"M=65" in lib.xb_last_error()
+    assert lib.xb_linear_fp8_small_m(None, 0, None, 0, None, None, 1, None, 1, None, 4, 64, 96, None) != 0
 
 
 def test_tvm_ffi_modules_export_reference_entry_points(built_lib):

@@ -73,3 +73,20 @@ def test_checkpoint_to_kernel_layout_matches_spec():
     assert zb == 128 + int(z2[19, 0])
     ref = torch.tensor((nib[0] - int(z2[19, 0])) * sc).to(torch.bfloat16).float().item()
     assert ref == wd[19, k0].item()
+
+
+def test_llama3_rope_scaling_matches_the_published_rule():
+    """xllm_b200.qwen2.llama3_scale_inv_freq (vectorised) against the element-by-element restatement in the oracle;
+    the scaled table changes only the low frequencies (Llama-3.1: factor 8, low 1, high 4, original 8192)."""
+    import torch
+    from oracle import ops as O
+    from xllm_b200.qwen2 import Qwen2Config, llama3_scale_inv_freq, make_cos_sin_cache
+    inv = O.compute_inv_freq(128, 500000.0)
+    got = llama3_scale_inv_freq(inv, 8.0, 1.0, 4.0, 8192)
+    ref = O.llama3_inv_freq(inv, 8.0, 1.0, 4.0, 8192)
+    assert torch.allclose(got, ref, rtol=1e-6, atol=0)
+    assert torch.equal(got[:20], inv[:20]) and torch.allclose(got[-5:], inv[-5:] / 8.0)
+    plain = make_cos_sin_cache(Qwen2Config.llama3_70b(max_position_embeddings=256), "cpu")
+    scaled = make_cos_sin_cache(Qwen2Config.llama3_70b(max_position_embeddings=256, rope_scaling=dict(
+        rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max_position_embeddings=8192)), "cpu")
+    assert torch.equal(plain[:, :20], scaled[:, :20]) and not torch.equal(plain[:, 40:64], scaled[:, 40:64])

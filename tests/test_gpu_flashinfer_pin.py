@@ -105,7 +105,7 @@ def test_decode_matches_flashinfer(kv_lens, HQ, HKV, D, page, tensor_cores, buil
     # and the oracle agrees with FlashInfer to the same bar: this is what pins the oracle's attention ladder
     qo = torch.arange(B + 1, dtype=torch.int32)
     orc = O.paged_attention(q, kc, vc, qo, indptr, indices, last, sm_scale, causal=False)
-    assert_close_attention(orc, ref, scale, rtol=2e-3, what=f"oracle vs flashinfer {kv_lens} (tensor_cores={tensor_cores})")
+    assert_close_attention(orc, ref, scale, rtol=2e-3, rel_l2=4e-3, what=f"oracle vs flashinfer {kv_lens} (tensor_cores={tensor_cores})")
 
 
 @pytest.mark.parametrize("lens,HQ,HKV,D", [([2048], 28, 4, 128), ([128, 77, 300], 28, 4, 128), ([1024], 14, 2, 64)])

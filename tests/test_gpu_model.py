@@ -15,7 +15,7 @@ def _small(quant):
                        name="tiny")
 
 
-@pytest.mark.parametrize("quant", ["w4a16", "bf16"])
+@pytest.mark.parametrize("quant", ["w4a16", "w8a16", "bf16"])
 @pytest.mark.parametrize("use_graph,fused", [(True, True), (False, False)])
 def test_decode_step_matches_oracle(quant, use_graph, fused, built_lib):
     cfg = _small(quant)

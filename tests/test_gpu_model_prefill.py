@@ -2,6 +2,7 @@
 Qwen2PrefillRunner, then greedy-decoded through Qwen2DecodeRunner on the SAME paged KV cache, against the CPU oracle:
 same tokens, last-token logits within the whole-step tolerance of tests/test_gpu_model.py.
 """
+import math
 import os
 
 import pytest
@@ -87,14 +88,17 @@ def test_cfg0_qwen2_0_5b_full_model_prompt128_greedy16(built_lib):
     of LlmModelImplBase::forward (xllm/models/llm/llm_model_base.h:60-131) against the CPU oracle.
 
     Two bf16 pipelines that are both correct drift by ~1 bf16 ulp per op, so "token-exact" is asserted wherever the
-    oracle's own top-2 margin exceeds that drift (|logit1 - logit2| > 2 % of |logit1|); every GPU token must in any case
-    be a near-argmax of the oracle's logits.  Decode steps are teacher-forced on the oracle's token so each step is
+    oracle's own top-2 margin exceeds that drift (|logit1 - logit2| > max(2 % of |logit1|, 4 bf16 ulps of logit1 - the
+    logits themselves are bf16)); every GPU token must in any case be a near-argmax of the oracle's logits.  Decode steps are teacher-forced on the oracle's token so each step is
     checked in isolation."""
     from xllm_b200.qwen2 import Qwen2Config, Qwen2DecodeRunner
     from xllm_b200.qwen2_prefill import Qwen2PrefillRunner
     cfg = Qwen2Config.qwen2_0_5b()
     assert (cfg.num_layers, cfg.hidden_size, cfg.vocab_size, cfg.block_size) == (24, 896, 151936, 128)
-    W, _, _, _ = MP.build_case(cfg, 1, [1], seed=2026)
+    # weights N(0, 0.02^2) like a real initialisation: with the helper's default 0.05 the 24-layer random stack has a
+    # per-layer gain > 1 and amplifies bf16 rounding noise chaotically (measured 5e-2 logits rel-L2 between two correct
+    # bf16 pipelines, argmax flips at 3-ulp margins)
+    W, _, _, _ = MP.build_case(cfg, 1, [1], seed=2026, w_std=0.02)
     g = torch.Generator().manual_seed(2026)
     prompt_len, n_decode = 128, 16
     bs = cfg.block_size
@@ -146,7 +150,8 @@ def test_cfg0_qwen2_0_5b_full_model_prompt128_greedy16(built_lib):
         worst = max(worst, l2)
         top2 = rl.topk(2).values
         margin = float(top2[0] - top2[1])
-        tol = 0.02 * abs(float(top2[0]))
+        top = abs(float(top2[0]))
+        tol = max(0.02 * top, 4 * 2.0 ** (math.floor(math.log2(max(top, 1e-30))) - 7))
         same = got_tokens[i] == ref_tokens[i]
         exact += int(same)
         near = float(rl[got_tokens[i]]) >= float(top2[0]) - tol
@@ -161,4 +166,4 @@ def test_cfg0_qwen2_0_5b_full_model_prompt128_greedy16(built_lib):
     from tests.util import REL_L2_LOG
     REL_L2_LOG.append((f"cfg0 Qwen2-0.5B full model: worst logits rel-L2 over {n_decode} steps; {exact}/{n_decode} tokens "
                        f"exact, {decided} steps with a decisive oracle margin", worst))
-    assert not bad and worst <= 5e-2 and exact >= n_decode - 2, "\n".join(report)
+    assert not bad and worst <= 3e-2 and exact >= n_decode - 2, "\n".join(report)

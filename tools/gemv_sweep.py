@@ -94,7 +94,59 @@ def run(name, N, K, M=1, gs=128, heads=None):
               f"({nbytes / t_g / 1e3 / PEAK:5.1%})", flush=True)
 
 
+def run_q8(name, N, K, M):
+    """W8A16 and FP8 W8A8 streaming kernels, and the small-M / tcgen05 crossover of the three weight formats."""
+    gs = 128
+    copies = max(2, int(400e6 / (N * K)) + 1)
+    x = torch.randn(M, K, device=DEV, dtype=BF16)
+    y = torch.empty(M, N, device=DEV, dtype=BF16)
+    w8 = []
+    for _ in range(copies):
+        qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (N // 16, K // 64, 32, 8), dtype=torch.int32, device=DEV)
+        sc = (torch.rand(K // gs, N, device=DEV) * 0.001 + 0.0001).to(BF16).view(torch.int16).to(torch.int32) & 0xFFFF
+        w8.append((qw, (sc | (128 << 16)).contiguous()))
+    nb = N * K + (K // gs) * N * 4 + M * K * 2 + M * N * 2
+    fns = [lambda i=i: ops.w8a16_linear_small_m(x, w8[i][0], w8[i][1], gs, None, y) for i in range(copies)]
+    t = graph_time(fns)
+    print(f"{name:8s} N={N:6d} K={K:6d} M={M:2d} w8a16 streaming      graph {t:7.2f} us ({nb / t / 1e3 / PEAK:5.1%})", flush=True)
+    if M > 16:
+        fns = [lambda i=i: ops.gemm_w8a16(x, w8[i][0], w8[i][1], gs, None, y) for i in range(copies)]
+        t = graph_time(fns)
+        print(f"{name:8s} N={N:6d} K={K:6d} M={M:2d} w8a16 tcgen05 GEMM   graph {t:7.2f} us ({nb / t / 1e3 / PEAK:5.1%})", flush=True)
+    del w8
+    f8 = [torch.randn(N, K, device=DEV).clamp(-3, 3).to(torch.float8_e4m3fn) for _ in range(copies)]
+    a8 = torch.randn(M, K, device=DEV).clamp(-3, 3).to(torch.float8_e4m3fn)
+    one = torch.ones(1, device=DEV)
+    nb = N * K + M * K + M * N * 2
+    fns = [lambda i=i: ops.cutlass_scaled_mm(y, a8, f8[i].t(), one, one, None) for i in range(copies)]
+    t = graph_time(fns)
+    print(f"{name:8s} N={N:6d} K={K:6d} M={M:2d} fp8 streaming (M<=64) graph {t:7.2f} us ({nb / t / 1e3 / PEAK:5.1%})", flush=True)
+    from xllm_b200._lib import c_i32, c_i64, check, lib
+    fns = [lambda i=i: check(lib().xb_gemm_fp8_scaled(ops._p(y), c_i64(y.stride(0)), ops._p(a8), c_i64(a8.stride(0)), ops._p(f8[i]),
+                                                      ops._p(one), c_i32(1), ops._p(one), c_i32(1), ops._p(None), c_i32(M), c_i32(N),
+                                                      c_i32(K), ops._stream()), "gemm_fp8") for i in range(copies)]
+    t = graph_time(fns)
+    print(f"{name:8s} N={N:6d} K={K:6d} M={M:2d} fp8 tcgen05 GEMM      graph {t:7.2f} us ({nb / t / 1e3 / PEAK:5.1%})", flush=True)
+    del f8
+    # W4 crossover
+    ws = weights(N, K, gs, max(2, int(400e6 / (N * K / 2)) + 1))
+    nb = N * K // 2 + (K // gs) * N * 4 + M * K * 2 + M * N * 2
+    fns = [lambda i=i: ops.w4a16_linear_small_m(x, ws[i][0], ws[i][1], gs, None, y) for i in range(len(ws))]
+    t = graph_time(fns)
+    print(f"{name:8s} N={N:6d} K={K:6d} M={M:2d} w4a16 streaming      graph {t:7.2f} us ({nb / t / 1e3 / PEAK:5.1%})", flush=True)
+    if M > 16:
+        fns = [lambda i=i: ops.gemm_w4a16(x, ws[i][0], ws[i][1], gs, None, y) for i in range(len(ws))]
+        t = graph_time(fns)
+        print(f"{name:8s} N={N:6d} K={K:6d} M={M:2d} w4a16 tcgen05 GEMM   graph {t:7.2f} us ({nb / t / 1e3 / PEAK:5.1%})", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "q8":
+        for M in (1, 32, 64):
+            run_q8("qkv70b", 10240, 8192, M)
+            run_q8("down", 3584, 18944, M)
+            run_q8("gate_up", 37888, 3584, M)
+        sys.exit(0)
     Ms = [int(a) for a in sys.argv[1:]] or [1]
     for M in Ms:
         run("qkv", 4608, 3584, M, heads=(28, 4, 128))

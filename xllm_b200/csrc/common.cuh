@@ -36,6 +36,12 @@ extern std::atomic<int> g_pdl_enabled;
     }                                                                         \
   } while (0)
 
+// Every kernel of a decode step asks for the SAME shared-memory carveout (the maximum).  Consecutive kernels with
+// different carveouts force the SM to drain before it is re-partitioned, which defeats programmatic dependent launch:
+// the dependent kernel's prologue (weight / KV prefetch) can then no longer run under its predecessor's tail.
+// XB_SMEM_CARVEOUT=0 leaves the driver's per-kernel heuristic in place (A/B measurements).
+void prefer_max_shared_carveout(const void* kernel);
+
 // Launch helper: counts launches, optionally attaches the PDL attribute.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block,
@@ -56,6 +62,7 @@ inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block,
   cfg.attrs = attr;
   cfg.numAttrs = n;
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(kernel));
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -85,6 +92,7 @@ inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
   cfg.attrs = attr;
   cfg.numAttrs = n;
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(kernel));
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -191,6 +199,38 @@ __device__ __forceinline__ uint8_t scaled_fp8_e4m3(float v, float inv_scale) {
   float x = v * inv_scale;
   float r = fmaxf(-448.0f, fminf(x, 448.0f));
   return (uint8_t)__nv_cvt_float_to_fp8(r, __NV_SATFINITE, __NV_E4M3);
+}
+
+__device__ __forceinline__ uint32_t hmul2_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// int8 weight-only dequant (oracle/quant.py, bits = 8): four unsigned bytes of one weight row (k ascending) -> two bf16x2
+// registers bf16((q - z) * s), bit-exact with the spec: 0x4B0000qq is float(2^23 + q), adding neg_mz = -(2^23 + z) gives
+// q - z exactly, the bf16x2 pack is exact for |q - z| <= 255 and the product by s rounds once.
+__device__ __forceinline__ void w8_dequant_word(uint32_t w, float neg_mz, uint32_t s2, uint32_t& lo, uint32_t& hi) {
+  const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)) + neg_mz;
+  const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651)) + neg_mz;
+  const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652)) + neg_mz;
+  const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653)) + neg_mz;
+  lo = hmul2_bf16x2(pack_bf16x2(f0, f1), s2);
+  hi = hmul2_bf16x2(pack_bf16x2(f2, f3), s2);
+}
+// W8 meta word (bf16 scale | zero << 16) -> bf16x2 scale, -(2^23 + zero)
+__device__ __forceinline__ void w8_meta(uint32_t m, uint32_t& s2, float& neg_mz) {
+  s2 = __byte_perm(m, 0, 0x1010);
+  neg_mz = __uint_as_float(0xCB000000u + (m >> 16));
+}
+
+// mma.sync m16n8k32 e4m3 x e4m3 -> f32 (register-resident fragments; FP8 W8A8 small-M kernel)
+__device__ __forceinline__ void mma_e4m3_16832(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.f32.e4m3.e4m3.f32 "
+      "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 // mma.sync m16n8k16 bf16 x bf16 -> f32 (register-resident fragments; used by

@@ -76,7 +76,8 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
   return 0;
 }
 
-enum { kKindBF16 = 0, kKindFP8 = 1, kKindW4 = 2 };
+enum { kKindBF16 = 0, kKindFP8 = 1, kKindW4 = 2, kKindW8 = 3 };
+constexpr bool kind_is_wq(int kind) { return kind == kKindW4 || kind == kKindW8; }   // weight-only: packed B + converter warps
 
 struct GemmParams {
   __nv_bfloat16* c;
@@ -104,15 +105,15 @@ struct GemmCfg {
   static constexpr int kUmmaK = 32 / kElemA;                       // 16 (bf16) / 32 (fp8) elements = 32 bytes
   static constexpr int kABytes = kCtaM * 128;
   static constexpr int kBBytes = kBlockN * 128;
-  static constexpr int kPackedBytes = kKind == kKindW4 ? kBlockN * kBlockK / 2 : 0;   // int4 tile
-  static constexpr int kMetaBytes = kKind == kKindW4 ? kBlockN * 4 : 0;
+  static constexpr int kPackedBytes = kKind == kKindW4 ? kBlockN * kBlockK / 2 : (kKind == kKindW8 ? kBlockN * kBlockK : 0);   // int4 / int8 tile
+  static constexpr int kMetaBytes = kind_is_wq(kKind) ? kBlockN * 4 : 0;
   // BF16 / FP8: a stage holds the A and B tiles.  W4: a stage holds A + the PACKED int4 B tile + its scale/zero words
   // (small, so the TMA ring can be deep enough to cover HBM latency) and the dequantised bf16 B lives in a separate
   // 2-deep ring written by the converter warps.
-  static constexpr int kStageBytes = kKind == kKindW4 ? kABytes + kPackedBytes + ((kMetaBytes + 1023) / 1024) * 1024
+  static constexpr int kStageBytes = kind_is_wq(kKind) ? kABytes + kPackedBytes + ((kMetaBytes + 1023) / 1024) * 1024
                                                       : kABytes + kBBytes;
-  static constexpr int kBStages = kKind == kKindW4 ? 2 : 0;
-  static constexpr int kConvWarps = kKind == kKindW4 ? 8 : 0;      // two converter warps per SM sub-partition
+  static constexpr int kBStages = kind_is_wq(kKind) ? 2 : 0;
+  static constexpr int kConvWarps = kind_is_wq(kKind) ? 8 : 0;      // two converter warps per SM sub-partition
   static constexpr int kEpiStageBytes = kNumEpiWarps * 2 * 4096;   // per epilogue warp: 2 x [32 rows x 64 cols] bf16
   static constexpr int kBudget = 227 * 1024 - 1024 - 512 - kEpiStageBytes - kBStages * kBBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
@@ -175,7 +176,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (kKind == kKindW4) tma_prefetch_desc(&tmap_m);
+    if (kind_is_wq(kKind)) tma_prefetch_desc(&tmap_m);
     if (p.use_tma_store) tma_prefetch_desc(&tmap_c);
   }
   if (warp == 1) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
@@ -196,12 +197,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int m_blk = tile % m_blocks, n_blk = tile / m_blocks;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1);
-          if (kKind == kKindW4) {
+          if (kind_is_wq(kKind)) {
             // packed B: the kBlockN/16 row tiles of this k tile are one 2-D TMA box (tensor [N/16][K/64 * 128 words],
             // box [kBlockN/16][128 words], no swizzle) - one instruction instead of kBlockN/16 bulk copies - plus the
             // group's scale/zero words for these kBlockN rows (tensor [K/g][N], box [1][kBlockN])
             mbar_expect_tx(packed_bar + s, Cfg::kPackedBytes + Cfg::kMetaBytes);
-            tma_load_2d(stage_packed(s), &tmap_b, packed_bar + s, kb * 128, n_blk * (kBlockN / 16));
+            // (W8: one byte per weight - 256 words per row tile and k tile instead of 128)
+            tma_load_2d(stage_packed(s), &tmap_b, packed_bar + s, kb * (kKind == kKindW8 ? 256 : 128), n_blk * (kBlockN / 16));
             tma_load_2d(stage_meta(s), &tmap_m, packed_bar + s, n_blk * kBlockN, kb >> p.gshift);
             mbar_expect_tx(full_bar + s, Cfg::kABytes);
             tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, m_blk * Cfg::kCtaM);
@@ -229,11 +231,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t d_tmem = tmem_base + as * Cfg::kAccCols;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar + s, ph);
-        if (kKind == kKindW4) mbar_wait(bready_bar + bs, bph);
+        if (kind_is_wq(kKind)) mbar_wait(bready_bar + bs, bph);
         tc_fence_after_sync();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(stage_a(s));
-          const uint32_t b_addr = smem_u32(kKind == kKindW4 ? b_ring(bs) : stage_b(s));
+          const uint32_t b_addr = smem_u32(kind_is_wq(kKind) ? b_ring(bs) : stage_b(s));
 #pragma unroll
           for (int k = 0; k < Cfg::kBlockK / Cfg::kUmmaK; ++k) {
             const uint64_t db = umma_desc_sw128(b_addr + k * 32);
@@ -245,12 +247,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           umma_commit(empty_bar + s);                 // smem slot is free once these MMAs have read it
-          if (kKind == kKindW4) umma_commit(bempty_bar + bs);
+          if (kind_is_wq(kKind)) umma_commit(bempty_bar + bs);
           if (kb == num_kb - 1) umma_commit(tmem_full + as);
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1; }
-        if (kKind == kKindW4 && ++bs == 2) { bs = 0; bph ^= 1; }
+        if (kind_is_wq(kKind) && ++bs == 2) { bs = 0; bph ^= 1; }
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
@@ -333,8 +335,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (++as == 2) { as = 0; aph ^= 1; }
     }
     if (p.use_tma_store && lane == 0) tma_store_wait_all();
-  } else if (kKind == kKindW4) {
-    // ======================= W4 converters (warps 6..13) =======================
+  } else if (kind_is_wq(kKind)) {
+    // ======================= W4 / W8 converters (warps 6..13) =======================
     // converter warp cw handles row tiles cw, cw+8, ... of the stage; a lane's 16 bytes of packed data are
     // rows (g, g+8) x k in [16t, 16t+16) of its row tile  ->  four 16-byte chunks of the swizzled bf16 tile.
     const int cw = warp - (2 + kNumEpiWarps);
@@ -352,11 +354,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint8_t* bt = b_ring(bs);
 #pragma unroll
         for (int r = cw; r < kBlockN / 16; r += Cfg::kConvWarps) {
-          const uint4 wq = *reinterpret_cast<const uint4*>(pk + r * 512 + lane * 16);
+          uint32_t lo[8], hi[8];   // row g / row g+8: 16 bf16 = 8 packed registers, k ascending
           const uint32_t m0 = mt[r * 16 + g], m1 = mt[r * 16 + g + 8];
+          if constexpr (kKind == kKindW8) {
+            // int8 tile: 32 bytes per lane (row g then row g+8), meta = bf16 scale | zero << 16 (common.cuh w8_dequant_word)
+            const uint4 wa = *reinterpret_cast<const uint4*>(pk + r * 1024 + lane * 32);
+            const uint4 wb = *reinterpret_cast<const uint4*>(pk + r * 1024 + lane * 32 + 16);
+            uint32_t s0, s1;
+            float nz0, nz1;
+            w8_meta(m0, s0, nz0);
+            w8_meta(m1, s1, nz1);
+            const uint32_t* av = &wa.x;
+            const uint32_t* bv = &wb.x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              w8_dequant_word(av[j], nz0, s0, lo[2 * j], lo[2 * j + 1]);
+              w8_dequant_word(bv[j], nz1, s1, hi[2 * j], hi[2 * j + 1]);
+            }
+          } else {
+          const uint4 wq = *reinterpret_cast<const uint4*>(pk + r * 512 + lane * 16);
           const uint32_t s0 = __byte_perm(m0, 0, 0x1010), z0 = __byte_perm(m0, 0, 0x3232);
           const uint32_t s1 = __byte_perm(m1, 0, 0x1010), z1 = __byte_perm(m1, 0, 0x3232);
-          uint32_t lo[8], hi[8];   // row g / row g+8: 16 bf16 = 8 packed registers, k ascending
           const uint32_t* wv = &wq.x;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -375,6 +393,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(hi[2 * j]) : "r"(d), "r"(s1));
             asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(q3), "r"(z1));
             asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(hi[2 * j + 1]) : "r"(d), "r"(s1));
+          }
           }
           // swizzled K-major tile: row n at n*128 bytes, 16-byte chunk c stored at chunk (c ^ (n & 7))
           const int n_lo = r * 16 + g, n_hi = n_lo + 8;
@@ -528,4 +547,39 @@ extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   if (bn == 256) return launch_gemm<kKindW4, 256>(ta, tb, p, (cudaStream_t)stream, &tm);
   return bn == 128 ? launch_gemm<kKindW4, 128>(ta, tb, p, (cudaStream_t)stream, &tm)
                    : launch_gemm<kKindW4, 64>(ta, tb, p, (cudaStream_t)stream, &tm);
+}
+
+// kind W8: B is the tile-packed int8 weight of linear_q8_small_m.cu ([N/16][K/64][32 lanes][8 words]); same pipeline as W4
+// with a 1 KB packed row tile per k64 step and the int8 converter (w8_dequant_word).
+extern "C" int xb_gemm_w8a16(void* c, int64_t ldc, const void* a, int64_t lda, const uint32_t* qweight, const uint32_t* meta,
+                             const void* bias, int M, int N, int K, int group_size, xb_stream_t stream) {
+  if (M == 0 || N == 0) return 0;
+  XB_CHECK(N % 64 == 0 && K % 64 == 0, "gemm_w8a16: N=%d and K=%d must be multiples of 64", N, K);
+  XB_CHECK(group_size >= 64 && K % group_size == 0, "gemm_w8a16: bad group_size %d", group_size);
+  const int tpg = group_size / 64;
+  XB_CHECK((tpg & (tpg - 1)) == 0, "gemm_w8a16: group_size/64 must be a power of two");
+  XB_CHECK(lda % 8 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0, "gemm_w8a16: a alignment");
+  GemmParams p{};
+  p.c = reinterpret_cast<__nv_bfloat16*>(c);
+  p.ldc = ldc;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.qweight = reinterpret_cast<const uint4*>(qweight);
+  p.meta = meta;
+  p.gshift = 0;
+  while ((1 << p.gshift) < tpg) ++p.gshift;
+  p.M = M; p.N = N; p.K = K;
+  int bn = pick_block_n(M, N);
+  if (bn == 256) bn = 128;                  // 256 rows of int8 + the bf16 ring leave too few TMA stages
+  if (bn == 128 && N % 128 != 0) bn = 64;
+  CUtensorMap ta, tb, tm;
+  if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, kBlockM, 64, 2)) return 1;
+  const uint64_t ktiles = K / 64;
+  if (make_tmap_2d_raw(&tb, qweight, CU_TENSOR_MAP_DATA_TYPE_UINT32, N / 16, ktiles * 256, ktiles * 1024, bn / 16, 256,
+                       CU_TENSOR_MAP_SWIZZLE_NONE))
+    return 1;
+  if (make_tmap_2d_raw(&tm, meta, CU_TENSOR_MAP_DATA_TYPE_UINT32, K / group_size, N, (uint64_t)N * 4, 1, bn,
+                       CU_TENSOR_MAP_SWIZZLE_NONE))
+    return 1;
+  return bn == 128 ? launch_gemm<kKindW8, 128>(ta, tb, p, (cudaStream_t)stream, &tm)
+                   : launch_gemm<kKindW8, 64>(ta, tb, p, (cudaStream_t)stream, &tm);
 }

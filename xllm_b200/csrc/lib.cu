@@ -1,7 +1,10 @@
 // Library-level plumbing of libxllm_b200_ops.so: error string, launch counter, PDL switch.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_set>
 
 namespace xb {
 std::atomic<uint64_t> g_launch_count{0};
@@ -12,6 +15,17 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+void prefer_max_shared_carveout(const void* kernel) {
+  static const bool enabled = [] { const char* e = getenv("XB_SMEM_CARVEOUT"); return !e || atoi(e) != 0; }();
+  if (!enabled) return;
+  static std::mutex mu;
+  static std::unordered_set<const void*> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.insert(kernel).second) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
+  }
 }
 }  // namespace xb
 

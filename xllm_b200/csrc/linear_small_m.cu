@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t hsub2_bf16(uint32_t a, uint32_t b) {
   asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
   return d;
 }
-__device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
+__device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {  // (same as hmul2_bf16x2 in common.cuh)
   uint32_t d;
   asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
   return d;
@@ -106,7 +106,8 @@ struct W4Fuse {
 template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth,
           int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */, int kOcc = 2 /* CTAs per SM */,
           int kEpi = 0 /* 0: bias; 1: gate/up rows interleaved, act(gate)*up; 2: rope + KV scatter (qkv) */,
-          bool kXs = false /* x staged (and optionally normalised) in shared memory by the prologue */>
+          bool kXs = false /* x staged (and optionally normalised) in shared memory by the prologue */,
+          bool kExact = false /* exact-weight form (one token tile): scale / zero applied once per group, see below */>
 __global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : kOcc)
 linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
                             int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
@@ -132,7 +133,7 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 
   // kAcc independent accumulator sets (one per k16 step of a tile when registers allow): legacy HMMA has a long
   // issue-to-result latency on sm_100, a single chain per warp leaves the scheduler with nothing eligible
-  constexpr int kAcc = kMT == 1 ? 4 : (kMT == 2 ? 2 : 1);
+  constexpr int kAcc = kExact ? 2 : (kMT == 1 ? 4 : (kMT == 2 ? 2 : 1));
   float accj[kAcc][kMT][4];
 #pragma unroll
   for (int a = 0; a < kAcc; ++a)
@@ -140,6 +141,14 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     for (int m = 0; m < kMT; ++m)
 #pragma unroll
       for (int i = 0; i < 4; ++i) accj[a][m][i] = 0.f;
+
+  // kExact (spec form "exact" of oracle/quant.py): y = sum_g s_g * (sum_{k in g} x_k (128 + q_k) - (128 + z_g) sum_{k in g} x_k).
+  // The nibbles go to the tensor core as the exact bf16 integers 128 + q (one LOP3 per weight pair, no HSUB2 / HMUL2);
+  // sum_k x_k comes from a second MMA against an all-ones A fragment (its accumulator lands in the same (token) slots);
+  // scale and zero are applied in fp32 once per quantisation group: 61 instead of 83 warp instructions per 512-byte tile.
+  static_assert(!kExact || kMT == 1, "the exact-weight form serves one token tile");
+  float yacc[4] = {0.f, 0.f, 0.f, 0.f};     // kExact: running result
+  float accx[4] = {0.f, 0.f, 0.f, 0.f};     // kExact: sum_k x_k of the open group (rows of the ones-MMA are identical)
 
   // running pointers (one 64-bit add per slot instead of a multiply per tile)
   const uint4* wp = qweight + ((int64_t)ntile * ktiles + (int64_t)s_begin * kTG) * 32 + lane;
@@ -262,13 +271,36 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   XRing<kMT> xbuf[2];
   if constexpr (kXs) load_xtile(xbuf[0]);
 
-  auto consume = [&](int i) {
+  // kExact: close the open quantisation group - fold its integer dot products into the fp32 result
+  auto flush_group = [&](const uint2 mt) {
+    const float s0 = bf16lo(mt.x), zo0 = bf16hi(mt.x), s1 = bf16lo(mt.y), zo1 = bf16hi(mt.y);   // scale, 128 + zero
+    float c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      c[i] = accj[0][0][i];
+#pragma unroll
+      for (int a = 1; a < kAcc; ++a) c[i] += accj[a][0][i];
+#pragma unroll
+      for (int a = 0; a < kAcc; ++a) accj[a][0][i] = 0.f;
+    }
+    yacc[0] = fmaf(s0, fmaf(-zo0, accx[0], c[0]), yacc[0]);
+    yacc[1] = fmaf(s0, fmaf(-zo0, accx[1], c[1]), yacc[1]);
+    yacc[2] = fmaf(s1, fmaf(-zo1, accx[2], c[2]), yacc[2]);
+    yacc[3] = fmaf(s1, fmaf(-zo1, accx[3], c[3]), yacc[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) accx[i] = 0.f;
+  };
+  uint2 open_meta = make_uint2(0, 0);     // kExact: meta words of the group being accumulated
+  const int group_tiles = 1 << gshift;
+
+  auto consume = [&](int i, int slot_abs) {
     uint4 wq[kTG];
 #pragma unroll
     for (int u = 0; u < kTG; ++u) wq[u] = lds_128(ring_w + i * kSlotBytes + u * 512);
     const uint2 mt = lds_64(ring_m + i * kSlotBytes);
     const uint32_t s0 = __byte_perm(mt.x, 0, 0x1010), z0 = __byte_perm(mt.x, 0, 0x3232);
     const uint32_t s1 = __byte_perm(mt.y, 0, 0x1010), z1 = __byte_perm(mt.y, 0, 0x3232);
+    if constexpr (kExact) open_meta = mt;
 #pragma unroll
     for (int u = 0; u < kTG; ++u) {
       const int par = (i * kTG + u) & 1;       // compile-time after unrolling (kDepth * kTG is even)
@@ -283,16 +315,27 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
         const uint32_t q1 = lop3_and_or(w >> 4, 0x000f000fu, 0x43004300u);
         const uint32_t q2 = lop3_and_or(w >> 8, 0x000f000fu, 0x43004300u);
         const uint32_t q3 = lop3_and_or(w >> 12, 0x000f000fu, 0x43004300u);
-        const uint32_t a0 = hmul2_bf16(hsub2_bf16(q0, z0), s0);
-        const uint32_t a1 = hmul2_bf16(hsub2_bf16(q1, z1), s1);
-        const uint32_t a2 = hmul2_bf16(hsub2_bf16(q2, z0), s0);
-        const uint32_t a3 = hmul2_bf16(hsub2_bf16(q3, z1), s1);
+        if constexpr (kExact) {
+          const uint32_t* xv = j < 2 ? &xf.lo[0].x : &xf.hi[0].x;
+          const uint32_t b0 = xv[(j & 1) * 2], b1 = xv[(j & 1) * 2 + 1];
+          mma_bf16_16816(accj[j % kAcc][0], q0, q1, q2, q3, b0, b1);
+          mma_bf16_16816(accx, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, b0, b1);
+        } else {
+          const uint32_t a0 = hmul2_bf16(hsub2_bf16(q0, z0), s0);
+          const uint32_t a1 = hmul2_bf16(hsub2_bf16(q1, z1), s1);
+          const uint32_t a2 = hmul2_bf16(hsub2_bf16(q2, z0), s0);
+          const uint32_t a3 = hmul2_bf16(hsub2_bf16(q3, z1), s1);
 #pragma unroll
-        for (int m = 0; m < kMT; ++m) {
-          // lane run element 4j+{0,1} -> b0, 4j+{2,3} -> b1
-          const uint32_t* xv = j < 2 ? &xf.lo[m].x : &xf.hi[m].x;
-          mma_bf16_16816(accj[j % kAcc][m], a0, a1, a2, a3, xv[(j & 1) * 2], xv[(j & 1) * 2 + 1]);
+          for (int m = 0; m < kMT; ++m) {
+            // lane run element 4j+{0,1} -> b0, 4j+{2,3} -> b1
+            const uint32_t* xv = j < 2 ? &xf.lo[m].x : &xf.hi[m].x;
+            mma_bf16_16816(accj[j % kAcc][m], a0, a1, a2, a3, xv[(j & 1) * 2], xv[(j & 1) * 2 + 1]);
+          }
         }
+      }
+      if constexpr (kExact) {
+        // a group ends after every group_tiles k64 tiles (counted from k = 0, so k-split warps agree)
+        if (((slot_abs * kTG + u + 1) & (group_tiles - 1)) == 0) flush_group(mt);
       }
     }
   };
@@ -309,7 +352,7 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 #pragma unroll
     for (int i = 0; i < kDepth; ++i) {
       cp_async_wait<kDepth - 1>();
-      consume(i);
+      consume(i, sl + i);
       if (sl + i + kDepth < s_end)
         issue(i, wp, slot_is_group ? mp : mbase + (int64_t)(((sl + i + kDepth) * kTG) >> gshift) * N);
       cp_async_commit();
@@ -321,19 +364,26 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   cp_async_wait<0>();
 #pragma unroll
   for (int i = 0; i < kDepth; ++i) {
-    if (sl + i < s_end) consume(i);
+    if (sl + i < s_end) consume(i, sl + i);
   }
   pdl_launch_dependents();
   float acc[kMT][4];
+  if constexpr (kExact) {
+    // a k range that ends inside a group (k-split warps with groups wider than a slot) still holds an open partial group
+    if (s_end > s_begin && ((s_end * kTG) & (group_tiles - 1)) != 0) flush_group(open_meta);
 #pragma unroll
-  for (int m = 0; m < kMT; ++m)
+    for (int i = 0; i < 4; ++i) acc[0][i] = yacc[i];
+  } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float v = accj[0][m][i];
+    for (int m = 0; m < kMT; ++m)
 #pragma unroll
-      for (int a = 1; a < kAcc; ++a) v += accj[a][m][i];
-      acc[m][i] = v;
-    }
+      for (int i = 0; i < 4; ++i) {
+        float v = accj[0][m][i];
+#pragma unroll
+        for (int a = 1; a < kAcc; ++a) v += accj[a][m][i];
+        acc[m][i] = v;
+      }
+  }
 
   // c0:(row g, tok 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
   // kGateUp: row g of the tile is gate row 8*ntile+g and row g+8 the matching up row, so SiLU*mul (activation.cu:45-130:
@@ -559,10 +609,14 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   while ((1 << gshift) < tpg) ++gshift;
   const bool tg2 = tpg >= 2;
   const size_t xs_bytes = xs ? w4_xs_bytes(M, K) : 0;
+  // one token tile (M <= 8): the exact-weight form of the spec (oracle/quant.py); XB_W4_EXACT=0 keeps the bf16-weight
+  // form for A/B measurements
+  static const bool exact_default = [] { const char* e = getenv("XB_W4_EXACT"); return !e || atoi(e) != 0; }();
+  const bool exact = exact_default && M <= 8;
   // (tuning note, B200: 3 CTAs/SM at <= 80 registers measured 10-13 % slower than 2 CTAs/SM for every decode shape)
-#define XB_W4_GO(MT, SP, DEPTH, TG, EPI, XS)                                                                       \
+#define XB_W4_GO(MT, SP, DEPTH, TG, EPI, XS, EX)                                                                   \
   {                                                                                                                 \
-    auto kern = linear_w4a16_small_m_kernel<MT, SP, DEPTH, TG, 2, EPI, XS>;                                         \
+    auto kern = linear_w4a16_small_m_kernel<MT, SP, DEPTH, TG, 2, EPI, XS, EX>;                                     \
     static bool attr_done = false; /* per instantiation: static reduction scratch + ring may exceed 48 KB */        \
     if (!attr_done) {                                                                                               \
       XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
@@ -572,9 +626,15 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
     XB_CUDA_OK(launch(kern, grid, block, w4_ring_bytes(DEPTH, TG) + xs_bytes, s, true, yy, y_stride, xx, x_stride,  \
                       qw, meta, bb, M, N, K, gshift, act_mode, fz));                                                \
   }
-#define XB_W4_TG(MT, SP, DP, EPI, XS)                                \
-  if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS) }            \
-  else { XB_W4_GO(MT, SP, DP, 1, EPI, XS) }
+#define XB_W4_TG(MT, SP, DP, EPI, XS)                                          \
+  if constexpr (MT == 1) {                                                     \
+    if (exact) {                                                               \
+      if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS, true) }            \
+      else { XB_W4_GO(MT, SP, DP, 1, EPI, XS, true) }                          \
+    } else if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS, false) }      \
+    else { XB_W4_GO(MT, SP, DP, 1, EPI, XS, false) }                           \
+  } else if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS, false) }        \
+  else { XB_W4_GO(MT, SP, DP, 1, EPI, XS, false) }
   // the fused variants (x staged in shared memory / rope epilogue) exist for one token tile (M <= 8) only
 #define XB_W4_LAUNCH(MT, SP, DP)                                                                               \
   {                                                                                                            \

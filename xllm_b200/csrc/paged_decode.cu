@@ -441,10 +441,12 @@ paged_decode_kernel(const DecodeParams p) {
   // a unit's CTAs ever spin (R <= (n + 1) / 2), the others never wait, and CTAs are dispatched in index order, so the
   // CTAs a spinner waits for are resident or ahead of every spinner in the dispatch queue (the assumption CUB's
   // decoupled look-back makes).
-  __threadfence();
   __syncthreads();
   int32_t* counter = p.counters + 2 * ((int64_t)b * gridDim.y + blockIdx.y);   // [0] arrivals, [1] team members done
-  if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1);
+  if (threadIdx.x == 0) {
+    __threadfence();       // one fence after the CTA barrier publishes every thread's partials (cumulativity)
+    s_ticket = atomicAdd(counter, 1);
+  }
   __syncthreads();
   const int n_arrive = n_parts * C;
   const int team = min(kTeam, (n_arrive + 1) >> 1);
@@ -460,82 +462,79 @@ paged_decode_kernel(const DecodeParams p) {
     } while (seen < n_arrive);
   }
   __syncthreads();
-  __threadfence();
   stamp(5);
-  const int n_splits_m = n_parts;      // number of partials to merge
-  // Stage 1: one warp per head turns the splits' base-2 LSEs into normalised weights in shared memory
-  // (lanes read different splits in parallel: no dependent-load chain).  sm_o is free again: reuse it.
-  float* sm_w = sm_o;                       // [kHeads][n_splits_m]
-  float* sm_lse = sm_m;                     // [kHeads] merged LSE
-  for (int h = warp; h < nheads; h += kWarpsT) {
-    const int64_t base = ((int64_t)b * p.num_qo_heads + head0 + h) * p.max_parts;
-    // all of this head's split LSEs in one round trip (<= 8 per lane: max_splits <= 2 * head_dim = 256)
-    float ls[8];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int s = lane + 32 * u;
-      ls[u] = s < n_splits_m ? __ldcg(p.part_lse + base + s) : -INFINITY;
-      mx = fmaxf(mx, ls[u]);
-    }
-    mx = warp_max(mx);
-    const float m_safe = mx == -INFINITY ? 0.f : mx;
-    float wsum = 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      ls[u] = fast_exp2(ls[u] - m_safe);     // 0 for the padding entries
-      wsum += ls[u];
-    }
-    wsum = warp_sum(wsum);
-    const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int s = lane + 32 * u;
-      if (s < n_splits_m) sm_w[h * n_splits_m + s] = ls[u] * inv;
-    }
-    if (lane == 0) sm_lse[h] = wsum > 0.f ? mx + log2f(wsum) : -INFINITY;
-  }
-  __syncthreads();
-  // Stage 2: this member's slice of the (head, 4 d) items; 8 lanes share an item and stride over the partials, so every
-  // thread has all its loads (<= n_parts / 8) in flight at once: one round trip to L2
+  // This member's slice of the (head, 4 d) items.  8 lanes share an item and stride over the partials: every lane loads
+  // the LSEs and the partial outputs of ITS partials together (all addresses known up front: ONE round trip to L2),
+  // the softmax weights across partials are then formed with 8-lane shuffles - no shared memory, no second pass.
   {
+    const int n_splits_m = n_parts;
     const int live_items = nheads * (kD / 4);
     const int per = (live_items + team - 1) / team;
     const int first = member * per, lim = min(live_items, first + per);
     const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    constexpr int kMaxPer = 32;                      // partials per lane: max_parts (<= 2 * 128) / 8
     for (int base_it = first; base_it < lim; base_it += kWarpsT * 4) {
       const int it = base_it + grp;
       const bool ok = it < lim;
       const int h = ok ? it / (kD / 4) : 0, d4 = ok ? (it % (kD / 4)) * 4 : 0;
       const int qh = head0 + h;
-      const float4* src = reinterpret_cast<const float4*>(p.part_o + (((int64_t)b * p.num_qo_heads + qh) * p.max_parts) * kD + d4);
-      const float* wrow = sm_w + h * n_splits_m;
+      const int64_t slot0 = ((int64_t)b * p.num_qo_heads + qh) * p.max_parts;
+      const float4* src = reinterpret_cast<const float4*>(p.part_o + slot0 * kD + d4);
+      const float* lsrc = p.part_lse + slot0;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) {
-        for (int s0 = sub; s0 < n_splits_m; s0 += 64) {
-          float4 v[8];
+      float mx = -INFINITY, wsum = 0.f;
+      // pass over this lane's partials in batches of 4 (registers), keeping a running maximum like the main loop
+      for (int s0 = sub; s0 < n_splits_m; s0 += 32) {
+        float4 v[4];
+        float ls[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)min(s0 + 8 * u, n_splits_m - 1) * (kD / 4));
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float w = s0 + 8 * u < n_splits_m ? wrow[s0 + 8 * u] : 0.f;
-            acc.x += v[u].x * w; acc.y += v[u].y * w; acc.z += v[u].z * w; acc.w += v[u].w * w;
-          }
+        for (int u = 0; u < 4; ++u) {
+          const int sidx = s0 + 8 * u;
+          const bool live = ok && sidx < n_splits_m;
+          ls[u] = live ? __ldcg(lsrc + sidx) : -INFINITY;
+          v[u] = live ? __ldcg(src + (int64_t)sidx * (kD / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        float m_new = fmaxf(fmaxf(fmaxf(ls[0], ls[1]), fmaxf(ls[2], ls[3])), mx);
+        const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+        const float alpha = fast_exp2(mx - m_safe);          // 0 when mx was -inf
+        acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
+        wsum *= alpha;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float w = fast_exp2(ls[u] - m_safe);          // 0 for absent / empty partials
+          wsum += w;
+          acc.x += v[u].x * w; acc.y += v[u].y * w; acc.z += v[u].z * w; acc.w += v[u].w * w;
+        }
+        mx = m_new;
       }
+      (void)kMaxPer;
+      // combine the 8 lanes of the item (fixed xor order: deterministic)
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        const float m_o = __shfl_xor_sync(0xffffffffu, mx, o);
+        const float w_o = __shfl_xor_sync(0xffffffffu, wsum, o);
+        float4 a_o;
+        a_o.x = __shfl_xor_sync(0xffffffffu, acc.x, o);
+        a_o.y = __shfl_xor_sync(0xffffffffu, acc.y, o);
+        a_o.z = __shfl_xor_sync(0xffffffffu, acc.z, o);
+        a_o.w = __shfl_xor_sync(0xffffffffu, acc.w, o);
+        const float m_new = fmaxf(mx, m_o);
+        const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+        const float sa = fast_exp2(mx - m_safe), sb = fast_exp2(m_o - m_safe);
+        acc.x = acc.x * sa + a_o.x * sb;
+        acc.y = acc.y * sa + a_o.y * sb;
+        acc.z = acc.z * sa + a_o.z * sb;
+        acc.w = acc.w * sa + a_o.w * sb;
+        wsum = wsum * sa + w_o * sb;
+        mx = m_new;
       }
       if (ok && sub == 0) {
+        const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
         uint2 ob;
-        ob.x = pack_bf16x2(acc.x, acc.y);
-        ob.y = pack_bf16x2(acc.z, acc.w);
+        ob.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+        ob.y = pack_bf16x2(acc.z * inv, acc.w * inv);
         *reinterpret_cast<uint2*>(p.o + (int64_t)b * p.o_stride_n + (int64_t)qh * p.o_stride_h + d4) = ob;
-        if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = sm_lse[h];
+        if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = wsum > 0.f ? mx + log2f(wsum) : -INFINITY;
       }
     }
   }

@@ -163,6 +163,15 @@ void cutlass_scaled_mm(torch::Tensor& c, torch::Tensor const& a, torch::Tensor c
   TORCH_CHECK(a.scalar_type() == torch::kFloat8_e4m3fn && b.scalar_type() == torch::kFloat8_e4m3fn, "fp8 e4m3 inputs expected");
   TORCH_CHECK(c.scalar_type() == torch::kBFloat16, "only bfloat16 output is implemented");
   const at::cuda::OptionalCUDAGuard guard(device_of(a));
+  if (a.size(0) <= 64 && a.size(1) % 64 == 0) {
+    // decode: the HBM-streaming swap-AB kernel (the reference's M <= 16 / <= 64 buckets,
+    // c3x/scaled_mm_sm100_fp8_dispatch.cuh:148-287)
+    ok(xb_linear_fp8_small_m(c.data_ptr(), c.stride(0), a.data_ptr(), a.stride(0), b.data_ptr(), a_scales.data_ptr<float>(),
+                             (int)a_scales.numel(), b_scales.data_ptr<float>(), (int)b_scales.numel(),
+                             bias ? bias->data_ptr() : nullptr, (int)a.size(0), (int)b.size(1), (int)a.size(1), stream()),
+       "cutlass_scaled_mm");
+    return;
+  }
   ok(xb_gemm_fp8_scaled(c.data_ptr(), c.stride(0), a.data_ptr(), a.stride(0), b.data_ptr(), a_scales.data_ptr<float>(),
                         (int)a_scales.numel(), b_scales.data_ptr<float>(), (int)b_scales.numel(),
                         bias ? bias->data_ptr() : nullptr, (int)a.size(0), (int)b.size(1), (int)a.size(1), stream()),
@@ -281,6 +290,31 @@ torch::Tensor w4a16_linear(const torch::Tensor& x, const torch::Tensor& qweight,
   else
     ok(xb_gemm_w4a16(out.data_ptr(), N, x2.data_ptr(), x2.stride(0), qw, mt, bp, (int)M, (int)N, (int)K, (int)group_size, stream()),
        "w4a16_linear");
+  auto shape = x.sizes().vec();
+  shape.back() = N;
+  return out.view(shape);
+}
+
+torch::Tensor w8a16_linear(const torch::Tensor& x, const torch::Tensor& qweight, const torch::Tensor& meta, int64_t group_size,
+                           const std::optional<torch::Tensor>& bias) {
+  need_bf16(x, "x");
+  need_dtype(qweight, torch::kInt32, "qweight");
+  need_dtype(meta, torch::kInt32, "meta");
+  if (bias.has_value() && bias->defined()) need_bf16(*bias, "bias");
+  XB_GUARD(x);
+  auto x2 = x.reshape({-1, x.size(-1)});
+  if (x2.stride(-1) != 1) x2 = x2.contiguous();
+  const int64_t M = x2.size(0), K = x2.size(1), N = meta.size(1);
+  auto out = torch::empty({M, N}, x.options());
+  const void* bp = bias.has_value() && bias->defined() ? bias->data_ptr() : nullptr;
+  auto* qw = reinterpret_cast<const uint32_t*>(qweight.data_ptr());
+  auto* mt = reinterpret_cast<const uint32_t*>(meta.data_ptr());
+  if (M <= 16)
+    ok(xb_linear_w8a16_small_m(out.data_ptr(), N, x2.data_ptr(), x2.stride(0), qw, mt, bp, (int)M, (int)N, (int)K, (int)group_size, stream()),
+       "w8a16_linear");
+  else
+    ok(xb_gemm_w8a16(out.data_ptr(), N, x2.data_ptr(), x2.stride(0), qw, mt, bp, (int)M, (int)N, (int)K, (int)group_size, stream()),
+       "w8a16_linear");
   auto shape = x.sizes().vec();
   shape.back() = N;
   return out.view(shape);

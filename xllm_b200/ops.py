@@ -34,6 +34,12 @@ def _cuda_bf16(t, name):
     _need(t.dtype == BF16, f"{name} must be bfloat16, got {t.dtype}")
 
 
+# largest M served by the HBM-streaming small-M kernels before the 128-row tcgen05 GEMMs take over (the streaming kernels
+# read the weight once per launch; at M = 64 they still move fewer bytes per flop than a 128-row tile wastes)
+FP8_SMALL_M_MAX = 64
+WQ_SMALL_M_MAX = 16
+
+
 # ---- K7 ---------------------------------------------------------------------
 def rms_norm(output: torch.Tensor, input: torch.Tensor, weight: torch.Tensor, eps: float) -> None:
     """cuda_ops_api.h:157-160 / norm.cu:430-460."""
@@ -315,6 +321,13 @@ def cutlass_scaled_mm(c, a, b, a_scales, b_scales, bias=None) -> None:
     _need(a_scales.numel() in (1, M) and b_scales.numel() in (1, N), "scale numel must be 1 or M / N")
     if bias is not None:
         _need(bias.numel() == N and bias.is_contiguous() and bias.dim() == 1 and bias.dtype == BF16, "bias must be [N] bf16")
+    if M <= FP8_SMALL_M_MAX and K % 64 == 0:
+        # decode: weights streamed once, tokens in the n8 slot of mma.sync e4m3 (the reference's swap-AB buckets,
+        # scaled_mm_sm100_fp8_dispatch.cuh:148-287)
+        check(lib().xb_linear_fp8_small_m(_p(c), c_i64(c.stride(0)), _p(a), c_i64(a.stride(0)), _p(b), _p(a_scales),
+                                          c_i32(a_scales.numel()), _p(b_scales), c_i32(b_scales.numel()), _p(bias),
+                                          c_i32(M), c_i32(N), c_i32(K), _stream()), "cutlass_scaled_mm (small M)")
+        return
     check(lib().xb_gemm_fp8_scaled(_p(c), c_i64(c.stride(0)), _p(a), c_i64(a.stride(0)), _p(b), _p(a_scales),
                                    c_i32(a_scales.numel()), _p(b_scales), c_i32(b_scales.numel()), _p(bias), c_i32(M),
                                    c_i32(N), c_i32(K), _stream()), "cutlass_scaled_mm")
@@ -473,3 +486,35 @@ def rope_and_cache_packed(positions, qkv_packed, qkv_out, cos_sin_cache, slot_id
                                               c_i64(qkv_out.stride(0)), _p(cos_sin_cache), _p(slot_ids), _p(key_cache),
                                               _p(value_cache), c_i32(num_heads), c_i32(num_kv_heads), c_i32(head_dim),
                                               c_i32(T), _stream()), "rope_and_cache_packed")
+
+
+# ---- W8A16 ------------------------------------------------------------------------------------------------------
+def w8a16_linear_small_m(x, qweight, meta, group_size, bias=None, out=None):
+    """additive boundary: y = x . dequant(W8)^T (+bias), M <= 64.  qweight/meta from quant.pack_w8."""
+    _cuda_bf16(x, "x")
+    _need(qweight.dtype == torch.int32 and meta.dtype == torch.int32, "qweight/meta must be int32 storage")
+    M, K = x.shape
+    N = meta.size(1)
+    y = out if out is not None else torch.empty(M, N, dtype=BF16, device=x.device)
+    check(lib().xb_linear_w8a16_small_m(_p(y), c_i64(y.stride(0)), _p(x), c_i64(x.stride(0)), _p(qweight), _p(meta),
+                                        _p(bias), c_i32(M), c_i32(N), c_i32(K), c_i32(group_size), _stream()),
+          "w8a16_linear_small_m")
+    return y
+
+
+def gemm_w8a16(x, qweight, meta, group_size, bias=None, out=None):
+    """always the tcgen05 dequant-GEMM (tests / benchmarks)."""
+    _cuda_bf16(x, "x")
+    M, K = x.shape
+    N = meta.size(1)
+    y = out if out is not None else torch.empty(M, N, dtype=BF16, device=x.device)
+    check(lib().xb_gemm_w8a16(_p(y), c_i64(y.stride(0)), _p(x), c_i64(x.stride(0)), _p(qweight), _p(meta), _p(bias),
+                              c_i32(M), c_i32(N), c_i32(K), c_i32(group_size), _stream()), "gemm_w8a16")
+    return y
+
+
+def w8a16_linear(x, qweight, meta, group_size, bias=None, out=None):
+    """weight-only int8 linear for any M: streaming kernel for decode batches, tcgen05 dequant-GEMM above."""
+    if x.shape[0] <= WQ_SMALL_M_MAX:
+        return w8a16_linear_small_m(x, qweight, meta, group_size, bias, out)
+    return gemm_w8a16(x, qweight, meta, group_size, bias, out)

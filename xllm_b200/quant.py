@@ -65,6 +65,30 @@ def pack_w4_qkv_rope(q, scales, zeros, num_heads, num_kv_heads, head_dim, group_
     return qw, meta, (bias[idx].contiguous() if bias is not None else None)
 
 
+def pack_w8(q: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor, group_size: int = 128):
+    """W8A16: q uint8 [N,K] in 0..255 -> (qweight int32 [N/16,K/64,32,8], meta int32 [K/g,N] = bf16 scale | zero << 16).
+    Lane 4g+t of a 16x64 tile holds rows g (words 0..3) and g+8 (words 4..7), k in [16t, 16t+16) ascending
+    (csrc/linear_q8_small_m.cu; the same tensor feeds the tcgen05 GEMM kind W8)."""
+    N, K = q.shape
+    assert N % 16 == 0 and K % 64 == 0 and K % group_size == 0 and group_size % 64 == 0
+    qq = q.to(torch.int32).view(N // 16, 2, 8, K // 64, 4, 4, 4)          # [nt, half, g, kt, t, j, byte]
+    w = qq[..., 0] | (qq[..., 1] << 8) | (qq[..., 2] << 16) | (qq[..., 3] << 24)     # [nt, half, g, kt, t, j]
+    qweight = w.permute(0, 3, 2, 4, 1, 5).reshape(N // 16, K // 64, 32, 8).contiguous()   # [nt, kt, g, t, half, j]
+    s_bits = scales.to(torch.bfloat16).view(torch.int16).to(torch.int32) & 0xFFFF
+    meta = (s_bits | (zeros.to(torch.int32) << 16)).t().contiguous()
+    return qweight, meta
+
+
+def pack_w8_c(q: torch.Tensor) -> torch.Tensor:
+    """byte packing through the C routine (tests pin the two packers against each other)."""
+    N, K = q.shape
+    qc = q.cpu().contiguous()
+    out = torch.empty(N // 16, K // 64, 32, 8, dtype=torch.int32)
+    check(lib().xb_w8_pack_rows(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(qc.data_ptr()), ctypes.c_int(N),
+                                ctypes.c_int(K)), "w8_pack_rows")
+    return out
+
+
 def pack_w4_c(q: torch.Tensor) -> torch.Tensor:
     """Same nibble packing through the C routine (used by tests to pin the two packers against each other)."""
     N, K = q.shape

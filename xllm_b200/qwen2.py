@@ -34,10 +34,15 @@ class Qwen2Config:
     rms_norm_eps: float = 1e-6
     max_position_embeddings: int = 32768
     block_size: int = 128                 # kv_cache_config.cpp:21
-    quant: str = "w4a16"                  # "w4a16" | "bf16" | "fp8" (W8A8 per-tensor static, linear.cpp:137-182)
+    quant: str = "w4a16"                  # "w4a16" | "w8a16" | "bf16" | "fp8" (W8A8 per-tensor static, linear.cpp:137-182)
     group_size: int = 128
     tie_word_embeddings: bool = False
     qkv_bias: bool = True                 # qwen2_attention.cpp:52; Llama: False
+    # Llama-3.1 "rope_scaling" {"rope_type": "llama3", factor, low_freq_factor, high_freq_factor,
+    # original_max_position_embeddings}; None = plain rope_theta.  (The reference's llama.h parses these fields,
+    # models/llm/npu/llama.h:341-346, but builds its table from rope_theta alone, :77-106; the CUDA registry entry of
+    # integration/patches/0002 applies them.)
+    rope_scaling: Optional[dict] = None
     name: str = "Qwen2-7B"
 
     @staticmethod
@@ -54,7 +59,9 @@ class Qwen2Config:
     @staticmethod
     def llama3_70b(**kw):
         """BASELINE configs[3] architecture (the reference registers Llama only under models/llm/npu/llama3.h; the layer
-        graph is Qwen2's without the qkv bias).  NOTE: llama3 rope scaling is not applied (plain rope_theta)."""
+        graph is Qwen2's without the qkv bias).  Llama-3-70B itself has no rope_scaling; pass
+        rope_scaling=dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0,
+        original_max_position_embeddings=8192) for the 3.1 checkpoints."""
         d = dict(hidden_size=8192, num_layers=80, n_heads=64, n_kv_heads=8, head_dim=128, intermediate_size=28672,
                  vocab_size=128256, rope_theta=500000.0, rms_norm_eps=1e-5, quant="fp8", qkv_bias=False,
                  max_position_embeddings=8192, name="Llama-3-70B")
@@ -102,6 +109,8 @@ class Linear:
                 self._x8 = torch.empty(x.shape, dtype=torch.float8_e4m3fn, device=x.device)
             x8, sc = ops.fp8_scaled_quantize(x, self._x8, self.input_scale)
             ops.fp8_scaled_matmul(x8, self.weight, sc, self.weight_scale, BF16, self.bias, out)
+        elif self.kind == "w8a16":
+            ops.w8a16_linear(x, self.qweight, self.meta, self.group_size, self.bias, out)
         else:
             ops.w4a16_linear(x, self.qweight, self.meta, self.group_size, self.bias, out)
         return out
@@ -124,6 +133,13 @@ class Qwen2Weights:
             lin.weight = (torch.randn(N, K, generator=gen, device=device)).clamp(-3, 3).to(torch.float8_e4m3fn)
             lin.weight_scale = torch.full((1,), std, dtype=torch.float32, device=device)
             lin.input_scale = torch.full((1,), 0.05, dtype=torch.float32, device=device)
+        elif kind == "w8a16":
+            lin.qweight = torch.randint(-2 ** 31, 2 ** 31 - 1, (N // 16, K // 64, 32, 8), generator=gen, device=device,
+                                        dtype=torch.int32)
+            s = (torch.rand(K // gs, N, generator=gen, device=device) * 0.5 + 0.75) * (std * 3.0 / 127.5)
+            z = torch.randint(120, 136, (K // gs, N), generator=gen, device=device)
+            s_bits = s.to(BF16).view(torch.int16).to(torch.int32) & 0xFFFF
+            lin.meta = (s_bits | (z.to(torch.int32) << 16)).contiguous()
         else:
             # uniform nibbles + scales such that w ~ N(0, std^2)-like spread; generated directly in packed form
             lin.qweight = torch.randint(-2 ** 31, 2 ** 31 - 1, (N // 16, K // 64, 32, 4), generator=gen, device=device,
@@ -175,12 +191,32 @@ class Qwen2Weights:
         return n
 
 
+def llama3_scale_inv_freq(inv_freq: torch.Tensor, factor: float, low_freq_factor: float, high_freq_factor: float,
+                          original_max_position_embeddings: int) -> torch.Tensor:
+    """Llama-3.1 frequency scaling (the published "llama3" rope_type): wavelengths above original_max / low_freq_factor
+    are slowed by `factor`, below original_max / high_freq_factor kept, the band between interpolated."""
+    import math
+    low_wl = original_max_position_embeddings / low_freq_factor
+    high_wl = original_max_position_embeddings / high_freq_factor
+    wavelen = 2.0 * math.pi / inv_freq
+    smooth = (original_max_position_embeddings / wavelen - low_freq_factor) / (high_freq_factor - low_freq_factor)
+    mid = (1.0 - smooth) * inv_freq / factor + smooth * inv_freq
+    scaled = torch.where(wavelen > low_wl, inv_freq / factor, inv_freq)
+    return torch.where((wavelen <= low_wl) & (wavelen >= high_wl), mid, scaled)
+
+
 def make_cos_sin_cache(cfg: Qwen2Config, device):
     """[max_pos, head_dim] = [cos_half | sin_half] in bf16 - the pre-sliced layout the CUDA kernel reads
     (rotary_embedding.cpp:31-52, rotary_embedding_util.cpp:115-144,303-310; rope_theta passes through int64)."""
     rot = cfg.head_dim
     sl = torch.arange(0, rot, 2, dtype=torch.float32)
     inv_freq = 1.0 / torch.pow(torch.tensor(float(int(cfg.rope_theta)), dtype=torch.float32), sl / float(rot))
+    rs = cfg.rope_scaling
+    if rs is not None:
+        if rs.get("rope_type", rs.get("type")) != "llama3":
+            raise ValueError(f"unsupported rope_scaling {rs}")
+        inv_freq = llama3_scale_inv_freq(inv_freq, float(rs["factor"]), float(rs["low_freq_factor"]),
+                                         float(rs["high_freq_factor"]), int(rs["original_max_position_embeddings"]))
     t = torch.arange(cfg.max_position_embeddings, dtype=torch.float32)
     freqs = torch.einsum("i,j->ij", t, inv_freq)
     return torch.cat([freqs.cos(), freqs.sin()], dim=-1).to(BF16).to(device)
@@ -245,6 +281,9 @@ class Qwen2DecodeRunner:
         self.qkv_raw = torch.empty_like(self.qkv)       # rope-pair packed projection output when RoPE is not fused
         self.res_pp = [torch.empty(B, H, dtype=BF16, device=dev) for _ in range(2)]   # residual stream ping-pong (fused GEMVs)
         w4 = cfg.quant == "w4a16" and all(L["qkv"].kind == "w4a16" for L in weights.layers)
+        import os
+        if os.environ.get("XB_FUSE_GEMV") is not None:          # A/B measurements
+            fuse_gemv = os.environ["XB_FUSE_GEMV"] != "0"
         self.fuse_gemv = bool(fuse_gemv and w4 and B <= 8 and ops.w4a16_decode_fused_fits(B, H))
         self.attn_out = torch.empty(B, self.q_size, dtype=BF16, device=dev)
         self.gate_up = torch.empty(B, 2 * self.inter, dtype=BF16, device=dev)
