@@ -234,6 +234,11 @@ int xb_linear_w4a16_gate_up_act_small_m(void* y, int64_t y_stride, const void* x
  *             2: qkv_proj: +bias, NeoX RoPE on q / k heads (rope.cu:27-137) and scatter of the new k / v rows into
  *                the paged caches (reshape_paged_cache.cu:23-62); weight rows packed by quant.pack_w4_qkv_rope;
  *                y [M, N] in logical [q | k | v] order.
+ *             3: row-parallel projection (o_proj / down_proj) as the PRODUCER of a split RMSNorm:
+ *                r = bf16(bf16(y) + residual_in) -> residual_out, per-(16-row tile, token) sums of r^2 ->
+ *                norm_stats_out [N/16][8] f32 (fixed order, no atomics); y is not written.
+ *   split norm consumer: norm_stats_in != NULL (with norm_weight): x is the residual stream r, the K/16 partials are
+ *             summed in a fixed order and x is normalised while it is staged - one L2 round trip in the prologue.
  * xb_linear_w4a16_decode_fused_fits(M, K) tells whether the [M, K] activation block fits the shared-memory stage. */
 int xb_linear_w4a16_decode_fused(void* y, int64_t y_stride, const void* x, int64_t x_stride,
                                  const uint32_t* qweight, const uint32_t* meta, const void* bias,
@@ -241,7 +246,8 @@ int xb_linear_w4a16_decode_fused(void* y, int64_t y_stride, const void* x, int64
                                  const void* residual_in, void* residual_out, int stage_x, int epilogue,
                                  int act_mode, const int64_t* positions, const void* cos_sin_cache,
                                  const int32_t* slot_ids, void* k_cache, void* v_cache, int num_heads,
-                                 int num_kv_heads, int head_dim, xb_stream_t stream);
+                                 int num_kv_heads, int head_dim, const float* norm_stats_in,
+                                 float* norm_stats_out, xb_stream_t stream);
 int xb_linear_w4a16_decode_fused_fits(int M, int K);
 
 /* ---- W8A16 weight-only linears (north-star "W4A16 / W8A16 / FP8"; additive boundary) -------------

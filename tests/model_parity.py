@@ -28,10 +28,7 @@ def build_case(cfg, B, kv_lens, seed=2026, w_std=0.05):
             w8 = (w.float() / w_scale).clamp(-448, 448).to(torch.float8_e4m3fn)
             return dict(w8=w8, w_scale=w_scale, in_scale=torch.tensor([0.02]), b=b)
         q, s, z = OQ.quantize(w, 8 if cfg.quant == "w8a16" else 4, cfg.group_size)
-        d = dict(q=q, s=s, z=z, b=b, w=OQ.dequantize(q, s, z, cfg.group_size))
-        if cfg.quant == "w4a16":
-            d["w_exact"] = OQ.dequantize_exact(q, s, z, cfg.group_size)    # form of the decode kernel at M <= 8
-        return d
+        return dict(q=q, s=s, z=z, b=b, w=OQ.dequantize(q, s, z, cfg.group_size))
 
     W = dict(embed=(torch.randn(cfg.vocab_size, H, generator=g) * 0.5).to(BF16),
              final_norm=(1 + 0.1 * torch.randn(H, generator=g)).to(BF16), layers=[])
@@ -63,9 +60,6 @@ def _olin(d):
     """oracle linear for one logical weight dict (bf16 / dequantised W4 / fp8 W8A8 static)."""
     if "w8" in d:
         return lambda x, _w=None, b=None: O.fp8_linear(x, d["w8"], d["w_scale"], d["in_scale"], d["b"])
-    if "w_exact" in d:
-        # W4A16: the library computes the exact-weight form for M <= 8 tokens, the bf16-weight form above (oracle/quant.py)
-        return lambda x, _w=None, b=None: O.linear(x, d["w_exact"] if OQ.w4a16_form(x.shape[0]) == "exact" else d["w"], d["b"])
     return lambda x, _w=None, b=None: O.linear(x, d["w"], d["b"])
 
 

@@ -106,7 +106,7 @@ def test_fused_rope_epilogue_equals_gemv_then_rope(M, nh, nkv, D, K, staged, bui
     assert torch.equal(kc2, kc1) and torch.equal(vc2, vc1), "fused KV scatter differs"
     # and against the oracle end to end (linear on the logical rows -> RoPE), within the linear's 1-ulp noise:
     # a 1-ulp flip of one linear output moves a rotated value by at most that ulp (|cos|, |sin| <= 1)
-    y = Q.linear_wna16(x.cpu(), q, s, z, gs, b, weights=Q.w4a16_form(M))
+    y = Q.linear_wna16(x.cpu(), q, s, z, gs, b)
     full, _, _ = _oracle_rope_cache(y, pos, slots, cs, kc, vc, nh, nkv, D)
     qs = nh * D
     mag = y.float().abs()
@@ -139,11 +139,11 @@ def test_fused_norm_prologue(M, N, K, epi, with_res, built_lib):
         normed, res_ref = O.rms_norm(x, nw, eps), x
     if epi == "act_mul":
         qw, meta, bp = quant.pack_w4_gate_up(q, s, z, gs, b)
-        ref = O.act_and_mul(Q.linear_wna16(normed, q, s, z, gs, b, weights=Q.w4a16_form(M)), "silu")
+        ref = O.act_and_mul(Q.linear_wna16(normed, q, s, z, gs, b), "silu")
     else:
         qw, meta = quant.pack_w4(q, s, z, gs)
         bp = b
-        ref = Q.linear_wna16(normed, q, s, z, gs, b, weights=Q.w4a16_form(M))
+        ref = Q.linear_wna16(normed, q, s, z, gs, b)
     res_out = torch.full((M, K), 7.0, dtype=BF16, device=DEV)
     y = ops.w4a16_decode_fused(x.to(DEV), qw.to(DEV), meta.to(DEV), gs, bp.to(DEV) if bp is not None else None,
                                norm_weight=nw.to(DEV), eps=eps, residual_in=res.to(DEV) if with_res else None,
@@ -155,8 +155,7 @@ def test_fused_norm_prologue(M, N, K, epi, with_res, built_lib):
         assert_close_bf16(y, ref, ulps=4, rel_l2=3e-3, what=f"norm + gate_up + act M={M}", atol=2.0 ** -12)
     else:
         wd = Q.dequantize(q, s, z, gs)
-        woff = (q.float() + 128.0).view(N, K // gs, gs) * s.float().unsqueeze(-1)       # offset-binary terms, see test_gpu_linear
-        scale = (normed.float().abs() @ (wd.float().abs() + woff.view(N, K) / 32.0).t() + (b.float().abs() if b is not None else 0))
+        scale = normed.float().abs() @ wd.float().abs().t() + (b.float().abs() if b is not None else 0)
         # rstd is summed in a different order than the oracle's: an occasional 1-ulp flip of a normalised activation
         # perturbs the dot product by 2^-8 of ONE term - covered by 3e-5 of the sum of the terms
         assert_close_sum(y, ref, scale, rtol=3e-5, what=f"norm prologue + linear M={M} N={N} K={K}")
@@ -178,3 +177,56 @@ def test_staged_x_is_bit_identical(N, K, built_lib):
         y1 = ops.w4a16_decode_fused(x, qw, meta, gs, stage_x=True)
         torch.cuda.synchronize()
         assert torch.equal(y0, y1), f"M={M}: staging x in shared memory changed the result"
+
+
+@pytest.mark.parametrize("H,Kin,Nout,epi", [(3584, 3584, 4608, "none"), (3584, 18944, 37888, "act_mul"), (896, 896, 1152, "none"),
+                                            (8192, 8192, 1280, "none")])
+@pytest.mark.parametrize("M", [1, 3, 8])
+def test_split_rms_norm_producer_and_consumer(M, H, Kin, Nout, epi, built_lib):
+    """RMSNorm split over two linears: the row-parallel projection (producer, epilogue "residual_stats") adds the
+    residual and emits the updated residual stream + per-tile partial sums of its squares; the next linear (consumer,
+    norm_stats_in) normalises that stream while staging it.  Checked against fused_add_rms_norm -> linear of the oracle:
+    (a) residual stream vs bf16(bf16(linear) + residual) within the linear's 1-ulp noise, (b) the partials sum to the sum of
+    squares of the stream the kernel wrote, (c) the consumer against the oracle fed with the kernel's own stream."""
+    from xllm_b200 import ops, quant
+    if not ops.w4a16_decode_fused_fits(M, H):
+        pytest.skip("the consumer's activation block does not fit the shared-memory stage")
+    gs = 128 if Kin % 128 == 0 and H % 128 == 0 else 64
+    g = torch.Generator().manual_seed(41)
+    q1, s1, z1, _ = _w4(H, Kin, gs, 5, bias=False)               # producer: [H, Kin] (o_proj / down_proj)
+    q2, s2, z2, b2 = _w4(Nout, H, gs, 6, bias=(Nout == 4608))    # consumer: [Nout, H] (qkv / gate_up)
+    x = torch.randn(M, Kin, generator=g).to(BF16)
+    res = torch.randn(M, H, generator=g).to(BF16)
+    nw = (1 + 0.1 * torch.randn(H, generator=g)).to(BF16)
+    eps = 1e-6
+    qw1, m1 = quant.pack_w4(q1, s1, z1, gs)
+    res_out = torch.empty(M, H, dtype=BF16, device=DEV)
+    stats = torch.full((H // 16, 8), -1.0, dtype=torch.float32, device=DEV)
+    ops.w4a16_decode_fused(x.to(DEV), qw1.to(DEV), m1.to(DEV), gs, None, None, epilogue="residual_stats", residual_in=res.to(DEV),
+                           residual_out=res_out, norm_stats_out=stats, stage_x=ops.w4a16_decode_fused_fits(M, Kin))
+    torch.cuda.synchronize()
+    y1 = Q.linear_wna16(x, q1, s1, z1, gs, None)
+    r_ref = (y1.float() + res.float()).to(BF16)
+    assert_close_bf16(res_out, r_ref, ulps=2, rel_l2=1e-3, what="residual stream of the producer", atol=2.0 ** -8)
+    r = res_out.cpu()
+    ss = stats.cpu()
+    assert torch.all(ss[:, M:] == 0), "partials of absent tokens must be zero"
+    tile_sq = (r.float() ** 2).view(M, H // 16, 16).sum(-1).t()          # [H/16, M]
+    assert torch.allclose(ss[:, :M], tile_sq, rtol=1e-6, atol=0), "per-tile partial sums of squares"
+    # consumer on the kernel's own stream
+    if epi == "act_mul":
+        qw2, m2, bp = quant.pack_w4_gate_up(q2, s2, z2, gs, b2)
+    else:
+        qw2, m2 = quant.pack_w4(q2, s2, z2, gs)
+        bp = b2
+    y = ops.w4a16_decode_fused(res_out, qw2.to(DEV), m2.to(DEV), gs, bp.to(DEV) if bp is not None else None, norm_weight=nw.to(DEV),
+                               eps=eps, norm_stats_in=stats, epilogue=epi, act_mode="silu")
+    torch.cuda.synchronize()
+    normed = O.rms_norm(r, nw, eps)
+    ref = Q.linear_wna16(normed, q2, s2, z2, gs, b2)
+    if epi == "act_mul":
+        assert_close_bf16(y, O.act_and_mul(ref, "silu"), ulps=4, rel_l2=3e-3, what="split norm + gate_up + act", atol=2.0 ** -12)
+    else:
+        wd = Q.dequantize(q2, s2, z2, gs)
+        scale = normed.float().abs() @ wd.float().abs().t() + (b2.float().abs() if b2 is not None else 0)
+        assert_close_sum(y, ref, scale, rtol=3e-5, what=f"split norm consumer M={M} N={Nout} K={H}")

@@ -162,7 +162,4 @@ def test_w4a16_decode_and_prefill_kernels_agree(built_lib):
     y1 = ops.gemm_w4a16(x, qw.to(DEV), meta.to(DEV), gs)
     y2 = ops.w4a16_linear_small_m(x, qw.to(DEV), meta.to(DEV), gs)
     wd = Q.dequantize(q, s, z, gs)
-    # M = 16: both kernels compute the bf16-weight form (the decode kernel switches to the exact-weight form at M <= 8)
     assert_close_sum(y1, y2, _abs_scale(x.cpu(), wd), rtol=1e-5, what="w4 prefill vs decode kernel")
-    y3 = ops.w4a16_linear_small_m(x[:8], qw.to(DEV), meta.to(DEV), gs)
-    assert_close_bf16(y3, y1[:8], ulps=1e9, rel_l2=4e-3, what="exact-weight decode form vs bf16-weight prefill form")

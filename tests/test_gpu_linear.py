@@ -58,22 +58,12 @@ def test_linear_w4a16_small_m(M, N, K, sym, built_lib):
     q, s, z = Q.quantize(w, 4, gs, sym=sym)
     x = torch.randn(M, K, generator=g).to(BF16)
     b = torch.randn(N, generator=g).to(BF16) if N == 4608 else None
-    form = Q.w4a16_form(M)                      # M <= 8: exact-weight form, else bf16-weight form (oracle/quant.py)
-    ref = Q.linear_wna16(x, q, s, z, gs, b, weights=form)
+    ref = Q.linear_wna16(x, q, s, z, gs, b)
     qw, meta = quant.pack_w4(q, s, z, gs)
     y = ops.w4a16_linear_small_m(x.to(DEV), qw.to(DEV), meta.to(DEV), gs, b.to(DEV) if b is not None else None)
     wd = Q.dequantize(q, s, z, gs)
-    scale = _abs_scale(x, wd, b)
-    if form == "exact":
-        # the tensor core accumulates the offset-binary terms x * (128 + q) before the zero point is removed: fp32
-        # accumulation error is relative to THAT magnitude (1e-5 / 32 = 2.6 * 2^-23 per unit of it)
-        woff = (q.float() + 128.0).view(N, K // gs, gs) * s.float().unsqueeze(-1)
-        scale = scale + x.float().abs() @ woff.view(N, K).t() / 32.0
-    assert_close_sum(y, ref, scale, rtol=1e-5, what=f"w4a16 M={M} N={N} K={K} sym={sym} ({form} form)")
+    assert_close_sum(y, ref, _abs_scale(x, wd, b), rtol=1e-5, what=f"w4a16 M={M} N={N} K={K} sym={sym}")
     assert_close_bf16(y, ref, ulps=1e9, rel_l2=1e-3, what="w4a16 rel L2")
-    # the two forms of the spec stay within the per-weight rounding of each other
-    other = Q.linear_wna16(x, q, s, z, gs, b, weights="bf16" if form == "exact" else "exact")
-    assert_close_bf16(y, other, ulps=1e9, rel_l2=4e-3, what="w4a16 vs the other form of the spec")
 
 
 def test_w4a16_dequant_is_bit_exact(built_lib):
@@ -91,10 +81,6 @@ def test_w4a16_dequant_is_bit_exact(built_lib):
         x[torch.arange(64), k0 + torch.arange(64)] = 1.0
         y = ops.w4a16_linear_small_m(x.to(DEV), qw.to(DEV), meta.to(DEV), gs)
         assert torch.equal(y.cpu(), wd[:, k0:k0 + 64].t().contiguous()), f"dequant mismatch in k block {k0}"
-        # exact-weight form (M <= 8): s * ((128 + q) - (128 + z)) is the same product, rounded once at the output
-        for r0 in range(0, 64, 8):
-            y8 = ops.w4a16_linear_small_m(x[r0:r0 + 8].to(DEV), qw.to(DEV), meta.to(DEV), gs)
-            assert torch.equal(y8.cpu(), wd[:, k0 + r0:k0 + r0 + 8].t().contiguous()), f"exact form: k {k0 + r0}"
 
 
 def test_linear_linearity_full_size(built_lib):
@@ -131,7 +117,7 @@ def test_w4a16_gate_up_act_fused(M, I, K, bias, built_lib):
     q, s, z = Q.quantize(w, 4, gs)
     b = (torch.randn(2 * I, generator=g) * 0.1).to(BF16) if bias else None
     x = torch.randn(M, K, generator=g).to(BF16)
-    ref = O.act_and_mul(Q.linear_wna16(x, q, s, z, gs, b, weights=Q.w4a16_form(M)), "silu")
+    ref = O.act_and_mul(Q.linear_wna16(x, q, s, z, gs, b), "silu")
     qw, meta, bi = quant.pack_w4_gate_up(q, s, z, gs, b)
     y = ops.w4a16_gate_up_act(x.to(DEV), qw.to(DEV), meta.to(DEV), gs, "silu", bi.to(DEV) if bi is not None else None)
     # act(gate)*up of two 1-ulp-accurate linears: a flip in either input moves the product by up to ~2 ulps

@@ -101,11 +101,11 @@ def test_w8a16_decode_and_prefill_kernels_agree(built_lib):
 
 
 # ---- FP8 W8A8 small-M ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("N,K", [(4608, 3584), (3584, 18944), (10240, 8192), (1024, 3584), (1000, 512)])
+@pytest.mark.parametrize("N,K", [(4608, 3584), (3584, 18944), (10240, 8192), (1024, 3584), (1008, 512)])
 @pytest.mark.parametrize("M", [1, 7, 16, 32, 64])
 @pytest.mark.parametrize("per_row", [False, True])
 def test_fp8_small_m_matches_oracle(M, N, K, per_row, built_lib):
-    """cutlass_scaled_mm at decode sizes (M <= 64 -> the streaming swap-AB kernel) against the oracle's
+    """the streaming swap-AB kernel behind cutlass_scaled_mm at decode sizes (M <= 64) against the oracle's
     fp8_scaled_matmul (scaled_mm_entry.cu:55-108 semantics) and against the tcgen05 FP8 GEMM on the same inputs."""
     from xllm_b200 import ops
     if N * K > 5e7 and M not in (1, 32):
@@ -118,8 +118,7 @@ def test_fp8_small_m_matches_oracle(M, N, K, per_row, built_lib):
     bias = torch.randn(N, generator=g).to(BF16) if N == 4608 else None
     ref = O.fp8_scaled_matmul(a, b, a_s, b_s, bias)
     c = torch.empty(M, N, dtype=BF16, device=DEV)
-    assert M <= ops.FP8_SMALL_M_MAX
-    ops.cutlass_scaled_mm(c, a.to(DEV), b.to(DEV).t(), a_s.to(DEV), b_s.to(DEV), bias.to(DEV) if bias is not None else None)
+    ops.fp8_scaled_mm_small_m(c, a.to(DEV), b.to(DEV).t(), a_s.to(DEV), b_s.to(DEV), bias.to(DEV) if bias is not None else None)
     scale = (a.float().abs() @ b.float().abs().t()) * a_s.view(-1, 1) * b_s.view(1, -1) + (bias.float().abs() if bias is not None else 0)
     assert_close_sum(c, ref, scale, rtol=1e-5, what=f"fp8 small-M {M}x{N}x{K} per_row={per_row}")
     assert_close_bf16(c, ref, ulps=1e9, rel_l2=1e-3, what="fp8 small-M rel L2")
@@ -145,6 +144,6 @@ def test_fp8_small_m_exact_products(built_lib):
     b = torch.randint(-4, 5, (N, K), generator=g).float().to(E4M3)
     one = torch.ones(1, dtype=torch.float32, device=DEV)
     c = torch.empty(M, N, dtype=BF16, device=DEV)
-    ops.cutlass_scaled_mm(c, a.to(DEV), b.to(DEV).t(), one, one * 0.5, None)
+    ops.fp8_scaled_mm_small_m(c, a.to(DEV), b.to(DEV).t(), one, one * 0.5, None)
     ref = (a.float() @ b.float().t() * 0.5).to(BF16)
     assert torch.equal(c.cpu(), ref)

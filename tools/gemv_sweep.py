@@ -118,7 +118,7 @@ def run_q8(name, N, K, M):
     a8 = torch.randn(M, K, device=DEV).clamp(-3, 3).to(torch.float8_e4m3fn)
     one = torch.ones(1, device=DEV)
     nb = N * K + M * K + M * N * 2
-    fns = [lambda i=i: ops.cutlass_scaled_mm(y, a8, f8[i].t(), one, one, None) for i in range(copies)]
+    fns = [lambda i=i: ops.fp8_scaled_mm_small_m(y, a8, f8[i].t(), one, one, None) for i in range(copies)]
     t = graph_time(fns)
     print(f"{name:8s} N={N:6d} K={K:6d} M={M:2d} fp8 streaming (M<=64) graph {t:7.2f} us ({nb / t / 1e3 / PEAK:5.1%})", flush=True)
     from xllm_b200._lib import c_i32, c_i64, check, lib

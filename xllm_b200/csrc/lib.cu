@@ -17,7 +17,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void prefer_max_shared_carveout(const void* kernel) {
-  static const bool enabled = [] { const char* e = getenv("XB_SMEM_CARVEOUT"); return !e || atoi(e) != 0; }();
+  static const bool enabled = [] { const char* e = getenv("XB_SMEM_CARVEOUT"); return e && atoi(e) != 0; }();
   if (!enabled) return;
   static std::mutex mu;
   static std::unordered_set<const void*> done;

@@ -95,6 +95,12 @@ struct W4Fuse {
   const __nv_bfloat16* res_in;
   __nv_bfloat16* res_out;
   float eps;
+  // split RMSNorm: the PRODUCER linear (epilogue 3: o_proj / down_proj) adds the residual, writes the updated residual
+  // stream r = bf16(bf16(y) + residual) to res_out and the per-(16-row tile, token) sums of r^2 to stats_out
+  // [N/16][8]; the CONSUMER linear (stats_in != null: qkv / gate_up) reads r as its x, sums the K/16 partials in a
+  // fixed order and normalises while staging x in shared memory - one L2 round trip, no reduction over K in any CTA.
+  const float* stats_in;
+  float* stats_out;
   const int64_t* positions;
   const __nv_bfloat16* cos_sin;   // [max_pos, head_dim] = [cos half | sin half]
   const int32_t* slots;
@@ -105,19 +111,21 @@ struct W4Fuse {
 
 template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth,
           int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */, int kOcc = 2 /* CTAs per SM */,
-          int kEpi = 0 /* 0: bias; 1: gate/up rows interleaved, act(gate)*up; 2: rope + KV scatter (qkv) */,
-          bool kXs = false /* x staged (and optionally normalised) in shared memory by the prologue */,
-          bool kExact = false /* exact-weight form (one token tile): scale / zero applied once per group, see below */>
+          int kEpi = 0 /* 0: bias; 1: gate/up rows interleaved, act(gate)*up; 2: rope + KV scatter (qkv);
+                          3: + residual -> residual stream and sum-of-squares partials (producer of a split RMSNorm) */,
+          bool kXs = false /* x staged (and optionally normalised) in shared memory by the prologue */>
 __global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : kOcc)
 linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
                             int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
                             const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int gshift /* log2(tiles per group) */,
                             int act_mode, const W4Fuse fz) {
   constexpr bool kGateUp = kEpi == 1;
-  constexpr bool kPair = kEpi != 0;                 // rows g / g+8 of a tile form an output pair
+  constexpr bool kPair = kEpi == 1 || kEpi == 2;    // rows g / g+8 of a tile form an output pair
+  static_assert(kEpi != 3 || (kSplit > 1 && kMT == 1), "the residual + statistics epilogue lives in the k-split reduction");
   constexpr int kTilesPerCta = kWarps / kSplit;
   __shared__ float red[kSplit > 1 ? kWarps : 1][kMT][16 * 8];
   __shared__ float s_ss[kXs ? kWarps : 1][8];
+  __shared__ float s_sq[kEpi == 3 ? kTilesPerCta : 1][16][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int ntiles = N >> 4;
@@ -133,7 +141,7 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 
   // kAcc independent accumulator sets (one per k16 step of a tile when registers allow): legacy HMMA has a long
   // issue-to-result latency on sm_100, a single chain per warp leaves the scheduler with nothing eligible
-  constexpr int kAcc = kExact ? 2 : (kMT == 1 ? 4 : (kMT == 2 ? 2 : 1));
+  constexpr int kAcc = kMT == 1 ? 4 : (kMT == 2 ? 2 : 1);
   float accj[kAcc][kMT][4];
 #pragma unroll
   for (int a = 0; a < kAcc; ++a)
@@ -141,14 +149,6 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     for (int m = 0; m < kMT; ++m)
 #pragma unroll
       for (int i = 0; i < 4; ++i) accj[a][m][i] = 0.f;
-
-  // kExact (spec form "exact" of oracle/quant.py): y = sum_g s_g * (sum_{k in g} x_k (128 + q_k) - (128 + z_g) sum_{k in g} x_k).
-  // The nibbles go to the tensor core as the exact bf16 integers 128 + q (one LOP3 per weight pair, no HSUB2 / HMUL2);
-  // sum_k x_k comes from a second MMA against an all-ones A fragment (its accumulator lands in the same (token) slots);
-  // scale and zero are applied in fp32 once per quantisation group: 61 instead of 83 warp instructions per 512-byte tile.
-  static_assert(!kExact || kMT == 1, "the exact-weight form serves one token tile");
-  float yacc[4] = {0.f, 0.f, 0.f, 0.f};     // kExact: running result
-  float accx[4] = {0.f, 0.f, 0.f, 0.f};     // kExact: sum_k x_k of the open group (rows of the ones-MMA are identical)
 
   // running pointers (one 64-bit add per slot instead of a multiply per tile)
   const uint4* wp = qweight + ((int64_t)ntile * ktiles + (int64_t)s_begin * kTG) * 32 + lane;
@@ -187,6 +187,46 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   if constexpr (kXs) {
     const int nvec = K >> 3;
     const bool do_norm = fz.norm_w != nullptr;
+    if (fz.stats_in != nullptr) {
+      // ---- consumer of a split RMSNorm: x IS the residual stream; sum(x^2) per token arrives as K/16 partials ----
+      // every load (x vectors, partials, norm weights) is issued up front: one round trip to L2
+      const int nst = K >> 4;
+      float part[8];
+#pragma unroll
+      for (int tk = 0; tk < 8; ++tk) part[tk] = 0.f;
+      for (int i = threadIdx.x; i < nst; i += kWarps * 32) {      // fixed assignment -> every CTA gets the same bits
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(fz.stats_in + (int64_t)i * 8));
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(fz.stats_in + (int64_t)i * 8 + 4));
+        part[0] += a.x; part[1] += a.y; part[2] += a.z; part[3] += a.w;
+        part[4] += b.x; part[5] += b.y; part[6] += b.z; part[7] += b.w;
+      }
+#pragma unroll
+      for (int tk = 0; tk < 8; ++tk) {
+        const float v = warp_sum(part[tk]);
+        if (lane == 0) s_ss[warp][tk] = v;
+      }
+      __syncthreads();
+      const uint4* wv = reinterpret_cast<const uint4*>(fz.norm_w);
+      for (int tok = 0; tok < M; ++tok) {
+        float var = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) var += s_ss[w][tok];
+        const float rstd = rsqrtf(var / (float)K + fz.eps);
+        const uint4* src = reinterpret_cast<const uint4*>(x + (int64_t)tok * x_stride);
+        uint4* dst = reinterpret_cast<uint4*>(xs + (int64_t)tok * xs_stride);
+        for (int idx = threadIdx.x; idx < nvec; idx += kWarps * 32) {
+          uint4 v = src[idx];
+          const uint4 w = __ldg(wv + idx);
+          uint32_t* vp = &v.x;
+          const uint32_t* wq = &w.x;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)  // bf16(x*rstd) then bf16 product with w (norm.cu:75-77,130-133)
+            vp[j] = pack_bf16x2(round_bf16(bf16lo(vp[j]) * rstd) * bf16lo(wq[j]), round_bf16(bf16hi(vp[j]) * rstd) * bf16hi(wq[j]));
+          dst[idx] = v;
+        }
+      }
+      __syncthreads();
+    } else {
     for (int tok = 0; tok < M; ++tok) {
       const uint4* src = reinterpret_cast<const uint4*>(x + (int64_t)tok * x_stride);
       const uint4* rsrc = fz.res_in ? reinterpret_cast<const uint4*>(fz.res_in + (int64_t)tok * K) : nullptr;
@@ -239,6 +279,7 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
       }
     }
     __syncthreads();
+    }
   }
 
   // x fragments: lane (g,t) needs x[tok = 8m+g][k0 + 16t .. +16) per tile
@@ -271,36 +312,13 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   XRing<kMT> xbuf[2];
   if constexpr (kXs) load_xtile(xbuf[0]);
 
-  // kExact: close the open quantisation group - fold its integer dot products into the fp32 result
-  auto flush_group = [&](const uint2 mt) {
-    const float s0 = bf16lo(mt.x), zo0 = bf16hi(mt.x), s1 = bf16lo(mt.y), zo1 = bf16hi(mt.y);   // scale, 128 + zero
-    float c[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      c[i] = accj[0][0][i];
-#pragma unroll
-      for (int a = 1; a < kAcc; ++a) c[i] += accj[a][0][i];
-#pragma unroll
-      for (int a = 0; a < kAcc; ++a) accj[a][0][i] = 0.f;
-    }
-    yacc[0] = fmaf(s0, fmaf(-zo0, accx[0], c[0]), yacc[0]);
-    yacc[1] = fmaf(s0, fmaf(-zo0, accx[1], c[1]), yacc[1]);
-    yacc[2] = fmaf(s1, fmaf(-zo1, accx[2], c[2]), yacc[2]);
-    yacc[3] = fmaf(s1, fmaf(-zo1, accx[3], c[3]), yacc[3]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) accx[i] = 0.f;
-  };
-  uint2 open_meta = make_uint2(0, 0);     // kExact: meta words of the group being accumulated
-  const int group_tiles = 1 << gshift;
-
-  auto consume = [&](int i, int slot_abs) {
+  auto consume = [&](int i) {
     uint4 wq[kTG];
 #pragma unroll
     for (int u = 0; u < kTG; ++u) wq[u] = lds_128(ring_w + i * kSlotBytes + u * 512);
     const uint2 mt = lds_64(ring_m + i * kSlotBytes);
     const uint32_t s0 = __byte_perm(mt.x, 0, 0x1010), z0 = __byte_perm(mt.x, 0, 0x3232);
     const uint32_t s1 = __byte_perm(mt.y, 0, 0x1010), z1 = __byte_perm(mt.y, 0, 0x3232);
-    if constexpr (kExact) open_meta = mt;
 #pragma unroll
     for (int u = 0; u < kTG; ++u) {
       const int par = (i * kTG + u) & 1;       // compile-time after unrolling (kDepth * kTG is even)
@@ -315,27 +333,16 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
         const uint32_t q1 = lop3_and_or(w >> 4, 0x000f000fu, 0x43004300u);
         const uint32_t q2 = lop3_and_or(w >> 8, 0x000f000fu, 0x43004300u);
         const uint32_t q3 = lop3_and_or(w >> 12, 0x000f000fu, 0x43004300u);
-        if constexpr (kExact) {
-          const uint32_t* xv = j < 2 ? &xf.lo[0].x : &xf.hi[0].x;
-          const uint32_t b0 = xv[(j & 1) * 2], b1 = xv[(j & 1) * 2 + 1];
-          mma_bf16_16816(accj[j % kAcc][0], q0, q1, q2, q3, b0, b1);
-          mma_bf16_16816(accx, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, b0, b1);
-        } else {
-          const uint32_t a0 = hmul2_bf16(hsub2_bf16(q0, z0), s0);
-          const uint32_t a1 = hmul2_bf16(hsub2_bf16(q1, z1), s1);
-          const uint32_t a2 = hmul2_bf16(hsub2_bf16(q2, z0), s0);
-          const uint32_t a3 = hmul2_bf16(hsub2_bf16(q3, z1), s1);
+        const uint32_t a0 = hmul2_bf16(hsub2_bf16(q0, z0), s0);
+        const uint32_t a1 = hmul2_bf16(hsub2_bf16(q1, z1), s1);
+        const uint32_t a2 = hmul2_bf16(hsub2_bf16(q2, z0), s0);
+        const uint32_t a3 = hmul2_bf16(hsub2_bf16(q3, z1), s1);
 #pragma unroll
-          for (int m = 0; m < kMT; ++m) {
-            // lane run element 4j+{0,1} -> b0, 4j+{2,3} -> b1
-            const uint32_t* xv = j < 2 ? &xf.lo[m].x : &xf.hi[m].x;
-            mma_bf16_16816(accj[j % kAcc][m], a0, a1, a2, a3, xv[(j & 1) * 2], xv[(j & 1) * 2 + 1]);
-          }
+        for (int m = 0; m < kMT; ++m) {
+          // lane run element 4j+{0,1} -> b0, 4j+{2,3} -> b1
+          const uint32_t* xv = j < 2 ? &xf.lo[m].x : &xf.hi[m].x;
+          mma_bf16_16816(accj[j % kAcc][m], a0, a1, a2, a3, xv[(j & 1) * 2], xv[(j & 1) * 2 + 1]);
         }
-      }
-      if constexpr (kExact) {
-        // a group ends after every group_tiles k64 tiles (counted from k = 0, so k-split warps agree)
-        if (((slot_abs * kTG + u + 1) & (group_tiles - 1)) == 0) flush_group(mt);
       }
     }
   };
@@ -352,7 +359,7 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 #pragma unroll
     for (int i = 0; i < kDepth; ++i) {
       cp_async_wait<kDepth - 1>();
-      consume(i, sl + i);
+      consume(i);
       if (sl + i + kDepth < s_end)
         issue(i, wp, slot_is_group ? mp : mbase + (int64_t)(((sl + i + kDepth) * kTG) >> gshift) * N);
       cp_async_commit();
@@ -364,26 +371,19 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   cp_async_wait<0>();
 #pragma unroll
   for (int i = 0; i < kDepth; ++i) {
-    if (sl + i < s_end) consume(i, sl + i);
+    if (sl + i < s_end) consume(i);
   }
   pdl_launch_dependents();
   float acc[kMT][4];
-  if constexpr (kExact) {
-    // a k range that ends inside a group (k-split warps with groups wider than a slot) still holds an open partial group
-    if (s_end > s_begin && ((s_end * kTG) & (group_tiles - 1)) != 0) flush_group(open_meta);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[0][i] = yacc[i];
-  } else {
+  for (int m = 0; m < kMT; ++m)
 #pragma unroll
-    for (int m = 0; m < kMT; ++m)
+    for (int i = 0; i < 4; ++i) {
+      float v = accj[0][m][i];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float v = accj[0][m][i];
-#pragma unroll
-        for (int a = 1; a < kAcc; ++a) v += accj[a][m][i];
-        acc[m][i] = v;
-      }
-  }
+      for (int a = 1; a < kAcc; ++a) v += accj[a][m][i];
+      acc[m][i] = v;
+    }
 
   // c0:(row g, tok 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
   // kGateUp: row g of the tile is gate row 8*ntile+g and row g+8 the matching up row, so SiLU*mul (activation.cu:45-130:
@@ -484,8 +484,30 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
             if constexpr (kGateUp) y[(int64_t)tok * y_stride + nt * 8 + r] = gate_up(sum, up);
             else rope_store(nt, r, tok, sum, up);
           }
+        } else if constexpr (kEpi == 3) {
+          // producer half of the split RMSNorm (fused_add_rms_norm, norm.cu:80-136): r = bf16(bf16(y) + residual)
+          const int n = nt * 16 + r;
+          const float rr = round_bf16(round_bf16(sum) + __bfloat162float(fz.res_in[(int64_t)tok * N + n]));
+          fz.res_out[(int64_t)tok * N + n] = __float2bfloat16_rn(rr);
+          s_sq[tl][r][c] = rr * rr;
         } else {
           y[(int64_t)tok * y_stride + nt * 16 + r] = __float2bfloat16_rn(sum);
+        }
+      } else if constexpr (kEpi == 3) {
+        if (tl < kTilesPerCta) s_sq[tl][r][c] = 0.f;
+      }
+    }
+    if constexpr (kEpi == 3) {
+      __syncthreads();
+      // per (row tile, token): the 16 squares in row order - fixed order, no atomics: bit-reproducible statistics
+      for (int i = threadIdx.x; i < kTilesPerCta * 8; i += blockDim.x) {
+        const int tl = i >> 3, c = i & 7;
+        const int nt = blockIdx.x * kTilesPerCta + tl;
+        if (nt < ntiles) {
+          float ssum = 0.f;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) ssum += s_sq[tl][r][c];
+          fz.stats_out[(int64_t)nt * 8 + c] = ssum;
         }
       }
     }
@@ -590,7 +612,7 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   XB_CHECK(group_size >= 64 && group_size % 64 == 0 && K % group_size == 0,
            "linear_w4a16_small_m: group_size %d must be a multiple of 64 dividing K=%d", group_size, K);
   XB_CHECK(x_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "linear_w4a16_small_m: x not 16B aligned");
-  XB_CHECK(!(xs || epi == 2) || M <= 8, "linear_w4a16_small_m: the fused prologue / rope epilogue serve M <= 8 (got %d)", M);
+  XB_CHECK(!(xs || epi >= 2) || M <= 8, "linear_w4a16_small_m: the fused prologue / epilogues serve M <= 8 (got %d)", M);
   XB_CHECK(!xs || w4_xs_bytes(M, K) <= kXsMaxBytes, "linear_w4a16_small_m: M=%d x K=%d does not fit the shared-memory x stage", M, K);
   W4Fuse fz{};
   if (fzp) fz = *fzp;
@@ -603,20 +625,17 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   const int ntiles = N / 16, ktiles = K / 64;
   int split = 1;
   while (split < 8 && ntiles * split < 148 * 16 && ktiles / (split * 2) >= 3) split *= 2;
+  if (epi == 3 && split < 2) split = 2;   // the residual + statistics epilogue lives in the k-split reduction
   const int tpg = group_size / 64;   // k64 tiles per quantisation group
   XB_CHECK((tpg & (tpg - 1)) == 0, "linear_w4a16_small_m: group_size/64 must be a power of two (got %d)", group_size);
   int gshift = 0;
   while ((1 << gshift) < tpg) ++gshift;
   const bool tg2 = tpg >= 2;
   const size_t xs_bytes = xs ? w4_xs_bytes(M, K) : 0;
-  // one token tile (M <= 8): the exact-weight form of the spec (oracle/quant.py); XB_W4_EXACT=0 keeps the bf16-weight
-  // form for A/B measurements
-  static const bool exact_default = [] { const char* e = getenv("XB_W4_EXACT"); return !e || atoi(e) != 0; }();
-  const bool exact = exact_default && M <= 8;
   // (tuning note, B200: 3 CTAs/SM at <= 80 registers measured 10-13 % slower than 2 CTAs/SM for every decode shape)
-#define XB_W4_GO(MT, SP, DEPTH, TG, EPI, XS, EX)                                                                   \
+#define XB_W4_GO(MT, SP, DEPTH, TG, EPI, XS)                                                                       \
   {                                                                                                                 \
-    auto kern = linear_w4a16_small_m_kernel<MT, SP, DEPTH, TG, 2, EPI, XS, EX>;                                     \
+    auto kern = linear_w4a16_small_m_kernel<MT, SP, DEPTH, TG, 2, EPI, XS>;                                         \
     static bool attr_done = false; /* per instantiation: static reduction scratch + ring may exceed 48 KB */        \
     if (!attr_done) {                                                                                               \
       XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
@@ -626,21 +645,20 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
     XB_CUDA_OK(launch(kern, grid, block, w4_ring_bytes(DEPTH, TG) + xs_bytes, s, true, yy, y_stride, xx, x_stride,  \
                       qw, meta, bb, M, N, K, gshift, act_mode, fz));                                                \
   }
-#define XB_W4_TG(MT, SP, DP, EPI, XS)                                          \
-  if constexpr (MT == 1) {                                                     \
-    if (exact) {                                                               \
-      if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS, true) }            \
-      else { XB_W4_GO(MT, SP, DP, 1, EPI, XS, true) }                          \
-    } else if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS, false) }      \
-    else { XB_W4_GO(MT, SP, DP, 1, EPI, XS, false) }                           \
-  } else if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS, false) }        \
-  else { XB_W4_GO(MT, SP, DP, 1, EPI, XS, false) }
+#define XB_W4_TG(MT, SP, DP, EPI, XS)                                \
+  if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS) }            \
+  else { XB_W4_GO(MT, SP, DP, 1, EPI, XS) }
   // the fused variants (x staged in shared memory / rope epilogue) exist for one token tile (M <= 8) only
 #define XB_W4_LAUNCH(MT, SP, DP)                                                                               \
   {                                                                                                            \
     dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                               \
     if constexpr (MT == 1) {                                                                                   \
-      if (xs) {                                                                                                \
+      if (epi == 3) {                                                                                          \
+        if constexpr (SP > 1) {                                                                                \
+          if (xs) { XB_W4_TG(1, SP, DP, 3, true) }                                                             \
+          else { XB_W4_TG(1, SP, DP, 3, false) }                                                               \
+        }                                                                                                      \
+      } else if (xs) {                                                                                         \
         if (epi == 2) { XB_W4_TG(1, SP, DP, 2, true) }                                                         \
         else if (epi == 1) { XB_W4_TG(1, SP, DP, 1, true) }                                                    \
         else { XB_W4_TG(1, SP, DP, 0, true) }                                                                  \
@@ -694,6 +712,10 @@ extern "C" int xb_linear_w4a16_gate_up_act_small_m(void* y, int64_t y_stride, co
 //   prologue: norm_weight != null: x := RMSNorm(x (+ residual_in)) * norm_weight (fused_add_rms_norm / rms_norm); the
 //             updated residual stream x + residual_in goes to residual_out (must not alias residual_in; null = not
 //             wanted).  norm_weight == null with stage_x != 0 only stages x in shared memory.
+//             Split form: norm_stats_in != null: x IS the residual stream and sum(x^2) per token arrives as K/16
+//             partials [K/16][8] written by the producer linear's epilogue 3 - the consumer only normalises.
+//   epilogue: 3 (o_proj / down_proj): r = bf16(bf16(y) + residual_in) -> residual_out, sum of r^2 per (16-row tile,
+//             token) -> norm_stats_out [N/16][8]; y is not written.
 //   epilogue: 0 bias; 1 act(gate) * up (act_mode; interleaved rows; y [M, N/2]); 2 RoPE (NeoX) on the q and k heads +
 //             scatter of the new k / v rows into the paged caches (rows packed by quant.pack_w4_qkv_rope; y [M, N] in
 //             logical [q | k | v] order; positions int64 [M], cos_sin_cache [max_pos, head_dim] bf16, slot_ids int32
@@ -704,8 +726,9 @@ extern "C" int xb_linear_w4a16_decode_fused(void* y, int64_t y_stride, const voi
                                             const void* residual_in, void* residual_out, int stage_x, int epilogue,
                                             int act_mode, const int64_t* positions, const void* cos_sin_cache,
                                             const int32_t* slot_ids, void* k_cache, void* v_cache, int num_heads,
-                                            int num_kv_heads, int head_dim, xb_stream_t stream) {
-  XB_CHECK(epilogue >= 0 && epilogue <= 2, "linear_w4a16_decode_fused: epilogue %d unknown", epilogue);
+                                            int num_kv_heads, int head_dim, const float* norm_stats_in,
+                                            float* norm_stats_out, xb_stream_t stream) {
+  XB_CHECK(epilogue >= 0 && epilogue <= 3, "linear_w4a16_decode_fused: epilogue %d unknown", epilogue);
   XB_CHECK(epilogue != 1 || (act_mode >= 0 && act_mode <= 2), "linear_w4a16_decode_fused: unsupported act mode %d", act_mode);
   XB_CHECK(M >= 0 && M <= 8, "linear_w4a16_decode_fused: M=%d out of range (0..8)", M);
   W4Fuse fz{};
@@ -713,7 +736,21 @@ extern "C" int xb_linear_w4a16_decode_fused(void* y, int64_t y_stride, const voi
   fz.res_in = reinterpret_cast<const __nv_bfloat16*>(residual_in);
   fz.res_out = reinterpret_cast<__nv_bfloat16*>(residual_out);
   fz.eps = eps;
-  XB_CHECK(!(residual_in || residual_out) || norm_weight, "linear_w4a16_decode_fused: a residual needs the norm prologue");
+  fz.stats_in = norm_stats_in;
+  fz.stats_out = norm_stats_out;
+  if (epilogue == 3) {
+    XB_CHECK(residual_in && residual_out && norm_stats_out && !norm_weight,
+             "linear_w4a16_decode_fused: epilogue 3 needs residual_in, residual_out and norm_stats_out (and no norm prologue)");
+    XB_CHECK((reinterpret_cast<uintptr_t>(norm_stats_out) & 15) == 0, "linear_w4a16_decode_fused: norm_stats_out must be 16-byte aligned");
+  } else {
+    XB_CHECK(!norm_stats_out, "linear_w4a16_decode_fused: norm_stats_out belongs to epilogue 3");
+    XB_CHECK(!(residual_in || residual_out) || norm_weight, "linear_w4a16_decode_fused: a residual needs the norm prologue");
+  }
+  if (norm_stats_in) {
+    XB_CHECK(norm_weight && !residual_in && !residual_out && K % 16 == 0 &&
+                 (reinterpret_cast<uintptr_t>(norm_stats_in) & 15) == 0,
+             "linear_w4a16_decode_fused: norm_stats_in goes with norm_weight, x = the residual stream and no residual pointers");
+  }
   XB_CHECK(!residual_in || residual_in != residual_out, "linear_w4a16_decode_fused: residual_out must not alias residual_in");
   XB_CHECK(!norm_weight || ((reinterpret_cast<uintptr_t>(norm_weight) | reinterpret_cast<uintptr_t>(residual_in) |
                              reinterpret_cast<uintptr_t>(residual_out)) & 15) == 0,

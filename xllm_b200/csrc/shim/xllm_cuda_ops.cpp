@@ -163,9 +163,9 @@ void cutlass_scaled_mm(torch::Tensor& c, torch::Tensor const& a, torch::Tensor c
   TORCH_CHECK(a.scalar_type() == torch::kFloat8_e4m3fn && b.scalar_type() == torch::kFloat8_e4m3fn, "fp8 e4m3 inputs expected");
   TORCH_CHECK(c.scalar_type() == torch::kBFloat16, "only bfloat16 output is implemented");
   const at::cuda::OptionalCUDAGuard guard(device_of(a));
-  if (a.size(0) <= 64 && a.size(1) % 64 == 0) {
-    // decode: the HBM-streaming swap-AB kernel (the reference's M <= 16 / <= 64 buckets,
-    // c3x/scaled_mm_sm100_fp8_dispatch.cuh:148-287)
+  if (a.size(0) <= 8 && b.size(1) <= 16384 && a.size(1) % 64 == 0) {
+    // decode on a narrow projection: the HBM-streaming swap-AB kernel (the reference's small-M buckets,
+    // c3x/scaled_mm_sm100_fp8_dispatch.cuh:148-287); measured crossover in xllm_b200/ops.py
     ok(xb_linear_fp8_small_m(c.data_ptr(), c.stride(0), a.data_ptr(), a.stride(0), b.data_ptr(), a_scales.data_ptr<float>(),
                              (int)a_scales.numel(), b_scales.data_ptr<float>(), (int)b_scales.numel(),
                              bias ? bias->data_ptr() : nullptr, (int)a.size(0), (int)b.size(1), (int)a.size(1), stream()),

@@ -34,10 +34,16 @@ def _cuda_bf16(t, name):
     _need(t.dtype == BF16, f"{name} must be bfloat16, got {t.dtype}")
 
 
-# largest M served by the HBM-streaming small-M kernels before the 128-row tcgen05 GEMMs take over (the streaming kernels
-# read the weight once per launch; at M = 64 they still move fewer bytes per flop than a 128-row tile wastes)
-FP8_SMALL_M_MAX = 64
+# Streaming (small-M) kernels vs the 128-row tcgen05 GEMMs, measured on B200 (tools/gemv_sweep.py q8, us per call):
+#   the GEMMs launch one CTA per 128 x 256 (fp8) / 128 x 128..256 (weight-only) output tile, so with few output columns most
+#   SMs idle; weight-only, M = 32: N 3584 44 vs 122, N 10240 49 vs 106, N 37888 52 vs 35; M = 64: 93 vs 122, 102 vs 106, 119 vs 36
+#   => weight-only: streaming up to M = 16 always, up to M = 64 when N <= 16384.
+#   fp8: M = 1: N 10240 41.6 vs 49.3, N 3584 32 vs 54, N 37888 63 vs 32; M = 32: 54 vs 43, 58 vs 48, 86 vs 32
+#   => fp8: streaming only up to M = 8 and N <= 16384 (the tcgen05 FP8 kernel streams 1 byte per weight already).
+FP8_SMALL_M_MAX = 8
 WQ_SMALL_M_MAX = 16
+WQ_SMALL_M_MAX_NARROW = 64      # ... when the projection has at most SMALL_N_MAX output columns
+SMALL_N_MAX = 16384
 
 
 # ---- K7 ---------------------------------------------------------------------
@@ -321,16 +327,23 @@ def cutlass_scaled_mm(c, a, b, a_scales, b_scales, bias=None) -> None:
     _need(a_scales.numel() in (1, M) and b_scales.numel() in (1, N), "scale numel must be 1 or M / N")
     if bias is not None:
         _need(bias.numel() == N and bias.is_contiguous() and bias.dim() == 1 and bias.dtype == BF16, "bias must be [N] bf16")
-    if M <= FP8_SMALL_M_MAX and K % 64 == 0:
-        # decode: weights streamed once, tokens in the n8 slot of mma.sync e4m3 (the reference's swap-AB buckets,
-        # scaled_mm_sm100_fp8_dispatch.cuh:148-287)
-        check(lib().xb_linear_fp8_small_m(_p(c), c_i64(c.stride(0)), _p(a), c_i64(a.stride(0)), _p(b), _p(a_scales),
-                                          c_i32(a_scales.numel()), _p(b_scales), c_i32(b_scales.numel()), _p(bias),
-                                          c_i32(M), c_i32(N), c_i32(K), _stream()), "cutlass_scaled_mm (small M)")
-        return
+    if M <= FP8_SMALL_M_MAX and N <= SMALL_N_MAX and K % 64 == 0:
+        return fp8_scaled_mm_small_m(c, a, b, a_scales, b_scales, bias)
     check(lib().xb_gemm_fp8_scaled(_p(c), c_i64(c.stride(0)), _p(a), c_i64(a.stride(0)), _p(b), _p(a_scales),
                                    c_i32(a_scales.numel()), _p(b_scales), c_i32(b_scales.numel()), _p(bias), c_i32(M),
                                    c_i32(N), c_i32(K), _stream()), "cutlass_scaled_mm")
+
+
+def fp8_scaled_mm_small_m(c, a, b, a_scales, b_scales, bias=None) -> None:
+    """the streaming swap-AB form of cutlass_scaled_mm for M <= 64 (same arguments: b is the [K, N] column-major view of
+    the [N, K] weight): weights streamed once, tokens in the n8 slot of mma.sync e4m3 (the reference's M <= 16 / <= 64
+    buckets, scaled_mm_sm100_fp8_dispatch.cuh:148-287)."""
+    M, K = a.shape
+    N = b.size(1)
+    _need(b.stride(0) == 1 and b.stride(1) == K, "b must be a dense column-major [K,N] view of a [N,K] weight")
+    check(lib().xb_linear_fp8_small_m(_p(c), c_i64(c.stride(0)), _p(a), c_i64(a.stride(0)), _p(b), _p(a_scales),
+                                      c_i32(a_scales.numel()), _p(b_scales), c_i32(b_scales.numel()), _p(bias),
+                                      c_i32(M), c_i32(N), c_i32(K), _stream()), "fp8_scaled_mm_small_m")
 
 
 def fp8_scaled_matmul(a, b, a_scale, b_scale, output_dtype=BF16, bias=None, output=None):
@@ -348,7 +361,7 @@ def w4a16_linear(x, qweight, meta, group_size, bias=None, out=None):
     M, K = x.shape
     N = meta.size(1)
     y = out if out is not None else torch.empty(M, N, dtype=BF16, device=x.device)
-    if M <= 16:
+    if M <= WQ_SMALL_M_MAX or (M <= WQ_SMALL_M_MAX_NARROW and N <= SMALL_N_MAX):
         return w4a16_linear_small_m(x, qweight, meta, group_size, bias, y)
     check(lib().xb_gemm_w4a16(_p(y), c_i64(y.stride(0)), _p(x), c_i64(x.stride(0)), _p(qweight), _p(meta), _p(bias),
                               c_i32(M), c_i32(N), c_i32(K), c_i32(group_size), _stream()), "w4a16_linear")
@@ -437,23 +450,29 @@ def w4a16_decode_fused_fits(M: int, K: int) -> bool:
 def w4a16_decode_fused(x, qweight, meta, group_size, bias=None, out=None, *, norm_weight=None, eps=1e-6, residual_in=None,
                        residual_out=None, stage_x=False, epilogue="none", act_mode="silu", positions=None,
                        cos_sin_cache=None, slot_ids=None, key_cache=None, value_cache=None, num_heads=0, num_kv_heads=0,
-                       head_dim=0):
+                       head_dim=0, norm_stats_in=None, norm_stats_out=None):
     """Decode-step form of a weight-only linear (M <= 8): the launches the reference makes around the GEMV ride in it.
       prologue  norm_weight: x := RMSNorm(x (+ residual_in)) * norm_weight  (rms_norm / fused_add_rms_norm,
                 cuda_ops_api.h:157-165); residual_out receives x + residual_in (must be a different buffer)
       epilogue  "none" | "act_mul" (DenseMLP's act_and_mul on interleaved gate/up rows, out [M, N/2]) |
                 "rope_cache" (rotary_embedding + reshape_paged_cache of qwen2_attention.cpp:147-171 /
-                flashinfer_attention.cpp:128-131; rows packed by quant.pack_w4_qkv_rope, out [M, N] logical order)"""
+                flashinfer_attention.cpp:128-131; rows packed by quant.pack_w4_qkv_rope, out [M, N] logical order) |
+                "residual_stats" (row-parallel projection as producer of a split RMSNorm: residual_out = bf16(y +
+                residual_in), norm_stats_out [N/16, 8] f32 = partial sums of its squares; `out` is not written)
+      split-norm consumer: norm_stats_in (+ norm_weight): x is the residual stream, the prologue only normalises"""
     _cuda_bf16(x, "x")
     _need(qweight.dtype == torch.int32 and meta.dtype == torch.int32, "qweight/meta must be int32 storage")
-    epi = {"none": 0, "act_mul": 1, "rope_cache": 2}.get(epilogue)
+    epi = {"none": 0, "act_mul": 1, "rope_cache": 2, "residual_stats": 3}.get(epilogue)
     _need(epi is not None, f"unknown epilogue {epilogue}")
     if epi == 1 and act_mode not in _ACT:
         raise XllmB200Error(f"Unsupported act mode: {act_mode}")
     M, K = x.shape
     N = meta.size(1)
     n_out = N // 2 if epi == 1 else N
-    y = out if out is not None else torch.empty(M, n_out, dtype=BF16, device=x.device)
+    y = out if out is not None else (x if epi == 3 else torch.empty(M, n_out, dtype=BF16, device=x.device))
+    for t, n in ((norm_stats_in, "norm_stats_in"), (norm_stats_out, "norm_stats_out")):
+        if t is not None:
+            _need(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), f"{n} must be a contiguous float32 CUDA tensor")
     for t, n in ((norm_weight, "norm_weight"), (residual_in, "residual_in"), (residual_out, "residual_out")):
         if t is not None:
             _cuda_bf16(t, n)
@@ -468,7 +487,8 @@ def w4a16_decode_fused(x, qweight, meta, group_size, bias=None, out=None, *, nor
         _p(y), c_i64(y.stride(0)), _p(x), c_i64(x.stride(0)), _p(qweight), _p(meta), _p(bias), c_i32(M), c_i32(N), c_i32(K),
         c_i32(group_size), _p(norm_weight), c_f32(eps), _p(residual_in), _p(residual_out), c_i32(1 if stage_x else 0),
         c_i32(epi), c_i32(_ACT.get(act_mode, 0)), _p(positions), _p(cos_sin_cache), _p(slot_ids), _p(key_cache),
-        _p(value_cache), c_i32(num_heads), c_i32(num_kv_heads), c_i32(head_dim), _stream()), "w4a16_decode_fused")
+        _p(value_cache), c_i32(num_heads), c_i32(num_kv_heads), c_i32(head_dim), _p(norm_stats_in), _p(norm_stats_out),
+        _stream()), "w4a16_decode_fused")
     return y
 
 
@@ -515,6 +535,7 @@ def gemm_w8a16(x, qweight, meta, group_size, bias=None, out=None):
 
 def w8a16_linear(x, qweight, meta, group_size, bias=None, out=None):
     """weight-only int8 linear for any M: streaming kernel for decode batches, tcgen05 dequant-GEMM above."""
-    if x.shape[0] <= WQ_SMALL_M_MAX:
+    M, N = x.shape[0], meta.size(1)
+    if M <= WQ_SMALL_M_MAX or (M <= WQ_SMALL_M_MAX_NARROW and N <= SMALL_N_MAX):
         return w8a16_linear_small_m(x, qweight, meta, group_size, bias, out)
     return gemm_w8a16(x, qweight, meta, group_size, bias, out)

@@ -280,6 +280,7 @@ class Qwen2DecodeRunner:
         self.qkv = torch.empty(B, self.q_size + 2 * self.kv_size, dtype=BF16, device=dev)
         self.qkv_raw = torch.empty_like(self.qkv)       # rope-pair packed projection output when RoPE is not fused
         self.res_pp = [torch.empty(B, H, dtype=BF16, device=dev) for _ in range(2)]   # residual stream ping-pong (fused GEMVs)
+        self.norm_stats = [torch.zeros(H // 16, 8, dtype=torch.float32, device=dev) for _ in range(2)]   # split-RMSNorm partials
         w4 = cfg.quant == "w4a16" and all(L["qkv"].kind == "w4a16" for L in weights.layers)
         import os
         if os.environ.get("XB_FUSE_GEMV") is not None:          # A/B measurements
@@ -325,7 +326,7 @@ class Qwen2DecodeRunner:
         ops.fused_add_rms_norm(out, self.residual, norm_w, cfg.rms_norm_eps)
         return out
 
-    def _qkv_and_rope(self, L, li, h, norm_w=None, res_in=None, res_out=None):
+    def _qkv_and_rope(self, L, li, h, norm_w=None, res_in=None, res_out=None, stats_in=None):
         """qkv_proj + RoPE + KV scatter of layer li (qwen2_attention.cpp:147-176, flashinfer_attention.cpp:128-131);
         with norm_w the add+RMSNorm in front of it rides in the same launch.  Leaves q | k | v (logical) in self.qkv."""
         cfg = self.cfg
@@ -335,7 +336,7 @@ class Qwen2DecodeRunner:
         if packed and h.size(0) <= 8 and (self.fuse_gemv or norm_w is None):
             ops.w4a16_decode_fused(h, lin.qweight, lin.meta, lin.group_size, lin.bias, self.qkv, norm_weight=norm_w,
                                    eps=cfg.rms_norm_eps, residual_in=res_in, residual_out=res_out, stage_x=self.fuse_gemv,
-                                   epilogue="rope_cache", positions=self.positions, cos_sin_cache=self.cos_sin,
+                                   norm_stats_in=stats_in, epilogue="rope_cache", positions=self.positions, cos_sin_cache=self.cos_sin,
                                    slot_ids=self.slots, key_cache=self.k_caches[li], value_cache=self.v_caches[li],
                                    num_heads=self.nh, num_kv_heads=self.nkv, head_dim=cfg.head_dim)
             return
@@ -361,34 +362,43 @@ class Qwen2DecodeRunner:
                          self.attn_out.view(-1, self.nh, cfg.head_dim))
 
     def _launch_step_fused(self):
-        """TP = 1, W4A16, batch <= 8: five launches per layer.  The residual add + RMSNorm that the reference runs as
-        its own kernel after o_proj / down_proj (qwen2_decoder_layer.cpp:89-112) is computed in the prologue of the NEXT
-        GEMV (every CTA normalises the 7 KB activation row into its shared memory), RoPE + KV scatter in the qkv
-        epilogue, SiLU*mul in the gate_up epilogue.  The residual stream ping-pongs between two buffers because the
-        CTAs of a GEMV read it while CTA 0 writes the updated one."""
+        """TP = 1, W4A16, batch <= 8: five launches per layer, RMSNorm split between producer and consumer linears.
+        The reference runs residual-add + RMSNorm as its own kernel after o_proj / down_proj
+        (qwen2_decoder_layer.cpp:89-112).  Here the row-parallel projection's epilogue adds the residual, writes the
+        updated residual stream and per-tile partial sums of its squares ("residual_stats"); the NEXT linear (qkv /
+        gate_up) takes the residual stream as its x, sums the partials in a fixed order and normalises while it stages x in
+        shared memory; RoPE + KV scatter ride in the qkv epilogue, SiLU*mul in the gate_up epilogue.  The residual stream
+        ping-pongs between two buffers (the producer's CTAs read the old one while they write the new one)."""
         cfg, w = self.cfg, self.w
+        eps = cfg.rms_norm_eps
         ops.embedding(self.hidden, self.token_ids, w.embed)
-        x, res_in, pp = self.hidden, None, 0          # pending un-normalised activations + residual stream
+        # layer 0's input norm has no producer linear: the plain kernel (one launch per step)
+        ops.rms_norm(self.normed, self.hidden, w.layers[0]["input_norm"], eps)
+        res, pp, stats = self.hidden, 0, None
+        B = self.hidden.size(0)
         for li, L in enumerate(w.layers):
-            self._qkv_and_rope(L, li, x, L["input_norm"], res_in, self.res_pp[pp])
-            res_in, pp = self.res_pp[pp], pp ^ 1
+            if li == 0:
+                self._qkv_and_rope(L, li, self.normed)
+            else:
+                self._qkv_and_rope(L, li, res, L["input_norm"], stats_in=stats)
             self._attention(li)
-            L["o"].forward(self.attn_out, self.buf_a)
-            gu = L["gate_up"]
+            o, gu, dn = L["o"], L["gate_up"], L["down"]
+            ops.w4a16_decode_fused(self.attn_out, o.qweight, o.meta, o.group_size, o.bias, self.buf_a, epilogue="residual_stats",
+                                   residual_in=res, residual_out=self.res_pp[pp], norm_stats_out=self.norm_stats[0])
+            res, pp = self.res_pp[pp], pp ^ 1
             epi = "act_mul" if gu.gate_up_interleaved else "none"
-            ops.w4a16_decode_fused(self.buf_a, gu.qweight, gu.meta, gu.group_size, gu.bias,
-                                   self.act if epi == "act_mul" else self.gate_up, norm_weight=L["post_norm"],
-                                   eps=cfg.rms_norm_eps, residual_in=res_in, residual_out=self.res_pp[pp], epilogue=epi,
+            ops.w4a16_decode_fused(res, gu.qweight, gu.meta, gu.group_size, gu.bias, self.act if epi == "act_mul" else self.gate_up,
+                                   norm_weight=L["post_norm"], eps=eps, norm_stats_in=self.norm_stats[0], epilogue=epi,
                                    act_mode="silu")
-            res_in, pp = self.res_pp[pp], pp ^ 1
             if epi == "none":
                 ops.act_and_mul(self.act, self.gate_up, "silu")
-            L["down"].forward(self.act, self.buf_b)
-            x = self.buf_b
-        # final add + norm in front of the (bf16) lm_head
-        self.residual = res_in
-        ops.fused_add_rms_norm(x, self.residual, w.final_norm, cfg.rms_norm_eps)
-        w.lm_head.forward(x, self.logits_local)
+            ops.w4a16_decode_fused(self.act, dn.qweight, dn.meta, dn.group_size, dn.bias, self.buf_b, epilogue="residual_stats",
+                                   residual_in=res, residual_out=self.res_pp[pp], norm_stats_out=self.norm_stats[1],
+                                   stage_x=ops.w4a16_decode_fused_fits(B, dn.K))
+            res, pp, stats = self.res_pp[pp], pp ^ 1, self.norm_stats[1]
+        self.residual = res
+        ops.rms_norm(self.normed, res, w.final_norm, eps)
+        w.lm_head.forward(self.normed, self.logits_local)
         ops.argmax(self.next_tokens, self.logits)
 
     def launch_step(self, trace=None):
