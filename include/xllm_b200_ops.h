@@ -305,6 +305,21 @@ int xb_prefill_paged_bf16(const void* q, int64_t q_stride_n, int64_t q_stride_h,
                           int batch, int64_t total_q, int max_qo_len, int num_qo_heads,
                           int num_kv_heads, int head_dim, int causal, float sm_scale,
                           xb_stream_t stream);
+/* split-KV form of paged_run for a short query chunk over a long KV (the reference's planner decides split_kv,
+ * layers/cuda/flashinfer_planinfo.cpp:168-247): the kv tiles of every (q tile, kv head, request) are divided over
+ * kv_splits CTAs, fp32 partials + LSEs go to workspace_f32 (xb_prefill_split_workspace_bytes) and a merge kernel
+ * finishes.  xb_prefill_plan_splits is the host-side decision (pure arithmetic); kv_splits == 1 is xb_prefill_paged_bf16. */
+int xb_prefill_paged_split_bf16(const void* q, int64_t q_stride_n, int64_t q_stride_h,
+                                const void* k_cache, const void* v_cache, int64_t num_pages,
+                                int page_size, const int32_t* qo_indptr, const int32_t* kv_indptr,
+                                const int32_t* kv_indices, const int32_t* kv_last_page_len, void* o,
+                                int64_t o_stride_n, int64_t o_stride_h, float* lse, int batch,
+                                int64_t total_q, int max_qo_len, int num_qo_heads, int num_kv_heads,
+                                int head_dim, int causal, float sm_scale, int kv_splits,
+                                void* workspace_f32, int64_t workspace_bytes, xb_stream_t stream);
+int64_t xb_prefill_split_workspace_bytes(int kv_splits, int64_t total_q, int num_qo_heads, int head_dim);
+int xb_prefill_plan_splits(int batch, int max_qo_len, int64_t max_kv_len, int num_qo_heads,
+                           int num_kv_heads, int num_sms);
 
 /* ---- tcgen05 GEMMs for prefill-sized M (any M; TMA zero-fills ragged edges) ---------------------
  * C[M,N] = A[M,K] . B[N,K]^T (+ bias), fp32 accumulation in TMEM, bf16 output.

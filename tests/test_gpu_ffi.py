@@ -190,3 +190,34 @@ def test_ffi_plan_under_cuda_graph_serves_longer_contexts(module, built_lib):
             ref = O.paged_attention(q, kc, vc, qo, indptr, indices, last, sc, causal=False)
             scale = O.paged_attention(q, kc, vc.abs(), qo, indptr, indices, last, sc, causal=False)
             assert_close_attention(out, ref, scale, what=f"{module} module, graph-time plan at {plan_lens}, run at {kv_lens}")
+
+
+def test_ffi_paged_run_splits_kv_for_short_chunks(built_lib):
+    """chunked prefill of a 16-token chunk over 6000 cached tokens through the prefill module: `plan` must decide a
+    KV split (the reference's planner does, flashinfer_planinfo.cpp:168-247) and `paged_run` must match the oracle."""
+    import tvm_ffi
+    mod = _load("prefill", 128)
+    HQ, HKV, D, page = 28, 4, 128, 16
+    g = torch.Generator().manual_seed(23)
+    kv_len, qn = 6016, 16
+    npg = (kv_len + page - 1) // page
+    kc = torch.randn(npg + 3, page, HKV, D, generator=g).to(BF16)
+    vc = torch.randn(npg + 3, page, HKV, D, generator=g).to(BF16)
+    idx = (torch.randperm(npg + 2, generator=g) + 1)[:npg].to(torch.int32)
+    indptr = torch.tensor([0, npg], dtype=torch.int32)
+    last = torch.tensor([(kv_len - 1) % page + 1], dtype=torch.int32)
+    qo = torch.tensor([0, qn], dtype=torch.int32)
+    q = torch.randn(qn, HQ, D, generator=g).to(BF16)
+    out = torch.empty(qn, HQ, D, dtype=BF16, device=DEV)
+    sc = 1.0 / math.sqrt(D)
+    fws, iws, pin = _ws()
+    with tvm_ffi.use_torch_stream():
+        plan = mod["plan"](fws, iws, pin, qo, indptr, torch.tensor([kv_len], dtype=torch.int32), qn, 1, HQ, HKV, page, False, D, D,
+                           True, -1, -1, False, 0)
+        assert len(plan) == 7 and plan[5] == 0 and plan[6] > 1, f"expected a KV split for 4 CTAs of work, plan = {list(plan)}"
+        mod["paged_run"](fws, iws, plan, q.to(DEV), kc.to(DEV), vc.to(DEV), qo.to(DEV), indptr.to(DEV), idx.to(DEV), last.to(DEV),
+                         out, None, 1, 0, -1, True, None, None, None, None, None, None, 0.0, sc, 1.0, 1.0 / 10000.0, 0)
+    torch.cuda.synchronize()
+    ref = O.paged_attention(q, kc, vc, qo, indptr, idx, last, sc, causal=True)
+    scale = O.paged_attention(q, kc, vc.abs(), qo, indptr, idx, last, sc, causal=True)
+    assert_close_attention(out, ref, scale, what="FFI paged_run with split KV")

@@ -106,3 +106,45 @@ def test_prefill_decode_kernels_agree(built_lib):
     ops.batch_decode(plan, q.to(DEV), *args, sc, o2)
     scale = O.paged_attention(q, kc, vc.abs(), qo, indptr, perm, last, sc, causal=False)
     assert_close_attention(o1, o2, scale, what="prefill-kernel decode vs decode kernel")
+
+
+@pytest.mark.parametrize("q_lens,kv_lens,page", [([16], [4096], 128), ([64, 8, 1], [3000, 8192, 700], 16), ([128], [2048], 128)])
+@pytest.mark.parametrize("splits", [2, 5, 8])
+def test_chunked_prefill_split_kv_matches_oracle_and_unsplit(q_lens, kv_lens, page, splits, built_lib):
+    """short query chunk over a long paged KV: the split-KV path (fp32 partials + merge kernel; the reference's planner
+    splits the same cases, flashinfer_planinfo.cpp:168-247) against the oracle and against the unsplit kernel."""
+    from xllm_b200 import ops
+    HQ, HKV, D = 28, 4, 128
+    g = torch.Generator().manual_seed(17)
+    B = len(q_lens)
+    npg = [(n + page - 1) // page for n in kv_lens]
+    nblocks = sum(npg) + 3
+    perm = (torch.randperm(nblocks - 1, generator=g) + 1)[:sum(npg)].to(torch.int32)
+    indptr = torch.tensor([0] + list(torch.tensor(npg).cumsum(0).tolist()), dtype=torch.int32)
+    last = torch.tensor([(n - 1) % page + 1 for n in kv_lens], dtype=torch.int32)
+    qo = torch.tensor([0] + list(torch.tensor(q_lens).cumsum(0).tolist()), dtype=torch.int32)
+    T = sum(q_lens)
+    q = torch.randn(T, HQ, D, generator=g).to(BF16)
+    kc = torch.randn(nblocks, page, HKV, D, generator=g).to(BF16)
+    vc = torch.randn(nblocks, page, HKV, D, generator=g).to(BF16)
+    sc = 1.0 / math.sqrt(D)
+    ref, ref_lse = O.paged_attention(q, kc, vc, qo, indptr, perm, last, sc, causal=True, return_lse=True)
+    scale = O.paged_attention(q, kc, vc.abs(), qo, indptr, perm, last, sc, causal=True)
+    args = (q.to(DEV), kc.to(DEV), vc.to(DEV), indptr.to(DEV), perm.to(DEV), last.to(DEV), sc)
+    out = torch.empty(T, HQ, D, dtype=BF16, device=DEV)
+    lse = torch.empty(T, HQ, dtype=torch.float32, device=DEV)
+    ops.batch_chunked_prefill(*args, out, lse, qo.to(DEV), True, max(q_lens), kv_splits=splits)
+    base = torch.empty_like(out)
+    ops.batch_chunked_prefill(*args, base, None, qo.to(DEV), True, max(q_lens))
+    torch.cuda.synchronize()
+    assert_close_attention(out, ref, scale, what=f"split-KV chunked prefill q={q_lens} kv={kv_lens} splits={splits}")
+    assert_close_attention(out, base, scale, what="split vs unsplit kernel")
+    assert torch.allclose(lse.cpu(), ref_lse, rtol=1e-4, atol=5e-3), "base-2 LSE of the merged result"
+
+
+def test_prefill_plan_splits_rule(built_lib):
+    from xllm_b200 import ops
+    assert ops.prefill_plan_splits(1, 2048, 2048, 28, 4) == 1          # 112 q tiles x 4 heads: plenty of CTAs
+    assert ops.prefill_plan_splits(1, 16, 8192, 28, 4) == 16           # 1 x 4 CTAs: min(148 / 4 = 37, 8192 / 512 = 16)
+    assert ops.prefill_plan_splits(1, 16, 600, 28, 4) == 1             # short KV: not worth a merge pass
+    assert ops.prefill_plan_splits(8, 18, 4096, 28, 4) == 4            # 8 x 4 = 32 CTAs -> 148 / 32 = 4

@@ -114,3 +114,17 @@ def test_launchers_validate_before_touching_the_gpu(built_lib):
     assert lib.xb_linear_w4a16_small_m(null, i64(0), null, i64(0), null, null, null, i32(0), i32(4608), i32(3584), i32(128),
                                        null) == 0
     assert lib.xb_linear_bf16_small_m(null, i64(0), null, i64(0), null, null, i32(0), i32(64), i32(64), null) == 0
+
+
+def test_prefill_split_kv_decision(built_lib):
+    """xb_prefill_plan_splits: host arithmetic of the split-KV decision for short-q / long-kv chunked prefill."""
+    lib = _lib.lib()
+    f = lambda *a: lib.xb_prefill_plan_splits(*a)
+    assert f(1, 2048, ctypes.c_int64(2048), 28, 4, 148) == 1          # 112 q tiles x 4 kv heads: enough CTAs
+    assert f(1, 16, ctypes.c_int64(8192), 28, 4, 148) == 16           # 4 CTAs: min(148 / 4, 8192 / 512)
+    assert f(1, 16, ctypes.c_int64(600), 28, 4, 148) == 1             # short KV: no merge pass
+    assert f(8, 18, ctypes.c_int64(4096), 28, 4, 148) == 4
+    assert f(1, 1, ctypes.c_int64(100000), 64, 8, 148) == 18          # 8 CTAs -> 148 / 8
+    lib.xb_prefill_split_workspace_bytes.restype = ctypes.c_int64
+    assert lib.xb_prefill_split_workspace_bytes(4, ctypes.c_int64(16), 28, 128) == 4 * 16 * 28 * 129 * 4
+    assert lib.xb_prefill_split_workspace_bytes(1, ctypes.c_int64(16), 28, 128) == 0

@@ -25,6 +25,7 @@ def lib():
         _lib.xb_last_error.restype = ctypes.c_char_p
         _lib.xb_launch_count.restype = ctypes.c_uint64
         _lib.xb_abi_version.restype = ctypes.c_int
+        _lib.xb_prefill_split_workspace_bytes.restype = ctypes.c_int64
     return _lib
 
 

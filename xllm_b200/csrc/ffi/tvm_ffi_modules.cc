@@ -120,14 +120,14 @@ void DecodeRun(TensorView float_ws, TensorView int_ws, Array<int64_t> plan_vec, 
 // ---------------------------------------------------------------------------------------------------------------
 // plan_info of the prefill module: [0] max_qo_len [1] batch [2] total rows [3] qo heads [4] causal
 //   [5] 1 = every request has exactly one query row: paged_run is served by the split-KV decode kernel, whose plan8
-//       follows in [6..13]  (a one-row query sees the whole KV under either mask mode: FlashInfer masks
+//       follows in [6..13]; 0: [6] = kv_splits of the tcgen05 paged kernel (1 = no split)  (a one-row query sees the whole KV under either mask mode: FlashInfer masks
 //       kv_idx + qo_len > kv_len + q_idx, prefill.cuh:1017)
 Array<int64_t> PrefillPlan(TensorView float_ws, TensorView int_ws, TensorView pinned_int_ws, TensorView qo_indptr_host,
                            TensorView kv_indptr_host, TensorView kv_len_arr_host, int64_t total_num_rows, int64_t batch_size,
                            int64_t num_qo_heads, int64_t num_kv_heads, int64_t page_size, bool enable_cuda_graph,
                            int64_t head_dim_qk, int64_t head_dim_vo, bool causal, int64_t window_left,
                            int64_t fixed_split_size, bool disable_split_kv, int64_t num_colocated_ctas) {
-  (void)pinned_int_ws; (void)kv_len_arr_host; (void)fixed_split_size; (void)disable_split_kv; (void)num_colocated_ctas;
+  (void)pinned_int_ws; (void)fixed_split_size; (void)num_colocated_ctas;
   if (window_left >= 0) TVM_FFI_THROW(ValueError) << "sliding window attention is not implemented";
   if (head_dim_qk != head_dim_vo) TVM_FFI_THROW(ValueError) << "head_dim_qk != head_dim_vo";
   const int32_t* qo = static_cast<const int32_t*>(ptr(qo_indptr_host));
@@ -145,6 +145,21 @@ Array<int64_t> PrefillPlan(TensorView float_ws, TensorView int_ws, TensorView pi
   out.push_back(num_qo_heads);
   out.push_back(causal ? 1 : 0);
   out.push_back(one_row ? 1 : 0);
+  if (!one_row) {
+    // split-KV decision for short-q / long-kv chunked prefill (FlashInfer's planner decides split_kv here too:
+    // flashinfer_planinfo.cpp:168-247): host arithmetic on the lengths the reference hands over
+    const int32_t* kvl = static_cast<const int32_t*>(ptr(kv_len_arr_host));
+    int64_t max_kv = 0;
+    for (int64_t b = 0; b < batch_size; ++b) max_kv = std::max<int64_t>(max_kv, kvl[b]);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int splits = (disable_split_kv || page_size <= 1) ? 1
+                     : xb_prefill_plan_splits((int)batch_size, (int)max_qo, max_kv, (int)num_qo_heads, (int)num_kv_heads, sms);
+    const int64_t ws_bytes = float_ws.numel() * (float_ws.dtype().bits / 8);
+    while (splits > 1 && xb_prefill_split_workspace_bytes(splits, total_num_rows, (int)num_qo_heads, (int)head_dim_qk) > ws_bytes) --splits;
+    out.push_back(splits);
+  }
   if (one_row) {
     int64_t plan[8];
     // page_size 1 with kv_indptr = cu_seq_lens is how the reference plans ragged prefill; only real page tables land here
@@ -218,6 +233,17 @@ void PagedRun(TensorView float_ws, TensorView int_ws, Array<int64_t> plan_vec, T
     return;
   }
   if (layout != 0) TVM_FFI_THROW(ValueError) << "paged_run: only the NHD cache layout is implemented";
+  if (plan_vec.size() >= 7 && plan_vec[6] > 1) {
+    check_rc(xb_prefill_paged_split_bf16(ptr(q), q.stride(0), q.stride(1), ptr(k_cache), ptr(v_cache), k_cache.size(0),
+                                         (int)k_cache.size(1), static_cast<const int32_t*>(ptr(qo_indptr)),
+                                         static_cast<const int32_t*>(ptr(kv_indptr)), static_cast<const int32_t*>(ptr(kv_indices)),
+                                         static_cast<const int32_t*>(ptr(kv_last_page_len)), ptr(o), o.stride(0), o.stride(1), lse,
+                                         (int)plan_vec[1], q.size(0), (int)plan_vec[0], (int)q.size(1), (int)k_cache.size(2),
+                                         (int)q.size(2), mask_mode_code == 1, (float)sm_scale, (int)plan_vec[6], ptr(float_ws),
+                                         float_ws.numel() * (float_ws.dtype().bits / 8), stream_of(q)),
+             "batch prefill paged_run (split KV)");
+    return;
+  }
   check_rc(xb_prefill_paged_bf16(ptr(q), q.stride(0), q.stride(1), ptr(k_cache), ptr(v_cache), k_cache.size(0),
                                  (int)k_cache.size(1), static_cast<const int32_t*>(ptr(qo_indptr)),
                                  static_cast<const int32_t*>(ptr(kv_indptr)), static_cast<const int32_t*>(ptr(kv_indices)),

@@ -229,8 +229,9 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     } else {
     for (int tok = 0; tok < M; ++tok) {
       const uint4* src = reinterpret_cast<const uint4*>(x + (int64_t)tok * x_stride);
-      const uint4* rsrc = fz.res_in ? reinterpret_cast<const uint4*>(fz.res_in + (int64_t)tok * K) : nullptr;
-      uint4* rdst = (fz.res_out && blockIdx.x == 0) ? reinterpret_cast<uint4*>(fz.res_out + (int64_t)tok * K) : nullptr;
+      // (under epilogue 3 the residual pointers belong to the EPILOGUE - the [M, N] residual stream - not to x)
+      const uint4* rsrc = (kEpi != 3 && fz.res_in) ? reinterpret_cast<const uint4*>(fz.res_in + (int64_t)tok * K) : nullptr;
+      uint4* rdst = (kEpi != 3 && fz.res_out && blockIdx.x == 0) ? reinterpret_cast<uint4*>(fz.res_out + (int64_t)tok * K) : nullptr;
       uint4* dst = reinterpret_cast<uint4*>(xs + (int64_t)tok * xs_stride);
       float ss = 0.f;
       for (int idx = threadIdx.x; idx < nvec; idx += kWarps * 32) {

@@ -33,6 +33,13 @@ struct PrefillParams {
   float scale_log2;
   int num_qo_heads, num_kv_heads, group, tokens_per_tile, causal;
   int box_rows;                    // kv rows per TMA load (min(page_size, 128) or 128 for ragged)
+  // split-KV (short q over a long KV: chunked prefill of a small chunk, flashinfer_planinfo.cpp:168-247 split_kv): the kv
+  // tiles of a work item are divided over kv_splits CTAs (blockIdx.z = request * kv_splits + split); each writes a
+  // normalised fp32 partial + base-2 LSE, prefill_merge_kernel combines them.  kv_splits == 1: direct output.
+  int kv_splits;
+  float* part_o;                   // [kv_splits][total_q][Hq][D]
+  float* part_lse;                 // [kv_splits][total_q][Hq]
+  int64_t total_q;
 };
 
 constexpr int kQT = 128;   // MMA rows
@@ -73,7 +80,7 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, kvh = blockIdx.y;
+  const int b = blockIdx.z / p.kv_splits, split = blockIdx.z - b * p.kv_splits, kvh = blockIdx.y;
   const int ti = gridDim.x - 1 - blockIdx.x;          // heavy (late, causal) tiles first
 
   if (threadIdx.x == 0) {
@@ -121,7 +128,11 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int kv_off = kv_len - qo_len;                  // causal offset of chunked prefill (prefill.cuh:1017 semantics)
   int kv_limit = p.causal ? min(kv_len, tq_last + kv_off + 1) : kv_len;
   if (kv_limit < 0) kv_limit = 0;
-  const int n_tiles = live ? (kv_limit + kKT - 1) / kKT : 0;
+  const int n_tiles_all = live ? (kv_limit + kKT - 1) / kKT : 0;
+  // this CTA's share of the kv tiles; j below counts LOCAL tiles (ring phases), j0 + j is the kv tile
+  const int per_split = (n_tiles_all + p.kv_splits - 1) / p.kv_splits;
+  const int j0 = split * per_split;
+  const int n_tiles = max(0, min(per_split, n_tiles_all - j0));
   const int rows_used = p.tokens_per_tile * p.group;
 
   if (warp == 0) {
@@ -142,7 +153,7 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           uint8_t* dst = (kv ? v_s : k_s) + st * Cfg::kKVBytes;
           const CUtensorMap* map = kv ? &tmap_v : &tmap_k;
           for (int i = 0; i < loads; ++i) {
-            const int t0 = j * kKT + i * p.box_rows;
+            const int t0 = (j0 + j) * kKT + i * p.box_rows;
             int row;
             if (p.paged) {
               int pg = t0 / p.page_size;
@@ -222,8 +233,8 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       const uint32_t s_tmem = tmem_base + sb * 128 + lane_addr;
       mbar_wait(s_full + sb, (j >> 1) & 1);
       tc_fence_after_sync();
-      const bool need_mask = (j + 1) * kKT > lim_first;
-      const int col_lim = my_lim - j * kKT;             // columns >= col_lim are masked
+      const bool need_mask = (j0 + j + 1) * kKT > lim_first;
+      const int col_lim = my_lim - (j0 + j) * kKT;      // columns >= col_lim are masked
       // ---- pass 1: row max ----
       float mx = -INFINITY;
 #pragma unroll 1
@@ -304,11 +315,19 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
     __nv_bfloat16* dst = nullptr;
+    float* pdst = nullptr;
     if (row_valid) {
       const int64_t tq = q0 + q_idx;
       const int head = kvh * p.group + head_local;
-      dst = p.o + tq * p.o_stride_n + (int64_t)head * p.o_stride_h;
-      if (p.lse) p.lse[tq * p.num_qo_heads + head] = l_run > 0.f ? m_run + log2f(l_run) : -INFINITY;
+      const float lse2 = l_run > 0.f ? m_run + log2f(l_run) : -INFINITY;
+      if (p.kv_splits == 1) {
+        dst = p.o + tq * p.o_stride_n + (int64_t)head * p.o_stride_h;
+        if (p.lse) p.lse[tq * p.num_qo_heads + head] = lse2;
+      } else {
+        const int64_t slot = ((int64_t)split * p.total_q + tq) * p.num_qo_heads + head;
+        pdst = p.part_o + slot * kD;
+        p.part_lse[slot] = lse2;
+      }
     }
 #pragma unroll 1
     for (int c = 0; c < kD / 32; ++c) {
@@ -320,7 +339,7 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0;
       }
-      if (row_valid) {
+      if (dst) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
@@ -330,12 +349,42 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
           *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
         }
+      } else if (pdst) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(pdst + c * 32 + i * 4) =
+              make_float4(__uint_as_float(v[4 * i]) * inv, __uint_as_float(v[4 * i + 1]) * inv,
+                          __uint_as_float(v[4 * i + 2]) * inv, __uint_as_float(v[4 * i + 3]) * inv);
       }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// Combines the kv_splits partials of every (q row, head): weights 2^(lse_s - max) / sum, fixed split order.
+__global__ void __launch_bounds__(128)
+prefill_merge_kernel(const PrefillParams p, int head_dim) {
+  const int64_t tq = blockIdx.x;
+  const int head = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
+  float mx = -INFINITY;
+  for (int s = 0; s < p.kv_splits; ++s) mx = fmaxf(mx, p.part_lse[((int64_t)s * p.total_q + tq) * p.num_qo_heads + head]);
+  const float m_safe = mx == -INFINITY ? 0.f : mx;
+  float wsum = 0.f;
+  for (int s = 0; s < p.kv_splits; ++s) wsum += fast_exp2(p.part_lse[((int64_t)s * p.total_q + tq) * p.num_qo_heads + head] - m_safe);
+  const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
+  for (int d = threadIdx.x; d < head_dim; d += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < p.kv_splits; ++s) {
+      const int64_t slot = ((int64_t)s * p.total_q + tq) * p.num_qo_heads + head;
+      acc += p.part_o[slot * head_dim + d] * fast_exp2(p.part_lse[slot] - m_safe);
+    }
+    p.o[tq * p.o_stride_n + (int64_t)head * p.o_stride_h + d] = __float2bfloat16_rn(acc * inv);
+  }
+  if (p.lse && threadIdx.x == 0) p.lse[tq * p.num_qo_heads + head] = wsum > 0.f ? mx + log2f(wsum) : -INFINITY;
 }
 
 template <int kD>
@@ -348,8 +397,10 @@ static int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  dim3 grid(q_tiles, p.num_kv_heads, batch), block(192);
+  dim3 grid(q_tiles, p.num_kv_heads, batch * p.kv_splits), block(192);
   XB_CUDA_OK(launch(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, tq, tk, tv, p));
+  if (p.kv_splits > 1)
+    XB_CUDA_OK(launch(prefill_merge_kernel, dim3((unsigned)p.total_q, p.num_qo_heads), dim3(kD < 128 ? kD : 128), 0, stream, true, p, kD));
   return 0;
 }
 
@@ -365,8 +416,16 @@ static int prefill_common(const void* q, int64_t q_stride_n, int64_t q_stride_h,
                           const int32_t* qo_indptr, const int32_t* kv_indptr, const int32_t* kv_indices,
                           const int32_t* kv_last_page_len, void* o, int64_t o_stride_n, int64_t o_stride_h, float* lse,
                           int batch, int max_qo_len, int num_qo_heads, int num_kv_heads, int head_dim, int causal,
-                          float sm_scale, cudaStream_t stream) {
+                          float sm_scale, cudaStream_t stream, int kv_splits = 1, void* workspace_f32 = nullptr,
+                          int64_t workspace_bytes = 0) {
   if (batch == 0 || total_q == 0 || max_qo_len == 0) return 0;
+  XB_CHECK(kv_splits >= 1 && kv_splits <= 64, "prefill attention: kv_splits %d out of range (1..64)", kv_splits);
+  if (kv_splits > 1) {
+    const int64_t need = (int64_t)kv_splits * total_q * num_qo_heads * (head_dim + 1) * 4;
+    XB_CHECK(workspace_f32 != nullptr && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace_f32) & 15) == 0,
+             "prefill attention: split-KV needs a 16-byte aligned float workspace of %lld bytes (got %lld)", (long long)need,
+             (long long)workspace_bytes);
+  }
   XB_CHECK(head_dim == 64 || head_dim == 128, "prefill attention: head_dim %d unsupported (64|128)", head_dim);
   XB_CHECK(num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0, "prefill attention: bad head counts %d/%d", num_qo_heads,
            num_kv_heads);
@@ -394,6 +453,10 @@ static int prefill_common(const void* q, int64_t q_stride_n, int64_t q_stride_h,
   p.group = group;
   p.tokens_per_tile = 128 / group;
   p.causal = causal;
+  p.kv_splits = kv_splits;
+  p.total_q = total_q;
+  p.part_o = reinterpret_cast<float*>(workspace_f32);
+  p.part_lse = p.part_o ? p.part_o + (int64_t)kv_splits * total_q * num_qo_heads * head_dim : nullptr;
   if (paged) {
     XB_CHECK(page_size > 0 && ((page_size <= 128 && 128 % page_size == 0) || page_size % 128 == 0),
              "prefill attention: page_size %d must divide 128 or be a multiple of it", page_size);
@@ -433,4 +496,43 @@ extern "C" int xb_prefill_paged_bf16(const void* q, int64_t q_stride_n, int64_t 
                         (int64_t)num_kv_heads * head_dim, 1, page_size, qo_indptr, kv_indptr, kv_indices, kv_last_page_len, o,
                         o_stride_n, o_stride_h, lse, batch, max_qo_len, num_qo_heads, num_kv_heads, head_dim, causal, sm_scale,
                         (cudaStream_t)stream);
+}
+
+// paged_run with the KV range of every work item divided over kv_splits CTAs (chunked prefill of a short chunk over a
+// long history: flashinfer_planinfo.cpp:168-247 decides split_kv; kernels/cuda/batch_chunked_prefill.cpp:63-91 runs it).
+// workspace_f32: kv_splits * total_q * num_qo_heads * (head_dim + 1) floats (xb_prefill_split_workspace_bytes).
+extern "C" int xb_prefill_paged_split_bf16(const void* q, int64_t q_stride_n, int64_t q_stride_h, const void* k_cache,
+                                           const void* v_cache, int64_t num_pages, int page_size, const int32_t* qo_indptr,
+                                           const int32_t* kv_indptr, const int32_t* kv_indices,
+                                           const int32_t* kv_last_page_len, void* o, int64_t o_stride_n, int64_t o_stride_h,
+                                           float* lse, int batch, int64_t total_q, int max_qo_len, int num_qo_heads,
+                                           int num_kv_heads, int head_dim, int causal, float sm_scale, int kv_splits,
+                                           void* workspace_f32, int64_t workspace_bytes, xb_stream_t stream) {
+  return prefill_common(q, q_stride_n, q_stride_h, total_q, k_cache, v_cache, num_pages * page_size,
+                        (int64_t)num_kv_heads * head_dim, 1, page_size, qo_indptr, kv_indptr, kv_indices, kv_last_page_len, o,
+                        o_stride_n, o_stride_h, lse, batch, max_qo_len, num_qo_heads, num_kv_heads, head_dim, causal, sm_scale,
+                        (cudaStream_t)stream, kv_splits, workspace_f32, workspace_bytes);
+}
+
+extern "C" int64_t xb_prefill_split_workspace_bytes(int kv_splits, int64_t total_q, int num_qo_heads, int head_dim) {
+  return kv_splits > 1 ? (int64_t)kv_splits * total_q * num_qo_heads * (head_dim + 1) * 4 : 0;
+}
+
+// Host-side split decision (pure arithmetic): how many KV splits make a short-q / long-kv batch fill the SMs.
+// grid = q tiles x kv heads x requests CTAs; split only when that leaves more than half of the SMs idle and the longest
+// KV spans several 128-token tiles; never more splits than 512-token pieces of the longest KV.
+extern "C" int xb_prefill_plan_splits(int batch, int max_qo_len, int64_t max_kv_len, int num_qo_heads, int num_kv_heads,
+                                      int num_sms) {
+  if (batch <= 0 || max_qo_len <= 0 || num_kv_heads <= 0 || num_qo_heads % num_kv_heads != 0) return 1;
+  if (num_sms <= 0) num_sms = 148;
+  const int group = num_qo_heads / num_kv_heads;
+  const int tokens_per_tile = group <= 128 ? 128 / group : 1;
+  const int64_t q_tiles = (max_qo_len + tokens_per_tile - 1) / tokens_per_tile;
+  const int64_t grid = q_tiles * num_kv_heads * batch;
+  if (grid * 2 > num_sms || max_kv_len < 1024) return 1;
+  int64_t splits = num_sms / grid;
+  const int64_t by_len = (max_kv_len + 511) / 512;
+  if (splits > by_len) splits = by_len;
+  if (splits > 32) splits = 32;
+  return splits < 1 ? 1 : (int)splits;
 }

@@ -400,9 +400,19 @@ def batch_prefill(query, key, value, q_cu_seq_lens, kv_cu_seq_lens, sm_scale, ou
           "batch_prefill")
 
 
+def prefill_plan_splits(batch, max_qo_len, max_kv_len, num_qo_heads, num_kv_heads, num_sms=148) -> int:
+    """host-side split-KV decision for a short query chunk over a long KV (what the reference's prefill `plan` decides,
+    flashinfer_planinfo.cpp:168-247)."""
+    return int(lib().xb_prefill_plan_splits(c_i32(batch), c_i32(max_qo_len), c_i64(max_kv_len), c_i32(num_qo_heads),
+                                            c_i32(num_kv_heads), c_i32(num_sms)))
+
+
 def batch_chunked_prefill(query, k_cache, v_cache, paged_kv_indptr, paged_kv_indices, paged_kv_last_page_len, sm_scale,
-                          output, output_lse=None, qo_indptr=None, causal=True, max_qo_len=None) -> None:
-    """xllm::kernel::cuda::batch_chunked_prefill (cuda_ops_api.h:110-128, batch_chunked_prefill.cpp:26-92)."""
+                          output, output_lse=None, qo_indptr=None, causal=True, max_qo_len=None, kv_splits=1,
+                          workspace=None) -> None:
+    """xllm::kernel::cuda::batch_chunked_prefill (cuda_ops_api.h:110-128, batch_chunked_prefill.cpp:26-92).
+    kv_splits > 1 (from prefill_plan_splits): split-KV kernel + merge; workspace = uint8/float CUDA buffer (allocated
+    here when absent)."""
     _cuda_bf16(query, "query"); _cuda_bf16(k_cache, "k_cache"); _cuda_bf16(v_cache, "v_cache"); _cuda_bf16(output, "output")
     _need(k_cache.is_contiguous() and v_cache.is_contiguous(), "caches must be contiguous NHD")
     T, Hq, D = query.shape
@@ -412,6 +422,17 @@ def batch_chunked_prefill(query, k_cache, v_cache, paged_kv_indptr, paged_kv_ind
         max_qo_len = 1
     if max_qo_len is None:
         max_qo_len = int((qo_indptr[1:] - qo_indptr[:-1]).max().item())
+    if kv_splits > 1:
+        need = int(lib().xb_prefill_split_workspace_bytes(c_i32(kv_splits), c_i64(T), c_i32(Hq), c_i32(D)))
+        if workspace is None:
+            workspace = torch.empty(need, dtype=torch.uint8, device=query.device)
+        check(lib().xb_prefill_paged_split_bf16(
+            _p(query), c_i64(query.stride(0)), c_i64(query.stride(1)), _p(k_cache), _p(v_cache), c_i64(k_cache.size(0)),
+            c_i32(k_cache.size(1)), _p(qo_indptr), _p(paged_kv_indptr), _p(paged_kv_indices), _p(paged_kv_last_page_len),
+            _p(output), c_i64(output.stride(0)), c_i64(output.stride(1)), _p(output_lse), c_i32(B), c_i64(T), c_i32(max_qo_len),
+            c_i32(Hq), c_i32(k_cache.size(2)), c_i32(D), c_i32(1 if causal else 0), c_f32(sm_scale), c_i32(kv_splits),
+            _p(workspace), c_i64(workspace.numel() * workspace.element_size()), _stream()), "batch_chunked_prefill (split KV)")
+        return
     check(lib().xb_prefill_paged_bf16(_p(query), c_i64(query.stride(0)), c_i64(query.stride(1)), _p(k_cache), _p(v_cache),
                                       c_i64(k_cache.size(0)), c_i32(k_cache.size(1)), _p(qo_indptr), _p(paged_kv_indptr),
                                       _p(paged_kv_indices), _p(paged_kv_last_page_len), _p(output), c_i64(output.stride(0)),
