@@ -558,6 +558,11 @@ def main():
 
     def gate_up_fn(li):
         gu = L[li]["gate_up"]
+        if gu.kind == "w4a16" and gu.gate_up_interleaved and runner.fuse_gemv and tp == 1:
+            # exactly the launch _launch_step_fused() makes: split-RMSNorm consumer prologue + SiLU*mul epilogue
+            return lambda: ops.w4a16_decode_fused(runner.res_pp[0], gu.qweight, gu.meta, gu.group_size, gu.bias, runner.act,
+                                                  norm_weight=L[li]["post_norm"], eps=cfg.rms_norm_eps,
+                                                  norm_stats_in=runner.norm_stats[0], epilogue="act_mul", act_mode="silu")
         if gu.kind == "w4a16" and gu.gate_up_interleaved:
             return lambda: ops.w4a16_gate_up_act(runner.buf_a, gu.qweight, gu.meta, gu.group_size, "silu", gu.bias, runner.act,
                                                  runner.gate_up)
