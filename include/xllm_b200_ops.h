@@ -338,6 +338,10 @@ int xb_gemm_fp8_scaled(void* c, int64_t ldc, const void* a_e4m3, int64_t lda,
 int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda,
                   const uint32_t* qweight, const uint32_t* meta, const void* bias,
                   int M, int N, int K, int group_size, xb_stream_t stream);
+/* Kernel selection of the four xb_gemm_* entry points (tuning / tests; results are the same spec either way):
+ * 0 = automatic, 1 = single-CTA kernels only, 2 = CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles) kernels for shapes
+ * with >= 74 pair tiles, 3 = CTA-pair kernels for every shape with M > 128 and N % 256 == 0.  Returns the old mode. */
+int xb_set_gemm_cta_pair(int mode);
 
 /* ---- tensor-parallel exchange over NVLink peer memory (decode-sized messages) ---------------------------------
  * replaces parallel_state::reduce -> ProcessGroup::allreduce (framework/parallel_state/parallel_state.cpp:183-192,

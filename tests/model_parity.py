@@ -149,12 +149,13 @@ def upload(cfg, W, device="cuda"):
     return w
 
 
-def run_decode_parity(cfg, kv_lens, use_graph=True, fused=True, seed=2026):
+def run_decode_parity(cfg, kv_lens, use_graph=True, fused=True, seed=2026, fuse_gemv=False):
     """returns (max bf16-ulp distance of logits, tokens equal?)."""
     from xllm_b200.qwen2 import Qwen2DecodeRunner
     B = len(kv_lens)
     W, kcs, vcs, meta = build_case(cfg, B, kv_lens, seed)
-    runner = Qwen2DecodeRunner(cfg, upload(cfg, W), B, max(kv_lens), num_blocks=meta["nblocks"], fused_rope_cache=fused)
+    runner = Qwen2DecodeRunner(cfg, upload(cfg, W), B, max(kv_lens), num_blocks=meta["nblocks"], fused_rope_cache=fused,
+                               fuse_gemv=fuse_gemv)
     for li in range(cfg.num_layers):
         runner.k_caches[li].copy_(kcs[li])
         runner.v_caches[li].copy_(vcs[li])

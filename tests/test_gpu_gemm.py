@@ -163,3 +163,82 @@ def test_w4a16_decode_and_prefill_kernels_agree(built_lib):
     y2 = ops.w4a16_linear_small_m(x, qw.to(DEV), meta.to(DEV), gs)
     wd = Q.dequantize(q, s, z, gs)
     assert_close_sum(y1, y2, _abs_scale(x.cpu(), wd), rtol=1e-5, what="w4 prefill vs decode kernel")
+
+
+# ---- CTA-pair (tcgen05 cta_group::2) variants: same spec, 256 x 256 tiles over two SMs --------------------------------
+@pytest.fixture
+def cta_pairs(built_lib):
+    from xllm_b200 import ops
+    old = ops.set_gemm_cta_pair(3)
+    yield
+    ops.set_gemm_cta_pair(old)
+
+
+PAIR_SHAPES = [(256, 256, 64), (256, 256, 512), (384, 512, 1024), (300, 768, 200), (1024, 3584, 3584), (512, 37888, 3584),
+               (2049, 4608, 3584)]
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+def test_gemm_bf16_cta_pair(M, N, K, cta_pairs):
+    from xllm_b200 import ops
+    g = torch.Generator().manual_seed(2026)
+    a = torch.randn(M, K, generator=g).to(BF16)
+    w = (torch.randn(N, K, generator=g) * 0.02).to(BF16)
+    b = torch.randn(N, generator=g).to(BF16) if N % 3 == 0 else None
+    ref = O.linear(a, w, b)
+    ad, wd, bd = a.to(DEV), w.to(DEV), b.to(DEV) if b is not None else None
+    y = ops.gemm_bf16(ad, wd, bd)
+    assert_close_sum(y, ref, _abs_scale(a, w, b), rtol=1e-5, what=f"gemm_bf16 pair {M}x{N}x{K}")
+    assert_close_bf16(y, ref, ulps=1e9, rel_l2=1e-3, what="gemm_bf16 pair rel L2")
+    ops.set_gemm_cta_pair(1)
+    y1 = ops.gemm_bf16(ad, wd, bd)
+    ops.set_gemm_cta_pair(3)
+    assert_close_sum(y, y1, _abs_scale(a, w, b), rtol=1e-5, what="pair vs single-CTA kernel")
+
+
+@pytest.mark.parametrize("M,N,K,per_token,per_channel,use_bias", [(512, 1024, 768, True, True, True), (300, 256, 400 // 16 * 16, True, False, False),
+                                                                  (2048, 3584, 3584, False, False, False)])
+def test_cutlass_scaled_mm_cta_pair(M, N, K, per_token, per_channel, use_bias, cta_pairs):
+    from xllm_b200 import ops
+    g = torch.Generator().manual_seed(2026)
+    a = torch.randn(M, K, generator=g).clamp(-3, 3).to(E4M3)
+    w = torch.randn(N, K, generator=g).clamp(-3, 3).to(E4M3)
+    a_s = (torch.rand(M if per_token else 1, generator=g) * 0.1 + 0.01).float()
+    b_s = (torch.rand(N if per_channel else 1, generator=g) * 0.1 + 0.01).float()
+    bias = torch.randn(N, generator=g).to(BF16) if use_bias else None
+    ref = O.fp8_scaled_matmul(a, w, a_s, b_s, bias)
+    c = torch.empty(M, N, dtype=BF16, device=DEV)
+    ops.cutlass_scaled_mm(c, a.to(DEV), w.to(DEV).t(), a_s.to(DEV), b_s.to(DEV), bias.to(DEV) if bias is not None else None)
+    scale = (a.float().abs() @ w.float().abs().t()) * a_s.reshape(-1, 1) * b_s.reshape(1, -1)
+    if bias is not None:
+        scale = scale + bias.float().abs()
+    assert_close_sum(c, ref, scale, rtol=1e-5, what=f"cutlass_scaled_mm pair {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (300, 512, 256), (1024, 3584, 3584), (512, 37888, 3584), (400, 3584, 18944)])
+def test_gemm_w4a16_cta_pair(M, N, K, cta_pairs):
+    from xllm_b200 import ops, quant
+    gs = 128
+    g = torch.Generator().manual_seed(2026)
+    w = (torch.randn(N, K, generator=g) * 0.02).to(BF16)
+    q, s, z = Q.quantize(w, 4, gs)
+    x = torch.randn(M, K, generator=g).to(BF16)
+    ref = Q.linear_wna16(x, q, s, z, gs, None)
+    qw, meta = quant.pack_w4(q, s, z, gs)
+    y = ops.gemm_w4a16(x.to(DEV), qw.to(DEV), meta.to(DEV), gs)
+    assert_close_sum(y, ref, _abs_scale(x, Q.dequantize(q, s, z, gs)), rtol=1e-5, what=f"gemm_w4a16 pair {M}x{N}x{K}")
+    assert_close_bf16(y, ref, ulps=1e9, rel_l2=1e-3, what="gemm_w4a16 pair rel L2")
+
+
+def test_gemm_w4a16_cta_pair_dequant_bit_exact(cta_pairs):
+    """identity activations read BOTH CTAs' dequantised halves of B back out of the pair MMA bit-for-bit."""
+    from xllm_b200 import ops, quant
+    g = torch.Generator().manual_seed(11)
+    N, K, gs = 512, 256, 128
+    w = torch.randn(N, K, generator=g).to(BF16)
+    q, s, z = Q.quantize(w, 4, gs)
+    wd = Q.dequantize(q, s, z, gs)
+    qw, meta = quant.pack_w4(q, s, z, gs)
+    x = torch.eye(K, dtype=BF16)
+    y = ops.gemm_w4a16(x.to(DEV), qw.to(DEV), meta.to(DEV), gs)
+    assert torch.equal(y.cpu(), wd.t().contiguous())

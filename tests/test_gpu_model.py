@@ -41,6 +41,16 @@ def test_decode_step_matches_oracle(quant, use_graph, fused, built_lib):
             assert_close_bf16(g[new_rows], r[new_rows], ulps=1e9, rel_l2=2e-2, what=f"{name}_cache[{li}] new rows")
 
 
+def test_decode_step_split_rmsnorm_variant(built_lib):
+    """the 5-launches-per-layer step (add+RMSNorm split between the o / down epilogues and the qkv / gate_up prologues;
+    opt-in: Qwen2DecodeRunner(fuse_gemv=True)) computes the same step."""
+    cfg = _small("w4a16")
+    logits, ref_logits, nxt, ref_next, runner, _ = run_decode_parity(cfg, [37, 300, 1], True, True, fuse_gemv=True)
+    assert runner.fuse_gemv
+    assert_close_bf16(logits, ref_logits, ulps=1e9, rel_l2=2e-2, what="decode-step logits (split RMSNorm)")
+    assert torch.equal(nxt.long().cpu()[:3], ref_next), "greedy tokens differ"
+
+
 def test_decode_step_qwen2_0_5b_shape(built_lib):
     """BASELINE configs[0] architecture (Qwen2-0.5B bf16, batch 1, ctx 128) with 2 layers to keep the oracle fast."""
     from xllm_b200.qwen2 import Qwen2Config

@@ -32,7 +32,11 @@ KEYS = OrderedDict([
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: an .ncu-rep (read through `ncu -i`) or the `--page raw --csv` dump of one made on the GPU box."""
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
@@ -51,6 +55,12 @@ def full(rep, dst, title):
         for i in tensor_cols:
             if hdr[i] not in KEYS:
                 lines.append(f"| `{hdr[i]}` | {r[i]} | {units[i]} |")
+        stalls = sorted(((float(r[i].replace(",", "")), k) for i, k in enumerate(hdr)
+                         if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio")),
+                        reverse=True)[:6]
+        if stalls:
+            lines += ["", "top warp stall reasons (warps stalled per issue-active cycle): " +
+                      ", ".join(f"{k.split('issue_stalled_')[1].split('_per_issue')[0]} {v:.2f}" for v, k in stalls)]
         rd, wr = r[hdr.index("dram__bytes_read.sum")], r[hdr.index("dram__bytes_write.sum")]
         lines += ["", f"traffic = dram read + write = {rd} {units[hdr.index('dram__bytes_read.sum')]} + {wr} "
                   f"{units[hdr.index('dram__bytes_write.sum')]}", ""]

@@ -97,16 +97,19 @@ struct GemmParams {
 constexpr int kBlockM = 128;
 constexpr int kNumEpiWarps = 4;
 
-template <int kKind, int kBlockN, int kMT = 1 /* 128-row M tiles per CTA sharing one B stage */>
+template <int kKind, int kBlockN, int kMT = 1 /* 128-row M tiles per CTA sharing one B stage */,
+          int kCG = 1 /* 2: CTA pair (cta_group::2): 256 x kBlockN tile, each CTA holds / converts kBlockN/2 rows of B */>
 struct GemmCfg {
+  static_assert(kCG == 1 || (kCG == 2 && kMT == 1), "the CTA-pair kernel takes one 128-row M tile per CTA");
   static constexpr int kCtaM = kBlockM * kMT;
+  static constexpr int kCtaN = kBlockN / kCG;                       // B rows staged (and dequantised) by ONE CTA
   static constexpr int kElemA = kKind == kKindFP8 ? 1 : 2;
   static constexpr int kBlockK = 128 / kElemA;                     // one 128-byte swizzle row per tile row
   static constexpr int kUmmaK = 32 / kElemA;                       // 16 (bf16) / 32 (fp8) elements = 32 bytes
   static constexpr int kABytes = kCtaM * 128;
-  static constexpr int kBBytes = kBlockN * 128;
-  static constexpr int kPackedBytes = kKind == kKindW4 ? kBlockN * kBlockK / 2 : (kKind == kKindW8 ? kBlockN * kBlockK : 0);   // int4 / int8 tile
-  static constexpr int kMetaBytes = kind_is_wq(kKind) ? kBlockN * 4 : 0;
+  static constexpr int kBBytes = kCtaN * 128;
+  static constexpr int kPackedBytes = kKind == kKindW4 ? kCtaN * kBlockK / 2 : (kKind == kKindW8 ? kCtaN * kBlockK : 0);   // int4 / int8 tile
+  static constexpr int kMetaBytes = kind_is_wq(kKind) ? kCtaN * 4 : 0;
   // BF16 / FP8: a stage holds the A and B tiles.  W4: a stage holds A + the PACKED int4 B tile + its scale/zero words
   // (small, so the TMA ring can be deep enough to cover HBM latency) and the dequantised bf16 B lives in a separate
   // 2-deep ring written by the converter warps.
@@ -124,13 +127,14 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBStages * kBBytes + kEpiStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
-template <int kKind, int kBlockN, int kMT>
-__global__ void __launch_bounds__(GemmCfg<kKind, kBlockN, kMT>::kThreads, 1)
+template <int kKind, int kBlockN, int kMT, int kCG>
+__global__ void __launch_bounds__(GemmCfg<kKind, kBlockN, kMT, kCG>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_m,
                     const GemmParams p) {
-  using Cfg = GemmCfg<kKind, kBlockN, kMT>;
+  using Cfg = GemmCfg<kKind, kBlockN, kMT, kCG>;
   constexpr int kStages = Cfg::kStages;
+  constexpr bool kPair = kCG == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bbuf = smem + kStages * Cfg::kStageBytes;                  // W4: [kBStages][kBBytes] dequantised B ring
@@ -146,7 +150,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blocks = (p.M + Cfg::kCtaM - 1) / Cfg::kCtaM;
+  // CTA pair: rank 0 (leader) issues the MMAs and owns the barriers both CTAs feed (full, B-ready, TMEM-empty); a work
+  // unit is one 256 x kBlockN tile, walked by both CTAs of the pair in the same order
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_blocks = (p.M + Cfg::kCtaM * kCG - 1) / (Cfg::kCtaM * kCG);
   const int n_blocks = (p.N + kBlockN - 1) / kBlockN;
   const int num_tiles = m_blocks * n_blocks;
   const int num_kb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;
@@ -164,12 +173,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(packed_bar + s, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bready_bar + s, Cfg::kConvWarps > 0 ? Cfg::kConvWarps : 1);   // one elected arrive per converter warp
+      mbar_init(bready_bar + s, Cfg::kConvWarps > 0 ? Cfg::kConvWarps * kCG : 1);   // one elected arrive per converter warp (of both CTAs)
       mbar_init(bempty_bar + s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full + s, 1);
-      mbar_init(tmem_empty + s, kNumEpiWarps);
+      mbar_init(tmem_empty + s, kNumEpiWarps * kCG);
     }
     fence_barrier_init();
   }
@@ -179,11 +188,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (kind_is_wq(kKind)) tma_prefetch_desc(&tmap_m);
     if (p.use_tma_store) tma_prefetch_desc(&tmap_c);
   }
-  if (warp == 1) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_cg2(tmem_base_smem, Cfg::kTmemCols);
+    else tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / complete_tx / commit
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_smem;
+  // the leader's copies of the shared barriers (shared::cluster addresses; for rank 0 these are its own)
+  const uint32_t full_bar_leader = kPair ? cluster_map(smem_u32(full_bar), 0) : smem_u32(full_bar);
+  const uint32_t bready_leader = kPair ? cluster_map(smem_u32(bready_bar), 0) : smem_u32(bready_bar);
+  const uint32_t tmem_empty_leader = kPair ? cluster_map(smem_u32(tmem_empty), 0) : smem_u32(tmem_empty);
 
   pdl_launch_dependents();
   pdl_wait();   // A (activations) comes from the producer kernel
@@ -193,45 +210,60 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
         const int m_blk = tile % m_blocks, n_blk = tile / m_blocks;
+        const int a_row = (m_blk * kCG + (int)rank) * Cfg::kCtaM;           // this CTA's 128 (x kMT) rows of A
+        const int b_row = n_blk * kBlockN + (int)rank * Cfg::kCtaN;         // this CTA's share of the B rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1);
           if (kind_is_wq(kKind)) {
-            // packed B: the kBlockN/16 row tiles of this k tile are one 2-D TMA box (tensor [N/16][K/64 * 128 words],
-            // box [kBlockN/16][128 words], no swizzle) - one instruction instead of kBlockN/16 bulk copies - plus the
-            // group's scale/zero words for these kBlockN rows (tensor [K/g][N], box [1][kBlockN])
+            // packed B: the kCtaN/16 row tiles of this k tile are one 2-D TMA box (tensor [N/16][K/64 * 128 words],
+            // box [kCtaN/16][128 words], no swizzle) - one instruction instead of kCtaN/16 bulk copies - plus the
+            // group's scale/zero words for these kCtaN rows (tensor [K/g][N], box [1][kCtaN]); both stay CTA-local
             mbar_expect_tx(packed_bar + s, Cfg::kPackedBytes + Cfg::kMetaBytes);
             // (W8: one byte per weight - 256 words per row tile and k tile instead of 128)
-            tma_load_2d(stage_packed(s), &tmap_b, packed_bar + s, kb * (kKind == kKindW8 ? 256 : 128), n_blk * (kBlockN / 16));
-            tma_load_2d(stage_meta(s), &tmap_m, packed_bar + s, n_blk * kBlockN, kb >> p.gshift);
-            mbar_expect_tx(full_bar + s, Cfg::kABytes);
-            tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, m_blk * Cfg::kCtaM);
+            tma_load_2d(stage_packed(s), &tmap_b, packed_bar + s, kb * (kKind == kKindW8 ? 256 : 128), b_row / 16);
+            tma_load_2d(stage_meta(s), &tmap_m, packed_bar + s, b_row, kb >> p.gshift);
+            if (kPair) {
+              if (rank == 0) mbar_expect_tx(full_bar + s, Cfg::kABytes * 2);   // both CTAs' A tiles complete on the leader
+              tma_load_2d_cg2(stage_a(s), &tmap_a, full_bar_leader + s * 8, kb * Cfg::kBlockK, a_row);
+            } else {
+              mbar_expect_tx(full_bar + s, Cfg::kABytes);
+              tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, a_row);
+            }
+          } else if (kPair) {
+            if (rank == 0) mbar_expect_tx(full_bar + s, (Cfg::kABytes + Cfg::kBBytes) * 2);
+            tma_load_2d_cg2(stage_a(s), &tmap_a, full_bar_leader + s * 8, kb * Cfg::kBlockK, a_row);
+            tma_load_2d_cg2(stage_b(s), &tmap_b, full_bar_leader + s * 8, kb * Cfg::kBlockK, b_row);
           } else {
             mbar_expect_tx(full_bar + s, Cfg::kABytes + Cfg::kBBytes);
-            tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, m_blk * Cfg::kCtaM);
-            tma_load_2d(stage_b(s), &tmap_b, full_bar + s, kb * Cfg::kBlockK, n_blk * kBlockN);
+            tma_load_2d(stage_a(s), &tmap_a, full_bar + s, kb * Cfg::kBlockK, a_row);
+            tma_load_2d(stage_b(s), &tmap_b, full_bar + s, kb * Cfg::kBlockK, b_row);
           }
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = kKind == kKindFP8 ? umma_idesc(0, 0, kBlockM, kBlockN) : umma_idesc(1, 1, kBlockM, kBlockN);
+  } else if (warp == 1 && rank == 0) {
+    // ======================= MMA issuer (leader CTA of a pair) =======================
+    constexpr uint32_t idesc = kKind == kKindFP8 ? umma_idesc(0, 0, kBlockM * kCG, kBlockN) : umma_idesc(1, 1, kBlockM * kCG, kBlockN);
     int s = 0;
     uint32_t ph = 0;
     int as = 0;
     uint32_t aph = 0;
     int bs = 0;
     uint32_t bph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(tmem_empty + as, aph ^ 1);     // epilogue has drained this accumulator stage
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      if (kPair) mbar_wait_cluster(tmem_empty + as, aph ^ 1);   // BOTH CTAs' epilogues have drained this accumulator stage
+      else mbar_wait(tmem_empty + as, aph ^ 1);     // epilogue has drained this accumulator stage
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + as * Cfg::kAccCols;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar + s, ph);
-        if (kind_is_wq(kKind)) mbar_wait(bready_bar + bs, bph);
+        if (kind_is_wq(kKind)) {
+          if (kPair) mbar_wait_cluster(bready_bar + bs, bph);
+          else mbar_wait(bready_bar + bs, bph);
+        }
         tc_fence_after_sync();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(stage_a(s));
@@ -242,13 +274,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
             for (int mt = 0; mt < kMT; ++mt) {       // the M tiles of this CTA reuse the same B stage
               const uint64_t da = umma_desc_sw128(a_addr + mt * (kBlockM * 128) + k * 32);
-              if (kKind == kKindFP8) umma_f8(d_tmem + mt * kBlockN, da, db, idesc, (kb | k) != 0);
+              if (kPair) {
+                // M = 256 over the pair: the same shared-memory offsets address this CTA's and the peer's A rows / B rows
+                if (kKind == kKindFP8) umma_f8_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
+                else umma_f16_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
+              } else if (kKind == kKindFP8) umma_f8(d_tmem + mt * kBlockN, da, db, idesc, (kb | k) != 0);
               else umma_f16(d_tmem + mt * kBlockN, da, db, idesc, (kb | k) != 0);
             }
           }
-          umma_commit(empty_bar + s);                 // smem slot is free once these MMAs have read it
-          if (kind_is_wq(kKind)) umma_commit(bempty_bar + bs);
-          if (kb == num_kb - 1) umma_commit(tmem_full + as);
+          if (kPair) {
+            umma_commit_cg2(empty_bar + s);            // multicast: both CTAs' producers may refill the slot
+            if (kind_is_wq(kKind)) umma_commit_cg2(bempty_bar + bs);
+            if (kb == num_kb - 1) umma_commit_cg2(tmem_full + as);
+          } else {
+            umma_commit(empty_bar + s);                 // smem slot is free once these MMAs have read it
+            if (kind_is_wq(kKind)) umma_commit(bempty_bar + bs);
+            if (kb == num_kb - 1) umma_commit(tmem_full + as);
+          }
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1; }
@@ -256,7 +298,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-  } else if (warp < 2 + kNumEpiWarps) {
+  } else if (warp >= 2 && warp < 2 + kNumEpiWarps) {
     // ======================= epilogue =======================
     // TMEM -> registers (tcgen05.ld 32x32b: thread = accumulator row) -> scale/bias -> bf16 -> 128B-swizzled staging
     // tile in smem -> TMA store (clips ragged M / N edges).  Falls back to direct global stores when C rows are not
@@ -267,13 +309,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int sbuf = 0;
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       const int m_blk = tile % m_blocks, n_blk = tile / m_blocks;
       mbar_wait(tmem_full + as, aph);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int mt = 0; mt < kMT; ++mt) {
-      const int row0 = m_blk * Cfg::kCtaM + mt * kBlockM + q * 32;
+      const int row0 = (m_blk * kCG + (int)rank) * Cfg::kCtaM + mt * kBlockM + q * 32;
       const int row = row0 + lane;
       float a_s = 1.f;
       if (kKind == kKindFP8) a_s = p.a_scale[p.a_scale_per_row ? min(row, p.M - 1) : 0];
@@ -331,11 +373,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + as);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(tmem_empty_leader + as * 8);
+        else mbar_arrive(tmem_empty + as);
+      }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
     if (p.use_tma_store && lane == 0) tma_store_wait_all();
-  } else if (kind_is_wq(kKind)) {
+  } else if (kind_is_wq(kKind) && warp >= 2 + kNumEpiWarps) {
     // ======================= W4 / W8 converters (warps 6..13) =======================
     // converter warp cw handles row tiles cw, cw+8, ... of the stage; a lane's 16 bytes of packed data are
     // rows (g, g+8) x k in [16t, 16t+16) of its row tile  ->  four 16-byte chunks of the swizzled bf16 tile.
@@ -345,7 +390,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t ph = 0;
     int bs = 0;
     uint32_t bph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(packed_bar + s, ph);          // packed tile + meta landed
         mbar_wait(bempty_bar + bs, bph ^ 1);    // the MMA has finished reading this B buffer
@@ -353,7 +398,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t* mt = reinterpret_cast<const uint32_t*>(stage_meta(s));
         uint8_t* bt = b_ring(bs);
 #pragma unroll
-        for (int r = cw; r < kBlockN / 16; r += Cfg::kConvWarps) {
+        for (int r = cw; r < Cfg::kCtaN / 16; r += Cfg::kConvWarps) {
           uint32_t lo[8], hi[8];   // row g / row g+8: 16 bf16 = 8 packed registers, k ascending
           const uint32_t m0 = mt[r * 16 + g], m1 = mt[r * 16 + g + 8];
           if constexpr (kKind == kKindW8) {
@@ -408,7 +453,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(bready_bar + bs);
+        if (lane == 0) {
+          if (kPair) mbar_arrive_cluster(bready_leader + bs * 8);   // the leader's MMA reads this CTA's half through the pair
+          else mbar_arrive(bready_bar + bs);
+        }
         if (++s == kStages) { s = 0; ph ^= 1; }
         if (++bs == 2) { bs = 0; bph ^= 1; }
       }
@@ -416,32 +464,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (kPair) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal its barriers / read its B half
+  else __syncthreads();
+  if (warp == 1) {
+    if (kPair) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
-template <int kKind, int kBlockN, int kMT = 1>
+template <int kKind, int kBlockN, int kMT = 1, int kCG = 1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream,
                        const CUtensorMap* tm = nullptr) {
-  using Cfg = GemmCfg<kKind, kBlockN, kMT>;
-  auto kern = gemm_tcgen05_kernel<kKind, kBlockN, kMT>;
+  using Cfg = GemmCfg<kKind, kBlockN, kMT, kCG>;
+  auto kern = gemm_tcgen05_kernel<kKind, kBlockN, kMT, kCG>;
   static bool attr_done = false;
+  static int max_ctas = 148;     // persistent CTAs: one per SM; CTA pairs: 2 x the pairs the device co-schedules
   if (!attr_done) {
     XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_ctas, cudaDevAttrMultiProcessorCount, dev);
+    if (kCG == 2) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(max_ctas & ~1);
+      cfg.blockDim = dim3(Cfg::kThreads);
+      cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_ctas = 2 * n;
+      else max_ctas &= ~1;
+      cudaGetLastError();
+    }
     attr_done = true;
   }
-  static int num_sms = [] {
-    int dev = 0, n = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
-  const int tiles = ((p.M + Cfg::kCtaM - 1) / Cfg::kCtaM) * ((p.N + kBlockN - 1) / kBlockN);
-  dim3 grid(tiles < num_sms ? tiles : num_sms), block(Cfg::kThreads);
+  const int units = ((p.M + Cfg::kCtaM * kCG - 1) / (Cfg::kCtaM * kCG)) * ((p.N + kBlockN - 1) / kBlockN);
+  const int want = units * kCG;
+  dim3 grid(want < max_ctas ? want : max_ctas), block(Cfg::kThreads);
   CUtensorMap tc = ta;   // placeholder when the direct-store epilogue is used
   p.use_tma_store = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
   if (p.use_tma_store && make_tmap_2d(&tc, p.c, p.M, p.N, (uint64_t)p.ldc * 2, 32, 64, 2)) return 1;
-  XB_CUDA_OK(launch(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, ta, tb, tc, tm ? *tm : ta, p));
+  XB_CUDA_OK(launch_cluster(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, kCG, ta, tb, tc, tm ? *tm : ta, p));
   return 0;
 }
 
@@ -462,6 +530,33 @@ static int pick_block_n(int M, int N) {
   return 64;
 }
 
+// CTA-pair (cta_group::2) kernel: 256 x 256 tiles, each CTA stages half of B, so the shared-memory traffic per MMA flop
+// drops by a third (bf16 / fp8) and the converter work per flop halves (W4 / W8).  Needs enough 256-row tiles to fill
+// the 74 pairs.  Mode: xb_set_gemm_cta_pair() / XB_GEMM_CG.
+static std::atomic<int> g_cta_pair_mode{-1};   // -1: not set -> XB_GEMM_CG, else 0 (auto)
+static bool use_cta_pair(int M, int N, int bn) {
+  int mode = g_cta_pair_mode.load(std::memory_order_relaxed);
+  if (mode < 0) {
+    const char* e = getenv("XB_GEMM_CG");
+    mode = e ? atoi(e) : 0;
+    g_cta_pair_mode.store(mode, std::memory_order_relaxed);
+  }
+  if (mode == 0) mode = 1;                         // TODO(default): flip to 2 once the B200 A/B run confirms parity and speed
+  if (mode == 1 || bn != 256 || N % 256 != 0) return false;
+  const int64_t units = (int64_t)((M + 255) / 256) * (N / 256);
+  if (mode == 3) return M > 128;                   // every shape that can form a pair tile (tests)
+  return M >= 512 && units >= 74;
+}
+
+extern "C" int xb_set_gemm_cta_pair(int mode) {
+  if (mode < 0 || mode > 3) {
+    set_error("set_gemm_cta_pair: mode %d (0 auto | 1 single | 2 pairs | 3 pairs always)", mode);
+    return -1;
+  }
+  const int old = g_cta_pair_mode.exchange(mode, std::memory_order_relaxed);
+  return old < 0 ? 0 : old;
+}
+
 extern "C" int xb_gemm_bf16(void* c, int64_t ldc, const void* a, int64_t lda, const void* b, const void* bias, int M, int N,
                             int K, xb_stream_t stream) {
   if (M == 0 || N == 0) return 0;
@@ -474,9 +569,11 @@ extern "C" int xb_gemm_bf16(void* c, int64_t ldc, const void* a, int64_t lda, co
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.M = M; p.N = N; p.K = K;
   const int bn = pick_block_n(M, N);
+  const bool pair = use_cta_pair(M, N, bn);
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, kBlockM, 64, 2)) return 1;
-  if (make_tmap_2d(&tb, b, N, K, (uint64_t)K * 2, bn, 64, 2)) return 1;
+  if (make_tmap_2d(&tb, b, N, K, (uint64_t)K * 2, pair ? bn / 2 : bn, 64, 2)) return 1;
+  if (pair) return launch_gemm<kKindBF16, 256, 1, 2>(ta, tb, p, (cudaStream_t)stream);
   if (bn == 256) return launch_gemm<kKindBF16, 256>(ta, tb, p, (cudaStream_t)stream);
   return bn == 128 ? launch_gemm<kKindBF16, 128>(ta, tb, p, (cudaStream_t)stream)
                    : launch_gemm<kKindBF16, 64>(ta, tb, p, (cudaStream_t)stream);
@@ -499,9 +596,11 @@ extern "C" int xb_gemm_fp8_scaled(void* c, int64_t ldc, const void* a, int64_t l
   p.a_scale_per_row = a_scale_numel > 1; p.b_scale_per_col = b_scale_numel > 1;
   p.M = M; p.N = N; p.K = K;
   const int bn = pick_block_n(M, N);
+  const bool pair = use_cta_pair(M, N, bn);
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda, kBlockM, 128, 1)) return 1;
-  if (make_tmap_2d(&tb, b, N, K, (uint64_t)K, bn, 128, 1)) return 1;
+  if (make_tmap_2d(&tb, b, N, K, (uint64_t)K, pair ? bn / 2 : bn, 128, 1)) return 1;
+  if (pair) return launch_gemm<kKindFP8, 256, 1, 2>(ta, tb, p, (cudaStream_t)stream);
   if (bn == 256) return launch_gemm<kKindFP8, 256>(ta, tb, p, (cudaStream_t)stream);
   return bn == 128 ? launch_gemm<kKindFP8, 128>(ta, tb, p, (cudaStream_t)stream)
                    : launch_gemm<kKindFP8, 64>(ta, tb, p, (cudaStream_t)stream);
@@ -534,15 +633,18 @@ extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   static const int force_mt = [] { const char* e = getenv("XB_GEMM_W4_MT"); return e ? atoi(e) : 0; }();
   const bool two_m = force_mt == 2 && M >= 256 && N % 128 == 0;
   if (two_m) bn = 128;
+  const bool pair = !two_m && use_cta_pair(M, N, bn);
+  const int cta_n = pair ? bn / 2 : bn;      // B rows one CTA stages and dequantises
   CUtensorMap ta, tb, tm;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, two_m ? 256 : kBlockM, 64, 2)) return 1;
   const uint64_t ktiles = K / 64;
-  if (make_tmap_2d_raw(&tb, qweight, CU_TENSOR_MAP_DATA_TYPE_UINT32, N / 16, ktiles * 128, ktiles * 512, bn / 16, 128,
+  if (make_tmap_2d_raw(&tb, qweight, CU_TENSOR_MAP_DATA_TYPE_UINT32, N / 16, ktiles * 128, ktiles * 512, cta_n / 16, 128,
                        CU_TENSOR_MAP_SWIZZLE_NONE))
     return 1;
-  if (make_tmap_2d_raw(&tm, meta, CU_TENSOR_MAP_DATA_TYPE_UINT32, K / group_size, N, (uint64_t)N * 4, 1, bn,
+  if (make_tmap_2d_raw(&tm, meta, CU_TENSOR_MAP_DATA_TYPE_UINT32, K / group_size, N, (uint64_t)N * 4, 1, cta_n,
                        CU_TENSOR_MAP_SWIZZLE_NONE))
     return 1;
+  if (pair) return launch_gemm<kKindW4, 256, 1, 2>(ta, tb, p, (cudaStream_t)stream, &tm);
   if (two_m) return launch_gemm<kKindW4, 128, 2>(ta, tb, p, (cudaStream_t)stream, &tm);
   if (bn == 256) return launch_gemm<kKindW4, 256>(ta, tb, p, (cudaStream_t)stream, &tm);
   return bn == 128 ? launch_gemm<kKindW4, 128>(ta, tb, p, (cudaStream_t)stream, &tm)
@@ -569,17 +671,20 @@ extern "C" int xb_gemm_w8a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   while ((1 << p.gshift) < tpg) ++p.gshift;
   p.M = M; p.N = N; p.K = K;
   int bn = pick_block_n(M, N);
-  if (bn == 256) bn = 128;                  // 256 rows of int8 + the bf16 ring leave too few TMA stages
+  const bool pair = use_cta_pair(M, N, bn);   // a pair stages 2 x 128 rows of int8: the single-CTA 256-row tile does not fit
+  if (bn == 256 && !pair) bn = 128;           // 256 rows of int8 + the bf16 ring leave too few TMA stages
   if (bn == 128 && N % 128 != 0) bn = 64;
+  const int cta_n = pair ? bn / 2 : bn;
   CUtensorMap ta, tb, tm;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, kBlockM, 64, 2)) return 1;
   const uint64_t ktiles = K / 64;
-  if (make_tmap_2d_raw(&tb, qweight, CU_TENSOR_MAP_DATA_TYPE_UINT32, N / 16, ktiles * 256, ktiles * 1024, bn / 16, 256,
+  if (make_tmap_2d_raw(&tb, qweight, CU_TENSOR_MAP_DATA_TYPE_UINT32, N / 16, ktiles * 256, ktiles * 1024, cta_n / 16, 256,
                        CU_TENSOR_MAP_SWIZZLE_NONE))
     return 1;
-  if (make_tmap_2d_raw(&tm, meta, CU_TENSOR_MAP_DATA_TYPE_UINT32, K / group_size, N, (uint64_t)N * 4, 1, bn,
+  if (make_tmap_2d_raw(&tm, meta, CU_TENSOR_MAP_DATA_TYPE_UINT32, K / group_size, N, (uint64_t)N * 4, 1, cta_n,
                        CU_TENSOR_MAP_SWIZZLE_NONE))
     return 1;
+  if (pair) return launch_gemm<kKindW8, 256, 1, 2>(ta, tb, p, (cudaStream_t)stream, &tm);
   return bn == 128 ? launch_gemm<kKindW8, 128>(ta, tb, p, (cudaStream_t)stream, &tm)
                    : launch_gemm<kKindW8, 64>(ta, tb, p, (cudaStream_t)stream, &tm);
 }

@@ -33,15 +33,28 @@ argmax_kernel(int32_t* __restrict__ out, const __nv_bfloat16* __restrict__ logit
   int besti = 0x7fffffff;
   const int nvec = vocab / 8;
   const uint4* rv = reinterpret_cast<const uint4*>(row);
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-    uint4 v = rv[i];
-    const uint32_t* p = &v.x;
+  // one CTA per row: batches of 8 independent 16-byte loads per thread (the row is read in 3 round trips for a 152 K
+  // vocabulary instead of 19 dependent ones)
+  constexpr int kBatch = 8;
+  for (int i0 = threadIdx.x; i0 < nvec; i0 += blockDim.x * kBatch) {
+    uint4 v[kBatch];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = bf16lo(p[j]), b = bf16hi(p[j]);
-      int ia = i * 8 + 2 * j, ib = ia + 1;
-      if (a > best || (a == best && ia < besti)) { best = a; besti = ia; }
-      if (b > best || (b == best && ib < besti)) { best = b; besti = ib; }
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * blockDim.x;
+      v[u] = i < nvec ? __ldcs(rv + i) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i >= nvec) continue;
+      const uint32_t* p = &v[u].x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = bf16lo(p[j]), b = bf16hi(p[j]);
+        int ia = i * 8 + 2 * j, ib = ia + 1;
+        if (a > best || (a == best && ia < besti)) { best = a; besti = ia; }
+        if (b > best || (b == best && ib < besti)) { best = b; besti = ib; }
+      }
     }
   }
   for (int i = nvec * 8 + threadIdx.x; i < vocab; i += blockDim.x) {

@@ -298,6 +298,12 @@ def matmul(a, b, bias=None, out=None):
     return y
 
 
+def set_gemm_cta_pair(mode: int) -> int:
+    """kernel selection of the tcgen05 GEMMs: 0 auto | 1 single-CTA | 2 CTA pairs (cta_group::2) when >= 74 pair tiles |
+    3 CTA pairs whenever M > 128 and N % 256 == 0.  Returns the previous mode."""
+    return int(lib().xb_set_gemm_cta_pair(c_i32(mode)))
+
+
 def gemm_bf16(a, b, bias=None, out=None):
     """always the tcgen05 kernel (tests / benchmarks)."""
     _cuda_bf16(a, "a"); _cuda_bf16(b, "b")

@@ -227,11 +227,14 @@ class Qwen2DecodeRunner:
 
     def __init__(self, cfg: Qwen2Config, weights: Qwen2Weights, max_batch: int, max_ctx: int, device="cuda",
                  num_blocks: Optional[int] = None, fused_rope_cache: bool = True, pg=None, exchange: str = "peer",
-                 fuse_gemv: bool = True):
+                 fuse_gemv: bool = False):
         """pg: xllm_b200.parallel.ProcessGroup for tensor parallelism (weights must already be this rank's shards);
         exchange: "peer" = NVLink one-shot all-reduce fused with add+RMSNorm, "nccl" = c10d all-reduce (baseline);
-        fuse_gemv: W4A16 decode with batch <= 8 folds add+RMSNorm into the prologue of the qkv / gate_up GEMVs and
-        RoPE + KV scatter into the qkv epilogue (5 launches per layer instead of 8)."""
+        fuse_gemv: W4A16 decode with batch <= 8 splits add+RMSNorm between the o / down epilogues and the qkv / gate_up
+        prologues (5 launches per layer instead of 7).  OFF by default: measured on B200 (profiles/r02a_*) the 145-launch
+        step runs at 1.90 ms against 1.74 ms for the 200-launch step whose small add+RMSNorm kernels overlap the next
+        GEMV's weight prefetch under PDL.  RoPE + KV scatter (qkv epilogue) and SiLU*mul (gate_up epilogue) ride in the
+        GEMVs either way."""
         self.cfg, self.w, self.B, self.device = cfg, weights, max_batch, device
         self.pg = pg if (pg is not None and pg.world_size > 1) else None
         self.tp = self.pg.world_size if self.pg else 1
