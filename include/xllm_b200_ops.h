@@ -249,6 +249,13 @@ int xb_linear_w4a16_decode_fused(void* y, int64_t y_stride, const void* x, int64
                                  int num_kv_heads, int head_dim, const float* norm_stats_in,
                                  float* norm_stats_out, xb_stream_t stream);
 int xb_linear_w4a16_decode_fused_fits(int M, int K);
+/* Arithmetic form of the W4A16 decode kernels (M <= 8; group_size 64 / 128), both defined in oracle/quant.py:
+ *   0  bf16-weight form: w = bf16((q - z) * s) per weight, then the bf16 linear (what the tcgen05 prefill GEMM computes)
+ *   1  exact-dequant form: y = bf16(sum_g s_g * sum_{k in g} x_k (q_k - z_g) + b), fp32 - the integer nibbles go to the
+ *      tensor core unscaled and scale / zero are applied once per (row, group); differs from form 0 only by the bf16
+ *      rounding of w that form 0 makes (<= 2^-9 relative per weight).
+ * Returns the previous form. */
+int xb_set_w4_decode_form(int form);
 
 /* ---- W8A16 weight-only linears (north-star "W4A16 / W8A16 / FP8"; additive boundary) -------------
  * spec oracle/quant.py with bits = 8: w = bf16((q - z) * s), y = bf16(sum_k f32(x) f32(w) + b).

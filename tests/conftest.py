@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "w4_exact: run with the exact-dequant form of the W4A16 decode kernels "
+                                       "(xb_set_w4_decode_form(1)); every other GPU test pins the bf16-weight form")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -27,6 +29,21 @@ def built_lib():
     """Make sure the C-ABI library exists (builds it with nvcc if not)."""
     from xllm_b200 import build
     return build.build()
+
+
+@pytest.fixture(autouse=True)
+def _pin_w4_decode_form(request):
+    """The W4A16 decode kernels have two arithmetic forms (oracle/quant.py).  Every GPU test states which one it checks:
+    the bf16-weight form unless marked `w4_exact` - independent of the library's default."""
+    import torch
+    if "gpu" not in request.keywords or not torch.cuda.is_available():
+        yield
+        return
+    from xllm_b200 import build, ops
+    build.build()
+    old = ops.set_w4_decode_form(1 if "w4_exact" in request.keywords else 0)
+    yield
+    ops.set_w4_decode_form(old)
 
 
 def pytest_sessionfinish(session, exitstatus):

@@ -83,10 +83,16 @@ def run(name, N, K, M=1, gs=128, heads=None):
         slots = torch.arange(M, dtype=torch.int32, device=DEV) + 128
         kc = torch.zeros(8, 128, nkv, D, device=DEV, dtype=BF16)
         vc = torch.zeros_like(kc)
+        variants += [("rope/cache epilogue", lambda i: ops.w4a16_decode_fused(x, ws[i][0], ws[i][1], gs, None, y, epilogue="rope_cache",
+                                                                              positions=pos, cos_sin_cache=cs, slot_ids=slots,
+                                                                              key_cache=kc, value_cache=vc, num_heads=nh,
+                                                                              num_kv_heads=nkv, head_dim=D))]
         variants += [("norm + rope/cache", lambda i: ops.w4a16_decode_fused(x, ws[i][0], ws[i][1], gs, None, y, norm_weight=nw, residual_in=res,
                                                                             residual_out=res_out, epilogue="rope_cache", positions=pos,
                                                                             cos_sin_cache=cs, slot_ids=slots, key_cache=kc, value_cache=vc,
                                                                             num_heads=nh, num_kv_heads=nkv, head_dim=D))]
+    if os.environ.get("XB_SWEEP_FEW"):          # A/B of the two arithmetic forms: only the variants the step launches
+        variants = [v for v in variants if v[0] in ("plain", "x staged", "act epilogue", "rope/cache epilogue")]
     for vn, fn in variants:
         fns = [lambda i=i: fn(i) for i in range(copies)]
         t_c, t_g = chained(fns), graph_time(fns)
@@ -148,6 +154,7 @@ if __name__ == "__main__":
             run_q8("gate_up", 37888, 3584, M)
         sys.exit(0)
     Ms = [int(a) for a in sys.argv[1:]] or [1]
+    print("W4 decode form:", "exact-dequant" if os.environ.get("XB_W4_EXACT", "0") not in ("0", "") else "bf16-weight (or library default)")
     for M in Ms:
         run("qkv", 4608, 3584, M, heads=(28, 4, 128))
         run("o", 3584, 3584, M)

@@ -47,6 +47,16 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint3
   return d;
 }
 
+// m16n8k16 with a zero accumulator input (opens a fresh accumulation chain without clearing registers)
+__device__ __forceinline__ void mma_bf16_16816_zero(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                    uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
+      "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+
 // x fragment for one k64 tile (4 k16 steps) and one n8 token tile:
 // lane (g,t) needs x[tok = tile*8+g][k0 + 16t .. +16) = 32 bytes.
 struct XFrag {
@@ -113,7 +123,8 @@ template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps 
           int kTG /* k64 tiles per ring slot: 2 when group_size >= 128, else 1 */, int kOcc = 2 /* CTAs per SM */,
           int kEpi = 0 /* 0: bias; 1: gate/up rows interleaved, act(gate)*up; 2: rope + KV scatter (qkv);
                           3: + residual -> residual stream and sum-of-squares partials (producer of a split RMSNorm) */,
-          bool kXs = false /* x staged (and optionally normalised) in shared memory by the prologue */>
+          bool kXs = false /* x staged (and optionally normalised) in shared memory by the prologue */,
+          bool kExact = false /* exact-dequant form: integer nibbles on the tensor core, scale / zero once per group */>
 __global__ void __launch_bounds__(kWarps * 32, kMT >= 8 ? 1 : kOcc)
 linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x,
                             int64_t x_stride, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
@@ -121,6 +132,12 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
                             int act_mode, const W4Fuse fz) {
   constexpr bool kGateUp = kEpi == 1;
   constexpr bool kPair = kEpi == 1 || kEpi == 2;    // rows g / g+8 of a tile form an output pair
+  // kExact ("exact" form of the spec, oracle/quant.py): y = sum_g s_g * ( sum_{k in g} x_k (128 + q_k) - (128 + z_g) X_g ),
+  // X_g = sum_{k in g} x_k.  The nibbles go to the tensor core as the exact bf16 integers 128 + q (LOP3 only: no HSUB2 /
+  // HMUL2 per weight pair), X_g is formed ONCE per CTA while x is staged in shared memory (it is the same for every
+  // row), and scale / zero are applied in fp32 once per (row, group): ~50 instead of 83 warp instructions per 512-byte
+  // tile.  Serves one token tile with a ring slot = one quantisation group (group_size 64 / 128).
+  static_assert(!kExact || (kMT == 1 && kXs), "the exact-dequant form stages x (and the group sums) in shared memory");
   static_assert(kEpi != 3 || (kSplit > 1 && kMT == 1), "the residual + statistics epilogue lives in the k-split reduction");
   constexpr int kTilesPerCta = kWarps / kSplit;
   __shared__ float red[kSplit > 1 ? kWarps : 1][kMT][16 * 8];
@@ -184,6 +201,8 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   // of slack after the last row: the one-tile-ahead fragment prefetch may read past a warp's k range
   const int xs_stride = K + 8;
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ring_smem + kWarps * kDepth * kSlotBytes);
+  // kExact: X_g per (group, token) as [K / group][8] fp32 behind the x stage (16-byte aligned: rows are K + 8 bf16)
+  float* gsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + (((size_t)M * (K + 8) * 2 + 256 + 15) & ~size_t(15)));
   if constexpr (kXs) {
     const int nvec = K >> 3;
     const bool do_norm = fz.norm_w != nullptr;
@@ -234,6 +253,25 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
       uint4* rdst = (kEpi != 3 && fz.res_out && blockIdx.x == 0) ? reinterpret_cast<uint4*>(fz.res_out + (int64_t)tok * K) : nullptr;
       uint4* dst = reinterpret_cast<uint4*>(xs + (int64_t)tok * xs_stride);
       float ss = 0.f;
+      if constexpr (kExact) {
+        // stage x and form the group sums X_g: a group is kTG * 8 consecutive 16-byte vectors = consecutive lanes
+        constexpr int kVecPerGroup = kTG * 8;
+        for (int base = 0; base < nvec; base += kWarps * 32) {     // warp-uniform trip count (full-warp shuffles)
+          const int idx = base + threadIdx.x;
+          float part = 0.f;
+          if (idx < nvec) {
+            const uint4 v = src[idx];
+            const uint32_t* vp = &v.x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) part += bf16lo(vp[j]) + bf16hi(vp[j]);
+            dst[idx] = v;
+          }
+#pragma unroll
+          for (int o = kVecPerGroup / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if (idx < nvec && (lane & (kVecPerGroup - 1)) == 0) gsum[(idx / kVecPerGroup) * 8 + tok] = part;
+        }
+        continue;
+      }
       for (int idx = threadIdx.x; idx < nvec; idx += kWarps * 32) {
         uint4 v = src[idx];
         if (rsrc) {
@@ -348,6 +386,46 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
     }
   };
 
+  // kExact: one ring slot = one quantisation group.  Two accumulation chains per group (opened with a zero-C MMA), then
+  // yacc += s * (c - (128 + z) * X_g) in fp32; rows g / g+8 use meta words x / y, token columns 2t / 2t+1 use X_g[2t..].
+  float yacc[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t gsum_a = smem_addr_u32(gsum) + t * 8;
+  auto consume_exact = [&](int i, int slot_abs) {
+    uint4 wq[kTG];
+#pragma unroll
+    for (int u = 0; u < kTG; ++u) wq[u] = lds_128(ring_w + i * kSlotBytes + u * 512);
+    const uint2 mt = lds_64(ring_m + i * kSlotBytes);
+    float c0[4], c1[4];
+#pragma unroll
+    for (int u = 0; u < kTG; ++u) {
+      const int par = (i * kTG + u) & 1;
+      load_xtile(xbuf[par ^ 1]);
+      const XRing<kMT>& xf = xbuf[par];
+      const uint32_t* wv = &wq[u].x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w = wv[j];
+        const uint32_t q0 = lop3_and_or(w, 0x000f000fu, 0x43004300u);
+        const uint32_t q1 = lop3_and_or(w >> 4, 0x000f000fu, 0x43004300u);
+        const uint32_t q2 = lop3_and_or(w >> 8, 0x000f000fu, 0x43004300u);
+        const uint32_t q3 = lop3_and_or(w >> 12, 0x000f000fu, 0x43004300u);
+        const uint32_t* xv = j < 2 ? &xf.lo[0].x : &xf.hi[0].x;
+        const uint32_t b0 = xv[(j & 1) * 2], b1 = xv[(j & 1) * 2 + 1];
+        if (u == 0 && j == 0) mma_bf16_16816_zero(c0, q0, q1, q2, q3, b0, b1);
+        else if (u == 0 && j == 1) mma_bf16_16816_zero(c1, q0, q1, q2, q3, b0, b1);
+        else if (j & 1) mma_bf16_16816(c1, q0, q1, q2, q3, b0, b1);
+        else mma_bf16_16816(c0, q0, q1, q2, q3, b0, b1);
+      }
+    }
+    const uint2 sxb = lds_64(gsum_a + (uint32_t)slot_abs * 32u);
+    const float sx0 = __uint_as_float(sxb.x), sx1 = __uint_as_float(sxb.y);
+    const float s0 = bf16lo(mt.x), nz0 = -bf16hi(mt.x), s1 = bf16lo(mt.y), nz1 = -bf16hi(mt.y);   // scale, -(128 + zero)
+    yacc[0] = fmaf(s0, fmaf(nz0, sx0, c0[0] + c1[0]), yacc[0]);
+    yacc[1] = fmaf(s0, fmaf(nz0, sx1, c0[1] + c1[1]), yacc[1]);
+    yacc[2] = fmaf(s1, fmaf(nz1, sx0, c0[2] + c1[2]), yacc[2]);
+    yacc[3] = fmaf(s1, fmaf(nz1, sx1, c0[3] + c1[3]), yacc[3]);
+  };
+
   // Meta words: when a ring slot is exactly one quantisation group (group 128 with kTG 2, group 64 with kTG 1) the
   // row pointer just advances by N per slot; otherwise it is recomputed from the slot index.
   const bool slot_is_group = (1 << gshift) == kTG;
@@ -360,7 +438,8 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
 #pragma unroll
     for (int i = 0; i < kDepth; ++i) {
       cp_async_wait<kDepth - 1>();
-      consume(i);
+      if constexpr (kExact) consume_exact(i, sl + i);
+      else consume(i);
       if (sl + i + kDepth < s_end)
         issue(i, wp, slot_is_group ? mp : mbase + (int64_t)(((sl + i + kDepth) * kTG) >> gshift) * N);
       cp_async_commit();
@@ -372,7 +451,10 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   cp_async_wait<0>();
 #pragma unroll
   for (int i = 0; i < kDepth; ++i) {
-    if (sl + i < s_end) consume(i);
+    if (sl + i < s_end) {
+      if constexpr (kExact) consume_exact(i, sl + i);
+      else consume(i);
+    }
   }
   pdl_launch_dependents();
   float acc[kMT][4];
@@ -383,7 +465,7 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
       float v = accj[0][m][i];
 #pragma unroll
       for (int a = 1; a < kAcc; ++a) v += accj[a][m][i];
-      acc[m][i] = v;
+      acc[m][i] = kExact ? yacc[i] : v;
     }
 
   // c0:(row g, tok 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
@@ -601,12 +683,34 @@ static constexpr size_t w4_ring_bytes(int depth, int tg) { return (size_t)kWarps
 // largest activation block ([M][K + 8] bf16 + slack) the kXs variants stage in shared memory next to the ring
 static constexpr size_t kXsMaxBytes = 72 * 1024;
 static inline size_t w4_xs_bytes(int M, int K) { return (size_t)M * (K + 8) * 2 + 256; }
+// exact-dequant form: the group sums X_g [K / group][8] fp32 live behind the x stage
+static inline size_t w4_gsum_bytes(int K, int group_size) { return (size_t)(K / group_size) * 32 + 16; }
+// 0: bf16-weight form (w = bf16((q - z) s), the prefill GEMM's form); 1: exact-dequant form for M <= 8, group 64 / 128
+static std::atomic<int> g_w4_decode_form{-1};
+static int w4_decode_form() {
+  int f = g_w4_decode_form.load(std::memory_order_relaxed);
+  if (f < 0) {
+    const char* e = getenv("XB_W4_EXACT");
+    f = e ? (atoi(e) != 0) : 0;     // TODO(default): flip once the B200 A/B run confirms parity and speed
+    g_w4_decode_form.store(f, std::memory_order_relaxed);
+  }
+  return f;
+}
+extern "C" int xb_set_w4_decode_form(int form) {
+  if (form < 0 || form > 1) {
+    set_error("set_w4_decode_form: form %d (0 bf16-weight | 1 exact-dequant)", form);
+    return -1;
+  }
+  const int old = w4_decode_form();
+  g_w4_decode_form.store(form, std::memory_order_relaxed);
+  return old;
+}
 
 // epi: 0 plain (+bias), 1 gate/up + activation (act_mode), 2 qkv rope + KV scatter (fz).  xs: stage x in shared memory
 // (required for the norm prologue).  fz may be null when neither the prologue nor epilogue 2 is used.
 static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_stride, const uint32_t* qweight,
                            const uint32_t* meta, const void* bias, int M, int N, int K, int group_size, int epi,
-                           int act_mode, bool xs, const W4Fuse* fzp, xb_stream_t stream) {
+                           int act_mode, bool xs, const W4Fuse* fzp, xb_stream_t stream) {  // (xs is forced on by the exact form)
   if (M == 0) return 0;
   XB_CHECK(M > 0 && M <= 64, "linear_w4a16_small_m: M=%d out of range (1..64); use the tcgen05 GEMM", M);
   XB_CHECK(N % 16 == 0 && K % 64 == 0, "linear_w4a16_small_m: N=%d must be %%16, K=%d %%64", N, K);
@@ -632,11 +736,15 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   int gshift = 0;
   while ((1 << gshift) < tpg) ++gshift;
   const bool tg2 = tpg >= 2;
-  const size_t xs_bytes = xs ? w4_xs_bytes(M, K) : 0;
+  // exact-dequant form: one token tile, ring slot = one group, no norm prologue, x + group sums fit the shared-memory stage
+  const bool exact = w4_decode_form() == 1 && M <= 8 && (tpg == 1 || tpg == 2) && fz.norm_w == nullptr &&
+                     w4_xs_bytes(M, K) + w4_gsum_bytes(K, group_size) <= kXsMaxBytes;
+  if (exact) xs = true;
+  const size_t xs_bytes = (xs ? w4_xs_bytes(M, K) : 0) + (exact ? w4_gsum_bytes(K, group_size) : 0);
   // (tuning note, B200: 3 CTAs/SM at <= 80 registers measured 10-13 % slower than 2 CTAs/SM for every decode shape)
-#define XB_W4_GO(MT, SP, DEPTH, TG, EPI, XS)                                                                       \
+#define XB_W4_GO(MT, SP, DEPTH, TG, EPI, XS, EX)                                                                   \
   {                                                                                                                 \
-    auto kern = linear_w4a16_small_m_kernel<MT, SP, DEPTH, TG, 2, EPI, XS>;                                         \
+    auto kern = linear_w4a16_small_m_kernel<MT, SP, DEPTH, TG, 2, EPI, XS, EX>;                                     \
     static bool attr_done = false; /* per instantiation: static reduction scratch + ring may exceed 48 KB */        \
     if (!attr_done) {                                                                                               \
       XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
@@ -646,15 +754,24 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
     XB_CUDA_OK(launch(kern, grid, block, w4_ring_bytes(DEPTH, TG) + xs_bytes, s, true, yy, y_stride, xx, x_stride,  \
                       qw, meta, bb, M, N, K, gshift, act_mode, fz));                                                \
   }
-#define XB_W4_TG(MT, SP, DP, EPI, XS)                                \
-  if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS) }            \
-  else { XB_W4_GO(MT, SP, DP, 1, EPI, XS) }
+#define XB_W4_TG(MT, SP, DP, EPI, XS)                                       \
+  if (tg2) { XB_W4_GO(MT, SP, (DP + 1) / 2, 2, EPI, XS, false) }            \
+  else { XB_W4_GO(MT, SP, DP, 1, EPI, XS, false) }
+#define XB_W4_EX(SP, DP, EPI)                                               \
+  if (tg2) { XB_W4_GO(1, SP, (DP + 1) / 2, 2, EPI, true, true) }            \
+  else { XB_W4_GO(1, SP, DP, 1, EPI, true, true) }
   // the fused variants (x staged in shared memory / rope epilogue) exist for one token tile (M <= 8) only
 #define XB_W4_LAUNCH(MT, SP, DP)                                                                               \
   {                                                                                                            \
     dim3 grid((ntiles + (kWarps / SP) - 1) / (kWarps / SP)), block(kWarps * 32);                               \
     if constexpr (MT == 1) {                                                                                   \
-      if (epi == 3) {                                                                                          \
+      if (exact) {                                                                                             \
+        if (epi == 3) {                                                                                        \
+          if constexpr (SP > 1) { XB_W4_EX(SP, DP, 3) }                                                        \
+        } else if (epi == 2) { XB_W4_EX(SP, DP, 2) }                                                           \
+        else if (epi == 1) { XB_W4_EX(SP, DP, 1) }                                                             \
+        else { XB_W4_EX(SP, DP, 0) }                                                                           \
+      } else if (epi == 3) {                                                                                   \
         if constexpr (SP > 1) {                                                                                \
           if (xs) { XB_W4_TG(1, SP, DP, 3, true) }                                                             \
           else { XB_W4_TG(1, SP, DP, 3, false) }                                                               \
@@ -688,6 +805,7 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   else { XB_W4(8, 8) }
 #undef XB_W4_GO
 #undef XB_W4_TG
+#undef XB_W4_EX
 #undef XB_W4_LAUNCH
 #undef XB_W4
   return 0;

@@ -469,6 +469,11 @@ def w4a16_gate_up_act(x, qweight, meta, group_size, act_mode="silu", bias=None, 
     return y
 
 
+def set_w4_decode_form(form: int) -> int:
+    """0: bf16-weight form, 1: exact-dequant form (oracle/quant.py) of the W4A16 decode kernels; returns the old form."""
+    return int(lib().xb_set_w4_decode_form(c_i32(form)))
+
+
 def w4a16_decode_fused_fits(M: int, K: int) -> bool:
     """whether w4a16_decode_fused can stage an [M, K] activation block in shared memory."""
     return bool(lib().xb_linear_w4a16_decode_fused_fits(c_i32(M), c_i32(K)))
