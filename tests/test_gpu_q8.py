@@ -147,3 +147,23 @@ def test_fp8_small_m_exact_products(built_lib):
     ops.fp8_scaled_mm_small_m(c, a.to(DEV), b.to(DEV).t(), one, one * 0.5, None)
     ref = (a.float() @ b.float().t() * 0.5).to(BF16)
     assert torch.equal(c.cpu(), ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (300, 512, 256), (1024, 3584, 3584)])
+def test_gemm_w8a16_cta_pair(M, N, K, built_lib):
+    """the CTA-pair (tcgen05 cta_group::2) kind-W8 kernel: each CTA of the pair converts 128 of the 256 B rows."""
+    from xllm_b200 import ops, quant
+    old = ops.set_gemm_cta_pair(3)
+    try:
+        gs = 128
+        g = torch.Generator().manual_seed(2026)
+        w = (torch.randn(N, K, generator=g) * 0.02).to(BF16)
+        q, s, z = Q.quantize(w, 8, gs)
+        x = torch.randn(M, K, generator=g).to(BF16)
+        qw, meta = quant.pack_w8(q, s, z, gs)
+        y = ops.gemm_w8a16(x.to(DEV), qw.to(DEV), meta.to(DEV), gs)
+        wd = Q.dequantize(q, s, z, gs)
+        ref = Q.linear_wna16(x, q, s, z, gs, None)
+        assert_close_sum(y, ref, _abs_scale(x, wd, None), rtol=1e-5, what=f"gemm_w8a16 pair {M}x{N}x{K}")
+    finally:
+        ops.set_gemm_cta_pair(old)

@@ -39,9 +39,11 @@ def test_linear_w4a16_exact_form(M, N, K, sym, built_lib):
     # (a) the form's own oracle.  The kernel forms sum x (128 + q) and (128 + z) sum x separately in fp32 (terms ~30x the
     # size of x (q - z)), so its summation noise is that much larger than a plain fp32 dot product: 3e-5 of sum |x||w|
     assert_close_sum(y, Q.linear_wna16(x, q, s, z, gs, b, form="exact"), scale, rtol=3e-5, what=f"w4 exact M={M} N={N} K={K}")
-    # (b) the other form: every weight rounded to bf16 first (<= 2^-9 relative per product)
+    # (b) the other form: every weight rounded to bf16 first (<= 2^-9 relative per product).  Expected relative L2
+    # distance: the rounding of w (RMS 1.66e-3 of every product, tests/util.py) and the two independent bf16 roundings of
+    # the outputs (1.1e-3 each) -> sqrt(1.66^2 + 2 * 1.1^2) e-3 = 2.3e-3 (measured 2.0-2.4e-3)
     ref_b = Q.linear_wna16(x, q, s, z, gs, b)
-    assert_close_sum(y, ref_b, scale, rtol=2.0 ** -9, rel_l2=2e-3, what="exact form vs bf16-weight form")
+    assert_close_sum(y, ref_b, scale, rtol=2.0 ** -9, rel_l2=3e-3, what="exact form vs bf16-weight form")
 
 
 def test_exact_form_is_selected_and_differs(built_lib):

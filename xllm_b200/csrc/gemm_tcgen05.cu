@@ -115,7 +115,10 @@ struct GemmCfg {
   // 2-deep ring written by the converter warps.
   static constexpr int kStageBytes = kind_is_wq(kKind) ? kABytes + kPackedBytes + ((kMetaBytes + 1023) / 1024) * 1024
                                                       : kABytes + kBBytes;
-  static constexpr int kBStages = kind_is_wq(kKind) ? 2 : 0;
+  // dequantised-B ring depth.  CTA pairs: the converters <-> MMA hand-off crosses SMs (multicast commit one way, remote
+  // mbarrier arrive the other: a few hundred cycles each), so the converters must run further ahead of the MMA
+  static constexpr int kBStages = kind_is_wq(kKind) ? (kCG == 2 ? 4 : 2) : 0;
+  static constexpr int kBRing = kBStages > 0 ? kBStages : 2;        // barriers of the ring (two dummies when unused)
   static constexpr int kConvWarps = kind_is_wq(kKind) ? 8 : 0;      // two converter warps per SM sub-partition
   static constexpr int kEpiStageBytes = kNumEpiWarps * 2 * 4096;   // per epilogue warp: 2 x [32 rows x 64 cols] bf16
   static constexpr int kBudget = 227 * 1024 - 1024 - 512 - kEpiStageBytes - kBStages * kBBytes;
@@ -143,9 +146,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_mem);          // [kStages] TMA -> MMA (A, and B for BF16/FP8)
   uint64_t* empty_bar = full_bar + kStages;                           // [kStages] MMA -> TMA
   uint64_t* packed_bar = empty_bar + kStages;                         // [kStages] TMA -> converters (W4)
-  uint64_t* bready_bar = packed_bar + kStages;                        // [2] converters -> MMA (W4 B ring)
-  uint64_t* bempty_bar = bready_bar + 2;                              // [2] MMA -> converters
-  uint64_t* tmem_full = bempty_bar + 2;                               // [2]
+  uint64_t* bready_bar = packed_bar + kStages;                        // [kBRing] converters -> MMA (W4 B ring)
+  uint64_t* bempty_bar = bready_bar + Cfg::kBRing;                    // [kBRing] MMA -> converters
+  uint64_t* tmem_full = bempty_bar + Cfg::kBRing;                     // [2]
   uint64_t* tmem_empty = tmem_full + 2;                               // [2]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -172,7 +175,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(empty_bar + s, 1);
       mbar_init(packed_bar + s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < Cfg::kBRing; ++s) {
       mbar_init(bready_bar + s, Cfg::kConvWarps > 0 ? Cfg::kConvWarps * kCG : 1);   // one elected arrive per converter warp (of both CTAs)
       mbar_init(bempty_bar + s, 1);
     }
@@ -294,7 +297,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1; }
-        if (kind_is_wq(kKind) && ++bs == 2) { bs = 0; bph ^= 1; }
+        if (kind_is_wq(kKind) && ++bs == Cfg::kBRing) { bs = 0; bph ^= 1; }
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
@@ -458,7 +461,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           else mbar_arrive(bready_bar + bs);
         }
         if (++s == kStages) { s = 0; ph ^= 1; }
-        if (++bs == 2) { bs = 0; bph ^= 1; }
+        if (++bs == Cfg::kBRing) { bs = 0; bph ^= 1; }
       }
     }
   }
@@ -534,14 +537,17 @@ static int pick_block_n(int M, int N) {
 // drops by a third (bf16 / fp8) and the converter work per flop halves (W4 / W8).  Needs enough 256-row tiles to fill
 // the 74 pairs.  Mode: xb_set_gemm_cta_pair() / XB_GEMM_CG.
 static std::atomic<int> g_cta_pair_mode{-1};   // -1: not set -> XB_GEMM_CG, else 0 (auto)
-static bool use_cta_pair(int M, int N, int bn) {
+static bool use_cta_pair(int M, int N, int bn, bool weight_only = false) {
   int mode = g_cta_pair_mode.load(std::memory_order_relaxed);
   if (mode < 0) {
     const char* e = getenv("XB_GEMM_CG");
     mode = e ? atoi(e) : 0;
     g_cta_pair_mode.store(mode, std::memory_order_relaxed);
   }
-  if (mode == 0) mode = 1;                         // TODO(default): flip to 2 once the B200 A/B run confirms parity and speed
+  // automatic: measured on B200 at M = 8192 (tools/gemm_sweep.py, profiles/r02b_gemm_sweep.md) pairs are +7..15 % for
+  // bf16 (1.34-1.47 PF/s) and +7..10 % for fp8 (2.57-2.77 PF/s); the weight-only kinds stay single-CTA until their
+  // pair variant (deeper dequantised-B ring) is measured
+  if (mode == 0) mode = weight_only ? 1 : 2;
   if (mode == 1 || bn != 256 || N % 256 != 0) return false;
   const int64_t units = (int64_t)((M + 255) / 256) * (N / 256);
   if (mode == 3) return M > 128;                   // every shape that can form a pair tile (tests)
@@ -633,7 +639,7 @@ extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   static const int force_mt = [] { const char* e = getenv("XB_GEMM_W4_MT"); return e ? atoi(e) : 0; }();
   const bool two_m = force_mt == 2 && M >= 256 && N % 128 == 0;
   if (two_m) bn = 128;
-  const bool pair = !two_m && use_cta_pair(M, N, bn);
+  const bool pair = !two_m && use_cta_pair(M, N, bn, true);
   const int cta_n = pair ? bn / 2 : bn;      // B rows one CTA stages and dequantises
   CUtensorMap ta, tb, tm;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, two_m ? 256 : kBlockM, 64, 2)) return 1;
@@ -671,7 +677,7 @@ extern "C" int xb_gemm_w8a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   while ((1 << p.gshift) < tpg) ++p.gshift;
   p.M = M; p.N = N; p.K = K;
   int bn = pick_block_n(M, N);
-  const bool pair = use_cta_pair(M, N, bn);   // a pair stages 2 x 128 rows of int8: the single-CTA 256-row tile does not fit
+  const bool pair = use_cta_pair(M, N, bn, true);   // a pair stages 2 x 128 rows of int8: the single-CTA 256-row tile does not fit
   if (bn == 256 && !pair) bn = 128;           // 256 rows of int8 + the bf16 ring leave too few TMA stages
   if (bn == 128 && N % 128 != 0) bn = 64;
   const int cta_n = pair ? bn / 2 : bn;

@@ -117,6 +117,9 @@ struct W4Fuse {
   __nv_bfloat16* k_cache;
   __nv_bfloat16* v_cache;
   int num_heads, num_kv_heads, head_dim;
+  // 1: griddepcontrol.launch_dependents at kernel START (the next kernel's CTAs take SM slots as this kernel's CTAs
+  // retire and fill their weight rings during this kernel's tail) instead of after the main loop
+  int early_trigger;
 };
 
 template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth,
@@ -145,6 +148,7 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   __shared__ float s_sq[kEpi == 3 ? kTilesPerCta : 1][16][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  if (fz.early_trigger) pdl_launch_dependents();
   const int ntiles = N >> 4;
   const int ntile = blockIdx.x * kTilesPerCta + warp / kSplit;
   const int split = warp % kSplit;
@@ -691,7 +695,8 @@ static int w4_decode_form() {
   int f = g_w4_decode_form.load(std::memory_order_relaxed);
   if (f < 0) {
     const char* e = getenv("XB_W4_EXACT");
-    f = e ? (atoi(e) != 0) : 0;     // TODO(default): flip once the B200 A/B run confirms parity and speed
+    f = e ? atoi(e) : 0;            // 2 (experiment): exact form only for the big shapes (N * K >= 2^25: gate_up, down)
+    if (f < 0 || f > 2) f = 0;
     g_w4_decode_form.store(f, std::memory_order_relaxed);
   }
   return f;
@@ -721,6 +726,8 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   XB_CHECK(!xs || w4_xs_bytes(M, K) <= kXsMaxBytes, "linear_w4a16_small_m: M=%d x K=%d does not fit the shared-memory x stage", M, K);
   W4Fuse fz{};
   if (fzp) fz = *fzp;
+  static const int early = [] { const char* e = getenv("XB_PDL_EARLY"); return e ? atoi(e) : 0; }();
+  fz.early_trigger = early;
   auto* yy = reinterpret_cast<__nv_bfloat16*>(y);
   auto* xx = reinterpret_cast<const __nv_bfloat16*>(x);
   auto* qw = reinterpret_cast<const uint4*>(qweight);
@@ -737,7 +744,8 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   while ((1 << gshift) < tpg) ++gshift;
   const bool tg2 = tpg >= 2;
   // exact-dequant form: one token tile, ring slot = one group, no norm prologue, x + group sums fit the shared-memory stage
-  const bool exact = w4_decode_form() == 1 && M <= 8 && (tpg == 1 || tpg == 2) && fz.norm_w == nullptr &&
+  const int form = w4_decode_form();
+  const bool exact = (form == 1 || (form == 2 && (int64_t)N * K >= (1ll << 25))) && M <= 8 && (tpg == 1 || tpg == 2) && fz.norm_w == nullptr &&
                      w4_xs_bytes(M, K) + w4_gsum_bytes(K, group_size) <= kXsMaxBytes;
   if (exact) xs = true;
   const size_t xs_bytes = (xs ? w4_xs_bytes(M, K) : 0) + (exact ? w4_gsum_bytes(K, group_size) : 0);

@@ -53,7 +53,7 @@ struct DecodeParams {
   float scale_log2;
   float* part_o;    // [batch, num_qo_heads, max_parts, D]
   float* part_lse;  // [batch, num_qo_heads, max_parts]
-  int32_t* counters;  // [batch, num_kv_heads * head_tiles]
+  int32_t* counters;  // [batch, num_kv_heads * head_tiles][2]: word 0 = self-resetting arrival counter (word 1 unused)
   int num_qo_heads, num_kv_heads, group, head_tiles;
   int page_size, page_shift;  // page_shift >= 0 when page_size is a power of two
   int min_chunk;              // smallest KV chunk a split may get (multiple of 16)
@@ -442,24 +442,28 @@ paged_decode_kernel(const DecodeParams p) {
   // CTAs a spinner waits for are resident or ahead of every spinner in the dispatch queue (the assumption CUB's
   // decoupled look-back makes).
   __syncthreads();
-  int32_t* counter = p.counters + 2 * ((int64_t)b * gridDim.y + blockIdx.y);   // [0] arrivals, [1] team members done
+  // One arrival counter per unit, SELF-RESETTING: atomicInc wraps to 0 on the n_arrive-th arrival, so the launch leaves
+  // the workspace as it found it without a second atomic on the completion path.  A waiting member sees "everyone has
+  // arrived" as "the counter is no longer above my own ticket" (before the wrap it is always >= ticket + 1; the next
+  // launch cannot touch it before this grid has completed).
+  uint32_t* counter = reinterpret_cast<uint32_t*>(p.counters) + 2 * ((int64_t)b * gridDim.y + blockIdx.y);
+  const int n_arrive = n_parts * C;
   if (threadIdx.x == 0) {
     __threadfence();       // one fence after the CTA barrier publishes every thread's partials (cumulativity)
-    s_ticket = atomicAdd(counter, 1);
+    s_ticket = (int)atomicInc(counter, (uint32_t)(n_arrive - 1));
   }
   __syncthreads();
-  const int n_arrive = n_parts * C;
   const int team = min(kTeam, (n_arrive + 1) >> 1);
   const int member = s_ticket - (n_arrive - team);
   if (member < 0) {
     if (C > 1) cluster_wait_acquire();
     return;
   }
-  if (threadIdx.x == 0) {
-    int seen;
+  if (threadIdx.x == 0 && s_ticket != n_arrive - 1) {
+    uint32_t seen;
     do {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-    } while (seen < n_arrive);
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen > (uint32_t)s_ticket);
   }
   __syncthreads();
   stamp(5);
@@ -472,7 +476,6 @@ paged_decode_kernel(const DecodeParams p) {
     const int per = (live_items + team - 1) / team;
     const int first = member * per, lim = min(live_items, first + per);
     const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
-    constexpr int kMaxPer = 32;                      // partials per lane: max_parts (<= 2 * 128) / 8
     for (int base_it = first; base_it < lim; base_it += kWarpsT * 4) {
       const int it = base_it + grp;
       const bool ok = it < lim;
@@ -483,31 +486,34 @@ paged_decode_kernel(const DecodeParams p) {
       const float* lsrc = p.part_lse + slot0;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       float mx = -INFINITY, wsum = 0.f;
-      // pass over this lane's partials in batches of 4 (registers), keeping a running maximum like the main loop
-      for (int s0 = sub; s0 < n_splits_m; s0 += 32) {
-        float4 v[4];
-        float ls[4];
+      // pass over this lane's partials in batches of 8 (all loads of a batch in flight together: up to 64 partials per
+      // item in ONE round trip to L2), keeping a running maximum like the main loop
+      constexpr int kB = 8;
+      for (int s0 = sub; s0 < n_splits_m; s0 += 8 * kB) {
+        float4 v[kB];
+        float ls[kB];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kB; ++u) {
           const int sidx = s0 + 8 * u;
           const bool live = ok && sidx < n_splits_m;
           ls[u] = live ? __ldcg(lsrc + sidx) : -INFINITY;
           v[u] = live ? __ldcg(src + (int64_t)sidx * (kD / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float m_new = fmaxf(fmaxf(fmaxf(ls[0], ls[1]), fmaxf(ls[2], ls[3])), mx);
+        float m_new = mx;
+#pragma unroll
+        for (int u = 0; u < kB; ++u) m_new = fmaxf(m_new, ls[u]);
         const float m_safe = m_new == -INFINITY ? 0.f : m_new;
         const float alpha = fast_exp2(mx - m_safe);          // 0 when mx was -inf
         acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
         wsum *= alpha;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kB; ++u) {
           const float w = fast_exp2(ls[u] - m_safe);          // 0 for absent / empty partials
           wsum += w;
           acc.x += v[u].x * w; acc.y += v[u].y * w; acc.z += v[u].z * w; acc.w += v[u].w * w;
         }
         mx = m_new;
       }
-      (void)kMaxPer;
       // combine the 8 lanes of the item (fixed xor order: deterministic)
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
@@ -536,15 +542,6 @@ paged_decode_kernel(const DecodeParams p) {
         *reinterpret_cast<uint2*>(p.o + (int64_t)b * p.o_stride_n + (int64_t)qh * p.o_stride_h + d4) = ob;
         if (p.lse && d4 == 0) p.lse[(int64_t)b * p.num_qo_heads + qh] = wsum > 0.f ? mx + log2f(wsum) : -INFINITY;
       }
-    }
-  }
-  // the member that finishes last restores both counters for the next launch
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int done = atomicAdd(counter + 1, 1);
-    if (done == team - 1) {
-      counter[0] = 0;
-      counter[1] = 0;
     }
   }
   stamp(6);
