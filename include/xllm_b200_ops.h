@@ -327,6 +327,9 @@ int xb_prefill_paged_split_bf16(const void* q, int64_t q_stride_n, int64_t q_str
 int64_t xb_prefill_split_workspace_bytes(int kv_splits, int64_t total_q, int num_qo_heads, int head_dim);
 int xb_prefill_plan_splits(int batch, int max_qo_len, int64_t max_kv_len, int num_qo_heads,
                            int num_kv_heads, int num_sms);
+/* Kernel variant of the prefill attention entry points (kv_splits == 1): 0 = one q tile per CTA, 1 = two q tiles per CTA
+ * with two softmax warpgroups ping-ponging on the tensor core.  Same arithmetic ladder; returns the old variant. */
+int xb_set_prefill_variant(int variant);
 
 /* ---- tcgen05 GEMMs for prefill-sized M (any M; TMA zero-fills ragged edges) ---------------------
  * C[M,N] = A[M,K] . B[N,K]^T (+ bias), fp32 accumulation in TMEM, bf16 output.

@@ -78,7 +78,7 @@ def _w4(N, K, gs, seed, bias):
 @pytest.mark.parametrize("nh,nkv,D,K", [(28, 4, 128, 3584), (14, 2, 64, 896), (8, 1, 128, 8192)])
 @pytest.mark.parametrize("M", [1, 3, 8])
 @pytest.mark.parametrize("staged", [False, True])
-def test_fused_rope_epilogue_equals_gemv_then_rope(M, nh, nkv, D, K, staged, built_lib):
+def test_fused_rope_epilogue_equals_gemv_then_rope(M, nh, nkv, D, K, staged, built_lib, oracle_form="bf16w"):
     from xllm_b200 import ops, quant
     N = (nh + 2 * nkv) * D
     gs = 128 if K % 128 == 0 else 64
@@ -106,7 +106,7 @@ def test_fused_rope_epilogue_equals_gemv_then_rope(M, nh, nkv, D, K, staged, bui
     assert torch.equal(kc2, kc1) and torch.equal(vc2, vc1), "fused KV scatter differs"
     # and against the oracle end to end (linear on the logical rows -> RoPE), within the linear's 1-ulp noise:
     # a 1-ulp flip of one linear output moves a rotated value by at most that ulp (|cos|, |sin| <= 1)
-    y = Q.linear_wna16(x.cpu(), q, s, z, gs, b)
+    y = Q.linear_wna16(x.cpu(), q, s, z, gs, b, form=oracle_form)
     full, _, _ = _oracle_rope_cache(y, pos, slots, cs, kc, vc, nh, nkv, D)
     qs = nh * D
     mag = y.float().abs()

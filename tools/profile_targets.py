@@ -5,6 +5,8 @@ captures a warmed-up launch (see profiles/ for the summaries made from these cap
   python tools/profile_targets.py qkv         W4A16 qkv GEMV, split-norm prologue + RoPE / KV-scatter epilogue (4608 x 3584)
   python tools/profile_targets.py decode      paged decode attention, batch 1, ctx 4096, 28 / 4 heads of 128
   python tools/profile_targets.py decode64    paged decode attention, batch 64, ctx 4096
+  python tools/profile_targets.py gemm_w4 | gemm_w4_pair | gemm_bf16_pair   tcgen05 GEMM 8192 x 4608 x 3584 (single CTA / CTA pair)
+  python tools/profile_targets.py prefill | prefill_v2    causal ragged prefill attention, 4 x 2048 tokens, 28 / 4 heads of 128
 """
 import math
 import os
@@ -71,6 +73,29 @@ def main(which, reps=4):
         plan = ops.DecodePlan(B, HQ, HKV, D, page, npg, DEV)
         fn = lambda i: ops.batch_decode(plan, q, caches[i % len(caches)][0], caches[i % len(caches)][1], indptr, indices, last,
                                         1 / math.sqrt(D), out)
+    elif which in ("gemm_w4", "gemm_w4_pair", "gemm_bf16_pair"):
+        # prefill GEMM of the qkv projection at a chunk of 8192 tokens (kept small: ncu replays every launch ~40 times)
+        M, N, K = 8192, 4608, 3584
+        ops.set_gemm_cta_pair(2 if which.endswith("pair") else 1)
+        a = torch.randn(M, K, device=DEV, dtype=BF16)
+        y = torch.empty(M, N, device=DEV, dtype=BF16)
+        if which == "gemm_bf16_pair":
+            wt = torch.randn(N, K, device=DEV, dtype=BF16) * 0.02
+            fn = lambda i: ops.gemm_bf16(a, wt, None, y)
+        else:
+            qw, meta = w4(N, K)
+            fn = lambda i: ops.gemm_w4a16(a, qw, meta, 128, None, y)
+    elif which in ("prefill", "prefill_v2"):
+        ops.set_prefill_variant(1 if which == "prefill_v2" else 0)
+        HQ, HKV, D, S, nreq = 28, 4, 128, 2048, 4
+        T = S * nreq
+        qkv = torch.randn(T, (HQ + 2 * HKV) * D, device=DEV, dtype=BF16)
+        cu = torch.arange(0, T + 1, S, dtype=torch.int32, device=DEV)
+        o = torch.empty(T, HQ, D, device=DEV, dtype=BF16)
+        q = qkv[:, :HQ * D].view(T, HQ, D)
+        k = qkv[:, HQ * D:(HQ + HKV) * D].view(T, HKV, D)
+        v = qkv[:, (HQ + HKV) * D:].view(T, HKV, D)
+        fn = lambda i: ops.batch_prefill(q, k, v, cu, cu, 1 / math.sqrt(D), o, None, max_qo_len=S)
     else:
         raise SystemExit(__doc__)
     for i in range(reps):

@@ -257,16 +257,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int bs = 0;
     uint32_t bph = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
-      if (kPair) mbar_wait_cluster(tmem_empty + as, aph ^ 1);   // BOTH CTAs' epilogues have drained this accumulator stage
-      else mbar_wait(tmem_empty + as, aph ^ 1);     // epilogue has drained this accumulator stage
+      // (pairs: BOTH CTAs' epilogues have drained this accumulator stage.  The wait is the plain CTA-scope one even for
+      // barriers the peer arrives on remotely: the waiting thread reads nothing the peer wrote through the generic proxy -
+      // it only issues MMAs - and a cluster-scope acquire costs an L1 invalidation (CCTL.IVALL) per k block, which
+      // halved the W4 pair kernel: 600 vs 1020 TF/s, profiles/r02c_gemm_w4_pair.md)
+      mbar_wait(tmem_empty + as, aph ^ 1);     // epilogue has drained this accumulator stage
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + as * Cfg::kAccCols;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar + s, ph);
-        if (kind_is_wq(kKind)) {
-          if (kPair) mbar_wait_cluster(bready_bar + bs, bph);
-          else mbar_wait(bready_bar + bs, bph);
-        }
+        if (kind_is_wq(kKind)) mbar_wait(bready_bar + bs, bph);
         tc_fence_after_sync();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(stage_a(s));

@@ -117,9 +117,6 @@ struct W4Fuse {
   __nv_bfloat16* k_cache;
   __nv_bfloat16* v_cache;
   int num_heads, num_kv_heads, head_dim;
-  // 1: griddepcontrol.launch_dependents at kernel START (the next kernel's CTAs take SM slots as this kernel's CTAs
-  // retire and fill their weight rings during this kernel's tail) instead of after the main loop
-  int early_trigger;
 };
 
 template <int kMT /* n8 token tiles: M <= 8*kMT */, int kSplit /* 1,2,4,8 warps per row tile */, int kDepth,
@@ -148,7 +145,6 @@ linear_w4a16_small_m_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, con
   __shared__ float s_sq[kEpi == 3 ? kTilesPerCta : 1][16][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  if (fz.early_trigger) pdl_launch_dependents();
   const int ntiles = N >> 4;
   const int ntile = blockIdx.x * kTilesPerCta + warp / kSplit;
   const int split = warp % kSplit;
@@ -726,8 +722,6 @@ static int w4_small_m_impl(void* y, int64_t y_stride, const void* x, int64_t x_s
   XB_CHECK(!xs || w4_xs_bytes(M, K) <= kXsMaxBytes, "linear_w4a16_small_m: M=%d x K=%d does not fit the shared-memory x stage", M, K);
   W4Fuse fz{};
   if (fzp) fz = *fzp;
-  static const int early = [] { const char* e = getenv("XB_PDL_EARLY"); return e ? atoi(e) : 0; }();
-  fz.early_trigger = early;
   auto* yy = reinterpret_cast<__nv_bfloat16*>(y);
   auto* xx = reinterpret_cast<const __nv_bfloat16*>(x);
   auto* qw = reinterpret_cast<const uint4*>(qweight);

@@ -363,6 +363,367 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Ping-pong variant (kv_splits == 1): one CTA owns TWO adjacent q tiles (A, B) of a (request, kv head) and two softmax
+// warpgroups, so the tensor core always has the other tile's MMAs to run while one tile is in its softmax:
+//   tensor-core order per kv tile j:  PV_A(j)  QK_A(j+1)  PV_B(j)  QK_B(j+1)
+//   warpgroup A works on S_A(j) while PV_B(j-1) / QK_B(j) execute, warpgroup B on S_B(j) while PV_A(j) / QK_A(j+1) do.
+// Both tiles read the same K / V tiles (fetched once per pair).  The S accumulator of a tile is single-buffered (the
+// other tile is the second buffer); P goes through a per-tile swizzled smem tile; tcgen05.ld of the S row is software
+// pipelined against the exponentials of the previous 32 columns.
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2..5 softmax A | warps 6..9 softmax B  (TMEM lane quarter = warp % 4)
+// TMEM: S_A [0,128)  S_B [128,256)  O_A [256,256+d)  O_B [384,384+d).
+// smem (d = 128): Q_A Q_B 64 KB | K x2 64 KB | V x1 32 KB | P_A P_B 64 KB = 224 KB.
+template <int kD>
+struct Prefill2Cfg {
+  static constexpr int kHalves = kD / 64;
+  static constexpr int kSub = 128 * 128;
+  static constexpr int kQBytes = kHalves * kSub;
+  static constexpr int kKVBytes = kHalves * kSub;
+  static constexpr int kPBytes = 2 * kSub;
+  static constexpr int kVStages = kD == 128 ? 1 : 2;
+  static constexpr int kSmemBytes = 2 * kQBytes + (2 + kVStages) * kKVBytes + 2 * kPBytes + 1024 + 256;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kThreads = 320;
+};
+
+template <int kD>
+__global__ void __launch_bounds__(Prefill2Cfg<kD>::kThreads, 1)
+prefill_attention2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                          const __grid_constant__ CUtensorMap tmap_v, const PrefillParams p) {
+  using Cfg = Prefill2Cfg<kD>;
+  constexpr int kVS = Cfg::kVStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;                               // [2][kQBytes]   tile A, tile B
+  uint8_t* k_s = q_s + 2 * Cfg::kQBytes;             // [2][kKVBytes]
+  uint8_t* v_s = k_s + 2 * Cfg::kKVBytes;            // [kVS][kKVBytes]
+  uint8_t* p_s = v_s + kVS * Cfg::kKVBytes;          // [2][kPBytes]   tile A, tile B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * Cfg::kPBytes);
+  uint64_t* q_full = bars;            // [2] per tile
+  uint64_t* k_full = bars + 2;        // [2] per stage
+  uint64_t* k_empty = bars + 4;       // [2]
+  uint64_t* v_full = bars + 6;        // [2] per stage (kVS used)
+  uint64_t* v_empty = bars + 8;       // [2]
+  uint64_t* s_full = bars + 10;       // [2] per tile
+  uint64_t* p_full = bars + 12;       // [2] per tile
+  uint64_t* pv_done = bars + 14;      // [2] per tile
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, kvh = blockIdx.y;
+  const int pair = gridDim.x - 1 - blockIdx.x;        // heavy (late, causal) pairs first
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full + i, 1);
+      mbar_init(k_full + i, 1);
+      mbar_init(k_empty + i, 1);
+      mbar_init(v_full + i, 1);
+      mbar_init(v_empty + i, 1);
+      mbar_init(s_full + i, 1);
+      mbar_init(p_full + i, 4);
+      mbar_init(pv_done + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // ---- work item geometry (uniform across the CTA) ------------------------------------------------------------
+  const int q0 = __ldg(p.qo_indptr + b);
+  const int qo_len = __ldg(p.qo_indptr + b + 1) - q0;
+  int kv_len, kv_base = 0, indptr0 = 0, n_pages = 0;
+  if (p.paged) {
+    indptr0 = __ldg(p.kv_indptr + b);
+    n_pages = __ldg(p.kv_indptr + b + 1) - indptr0;
+    kv_len = n_pages > 0 ? (n_pages - 1) * p.page_size + __ldg(p.kv_last_page_len + b) : 0;
+  } else {
+    kv_base = __ldg(p.kv_indptr + b);
+    kv_len = __ldg(p.kv_indptr + b + 1) - kv_base;
+  }
+  const int kv_off = kv_len - qo_len;                  // causal offset of chunked prefill (prefill.cuh:1017 semantics)
+  const int rows_used = p.tokens_per_tile * p.group;
+  int tq0x[2], ntx[2];
+  bool livex[2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    tq0x[x] = (2 * pair + x) * p.tokens_per_tile;       // first q token of tile x (request-local)
+    livex[x] = tq0x[x] < qo_len;
+    const int tq_last = min(qo_len, tq0x[x] + p.tokens_per_tile) - 1;
+    int kv_limit = p.causal ? min(kv_len, tq_last + kv_off + 1) : kv_len;
+    if (kv_limit < 0) kv_limit = 0;
+    ntx[x] = livex[x] ? (kv_limit + kKT - 1) / kKT : 0;
+  }
+  const int n_max = max(ntx[0], ntx[1]);
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0 && n_max > 0) {
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (ntx[x] > 0) {
+          mbar_expect_tx(q_full + x, rows_used * kD * 2);
+#pragma unroll
+          for (int h = 0; h < Cfg::kHalves; ++h)
+            tma_load_3d(q_s + x * Cfg::kQBytes + h * Cfg::kSub, &tmap_q, q_full + x, h * 64, kvh * p.group, q0 + tq0x[x]);
+        }
+      }
+      const int loads = kKT / p.box_rows;
+      auto load_tile = [&](int j, int is_v) {
+        const int st = is_v ? (j % kVS) : (j & 1);
+        const int use = is_v ? (j / kVS) : (j >> 1);        // how many times this stage has been filled before
+        uint64_t* full = is_v ? v_full + st : k_full + st;
+        mbar_wait(is_v ? v_empty + st : k_empty + st, (use & 1) ^ 1);
+        mbar_expect_tx(full, kKT * kD * 2);
+        uint8_t* dst = (is_v ? v_s : k_s) + st * Cfg::kKVBytes;
+        const CUtensorMap* map = is_v ? &tmap_v : &tmap_k;
+        for (int i = 0; i < loads; ++i) {
+          const int t0 = j * kKT + i * p.box_rows;
+          int row;
+          if (p.paged) {
+            int pg = t0 / p.page_size;
+            if (pg >= n_pages) pg = n_pages - 1;    // beyond the request: masked anyway, keep the address valid
+            row = __ldg(p.kv_indices + indptr0 + pg) * p.page_size + (t0 % p.page_size);
+          } else {
+            row = kv_base + t0;
+          }
+#pragma unroll
+          for (int h = 0; h < Cfg::kHalves; ++h)
+            tma_load_2d(dst + h * Cfg::kSub + i * p.box_rows * 128, map, full, kvh * kD + h * 64, row);
+        }
+      };
+      load_tile(0, 0);
+      for (int j = 0; j < n_max; ++j) {
+        if (j + 1 < n_max) load_tile(j + 1, 0);     // K(j+1) is wanted right after PV_A(j)
+        load_tile(j, 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc_qk = umma_idesc(1, 1, kQT, kKT);
+    constexpr uint32_t idesc_pv = umma_idesc(1, 1, kQT, kD, 0, 1);     // B = V is MN-major
+    auto issue_qk = [&](int x, int j) {                 // S_x = Q_x K(j)^T
+      if (lane == 0) {
+        const uint32_t qa = smem_u32(q_s + x * Cfg::kQBytes), ka = smem_u32(k_s + (j & 1) * Cfg::kKVBytes);
+#pragma unroll
+        for (int s = 0; s < kD / 16; ++s) {
+          const uint32_t off = (s >> 2) * Cfg::kSub + (s & 3) * 32;
+          umma_f16(tmem_base + x * 128, umma_desc_sw128(qa + off), umma_desc_sw128(ka + off), idesc_qk, s != 0);
+        }
+        umma_commit(s_full + x);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int x, int j) {                 // O_x += P_x V(j)
+      if (lane == 0) {
+        const uint32_t pa = smem_u32(p_s + x * Cfg::kPBytes), va = smem_u32(v_s + (j % kVS) * Cfg::kKVBytes);
+#pragma unroll
+        for (int s = 0; s < kKT / 16; ++s) {
+          const uint64_t da = umma_desc_sw128(pa + (s >> 2) * Cfg::kSub + (s & 3) * 32);
+          const uint64_t db = umma_desc_sw128_mn(va + s * 2048, Cfg::kSub, 1024);
+          umma_f16(tmem_base + 256 + x * 128, da, db, idesc_pv, (j | s) != 0);
+        }
+        umma_commit(pv_done + x);
+      }
+      __syncwarp();
+    };
+    if (n_max > 0) {
+      mbar_wait(k_full + 0, 0);
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (ntx[x] > 0) {
+          mbar_wait(q_full + x, 0);
+          tc_fence_after_sync();
+          issue_qk(x, 0);
+        }
+      }
+      if (lane == 0) umma_commit(k_empty + 0);
+      __syncwarp();
+      for (int j = 0; j < n_max; ++j) {
+        const bool more = j + 1 < n_max;
+        mbar_wait(v_full + (j % kVS), (j / kVS) & 1);
+        bool k_ready = false;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          if (j < ntx[x]) {
+            mbar_wait(p_full + x, j & 1);               // P_x(j) written; S_x(j) fully read
+            tc_fence_after_sync();
+            issue_pv(x, j);
+          }
+          if (j + 1 < ntx[x]) {
+            if (!k_ready) {
+              mbar_wait(k_full + ((j + 1) & 1), ((j + 1) >> 1) & 1);
+              tc_fence_after_sync();
+              k_ready = true;
+            }
+            issue_qk(x, j + 1);
+          }
+        }
+        if (lane == 0) {
+          umma_commit(v_empty + (j % kVS));             // after the last PV that reads V(j)
+          if (more) umma_commit(k_empty + ((j + 1) & 1));   // after the last QK that reads K(j+1)
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================== softmax / correction / epilogue: warpgroup x owns tile x ==============================
+    const int x = (warp - 2) >> 2;                      // 0: tile A (warps 2..5), 1: tile B (warps 6..9)
+    const int qd = warp & 3;                            // TMEM lane quarter this warp may access
+    const int r = qd * 32 + lane;                       // my row of the tile = my TMEM lane
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const int tq0 = tq0x[x], n_tiles = ntx[x];
+    const bool live = livex[x];
+    const int tok_local = r / p.group, head_local = r - tok_local * p.group;
+    const int q_idx = tq0 + tok_local;
+    const bool row_valid = live && r < rows_used && q_idx < qo_len;
+    const int my_lim = p.causal ? min(kv_len, q_idx + kv_off + 1) : kv_len;       // #visible keys of my row
+    const int lim_first = p.causal ? min(kv_len, tq0 + kv_off + 1) : kv_len;      // smallest limit in the tile
+    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t s_tmem = tmem_base + x * 128 + lane_addr;
+    const uint32_t o_tmem = tmem_base + 256 + x * 128 + lane_addr;
+    uint8_t* my_p = p_s + x * Cfg::kPBytes;
+    const float sc = p.scale_log2;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full + x, j & 1);
+      tc_fence_after_sync();
+      const bool need_mask = (j + 1) * kKT > lim_first;
+      const int col_lim = my_lim - j * kKT;             // columns >= col_lim are masked
+      // ---- pass 1: row max; the load of the next 32 columns is in flight while these are reduced ----
+      float mx = -INFINITY;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(s_tmem, va);
+        tmem_ld_wait(va);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+          if (c < 3) tmem_ld_32x32b_x32(s_tmem + (c + 1) * 32, nxt);
+          if (need_mask) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i) < col_lim ? __uint_as_float(cur[i]) : -INFINITY);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+          }
+          if (c < 3) tmem_ld_wait(nxt);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * sc);
+      const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+      const float alpha = fast_exp2(m_run - m_safe);
+      // ---- P_x smem / O_x are free once PV_x(j-1) has completed ----
+      if (j > 0) {
+        mbar_wait(pv_done + x, (j - 1) & 1);
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha < 1.0f)) {     // lazy correction: only when some row's max moved
+#pragma unroll 1
+          for (int c = 0; c < kD / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(o_tmem + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(o_tmem + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // ---- pass 2: P = exp2(s*scale - m), rounded to bf16, into the swizzled [128 x 128] K-major tile ----
+      float psum = 0.f;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(s_tmem, va);
+        tmem_ld_wait(va);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+          if (c < 3) tmem_ld_32x32b_x32(s_tmem + (c + 1) * 32, nxt);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(cur[i]), sc, -m_safe));
+            float p1 = fast_exp2(fmaf(__uint_as_float(cur[i + 1]), sc, -m_safe));
+            if (need_mask) {
+              if (c * 32 + i >= col_lim) p0 = 0.f;
+              if (c * 32 + i + 1 >= col_lim) p1 = 0.f;
+            }
+            const uint32_t pp = pack_bf16x2(p0, p1);
+            pk[i >> 1] = pp;
+            psum += bf16lo(pp) + bf16hi(pp);              // denominator from the ROUNDED P (reference ladder)
+          }
+          // row r, columns [32c, 32c+32): sub-tile (c >> 1), 16-byte chunks ((c & 1) * 4 + i) ^ (r & 7)
+          uint8_t* rowp = my_p + (c >> 1) * Cfg::kSub + r * 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int chunk = ((c & 1) * 4 + i) ^ (r & 7);
+            *reinterpret_cast<uint4*>(rowp + (chunk << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+          if (c < 3) tmem_ld_wait(nxt);
+        }
+      }
+      l_run = l_run * alpha + psum;
+      m_run = m_new;
+      tc_fence_before_sync();          // my TMEM reads of S (and O stores) are ordered before the arrive below
+      fence_proxy_async_smem();        // P stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + x);
+    }
+    // ---- epilogue: O / l -> bf16 -> global ----
+    if (n_tiles > 0) {
+      mbar_wait(pv_done + x, (n_tiles - 1) & 1);
+      tc_fence_after_sync();
+    }
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* dst = nullptr;
+    if (row_valid) {
+      const int64_t tq = q0 + q_idx;
+      const int head = kvh * p.group + head_local;
+      dst = p.o + tq * p.o_stride_n + (int64_t)head * p.o_stride_h;
+      if (p.lse) p.lse[tq * p.num_qo_heads + head] = l_run > 0.f ? m_run + log2f(l_run) : -INFINITY;
+    }
+#pragma unroll 1
+    for (int c = 0; c < kD / 32; ++c) {
+      uint32_t v[32];
+      if (n_tiles > 0) {
+        tmem_ld_32x32b_x32(o_tmem + c * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0;
+      }
+      if (dst) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
 // Combines the kv_splits partials of every (q row, head): weights 2^(lse_s - max) / sum, fixed split order.
 __global__ void __launch_bounds__(128)
 prefill_merge_kernel(const PrefillParams p, int head_dim) {
@@ -404,11 +765,48 @@ static int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tk, const CU
   return 0;
 }
 
+template <int kD>
+static int launch_prefill2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const PrefillParams& p,
+                           int batch, int q_tiles, cudaStream_t stream) {
+  using Cfg = Prefill2Cfg<kD>;
+  auto kern = prefill_attention2_kernel<kD>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    XB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  dim3 grid((q_tiles + 1) / 2, p.num_kv_heads, batch), block(Cfg::kThreads);
+  XB_CUDA_OK(launch(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, tq, tk, tv, p));
+  return 0;
+}
+
 }  // namespace tc
 }  // namespace xb
 
 using namespace xb;
 using namespace xb::tc;
+
+// 0: one q tile per CTA (prefill_attention_kernel); 1: two q tiles per CTA, two softmax warpgroups (ping-pong).  Split-KV
+// launches always take variant 0.
+static std::atomic<int> g_prefill_variant{-1};
+static int prefill_variant() {
+  int v = g_prefill_variant.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("XB_PREFILL_V2");
+    v = e ? (atoi(e) != 0) : 0;     // TODO(default): flip once the B200 run confirms parity and speed
+    g_prefill_variant.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+extern "C" int xb_set_prefill_variant(int variant) {
+  if (variant < 0 || variant > 1) {
+    set_error("set_prefill_variant: variant %d (0 one q tile per CTA | 1 ping-pong pair)", variant);
+    return -1;
+  }
+  const int old = prefill_variant();
+  g_prefill_variant.store(variant, std::memory_order_relaxed);
+  return old;
+}
 
 // Shared host path of ragged_run / paged_run.
 static int prefill_common(const void* q, int64_t q_stride_n, int64_t q_stride_h, int64_t total_q, const void* k,
@@ -471,6 +869,9 @@ static int prefill_common(const void* q, int64_t q_stride_n, int64_t q_stride_h,
   if (make_tmap_2d(&tk, k, kv_rows, (uint64_t)num_kv_heads * head_dim, (uint64_t)kv_row_stride * 2, p.box_rows, 64, 2)) return 1;
   if (make_tmap_2d(&tv, v, kv_rows, (uint64_t)num_kv_heads * head_dim, (uint64_t)kv_row_stride * 2, p.box_rows, 64, 2)) return 1;
   const int q_tiles = (max_qo_len + p.tokens_per_tile - 1) / p.tokens_per_tile;
+  if (kv_splits == 1 && q_tiles >= 2 && prefill_variant() == 1)
+    return head_dim == 128 ? launch_prefill2<128>(tq, tk, tv, p, batch, q_tiles, stream)
+                           : launch_prefill2<64>(tq, tk, tv, p, batch, q_tiles, stream);
   return head_dim == 128 ? launch_prefill<128>(tq, tk, tv, p, batch, q_tiles, stream)
                          : launch_prefill<64>(tq, tk, tv, p, batch, q_tiles, stream);
 }

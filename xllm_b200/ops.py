@@ -386,6 +386,12 @@ def gemm_w4a16(x, qweight, meta, group_size, bias=None, out=None):
 
 
 # ---- K3 / K2 prefill attention ------------------------------------------------------
+def set_prefill_variant(variant: int) -> int:
+    """0: one q tile per CTA; 1: ping-pong pair of q tiles with two softmax warpgroups.  Returns the old variant."""
+    return int(lib().xb_set_prefill_variant(c_i32(variant)))
+
+
+
 def batch_prefill(query, key, value, q_cu_seq_lens, kv_cu_seq_lens, sm_scale, output, output_lse=None, max_qo_len=None,
                   causal=True) -> None:
     """xllm::kernel::cuda::batch_prefill (cuda_ops_api.h:52-66, batch_prefill.cpp:21-163): contiguous ragged q/k/v.
