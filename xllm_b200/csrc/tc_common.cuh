@@ -21,17 +21,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the warp in hardware up to the hint (ns scale) before it returns false: without it a waiting role
+// (TMA producer, MMA issuer, a softmax warp waiting for S) spins through SYNCS / BRA / YIELD issue slots of the SMSP it
+// shares with working warps - 19 % of all issued instructions of the prefill kernel (profiles/r02c_prefill_v2.md)
+constexpr uint32_t kMbarSuspendHint = 0x989680u;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "XB_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra XB_DONE_%=;\n"
       "bra XB_WAIT_%=;\n"
       "XB_DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(kMbarSuspendHint)
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -133,8 +137,12 @@ __device__ __forceinline__ uint32_t cluster_map(uint32_t local_addr, uint32_t ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // release at cluster scope
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// arrive on a barrier that may live in the peer CTA.  Default (CTA-scope release) semantics: what crosses the CTAs here is
+// consumed by the tensor core through the async proxy (ordered by fence.proxy.async / tcgen05 fences before the arrive),
+// not by generic-proxy loads of the waiting thread; a cluster-scope release costs a MEMBAR per arrive (the top stall of
+// the first W4 pair kernel: membar 5.75 warps per issue cycle, profiles/r02c_gemm_w4_pair.md)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
   asm volatile(
