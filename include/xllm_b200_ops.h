@@ -352,6 +352,10 @@ int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda,
  * 0 = automatic, 1 = single-CTA kernels only, 2 = CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles) kernels for shapes
  * with >= 74 pair tiles, 3 = CTA-pair kernels for every shape with M > 128 and N % 256 == 0.  Returns the old mode. */
 int xb_set_gemm_cta_pair(int mode);
+/* xb_gemm_fp8_scaled with M <= max_m (<= 64) runs swap-AB: the weight rows take the 128-row MMA M slot and the tokens the
+ * N tile (what the reference's M <= 16 / M <= 64 buckets of scaled_mm_sm100_fp8_dispatch.cuh:148-287 do), so a
+ * decode-sized batch streams every weight tile on its own CTA.  0 = never.  Returns the old value. */
+int xb_set_fp8_swap_max_m(int max_m);
 
 /* ---- tensor-parallel exchange over NVLink peer memory (decode-sized messages) ---------------------------------
  * replaces parallel_state::reduce -> ProcessGroup::allreduce (framework/parallel_state/parallel_state.cpp:183-192,

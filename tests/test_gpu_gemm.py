@@ -242,3 +242,29 @@ def test_gemm_w4a16_cta_pair_dequant_bit_exact(cta_pairs):
     x = torch.eye(K, dtype=BF16)
     y = ops.gemm_w4a16(x.to(DEV), qw.to(DEV), meta.to(DEV), gs)
     assert torch.equal(y.cpu(), wd.t().contiguous())
+
+
+@pytest.mark.parametrize("M,N,K,per_token,per_channel,use_bias", [(1, 256, 128, False, False, False), (32, 1280, 8192, True, True, True),
+                                                                  (17, 8192, 1024, False, True, False), (64, 7168, 8192, True, False, True),
+                                                                  (33, 1000, 416, False, False, False)])
+def test_cutlass_scaled_mm_swap_ab(M, N, K, per_token, per_channel, use_bias, built_lib):
+    """decode-sized M through the tcgen05 kernel with the weight rows in the MMA M slot (xb_set_fp8_swap_max_m): same spec."""
+    from xllm_b200 import ops
+    g = torch.Generator().manual_seed(2026)
+    a = torch.randn(M, K, generator=g).clamp(-3, 3).to(E4M3)
+    w = torch.randn(N, K, generator=g).clamp(-3, 3).to(E4M3)
+    a_s = (torch.rand(M if per_token else 1, generator=g) * 0.1 + 0.01).float()
+    b_s = (torch.rand(N if per_channel else 1, generator=g) * 0.1 + 0.01).float()
+    bias = torch.randn(N, generator=g).to(BF16) if use_bias else None
+    ref = O.fp8_scaled_matmul(a, w, a_s, b_s, bias)
+    c = torch.zeros(M, N, dtype=BF16, device=DEV)
+    old = ops.set_fp8_swap_max_m(64)
+    try:
+        ops.gemm_fp8_scaled(c, a.to(DEV), w.to(DEV), a_s.to(DEV), b_s.to(DEV), bias.to(DEV) if bias is not None else None)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_fp8_swap_max_m(old)
+    scale = (a.float().abs() @ w.float().abs().t()) * a_s.reshape(-1, 1) * b_s.reshape(1, -1)
+    if bias is not None:
+        scale = scale + bias.float().abs()
+    assert_close_sum(c, ref, scale, rtol=1e-5, what=f"fp8 swap-AB {M}x{N}x{K}")

@@ -92,6 +92,11 @@ struct GemmParams {
   int gshift;                  // log2(k64 tiles per quantisation group)
   int M, N, K;
   int use_tma_store;           // C rows are 16-byte aligned: epilogue stages through smem and TMA-stores
+  // swap-AB (decode-sized M): the WEIGHT rows ride in the 128-row MMA M slot and the tokens are the N tile, so every CTA
+  // streams 128 weight rows instead of idling 3/4 of a 128-token tile.  M / N / a_scale / b_scale are already in the
+  // swapped roles (M = output channels, N = tokens, a_scale per channel, b_scale per token); the epilogue indexes bias by
+  // row, keeps the reference's product order token_scale * (channel_scale * acc) and stores C transposed: c[col][row]
+  int swap_ab;
 };
 
 constexpr int kBlockM = 128;
@@ -336,14 +341,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (kKind == kKindFP8) {
             const float b0 = p.b_scale[p.b_scale_per_col ? min(col, p.N - 1) : 0];
             const float b1 = p.b_scale[p.b_scale_per_col ? min(col + 1, p.N - 1) : 0];
-            x0 = a_s * (b0 * x0);                 // ScaledEpilogue order: scale_a * (scale_b * acc)
-            x1 = a_s * (b1 * x1);
+            if (p.swap_ab) {                      // rows = channels (scale_b), columns = tokens (scale_a): same product order
+              x0 = b0 * (a_s * x0);
+              x1 = b1 * (a_s * x1);
+            } else {
+              x0 = a_s * (b0 * x0);               // ScaledEpilogue order: scale_a * (scale_b * acc)
+              x1 = a_s * (b1 * x1);
+            }
           }
           if (p.bias) {
-            x0 += __bfloat162float(p.bias[min(col, p.N - 1)]);
-            x1 += __bfloat162float(p.bias[min(col + 1, p.N - 1)]);
+            if (p.swap_ab) {
+              const float bv = __bfloat162float(p.bias[min(row, p.M - 1)]);
+              x0 += bv;
+              x1 += bv;
+            } else {
+              x0 += __bfloat162float(p.bias[min(col, p.N - 1)]);
+              x1 += __bfloat162float(p.bias[min(col + 1, p.N - 1)]);
+            }
           }
           o[j >> 1] = pack_bf16x2(x0, x1);
+        }
+        if (p.swap_ab) {
+          // transposed store: this thread owns output channel `row`, registers hold tokens col0 .. col0 + 31; a warp writes
+          // 32 consecutive channels (64 bytes) of one token row per instruction
+          if (row < p.M) {
+            const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(o);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) p.c[(int64_t)(col0 + j) * p.ldc + row] = ob[j];
+          }
+          continue;
         }
         if (p.use_tma_store) {
           // staging tile [32 rows][64 cols] bf16, row = 128 bytes, 16-byte chunk j stored at (j ^ (row & 7))
@@ -510,7 +537,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
   const int want = units * kCG;
   dim3 grid(want < max_ctas ? want : max_ctas), block(Cfg::kThreads);
   CUtensorMap tc = ta;   // placeholder when the direct-store epilogue is used
-  p.use_tma_store = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+  p.use_tma_store = !p.swap_ab && (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
   if (p.use_tma_store && make_tmap_2d(&tc, p.c, p.M, p.N, (uint64_t)p.ldc * 2, 32, 64, 2)) return 1;
   XB_CUDA_OK(launch_cluster(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, kCG, ta, tb, tc, tm ? *tm : ta, p));
   return 0;
@@ -553,6 +580,27 @@ static bool use_cta_pair(int M, int N, int bn, bool weight_only = false) {
   const int64_t units = (int64_t)((M + 255) / 256) * (N / 256);
   if (mode == 3) return M > 128;                   // every shape that can form a pair tile (tests)
   return M >= 512 && units >= 74;
+}
+
+static std::atomic<int> g_fp8_swap_max_m{-1};
+static int fp8_swap_max_m() {
+  int v = g_fp8_swap_max_m.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("XB_FP8_SWAP_MAX_M");
+    v = e ? atoi(e) : 0;            // TODO(default): set from the B200 probe
+    if (v < 0) v = 0;
+    g_fp8_swap_max_m.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+extern "C" int xb_set_fp8_swap_max_m(int max_m) {
+  if (max_m < 0 || max_m > 64) {
+    set_error("set_fp8_swap_max_m: %d out of range (0 = never swap .. 64)", max_m);
+    return -1;
+  }
+  const int old = fp8_swap_max_m();
+  g_fp8_swap_max_m.store(max_m, std::memory_order_relaxed);
+  return old;
 }
 
 extern "C" int xb_set_gemm_cta_pair(int mode) {
@@ -602,6 +650,22 @@ extern "C" int xb_gemm_fp8_scaled(void* c, int64_t ldc, const void* a, int64_t l
   p.a_scale = a_scale; p.b_scale = b_scale;
   p.a_scale_per_row = a_scale_numel > 1; p.b_scale_per_col = b_scale_numel > 1;
   p.M = M; p.N = N; p.K = K;
+  // decode-sized M: swap-AB (see GemmParams::swap_ab).  Measured on B200 (tools/fp8_swap_probe.py) against the token-major
+  // tile and the mma.sync streaming kernel.  XB_FP8_SWAP_MAX_M: largest M that swaps (0 disables).
+  if (M <= fp8_swap_max_m() && M <= 64 && N >= 128) {
+    p.swap_ab = 1;
+    p.M = N; p.N = M;
+    p.a_scale = b_scale; p.b_scale = a_scale;          // per-row = channel scales, per-column = token scales
+    p.a_scale_per_row = b_scale_numel > 1; p.b_scale_per_col = a_scale_numel > 1;
+    CUtensorMap tw, tx;
+    if (make_tmap_2d(&tw, b, N, K, (uint64_t)K, kBlockM, 128, 1)) return 1;
+    if (M <= 32) {
+      if (make_tmap_2d(&tx, a, M, K, (uint64_t)lda, 32, 128, 1)) return 1;
+      return launch_gemm<kKindFP8, 32>(tw, tx, p, (cudaStream_t)stream);
+    }
+    if (make_tmap_2d(&tx, a, M, K, (uint64_t)lda, 64, 128, 1)) return 1;
+    return launch_gemm<kKindFP8, 64>(tw, tx, p, (cudaStream_t)stream);
+  }
   const int bn = pick_block_n(M, N);
   const bool pair = use_cta_pair(M, N, bn);
   CUtensorMap ta, tb;

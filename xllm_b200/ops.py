@@ -304,6 +304,20 @@ def set_gemm_cta_pair(mode: int) -> int:
     return int(lib().xb_set_gemm_cta_pair(c_i32(mode)))
 
 
+def set_fp8_swap_max_m(max_m: int) -> int:
+    """largest M for which xb_gemm_fp8_scaled runs swap-AB (weight rows in the MMA M slot); 0 = never.  Returns the old value."""
+    return int(lib().xb_set_fp8_swap_max_m(c_i32(max_m)))
+
+
+def gemm_fp8_scaled(c, a, w, a_scales, b_scales, bias=None) -> None:
+    """the tcgen05 FP8 kernel directly (no small-M dispatch): a [M,K] e4m3, w [N,K] e4m3 (the reference's weight layout)."""
+    M, K = a.shape
+    N = w.size(0)
+    check(lib().xb_gemm_fp8_scaled(_p(c), c_i64(c.stride(0)), _p(a), c_i64(a.stride(0)), _p(w), _p(a_scales),
+                                   c_i32(a_scales.numel()), _p(b_scales), c_i32(b_scales.numel()), _p(bias), c_i32(M),
+                                   c_i32(N), c_i32(K), _stream()), "gemm_fp8_scaled")
+
+
 def gemm_bf16(a, b, bias=None, out=None):
     """always the tcgen05 kernel (tests / benchmarks)."""
     _cuda_bf16(a, "a"); _cuda_bf16(b, "b")
