@@ -587,8 +587,10 @@ static int fp8_swap_max_m() {
   int v = g_fp8_swap_max_m.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("XB_FP8_SWAP_MAX_M");
-    v = e ? atoi(e) : 0;            // TODO(default): set from the B200 probe
-    if (v < 0) v = 0;
+    // default 64: measured on B200 at M = 32 (tools/fp8_swap_probe.py, profiles/r02f_fp8_swap.md) swap-AB is 1.0-1.8x the
+    // token-major tile on the Llama-3-70B projections (qkv 43 -> 24 us unsharded, down TP8 shard 16.4 -> 12.7 us)
+    v = e ? atoi(e) : 64;
+    if (v < 0 || v > 64) v = 64;
     g_fp8_swap_max_m.store(v, std::memory_order_relaxed);
   }
   return v;
