@@ -381,6 +381,25 @@ int xb_embedding_bf16(void* out, const int32_t* token_ids, const void* table,
 int xb_argmax_bf16(int32_t* out, const void* logits, int64_t stride, int rows,
                    int vocab, xb_stream_t stream);
 
+/* ---- CUDA-graph decode metadata refresh ---------------------------------------------------------------
+ * replaces xllm::kernel::cuda::update_llm_decode_metadata (kernels/cuda/llm_decode_metadata_update.h:35-58,
+ * llm_decode_metadata_update.cu:29-96; caller runtime/cuda_graph_executor_impl.cpp:218-258): same fields, same padding
+ * rule (tokens / slots of rows actual..padded are zeroed, positions are left), kv_seq_lens_delta[i] = kv_seq_lens[i+1] -
+ * kv_seq_lens[i].  plan_counters / n_counter_words (optional): the int workspace words of this library's decode plan to
+ * re-zero in the same launch - with them the host-side `plan` the reference re-runs before every replay
+ * (cuda_graph_executor_impl.cpp:751-822) is not needed for this library's attention modules: their split geometry is
+ * derived on the device from the refreshed paged triplet. */
+int xb_decode_metadata_update(const int32_t* src_tokens, const int32_t* src_positions,
+                              const int32_t* src_new_cache_slots, const int32_t* src_kv_seq_lens,
+                              const int32_t* src_paged_kv_indptr, const int32_t* src_paged_kv_indices,
+                              const int32_t* src_paged_kv_last_page_len, int32_t* dst_tokens,
+                              int32_t* dst_positions, int32_t* dst_new_cache_slots, int32_t* dst_kv_seq_lens,
+                              int32_t* dst_kv_seq_lens_delta, int32_t* dst_paged_kv_indptr,
+                              int32_t* dst_paged_kv_indices, int32_t* dst_paged_kv_last_page_len,
+                              int64_t actual_num_tokens, int64_t padded_num_tokens, int64_t actual_batch_size,
+                              int64_t actual_indices_size, int32_t* plan_counters, int64_t n_counter_words,
+                              xb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

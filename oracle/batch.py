@@ -71,3 +71,23 @@ def build_paged_meta(seqs: List[SeqState], block_size: int, min_decoding_batch_s
             m.paged_kv_indptr.append(m.paged_kv_indptr[-1] + 1)
             m.paged_kv_last_page_len.append(1)
     return m
+
+
+def update_llm_decode_metadata(src: dict, dst: dict, actual_num_tokens: int, padded_num_tokens: int, actual_batch_size: int,
+                               actual_indices_size: int) -> dict:
+    """CPU restatement of llm_decode_metadata_update_kernel (xllm/core/kernels/cuda/llm_decode_metadata_update.cu:29-62):
+    dst is modified in place (numpy / torch int32 arrays) and returned.  Rows beyond the written ranges keep their old
+    content (the persistent buffers of the graph executor are larger than the live step)."""
+    n, pn, b, ni = actual_num_tokens, padded_num_tokens, actual_batch_size, actual_indices_size
+    dst["tokens"][:n] = src["tokens"][:n]
+    dst["positions"][:n] = src["positions"][:n]
+    dst["new_cache_slots"][:n] = src["new_cache_slots"][:n]
+    if pn > n:
+        dst["tokens"][n:pn] = 0
+        dst["new_cache_slots"][n:pn] = 0
+    dst["kv_seq_lens"][:b + 1] = src["kv_seq_lens"][:b + 1]
+    dst["paged_kv_indptr"][:b + 1] = src["paged_kv_indptr"][:b + 1]
+    dst["kv_seq_lens_delta"][:b] = src["kv_seq_lens"][1:b + 1] - src["kv_seq_lens"][:b]
+    dst["paged_kv_last_page_len"][:b] = src["paged_kv_last_page_len"][:b]
+    dst["paged_kv_indices"][:ni] = src["paged_kv_indices"][:ni]
+    return dst

@@ -91,6 +91,7 @@ def test_tvm_ffi_modules_export_reference_entry_points(built_lib):
     for uri in dec:
         so = ctypes.CDLL(os.path.join(ops_dir, uri, uri + ".so"))
         assert hasattr(so, "__tvm_ffi_plan") and hasattr(so, "__tvm_ffi_run")
+        assert hasattr(so, "__tvm_ffi_plan_is_replay_invariant")     # capability probe of integration/patches/0003
     for uri in pre:
         so = ctypes.CDLL(os.path.join(ops_dir, uri, uri + ".so"))
         assert all(hasattr(so, "__tvm_ffi_" + n) for n in ("plan", "ragged_run", "paged_run"))
@@ -104,5 +105,6 @@ def test_cpp_shim_exports_reference_namespace(built_lib):
     syms = subprocess.run(["nm", "-D", "-C", so], capture_output=True, text=True).stdout
     for fn in ("rotary_embedding", "act_and_mul", "reshape_paged_cache", "rms_norm", "fused_add_rms_norm", "matmul",
                "cutlass_scaled_mm", "static_scaled_fp8_quant", "fp8_scaled_quantize", "rms_norm_static_fp8_quant",
-               "fused_add_rms_norm_static_fp8_quant", "fp8_scaled_matmul", "fused_qk_norm_rope"):
+               "fused_add_rms_norm_static_fp8_quant", "fp8_scaled_matmul", "fused_qk_norm_rope",
+               "update_llm_decode_metadata"):
         assert f"xllm::kernel::cuda::{fn}(" in syms, fn

@@ -143,3 +143,25 @@ def test_qwen2_attention_mixed_prefill_kat():
     out = attn.forward(positions, hidden, meta, k_cache, v_cache)
     _check(out.flatten()[:10], [0.07763672, 0.08349609, 0.08496094, 0.08349609, 0.07958984, 0.08740234, 0.09130859,
                                 0.08398438, 0.08642578, 0.07958984])
+
+
+def test_update_llm_decode_metadata_restatement():
+    """hand-checked case of llm_decode_metadata_update_kernel (llm_decode_metadata_update.cu:29-62): 2 live requests in a
+    graph captured for 4, persistent buffers larger than the step."""
+    import numpy as np
+    from oracle import batch as OB
+    i32 = lambda *v: np.array(v, dtype=np.int32)
+    src = dict(tokens=i32(11, 12), positions=i32(7, 3), new_cache_slots=i32(39, 20), kv_seq_lens=i32(0, 8, 12),
+               paged_kv_indptr=i32(0, 2, 3), paged_kv_indices=i32(5, 9, 4), paged_kv_last_page_len=i32(4, 4))
+    dst = dict(tokens=i32(9, 9, 9, 9, 9), positions=i32(9, 9, 9, 9, 9), new_cache_slots=i32(9, 9, 9, 9, 9),
+               kv_seq_lens=i32(9, 9, 9, 9, 9), kv_seq_lens_delta=i32(9, 9, 9, 9), paged_kv_indptr=i32(9, 9, 9, 9, 9),
+               paged_kv_indices=i32(9, 9, 9, 9, 9, 9), paged_kv_last_page_len=i32(9, 9, 9, 9))
+    OB.update_llm_decode_metadata(src, dst, actual_num_tokens=2, padded_num_tokens=4, actual_batch_size=2, actual_indices_size=3)
+    assert dst["tokens"].tolist() == [11, 12, 0, 0, 9]            # padding rows zeroed, tail untouched
+    assert dst["positions"].tolist() == [7, 3, 9, 9, 9]           # positions of padding rows are NOT written
+    assert dst["new_cache_slots"].tolist() == [39, 20, 0, 0, 9]
+    assert dst["kv_seq_lens"].tolist() == [0, 8, 12, 9, 9]
+    assert dst["kv_seq_lens_delta"].tolist() == [8, 4, 9, 9]
+    assert dst["paged_kv_indptr"].tolist() == [0, 2, 3, 9, 9]
+    assert dst["paged_kv_indices"].tolist() == [5, 9, 4, 9, 9, 9]
+    assert dst["paged_kv_last_page_len"].tolist() == [4, 4, 9, 9]

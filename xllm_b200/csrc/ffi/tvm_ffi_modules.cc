@@ -253,8 +253,15 @@ void PagedRun(TensorView float_ws, TensorView int_ws, Array<int64_t> plan_vec, T
            "batch prefill paged_run");
 }
 
+// Optional capability probe (integration/patches/0003): a decode plan made under enable_cuda_graph depends only on the
+// captured (padded) batch and the workspace sizes - the kernels derive the split geometry on the device from the live paged
+// triplet and the arrival counters reset themselves - so a CUDA-graph executor may plan once and skip the host-side plan
+// before every replay (cuda_graph_executor_impl.cpp:751-822).
+int64_t PlanIsReplayInvariant() { return 1; }
+
 }  // namespace
 
+TVM_FFI_DLL_EXPORT_TYPED_FUNC(plan_is_replay_invariant, PlanIsReplayInvariant);
 #ifdef XB_FFI_DECODE_MODULE
 TVM_FFI_DLL_EXPORT_TYPED_FUNC(plan, DecodePlan);
 TVM_FFI_DLL_EXPORT_TYPED_FUNC(run, DecodeRun);

@@ -83,9 +83,97 @@ argmax_kernel(int32_t* __restrict__ out, const __nv_bfloat16* __restrict__ logit
   pdl_launch_dependents();
 }
 
+// Decode-step metadata refresh of a CUDA-graph replay, on the device (one launch, no host sync): copies the live step's
+// tokens / positions / slots / paged triplet into the graph's persistent buffers, zero-pads the token rows up to the
+// captured batch and derives the per-request kv lengths.  Same field-by-field semantics as
+// xllm::kernel::cuda::llm_decode_metadata_update_kernel (kernels/cuda/llm_decode_metadata_update.cu:29-62), which
+// CudaGraphPersistentParam::update_llm_decode_metadata_fast_path launches before every replay
+// (runtime/cuda_graph_executor_impl.cpp:218-258).  Plus, optionally, what the reference still does on the HOST before each
+// replay - re-running the attention `plan` for the new context lengths (cuda_graph_executor_impl.cpp:751-822): the split
+// geometry of this library's kernels is derived on the device from the refreshed kv_indptr / last_page_len, so the only
+// per-replay state a plan owns are the arrival counters, which this kernel re-zeroes (n_counter_words > 0).
+struct DecodeMetaParams {
+  const int32_t* src_tokens;
+  const int32_t* src_positions;
+  const int32_t* src_new_cache_slots;
+  const int32_t* src_kv_seq_lens;
+  const int32_t* src_paged_kv_indptr;
+  const int32_t* src_paged_kv_indices;
+  const int32_t* src_paged_kv_last_page_len;
+  int32_t* dst_tokens;
+  int32_t* dst_positions;
+  int32_t* dst_new_cache_slots;
+  int32_t* dst_kv_seq_lens;
+  int32_t* dst_kv_seq_lens_delta;
+  int32_t* dst_paged_kv_indptr;
+  int32_t* dst_paged_kv_indices;
+  int32_t* dst_paged_kv_last_page_len;
+  int64_t actual_num_tokens, padded_num_tokens, actual_batch_size, actual_indices_size;
+  int32_t* plan_counters;        // int workspace of the decode plan (arrival counters), or null
+  int64_t n_counter_words;
+};
+
+__global__ void __launch_bounds__(256)
+decode_metadata_update_kernel(const DecodeMetaParams p, int64_t max_work) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t step = (int64_t)blockDim.x * gridDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < max_work; i += step) {
+    if (i < p.actual_num_tokens) {
+      p.dst_tokens[i] = p.src_tokens[i];
+      p.dst_positions[i] = p.src_positions[i];
+      p.dst_new_cache_slots[i] = p.src_new_cache_slots[i];
+    } else if (i < p.padded_num_tokens) {       // padding rows of the captured batch: token 0, slot 0 (block 0 = padding block)
+      p.dst_tokens[i] = 0;
+      p.dst_new_cache_slots[i] = 0;
+    }
+    if (i < p.actual_batch_size + 1) {
+      p.dst_kv_seq_lens[i] = p.src_kv_seq_lens[i];
+      p.dst_paged_kv_indptr[i] = p.src_paged_kv_indptr[i];
+    }
+    if (i < p.actual_batch_size) {
+      p.dst_kv_seq_lens_delta[i] = p.src_kv_seq_lens[i + 1] - p.src_kv_seq_lens[i];
+      p.dst_paged_kv_last_page_len[i] = p.src_paged_kv_last_page_len[i];
+    }
+    if (i < p.actual_indices_size) p.dst_paged_kv_indices[i] = p.src_paged_kv_indices[i];
+    if (i < p.n_counter_words) p.plan_counters[i] = 0;
+  }
+}
+
 }  // namespace xb
 
 using namespace xb;
+
+extern "C" int xb_decode_metadata_update(const int32_t* src_tokens, const int32_t* src_positions,
+                                         const int32_t* src_new_cache_slots, const int32_t* src_kv_seq_lens,
+                                         const int32_t* src_paged_kv_indptr, const int32_t* src_paged_kv_indices,
+                                         const int32_t* src_paged_kv_last_page_len, int32_t* dst_tokens,
+                                         int32_t* dst_positions, int32_t* dst_new_cache_slots, int32_t* dst_kv_seq_lens,
+                                         int32_t* dst_kv_seq_lens_delta, int32_t* dst_paged_kv_indptr,
+                                         int32_t* dst_paged_kv_indices, int32_t* dst_paged_kv_last_page_len,
+                                         int64_t actual_num_tokens, int64_t padded_num_tokens, int64_t actual_batch_size,
+                                         int64_t actual_indices_size, int32_t* plan_counters, int64_t n_counter_words,
+                                         xb_stream_t stream) {
+  XB_CHECK(actual_num_tokens >= 0 && padded_num_tokens >= 0 && actual_batch_size >= 0 && actual_indices_size >= 0 &&
+               n_counter_words >= 0,
+           "decode_metadata_update: negative size");
+  XB_CHECK(n_counter_words == 0 || plan_counters != nullptr, "decode_metadata_update: plan_counters is null");
+  DecodeMetaParams p{src_tokens, src_positions, src_new_cache_slots, src_kv_seq_lens, src_paged_kv_indptr,
+                     src_paged_kv_indices, src_paged_kv_last_page_len, dst_tokens, dst_positions, dst_new_cache_slots,
+                     dst_kv_seq_lens, dst_kv_seq_lens_delta, dst_paged_kv_indptr, dst_paged_kv_indices,
+                     dst_paged_kv_last_page_len, actual_num_tokens, padded_num_tokens, actual_batch_size,
+                     actual_indices_size, plan_counters, n_counter_words};
+  int64_t max_work = actual_num_tokens;
+  if (padded_num_tokens > max_work) max_work = padded_num_tokens;
+  if (actual_batch_size + 1 > max_work) max_work = actual_batch_size + 1;
+  if (actual_indices_size > max_work) max_work = actual_indices_size;
+  if (n_counter_words > max_work) max_work = n_counter_words;
+  if (max_work <= 0) return 0;
+  int64_t blocks = (max_work + 255) / 256;
+  if (blocks > 4096) blocks = 4096;            // strided loop: bounded launch size (llm_decode_metadata_update.cu:84-87)
+  XB_CUDA_OK(launch(decode_metadata_update_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, true, p, max_work));
+  return 0;
+}
 
 extern "C" int xb_embedding_bf16(void* out, const int32_t* token_ids, const void* table, int num_tokens, int hidden,
                                  int vocab, xb_stream_t stream) {

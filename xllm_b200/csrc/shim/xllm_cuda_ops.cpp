@@ -320,4 +320,38 @@ torch::Tensor w8a16_linear(const torch::Tensor& x, const torch::Tensor& qweight,
   return out.view(shape);
 }
 
+
+// ---- kernels/cuda/llm_decode_metadata_update.h:35-58 (same struct, same entry point) -------------------------------------
+struct LlmDecodeMetadataUpdateParams {
+  const int32_t* src_tokens;
+  const int32_t* src_positions;
+  const int32_t* src_new_cache_slots;
+  const int32_t* src_kv_seq_lens;
+  const int32_t* src_paged_kv_indptr;
+  const int32_t* src_paged_kv_indices;
+  const int32_t* src_paged_kv_last_page_len;
+  int32_t* dst_tokens;
+  int32_t* dst_positions;
+  int32_t* dst_new_cache_slots;
+  int32_t* dst_kv_seq_lens;
+  int32_t* dst_kv_seq_lens_delta;
+  int32_t* dst_paged_kv_indptr;
+  int32_t* dst_paged_kv_indices;
+  int32_t* dst_paged_kv_last_page_len;
+  int64_t actual_num_tokens;
+  int64_t padded_num_tokens;
+  int64_t actual_batch_size;
+  int64_t actual_indices_size;
+};
+using LlmDecodeMetadataUpdateStream = cudaStream_t;
+
+void update_llm_decode_metadata(const LlmDecodeMetadataUpdateParams& p, LlmDecodeMetadataUpdateStream stream) {
+  ok(xb_decode_metadata_update(p.src_tokens, p.src_positions, p.src_new_cache_slots, p.src_kv_seq_lens, p.src_paged_kv_indptr,
+                               p.src_paged_kv_indices, p.src_paged_kv_last_page_len, p.dst_tokens, p.dst_positions,
+                               p.dst_new_cache_slots, p.dst_kv_seq_lens, p.dst_kv_seq_lens_delta, p.dst_paged_kv_indptr,
+                               p.dst_paged_kv_indices, p.dst_paged_kv_last_page_len, p.actual_num_tokens, p.padded_num_tokens,
+                               p.actual_batch_size, p.actual_indices_size, nullptr, 0, (xb_stream_t)stream),
+     "update_llm_decode_metadata");
+}
+
 }  // namespace xllm::kernel::cuda

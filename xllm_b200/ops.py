@@ -274,6 +274,25 @@ def embedding(out, token_ids, table) -> None:
                                   c_i32(table.size(0)), _stream()), "embedding")
 
 
+def update_llm_decode_metadata(src: dict, dst: dict, actual_num_tokens: int, padded_num_tokens: int, actual_batch_size: int,
+                               actual_indices_size: int, plan_counters=None) -> None:
+    """xllm::kernel::cuda::update_llm_decode_metadata (llm_decode_metadata_update.h:35-58): src / dst are dicts of int32
+    CUDA tensors with the fields of LlmDecodeMetadataUpdateParams (src: tokens, positions, new_cache_slots, kv_seq_lens,
+    paged_kv_indptr, paged_kv_indices, paged_kv_last_page_len; dst: the same + kv_seq_lens_delta).  plan_counters: optional
+    int32 workspace of a DecodePlan to re-zero in the same launch."""
+    for d in (src, dst):
+        for k, t in d.items():
+            _need(t.is_cuda and t.dtype == torch.int32 and t.is_contiguous(), f"{k} must be a contiguous int32 CUDA tensor")
+    nc = plan_counters.numel() if plan_counters is not None else 0
+    check(lib().xb_decode_metadata_update(
+        _p(src["tokens"]), _p(src["positions"]), _p(src["new_cache_slots"]), _p(src["kv_seq_lens"]), _p(src["paged_kv_indptr"]),
+        _p(src["paged_kv_indices"]), _p(src["paged_kv_last_page_len"]), _p(dst["tokens"]), _p(dst["positions"]),
+        _p(dst["new_cache_slots"]), _p(dst["kv_seq_lens"]), _p(dst["kv_seq_lens_delta"]), _p(dst["paged_kv_indptr"]),
+        _p(dst["paged_kv_indices"]), _p(dst["paged_kv_last_page_len"]), c_i64(actual_num_tokens), c_i64(padded_num_tokens),
+        c_i64(actual_batch_size), c_i64(actual_indices_size), _p(plan_counters), c_i64(nc), _stream()),
+        "update_llm_decode_metadata")
+
+
 def argmax(out, logits) -> None:
     """greedy sampling: out int32 [rows]."""
     _cuda_bf16(logits, "logits")
