@@ -381,6 +381,27 @@ int xb_embedding_bf16(void* out, const int32_t* token_ids, const void* table,
 int xb_argmax_bf16(int32_t* out, const void* logits, int64_t stride, int rows,
                    int vocab, xb_stream_t stream);
 
+/* ---- Mixture of experts, decode-sized token counts ---------------------------------------------------------
+ * xb_moe_fused_topk replaces xllm::kernel::cuda::moe_fused_topk (cuda_ops_api.h:251-256, moe/moe_fused_topk.cu:22-58):
+ *   gating_output [T, E] fp32 or bf16 (row stride in elements), scoring softmax (scoring_sigmoid = 0) or sigmoid with an
+ *   optional fp32 correction bias [E] (added for the selection, subtracted from the returned weight), top-k with ties to the
+ *   lower expert index, optional renormalisation by the sum of the selected weights; outputs topk_weights fp32 [T, k],
+ *   topk_ids int32 [T, k].  E <= 512, k <= 32.
+ * xb_moe_experts_bf16 replaces xllm::kernel::cuda::cutlass_fused_moe (cuda_ops_api.h:260-289, moe/fused_moe.cpp:23-124) for
+ *   unquantised bf16 experts (all the reference's CUDA FusedMoE accepts, layers/cuda/fused_moe.cpp:39-42): fc1 [E_local, 2I, H]
+ *   in [up | gate] row order, fc2 [E_local, H, I]; out[t] = bf16(sum_k scale[t,k] * bf16(fc2_e . bf16(silu(gate) * up))).
+ *   Experts outside [expert_begin, expert_begin + num_local_experts) contribute zero (expert parallelism: the caller
+ *   all-reduces, layers/cuda/fused_moe.cpp:116-117).  workspace: xb_moe_experts_workspace_bytes. */
+int xb_moe_fused_topk(float* topk_weights, int32_t* topk_ids, const void* gating_output, int gating_is_bf16,
+                      int64_t gating_stride, const float* correction_bias, int num_tokens, int num_experts, int topk,
+                      int renormalize, int scoring_sigmoid, xb_stream_t stream);
+int64_t xb_moe_experts_workspace_bytes(int num_tokens, int topk, int hidden, int inter);
+int xb_moe_experts_bf16(void* out, int64_t out_stride, const void* input, int64_t in_stride,
+                        const int32_t* token_selected_experts, const float* token_final_scales,
+                        const void* fc1_weights, const void* fc2_weights, int num_tokens, int topk, int hidden,
+                        int inter, int num_local_experts, int expert_begin, void* workspace,
+                        int64_t workspace_bytes, xb_stream_t stream);
+
 /* ---- CUDA-graph decode metadata refresh ---------------------------------------------------------------
  * replaces xllm::kernel::cuda::update_llm_decode_metadata (kernels/cuda/llm_decode_metadata_update.h:35-58,
  * llm_decode_metadata_update.cu:29-96; caller runtime/cuda_graph_executor_impl.cpp:218-258): same fields, same padding

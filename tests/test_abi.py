@@ -106,5 +106,5 @@ def test_cpp_shim_exports_reference_namespace(built_lib):
     for fn in ("rotary_embedding", "act_and_mul", "reshape_paged_cache", "rms_norm", "fused_add_rms_norm", "matmul",
                "cutlass_scaled_mm", "static_scaled_fp8_quant", "fp8_scaled_quantize", "rms_norm_static_fp8_quant",
                "fused_add_rms_norm_static_fp8_quant", "fp8_scaled_matmul", "fused_qk_norm_rope",
-               "update_llm_decode_metadata"):
+               "update_llm_decode_metadata", "moe_fused_topk", "cutlass_fused_moe"):
         assert f"xllm::kernel::cuda::{fn}(" in syms, fn

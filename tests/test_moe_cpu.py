@@ -1,0 +1,54 @@
+"""CPU: the MoE router restatement (oracle/moe.py) against the ordering the reference's own test pins
+(tests/core/kernels/cuda/moe/moe_topk_test.cu:31-55 cpuTopK: value descending, ties to the smaller index) and the documented
+semantics of moe_fused_topk (softmax / sigmoid + correction bias / renormalize)."""
+import numpy as np
+import torch
+
+from oracle import moe as OM
+
+
+def _cpu_topk(values, k):
+    """moe_topk_test.cu:31-55"""
+    order = sorted(range(len(values)), key=lambda i: (-values[i], i))
+    return order[:k]
+
+
+def test_topk_ordering_matches_reference_cpu_topk():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(7, 64, generator=g)
+    x[2, 5] = x[2, 40] = x[2].max() + 1.0            # an exact tie at the top: lower index first
+    w, ids = OM.moe_fused_topk(x, 6, False, None, "softmax")
+    p = torch.softmax(x.float(), dim=1)
+    for t in range(7):
+        assert ids[t].tolist() == _cpu_topk(p[t].tolist(), 6)
+        assert np.allclose(w[t].numpy(), p[t][ids[t].long()].numpy(), rtol=1e-6)
+    assert ids[2, 0] == 5 and ids[2, 1] == 40
+
+
+def test_sigmoid_bias_and_renormalize_semantics():
+    x = torch.tensor([[0.0, 2.0, -1.0, 2.0]])
+    bias = torch.tensor([10.0, 0.0, 0.0, 0.0])
+    w, ids = OM.moe_fused_topk(x, 2, True, bias, "sigmoid")
+    # selection uses sigmoid + bias (expert 0 wins through its bias), the weight is the biased value minus the bias
+    assert ids[0].tolist() == [0, 1]
+    s = torch.sigmoid(x[0])
+    raw = np.array([np.float32(np.float32(s[0] + 10.0) - 10.0), np.float32(s[1])], np.float32)
+    assert np.allclose(w[0].numpy(), raw / raw.sum(), rtol=1e-6)
+    assert abs(float(w.sum()) - 1.0) < 1e-6
+    w2, _ = OM.moe_fused_topk(x, 2, False, None, "sigmoid")
+    assert np.allclose(w2[0].numpy(), [s[1], s[3]], rtol=1e-6)         # tie between experts 1 and 3 -> 1 first
+
+
+def test_fused_moe_zero_for_foreign_experts():
+    g = torch.Generator().manual_seed(3)
+    H, I, E = 64, 32, 4
+    x = torch.randn(2, H, generator=g).to(torch.bfloat16)
+    fc1 = (torch.randn(E, 2 * I, H, generator=g) * 0.1).to(torch.bfloat16)
+    fc2 = (torch.randn(E, H, I, generator=g) * 0.1).to(torch.bfloat16)
+    ids = torch.tensor([[0, 3], [2, 1]], dtype=torch.int32)
+    sc = torch.tensor([[0.6, 0.4], [0.5, 0.5]])
+    full = OM.fused_moe(x, ids, sc, fc1, fc2)
+    lo = OM.fused_moe(x, ids, sc, fc1[:2], fc2[:2], expert_begin=0)
+    hi = OM.fused_moe(x, ids, sc, fc1[2:], fc2[2:], expert_begin=2)
+    # expert parallelism: the two halves add up (before the final rounding) to the full result
+    assert torch.allclose(lo.float() + hi.float(), full.float(), atol=2e-2, rtol=2e-2)

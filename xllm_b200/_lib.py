@@ -26,6 +26,7 @@ def lib():
         _lib.xb_launch_count.restype = ctypes.c_uint64
         _lib.xb_abi_version.restype = ctypes.c_int
         _lib.xb_prefill_split_workspace_bytes.restype = ctypes.c_int64
+        _lib.xb_moe_experts_workspace_bytes.restype = ctypes.c_int64
     return _lib
 
 

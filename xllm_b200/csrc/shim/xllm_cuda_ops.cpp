@@ -14,6 +14,7 @@
 #include <optional>
 #include <string>
 #include <tuple>
+#include <vector>
 
 #include "../../../include/xllm_b200_ops.h"
 
@@ -352,6 +353,78 @@ void update_llm_decode_metadata(const LlmDecodeMetadataUpdateParams& p, LlmDecod
                                p.dst_paged_kv_indices, p.dst_paged_kv_last_page_len, p.actual_num_tokens, p.padded_num_tokens,
                                p.actual_batch_size, p.actual_indices_size, nullptr, 0, (xb_stream_t)stream),
      "update_llm_decode_metadata");
+}
+
+
+// ---- cuda_ops_api.h:251-256 ------------------------------------------------------------------------------------------------
+std::tuple<torch::Tensor, torch::Tensor> moe_fused_topk(torch::Tensor& gating_output, int64_t topk, bool renormalize,
+                                                        const std::optional<torch::Tensor>& correction_bias,
+                                                        const std::string& scoring_func) {
+  TORCH_CHECK(scoring_func == "softmax" || scoring_func == "sigmoid", "Unsupported scoring function for moe topk: ", scoring_func,
+              "only softmax and sigmoid are supported");
+  TORCH_CHECK(gating_output.is_cuda() && gating_output.dim() == 2 && gating_output.stride(1) == 1, "gating_output [tokens, experts]");
+  const bool is_bf16 = gating_output.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(is_bf16 || gating_output.scalar_type() == torch::kFloat32, "moe_fused_topk: gating_output must be float32 or bfloat16");
+  XB_GUARD(gating_output);
+  const int64_t T = gating_output.size(0);
+  auto w = torch::empty({T, topk}, torch::dtype(torch::kFloat32).device(gating_output.device()));
+  auto ids = torch::empty({T, topk}, torch::dtype(torch::kInt32).device(gating_output.device()));
+  const bool sig = scoring_func == "sigmoid";
+  const float* bias = nullptr;
+  if (sig && correction_bias.has_value() && correction_bias->defined()) {       // dropped on the softmax path (moe_fused_topk.cu:36-43)
+    TORCH_CHECK(correction_bias->scalar_type() == torch::kFloat32 && correction_bias->is_contiguous(), "correction_bias must be float32");
+    bias = correction_bias->data_ptr<float>();
+  }
+  ok(xb_moe_fused_topk(w.data_ptr<float>(), ids.data_ptr<int32_t>(), gating_output.data_ptr(), is_bf16 ? 1 : 0, gating_output.stride(0),
+                       bias, (int)T, (int)gating_output.size(1), (int)topk, renormalize ? 1 : 0, sig ? 1 : 0, stream()),
+     "moe_fused_topk");
+  return std::make_tuple(w, ids);
+}
+
+// ---- cuda_ops_api.h:260-289 (utils.h:61-71 ActivationType) -------------------------------------------------------------------
+enum class ActivationType : int8_t { GELU = 0, RELU = 1, SILU = 2, SWIGLU = 3, GEGLU = 4, SWIGLU_BIAS = 5, RELU2 = 6, IDENTITY = 7, INVALID_TYPE = 8 };
+
+torch::Tensor cutlass_fused_moe(const torch::Tensor& input, const torch::Tensor& token_selected_experts,
+                                const torch::Tensor& token_final_scales, const torch::Tensor& fc1_expert_weights,
+                                const torch::Tensor& fc2_expert_weights, torch::ScalarType output_dtype,
+                                const std::vector<torch::Tensor>& quant_scales, int32_t tp_size, int32_t tp_rank, int32_t ep_size,
+                                int32_t ep_rank, int32_t cluster_size, int32_t cluster_rank,
+                                const std::optional<torch::Tensor>& fc1_expert_biases, const std::optional<torch::Tensor>& fc2_expert_biases,
+                                const std::optional<torch::Tensor>& input_sf, const std::optional<torch::Tensor>& swiglu_alpha,
+                                const std::optional<torch::Tensor>& swiglu_beta, const std::optional<torch::Tensor>& swiglu_limit,
+                                const std::optional<torch::Tensor>& output, bool enable_alltoall, bool use_deepseek_fp8_block_scale,
+                                bool use_w4_group_scaling, bool use_mxfp8_act_scaling, bool min_latency_mode, bool use_packed_weights,
+                                int32_t /*tune_max_num_tokens*/, ActivationType activation_type) {
+  // what layers/cuda/fused_moe.cpp:97-115 asks for: bf16 experts, no quant scales, SwiGLU, result reduction by the caller
+  TORCH_CHECK(quant_scales.empty() && !use_deepseek_fp8_block_scale && !use_w4_group_scaling && !use_mxfp8_act_scaling &&
+                  !use_packed_weights && !input_sf.has_value(),
+              "cutlass_fused_moe: only unquantized bf16 experts are supported");
+  TORCH_CHECK(!fc1_expert_biases.has_value() && !fc2_expert_biases.has_value() && !swiglu_alpha.has_value() &&
+                  !swiglu_beta.has_value() && !swiglu_limit.has_value(),
+              "cutlass_fused_moe: expert biases / swiglu alpha, beta, limit are not supported");
+  TORCH_CHECK(activation_type == ActivationType::SWIGLU, "cutlass_fused_moe: only SWIGLU experts are supported");
+  TORCH_CHECK(!enable_alltoall && !min_latency_mode && cluster_size == 1 && cluster_rank == 0, "cutlass_fused_moe: unsupported mode");
+  TORCH_CHECK(output_dtype == torch::kBFloat16 && input.scalar_type() == torch::kBFloat16 &&
+                  fc1_expert_weights.scalar_type() == torch::kBFloat16 && fc2_expert_weights.scalar_type() == torch::kBFloat16,
+              "cutlass_fused_moe: bf16 only");
+  TORCH_CHECK(token_selected_experts.scalar_type() == torch::kInt32 && token_final_scales.scalar_type() == torch::kFloat32,
+              "cutlass_fused_moe: ids int32 / scales float32");
+  TORCH_CHECK(input.dim() == 2 && input.stride(1) == 1 && fc1_expert_weights.is_contiguous() && fc2_expert_weights.is_contiguous() &&
+                  token_selected_experts.is_contiguous() && token_final_scales.is_contiguous(),
+              "cutlass_fused_moe: layout");
+  (void)tp_size; (void)tp_rank;            // the intermediate dimension is already this rank's slice (load_experts)
+  XB_GUARD(input);
+  const int64_t T = input.size(0), H = fc2_expert_weights.size(1), I = fc2_expert_weights.size(2), El = fc1_expert_weights.size(0);
+  const int64_t k = token_selected_experts.size(1);
+  torch::Tensor out = (output.has_value() && output->defined()) ? *output : torch::empty({T, H}, input.options());
+  const int64_t need = xb_moe_experts_workspace_bytes((int)T, (int)k, (int)H, (int)I);
+  auto ws = torch::empty({need}, torch::dtype(torch::kUInt8).device(input.device()));
+  ok(xb_moe_experts_bf16(out.data_ptr(), out.stride(0), input.data_ptr(), input.stride(0), token_selected_experts.data_ptr<int32_t>(),
+                         token_final_scales.data_ptr<float>(), fc1_expert_weights.data_ptr(), fc2_expert_weights.data_ptr(), (int)T,
+                         (int)k, (int)H, (int)I, (int)El, (int)(ep_rank * El), ws.data_ptr(), need, stream()),
+     "cutlass_fused_moe");
+  (void)ep_size;
+  return out;
 }
 
 }  // namespace xllm::kernel::cuda

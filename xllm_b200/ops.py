@@ -610,3 +610,47 @@ def w8a16_linear(x, qweight, meta, group_size, bias=None, out=None):
     if M <= WQ_SMALL_M_MAX or (M <= WQ_SMALL_M_MAX_NARROW and N <= SMALL_N_MAX):
         return w8a16_linear_small_m(x, qweight, meta, group_size, bias, out)
     return gemm_w8a16(x, qweight, meta, group_size, bias, out)
+
+
+# ---- mixture of experts ------------------------------------------------
+def moe_fused_topk(gating_output, topk: int, renormalize: bool, correction_bias=None, scoring_func: str = "softmax"):
+    """xllm::kernel::cuda::moe_fused_topk (cuda_ops_api.h:251-256): -> (topk_weights fp32 [T, k], topk_ids int32 [T, k])."""
+    _need(gating_output.is_cuda and gating_output.dim() == 2 and gating_output.stride(1) == 1, "gating_output [T, E] on device")
+    _need(gating_output.dtype in (torch.float32, BF16), "gating_output must be float32 or bfloat16")
+    if scoring_func not in ("softmax", "sigmoid"):
+        raise XllmB200Error(f"Unsupported scoring function for moe topk: {scoring_func}")
+    if correction_bias is not None:
+        _need(correction_bias.dtype == torch.float32 and correction_bias.is_contiguous(), "correction_bias must be float32")
+        if scoring_func == "softmax":
+            correction_bias = None          # the reference drops it on the softmax path (moe_fused_topk.cu:36-43)
+    T, E = gating_output.shape
+    w = torch.empty(T, topk, dtype=torch.float32, device=gating_output.device)
+    ids = torch.empty(T, topk, dtype=torch.int32, device=gating_output.device)
+    check(lib().xb_moe_fused_topk(_p(w), _p(ids), _p(gating_output), c_i32(1 if gating_output.dtype == BF16 else 0),
+                                  c_i64(gating_output.stride(0)), _p(correction_bias), c_i32(T), c_i32(E), c_i32(topk),
+                                  c_i32(1 if renormalize else 0), c_i32(1 if scoring_func == "sigmoid" else 0), _stream()),
+          "moe_fused_topk")
+    return w, ids
+
+
+def cutlass_fused_moe(input, token_selected_experts, token_final_scales, fc1_expert_weights, fc2_expert_weights, ep_size: int = 1,
+                      ep_rank: int = 0, output=None, workspace=None):
+    """xllm::kernel::cuda::cutlass_fused_moe (cuda_ops_api.h:260-289) for unquantised bf16 experts and decode-sized token
+    counts: fc1 [E_local, 2I, H] ([up | gate]), fc2 [E_local, H, I]; experts of other EP ranks contribute zero."""
+    _cuda_bf16(input, "input"); _cuda_bf16(fc1_expert_weights, "fc1_expert_weights"); _cuda_bf16(fc2_expert_weights, "fc2_expert_weights")
+    _need(token_selected_experts.dtype == torch.int32 and token_final_scales.dtype == torch.float32, "ids int32 / scales float32")
+    _need(token_selected_experts.is_contiguous() and token_final_scales.is_contiguous() and fc1_expert_weights.is_contiguous() and
+          fc2_expert_weights.is_contiguous(), "contiguous ids / scales / expert weights")
+    T, H = input.shape
+    k = token_selected_experts.size(1)
+    El, I2, _ = fc1_expert_weights.shape
+    inter = I2 // 2
+    _need(tuple(fc2_expert_weights.shape) == (El, H, inter), "fc2_expert_weights must be [E_local, H, I]")
+    out = output if output is not None else torch.empty(T, H, dtype=BF16, device=input.device)
+    need = int(lib().xb_moe_experts_workspace_bytes(c_i32(T), c_i32(k), c_i32(H), c_i32(inter)))
+    ws = workspace if workspace is not None and workspace.numel() >= need else torch.empty(need, dtype=torch.uint8, device=input.device)
+    check(lib().xb_moe_experts_bf16(_p(out), c_i64(out.stride(0)), _p(input), c_i64(input.stride(0)), _p(token_selected_experts),
+                                    _p(token_final_scales), _p(fc1_expert_weights), _p(fc2_expert_weights), c_i32(T), c_i32(k),
+                                    c_i32(H), c_i32(inter), c_i32(El), c_i32(ep_rank * El), _p(ws), c_i64(ws.numel()), _stream()),
+          "cutlass_fused_moe")
+    return out
