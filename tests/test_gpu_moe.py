@@ -59,7 +59,13 @@ def test_cutlass_fused_moe_decode(T, k, E, H, I, built_lib):
                                ep_size=2, ep_rank=0)
     hi = ops.cutlass_fused_moe(x.to(DEV), ids.to(DEV), sc.to(DEV), fc1[half:].contiguous().to(DEV), fc2[half:].contiguous().to(DEV),
                                ep_size=2, ep_rank=1)
-    assert_close_bf16((lo.float() + hi.float()).to(BF16), ref, ulps=6, rel_l2=5e-3, what="EP halves", atol=2.0 ** -9)
+    # each half is rounded to bf16 on its own before the all-reduce adds them: where the halves cancel, the error is an ulp of
+    # the (larger) halves, not of the sum
+    both = lo.float().cpu() + hi.float().cpu()
+    err = (both - ref.float()).abs()
+    bound = 2.0 ** -7 * (lo.float().abs().cpu() + hi.float().abs().cpu() + ref.float().abs()) + 2.0 ** -9
+    assert bool((err <= bound).all()), f"EP halves: worst err/bound {(err / bound).max():.2f}"
+    assert float((both - ref.float()).norm() / ref.float().norm()) <= 5e-3
 
 
 def test_fused_moe_layer(built_lib):
