@@ -52,13 +52,14 @@ def moe_fused_topk(gating_output: torch.Tensor, topk: int, renormalize: bool, co
     return torch.from_numpy(w), torch.from_numpy(ids)
 
 
-def fused_moe(x, token_selected_experts, token_final_scales, fc1, fc2, expert_begin=0):
+def fused_moe(x, token_selected_experts, token_final_scales, fc1, fc2, expert_begin=0, return_abs=False):
     """x [T, H] bf16, ids int32 [T, k], scales fp32 [T, k], fc1 [E_local, 2I, H] ([up | gate]), fc2 [E_local, H, I] -> [T, H]
     bf16.  Experts outside [expert_begin, expert_begin + E_local) contribute zero."""
     T, H = x.shape
     El, I2, _ = fc1.shape
     inter = I2 // 2
     out = torch.zeros(T, H, dtype=F32)
+    mag = torch.zeros(T, H, dtype=F32)          # sum_k scale_k |y2_k|: the magnitude the rounding errors of the terms scale with
     for t in range(T):
         acc = torch.zeros(H, dtype=F32)
         for k in range(token_selected_experts.size(1)):
@@ -71,5 +72,6 @@ def fused_moe(x, token_selected_experts, token_final_scales, fc1, fc2, expert_be
             else:
                 y2 = torch.zeros(H, dtype=F32)
             acc = torch.addcmul(acc, y2, token_final_scales[t, k].to(F32))
+            mag[t] += y2.abs() * token_final_scales[t, k].to(F32).abs()
         out[t] = acc
-    return out.to(BF16)
+    return (out.to(BF16), mag) if return_abs else out.to(BF16)

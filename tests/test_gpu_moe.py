@@ -48,11 +48,15 @@ def test_cutlass_fused_moe_decode(T, k, E, H, I, built_lib):
     fc2 = (torch.randn(E, H, I, generator=g) * I ** -0.5).to(BF16)
     ids = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(T)]).to(torch.int32)
     sc = torch.rand(T, k, generator=g).float()
-    ref = OM.fused_moe(x, ids, sc, fc1, fc2)
+    ref, mag = OM.fused_moe(x, ids, sc, fc1, fc2, return_abs=True)
     out = ops.cutlass_fused_moe(x.to(DEV), ids.to(DEV), sc.to(DEV), fc1.to(DEV), fc2.to(DEV))
     torch.cuda.synchronize()
-    # three roundings to bf16 (activation, expert output, final) - a 1-ulp flip of an activation moves y2 by ~1 ulp
-    assert_close_bf16(out, ref, ulps=4, rel_l2=3e-3, what=f"fused_moe T={T} k={k} E={E}", atol=2.0 ** -10)
+    # three roundings to bf16 (activation, expert output, final): a 1-ulp flip of one expert output y2_k moves the weighted
+    # sum by an ulp of THAT term, which can exceed an ulp of a sum that cancels: bound on sum_k scale_k |y2_k|
+    err = (out.float().cpu() - ref.float()).abs()
+    bound = 2.0 ** -7 * mag + 2.0 ** -7 * ref.float().abs() + 2.0 ** -10
+    assert bool((err <= bound).all()), f"fused_moe T={T} k={k} E={E}: worst err/bound {(err / bound).max():.2f}"
+    assert float((out.float().cpu() - ref.float()).norm() / ref.float().norm()) <= 3e-3
     # expert parallelism: two ranks' partial outputs add up to the full result
     half = E // 2
     lo = ops.cutlass_fused_moe(x.to(DEV), ids.to(DEV), sc.to(DEV), fc1[:half].contiguous().to(DEV), fc2[:half].contiguous().to(DEV),
