@@ -634,25 +634,10 @@ def main():
             except Exception as e:
                 comparators = [{"error": str(e)[:200]}]
 
-    # ---- the configuration the 1 -> 8 scaling target is defined on (extra key; the headline stays Qwen2-7B) ----------
-    scale_target = None
-    if not args.no_scale_target and args.parallelism == "tp" and world in (1, 2, 4, 8):
-        plan_info = (runner.plan.chunk_tokens, runner.plan.max_splits, runner.plan.cluster)
-        exch_mode = runner.exchange_mode if tp > 1 else None
-        h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
-        weights_bytes = weights.weight_bytes()
-        # release the Qwen2-7B runner (weights, caches, graph) before the 70B shard is built
-        runner = weights = L = gu = q3 = o3 = at_fns = gu_fns = gate_up_fn = None
-        import gc
-        gc.collect()
-        torch.cuda.empty_cache()
-        scale_target = scale_target_llama70b(torch, dist, dev, rank, world, exchange)
-        log(f"scale target {scale_target}")
-    else:
-        plan_info = (runner.plan.chunk_tokens, runner.plan.max_splits, runner.plan.cluster)
-        exch_mode = runner.exchange_mode if tp > 1 else None
-        h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
-        weights_bytes = weights.weight_bytes()
+    plan_info = (runner.plan.chunk_tokens, runner.plan.max_splits, runner.plan.cluster)
+    exch_mode = runner.exchange_mode if tp > 1 else None
+    h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
+    weights_bytes = weights.weight_bytes()
 
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
     t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
@@ -663,13 +648,15 @@ def main():
     value = total_tokens / (ms / 1e3)
     e2e_value = total_tokens / (e2e_ms / 1e3)
     step_bytes = weights_bytes + cfg.num_layers * at_bytes      # per rank
-    if rank == 0:
+
+    def emit(scale_target, with_cpu=True):
+        """rank 0: build and print THE JSON line (called once)."""
         cpu = None
-        if not args.no_cpu_baseline:
+        if with_cpu and not args.no_cpu_baseline:
             tps, step_s, threads, sample, spread = cpu_layer_baseline(budget_s=15.0)
             cpu = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "spread": spread}
         ach = gu_bytes / gu_us_avg / 1e3
-        traffic_file = "r02_w4_gemv_gateup_fused.md"
+        traffic_file = "r02_w4_gemv_gateup.md"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -718,6 +705,32 @@ def main():
         if scale_target is not None:
             line["scale_target"] = scale_target
         print(json.dumps(line), flush=True)
+
+    # ---- the configuration the 1 -> 8 scaling target is defined on (extra key; the headline stays Qwen2-7B) ----------
+    # It builds a second model and (N > 1) a second symmetric-memory rendezvous on the world group: a guard timer makes
+    # sure the headline line is printed even if that extra measurement wedges (scale_target then carries the error).
+    scale_target = None
+    if not args.no_scale_target and args.parallelism == "tp" and world in (1, 2, 4, 8):
+        # release the Qwen2-7B runner (weights, caches, graph) before the 70B shard is built
+        runner = weights = L = gu = q3 = o3 = at_fns = gu_fns = gate_up_fn = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        guard_s = float(os.environ.get("XB_SCALE_TARGET_TIMEOUT", "300"))
+
+        def bail():
+            if rank == 0:
+                emit({"error": f"scale target did not finish within {guard_s:.0f} s (headline unaffected)"}, with_cpu=False)
+            sys.stdout.flush()
+            os._exit(0)
+        guard = threading.Timer(guard_s, bail)
+        guard.daemon = True
+        guard.start()
+        scale_target = scale_target_llama70b(torch, dist, dev, rank, world, exchange)
+        guard.cancel()
+        log(f"scale target {scale_target}")
+    if rank == 0:
+        emit(scale_target)
     if world > 1:
         # destroy_process_group() blocks here (captured NCCL / symmetric-memory graphs still hold communicator
         # references); every rank is done and rank 0 has printed, so leave without the collective teardown

@@ -1,8 +1,8 @@
 """Launches ONE target kernel a few times on BASELINE configs[1] shapes so that `ncu --set full -k regex:<name> -s 2 -c 1`
 captures a warmed-up launch (see profiles/ for the summaries made from these captures).
-  python tools/profile_targets.py gate_up     W4A16 gate_up GEMV, split-norm consumer prologue + SiLU*mul epilogue (37888 x 3584)
-  python tools/profile_targets.py down        W4A16 down GEMV, residual + statistics epilogue (3584 x 18944)
-  python tools/profile_targets.py qkv         W4A16 qkv GEMV, split-norm prologue + RoPE / KV-scatter epilogue (4608 x 3584)
+  python tools/profile_targets.py gate_up     W4A16 gate_up GEMV + SiLU*mul epilogue (37888 x 3584): the step's dominant launch
+  python tools/profile_targets.py down        W4A16 down GEMV (3584 x 18944)
+  python tools/profile_targets.py qkv         W4A16 qkv GEMV + RoPE / KV-scatter epilogue (4608 x 3584)
   python tools/profile_targets.py decode      paged decode attention, batch 1, ctx 4096, 28 / 4 heads of 128
   python tools/profile_targets.py decode64    paged decode attention, batch 64, ctx 4096
   python tools/profile_targets.py gemm_w4 | gemm_w4_pair | gemm_bf16_pair   tcgen05 GEMM 8192 x 4608 x 3584 (single CTA / CTA pair)
@@ -29,16 +29,13 @@ def w4(N, K, gs=128):
 def main(which, reps=4):
     H = 3584
     if which in ("gate_up", "qkv"):
+        # the launches of the shipped 200-launch decode step (Qwen2DecodeRunner.launch_step)
         N = 37888 if which == "gate_up" else 4608
         ws = [w4(N, H) for _ in range(reps)]
-        r = torch.randn(1, H, device=DEV, dtype=BF16)
-        stats = (r.float() ** 2).view(H // 16, 16).sum(-1, keepdim=True).repeat(1, 8).contiguous()
-        stats[:, 1:] = 0
-        nw = torch.ones(H, device=DEV, dtype=BF16)
+        x = torch.randn(1, H, device=DEV, dtype=BF16)
         if which == "gate_up":
             y = torch.empty(1, N // 2, device=DEV, dtype=BF16)
-            fn = lambda i: ops.w4a16_decode_fused(r, ws[i][0], ws[i][1], 128, None, y, norm_weight=nw, norm_stats_in=stats,
-                                                  epilogue="act_mul")
+            fn = lambda i: ops.w4a16_gate_up_act(x, ws[i][0], ws[i][1], 128, "silu", None, y)
         else:
             y = torch.empty(1, N, device=DEV, dtype=BF16)
             pos = torch.full((1,), 4095, dtype=torch.int64, device=DEV)
@@ -46,18 +43,15 @@ def main(which, reps=4):
             slots = torch.full((1,), 300, dtype=torch.int32, device=DEV)
             kc = torch.zeros(8, 128, 4, 128, device=DEV, dtype=BF16)
             vc = torch.zeros_like(kc)
-            fn = lambda i: ops.w4a16_decode_fused(r, ws[i][0], ws[i][1], 128, None, y, norm_weight=nw, norm_stats_in=stats,
-                                                  epilogue="rope_cache", positions=pos, cos_sin_cache=cs, slot_ids=slots,
-                                                  key_cache=kc, value_cache=vc, num_heads=28, num_kv_heads=4, head_dim=128)
+            fn = lambda i: ops.w4a16_decode_fused(x, ws[i][0], ws[i][1], 128, None, y, epilogue="rope_cache", positions=pos,
+                                                  cos_sin_cache=cs, slot_ids=slots, key_cache=kc, value_cache=vc, num_heads=28,
+                                                  num_kv_heads=4, head_dim=128)
     elif which == "down":
         K = 18944
         ws = [w4(H, K) for _ in range(reps)]
         x = torch.randn(1, K, device=DEV, dtype=BF16)
-        res = torch.randn(1, H, device=DEV, dtype=BF16)
-        res_out = torch.empty_like(res)
-        stats = torch.zeros(H // 16, 8, device=DEV)
-        fn = lambda i: ops.w4a16_decode_fused(x, ws[i][0], ws[i][1], 128, None, None, epilogue="residual_stats", residual_in=res,
-                                              residual_out=res_out, norm_stats_out=stats, stage_x=True)
+        y = torch.empty(1, H, device=DEV, dtype=BF16)
+        fn = lambda i: ops.w4a16_linear_small_m(x, ws[i][0], ws[i][1], 128, None, y)
     elif which in ("decode", "decode64"):
         B = 1 if which == "decode" else 64
         HQ, HKV, D, page, ctx = 28, 4, 128, 128, 4096
