@@ -124,7 +124,13 @@ struct GemmCfg {
   // mbarrier arrive the other: a few hundred cycles each), so the converters must run further ahead of the MMA
   static constexpr int kBStages = kind_is_wq(kKind) ? (kCG == 2 ? 4 : 2) : 0;
   static constexpr int kBRing = kBStages > 0 ? kBStages : 2;        // barriers of the ring (two dummies when unused)
-  static constexpr int kConvWarps = kind_is_wq(kKind) ? 8 : 0;      // two converter warps per SM sub-partition
+  // converters: 8 warps convert one B stage (two per SM sub-partition).  A converter's k block is a latency chain (shared
+  // loads -> ALU -> shared stores -> proxy fence -> arrive, ~2/3 of the 512 MMA cycles of a pair k block: ncu showed the
+  // converter warps parked at the fence and the MMA issuer asleep on B-ready, tensor pipe 61 %), so CTA pairs run TWO sets
+  // of 8 warps that take alternate k blocks: each set has two MMA periods per stage
+  static constexpr int kConvSets = kind_is_wq(kKind) ? (kCG == 2 ? 2 : 1) : 0;
+  static constexpr int kConvPerStage = kind_is_wq(kKind) ? 8 : 0;
+  static constexpr int kConvWarps = kConvSets * kConvPerStage;
   static constexpr int kEpiStageBytes = kNumEpiWarps * 2 * 4096;   // per epilogue warp: 2 x [32 rows x 64 cols] bf16
   static constexpr int kBudget = 227 * 1024 - 1024 - 512 - kEpiStageBytes - kBStages * kBBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
@@ -181,7 +187,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(packed_bar + s, 1);
     }
     for (int s = 0; s < Cfg::kBRing; ++s) {
-      mbar_init(bready_bar + s, Cfg::kConvWarps > 0 ? Cfg::kConvWarps * kCG : 1);   // one elected arrive per converter warp (of both CTAs)
+      mbar_init(bready_bar + s, Cfg::kConvPerStage > 0 ? Cfg::kConvPerStage * kCG : 1);   // one elected arrive per converter warp of the stage's set (of both CTAs)
       mbar_init(bempty_bar + s, 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -411,30 +417,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if (p.use_tma_store && lane == 0) tma_store_wait_all();
   } else if (kind_is_wq(kKind) && warp >= 2 + kNumEpiWarps) {
-    // ======================= W4 / W8 converters (warps 6..13) =======================
+    // ======================= W4 / W8 converters (warps 6..13, pairs: 6..21 in two sets) =======================
     // converter warp cw handles row tiles cw, cw+8, ... of the stage; a lane's 16 bytes of packed data are
     // rows (g, g+8) x k in [16t, 16t+16) of its row tile  ->  four 16-byte chunks of the swizzled bf16 tile.
-    const int cw = warp - (2 + kNumEpiWarps);
+    const int cw = (warp - (2 + kNumEpiWarps)) % Cfg::kConvPerStage;     // row-tile lane of this warp within its set
+    const int cset = (warp - (2 + kNumEpiWarps)) / Cfg::kConvPerStage;    // which alternate k blocks this warp converts
     const int g = lane >> 2, t = lane & 3;
-    int s = 0;
-    uint32_t ph = 0;
-    int bs = 0;
-    uint32_t bph = 0;
+    int it = 0;                                  // k blocks since kernel start (every set walks all of them)
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        if (Cfg::kConvSets > 1 && (it % Cfg::kConvSets) != cset) continue;
+        const int s = it % kStages, bs = it % Cfg::kBRing;
+        const uint32_t ph = (it / kStages) & 1, bph = (it / Cfg::kBRing) & 1;
         mbar_wait(packed_bar + s, ph);          // packed tile + meta landed
         mbar_wait(bempty_bar + bs, bph ^ 1);    // the MMA has finished reading this B buffer
-        const uint8_t* pk = stage_packed(s);
-        const uint32_t* mt = reinterpret_cast<const uint32_t*>(stage_meta(s));
-        uint8_t* bt = b_ring(bs);
+        // explicit shared-space addresses: through generic pointers these compile to LD.E / ST.E (address-space
+        // resolution per access) instead of LDS / STS
+        const uint32_t pk = smem_u32(stage_packed(s));
+        const uint32_t mt = smem_u32(stage_meta(s));
+        const uint32_t bt = smem_u32(b_ring(bs));
 #pragma unroll
-        for (int r = cw; r < Cfg::kCtaN / 16; r += Cfg::kConvWarps) {
+        for (int r = cw; r < Cfg::kCtaN / 16; r += Cfg::kConvPerStage) {
           uint32_t lo[8], hi[8];   // row g / row g+8: 16 bf16 = 8 packed registers, k ascending
-          const uint32_t m0 = mt[r * 16 + g], m1 = mt[r * 16 + g + 8];
+          const uint32_t m0 = lds_32(mt + (r * 16 + g) * 4), m1 = lds_32(mt + (r * 16 + g + 8) * 4);
           if constexpr (kKind == kKindW8) {
             // int8 tile: 32 bytes per lane (row g then row g+8), meta = bf16 scale | zero << 16 (common.cuh w8_dequant_word)
-            const uint4 wa = *reinterpret_cast<const uint4*>(pk + r * 1024 + lane * 32);
-            const uint4 wb = *reinterpret_cast<const uint4*>(pk + r * 1024 + lane * 32 + 16);
+            const uint4 wa = lds_128(pk + r * 1024 + lane * 32);
+            const uint4 wb = lds_128(pk + r * 1024 + lane * 32 + 16);
             uint32_t s0, s1;
             float nz0, nz1;
             w8_meta(m0, s0, nz0);
@@ -447,7 +456,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               w8_dequant_word(bv[j], nz1, s1, hi[2 * j], hi[2 * j + 1]);
             }
           } else {
-          const uint4 wq = *reinterpret_cast<const uint4*>(pk + r * 512 + lane * 16);
+          const uint4 wq = lds_128(pk + r * 512 + lane * 16);
           const uint32_t s0 = __byte_perm(m0, 0, 0x1010), z0 = __byte_perm(m0, 0, 0x3232);
           const uint32_t s1 = __byte_perm(m1, 0, 0x1010), z1 = __byte_perm(m1, 0, 0x3232);
           const uint32_t* wv = &wq.x;
@@ -475,10 +484,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = 2 * t + h;
-            *reinterpret_cast<uint4*>(bt + n_lo * 128 + ((c ^ (n_lo & 7)) << 4)) =
-                make_uint4(lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
-            *reinterpret_cast<uint4*>(bt + n_hi * 128 + ((c ^ (n_hi & 7)) << 4)) =
-                make_uint4(hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
+            sts_128(bt + n_lo * 128 + ((c ^ (n_lo & 7)) << 4), make_uint4(lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]));
+            sts_128(bt + n_hi * 128 + ((c ^ (n_hi & 7)) << 4), make_uint4(hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]));
           }
         }
         fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core's async-proxy reads
@@ -487,8 +494,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (kPair) mbar_arrive_cluster(bready_leader + bs * 8);   // the leader's MMA reads this CTA's half through the pair
           else mbar_arrive(bready_bar + bs);
         }
-        if (++s == kStages) { s = 0; ph ^= 1; }
-        if (++bs == Cfg::kBRing) { bs = 0; bph ^= 1; }
       }
     }
   }
