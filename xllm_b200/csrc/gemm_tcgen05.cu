@@ -118,8 +118,10 @@ struct GemmCfg {
   // BF16 / FP8: a stage holds the A and B tiles.  W4: a stage holds A + the PACKED int4 B tile + its scale/zero words
   // (small, so the TMA ring can be deep enough to cover HBM latency) and the dequantised bf16 B lives in a separate
   // 2-deep ring written by the converter warps.
-  static constexpr int kStageBytes = kind_is_wq(kKind) ? kABytes + kPackedBytes + ((kMetaBytes + 1023) / 1024) * 1024
+  static constexpr int kPackedRegion = ((kPackedBytes + 1023) / 1024) * 1024;      // stages stay 1024-byte aligned (SW128 A tiles)
+  static constexpr int kStageBytes = kind_is_wq(kKind) ? kABytes + kPackedRegion + ((kMetaBytes + 1023) / 1024) * 1024
                                                       : kABytes + kBBytes;
+  static_assert(kStageBytes % 1024 == 0 && kBBytes % 1024 == 0, "128B-swizzled tiles need 1024-byte aligned stages");
   // dequantised-B ring depth.  CTA pairs: the converters <-> MMA hand-off crosses SMs (multicast commit one way, remote
   // mbarrier arrive the other: a few hundred cycles each), so the converters must run further ahead of the MMA
   static constexpr int kBStages = kind_is_wq(kKind) ? (kCG == 2 ? 4 : 2) : 0;
@@ -136,8 +138,9 @@ struct GemmCfg {
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kThreads = (2 + kNumEpiWarps + kConvWarps) * 32;
   static constexpr int kAccCols = kMT * kBlockN;                     // one accumulator stage
-  static constexpr int kTmemCols = 2 * kAccCols;                   // two accumulator stages
-  static_assert(kTmemCols <= 512, "TMEM has 512 columns");
+  static constexpr int kTmemUsed = 2 * kAccCols;                   // two accumulator stages
+  static_assert(kTmemUsed <= 512, "TMEM has 512 columns");
+  static constexpr int kTmemCols = kTmemUsed <= 32 ? 32 : kTmemUsed <= 64 ? 64 : kTmemUsed <= 128 ? 128 : kTmemUsed <= 256 ? 256 : 512;   // allocations are powers of two
   static constexpr int kSmemBytes = kStages * kStageBytes + kBStages * kBBytes + kEpiStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
@@ -177,7 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto stage_a = [&](int s) { return smem + s * Cfg::kStageBytes; };
   auto stage_b = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes; };               // BF16 / FP8
   auto stage_packed = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes; };          // W4
-  auto stage_meta = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes + Cfg::kPackedBytes; };
+  auto stage_meta = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes + Cfg::kPackedRegion; };
   auto b_ring = [&](int bs) { return bbuf + bs * Cfg::kBBytes; };
 
   if (threadIdx.x == 0) {
@@ -378,7 +381,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           continue;
         }
-        if (p.use_tma_store) {
+        if (p.use_tma_store && (kBlockN / 32) % 2 == 1 && c == kBlockN / 32 - 1) {
+          // an odd number of 32-column chunks (BLOCK_N 224): the last one has no partner for a 64-column TMA box; four
+          // 16-byte stores per row instead (C rows are 16-byte aligned in this mode)
+          if (row < p.M && col0 < p.N) {
+            uint4* dst = reinterpret_cast<uint4*>(p.c + (int64_t)row * p.ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col0 + 8 * j < p.N) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+        } else if (p.use_tma_store) {
           // staging tile [32 rows][64 cols] bf16, row = 128 bytes, 16-byte chunk j stored at (j ^ (row & 7))
           uint8_t* st = my_stage + sbuf * 4096;
           if ((c & 1) == 0) tma_store_wait_read<1>();   // the buffer we are about to overwrite was stored 2 groups ago
@@ -600,6 +612,22 @@ static int fp8_swap_max_m() {
   }
   return v;
 }
+// BLOCK_N of a pair tile: 256, or 224 when that fills the last wave of the 74 pairs better (N = 3584: 14 x 32 = 448 tiles are
+// 6.05 waves = 86 % of 7 waves; 16 x 32 = 512 tiles of 224 columns are 6.92 waves = 99 %, at ~3 % less operand reuse)
+static int pair_block_n(int M, int N) {
+  static const int force = [] { const char* e = getenv("XB_GEMM_PAIR_BN"); return e ? atoi(e) : 0; }();
+  if (force == 256 || N % 224 != 0) return 256;
+  if (force == 224) return 224;
+  if (N % 256 != 0) return 224;
+  const int64_t mp = (M + 255) / 256;
+  auto eff = [&](int bn) {
+    const int64_t units = mp * (N / bn);
+    const int64_t waves = (units + 73) / 74;
+    return (double)units / (double)(waves * 74) * (bn == 224 ? 0.97 : 1.0);
+  };
+  return eff(224) > eff(256) ? 224 : 256;
+}
+
 extern "C" int xb_set_fp8_swap_max_m(int max_m) {
   if (max_m < 0 || max_m > 64) {
     set_error("set_fp8_swap_max_m: %d out of range (0 = never swap .. 64)", max_m);
@@ -632,9 +660,11 @@ extern "C" int xb_gemm_bf16(void* c, int64_t ldc, const void* a, int64_t lda, co
   p.M = M; p.N = N; p.K = K;
   const int bn = pick_block_n(M, N);
   const bool pair = use_cta_pair(M, N, bn);
+  const int pbn = pair ? pair_block_n(M, N) : 0;
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, kBlockM, 64, 2)) return 1;
-  if (make_tmap_2d(&tb, b, N, K, (uint64_t)K * 2, pair ? bn / 2 : bn, 64, 2)) return 1;
+  if (make_tmap_2d(&tb, b, N, K, (uint64_t)K * 2, pair ? pbn / 2 : bn, 64, 2)) return 1;
+  if (pair && pbn == 224) return launch_gemm<kKindBF16, 224, 1, 2>(ta, tb, p, (cudaStream_t)stream);
   if (pair) return launch_gemm<kKindBF16, 256, 1, 2>(ta, tb, p, (cudaStream_t)stream);
   if (bn == 256) return launch_gemm<kKindBF16, 256>(ta, tb, p, (cudaStream_t)stream);
   return bn == 128 ? launch_gemm<kKindBF16, 128>(ta, tb, p, (cudaStream_t)stream)
@@ -675,9 +705,11 @@ extern "C" int xb_gemm_fp8_scaled(void* c, int64_t ldc, const void* a, int64_t l
   }
   const int bn = pick_block_n(M, N);
   const bool pair = use_cta_pair(M, N, bn);
+  const int pbn = pair ? pair_block_n(M, N) : 0;
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda, kBlockM, 128, 1)) return 1;
-  if (make_tmap_2d(&tb, b, N, K, (uint64_t)K, pair ? bn / 2 : bn, 128, 1)) return 1;
+  if (make_tmap_2d(&tb, b, N, K, (uint64_t)K, pair ? pbn / 2 : bn, 128, 1)) return 1;
+  if (pair && pbn == 224) return launch_gemm<kKindFP8, 224, 1, 2>(ta, tb, p, (cudaStream_t)stream);
   if (pair) return launch_gemm<kKindFP8, 256, 1, 2>(ta, tb, p, (cudaStream_t)stream);
   if (bn == 256) return launch_gemm<kKindFP8, 256>(ta, tb, p, (cudaStream_t)stream);
   return bn == 128 ? launch_gemm<kKindFP8, 128>(ta, tb, p, (cudaStream_t)stream)
@@ -712,7 +744,8 @@ extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   const bool two_m = force_mt == 2 && M >= 256 && N % 128 == 0;
   if (two_m) bn = 128;
   const bool pair = !two_m && use_cta_pair(M, N, bn, true);
-  const int cta_n = pair ? bn / 2 : bn;      // B rows one CTA stages and dequantises
+  const int pbn = pair ? pair_block_n(M, N) : 0;
+  const int cta_n = pair ? pbn / 2 : bn;     // B rows one CTA stages and dequantises
   CUtensorMap ta, tb, tm;
   if (make_tmap_2d(&ta, a, M, K, (uint64_t)lda * 2, two_m ? 256 : kBlockM, 64, 2)) return 1;
   const uint64_t ktiles = K / 64;
@@ -722,6 +755,7 @@ extern "C" int xb_gemm_w4a16(void* c, int64_t ldc, const void* a, int64_t lda, c
   if (make_tmap_2d_raw(&tm, meta, CU_TENSOR_MAP_DATA_TYPE_UINT32, K / group_size, N, (uint64_t)N * 4, 1, cta_n,
                        CU_TENSOR_MAP_SWIZZLE_NONE))
     return 1;
+  if (pair && pbn == 224) return launch_gemm<kKindW4, 224, 1, 2>(ta, tb, p, (cudaStream_t)stream, &tm);
   if (pair) return launch_gemm<kKindW4, 256, 1, 2>(ta, tb, p, (cudaStream_t)stream, &tm);
   if (two_m) return launch_gemm<kKindW4, 128, 2>(ta, tb, p, (cudaStream_t)stream, &tm);
   if (bn == 256) return launch_gemm<kKindW4, 256>(ta, tb, p, (cudaStream_t)stream, &tm);
