@@ -334,8 +334,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int mt = 0; mt < kMT; ++mt) {
       const int row0 = (m_blk * kCG + (int)rank) * Cfg::kCtaM + mt * kBlockM + q * 32;
       const int row = row0 + lane;
-      float a_s = 1.f;
-      if (kKind == kKindFP8) a_s = p.a_scale[p.a_scale_per_row ? min(row, p.M - 1) : 0];
+      float a_s = 1.f, b_s_uniform = 1.f;
+      if (kKind == kKindFP8) {
+        a_s = p.a_scale[p.a_scale_per_row ? min(row, p.M - 1) : 0];
+        b_s_uniform = p.b_scale[0];
+      }
 #pragma unroll 1
       for (int c = 0; c < kBlockN / 32; ++c) {
         uint32_t r[32];
@@ -348,8 +351,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           float x0 = __uint_as_float(r[j]), x1 = __uint_as_float(r[j + 1]);
           const int col = col0 + j;
           if (kKind == kKindFP8) {
-            const float b0 = p.b_scale[p.b_scale_per_col ? min(col, p.N - 1) : 0];
-            const float b1 = p.b_scale[p.b_scale_per_col ? min(col + 1, p.N - 1) : 0];
+            // per-tensor scale: one load per tile row (b_s_uniform), not two global loads per element
+            const float b0 = p.b_scale_per_col ? p.b_scale[min(col, p.N - 1)] : b_s_uniform;
+            const float b1 = p.b_scale_per_col ? p.b_scale[min(col + 1, p.N - 1)] : b_s_uniform;
             if (p.swap_ab) {                      // rows = channels (scale_b), columns = tokens (scale_a): same product order
               x0 = b0 * (a_s * x0);
               x1 = b1 * (a_s * x1);
