@@ -131,3 +131,29 @@ def test_interleave_index_is_a_permutation():
     idx = quant.interleave_gate_up_index(64)
     assert sorted(idx.tolist()) == list(range(128))
     assert idx[:16].tolist() == list(range(8)) + list(range(64, 72))
+
+
+@pytest.mark.parametrize("fmt", ["awq", "gptq"])
+def test_checkpoint_layout_tensor_through_the_kernels(fmt, built_lib):
+    """SURVEY 8f n1 end to end on the GPU: tensors in the AutoAWQ / AutoGPTQ checkpoint layout -> from_awq / from_gptq ->
+    kernel layout (xb_w4_pack_rows) -> the decode GEMV and the tcgen05 dequant-GEMM, against the oracle on the logical form."""
+    from tests.test_checkpoint_surface import _logical, _pack_awq, _pack_seq_lastdim
+    from xllm_b200 import ops, quant
+    N, K, gs = 1152, 1024, 128
+    q, z, s = _logical(N=N, K=K, gs=gs, seed=4)
+    if fmt == "awq":
+        q2, s2, z2 = quant.from_awq(_pack_awq(q.t().contiguous()), _pack_awq(z.t().contiguous()), s.t().contiguous(), gs)
+    else:
+        qw_ckpt = _pack_seq_lastdim(q).t().contiguous()
+        qz_ckpt = _pack_seq_lastdim((z.t().to(torch.int16) - 1).contiguous())
+        g_idx = torch.arange(K, dtype=torch.int32) // gs
+        q2, s2, z2 = quant.from_gptq(qw_ckpt, qz_ckpt, s.t().contiguous(), g_idx, gs)
+    assert torch.equal(q2, q) and torch.equal(z2, z)
+    qw, meta = quant.pack_w4(q2, s2, z2, gs)
+    g = torch.Generator().manual_seed(8)
+    for M in (1, 7, 300):
+        x = torch.randn(M, K, generator=g).to(BF16)
+        ref = Q.linear_wna16(x, q2, s2, z2, gs, None)
+        y = ops.w4a16_linear(x.to(DEV), qw.to(DEV), meta.to(DEV), gs) if hasattr(ops, "w4a16_linear") else \
+            (ops.w4a16_linear_small_m if M <= 64 else ops.gemm_w4a16)(x.to(DEV), qw.to(DEV), meta.to(DEV), gs)
+        assert_close_sum(y, ref, _abs_scale(x, Q.dequantize(q2, s2, z2, gs)), rtol=1e-5, what=f"{fmt} checkpoint M={M}")

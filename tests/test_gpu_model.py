@@ -51,6 +51,16 @@ def test_decode_step_split_rmsnorm_variant(built_lib):
     assert torch.equal(nxt.long().cpu()[:3], ref_next), "greedy tokens differ"
 
 
+def test_decode_step_mlp_norm_variant(built_lib, monkeypatch):
+    """XB_FUSE_MLP_NORM=1: the post-attention add+RMSNorm rides in the gate_up GEMV's prologue; same step."""
+    monkeypatch.setenv("XB_FUSE_MLP_NORM", "1")
+    cfg = _small("w4a16")
+    logits, ref_logits, nxt, ref_next, runner, _ = run_decode_parity(cfg, [37, 300, 1], True, True)
+    assert runner.fuse_mlp_norm
+    assert_close_bf16(logits, ref_logits, ulps=1e9, rel_l2=2e-2, what="decode-step logits (gate_up norm prologue)")
+    assert torch.equal(nxt.long().cpu()[:3], ref_next), "greedy tokens differ"
+
+
 def test_decode_step_qwen2_0_5b_shape(built_lib):
     """BASELINE configs[0] architecture (Qwen2-0.5B bf16, batch 1, ctx 128) with 2 layers to keep the oracle fast."""
     from xllm_b200.qwen2 import Qwen2Config

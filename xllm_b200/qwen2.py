@@ -289,6 +289,10 @@ class Qwen2DecodeRunner:
         if os.environ.get("XB_FUSE_GEMV") is not None:          # A/B measurements
             fuse_gemv = os.environ["XB_FUSE_GEMV"] != "0"
         self.fuse_gemv = bool(fuse_gemv and w4 and B <= 8 and ops.w4a16_decode_fused_fits(B, H))
+        # post-attention add+RMSNorm folded into the gate_up GEMV's prologue only (XB_FUSE_MLP_NORM=1; experiment): the wide
+        # gate_up launch hides the prologue (+0.5 us measured) while the separate add+norm kernel costs ~2.2 us
+        self.fuse_mlp_norm = bool(os.environ.get("XB_FUSE_MLP_NORM", "0") != "0" and w4 and B <= 8 and
+                                  ops.w4a16_decode_fused_fits(B, H) and not self.fuse_gemv)
         self.attn_out = torch.empty(B, self.q_size, dtype=BF16, device=dev)
         self.gate_up = torch.empty(B, 2 * self.inter, dtype=BF16, device=dev)
         self.act = torch.empty(B, self.inter, dtype=BF16, device=dev)
@@ -404,11 +408,41 @@ class Qwen2DecodeRunner:
         w.lm_head.forward(self.normed, self.logits_local)
         ops.argmax(self.next_tokens, self.logits)
 
+    def _launch_step_mlp_norm(self):
+        """TP = 1, W4A16, batch <= 8: the shipped step, except that the post-attention add+RMSNorm
+        (qwen2_decoder_layer.cpp:89-101) rides in the gate_up GEMV's prologue (every CTA recomputes the 7 KB row); the residual
+        stream ping-pongs between two buffers because the prologue's CTAs read the old one while CTA 0 writes the new one."""
+        cfg, w = self.cfg, self.w
+        eps = cfg.rms_norm_eps
+        ops.embedding(self.hidden, self.token_ids, w.embed)
+        res, pp = self.hidden, 0
+        ops.rms_norm(self.normed, self.hidden, w.layers[0]["input_norm"], eps)
+        h = self.normed
+        n_layers = len(w.layers)
+        for li, L in enumerate(w.layers):
+            self._qkv_and_rope(L, li, h)
+            self._attention(li)
+            L["o"].forward(self.attn_out, self.buf_a)
+            gu, dn = L["gate_up"], L["down"]
+            # x = o_proj output, residual_in = stream; residual_out = stream + x; act = silu(gate) * up of the normed row
+            ops.w4a16_decode_fused(self.buf_a, gu.qweight, gu.meta, gu.group_size, gu.bias, self.act, norm_weight=L["post_norm"],
+                                   eps=eps, residual_in=res, residual_out=self.res_pp[pp], epilogue="act_mul", act_mode="silu")
+            res, pp = self.res_pp[pp], pp ^ 1
+            dn.forward(self.act, self.buf_b)
+            next_w = w.layers[li + 1]["input_norm"] if li + 1 < n_layers else w.final_norm
+            ops.fused_add_rms_norm(self.buf_b, res, next_w, eps)       # buf_b := normed, res := res + down output (in place)
+            h = self.buf_b
+        self.residual = res
+        w.lm_head.forward(h, self.logits_local)
+        ops.argmax(self.next_tokens, self.logits)
+
     def launch_step(self, trace=None):
         """trace (eager only): list that receives (normed layer output, residual) clones after every decoder layer."""
         cfg, w = self.cfg, self.w
         if self.fuse_gemv and self.pg is None and trace is None:
             return self._launch_step_fused()
+        if self.fuse_mlp_norm and self.pg is None and trace is None:
+            return self._launch_step_mlp_norm()
         ops.embedding(self.hidden, self.token_ids, w.embed)
         # apply_norm, first layer (qwen2_decoder_layer.cpp:72-79): the residual stream aliases the embedding output
         self.residual = self.hidden
