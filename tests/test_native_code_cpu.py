@@ -49,9 +49,14 @@ def test_gemm_kernels_use_tcgen05_tmem_tma(sass):
     for name, ops in _ops(sass, "gemm_tcgen05_kernel").items():
         assert ops & {"UTCHMMA", "UTCQMMA"}, f"{name}: no tcgen05.mma"
         assert "LDTM" in ops, f"{name}: no TMEM load in the epilogue"
-        assert "UTMALDG" in ops and "UTMASTG" in ops, f"{name}: no TMA tensor load/store"
+        assert "UTMALDG" in ops, f"{name}: no TMA tensor load"
+        # the 32-column instantiation exists only for the swap-AB decode path (transposed plain stores, no TMA store box)
+        if "ILi1ELi32E" not in name:
+            assert "UTMASTG" in ops, f"{name}: no TMA tensor store"
         assert "SYNCS" in ops, f"{name}: no mbarrier pipeline"
         assert "HMMA" not in ops, f"{name}: legacy mma.sync in a tcgen05 kernel"
+    pair = [k for k in sass if "gemm_tcgen05_kernel" in k and k.endswith("ELi2EEEv14CUtensorMap_stS2_S2_S2_NS0_10GemmParamsE")]
+    assert pair, "CTA-pair (cta_group::2) GEMM instantiations must be in the library"
     fp8 = [k for k in sass if "gemm_tcgen05_kernel" in k and "UTCQMMA" in set(sass[k])]
     assert fp8, "the FP8 GEMM must issue kind::f8f6f4 MMAs (UTCQMMA)"
 
@@ -60,6 +65,21 @@ def test_prefill_attention_uses_tcgen05(sass):
     for name, ops in _ops(sass, "prefill_attention_kernel").items():
         assert "UTCHMMA" in ops and "LDTM" in ops and "STTM" in ops, name   # S/O in TMEM, lazy O rescale
         assert "UTMALDG" in ops and "MUFU" in ops, name
+
+
+def test_pingpong_prefill_attention_uses_tcgen05(sass):
+    for name, ops in _ops(sass, "prefill_attention2_kernel").items():
+        assert "UTCHMMA" in ops and "LDTM" in ops and "STTM" in ops, name
+        assert "UTMALDG" in ops and "MUFU" in ops and "HMMA" not in ops, name
+
+
+def test_pair_gemm_uses_2cta_instructions(sass):
+    """cta_group::2 shows up as .2CTA variants of the MMA, the TMA load and the commit (UTCBAR ... MULTICAST)."""
+    import subprocess as sp
+    from xllm_b200 import build
+    fun = "_ZN2xb2tc19gemm_tcgen05_kernelILi0ELi256ELi1ELi2EEEv14CUtensorMap_stS2_S2_S2_NS0_10GemmParamsE"
+    out = sp.run([CUOBJDUMP, "-sass", "-fun", fun, build.LIB], capture_output=True, text=True).stdout
+    assert "UTCHMMA.2CTA" in out and "UTMALDG.2D.2CTA" in out and "UTCBAR.2CTA.MULTICAST" in out
 
 
 def test_streaming_kernels_shape(sass):
