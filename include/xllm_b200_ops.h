@@ -402,6 +402,17 @@ int xb_moe_experts_bf16(void* out, int64_t out_stride, const void* input, int64_
                         int inter, int num_local_experts, int expert_begin, void* workspace,
                         int64_t workspace_bytes, xb_stream_t stream);
 
+/* W4A16 experts (BASELINE configs[4] "MoE W4A16"; additive like the dense weight-only linears): per expert the tile-packed
+ * int4 layout of xb_linear_w4a16_small_m - fc1 qweight [E_local, 2I/16, H/64, 32, 4] u32 + meta [E_local, H/g, 2I] u32 (rows
+ * [up | gate]), fc2 qweight [E_local, H/16, I/64, 32, 4] + meta [E_local, I/g, H]; same arithmetic as xb_moe_experts_bf16 on
+ * the dequantised weights w = bf16((q - z) * s). */
+int xb_moe_experts_w4a16(void* out, int64_t out_stride, const void* input, int64_t in_stride,
+                         const int32_t* token_selected_experts, const float* token_final_scales,
+                         const uint32_t* fc1_qweight, const uint32_t* fc1_meta, const uint32_t* fc2_qweight,
+                         const uint32_t* fc2_meta, int group_size, int num_tokens, int topk, int hidden, int inter,
+                         int num_local_experts, int expert_begin, void* workspace, int64_t workspace_bytes,
+                         xb_stream_t stream);
+
 /* ---- CUDA-graph decode metadata refresh ---------------------------------------------------------------
  * replaces xllm::kernel::cuda::update_llm_decode_metadata (kernels/cuda/llm_decode_metadata_update.h:35-58,
  * llm_decode_metadata_update.cu:29-96; caller runtime/cuda_graph_executor_impl.cpp:218-258): same fields, same padding

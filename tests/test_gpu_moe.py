@@ -88,3 +88,33 @@ def test_fused_moe_layer(built_lib):
     sc, ids = OM.moe_fused_topk(logits, k, True, None, "softmax")
     ref = OM.fused_moe(x, ids, sc, w13, w2)
     assert_close_bf16(y, ref, ulps=6, rel_l2=5e-3, what="FusedMoE layer", atol=2.0 ** -9)
+
+
+@pytest.mark.parametrize("T,k,E,H,I,gs", [(1, 2, 4, 256, 128, 64), (4, 8, 32, 1024, 512, 128), (3, 6, 16, 2048, 1408, 128)])
+def test_fused_moe_w4a16_decode(T, k, E, H, I, gs, built_lib):
+    """W4A16 experts (additive, BASELINE configs[4]): per-expert tile-packed int4 weights through the expert-indexed GEMVs vs the
+    oracle MoE on the dequantised weights (spec form 1 of oracle/quant.py: w = bf16((q - z) s))."""
+    from oracle import quant as Q
+    from xllm_b200 import ops, quant
+    g = torch.Generator().manual_seed(E * 7 + H)
+    x = torch.randn(T, H, generator=g).to(BF16)
+    fc1 = (torch.randn(E, 2 * I, H, generator=g) * H ** -0.5).to(BF16)
+    fc2 = (torch.randn(E, H, I, generator=g) * I ** -0.5).to(BF16)
+    q1w, m1, q2w, m2, d1, d2 = [], [], [], [], [], []
+    for e in range(E):
+        q, s, z = Q.quantize(fc1[e], 4, gs)
+        a, b = quant.pack_w4(q, s, z, gs)
+        q1w.append(a); m1.append(b); d1.append(Q.dequantize(q, s, z, gs))
+        q, s, z = Q.quantize(fc2[e], 4, gs)
+        a, b = quant.pack_w4(q, s, z, gs)
+        q2w.append(a); m2.append(b); d2.append(Q.dequantize(q, s, z, gs))
+    ids = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(T)]).to(torch.int32)
+    sc = torch.rand(T, k, generator=g).float()
+    ref, mag = OM.fused_moe(x, ids, sc, torch.stack(d1), torch.stack(d2), return_abs=True)
+    out = ops.fused_moe_w4a16(x.to(DEV), ids.to(DEV), sc.to(DEV), torch.stack(q1w).to(DEV), torch.stack(m1).to(DEV),
+                              torch.stack(q2w).to(DEV), torch.stack(m2).to(DEV), gs)
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - ref.float()).abs()
+    bound = 2.0 ** -7 * mag + 2.0 ** -7 * ref.float().abs() + 2.0 ** -10
+    assert bool((err <= bound).all()), f"fused_moe_w4a16 T={T} k={k} E={E}: worst err/bound {(err / bound).max():.2f}"
+    assert float((out.float().cpu() - ref.float()).norm() / ref.float().norm()) <= 3e-3

@@ -212,6 +212,125 @@ moe_expert_gemv_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// W4A16 experts (SURVEY cfg[4] "MoE W4A16"; additive like the dense W4A16 linears - the reference's CUDA FusedMoE takes
+// unquantised experts only): the same expert-indexed GEMV over the tile-packed int4 layout of linear_small_m.cu, per expert
+//   qweight [E][rows/16][K/64][32 lanes][4] u32,  meta [E][K/g][rows] u32 (bf16 scale | bf16(128 + zero) << 16),
+// dequantised bit-exactly as w = bf16((q - z) * s) (spec form 1 of oracle/quant.py) right before the mma.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t moe_lop3_and_or(uint32_t a, uint32_t mask, uint32_t orv) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xea;" : "=r"(d) : "r"(a), "r"(mask), "r"(orv));
+  return d;
+}
+__device__ __forceinline__ uint32_t moe_hsub2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
+template <bool kSwiGLU>
+__global__ void __launch_bounds__(256)
+moe_expert_gemv_w4_kernel(__nv_bfloat16* __restrict__ y, int64_t y_stride, const __nv_bfloat16* __restrict__ x, int64_t x_stride,
+                          int x_row_div, const uint4* __restrict__ qweight, const uint32_t* __restrict__ meta,
+                          const int32_t* __restrict__ expert_ids, int N /* output rows per expert (I for SwiGLU) */, int K,
+                          int gshift /* log2(k64 tiles per quantisation group) */, int expert_begin, int expert_end) {
+  constexpr int kW = 8, kH = kSwiGLU ? 2 : 1;
+  __shared__ float red[kW][kH][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int pair = blockIdx.y;
+  const int n0 = blockIdx.x * 16;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int e_glob = expert_ids[pair];
+  const bool mine = e_glob >= expert_begin && e_glob < expert_end;
+  const int e = mine ? e_glob - expert_begin : 0;
+  const int rows = kSwiGLU ? 2 * N : N;
+  const int ktiles = K >> 6;
+  const uint4* qe = qweight + (int64_t)e * (rows >> 4) * ktiles * 32;
+  const uint32_t* me = meta + (int64_t)e * ((ktiles >> gshift) * (int64_t)rows);
+  const __nv_bfloat16* xr = x + (int64_t)(pair / x_row_div) * x_stride;
+  float acc[kH][4];
+#pragma unroll
+  for (int h = 0; h < kH; ++h)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[h][i] = 0.f;
+  if (mine && n0 < N) {
+    constexpr int kU = 4;
+    for (int kt0 = warp; kt0 < ktiles; kt0 += kW * kU) {
+      uint4 wq[kH][kU];
+      uint32_t m0[kH][kU], m1[kH][kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int kt = kt0 + u * kW;
+#pragma unroll
+        for (int h = 0; h < kH; ++h) {
+          wq[h][u] = make_uint4(0, 0, 0, 0);
+          m0[h][u] = m1[h][u] = 0;
+          if (kt < ktiles) {
+            const int row0 = h * N + n0;                       // up rows, then the matching gate rows
+            wq[h][u] = ldg_stream(qe + ((int64_t)(row0 >> 4) * ktiles + kt) * 32 + lane);
+            const uint32_t* mr = me + (int64_t)(kt >> gshift) * rows + row0;
+            m0[h][u] = __ldg(mr + g);
+            m1[h][u] = __ldg(mr + g + 8);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int kt = kt0 + u * kW;
+        if (kt < ktiles) {
+          uint4 xlo = make_uint4(0, 0, 0, 0), xhi = make_uint4(0, 0, 0, 0);
+          if (g == 0) {                                        // the token sits in column 0 of the n8 slot
+            const uint4* xp = reinterpret_cast<const uint4*>(xr + (kt << 6) + 16 * t);
+            xlo = xp[0];
+            xhi = xp[1];
+          }
+#pragma unroll
+          for (int h = 0; h < kH; ++h) {
+            const uint32_t s0 = __byte_perm(m0[h][u], 0, 0x1010), z0 = __byte_perm(m0[h][u], 0, 0x3232);
+            const uint32_t s1 = __byte_perm(m1[h][u], 0, 0x1010), z1 = __byte_perm(m1[h][u], 0, 0x3232);
+            const uint32_t* wv = &wq[h][u].x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w = wv[j];
+              const uint32_t a0 = hmul2_bf16x2(moe_hsub2(moe_lop3_and_or(w, 0x000f000fu, 0x43004300u), z0), s0);
+              const uint32_t a1 = hmul2_bf16x2(moe_hsub2(moe_lop3_and_or(w >> 4, 0x000f000fu, 0x43004300u), z1), s1);
+              const uint32_t a2 = hmul2_bf16x2(moe_hsub2(moe_lop3_and_or(w >> 8, 0x000f000fu, 0x43004300u), z0), s0);
+              const uint32_t a3 = hmul2_bf16x2(moe_hsub2(moe_lop3_and_or(w >> 12, 0x000f000fu, 0x43004300u), z1), s1);
+              const uint32_t* xv = j < 2 ? &xlo.x : &xhi.x;
+              mma_bf16_16816(acc[h], a0, a1, a2, a3, xv[(j & 1) * 2], xv[(j & 1) * 2 + 1]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (t == 0) {
+#pragma unroll
+    for (int h = 0; h < kH; ++h) {
+      red[warp][h][g] = acc[h][0];
+      red[warp][h][g + 8] = acc[h][2];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int r = threadIdx.x;
+    if (n0 + r < N) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kW; ++ww) {
+        s0 += red[ww][0][r];
+        if (kSwiGLU) s1 += red[ww][1][r];
+      }
+      float out = s0;
+      if (kSwiGLU) out = (s1 / (1.0f + expf(-s1))) * s0;
+      y[(int64_t)pair * y_stride + n0 + r] = __float2bfloat16_rn(mine ? out : 0.f);
+    }
+  }
+}
+
 // out[t] = bf16( sum_k scale[t,k] * y2[t*k + kk] ), fp32, selection order
 __global__ void __launch_bounds__(256)
 moe_combine_kernel(__nv_bfloat16* __restrict__ out, int64_t out_stride, const __nv_bfloat16* __restrict__ y2, const float* __restrict__ scales,
@@ -288,6 +407,44 @@ extern "C" int xb_moe_experts_bf16(void* out, int64_t out_stride, const void* in
                     reinterpret_cast<const __nv_bfloat16*>(act), (int64_t)inter, 1,
                     reinterpret_cast<const __nv_bfloat16*>(fc2_weights), token_selected_experts, hidden, inter, expert_begin,
                     expert_begin + num_local_experts));
+  const int cx = (hidden / 2 + 255) / 256;
+  XB_CUDA_OK(launch(moe_combine_kernel, dim3(cx, num_tokens), dim3(256), 0, s, true, reinterpret_cast<__nv_bfloat16*>(out),
+                    out_stride, reinterpret_cast<const __nv_bfloat16*>(y2), token_final_scales, topk, hidden));
+  return 0;
+}
+
+extern "C" int xb_moe_experts_w4a16(void* out, int64_t out_stride, const void* input, int64_t in_stride,
+                                    const int32_t* token_selected_experts, const float* token_final_scales,
+                                    const uint32_t* fc1_qweight, const uint32_t* fc1_meta, const uint32_t* fc2_qweight,
+                                    const uint32_t* fc2_meta, int group_size, int num_tokens, int topk, int hidden, int inter,
+                                    int num_local_experts, int expert_begin, void* workspace, int64_t workspace_bytes,
+                                    xb_stream_t stream) {
+  if (num_tokens == 0) return 0;
+  XB_CHECK(hidden % 64 == 0 && inter % 64 == 0, "moe_experts_w4a16: hidden %d / inter %d must be multiples of 64", hidden, inter);
+  XB_CHECK(group_size >= 64 && group_size % 64 == 0 && hidden % group_size == 0 && inter % group_size == 0,
+           "moe_experts_w4a16: group_size %d must be a multiple of 64 dividing hidden and inter", group_size);
+  const int tpg = group_size / 64;
+  XB_CHECK((tpg & (tpg - 1)) == 0, "moe_experts_w4a16: group_size / 64 must be a power of two");
+  int gshift = 0;
+  while ((1 << gshift) < tpg) ++gshift;
+  XB_CHECK(topk >= 1 && num_local_experts >= 1 && (int64_t)num_tokens * topk <= 65535, "moe_experts_w4a16: bad topk / experts / pairs");
+  XB_CHECK(workspace != nullptr && workspace_bytes >= xb_moe_experts_workspace_bytes(num_tokens, topk, hidden, inter),
+           "moe_experts_w4a16: workspace too small (need %lld bytes)",
+           (long long)xb_moe_experts_workspace_bytes(num_tokens, topk, hidden, inter));
+  XB_CHECK(in_stride % 8 == 0 && out_stride % 2 == 0 &&
+               ((reinterpret_cast<uintptr_t>(input) | reinterpret_cast<uintptr_t>(fc1_qweight) |
+                 reinterpret_cast<uintptr_t>(fc2_qweight) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
+           "moe_experts_w4a16: 16-byte alignment");
+  const int pairs = num_tokens * topk;
+  auto* act = reinterpret_cast<__nv_bfloat16*>(workspace);
+  auto* y2 = act + (int64_t)pairs * inter;
+  cudaStream_t s = (cudaStream_t)stream;
+  XB_CUDA_OK(launch(moe_expert_gemv_w4_kernel<true>, dim3(inter / 16, pairs), dim3(256), 0, s, true, act, (int64_t)inter,
+                    reinterpret_cast<const __nv_bfloat16*>(input), in_stride, topk, reinterpret_cast<const uint4*>(fc1_qweight),
+                    fc1_meta, token_selected_experts, inter, hidden, gshift, expert_begin, expert_begin + num_local_experts));
+  XB_CUDA_OK(launch(moe_expert_gemv_w4_kernel<false>, dim3(hidden / 16, pairs), dim3(256), 0, s, true, y2, (int64_t)hidden,
+                    reinterpret_cast<const __nv_bfloat16*>(act), (int64_t)inter, 1, reinterpret_cast<const uint4*>(fc2_qweight),
+                    fc2_meta, token_selected_experts, hidden, inter, gshift, expert_begin, expert_begin + num_local_experts));
   const int cx = (hidden / 2 + 255) / 256;
   XB_CUDA_OK(launch(moe_combine_kernel, dim3(cx, num_tokens), dim3(256), 0, s, true, reinterpret_cast<__nv_bfloat16*>(out),
                     out_stride, reinterpret_cast<const __nv_bfloat16*>(y2), token_final_scales, topk, hidden));

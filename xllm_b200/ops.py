@@ -654,3 +654,27 @@ def cutlass_fused_moe(input, token_selected_experts, token_final_scales, fc1_exp
                                     c_i32(H), c_i32(inter), c_i32(El), c_i32(ep_rank * El), _p(ws), c_i64(ws.numel()), _stream()),
           "cutlass_fused_moe")
     return out
+
+
+def fused_moe_w4a16(input, token_selected_experts, token_final_scales, fc1_qweight, fc1_meta, fc2_qweight, fc2_meta, group_size,
+                    ep_size: int = 1, ep_rank: int = 0, output=None, workspace=None):
+    """W4A16 experts (additive; BASELINE configs[4]): fc1 [E_local, 2I/16, H/64, 32, 4] + meta [E_local, H/g, 2I] ([up | gate]
+    rows, quant.pack_w4 per expert), fc2 [E_local, H/16, I/64, 32, 4] + meta [E_local, I/g, H]."""
+    _cuda_bf16(input, "input")
+    for t_, n in ((fc1_qweight, "fc1_qweight"), (fc1_meta, "fc1_meta"), (fc2_qweight, "fc2_qweight"), (fc2_meta, "fc2_meta")):
+        _need(t_.is_cuda and t_.dtype == torch.int32 and t_.is_contiguous(), f"{n} must be contiguous int32 storage on device")
+    _need(token_selected_experts.dtype == torch.int32 and token_final_scales.dtype == torch.float32 and
+          token_selected_experts.is_contiguous() and token_final_scales.is_contiguous(), "ids int32 / scales float32, contiguous")
+    T, H = input.shape
+    k = token_selected_experts.size(1)
+    El = fc1_qweight.size(0)
+    inter = fc1_meta.size(2) // 2
+    _need(tuple(fc2_meta.shape[:1]) == (El,) and fc2_meta.size(2) == H, "fc2_meta must be [E_local, I/g, H]")
+    out = output if output is not None else torch.empty(T, H, dtype=BF16, device=input.device)
+    need = int(lib().xb_moe_experts_workspace_bytes(c_i32(T), c_i32(k), c_i32(H), c_i32(inter)))
+    ws = workspace if workspace is not None and workspace.numel() >= need else torch.empty(need, dtype=torch.uint8, device=input.device)
+    check(lib().xb_moe_experts_w4a16(_p(out), c_i64(out.stride(0)), _p(input), c_i64(input.stride(0)), _p(token_selected_experts),
+                                     _p(token_final_scales), _p(fc1_qweight), _p(fc1_meta), _p(fc2_qweight), _p(fc2_meta),
+                                     c_i32(group_size), c_i32(T), c_i32(k), c_i32(H), c_i32(inter), c_i32(El), c_i32(ep_rank * El),
+                                     _p(ws), c_i64(ws.numel()), _stream()), "fused_moe_w4a16")
+    return out
