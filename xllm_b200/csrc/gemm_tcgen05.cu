@@ -97,6 +97,7 @@ struct GemmParams {
   // swapped roles (M = output channels, N = tokens, a_scale per channel, b_scale per token); the epilogue indexes bias by
   // row, keeps the reference's product order token_scale * (channel_scale * acc) and stores C transposed: c[col][row]
   int swap_ab;
+  int debug_skip_convert;      // XB_GEMM_DEBUG_SKIP_CONVERT=1 (timing diagnosis only, results are garbage): converters only hand the stage over
 };
 
 constexpr int kBlockM = 128;
@@ -454,6 +455,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t bt = smem_u32(b_ring(bs));
 #pragma unroll
         for (int r = cw; r < Cfg::kCtaN / 16; r += Cfg::kConvPerStage) {
+          if (p.debug_skip_convert) break;
           uint32_t lo[8], hi[8];   // row g / row g+8: 16 bf16 = 8 packed registers, k ascending
           const uint32_t m0 = lds_32(mt + (r * 16 + g) * 4), m1 = lds_32(mt + (r * 16 + g + 8) * 4);
           if constexpr (kKind == kKindW8) {
@@ -559,6 +561,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
   dim3 grid(want < max_ctas ? want : max_ctas), block(Cfg::kThreads);
   CUtensorMap tc = ta;   // placeholder when the direct-store epilogue is used
   p.use_tma_store = !p.swap_ab && (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+  static const int dbg_skip = [] { const char* e = getenv("XB_GEMM_DEBUG_SKIP_CONVERT"); return e ? atoi(e) : 0; }();
+  p.debug_skip_convert = dbg_skip;
   if (p.use_tma_store && make_tmap_2d(&tc, p.c, p.M, p.N, (uint64_t)p.ldc * 2, 32, 64, 2)) return 1;
   XB_CUDA_OK(launch_cluster(kern, grid, block, (size_t)Cfg::kSmemBytes, stream, true, kCG, ta, tb, tc, tm ? *tm : ta, p));
   return 0;
