@@ -307,6 +307,7 @@ class Qwen2DecodeRunner:
                 warnings.warn(f"NVLink peer exchange unavailable ({e}); falling back to NCCL all-reduce")
                 self.exchange, self.exchange_mode = None, "nccl (peer exchange unavailable)"
         self.next_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.embed_local = torch.empty(B, weights.embed.size(1), dtype=BF16, device=dev) if weights.embed.size(1) != H else None
         self.plan = ops.DecodePlan(B, self.nh, self.nkv, cfg.head_dim, bs, self.max_pages, dev, early_prefetch=True)
         self.graph = None
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in
@@ -408,6 +409,17 @@ class Qwen2DecodeRunner:
         w.lm_head.forward(self.normed, self.logits_local)
         ops.argmax(self.next_tokens, self.logits)
 
+    def _embed(self):
+        """token embedding into self.hidden; a table sharded along the hidden dimension (word_embedding_impl.cpp:48-56: each
+        rank holds H / tp columns) is looked up locally and all-gathered."""
+        w = self.w
+        if self.pg is not None and w.embed.size(1) != self.cfg.hidden_size:
+            from .parallel import gather
+            ops.embedding(self.embed_local, self.token_ids, w.embed)
+            self.hidden.copy_(gather(self.embed_local, self.pg, dim=-1))
+        else:
+            ops.embedding(self.hidden, self.token_ids, w.embed)
+
     def _launch_step_mlp_norm(self):
         """TP = 1, W4A16, batch <= 8: the shipped step, except that the post-attention add+RMSNorm
         (qwen2_decoder_layer.cpp:89-101) rides in the gate_up GEMV's prologue (every CTA recomputes the 7 KB row); the residual
@@ -443,7 +455,7 @@ class Qwen2DecodeRunner:
             return self._launch_step_fused()
         if self.fuse_mlp_norm and self.pg is None and trace is None:
             return self._launch_step_mlp_norm()
-        ops.embedding(self.hidden, self.token_ids, w.embed)
+        self._embed()
         # apply_norm, first layer (qwen2_decoder_layer.cpp:72-79): the residual stream aliases the embedding output
         self.residual = self.hidden
         ops.rms_norm(self.normed, self.hidden, w.layers[0]["input_norm"], cfg.rms_norm_eps)

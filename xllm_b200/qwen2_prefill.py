@@ -8,9 +8,13 @@ Eager library launches through the C ABI (token counts change every step, so no 
 and the cos/sin table with a Qwen2DecodeRunner, which takes over after the prompt.  Logits are produced for the LAST
 token of every sequence only (the rows the sampler reads).
 
-Status (round 1): the composition is exercised on CPU with the oracle ops swapped in for the library
-(tests/test_prefill_composition_cpu.py); every kernel it launches has its own GPU parity test; the end-to-end GPU test
-(tests/test_gpu_model_prefill.py) is opt-in until its first run on a GPU box.
+Tensor parallel (the reference reduces [T, H] after every row-parallel linear at any T: layers/common/linear.cpp:1518-1520):
+heads / intermediate columns are this rank's shards, o_proj and down_proj outputs are all-reduced over the TP group
+(NCCL: prefill-sized messages) before the add+RMSNorm, the column-parallel lm_head is gathered; an embedding table sharded
+along the hidden dimension (word_embedding_impl.cpp:48-56) is gathered after the lookup.
+
+Composition exercised on CPU with the oracle ops swapped in (tests/test_prefill_composition_cpu.py), end to end on the GPU
+(tests/test_gpu_model_prefill.py) and under TP by tp_check.tp_prefill_parity (tests/test_gpu_tp.py).
 """
 from typing import Optional, Tuple
 
@@ -22,18 +26,22 @@ BF16 = torch.bfloat16
 
 
 class Qwen2PrefillRunner:
-    def __init__(self, cfg, weights, k_caches, v_caches, cos_sin, device="cuda"):
+    def __init__(self, cfg, weights, k_caches, v_caches, cos_sin, device="cuda", pg=None):
         self.cfg, self.w, self.device = cfg, weights, device
         self.k_caches, self.v_caches, self.cos_sin = k_caches, v_caches, cos_sin
-        self.nh, self.nkv = cfg.n_heads, cfg.n_kv_heads
+        self.pg = pg if (pg is not None and pg.world_size > 1) else None
+        tp = self.pg.world_size if self.pg else 1
+        from .parallel import partition_heads
+        hp = partition_heads(cfg.n_heads, cfg.n_kv_heads, self.pg.rank if self.pg else 0, tp)
+        self.nh, self.nkv = hp.num_heads, hp.num_kv_heads
         self.q_size, self.kv_size = self.nh * cfg.head_dim, self.nkv * cfg.head_dim
+        self.inter = cfg.intermediate_size // tp
+        self.tp = tp
 
     @classmethod
     def from_decode_runner(cls, r):
-        """same weights / caches / rope table as the decode runner (single GPU: TP prefill is not wired yet)."""
-        if r.pg is not None:
-            raise NotImplementedError("tensor-parallel prefill runner")
-        return cls(r.cfg, r.w, r.k_caches, r.v_caches, r.cos_sin, r.device)
+        """same weights (this rank's shards) / caches / rope table / TP group as the decode runner."""
+        return cls(r.cfg, r.w, r.k_caches, r.v_caches, r.cos_sin, r.device, pg=r.pg)
 
     def forward(self, token_ids, positions, slots, q_cu_seq_lens, kv_cu_seq_lens=None, paged_kv_indptr=None,
                 paged_kv_indices=None, paged_kv_last_page_len=None, chunked: bool = False,
@@ -61,11 +69,18 @@ class Qwen2PrefillRunner:
         qkv = torch.empty(T, qs + 2 * kvs, dtype=BF16, device=dev)
         qkv_raw = torch.empty_like(qkv) if any(L["qkv"].qkv_rope_packed for L in w.layers) else None
         attn_out = torch.empty(T, qs, dtype=BF16, device=dev)
-        inter = cfg.intermediate_size
+        inter = self.inter
         gate_up = torch.empty(T, 2 * inter, dtype=BF16, device=dev)
         act = torch.empty(T, inter, dtype=BF16, device=dev)
 
-        ops.embedding(hidden, token_ids, w.embed)
+        if self.pg is not None and w.embed.size(1) != H:
+            # embedding sharded along the hidden dimension: local lookup + all-gather (word_embedding_impl.cpp:48-56)
+            from .parallel import gather
+            local = torch.empty(T, w.embed.size(1), dtype=BF16, device=dev)
+            ops.embedding(local, token_ids, w.embed)
+            hidden.copy_(gather(local, self.pg, dim=-1))
+        else:
+            ops.embedding(hidden, token_ids, w.embed)
         residual = hidden                                   # apply_norm, first layer (qwen2_decoder_layer.cpp:72-79)
         ops.rms_norm(normed, hidden, w.layers[0]["input_norm"], cfg.rms_norm_eps)
         h = normed
@@ -89,6 +104,8 @@ class Qwen2PrefillRunner:
                 ops.batch_prefill(q3, k.view(T, self.nkv, D), v.view(T, self.nkv, D), q_cu_seq_lens, kv_cu_seq_lens, scale,
                                   o3, None, max_qo_len, True)
             L["o"].forward(attn_out, buf_a)
+            if self.pg is not None:
+                self.pg.allreduce(buf_a)                      # row-parallel o_proj (linear.cpp:1518-1520)
             ops.fused_add_rms_norm(buf_a, residual, L["post_norm"], cfg.rms_norm_eps)
             gu = L["gate_up"]
             if gu.kind == "w4a16" and gu.gate_up_interleaved:
@@ -97,6 +114,8 @@ class Qwen2PrefillRunner:
                 gu.forward(buf_a, gate_up)
                 ops.act_and_mul(act, gate_up, "silu")
             L["down"].forward(act, buf_b)
+            if self.pg is not None:
+                self.pg.allreduce(buf_b)                      # row-parallel down_proj
             next_w = w.layers[li + 1]["input_norm"] if li + 1 < n_layers else w.final_norm
             ops.fused_add_rms_norm(buf_b, residual, next_w, cfg.rms_norm_eps)
             h = buf_b
@@ -106,7 +125,14 @@ class Qwen2PrefillRunner:
         last = (q_cu_seq_lens[1:].to(torch.int64) - 1)
         h_last = h.index_select(0, last).contiguous()
         logits = torch.empty(B, cfg.vocab_size, dtype=BF16, device=dev)
-        w.lm_head.forward(h_last, logits)
+        if self.pg is not None:
+            # column-parallel lm_head with gather_output (linear.cpp:712-714 -> parallel_state.cpp:89-102)
+            from .parallel import gather
+            local = torch.empty(B, cfg.vocab_size // self.tp, dtype=BF16, device=dev)
+            w.lm_head.forward(h_last, local)
+            logits.copy_(gather(local, self.pg, dim=-1))
+        else:
+            w.lm_head.forward(h_last, logits)
         tokens = torch.zeros(B, dtype=torch.int32, device=dev)
         ops.argmax(tokens, logits)
         return logits, tokens

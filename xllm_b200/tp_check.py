@@ -46,11 +46,17 @@ def logical_weights(cfg: Qwen2Config, seed: int = 2026) -> dict:
     return W
 
 
-def shard_weights(cfg: Qwen2Config, W: dict, rank: int, tp: int, device, fuse_gate_up: bool = True):
-    """this rank's Qwen2Weights (kernel layout, on `device`) from logical W4 weights; tp == 1 gives the full model."""
+def shard_weights(cfg: Qwen2Config, W: dict, rank: int, tp: int, device, fuse_gate_up: bool = True, shard_embedding: bool = False):
+    """this rank's Qwen2Weights (kernel layout, on `device`) from logical W4 weights; tp == 1 gives the full model.
+    shard_embedding: the embedding table is split along the hidden dimension as the reference's WordEmbedding does
+    (LOAD_SHARDED_WEIGHT(weight, 1), word_embedding_impl.cpp:60-64) instead of replicated."""
     hp = P.partition_heads(cfg.n_heads, cfg.n_kv_heads, rank, tp)
     w = Qwen2Weights(cfg)
-    w.embed = W["embed"].to(device)
+    if shard_embedding and tp > 1:
+        hs = cfg.hidden_size // tp
+        w.embed = W["embed"][:, rank * hs:(rank + 1) * hs].contiguous().to(device)
+    else:
+        w.embed = W["embed"].to(device)
     w.final_norm = W["final_norm"].to(device)
     vs = cfg.vocab_size // tp
     w.lm_head = Linear(vs, cfg.hidden_size, "bf16")
@@ -142,3 +148,54 @@ def tp_parity(pg: P.ProcessGroup, device, exchange: str = "peer", kv_lens=(37, 3
     dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=pg.group)
     return {"rel_l2": float(mx[0]), "tokens_equal": bool(mn[1] > 0.5), "ranks_bit_identical": bool(mn[2] > 0.5),
             "exchange": run.exchange_mode, "tp": tp, "config": "3-layer W4A16 stack (H=512, 8/2 heads), batch 3, graph replay"}
+
+
+def tp_prefill_parity(pg: P.ProcessGroup, device, lens=(37, 130, 5), shard_embedding: bool = True) -> dict:
+    """prompt prefill (ragged, first chunk) through the TP-sharded Qwen2PrefillRunner vs the single-GPU runner on the same
+    logical weights: last-token logits, greedy tokens, the KV rows this rank owns, cross-rank bit-identity.  Collective."""
+    from .qwen2_prefill import Qwen2PrefillRunner
+    tp, rank = pg.world_size, pg.rank
+    cfg = tiny_config(tp)
+    W = logical_weights(cfg)
+    lens = list(lens)
+    B, T = len(lens), sum(lens)
+    g = torch.Generator().manual_seed(11)
+    bs = cfg.block_size
+    npg = [(n + bs - 1) // bs for n in lens]
+    nblocks = sum(npg) + 2
+    perm = (torch.randperm(nblocks - 1, generator=g) + 1)[:sum(npg)].tolist()
+    tokens = torch.randint(0, cfg.vocab_size, (T,), generator=g, dtype=torch.int32)
+    positions = torch.cat([torch.arange(n) for n in lens]).to(torch.int64)
+    slots, off = [], 0
+    for b, n in enumerate(lens):
+        for i in range(n):
+            slots.append(perm[off + i // bs] * bs + i % bs)
+        off += npg[b]
+    slots = torch.tensor(slots, dtype=torch.int32)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+
+    def run(w, hp, group):
+        r = Qwen2DecodeRunner(cfg, w, B, max(lens) + 1, device=device, num_blocks=nblocks, pg=group, exchange="nccl")
+        pr = Qwen2PrefillRunner.from_decode_runner(r)
+        logits, toks = pr.forward(tokens.to(device), positions.to(device), slots.to(device), cu.to(device), max_qo_len=max(lens))
+        torch.cuda.synchronize()
+        return logits, toks, r
+    w1, hp1 = shard_weights(cfg, W, 0, 1, device)
+    ref_logits, ref_toks, r1 = run(w1, hp1, None)
+    w, hp = shard_weights(cfg, W, rank, tp, device, shard_embedding=shard_embedding)
+    logits, toks, r = run(w, hp, pg)
+    rel = ((logits.float() - ref_logits.float()).norm() / ref_logits.float().norm()).item()
+    sl = slice(hp.kv_head0, hp.kv_head0 + hp.num_kv_heads)
+    kv_rel = 0.0
+    for li in range(cfg.num_layers):
+        a, b_ = r.k_caches[li].float(), r1.k_caches[li][:, :, sl].float()
+        kv_rel = max(kv_rel, ((a - b_).norm() / b_.norm().clamp_min(1e-9)).item())
+    gathered = [torch.empty_like(logits) for _ in range(tp)]
+    dist.all_gather(gathered, logits, group=pg.group)
+    same = all(torch.equal(gathered[0], t) for t in gathered[1:])
+    flags = torch.tensor([float(rel), float(kv_rel), float(torch.equal(toks, ref_toks)), float(same)], device=device, dtype=torch.float64)
+    mx, mn = flags.clone(), flags.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=pg.group)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=pg.group)
+    return {"rel_l2": float(mx[0]), "kv_rel_l2": float(mx[1]), "tokens_equal": bool(mn[2] > 0.5), "ranks_bit_identical": bool(mn[3] > 0.5),
+            "tp": tp, "sharded_embedding": bool(shard_embedding and tp > 1)}
