@@ -356,6 +356,15 @@ int xb_set_gemm_cta_pair(int mode);
  * N tile (what the reference's M <= 16 / M <= 64 buckets of scaled_mm_sm100_fp8_dispatch.cuh:148-287 do), so a
  * decode-sized batch streams every weight tile on its own CTA.  0 = never.  Returns the old value. */
 int xb_set_fp8_swap_max_m(int max_m);
+/* split-K for the swap-AB FP8 GEMM: a decode-sized GEMM has only N/128 weight tiles (10 for a TP8 qkv shard of Llama-3-70B), so
+ * each tile's K is cut into up to `max_split` ranges walked by different CTAs; fp32 partials meet in a caller-owned workspace
+ * and the last CTA to arrive sums them in split order (bit-reproducible) and runs the epilogue.  Off until a workspace of
+ * xb_gemm_splitk_workspace_bytes() is registered (the library never allocates); the first 4 KB are zeroed by the setter
+ * (cudaMemset: call it outside stream capture) and reset themselves afterwards, so CUDA-graph replays need no memset.
+ * Launches that share the workspace must be stream-ordered.  ws = NULL switches split-K off again. */
+size_t xb_gemm_splitk_workspace_bytes(void);
+int xb_set_gemm_splitk_workspace(void* ws, size_t bytes);
+int xb_set_fp8_splitk_max(int max_split);   /* 1 = never split .. 32; default 8 (XB_FP8_SPLITK_MAX); returns the old value */
 
 /* ---- tensor-parallel exchange over NVLink peer memory (decode-sized messages) ---------------------------------
  * replaces parallel_state::reduce -> ProcessGroup::allreduce (framework/parallel_state/parallel_state.cpp:183-192,

@@ -268,3 +268,41 @@ def test_cutlass_scaled_mm_swap_ab(M, N, K, per_token, per_channel, use_bias, bu
     if bias is not None:
         scale = scale + bias.float().abs()
     assert_close_sum(c, ref, scale, rtol=1e-5, what=f"fp8 swap-AB {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K,per_token,per_channel,use_bias", [(32, 1280, 8192, True, True, True), (17, 8192, 1024, False, True, False),
+                                                                  (64, 7168, 8192, True, False, True), (5, 256, 4736, False, False, False),
+                                                                  (32, 8192, 3584, False, False, False), (1, 128, 28672, True, True, True)])
+def test_cutlass_scaled_mm_swap_ab_split_k(M, N, K, per_token, per_channel, use_bias, built_lib):
+    """swap-AB FP8 GEMM with K cut into ranges over otherwise idle SMs (xb_set_gemm_splitk_workspace): same spec, the same bits
+    on every call (partials are summed in split order; the arrival tickets reset themselves), and back to the unsplit kernel
+    when the workspace is withdrawn."""
+    from xllm_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    a = torch.randn(M, K, generator=g).clamp(-3, 3).to(E4M3)
+    w = torch.randn(N, K, generator=g).clamp(-3, 3).to(E4M3)
+    a_s = (torch.rand(M if per_token else 1, generator=g) * 0.1 + 0.01).float()
+    b_s = (torch.rand(N if per_channel else 1, generator=g) * 0.1 + 0.01).float()
+    bias = torch.randn(N, generator=g).to(BF16) if use_bias else None
+    ref = O.fp8_scaled_matmul(a, w, a_s, b_s, bias)
+    ad, wd, asd, bsd = a.to(DEV), w.to(DEV), a_s.to(DEV), b_s.to(DEV)
+    bd = bias.to(DEV) if bias is not None else None
+    outs = []
+    ops.enable_fp8_splitk(DEV)
+    try:
+        for _ in range(3):
+            c = torch.zeros(M, N, dtype=BF16, device=DEV)
+            ops.gemm_fp8_scaled(c, ad, wd, asd, bsd, bd)
+            torch.cuda.synchronize()
+            outs.append(c.cpu())
+    finally:
+        ops.disable_fp8_splitk()
+    c1 = torch.zeros(M, N, dtype=BF16, device=DEV)
+    ops.gemm_fp8_scaled(c1, ad, wd, asd, bsd, bd)
+    torch.cuda.synchronize()
+    scale = (a.float().abs() @ w.float().abs().t()) * a_s.reshape(-1, 1) * b_s.reshape(1, -1)
+    if bias is not None:
+        scale = scale + bias.float().abs()
+    assert_close_sum(outs[0], ref, scale, rtol=1e-5, what=f"fp8 swap-AB split-K {M}x{N}x{K}")
+    assert_close_sum(c1, ref, scale, rtol=1e-5, what=f"fp8 swap-AB unsplit {M}x{N}x{K}")
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]), "split-K result changed between calls"

@@ -97,6 +97,14 @@ struct GemmParams {
   // swapped roles (M = output channels, N = tokens, a_scale per channel, b_scale per token); the epilogue indexes bias by
   // row, keeps the reference's product order token_scale * (channel_scale * acc) and stores C transposed: c[col][row]
   int swap_ab;
+  // split-K (swap-AB FP8 only): a decode-sized GEMM has N/128 tiles - 10 for a TP8 qkv shard - so most SMs would idle while a
+  // few CTAs stream all of K.  Each output tile is cut into split_k k-ranges walked by different CTAs; every CTA leaves its
+  // fp32 partial in splitk_ws, takes a ticket (self-resetting atomicInc, so graph replays need no memset), and the LAST
+  // arriver sums the partials in split order (deterministic) and runs the epilogue.  Nobody waits, so no co-residency
+  // requirement.  Workspace: caller-owned (xb_set_gemm_splitk_workspace).
+  int split_k;
+  float* splitk_ws;            // [tiles][split_k][kBlockN][128] fp32
+  unsigned int* splitk_tickets;  // [tiles], zero at rest
   int debug_skip_convert;      // XB_GEMM_DEBUG_SKIP_CONVERT=1 (timing diagnosis only, results are garbage): converters only hand the stage over
 };
 
@@ -175,8 +183,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int unit_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int m_blocks = (p.M + Cfg::kCtaM * kCG - 1) / (Cfg::kCtaM * kCG);
   const int n_blocks = (p.N + kBlockN - 1) / kBlockN;
-  const int num_tiles = m_blocks * n_blocks;
   const int num_kb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;
+  // split-K exists in the swap-AB FP8 instantiations only (compile-time off elsewhere: no extra registers in the big tiles)
+  constexpr bool kSplitOK = kKind == kKindFP8 && kBlockN <= 64 && kCG == 1 && kMT == 1;
+  const int split_k = kSplitOK ? p.split_k : 1;
+  const int kb_per = (num_kb + split_k - 1) / split_k;
+  const int num_tiles = m_blocks * n_blocks * split_k;      // work units: (output tile, k range); the splits of a tile are adjacent
 
   auto stage_a = [&](int s) { return smem + s * Cfg::kStageBytes; };
   auto stage_b = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes; };               // BF16 / FP8
@@ -229,10 +241,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int s = 0;
       uint32_t ph = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
-        const int m_blk = tile % m_blocks, n_blk = tile / m_blocks;
+        const int otile = tile / split_k, ks = tile - otile * split_k;
+        const int m_blk = otile % m_blocks, n_blk = otile / m_blocks;
         const int a_row = (m_blk * kCG + (int)rank) * Cfg::kCtaM;           // this CTA's 128 (x kMT) rows of A
         const int b_row = n_blk * kBlockN + (int)rank * Cfg::kCtaN;         // this CTA's share of the B rows
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1);
           if (kind_is_wq(kKind)) {
             // packed B: the kCtaN/16 row tiles of this k tile are one 2-D TMA box (tensor [N/16][K/64 * 128 words],
@@ -279,7 +293,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(tmem_empty + as, aph ^ 1);     // epilogue has drained this accumulator stage
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + as * Cfg::kAccCols;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int ks = tile % split_k;
+      const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar + s, ph);
         if (kind_is_wq(kKind)) mbar_wait(bready_bar + bs, bph);
         tc_fence_after_sync();
@@ -294,20 +310,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               const uint64_t da = umma_desc_sw128(a_addr + mt * (kBlockM * 128) + k * 32);
               if (kPair) {
                 // M = 256 over the pair: the same shared-memory offsets address this CTA's and the peer's A rows / B rows
-                if (kKind == kKindFP8) umma_f8_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
-                else umma_f16_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
-              } else if (kKind == kKindFP8) umma_f8(d_tmem + mt * kBlockN, da, db, idesc, (kb | k) != 0);
-              else umma_f16(d_tmem + mt * kBlockN, da, db, idesc, (kb | k) != 0);
+                if (kKind == kKindFP8) umma_f8_cg2(d_tmem, da, db, idesc, ((kb - kb0) | k) != 0);
+                else umma_f16_cg2(d_tmem, da, db, idesc, ((kb - kb0) | k) != 0);
+              } else if (kKind == kKindFP8) umma_f8(d_tmem + mt * kBlockN, da, db, idesc, ((kb - kb0) | k) != 0);
+              else umma_f16(d_tmem + mt * kBlockN, da, db, idesc, ((kb - kb0) | k) != 0);
             }
           }
           if (kPair) {
             umma_commit_cg2(empty_bar + s);            // multicast: both CTAs' producers may refill the slot
             if (kind_is_wq(kKind)) umma_commit_cg2(bempty_bar + bs);
-            if (kb == num_kb - 1) umma_commit_cg2(tmem_full + as);
+            if (kb == kb1 - 1) umma_commit_cg2(tmem_full + as);
           } else {
             umma_commit(empty_bar + s);                 // smem slot is free once these MMAs have read it
             if (kind_is_wq(kKind)) umma_commit(bempty_bar + bs);
-            if (kb == num_kb - 1) umma_commit(tmem_full + as);
+            if (kb == kb1 - 1) umma_commit(tmem_full + as);
           }
         }
         __syncwarp();
@@ -328,9 +344,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int as = 0;
     uint32_t aph = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
-      const int m_blk = tile % m_blocks, n_blk = tile / m_blocks;
+      const int otile = tile / split_k;
+      const int m_blk = otile % m_blocks, n_blk = otile / m_blocks;
       mbar_wait(tmem_full + as, aph);
       tc_fence_after_sync();
+      bool reduce_here = false;          // split-K: this CTA arrived last and owns the tile's epilogue
+      const float* ws_tile = nullptr;
+      if (kSplitOK && split_k > 1) {
+        // leave this k range's fp32 partial in the workspace: [split][column][row] so a warp writes 128 contiguous bytes
+        const int ks = tile - otile * split_k;
+        float* wp = p.splitk_ws + ((size_t)otile * split_k + ks) * (kBlockN * kBlockM) + q * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < kBlockN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::kAccCols + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(wp + (c * 32 + j) * kBlockM, __uint_as_float(r[j]));
+        }
+        __threadfence();
+        volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(epi_stage);
+        asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+        if (ew == 0 && lane == 0) *flag = atomicInc(p.splitk_tickets + otile, (unsigned)split_k - 1u);
+        asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+        reduce_here = *flag == (uint32_t)split_k - 1u;
+        if (reduce_here) {
+          __threadfence();
+          ws_tile = p.splitk_ws + (size_t)otile * split_k * (kBlockN * kBlockM) + q * 32 + lane;
+        }
+      }
+      if (!(kSplitOK && split_k > 1) || reduce_here) {
 #pragma unroll 1
       for (int mt = 0; mt < kMT; ++mt) {
       const int row0 = (m_blk * kCG + (int)rank) * Cfg::kCtaM + mt * kBlockM + q * 32;
@@ -343,8 +386,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
       for (int c = 0; c < kBlockN / 32; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::kAccCols + mt * kBlockN + c * 32, r);
-        tmem_ld_wait();
+        if (kSplitOK && split_k > 1) {
+          // sum the partials in split order (the same order whichever CTA arrived last: bit-reproducible)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__ldcg(ws_tile + (c * 32 + j) * kBlockM));
+#pragma unroll 1
+          for (int sp = 1; sp < split_k; ++sp) {
+            const float* wsp = ws_tile + (size_t)sp * (kBlockN * kBlockM);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldcg(wsp + (c * 32 + j) * kBlockM));
+          }
+        } else {
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::kAccCols + mt * kBlockN + c * 32, r);
+          tmem_ld_wait();
+        }
         const int col0 = n_blk * kBlockN + c * 32;
         uint32_t o[16];
 #pragma unroll
@@ -422,6 +477,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(o);
           for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = ob[j];
         }
+      }
       }
       }
       tc_fence_before_sync();
@@ -556,7 +612,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
     }
     attr_done = true;
   }
-  const int units = ((p.M + Cfg::kCtaM * kCG - 1) / (Cfg::kCtaM * kCG)) * ((p.N + kBlockN - 1) / kBlockN);
+  const int units = ((p.M + Cfg::kCtaM * kCG - 1) / (Cfg::kCtaM * kCG)) * ((p.N + kBlockN - 1) / kBlockN) * (p.split_k > 1 ? p.split_k : 1);
+  if (p.split_k < 1) p.split_k = 1;
   const int want = units * kCG;
   dim3 grid(want < max_ctas ? want : max_ctas), block(Cfg::kThreads);
   CUtensorMap tc = ta;   // placeholder when the direct-store epilogue is used
@@ -636,6 +693,70 @@ static int pair_block_n(int M, int N) {
   return eff(224) > eff(256) ? 224 : 256;
 }
 
+// split-K workspace of the swap-AB FP8 GEMM (caller-owned device memory; every split-K launch uses it, so launches that share
+// it must be stream-ordered - the decode step's are).  Layout: 4 KB of tickets (zeroed here, self-resetting afterwards), then
+// the fp32 partials.
+static std::atomic<void*> g_splitk_ws{nullptr};
+static std::atomic<size_t> g_splitk_bytes{0};
+static std::atomic<int> g_splitk_max{-1};
+constexpr size_t kSplitKTicketBytes = 4096;
+static int splitk_max() {
+  int v = g_splitk_max.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("XB_FP8_SPLITK_MAX");
+    v = e ? atoi(e) : 8;
+    if (v < 1 || v > 32) v = 8;
+    g_splitk_max.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+// k ranges for `tiles` output tiles over `num_kb` k blocks: fill the SMs once (tiles * split <= sm_count), keep >= 12 k blocks
+// per range and no empty range.  Measured on B200 at M = 32 (tools/fp8_splitk_probe.py, profiles/r02i_fp8_splitk.md): ranges of
+// 4 / 8 k blocks LOSE (o_proj TP8 shard, K = 1024: 7.3 -> 8.7 us; TP4, K = 2048: 9.9 -> 10.2 us - ring fill + the ticket round
+// trip outweigh the extra CTAs), 14 and more win (down TP8 13.3 -> 12.1 us, qkv TP8 22.5 -> 11.8 us, down unsharded 70 -> 46 us)
+static int pick_split_k(int tiles, int num_kb, int tokens_bn, size_t* need_bytes) {
+  *need_bytes = 0;
+  if (g_splitk_ws.load(std::memory_order_relaxed) == nullptr) return 1;
+  static int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+  int split = sms / tiles;
+  if (split > splitk_max()) split = splitk_max();
+  if (split > num_kb / 12) split = num_kb / 12;
+  if (split < 2) return 1;
+  const int kb_per = (num_kb + split - 1) / split;
+  split = (num_kb + kb_per - 1) / kb_per;
+  if (split < 2) return 1;
+  const size_t need = kSplitKTicketBytes + (size_t)tiles * split * tokens_bn * kBlockM * sizeof(float);
+  if ((size_t)tiles * sizeof(unsigned) > kSplitKTicketBytes || need > g_splitk_bytes.load(std::memory_order_relaxed)) return 1;
+  *need_bytes = need;
+  return split;
+}
+
+extern "C" size_t xb_gemm_splitk_workspace_bytes(void) {
+  // one wave of 148 CTAs x the largest token tile (64) is the most the heuristic ever asks for
+  return kSplitKTicketBytes + (size_t)148 * 64 * kBlockM * sizeof(float);
+}
+
+extern "C" int xb_set_gemm_splitk_workspace(void* ws, size_t bytes) {
+  if (ws != nullptr && (bytes <= kSplitKTicketBytes || (reinterpret_cast<uintptr_t>(ws) & 15) != 0)) {
+    set_error("set_gemm_splitk_workspace: need a 16-byte aligned buffer of more than %zu bytes", kSplitKTicketBytes);
+    return -1;
+  }
+  if (ws != nullptr) XB_CUDA_OK(cudaMemset(ws, 0, kSplitKTicketBytes));
+  g_splitk_ws.store(ws, std::memory_order_relaxed);
+  g_splitk_bytes.store(ws ? bytes : 0, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int xb_set_fp8_splitk_max(int max_split) {
+  if (max_split < 1 || max_split > 32) {
+    set_error("set_fp8_splitk_max: %d out of range (1 = never split .. 32)", max_split);
+    return -1;
+  }
+  const int old = splitk_max();
+  g_splitk_max.store(max_split, std::memory_order_relaxed);
+  return old;
+}
+
 extern "C" int xb_set_fp8_swap_max_m(int max_m) {
   if (max_m < 0 || max_m > 64) {
     set_error("set_fp8_swap_max_m: %d out of range (0 = never swap .. 64)", max_m);
@@ -702,6 +823,16 @@ extern "C" int xb_gemm_fp8_scaled(void* c, int64_t ldc, const void* a, int64_t l
     p.M = N; p.N = M;
     p.a_scale = b_scale; p.b_scale = a_scale;          // per-row = channel scales, per-column = token scales
     p.a_scale_per_row = b_scale_numel > 1; p.b_scale_per_col = a_scale_numel > 1;
+    {
+      size_t need = 0;
+      const int split = pick_split_k((N + kBlockM - 1) / kBlockM, (K + 127) / 128, M <= 32 ? 32 : 64, &need);
+      if (split > 1) {
+        uint8_t* ws = static_cast<uint8_t*>(g_splitk_ws.load(std::memory_order_relaxed));
+        p.split_k = split;
+        p.splitk_tickets = reinterpret_cast<unsigned int*>(ws);
+        p.splitk_ws = reinterpret_cast<float*>(ws + kSplitKTicketBytes);
+      }
+    }
     CUtensorMap tw, tx;
     if (make_tmap_2d(&tw, b, N, K, (uint64_t)K, kBlockM, 128, 1)) return 1;
     if (M <= 32) {

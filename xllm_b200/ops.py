@@ -328,6 +328,35 @@ def set_fp8_swap_max_m(max_m: int) -> int:
     return int(lib().xb_set_fp8_swap_max_m(c_i32(max_m)))
 
 
+_splitk_ws = None
+
+
+def enable_fp8_splitk(device=None) -> None:
+    """register a split-K workspace for the decode-sized (swap-AB) FP8 GEMMs (xb_set_gemm_splitk_workspace); idempotent.  The
+    buffer lives as long as the process (the library keeps the pointer)."""
+    global _splitk_ws
+    if _splitk_ws is not None:
+        return
+    import ctypes
+    L = lib()
+    L.xb_gemm_splitk_workspace_bytes.restype = ctypes.c_size_t
+    n = int(L.xb_gemm_splitk_workspace_bytes())
+    ws = torch.empty(n, dtype=torch.uint8, device=device if device is not None else torch.cuda.current_device())
+    check(L.xb_set_gemm_splitk_workspace(_p(ws), ctypes.c_size_t(n)), "set_gemm_splitk_workspace")
+    _splitk_ws = ws
+
+
+def disable_fp8_splitk() -> None:
+    global _splitk_ws
+    import ctypes
+    check(lib().xb_set_gemm_splitk_workspace(None, ctypes.c_size_t(0)), "set_gemm_splitk_workspace")
+    _splitk_ws = None
+
+
+def set_fp8_splitk_max(max_split: int) -> int:
+    return int(lib().xb_set_fp8_splitk_max(c_i32(max_split)))
+
+
 def gemm_fp8_scaled(c, a, w, a_scales, b_scales, bias=None) -> None:
     """the tcgen05 FP8 kernel directly (no small-M dispatch): a [M,K] e4m3, w [N,K] e4m3 (the reference's weight layout)."""
     M, K = a.shape

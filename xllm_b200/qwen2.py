@@ -14,6 +14,8 @@ triplet) are exactly the reference's ForwardInput integers
 from dataclasses import dataclass
 from typing import List, Optional
 
+import os
+
 import torch
 
 from . import ops, quant
@@ -307,6 +309,9 @@ class Qwen2DecodeRunner:
                 warnings.warn(f"NVLink peer exchange unavailable ({e}); falling back to NCCL all-reduce")
                 self.exchange, self.exchange_mode = None, "nccl (peer exchange unavailable)"
         self.next_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
+        if cfg.quant == "fp8" and os.environ.get("XB_FP8_SPLITK", "1") != "0":
+            # decode-sized FP8 linears: K split over otherwise idle SMs (shard-sized N leaves 10-64 weight tiles for 148 SMs)
+            ops.enable_fp8_splitk(dev)
         self.embed_local = torch.empty(B, weights.embed.size(1), dtype=BF16, device=dev) if weights.embed.size(1) != H else None
         self.plan = ops.DecodePlan(B, self.nh, self.nkv, cfg.head_dim, bs, self.max_pages, dev, early_prefetch=True)
         self.graph = None
