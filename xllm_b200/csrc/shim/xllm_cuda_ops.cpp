@@ -8,6 +8,7 @@
 // cutlass_w8a8/, and link libxllm_b200_ops.so.  Attention is served through the TVM-FFI modules
 // (csrc/ffi/tvm_ffi_modules.cc), which needs no source change in xLLM at all.
 #include <ATen/cuda/CUDAContext.h>
+#include <ATen/cuda/CUDAGraphsUtils.cuh>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/torch.h>
 
@@ -164,6 +165,17 @@ void cutlass_scaled_mm(torch::Tensor& c, torch::Tensor const& a, torch::Tensor c
   TORCH_CHECK(a.scalar_type() == torch::kFloat8_e4m3fn && b.scalar_type() == torch::kFloat8_e4m3fn, "fp8 e4m3 inputs expected");
   TORCH_CHECK(c.scalar_type() == torch::kBFloat16, "only bfloat16 output is implemented");
   const at::cuda::OptionalCUDAGuard guard(device_of(a));
+  {
+    // split-K workspace of the decode-sized GEMM: owned here, registered once per process (xLLM runs one process per GPU) on
+    // the first call that is not inside a stream capture (the setter clears the ticket words with a synchronous memset)
+    static torch::Tensor splitk_ws;
+    if (!splitk_ws.defined() && a.size(0) <= 64 &&
+        at::cuda::currentStreamCaptureStatus() == at::cuda::CaptureStatus::None) {
+      const auto bytes = (int64_t)xb_gemm_splitk_workspace_bytes();
+      splitk_ws = torch::empty({bytes}, torch::TensorOptions().dtype(torch::kUInt8).device(a.device()));
+      ok(xb_set_gemm_splitk_workspace(splitk_ws.data_ptr(), (size_t)bytes), "cutlass_scaled_mm (split-K workspace)");
+    }
+  }
   if (a.size(0) <= 8 && b.size(1) <= 16384 && a.size(1) % 64 == 0) {
     // decode on a narrow projection: the HBM-streaming swap-AB kernel (the reference's small-M buckets,
     // c3x/scaled_mm_sm100_fp8_dispatch.cuh:148-287); measured crossover in xllm_b200/ops.py
