@@ -67,21 +67,30 @@ class Qwen2AttentionOracle:
 
 
 class Qwen2DecoderLayerOracle:
-    """qwen2_decoder_layer.cpp:89-112 with plain (non-fp8) norms."""
+    """qwen2_decoder_layer.cpp:89-112.  pre_fp8_scale / post_fp8_scale: the static input scales of qkv_proj / gate_up_proj of an
+    FP8 checkpoint (get_fp8_input_scale, qwen2_attention.cpp:204-209 / dense_mlp.cpp:137-142): apply_norm (:64-84) then takes
+    RMSNormImpl::forward_fp8 (rms_norm.cpp:94-128) and hands e4m3 activations to the linear, which skips its own quantisation
+    (linear.cpp:150-157).  None = plain norms."""
 
     def __init__(self, attn: Qwen2AttentionOracle, input_norm_w, post_norm_w, eps, gate_up, down,
-                 linear: Callable = ops.linear):
+                 linear: Callable = ops.linear, pre_fp8_scale=None, post_fp8_scale=None):
         self.attn, self.in_w, self.post_w, self.eps = attn, input_norm_w, post_norm_w, eps
         self.gate_up, self.down = gate_up, down      # callables x -> y
         self.linear = linear
+        self.pre_s, self.post_s = pre_fp8_scale, post_fp8_scale
+
+    def _apply_norm(self, x, residual, w, scale):
+        vec = x.shape[-1] % 8 == 0                                        # norm.cu:283-345 width-8 path vs :350-396
+        if residual is None:                                              # apply_norm :72-79
+            h = ops.rms_norm(x, w, self.eps) if scale is None else ops.rms_norm_static_fp8_quant(x, w, scale, self.eps)
+            return h, x
+        if scale is None:
+            return ops.fused_add_rms_norm(x, residual, w, self.eps)
+        return ops.fused_add_rms_norm_static_fp8_quant(x, residual, w, scale, self.eps, vectorized=vec)
 
     def forward(self, x, residual, positions, meta, k_cache, v_cache):
-        if residual is None:                                              # apply_norm :72-79
-            residual = x
-            h = ops.rms_norm(x, self.in_w, self.eps)
-        else:
-            h, residual = ops.fused_add_rms_norm(x, residual, self.in_w, self.eps)
+        h, residual = self._apply_norm(x, residual, self.in_w, self.pre_s)
         h = self.attn.forward(positions, h, meta, k_cache, v_cache)
-        h, residual = ops.fused_add_rms_norm(h, residual, self.post_w, self.eps)
+        h, residual = self._apply_norm(h, residual, self.post_w, self.post_s)
         h = self.down(ops.act_and_mul(self.gate_up(h), "silu"))           # dense_mlp.cpp:97-118
         return h, residual

@@ -63,8 +63,9 @@ def _olin(d):
     return lambda x, _w=None, b=None: O.linear(x, d["w"], d["b"])
 
 
-def oracle_step(cfg, W, kcs, vcs, meta):
-    """reference composition on CPU: returns (logits bf16 [B, vocab], next tokens)."""
+def oracle_step(cfg, W, kcs, vcs, meta, fp8_norm_quant=False, trace=None):
+    """reference composition on CPU: returns (logits bf16 [B, vocab], next tokens).  fp8_norm_quant: the norms in front of
+    qkv_proj / gate_up_proj emit e4m3 with those linears' static input scales (the reference's apply_norm for FP8 checkpoints)."""
     B = len(meta["tokens"])
     cs = O.compute_cos_sin_cache(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, BF16)
     positions = torch.tensor(meta["positions"])
@@ -76,9 +77,14 @@ def oracle_step(cfg, W, kcs, vcs, meta):
     for li, L in enumerate(W["layers"]):
         attn = OL.Qwen2AttentionOracle(None, None, None, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cs,
                                        linear=_olin(L["qkv"]), o_linear=_olin(L["o"]))
+        nq = fp8_norm_quant and "in_scale" in L["qkv"]
         dl = OL.Qwen2DecoderLayerOracle(attn, L["input_norm"], L["post_norm"], cfg.rms_norm_eps,
-                                        _olin(L["gate_up"]), _olin(L["down"]))
+                                        _olin(L["gate_up"]), _olin(L["down"]),
+                                        pre_fp8_scale=L["qkv"]["in_scale"] if nq else None,
+                                        post_fp8_scale=L["gate_up"]["in_scale"] if nq else None)
         x, residual = dl.forward(x, residual, positions, am, kcs[li], vcs[li])
+        if trace is not None:
+            trace.append((x, residual))          # (MLP output, residual stream before it is added)
     x, _ = O.fused_add_rms_norm(x, residual, W["final_norm"], cfg.rms_norm_eps)
     logits = O.linear(x, W["lm_head"])
     return logits, logits.to(torch.float32).argmax(-1)
@@ -149,13 +155,15 @@ def upload(cfg, W, device="cuda"):
     return w
 
 
-def run_decode_parity(cfg, kv_lens, use_graph=True, fused=True, seed=2026, fuse_gemv=False):
-    """returns (max bf16-ulp distance of logits, tokens equal?)."""
+def run_decode_parity(cfg, kv_lens, use_graph=True, fused=True, seed=2026, fuse_gemv=False, fp8_norm_quant=None):
+    """returns (logits, oracle logits, tokens, oracle tokens, runner, caches).  fp8_norm_quant: None = the runner's default."""
     from xllm_b200.qwen2 import Qwen2DecodeRunner
     B = len(kv_lens)
     W, kcs, vcs, meta = build_case(cfg, B, kv_lens, seed)
     runner = Qwen2DecodeRunner(cfg, upload(cfg, W), B, max(kv_lens), num_blocks=meta["nblocks"], fused_rope_cache=fused,
                                fuse_gemv=fuse_gemv)
+    if fp8_norm_quant is not None:
+        runner.fp8_norm_quant = bool(fp8_norm_quant)
     for li in range(cfg.num_layers):
         runner.k_caches[li].copy_(kcs[li])
         runner.v_caches[li].copy_(vcs[li])
@@ -168,7 +176,7 @@ def run_decode_parity(cfg, kv_lens, use_graph=True, fused=True, seed=2026, fuse_
         runner.capture()
     nxt = runner.step().clone()
     logits = runner.logits.cpu()
-    ref_logits, ref_next = oracle_step(cfg, W, kcs, vcs, meta)
+    ref_logits, ref_next = oracle_step(cfg, W, kcs, vcs, meta, fp8_norm_quant=runner.fp8_norm_quant)
     # KV caches after the step: the new token's rotated K and V must have been scattered bit-exactly
     # (same qkv GEMM inputs -> within tolerance; compare the untouched part exactly)
     return logits, ref_logits, nxt, ref_next, runner, (kcs, vcs)

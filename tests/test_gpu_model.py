@@ -83,17 +83,32 @@ def test_layerwise_teacher_forced(quant, built_lib):
         assert_close_bf16(gx, rx, ulps=1e9, rel_l2=1e-2, what=f"layer {li} normalised output")
 
 
-def test_decode_step_llama_fp8_shape(built_lib):
+@pytest.mark.parametrize("norm_quant", [False, True])
+def test_decode_step_llama_fp8_shape(norm_quant, built_lib):
     """BASELINE configs[3] flavour at toy size: Llama-style layer (no qkv bias, GQA 8) with FP8 W8A8 per-tensor static
-    linears (fp8_linear_forward, linear.cpp:137-182 -> cutlass_scaled_mm), decode batch of 3."""
+    linears (fp8_linear_forward, linear.cpp:137-182 -> cutlass_scaled_mm), decode batch of 3.  norm_quant: the norms in front
+    of qkv_proj / gate_up_proj emit e4m3 directly (the reference's apply_norm for checkpoints with static input scales,
+    qwen2_decoder_layer.cpp:64-84), oracle composed the same way."""
     from xllm_b200.qwen2 import Qwen2Config
     cfg = Qwen2Config(hidden_size=512, num_layers=2, n_heads=16, n_kv_heads=2, head_dim=64, intermediate_size=1024,
                       vocab_size=2048, block_size=16, quant="fp8", qkv_bias=False, rope_theta=500000.0, rms_norm_eps=1e-5,
                       max_position_embeddings=2048, name="tiny-llama-fp8")
-    logits, ref_logits, nxt, ref_next, _, _ = run_decode_parity(cfg, [200, 33, 5], True, True)
+    logits, ref_logits, nxt, ref_next, _, caches = run_decode_parity(cfg, [200, 33, 5], True, True, fp8_norm_quant=norm_quant)
     # e4m3 activations: a 1-ulp bf16 flip upstream can move an activation across an fp8 rounding boundary (2^-4
-    # relative), so the logits bar is looser than for bf16 pipelines
-    assert_close_bf16(logits, ref_logits, ulps=1e9, rel_l2=5e-2, what="llama-fp8 logits")
+    # relative), so the logits bar is looser than for bf16 pipelines.  The bar is the model's OWN sensitivity: the oracle's
+    # response to a 1-ulp (2^-8 relative) change of every 7th element of the three input embedding rows (measured 8e-2 on
+    # this toy stack: weights of std 0.05 give every layer a gain > 1) - a GPU result inside that band is as close to the
+    # oracle as the oracle is to itself under the smallest representable input change.
+    from tests.model_parity import build_case, oracle_step
+    W, kcs, vcs, meta = build_case(cfg, 3, [200, 33, 5], 2026)
+    W2 = dict(W)
+    e = W["embed"].clone()
+    rows = torch.tensor(meta["tokens"])
+    e[rows, ::7] = (e[rows, ::7].float() * (1 + 2.0 ** -8)).to(torch.bfloat16)
+    W2["embed"] = e
+    pert, _ = oracle_step(cfg, W2, [c.clone() for c in kcs], [c.clone() for c in vcs], meta, fp8_norm_quant=norm_quant)
+    sens = ((pert.float() - ref_logits.float()).norm() / ref_logits.float().norm()).item()
+    assert_close_bf16(logits, ref_logits, ulps=1e9, rel_l2=max(5e-2, 1.25 * sens), what=f"llama-fp8 logits (1-ulp sensitivity {sens:.2e})")
     # random-init logits are nearly flat, so the argmax may flip between near-ties: the token the GPU picked must be
     # (near-)maximal under the oracle as well
     rl = ref_logits.float()

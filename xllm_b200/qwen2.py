@@ -106,6 +106,12 @@ class Linear:
         (linear.cpp:137-182): quantise the activation (static scale if present) then the scaled matmul."""
         if self.kind == "bf16":
             ops.matmul(x, self.weight, self.bias, out)
+        elif self.kind == "fp8" and x.dtype == torch.float8_e4m3fn:
+            # already quantised by the norm in front (RMSNormImpl::forward_fp8): fp8_linear_forward skips its own
+            # quantisation and uses input_scale directly (linear.cpp:150-157)
+            if self.input_scale is None:
+                raise ValueError("input_scale must be provided when input is already FP8")
+            ops.fp8_scaled_matmul(x, self.weight, self.input_scale, self.weight_scale, BF16, self.bias, out)
         elif self.kind == "fp8":
             if self._x8 is None or self._x8.shape != x.shape:
                 self._x8 = torch.empty(x.shape, dtype=torch.float8_e4m3fn, device=x.device)
@@ -309,6 +315,11 @@ class Qwen2DecodeRunner:
                 warnings.warn(f"NVLink peer exchange unavailable ({e}); falling back to NCCL all-reduce")
                 self.exchange, self.exchange_mode = None, "nccl (peer exchange unavailable)"
         self.next_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
+        # norm + static FP8 quantisation in one kernel where the consumer is an FP8 linear with a static input scale (the
+        # reference's composition for such checkpoints).  Not under the one-shot NVLink exchange, whose fused add+norm emits bf16.
+        self.fp8_norm_quant = (cfg.quant == "fp8" and os.environ.get("XB_FP8_NORM_QUANT", "1") != "0" and
+                               all(L[k].input_scale is not None for L in weights.layers for k in ("qkv", "gate_up")))
+        self.normed8 = torch.empty(B, H, dtype=torch.float8_e4m3fn, device=dev) if cfg.quant == "fp8" else None
         if cfg.quant == "fp8" and os.environ.get("XB_FP8_SPLITK", "1") != "0":
             # decode-sized FP8 linears: K split over otherwise idle SMs (shard-sized N leaves 10-64 weight tiles for 148 SMs)
             ops.enable_fp8_splitk(dev)
@@ -321,14 +332,22 @@ class Qwen2DecodeRunner:
         self.d2h_bytes = self.h_next.numel() * 4
 
     # -- one decode step worth of launches (capturable) -----------------------------------
-    def _row_parallel(self, lin, x, which, norm_w, out):
+    def _row_parallel(self, lin, x, which, norm_w, out, fp8_scale=None):
         """row-parallel linear + exchange + the fused add+RMSNorm that follows it in the layer
-        (linear.cpp:1405-1522 + qwen2_decoder_layer.cpp:103-109).  Returns the normalised activations."""
+        (linear.cpp:1405-1522 + qwen2_decoder_layer.cpp:103-109).  Returns the normalised activations.  fp8_scale: static
+        input scale of the linear that consumes them - the norm then emits e4m3 directly, as the reference's apply_norm does
+        for FP8 checkpoints (qwen2_decoder_layer.cpp:64-84 -> RMSNormImpl::forward_fp8, rms_norm.cpp:94-128)."""
         cfg = self.cfg
-        if self.pg is None:
-            lin.forward(x, out)
+
+        def add_norm():
+            if fp8_scale is not None:
+                ops.fused_add_rms_norm_static_fp8_quant(self.normed8, out, self.residual, norm_w, fp8_scale, cfg.rms_norm_eps)
+                return self.normed8
             ops.fused_add_rms_norm(out, self.residual, norm_w, cfg.rms_norm_eps)
             return out
+        if self.pg is None:
+            lin.forward(x, out)
+            return add_norm()
         if self.exchange is not None and x.size(0) <= self.exchange.MAX_CTAS:
             part = self.exchange.partial_buffer(which, x.size(0))
             lin.forward(x, part)                                    # partial straight into the symmetric buffer
@@ -336,8 +355,7 @@ class Qwen2DecodeRunner:
             return out
         lin.forward(x, out)
         self.pg.allreduce(out)                                      # NCCL baseline
-        ops.fused_add_rms_norm(out, self.residual, norm_w, cfg.rms_norm_eps)
-        return out
+        return add_norm()
 
     def _qkv_and_rope(self, L, li, h, norm_w=None, res_in=None, res_out=None, stats_in=None):
         """qkv_proj + RoPE + KV scatter of layer li (qwen2_attention.cpp:147-176, flashinfer_attention.cpp:128-131);
@@ -463,14 +481,25 @@ class Qwen2DecodeRunner:
         self._embed()
         # apply_norm, first layer (qwen2_decoder_layer.cpp:72-79): the residual stream aliases the embedding output
         self.residual = self.hidden
-        ops.rms_norm(self.normed, self.hidden, w.layers[0]["input_norm"], cfg.rms_norm_eps)
-        h = self.normed
+        # FP8 checkpoints with static activation scales: every norm in front of a quantised linear emits e4m3 with that
+        # linear's input scale (get_fp8_input_scale: qwen2_attention.cpp:204-209, dense_mlp.cpp:137-142)
+        nq = self.fp8_norm_quant
+
+        def in_scale(lin):
+            return lin.input_scale if (nq and lin.kind == "fp8") else None
+        if in_scale(w.layers[0]["qkv"]) is not None:
+            ops.rms_norm_static_fp8_quant(self.normed8, self.hidden, w.layers[0]["input_norm"], w.layers[0]["qkv"].input_scale,
+                                          cfg.rms_norm_eps)
+            h = self.normed8
+        else:
+            ops.rms_norm(self.normed, self.hidden, w.layers[0]["input_norm"], cfg.rms_norm_eps)
+            h = self.normed
         n_layers = len(w.layers)
         for li, L in enumerate(w.layers):
             self._qkv_and_rope(L, li, h)
             self._attention(li)
             # o_proj (+ all-reduce) + post-attention add+norm
-            h = self._row_parallel(L["o"], self.attn_out, 0, L["post_norm"], self.buf_a)
+            h = self._row_parallel(L["o"], self.attn_out, 0, L["post_norm"], self.buf_a, in_scale(L["gate_up"]))
             gu = L["gate_up"]
             if gu.kind == "w4a16" and gu.gate_up_interleaved:
                 # gate_up GEMV with SiLU*mul in its epilogue (one launch instead of two)
@@ -480,7 +509,8 @@ class Qwen2DecodeRunner:
                 ops.act_and_mul(self.act, self.gate_up, "silu")
             # down_proj (+ all-reduce) + the NEXT layer's input add+norm (or the final norm)
             next_w = w.layers[li + 1]["input_norm"] if li + 1 < n_layers else w.final_norm
-            h = self._row_parallel(L["down"], self.act, 1, next_w, self.buf_b)
+            h = self._row_parallel(L["down"], self.act, 1, next_w, self.buf_b,
+                                   in_scale(w.layers[li + 1]["qkv"]) if li + 1 < n_layers else None)
             if trace is not None:
                 trace.append((h.clone(), self.residual.clone()))
         w.lm_head.forward(h, self.logits_local)
