@@ -44,6 +44,11 @@ def _pin_w4_decode_form(request):
     old = ops.set_w4_decode_form(1 if "w4_exact" in request.keywords else 0)
     yield
     ops.set_w4_decode_form(old)
+    if ops._splitk_ws is not None:
+        # an FP8 runner registered the process-wide split-K workspace: withdraw it so that the next test's FP8 GEMMs do not
+        # depend on which tests ran before it
+        torch.cuda.synchronize()
+        ops.disable_fp8_splitk()
 
 
 def pytest_sessionfinish(session, exitstatus):
