@@ -364,6 +364,9 @@ int xb_set_fp8_swap_max_m(int max_m);
  * Launches that share the workspace must be stream-ordered.  ws = NULL switches split-K off again. */
 size_t xb_gemm_splitk_workspace_bytes(void);
 int xb_set_gemm_splitk_workspace(void* ws, size_t bytes);
+/* host-only query (no device needed): k ranges xb_gemm_fp8_scaled uses for [M,K] x [N,K]^T on a device with sm_count SMs once a
+ * workspace is registered (1 = unsplit): fill the SMs once, >= 12 k blocks of 128 per range, no empty range. */
+int xb_gemm_fp8_split_k(int M, int N, int K, int sm_count);
 int xb_set_fp8_splitk_max(int max_split);   /* 1 = never split .. 32; default 8 (XB_FP8_SPLITK_MAX); returns the old value */
 
 /* ---- tensor-parallel exchange over NVLink peer memory (decode-sized messages) ---------------------------------

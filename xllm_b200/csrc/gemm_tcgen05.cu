@@ -698,6 +698,7 @@ static int pair_block_n(int M, int N) {
 // the fp32 partials.
 static std::atomic<void*> g_splitk_ws{nullptr};
 static std::atomic<size_t> g_splitk_bytes{0};
+static std::atomic<int> g_splitk_device{-1};     // the device the workspace lives on: GEMMs on another device run unsplit
 static std::atomic<int> g_splitk_max{-1};
 constexpr size_t kSplitKTicketBytes = 4096;
 static int splitk_max() {
@@ -714,21 +715,37 @@ static int splitk_max() {
 // per range and no empty range.  Measured on B200 at M = 32 (tools/fp8_splitk_probe.py, profiles/r02i_fp8_splitk.md): ranges of
 // 4 / 8 k blocks LOSE (o_proj TP8 shard, K = 1024: 7.3 -> 8.7 us; TP4, K = 2048: 9.9 -> 10.2 us - ring fill + the ticket round
 // trip outweigh the extra CTAs), 14 and more win (down TP8 13.3 -> 12.1 us, qkv TP8 22.5 -> 11.8 us, down unsharded 70 -> 46 us)
-static int pick_split_k(int tiles, int num_kb, int tokens_bn, size_t* need_bytes) {
-  *need_bytes = 0;
-  if (g_splitk_ws.load(std::memory_order_relaxed) == nullptr) return 1;
-  static int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+static int split_k_for(int tiles, int num_kb, int sms) {
   int split = sms / tiles;
   if (split > splitk_max()) split = splitk_max();
   if (split > num_kb / 12) split = num_kb / 12;
   if (split < 2) return 1;
   const int kb_per = (num_kb + split - 1) / split;
   split = (num_kb + kb_per - 1) / kb_per;
+  return split < 2 ? 1 : split;
+}
+static int pick_split_k(int tiles, int num_kb, int tokens_bn, size_t* need_bytes) {
+  *need_bytes = 0;
+  if (g_splitk_ws.load(std::memory_order_relaxed) == nullptr) return 1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != g_splitk_device.load(std::memory_order_relaxed)) {
+    cudaGetLastError();
+    return 1;
+  }
+  static int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+  int split = split_k_for(tiles, num_kb, sms);
   if (split < 2) return 1;
   const size_t need = kSplitKTicketBytes + (size_t)tiles * split * tokens_bn * kBlockM * sizeof(float);
   if ((size_t)tiles * sizeof(unsigned) > kSplitKTicketBytes || need > g_splitk_bytes.load(std::memory_order_relaxed)) return 1;
   *need_bytes = need;
   return split;
+}
+
+// host-only query (no device needed): the number of k ranges xb_gemm_fp8_scaled would use for an [M, K] x [N, K]^T product on a
+// device with `sm_count` SMs once a workspace is registered; 1 = unsplit.  For capacity planning and the CPU tests.
+extern "C" int xb_gemm_fp8_split_k(int M, int N, int K, int sm_count) {
+  if (M <= 0 || N < 128 || K <= 0 || sm_count <= 0 || M > 64 || M > fp8_swap_max_m()) return 1;
+  return split_k_for((N + kBlockM - 1) / kBlockM, (K + 127) / 128, sm_count);
 }
 
 extern "C" size_t xb_gemm_splitk_workspace_bytes(void) {
@@ -741,7 +758,14 @@ extern "C" int xb_set_gemm_splitk_workspace(void* ws, size_t bytes) {
     set_error("set_gemm_splitk_workspace: need a 16-byte aligned buffer of more than %zu bytes", kSplitKTicketBytes);
     return -1;
   }
-  if (ws != nullptr) XB_CUDA_OK(cudaMemset(ws, 0, kSplitKTicketBytes));
+  int dev = -1;
+  if (ws != nullptr) {
+    XB_CUDA_OK(cudaMemset(ws, 0, kSplitKTicketBytes));
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, ws) == cudaSuccess) dev = attr.device;
+    else { cudaGetLastError(); cudaGetDevice(&dev); }
+  }
+  g_splitk_device.store(dev, std::memory_order_relaxed);
   g_splitk_ws.store(ws, std::memory_order_relaxed);
   g_splitk_bytes.store(ws ? bytes : 0, std::memory_order_relaxed);
   return 0;
