@@ -367,6 +367,10 @@ int xb_set_gemm_splitk_workspace(void* ws, size_t bytes);
 /* host-only query (no device needed): k ranges xb_gemm_fp8_scaled uses for [M,K] x [N,K]^T on a device with sm_count SMs once a
  * workspace is registered (1 = unsplit): fill the SMs once, >= 12 k blocks of 128 per range, no empty range. */
 int xb_gemm_fp8_split_k(int M, int N, int K, int sm_count);
+/* host-only (no device needed): the kernel variant the tcgen05 GEMM entry points pick for a shape, as text ("bf16 pair 256x224",
+ * "fp8 swap-AB bn=32 split_k=5", "w4 single bn=128").  kind: 0 bf16 | 1 fp8 | 2 w4a16 | 3 w8a16.  Returns the length, -1 on a bad
+ * kind.  For capacity planning and the dispatch tests (tests/test_splitk_host_cpu.py). */
+int xb_gemm_describe(int kind, int M, int N, int K, int sm_count, char* buf, int buf_len);
 int xb_set_fp8_splitk_max(int max_split);   /* 1 = never split .. 32; default 8 (XB_FP8_SPLITK_MAX); returns the old value */
 
 /* ---- tensor-parallel exchange over NVLink peer memory (decode-sized messages) ---------------------------------

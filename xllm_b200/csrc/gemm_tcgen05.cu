@@ -748,6 +748,35 @@ extern "C" int xb_gemm_fp8_split_k(int M, int N, int K, int sm_count) {
   return split_k_for((N + kBlockM - 1) / kBlockM, (K + 127) / 128, sm_count);
 }
 
+// host-only (no device needed): which kernel variant the tcgen05 GEMM entry points pick for a shape, as text, e.g.
+// "bf16 pair 256x224", "fp8 swap-AB bn=32 split_k=5", "w4 single bn=128".  kind: 0 bf16 | 1 fp8 | 2 w4a16 | 3 w8a16.  Mirrors
+// the decision order of xb_gemm_bf16 / xb_gemm_fp8_scaled / xb_gemm_w4a16 / xb_gemm_w8a16 below (keep the two in step); split_k is
+// what a registered workspace would allow on a device with sm_count SMs.  Returns the length written, -1 on a bad kind.
+extern "C" int xb_gemm_describe(int kind, int M, int N, int K, int sm_count, char* buf, int buf_len) {
+  static const char* names[] = {"bf16", "fp8", "w4", "w8"};
+  if (kind < 0 || kind > 3 || buf == nullptr || buf_len <= 0) return -1;
+  if (kind == 1 && M <= fp8_swap_max_m() && M <= 64 && N >= 128)
+    return snprintf(buf, (size_t)buf_len, "fp8 swap-AB bn=%d split_k=%d", M <= 32 ? 32 : 64, xb_gemm_fp8_split_k(M, N, K, sm_count));
+  int bn = pick_block_n(M, N);
+  bool pair;
+  int pbn = 0;
+  if (kind == 3) {
+    pair = use_cta_pair(M, N, bn, true);
+    if (bn == 256 && !pair) bn = 128;
+    if (bn == 128 && N % 128 != 0) bn = 64;
+    pbn = pair ? 256 : 0;
+  } else {
+    if (kind == 2) {
+      if (bn == 256 && N % 256 != 0) bn = 128;
+      if (bn == 128 && N % 128 != 0) bn = 64;
+    }
+    pair = use_cta_pair(M, N, bn, kind == 2);
+    pbn = pair ? pair_block_n(M, N) : 0;
+  }
+  if (pair) return snprintf(buf, (size_t)buf_len, "%s pair 256x%d", names[kind], pbn);
+  return snprintf(buf, (size_t)buf_len, "%s single bn=%d", names[kind], bn);
+}
+
 extern "C" size_t xb_gemm_splitk_workspace_bytes(void) {
   // one wave of 148 CTAs x the largest token tile (64) is the most the heuristic ever asks for
   return kSplitKTicketBytes + (size_t)148 * 64 * kBlockM * sizeof(float);
