@@ -2,6 +2,7 @@
 (tests/core/kernels/cuda/moe/moe_topk_test.cu:31-55 cpuTopK: value descending, ties to the smaller index) and the documented
 semantics of moe_fused_topk (softmax / sigmoid + correction bias / renormalize)."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import moe as OM
@@ -52,3 +53,30 @@ def test_fused_moe_zero_for_foreign_experts():
     hi = OM.fused_moe(x, ids, sc, fc1[2:], fc2[2:], expert_begin=2)
     # expert parallelism: the two halves add up (before the final rounding) to the full result
     assert torch.allclose(lo.float() + hi.float(), full.float(), atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("case,tokens,hidden,experts,scoring,with_bias,route_scale,rw,eid", [
+    ("sigmoid", 512, 7168, 16, "sigmoid", True, 2.5, (1.25, 1.25, 1280.0), (6.0, 7.0, 6656.0)),
+    ("softmax", 512, 7168, 16, "softmax", False, 2.5, (3.16604e-14, 2.5, 1280.0), (0.0, 14.0, 4413.0)),
+    ("sigmoid_topk1", 128, 1024, 8, "sigmoid", False, 1.0, (0.5, 0.5, 128.0), (0.0, 1.0, 128.0))])
+def test_router_reproduces_the_reference_moe_gate_known_answers(case, tokens, hidden, experts, scoring, with_bias, route_scale, rw, eid):
+    """tests/core/layers/mlu/moe_gate_test.cpp:143-268 (MoEGateTest.Sigmoid / Softmax / SigmoidTopkGroup1): gate linear over
+    `seeded_tensor` inputs -> scoring -> top-2 -> renormalise -> route scale, expected min / max / sum of the routing weights and of
+    the expert ids recorded from the reference's hardware (expect_tensor_stats: rtol 1e-2, atol 1e-5, tests_utils.cpp:90-117).  All
+    three configurations keep every expert group (topk_group == n_group), i.e. exactly the routing xllm::kernel::cuda::moe_fused_topk
+    restated in oracle/moe.py implements; the gate linear is the reference's bf16 F::linear (oracle.ops.linear)."""
+    from oracle import ops as O
+    from oracle import seeded
+    W = seeded.seeded_tensor("moe_gate_tests.gate_proj.weight", (experts, hidden), torch.bfloat16)
+    x = seeded.seeded_tensor(f"moe_gate_tests.{case}.hidden_states", (tokens, hidden), torch.bfloat16)
+    bias = seeded.seeded_tensor("moe_gate_tests.e_score_correction_bias", (experts,), torch.bfloat16).float() if with_bias else None
+    w, ids = OM.moe_fused_topk(O.linear(x, W, None), 2, True, bias, scoring)
+    w = w * route_scale
+
+    def close(actual, expected):
+        return abs(actual - expected) <= 1e-5 + 1e-2 * abs(expected)
+    for got, exp in (((w.min().item(), w.max().item(), w.double().sum().item()), rw),
+                     ((float(ids.min()), float(ids.max()), float(ids.sum())), eid)):
+        assert all(close(a, e) for a, e in zip(got, exp)), (case, got, exp)
+    if case == "softmax":
+        assert int(ids.sum()) == 4413 and abs(w.min().item() / 3.16604e-14 - 1) < 1e-4      # far inside the reference's tolerance
