@@ -83,7 +83,30 @@ def _worker(rank, world, port, shard_embedding, out_q):
     i32 = lambda v: torch.tensor(v, dtype=torch.int32)
     logits, tokens = r.forward(i32(toks), torch.tensor(meta.positions, dtype=torch.int64), i32(meta.new_cache_slots),
                                i32(meta.q_cu_seq_lens), i32(meta.kv_cu_seq_lens))
-    out_q.put((rank, logits.float().numpy(), tokens.numpy(), [k.float().numpy() for k in kcs], [v.float().numpy() for v in vcs]))
+    # the same prompts in two chunks ([first 3 | rest], sequence 2 finishes in chunk 1) through the TP runner: chunked prefill over
+    # the paged cache must reproduce the one-shot TP result bit for bit (rows are independent in every exchange)
+    cut = [3, 3, 1]
+    bs = cfg.block_size
+    kc2, vc2 = mk(), mk()
+    r2 = Qwen2PrefillRunner(cfg, w, kc2, vc2, Q2.make_cos_sin_cache(cfg, "cpu"), device="cpu", pg=P.ProcessGroup())
+    seqs = []
+    off = 0
+    for n in LENS:
+        seqs.append(toks[off:off + n])
+        off += n
+    m1 = OB.build_paged_meta([OB.SeqState(b[: (c + bs - 1) // bs], 0, c) for b, c in zip(BLOCKS, cut)], bs)
+    first = [t for sq, c in zip(seqs, cut) for t in sq[:c]]
+    r2.forward(i32(first), torch.tensor(m1.positions, dtype=torch.int64), i32(m1.new_cache_slots), i32(m1.q_cu_seq_lens),
+               i32(m1.kv_cu_seq_lens))
+    rest = [(b, c, n) for b, c, n in zip(BLOCKS, cut, LENS) if n > c]
+    m2 = OB.build_paged_meta([OB.SeqState(b, c, n) for b, c, n in rest], bs)
+    second = [t for sq, c, n in zip(seqs, cut, LENS) if n > c for t in sq[c:]]
+    logits2, tokens2 = r2.forward(i32(second), torch.tensor(m2.positions, dtype=torch.int64), i32(m2.new_cache_slots),
+                                  i32(m2.q_cu_seq_lens), None, i32(m2.paged_kv_indptr), i32(m2.paged_kv_indices),
+                                  i32(m2.paged_kv_last_page_len), chunked=True)
+    chunk_ok = bool(torch.equal(logits2, logits[:2]) and torch.equal(tokens2, tokens[:2]) and
+                    all(torch.equal(a, b) for a, b in zip(kc2 + vc2, kcs + vcs)))
+    out_q.put((rank, logits.float().numpy(), tokens.numpy(), [k.float().numpy() for k in kcs], [v.float().numpy() for v in vcs], chunk_ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -120,6 +143,7 @@ def test_tp2_prefill_composition_matches_single_rank_oracle():
         # per-rank partial sums are rounded to bf16 before the exchange (the reference's NCCL all-reduce does the same)
         assert rel <= 2e-2, f"TP2 prefill logits rel-L2 {rel:.3e}"
         assert torch.equal(torch.from_numpy(got[0][1]).long(), ref.float().argmax(-1))
+        assert got[0][4] and got[1][4], "TP chunked prefill differs from TP one-shot prefill"
         for rank in (0, 1):
             sl = slice(rank, rank + 1)                                   # one kv head per rank
             k0, v0 = torch.from_numpy(got[rank][2][0]), torch.from_numpy(got[rank][3][0])
