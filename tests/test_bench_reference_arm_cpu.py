@@ -38,3 +38,14 @@ def test_reference_arm_under_torchrun_prints_once():
     lines = _json_lines(r.stdout)
     assert len(lines) == 1, "exactly one rank prints the line"
     _check(lines[0], 2)
+
+
+def test_product_arm_has_no_cpu_fallback():
+    """without a GPU the product arm must fail loudly - no JSON line, non-zero exit - never time a CPU path as the product"""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--no-comparators",
+                        "--no-scale-target"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and not _json_lines(r.stdout)
