@@ -193,3 +193,36 @@ def test_row_parallel_bias_only_on_rank0():
     # column-parallel shards keep their own rows of the bias on every rank
     rows = torch.arange(8, 16)
     assert torch.equal(P.shard_linear("bf16", dict(w=w, b=b), rows, None, 64, 3)["b"], b[rows])
+
+
+def test_fp8_linear_shards_column_and_row_parallel():
+    """FP8 W8A8 logical weights (e4m3 weight, per-tensor or per-channel weight scale, static activation scale) through shard_linear:
+    column-parallel shards concatenate to the full output exactly; row-parallel partials (each rounded to bf16, as every rank's
+    cutlass_scaled_mm does before the all-reduce, linear.cpp:1518-1520) sum to the full output within the partials' rounding."""
+    g = torch.Generator().manual_seed(9)
+    N, K, tp = 96, 256, 2
+    w = torch.randn(N, K, generator=g) * 0.05
+    x = torch.randn(5, K, generator=g).to(BF16)
+    in_scale = torch.tensor([0.02])
+    for per_channel in (False, True):
+        w_scale = (w.abs().amax(1) / 448.0) if per_channel else (w.abs().max() / 448.0).reshape(1)
+        w8 = (w / (w_scale[:, None] if per_channel else w_scale)).clamp(-448, 448).to(torch.float8_e4m3fn)
+        part = dict(w8=w8, w_scale=w_scale, in_scale=in_scale, b=None)
+        full = O.fp8_linear(x, w8, w_scale, in_scale)
+        cols_out = []
+        for r in range(tp):
+            rows = torch.arange(r * N // tp, (r + 1) * N // tp)
+            sh = P.shard_linear("fp8", part, rows, None, 0, r)
+            assert sh["w8"].shape == (N // tp, K) and sh["in_scale"] is in_scale
+            assert sh["w_scale"].numel() == (N // tp if per_channel else 1)
+            cols_out.append(O.fp8_linear(x, sh["w8"], sh["w_scale"], sh["in_scale"]))
+        assert torch.equal(torch.cat(cols_out, 1), full)
+        x8, _ = O.fp8_scaled_quantize(x, in_scale)
+        acc = torch.zeros(5, N)
+        for r in range(tp):
+            sh = P.shard_linear("fp8", part, None, P.shard_cols(K, r, tp), 0, r)
+            assert sh["w8"].shape == (N, K // tp)
+            cs = P.shard_cols(K, r, tp)
+            acc += O.fp8_scaled_matmul(x8[:, cs], sh["w8"], in_scale, sh["w_scale"]).float()
+        scale = (x8.float().abs() @ w8.float().abs().t()) * in_scale * (w_scale[None, :] if per_channel else w_scale)
+        assert ((acc - full.float()).abs() <= 2.0 ** -7 * scale + 1e-6).all()

@@ -103,6 +103,18 @@ def shard_linear(kind: str, part: dict, rows: Optional[torch.Tensor], cols: Opti
         if cols is not None:
             w = w[:, cols]
         out["w"] = w.contiguous()
+    w8 = part.get("w8")
+    if w8 is not None:
+        # FP8 W8A8 (fp8 linear, linear.cpp:137-182): e4m3 weight [N, K] sliced like a bf16 one; a per-tensor weight scale and the
+        # static activation scale are shared by every shard, a per-channel weight scale [N] follows the output rows
+        if rows is not None:
+            w8 = w8[rows]
+        if cols is not None:
+            w8 = w8[:, cols]
+        ws = part["w_scale"]
+        if rows is not None and ws.numel() > 1:
+            ws = ws.reshape(-1)[rows]
+        out.update(w8=w8.contiguous(), w_scale=ws.contiguous(), in_scale=part.get("in_scale"))
     b = part.get("b")
     if b is not None:
         # bias is added once: column-parallel shards carry their rows; row-parallel only on rank 0 (linear.cpp:1508-1511)
