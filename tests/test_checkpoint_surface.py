@@ -90,3 +90,21 @@ def test_llama3_rope_scaling_matches_the_published_rule():
     scaled = make_cos_sin_cache(Qwen2Config.llama3_70b(max_position_embeddings=256, rope_scaling=dict(
         rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max_position_embeddings=8192)), "cpu")
     assert torch.equal(plain[:, :20], scaled[:, :20]) and not torch.equal(plain[:, 40:64], scaled[:, 40:64])
+
+
+def test_llama3_rope_scaling_matches_transformers():
+    """the same frequencies as the public implementation the checkpoints are trained with (transformers' "llama3" rope init):
+    bit-identical inv_freq for Llama-3.1-70B's parameters"""
+    pytest = __import__("pytest")
+    tf = pytest.importorskip("transformers")
+    from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+    from xllm_b200.qwen2 import llama3_scale_inv_freq
+    rs = dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max_position_embeddings=8192)
+    try:
+        cfg = tf.LlamaConfig(hidden_size=8192, num_attention_heads=64, rope_theta=500000.0, max_position_embeddings=131072, rope_scaling=rs)
+        inv, att = ROPE_INIT_FUNCTIONS["llama3"](cfg, "cpu")
+    except Exception as e:                                                # config surface differs between transformers versions
+        pytest.skip(f"transformers rope init not callable here: {e}")
+    sl = torch.arange(0, 128, 2, dtype=torch.float32)
+    base = 1.0 / torch.pow(torch.tensor(500000.0), sl / 128.0)
+    assert att == 1.0 and torch.equal(inv, llama3_scale_inv_freq(base, 8.0, 1.0, 4.0, 8192))
