@@ -108,3 +108,28 @@ def test_llama3_rope_scaling_matches_transformers():
     sl = torch.arange(0, 128, 2, dtype=torch.float32)
     base = 1.0 / torch.pow(torch.tensor(500000.0), sl / 128.0)
     assert att == 1.0 and torch.equal(inv, llama3_scale_inv_freq(base, 8.0, 1.0, 4.0, 8192))
+
+
+def test_awq_gptq_unpackers_match_vllm_pack_definitions():
+    """xllm_b200.quant.from_awq / from_gptq against an independent public definition of the two checkpoint layouts: vLLM's
+    awq_pack / gptq_pack / pack_cols (model_executor/layers/quantization/utils/quant_utils.py) applied to random 4-bit weights and
+    zero points must round-trip through our loaders."""
+    pytest = __import__("pytest")
+    try:
+        from vllm.model_executor.layers.quantization.utils import quant_utils as qu
+    except Exception as e:
+        pytest.skip(f"vllm quant utils not importable here: {e}")
+    from xllm_b200 import quant
+    g = torch.Generator().manual_seed(4)
+    K, N, gs = 256, 64, 128
+    q = torch.randint(0, 16, (K, N), generator=g, dtype=torch.int32)            # logical [K, N] nibbles (checkpoint orientation)
+    z = torch.randint(0, 16, (K // gs, N), generator=g, dtype=torch.int32)
+    s = (torch.rand(K // gs, N, generator=g) * 0.01 + 0.001).to(torch.float16)
+    # AutoAWQ GEMM layout: qweight [K, N/8] and qzeros [K/g, N/8], nibbles interleaved 0 2 4 6 1 3 5 7
+    q2, s2, z2 = quant.from_awq(qu.awq_pack(q, 4, K, N), qu.awq_pack(z, 4, K // gs, N), s, gs)
+    assert torch.equal(q2.to(torch.int32), q.t()) and torch.equal(z2.to(torch.int32), z.t())
+    assert torch.equal(s2, s.to(torch.bfloat16).t())
+    # AutoGPTQ layout: qweight [K/8, N] packed along K, qzeros [K/g, N/8] packed along N in plain order, stored minus one
+    zm1 = (z - 1).clamp(min=0)
+    q3, s3, z3 = quant.from_gptq(qu.gptq_pack(q, 4, K, N), qu.pack_cols(zm1, 4, K // gs, N), s, None, gs)
+    assert torch.equal(q3.to(torch.int32), q.t()) and torch.equal(z3.to(torch.int32), (zm1 + 1).t())
