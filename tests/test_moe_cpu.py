@@ -80,3 +80,39 @@ def test_router_reproduces_the_reference_moe_gate_known_answers(case, tokens, hi
         assert all(close(a, e) for a, e in zip(got, exp)), (case, got, exp)
     if case == "softmax":
         assert int(ids.sum()) == 4413 and abs(w.min().item() / 3.16604e-14 - 1) < 1e-4      # far inside the reference's tolerance
+
+
+def test_experts_and_router_match_transformers_mixtral():
+    """oracle.moe.fused_moe / moe_fused_topk against the public implementation of a gated-MoE block: transformers' MixtralExperts
+    (gate_up_proj [E, 2I, H] in [gate | up] order, SiLU(gate) * up, down_proj, weighted index_add) and its softmax -> top-k ->
+    renormalise routing.  The reference stacks fc1 as [up | gate] (layers/cuda/fused_moe.cpp:124-126), so the halves are swapped when
+    handing the same weights to the two implementations."""
+    tf = pytest.importorskip("transformers")
+    try:
+        from transformers.models.mixtral import modeling_mixtral as mm
+        cfg = tf.MixtralConfig(hidden_size=64, intermediate_size=96, num_local_experts=8, num_experts_per_tok=2, num_hidden_layers=1,
+                               num_attention_heads=4, num_key_value_heads=2, vocab_size=128)
+        experts = mm.MixtralExperts(cfg).to(torch.bfloat16)
+        assert tuple(experts.gate_up_proj.shape) == (8, 192, 64) and tuple(experts.down_proj.shape) == (8, 64, 96)
+    except Exception as e:
+        pytest.skip(f"transformers MixtralExperts not constructible here: {e}")
+    g = torch.Generator().manual_seed(5)
+    E, H, I, T, k = 8, 64, 96, 11, 2
+    gate = (torch.randn(E, I, H, generator=g) * 0.1).to(torch.bfloat16)
+    up = (torch.randn(E, I, H, generator=g) * 0.1).to(torch.bfloat16)
+    down = (torch.randn(E, H, I, generator=g) * 0.1).to(torch.bfloat16)
+    x = torch.randn(T, H, generator=g).to(torch.bfloat16)
+    logits = torch.randn(T, E, generator=g)
+    w, ids = OM.moe_fused_topk(logits, k, True, None, "softmax")
+    # routing: softmax over all experts, top-k, renormalise (MixtralSparseMoeBlock / MixtralTopKRouter)
+    p = torch.softmax(logits.float(), -1)
+    tw, ti = torch.topk(p, k, dim=-1)
+    tw = tw / tw.sum(-1, keepdim=True)
+    assert torch.equal(ids.long(), ti) and torch.allclose(w, tw, rtol=1e-6, atol=1e-7)
+    with torch.no_grad():
+        experts.gate_up_proj.copy_(torch.cat([gate, up], 1))
+        experts.down_proj.copy_(down)
+        theirs = experts(x, ti, tw.to(torch.bfloat16))
+    ours = OM.fused_moe(x, ids, w, torch.cat([up, gate], 1), down)
+    rel = ((ours.float() - theirs.float()).norm() / theirs.float().norm()).item()
+    assert rel <= 1e-2, rel
