@@ -254,3 +254,27 @@ def test_matmul_dcu_cases(shape_a, shape_b, with_bias):
     out = O.linear(a.reshape(-1, shape_a[-1]), b, bias).reshape(*shape_a[:-1], shape_b[0])
     ref = torch.nn.functional.linear(a, b, bias)
     assert torch.allclose(out.float(), ref.float(), rtol=2e-2, atol=2e-2)
+
+
+def test_e4m3_conversion_is_rne_saturating_bit_level():
+    """scaled_fp8_conversion (fp8_quant_utils.cuh:78-129) = clamp to +-448 then __nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3):
+    round-to-nearest-even onto the e4m3fn grid (3 mantissa bits, exponent bias 7, subnormal step 2^-9, max 448).  The oracle leans
+    on torch's float8_e4m3fn cast for the rounding; this checks that cast against an independent construction of the grid: every
+    representable value, every midpoint between neighbours (ties to the even code), and values just either side of the midpoints."""
+    import numpy as np
+    codes = np.arange(0, 127, dtype=np.uint8)                              # 0x00 .. 0x7e: +0 .. 448 (0x7f is NaN)
+    e, m = codes >> 3, (codes & 7).astype(np.float64)
+    grid = np.where(e == 0, m * 2.0 ** -9, (1 + m / 8) * 2.0 ** (e.astype(np.float64) - 7))
+    assert grid[-1] == 448.0 and grid[1] == 2.0 ** -9 and (np.diff(grid) > 0).all()
+    assert torch.equal(torch.tensor(grid, dtype=torch.float32).to(E4M3).view(torch.uint8), torch.tensor(codes))
+    mid = (grid[:-1] + grid[1:]) / 2
+    want_tie = np.where(codes[:-1] % 2 == 0, codes[:-1], codes[1:])        # ties go to the even code
+    got = torch.tensor(mid, dtype=torch.float32).to(E4M3).view(torch.uint8).numpy()
+    assert (got == want_tie).all()
+    below = torch.tensor(np.nextafter(mid.astype(np.float32), np.float32(0)), dtype=torch.float32).to(E4M3).view(torch.uint8).numpy()
+    above = torch.tensor(np.nextafter(mid.astype(np.float32), np.float32(1e9)), dtype=torch.float32).to(E4M3).view(torch.uint8).numpy()
+    assert (below == codes[:-1]).all() and (above == codes[1:]).all()
+    # through the oracle: scale, clamp, convert - and the sign is carried
+    x = torch.tensor([[465.0, -1000.0, 0.3, -0.3, 2.0 ** -10, 2.0 ** -11]])
+    out = O.static_scaled_fp8_quant(x, torch.tensor([1.0])).float().tolist()[0]
+    assert out == [448.0, -448.0, 0.3125, -0.3125, 0.0, 0.0]             # 2^-10 is the midpoint of 0 and 2^-9: tie to even = 0
