@@ -226,3 +226,46 @@ def test_fp8_linear_shards_column_and_row_parallel():
             acc += O.fp8_scaled_matmul(x8[:, cs], sh["w8"], in_scale, sh["w_scale"]).float()
         scale = (x8.float().abs() @ w8.float().abs().t()) * in_scale * (w_scale[None, :] if per_channel else w_scale)
         assert ((acc - full.float()).abs() <= 2.0 ** -7 * scale + 1e-6).all()
+
+
+def test_partition_properties_over_the_supported_head_configs():
+    """for every (q heads, kv heads, tp) the reference accepts (qwen2_attention.cpp:47-65: q heads divisible by tp; kv heads either
+    divisible by tp or tp divisible by kv heads, then replicated): q rows of all ranks partition the q block exactly; k / v rows
+    cover every kv head, each exactly max(1, tp / kv) times; every rank's q heads map onto the kv heads it holds (GQA group intact);
+    gate/up rows and row-parallel column slices partition their dimension."""
+    D = 8
+    for hq, hkv in ((28, 4), (64, 8), (32, 8), (16, 16), (8, 1), (12, 2)):
+        for tp in (1, 2, 4, 8, 16):
+            if hq % tp or not (hkv % tp == 0 or tp % hkv == 0):
+                with pytest.raises(ValueError):
+                    P.partition_heads(hq, hkv, 0, tp)
+                continue
+            group = hq // hkv
+            q_rows, k_count, v_count = [], torch.zeros(hkv, dtype=torch.int64), torch.zeros(hkv, dtype=torch.int64)
+            for r in range(tp):
+                hp = P.partition_heads(hq, hkv, r, tp)
+                assert hp.num_heads == hq // tp and hp.num_kv_heads == max(1, hkv // tp) and hp.kv_replicas == max(1, tp // hkv)
+                rows = P.shard_qkv_rows(hq, hkv, D, r, tp)
+                nq, nkv = hp.num_heads * D, hp.num_kv_heads * D
+                q, k, v = rows[:nq], rows[nq:nq + nkv], rows[nq + nkv:]
+                assert len(v) == nkv and (q < hq * D).all() and ((k >= hq * D) & (k < (hq + hkv) * D)).all() and (v >= (hq + hkv) * D).all()
+                q_rows.append(q)
+                kh = ((k - hq * D) // D).unique()
+                vh = ((v - (hq + hkv) * D) // D).unique()
+                assert torch.equal(kh, vh) and kh.tolist() == list(range(hp.kv_head0, hp.kv_head0 + hp.num_kv_heads))
+                k_count[kh] += 1
+                v_count[vh] += 1
+                # GQA: the kv head of every local q head is one this rank holds
+                qh = (q // D).unique()
+                assert set((qh // group).tolist()) <= set(kh.tolist())
+            assert sorted(torch.cat(q_rows).tolist()) == list(range(hq * D))
+            assert (k_count == max(1, tp // hkv)).all() and (v_count == max(1, tp // hkv)).all()
+    for inter, tp in ((18944, 4), (28672, 8), (96, 2)):
+        gu = torch.cat([P.shard_gate_up_rows(inter, r, tp) for r in range(tp)])
+        assert sorted(gu.tolist()) == list(range(2 * inter))
+        for r in range(tp):                                               # a rank's gate rows and up rows are the SAME intermediate columns
+            rows = P.shard_gate_up_rows(inter, r, tp)
+            half = len(rows) // 2
+            assert torch.equal(rows[:half] + inter, rows[half:])
+            cs = P.shard_cols(inter, r, tp)
+            assert rows[0].item() == cs.start and rows[half - 1].item() == cs.stop - 1
