@@ -41,7 +41,8 @@ def test_product_package_never_imports_the_oracle_or_a_compat_layer():
 
 
 def test_bench_and_entry_import_the_oracle_only_in_the_cpu_legs_and_smoke():
-    allowed = {"bench.py": {"cpu_layer_baseline"}, "__graft_entry__.py": {"smoke"}}
+    # build() may import oracle.build_ref and nothing else of the oracle: it BUILDS the checker (oracle/_ref), it does not use it
+    allowed = {"bench.py": {"cpu_layer_baseline"}, "__graft_entry__.py": {"smoke", "build"}}
     for fname, funcs in allowed.items():
         tree = ast.parse(open(os.path.join(ROOT, fname)).read())
         for node in tree.body:                                            # module level: no oracle / tests imports
@@ -53,6 +54,9 @@ def test_bench_and_entry_import_the_oracle_only_in_the_cpu_legs_and_smoke():
                 uses = [n for n in ast.walk(node) if isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] in ("oracle", "tests")]
                 if uses:
                     assert node.name in funcs, f"{fname}: {node.name}() imports the oracle / tests"
+                    if node.name == "build":
+                        names = {(n.module, a.name) for n in uses for a in n.names}
+                        assert names == {("oracle", "build_ref")}, names
 
 
 def test_nothing_outside_tools_and_fixture_scripts_reads_the_reference_tree():
