@@ -18,8 +18,14 @@ Parity pinning:
     with the seeded_tensor generator (tests_utils.cpp:159-274); values produced on
     MLU hardware, reproduced here to bf16 rounding (see the test for the tolerance)
   * RMSNorm / RoPE / KV scatter / SiLU*mul / FP8 quant follow the reference .cu
-    files line by line (the reference's own tests compare them with torch
-    expressions, no stored vectors)
+    files line by line; the reference's own kernel tests (torch expressions, no
+    stored vectors) are restated on the oracle in tests/test_oracle_reference_kats_cpu.py,
+    and the reference's kernels THEMSELVES are compiled from its sources into
+    oracle/_ref/ (oracle/build_ref.py) for the GPU-side comparison of
+    tools/ref_kernel_parity.py / tests/test_gpu_zzz_ref_kernels.py
+  * MoE router -> pinned by the known answers of tests/core/layers/mlu/moe_gate_test.cpp:143-268
+    (tests/test_moe_cpu.py); whole-model composition -> transformers' Qwen2 / Llama
+    (tests/test_oracle_vs_transformers_cpu.py)
   * CUDA paged-attention numerics live in un-vendored FlashInfer v0.6.2
     (docker/Dockerfile.cuda:16): restated from its published algorithm
     (fp32 scores, base-2 online softmax, P rounded to bf16, denominator summed
