@@ -1,6 +1,6 @@
 """oracle/_ref: the reference's OWN elementwise CUDA kernels, compiled from the sources where they lie under /root/reference (nothing
-is copied into this repository): activation.cu, norm.cu, rope.cu, reshape_paged_cache.cu, fp8_quant.cu, fused_qknorm_rope.cu of
-xllm/core/kernels/cuda, with nvcc for sm_100a against the libtorch of this image.  They need no part of the reference's build system;
+is copied into this repository): activation.cu, norm.cu, rope.cu, reshape_paged_cache.cu, fp8_quant.cu, fused_qknorm_rope.cu,
+moe/moe_fused_topk.cu and llm_decode_metadata_update.cu of xllm/core/kernels/cuda, with nvcc for sm_100a against the libtorch of this image.  They need no part of the reference's build system;
 the only missing header is <glog/logging.h>, for which oracle/ref_stubs/ forwards to c10's glog-compatible macros.  (Attention =
 FlashInfer and the FP8 GEMM = CUTLASS are un-vendored third-party code and stay "unbuildable": DESIGN.md section 2.)
 
@@ -20,7 +20,8 @@ KDIR = os.path.join(REF, "xllm", "core", "kernels", "cuda")
 OUT = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT, "libxllm_ref_kernels.so")
 PYMOD = os.path.join(OUT, "xllm_ref_kernels_py.so")
-SOURCES = ["activation.cu", "norm.cu", "rope.cu", "reshape_paged_cache.cu", "fp8_quant.cu", "fused_qknorm_rope.cu"]
+SOURCES = ["activation.cu", "norm.cu", "rope.cu", "reshape_paged_cache.cu", "fp8_quant.cu", "fused_qknorm_rope.cu",
+           "moe/moe_fused_topk.cu", "llm_decode_metadata_update.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
@@ -30,7 +31,7 @@ def available() -> bool:
 
 def build(verbose=False, force=False):
     """-> path of the python module, or None when neither the reference tree nor a prebuilt oracle/_ref is present"""
-    if available() and not force:
+    if available() and not force and os.path.getmtime(PYMOD) >= os.path.getmtime(os.path.join(HERE, "ref_binding.cpp")):
         return PYMOD
     if not os.path.isdir(KDIR):
         return None
@@ -41,12 +42,13 @@ def build(verbose=False, force=False):
     ti = os.path.dirname(torch.__file__)
     tv = os.path.join(os.path.dirname(tvm_ffi.__file__), "include")
     os.makedirs(os.path.join(OUT, "obj"), exist_ok=True)
-    inc = [f"-I{os.path.join(HERE, 'ref_stubs')}", f"-I{KDIR}", f"-I{os.path.join(REF, 'xllm')}", f"-I{REF}", f"-I{ti}/include",
+    inc = [f"-I{os.path.join(HERE, 'ref_stubs')}", f"-I{KDIR}", f"-I{os.path.join(KDIR, 'moe')}", f"-I{os.path.join(REF, 'xllm', 'core')}",
+           f"-I{os.path.join(REF, 'xllm')}", f"-I{REF}", f"-I{ti}/include",
            f"-I{ti}/include/torch/csrc/api/include", f"-I{tv}", f"-I{sysconfig.get_paths()['include']}",      # fp8_quant.cu pulls torch/extension.h -> Python.h
            "-D_GLIBCXX_USE_CXX11_ABI=1", "-DUSE_CUDA"]
     jobs, objs = [], []
     for s in SOURCES:
-        obj = os.path.join(OUT, "obj", s.rsplit(".", 1)[0] + ".o")
+        obj = os.path.join(OUT, "obj", os.path.basename(s).rsplit(".", 1)[0] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj):
             jobs.append([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "--expt-relaxed-constexpr",

@@ -1,5 +1,6 @@
 """This library's elementwise kernels against the REFERENCE'S OWN CUDA kernels on the GPU: oracle/_ref holds activation.cu, norm.cu,
-rope.cu, reshape_paged_cache.cu, fp8_quant.cu and fused_qknorm_rope.cu compiled from /root/reference by oracle/build_ref.py (nothing
+rope.cu, reshape_paged_cache.cu, fp8_quant.cu, fused_qknorm_rope.cu, moe/moe_fused_topk.cu and llm_decode_metadata_update.cu compiled
+from /root/reference by oracle/build_ref.py (nothing
 copied; the prebuilt .so travels to the GPU box).  tools/ref_kernel_parity.py runs both on the same seeded inputs IN ITS OWN PROCESS
 (a fault inside either kernel must not take the session's CUDA context with it) and reports, per op, how many cases were bit-identical.
 
@@ -17,7 +18,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OPS = ["rms_norm", "fused_add_rms_norm", "rms_norm_static_fp8_quant", "fused_add_rms_norm_static_fp8_quant", "static_scaled_fp8_quant",
-       "act_and_mul", "rotary_embedding", "reshape_paged_cache", "fused_qk_norm_rope"]
+       "act_and_mul", "rotary_embedding", "reshape_paged_cache", "fused_qk_norm_rope", "moe_fused_topk", "update_llm_decode_metadata"]
 
 
 @pytest.fixture(scope="module")

@@ -1,5 +1,6 @@
 """GPU parity of this library's elementwise kernels against the REFERENCE'S OWN kernels (oracle/_ref: activation.cu, norm.cu, rope.cu,
-reshape_paged_cache.cu, fp8_quant.cu, fused_qknorm_rope.cu compiled from /root/reference by oracle/build_ref.py), on the same seeded
+reshape_paged_cache.cu, fp8_quant.cu, fused_qknorm_rope.cu, moe/moe_fused_topk.cu, llm_decode_metadata_update.cu compiled from
+/root/reference by oracle/build_ref.py), on the same seeded
 bf16 inputs.  Prints one JSON object: per op the number of cases, how many were bit-identical, and the worst difference otherwise.
 Runs in its own process so that a fault inside a kernel cannot take the test session with it (tests/test_gpu_zzz_ref_kernels.py).
   python tools/ref_kernel_parity.py [out.json]"""
@@ -134,6 +135,42 @@ def main():
             ref.fused_qk_norm_rope(b, hq, hk, hk, D, 1e-6, qw, kw, cache, inter, pos)
             record("fused_qk_norm_rope", f"T{T} {hq}/{hk}x{D} interleaved={inter}", [(a, b)])
         guarded("fused_qk_norm_rope", f"T{T} {hq}/{hk}x{D} interleaved={inter}", qknorm)
+    # MoE router (n4): moe_fused_topk.cu + moe_topk_{softmax,sigmoid}_kernels.cuh
+    for T, E, k, dt in ((7, 16, 2, torch.float32), (33, 64, 8, torch.float32), (512, 16, 2, BF16), (5, 256, 8, BF16), (1, 8, 1, torch.float32)):
+        logits = (torch.randn(T, E, generator=g, device=DEV) * 3).to(dt)
+        bias = torch.randn(E, generator=g, device=DEV) * 0.1
+        for scoring, use_bias in (("softmax", False), ("sigmoid", False), ("sigmoid", True)):
+            for renorm in (True, False):
+                name = f"{T}x{E} top{k} {str(dt).split('.')[-1]} {scoring} bias={use_bias} renorm={renorm}"
+
+                def router():
+                    w1, i1 = ops.moe_fused_topk(logits, k, renorm, bias if use_bias else None, scoring)
+                    w2, i2 = ref.moe_fused_topk(logits.clone(), k, renorm, bias if use_bias else None, scoring)
+                    record("moe_fused_topk", name, [(w1.float(), w2.float()), (i1.to(torch.int64), i2.to(torch.int64))])
+                guarded("moe_fused_topk", name, router)
+    # CUDA-graph decode metadata refresh (n3): llm_decode_metadata_update.cu - integer work, every destination buffer compared whole
+    I32 = torch.int32
+    FIELDS = ("tokens", "positions", "new_cache_slots", "kv_seq_lens", "paged_kv_indptr", "paged_kv_indices", "paged_kv_last_page_len")
+    DFIELDS = ("tokens", "positions", "new_cache_slots", "kv_seq_lens", "kv_seq_lens_delta", "paged_kv_indptr", "paged_kv_indices",
+               "paged_kv_last_page_len")
+    for n_tok, padded, batch, n_idx in ((5, 8, 5, 37), (1, 1, 1, 1), (64, 64, 64, 4000), (3, 16, 3, 0), (300, 512, 300, 70000)):
+        def metadata():
+            ri = lambda n, hi=100000: torch.randint(0, hi, (n,), generator=g, device=DEV, dtype=I32)
+            zero = torch.zeros(1, dtype=I32, device=DEV)
+            src = dict(tokens=ri(n_tok), positions=ri(n_tok), new_cache_slots=ri(n_tok),
+                       kv_seq_lens=torch.cat([zero, ri(batch, 500).cumsum(0).to(I32)]),
+                       paged_kv_indptr=torch.cat([zero, ri(batch, 40).cumsum(0).to(I32)]), paged_kv_indices=ri(max(n_idx, 1)),
+                       paged_kv_last_page_len=ri(max(batch, 1), 128) + 1)
+            cap_tok, cap_batch, cap_idx = max(padded, n_tok) + 7, batch + 5, n_idx + 11
+            dst = dict(tokens=ri(cap_tok), positions=ri(cap_tok), new_cache_slots=ri(cap_tok), kv_seq_lens=ri(cap_batch + 1),
+                       kv_seq_lens_delta=ri(cap_batch), paged_kv_indptr=ri(cap_batch + 1), paged_kv_indices=ri(cap_idx),
+                       paged_kv_last_page_len=ri(cap_batch))
+            d1 = {k_: v.clone() for k_, v in dst.items()}
+            d2 = {k_: v.clone() for k_, v in dst.items()}
+            ops.update_llm_decode_metadata(src, d1, n_tok, padded, batch, n_idx)
+            ref.update_llm_decode_metadata([src[f] for f in FIELDS], [d2[f] for f in DFIELDS], n_tok, padded, batch, n_idx)
+            record("update_llm_decode_metadata", f"tokens {n_tok}/{padded} batch {batch} indices {n_idx}", [(d1[f], d2[f]) for f in DFIELDS])
+        guarded("update_llm_decode_metadata", f"tokens {n_tok}/{padded} batch {batch}", metadata)
     torch.cuda.synchronize()
     out = {"device": torch.cuda.get_device_name(0), "ops": res}
     print(json.dumps(out))
