@@ -1,6 +1,6 @@
 """oracle/_ref: the reference's OWN elementwise CUDA kernels, compiled from the sources where they lie under /root/reference (nothing
 is copied into this repository): activation.cu, norm.cu, rope.cu, reshape_paged_cache.cu, fp8_quant.cu, fused_qknorm_rope.cu,
-moe/moe_fused_topk.cu and llm_decode_metadata_update.cu of xllm/core/kernels/cuda, with nvcc for sm_100a against the libtorch of this image.  They need no part of the reference's build system;
+moe/moe_fused_topk.cu, llm_decode_metadata_update.cu and fp8_scaled_quantize.cpp of xllm/core/kernels/cuda, with nvcc for sm_100a against the libtorch of this image.  They need no part of the reference's build system;
 the only missing header is <glog/logging.h>, for which oracle/ref_stubs/ forwards to c10's glog-compatible macros.  (Attention =
 FlashInfer and the FP8 GEMM = CUTLASS are un-vendored third-party code and stay "unbuildable": DESIGN.md section 2.)
 
@@ -21,7 +21,7 @@ OUT = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT, "libxllm_ref_kernels.so")
 PYMOD = os.path.join(OUT, "xllm_ref_kernels_py.so")
 SOURCES = ["activation.cu", "norm.cu", "rope.cu", "reshape_paged_cache.cu", "fp8_quant.cu", "fused_qknorm_rope.cu",
-           "moe/moe_fused_topk.cu", "llm_decode_metadata_update.cu"]
+           "moe/moe_fused_topk.cu", "llm_decode_metadata_update.cu", "fp8_scaled_quantize.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 

@@ -26,6 +26,8 @@ void fused_add_rms_norm_static_fp8_quant(torch::Tensor& out, torch::Tensor& inpu
 void fused_qk_norm_rope(torch::Tensor& qkv, int64_t num_heads_q, int64_t num_heads_k, int64_t num_heads_v, int64_t head_dim, double eps,
                         const torch::Tensor& q_weight, const torch::Tensor& k_weight, const torch::Tensor& cos_sin_cache,
                         bool interleaved, const torch::Tensor& position_ids);
+std::tuple<torch::Tensor, torch::Tensor> fp8_scaled_quantize(const torch::Tensor& input, const std::optional<torch::Tensor>& output,
+                                                             const std::optional<torch::Tensor>& scale);
 std::tuple<torch::Tensor, torch::Tensor> moe_fused_topk(torch::Tensor& gating_output, int64_t topk, bool renormalize,
                                                         const std::optional<torch::Tensor>& correction_bias,
                                                         const std::string& scoring_func);
@@ -72,6 +74,9 @@ PYBIND11_MODULE(xllm_ref_kernels_py, m) {
   });
   m.def("fused_add_rms_norm_static_fp8_quant", [](torch::Tensor out, torch::Tensor in, torch::Tensor res, torch::Tensor w, torch::Tensor scale,
                                                   double eps) { xk::fused_add_rms_norm_static_fp8_quant(out, in, res, w, scale, eps); });
+  m.def("fp8_scaled_quantize", [](torch::Tensor input, std::optional<torch::Tensor> output, std::optional<torch::Tensor> scale) {
+    return xk::fp8_scaled_quantize(input, output, scale);
+  });
   m.def("moe_fused_topk", [](torch::Tensor gating, int64_t topk, bool renormalize, std::optional<torch::Tensor> bias,
                              const std::string& scoring) { return xk::moe_fused_topk(gating, topk, renormalize, bias, scoring); });
   // src: tokens, positions, new_cache_slots, kv_seq_lens, paged_kv_indptr, paged_kv_indices, paged_kv_last_page_len (int32 CUDA);

@@ -18,7 +18,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OPS = ["rms_norm", "fused_add_rms_norm", "rms_norm_static_fp8_quant", "fused_add_rms_norm_static_fp8_quant", "static_scaled_fp8_quant",
-       "act_and_mul", "rotary_embedding", "reshape_paged_cache", "fused_qk_norm_rope", "moe_fused_topk", "update_llm_decode_metadata"]
+       "act_and_mul", "rotary_embedding", "reshape_paged_cache", "fused_qk_norm_rope", "fp8_scaled_quantize", "moe_fused_topk", "update_llm_decode_metadata"]
 
 
 @pytest.fixture(scope="module")

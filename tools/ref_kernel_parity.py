@@ -135,6 +135,14 @@ def main():
             ref.fused_qk_norm_rope(b, hq, hk, hk, D, 1e-6, qw, kw, cache, inter, pos)
             record("fused_qk_norm_rope", f"T{T} {hq}/{hk}x{D} interleaved={inter}", [(a, b)])
         guarded("fused_qk_norm_rope", f"T{T} {hq}/{hk}x{D} interleaved={inter}", qknorm)
+    # dynamic per-tensor FP8 quantisation (fp8_scaled_quantize.cpp:36-41: the scale is formed in the tensor's dtype, then cast)
+    for T, H, sc_ in ((7, 3584, 1.0), (32, 8192, 5.0), (1, 256, 0.01), (64, 1024, 40.0)):
+        def dyn():
+            x = rnd(T, H, scale=sc_)
+            q1, s1 = ops.fp8_scaled_quantize(x)
+            q2, s2 = ref.fp8_scaled_quantize(x, None, None)
+            record("fp8_scaled_quantize", f"{T}x{H} x{sc_}", [(q1, q2), (s1.reshape(-1).float(), s2.reshape(-1).float())])
+        guarded("fp8_scaled_quantize", f"{T}x{H} x{sc_}", dyn)
     # MoE router (n4): moe_fused_topk.cu + moe_topk_{softmax,sigmoid}_kernels.cuh
     for T, E, k, dt in ((7, 16, 2, torch.float32), (33, 64, 8, torch.float32), (512, 16, 2, BF16), (5, 256, 8, BF16), (1, 8, 1, torch.float32)):
         logits = (torch.randn(T, E, generator=g, device=DEV) * 3).to(dt)
