@@ -31,10 +31,10 @@ def available() -> bool:
 
 def build(verbose=False, force=False):
     """-> path of the python module, or None when neither the reference tree nor a prebuilt oracle/_ref is present"""
+    if not os.path.isdir(KDIR):
+        return PYMOD if available() else None       # GPU box: no reference tree - the prebuilt files are all there is
     if available() and not force and os.path.getmtime(PYMOD) >= os.path.getmtime(os.path.join(HERE, "ref_binding.cpp")):
         return PYMOD
-    if not os.path.isdir(KDIR):
-        return None
     import pybind11
     import sysconfig
     import torch
