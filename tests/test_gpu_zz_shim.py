@@ -12,8 +12,12 @@ DEV, BF16, E4M3 = "cuda", torch.bfloat16, torch.float8_e4m3fn
 
 @pytest.fixture(scope="module")
 def shim(built_lib):
-    from xllm_b200 import build_shim
-    return build_shim.load_py()
+    from xllm_b200 import build_shim, ops
+    yield build_shim.load_py()
+    # the shim's cutlass_scaled_mm registers its own split-K workspace with the library on first use: withdraw it so that tests
+    # collected after this module see the library's default state
+    torch.cuda.synchronize()
+    ops.disable_fp8_splitk()
 
 
 def _g(seed):
