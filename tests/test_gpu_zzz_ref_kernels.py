@@ -28,15 +28,20 @@ def parity(built_lib):
         pytest.skip("oracle/_ref is not built and the reference tree is absent")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     out = os.path.join(ROOT, "gpurun_out", "ref_kernel_parity.json")
+    if os.path.exists(out):
+        os.remove(out)
     try:
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_kernel_parity.py"), out], cwd=ROOT, capture_output=True,
                            text=True, timeout=600)
     except subprocess.TimeoutExpired:
         pytest.skip("reference-kernel parity run timed out")
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-    if r.returncode != 0 or not lines:
+    if r.returncode == 0 and lines:
+        d = json.loads(lines[-1])
+    elif os.path.exists(out):                                             # the run died part-way: what it compared before is on disk
+        d = json.load(open(out))
+    else:
         pytest.skip(f"reference-kernel parity run did not complete (rc {r.returncode}): {r.stderr[-600:]}")
-    d = json.loads(lines[-1])
     if "unavailable" in d:
         pytest.skip(d["unavailable"])
     return d["ops"]
@@ -45,6 +50,8 @@ def parity(built_lib):
 @pytest.mark.xfail(strict=False, reason="first execution on a GPU is the round-end run (see module docstring): XPASS = bit-identical to the reference's kernel")
 @pytest.mark.parametrize("op", OPS)
 def test_kernel_is_bit_identical_to_the_reference_kernel(op, parity):
+    if op not in parity:
+        pytest.skip("the parity run ended before this op")
     r = parity[op]
     assert r["cases"] > 0 and not r.get("errors"), f"{op}: {r.get('errors')}"
     assert r["bit_identical"] == r["cases"], f"{op}: {r['bit_identical']} / {r['cases']} cases bit-identical; worst {r['worst']}"
@@ -55,6 +62,8 @@ def test_router_weights_match_the_reference_kernel(parity):
     """fp32 routing weights: the reference has two softmax kernels (fused for power-of-two expert counts, generic otherwise) whose
     reductions sum in different orders, so the floating-point bar is 1e-6 relative rather than bit identity (the expert ids - index
     work - are held to identity above)."""
+    if "moe_fused_topk_weights" not in parity:
+        pytest.skip("the parity run ended before this op")
     r = parity["moe_fused_topk_weights"]
     assert r["cases"] > 0 and not r.get("errors"), r.get("errors")
     assert r["bit_identical"] == r["cases"] or r.get("max_rel_diff", 1.0) <= 1e-6, r

@@ -40,6 +40,14 @@ def main():
             if r["worst"] is None or d > r["worst"]["max_abs_diff"]:
                 r["worst"] = {"case": case, "max_abs_diff": d, "elements_differing": n}
 
+    out_path = sys.argv[1] if len(sys.argv) > 1 else None
+
+    def dump():
+        """partial results after every comparison: if a later kernel takes the process down, what ran before is still on disk"""
+        if out_path:
+            with open(out_path, "w") as f:
+                json.dump({"device": torch.cuda.get_device_name(0), "ops": res, "complete": False}, f, indent=1)
+
     def guarded(op, case, fn):
         """one comparison; an exception of either implementation (unsupported shape, failed check) is recorded, not fatal"""
         try:
@@ -48,6 +56,11 @@ def main():
             r = res.setdefault(op, {"cases": 0, "bit_identical": 0, "worst": None, "errors": []})
             r["cases"] += 1
             r["errors"].append(f"{case}: {type(e).__name__}: {str(e)[:160]}")
+        try:
+            torch.cuda.synchronize()
+            dump()
+        except Exception:                                                  # noqa: BLE001
+            pass
 
     for T, H in ((7, 3584), (64, 4096), (1, 256), (33, 1024), (300, 8192)):
         x, r0, w = rnd(T, H), rnd(T, H), (1 + 0.1 * torch.randn(H, generator=g, device=DEV)).to(BF16)
@@ -184,10 +197,10 @@ def main():
             record("update_llm_decode_metadata", f"tokens {n_tok}/{padded} batch {batch} indices {n_idx}", [(d1[f], d2[f]) for f in DFIELDS])
         guarded("update_llm_decode_metadata", f"tokens {n_tok}/{padded} batch {batch}", metadata)
     torch.cuda.synchronize()
-    out = {"device": torch.cuda.get_device_name(0), "ops": res}
+    out = {"device": torch.cuda.get_device_name(0), "ops": res, "complete": True}
     print(json.dumps(out))
-    if len(sys.argv) > 1:
-        with open(sys.argv[1], "w") as f:
+    if out_path:
+        with open(out_path, "w") as f:
             json.dump(out, f, indent=1)
     return 0
 
