@@ -108,3 +108,16 @@ def test_cpp_shim_exports_reference_namespace(built_lib):
                "fused_add_rms_norm_static_fp8_quant", "fp8_scaled_matmul", "fused_qk_norm_rope",
                "update_llm_decode_metadata", "moe_fused_topk", "cutlass_fused_moe"):
         assert f"xllm::kernel::cuda::{fn}(" in syms, fn
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """the boundary a cgo / JNI / ctypes / C++ caller binds: include/xllm_b200_ops.h must compile as C11 (pedantic) and as C++17 on
+    its own - no C++-only constructs, no missing includes"""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "xllm_b200_ops.h"\\nint main(void) { return 0; }\\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
