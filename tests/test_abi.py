@@ -115,7 +115,7 @@ def test_header_is_plain_c_and_cxx(tmp_path):
     its own - no C++-only constructs, no missing includes"""
     import subprocess
     src = tmp_path / "abi.c"
-    src.write_text('#include "xllm_b200_ops.h"\\nint main(void) { return 0; }\\n')
+    src.write_text('#include "xllm_b200_ops.h"\nint main(void) { return 0; }\n')
     inc = os.path.join(ROOT, "include")
     for cmd in (["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
                 ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)]):
