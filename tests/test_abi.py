@@ -121,3 +121,39 @@ def test_header_is_plain_c_and_cxx(tmp_path):
                 ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)]):
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_plain_c_caller_links_and_runs(tmp_path, built_lib):
+    """a C program - what a cgo / JNI / FFI binding boils down to - includes the header, links the shared library and calls
+    host-only entry points (no device needed): ABI version, the GEMM dispatch description, a decode plan, an argument error with its
+    message."""
+    import subprocess
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "xllm_b200_ops.h"
+int main(void) {
+  char buf[96];
+  long long plan[8];
+  int64_t p64[8];
+  if (xb_abi_version() != 1) return 1;
+  if (xb_gemm_describe(1, 32, 1280, 8192, 148, buf, (int)sizeof buf) <= 0) return 2;
+  printf("%s\n", buf);
+  if (xb_decode_plan(p64, 3, 28, 4, 128, 16, 300, 148) != 0) return 3;
+  for (int i = 0; i < 8; ++i) plan[i] = (long long)p64[i];
+  printf("plan %lld %lld\n", plan[4], plan[5]);
+  if (xb_decode_plan(p64, 3, 28, 5, 128, 16, 300, 148) == 0) return 4;      /* 28 q heads over 5 kv heads: rejected */
+  printf("err %s\n", strlen(xb_last_error()) > 0 ? "set" : "empty");
+  return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(built_lib)
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        f"-L{libdir}", "-lxllm_b200_ops", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    out = r.stdout.splitlines()
+    assert out[0] == "fp8 swap-AB bn=32 split_k=5" and out[1] == "plan 3 28" and out[2] == "err set"
