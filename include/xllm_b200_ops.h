@@ -32,10 +32,12 @@ extern "C" {
 
 typedef void* xb_stream_t; /* cudaStream_t */
 
-/* ---- library ------------------------------------------------------------ */
+/* ---- library ------------------------------------------------------------
+ * library-level entries (no reference counterpart): ABI version, the message of the last failed call on this thread (the
+ * reference reports through glog CHECK / c10::Error; a C ABI returns a code + this string), launch counter for the benches. */
 int xb_abi_version(void);
 const char* xb_last_error(void);
-/* number of kernels this library has launched in this process (all threads);
+/* library-level: number of kernels this library has launched in this process (all threads);
  * bench.py reports the delta over the timed region as "gpu_launches". */
 uint64_t xb_launch_count(void);
 /* enable (1) / disable (0) programmatic dependent launch on our launches.
@@ -121,8 +123,8 @@ int xb_rope_and_cache_bf16(const int64_t* positions, void* query, void* key,
                            int block_size, int is_neox, int num_tokens,
                            xb_stream_t stream);
 
-/* the same two ops on a qkv projection whose output columns are in the rope-pair packed order of the weight-only
- * decode layout (quant.pack_w4_qkv_rope; the decode GEMV does this work in its epilogue, see
+/* additive (no reference counterpart; same arithmetic as rope.cu:27-54 + reshape_paged_cache.cu:23-62): the same two ops on a
+ * qkv projection whose output columns are in the rope-pair packed order of the weight-only decode layout (quant.pack_w4_qkv_rope; the decode GEMV does this work in its epilogue, see
  * xb_linear_w4a16_decode_fused): reads qkv_packed [T, (Hq+2Hkv)*D], writes q | k | v in LOGICAL order to qkv_out
  * (a different buffer) and the new k / v rows to the paged caches.  NeoX halves, full rotary. */
 int xb_rope_and_cache_packed_bf16(const int64_t* positions, const void* qkv_packed,
@@ -177,7 +179,7 @@ int xb_act_and_mul_bf16(void* out, const void* input, int d, int num_tokens,
 int xb_decode_plan(int64_t* plan8, int batch, int num_qo_heads, int num_kv_heads,
                    int head_dim, int page_size, int max_pages_per_request,
                    int num_sms);
-/* flags bit 0 ("early prefetch"): the caller guarantees that no kernel still in flight writes KV rows other than the
+/* additive (no reference counterpart).  flags bit 0 ("early prefetch"): the caller guarantees that no kernel still in flight writes KV rows other than the
  * newest token of each request, nor the paged triplet (true inside a decode step); the kernel then streams KV before
  * its programmatic-dependent-launch wait, overlapping the producer kernel's tail. */
 int xb_decode_plan_set_flags(int64_t* plan8, int flags);
@@ -249,7 +251,8 @@ int xb_linear_w4a16_decode_fused(void* y, int64_t y_stride, const void* x, int64
                                  int num_kv_heads, int head_dim, const float* norm_stats_in,
                                  float* norm_stats_out, xb_stream_t stream);
 int xb_linear_w4a16_decode_fused_fits(int M, int K);
-/* Arithmetic form of the W4A16 decode kernels (M <= 8; group_size 64 / 128), both defined in oracle/quant.py:
+/* additive (the reference has no weight-only kernel).  Arithmetic form of the W4A16 decode kernels (M <= 8; group_size
+ * 64 / 128), both defined in oracle/quant.py:
  *   0  bf16-weight form: w = bf16((q - z) * s) per weight, then the bf16 linear (what the tcgen05 prefill GEMM computes)
  *   1  exact-dequant form: y = bf16(sum_g s_g * sum_{k in g} x_k (q_k - z_g) + b), fp32 - the integer nibbles go to the
  *      tensor core unscaled and scale / zero are applied once per (row, group); differs from form 0 only by the bf16
@@ -281,11 +284,12 @@ int xb_linear_fp8_small_m(void* c, int64_t ldc, const void* a, int64_t lda, cons
                           int b_scale_numel, const void* bias, int M, int N, int K,
                           xb_stream_t stream);
 
-/* act_and_mul over that interleaved column layout (prefill path sharing the same packed weight):
+/* additive (arithmetic of activation.cu:97-125): act_and_mul over that interleaved column layout (prefill path sharing the same
+ * packed weight):
  * out[t, 8j+i] = act(x[t, 16j+i]) * x[t, 16j+8+i]. */
 int xb_act_and_mul_interleaved8_bf16(void* out, const void* input, int d, int num_tokens,
                                      int act_mode, xb_stream_t stream);
-/* host-side packer (plain C, no CUDA): q[N,K] uint8 (0..15) -> qweight tiles. */
+/* additive, host-side packer (plain C, no CUDA; layout spec: oracle/quant.py): q[N,K] uint8 (0..15) -> qweight tiles. */
 int xb_w4_pack_rows(uint32_t* qweight_out, const uint8_t* q, int N, int K);
 
 /* ---- K3 / K2: prefill and chunked-prefill attention (tcgen05 + TMEM + TMA) ---------------------------

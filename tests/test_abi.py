@@ -157,3 +157,18 @@ int main(void) {
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     out = r.stdout.splitlines()
     assert out[0] == "fp8 swap-AB bn=32 split_k=5" and out[1] == "plan 3 28" and out[2] == "err set"
+
+
+def test_every_abi_entry_states_what_it_replaces():
+    """include/*.h declares the boundary "citing the reference interface each one replaces (file:line)": the comment in front of every
+    xb_* declaration either cites a reference source line or says that the entry is additive / library-level / a host-only query / a
+    tuning setter (things the reference has no counterpart for)."""
+    src = open(os.path.join(ROOT, "include", "xllm_b200_ops.h")).read()
+    last, missing = "", []
+    for m in re.finditer(r"/\*.*?\*/|\b(?:int|size_t|int64_t|const char\*|uint64_t|void)\s+(xb_[a-z0-9_]+)\s*\(", src, flags=re.S):
+        if m.group(0).startswith("/*"):
+            last = m.group(0)
+        elif not re.search(r"\.(cpp|cu|cuh|h):\d+|additive|library-level|debug aid|host-only|SURVEY|setter|returns the old|Returns the old",
+                           last):
+            missing.append(m.group(1))
+    assert not missing, missing
